@@ -1,0 +1,338 @@
+"""Host-side mirror of the reference bundle-adjustment call surface.
+
+Same names, argument meaning and error behaviour as
+  bundle_adjustment()        src/base3d/bundle_adjustment.h:221-230, .cc:449-613
+  pose_refinement()          src/base3d/bundle_adjustment.h:212-218, .cc:139-225
+  BundleAdjustmentOptions    src/base3d/bundle_adjustment.h:38-114
+  BA_POSE_{FREE,FIXED,FIXED_X}  src/base3d/bundle_adjustment.h:33-35
+The body only flattens the FeatureManager subset into the SoA `mm_ba_problem`
+(which observations enter, their order and which parameter blocks are constant follow
+bundle_adjustment.cc:228-387, 459-471, 545-549) and calls the C ABI
+(include/mavmap_b200.h); all arithmetic runs in the CUDA library.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _abi
+from ._abi import (BAOptions, BAProblem, BASummary, MODEL_NUM_PARAMS, MM_INTR_STRIDE, as_ptr,
+                   p_f64, p_i32, p_u8)
+
+BA_POSE_FREE, BA_POSE_FIXED, BA_POSE_FIXED_X = 0, 1, 2
+
+
+class BundleAdjustmentOptions:
+    """Field-for-field mirror of the reference struct (defaults bundle_adjustment.h:40-50)."""
+
+    def __init__(self, **kw):
+        self.max_num_iterations = 100
+        self.function_tolerance = 1e-4
+        self.gradient_tolerance = 1e-8
+        self.update_point3D_errors = False
+        self.min_track_len = 2
+        self.loss_scale_factor = 1.0
+        self.constrain_rotation = False
+        self.constrain_rotation_weight = 0.0
+        self.refine_camera_params = False
+        self.print_progress = False
+        self.print_summary = True
+        # engine knobs (not in the reference struct)
+        self.pcg_tolerance = 1e-13
+        self.pcg_max_iterations = 2000
+        for k, v in kw.items():
+            if not hasattr(self, k):
+                raise TypeError("unknown option %r" % k)
+            setattr(self, k, v)
+
+
+def default_c_options():
+    o = BAOptions()
+    o.max_num_iterations = 100
+    o.function_tolerance = 1e-4
+    o.gradient_tolerance = 1e-8
+    o.loss_type = _abi.MM_LOSS_CAUCHY
+    o.loss_scale = 1.0
+    o.parameter_tolerance = 1e-8
+    o.initial_trust_region_radius = 1e4
+    o.max_trust_region_radius = 1e16
+    o.min_trust_region_radius = 1e-32
+    o.min_relative_decrease = 1e-3
+    o.min_lm_diagonal = 1e-6
+    o.max_lm_diagonal = 1e32
+    o.jacobi_scaling = 1
+    o.max_num_consecutive_invalid_steps = 10
+    o.linear_solver = _abi.MM_SOLVER_PCG
+    o.pcg_tolerance = 1e-13
+    o.pcg_max_iterations = 2000
+    o.print_progress = 0
+    return o
+
+
+def to_c_options(options):
+    o = default_c_options()
+    o.max_num_iterations = int(options.max_num_iterations)
+    o.function_tolerance = float(options.function_tolerance)
+    o.gradient_tolerance = float(options.gradient_tolerance)
+    o.loss_scale = float(options.loss_scale_factor)
+    o.print_progress = int(bool(options.print_progress))
+    o.pcg_tolerance = float(getattr(options, "pcg_tolerance", 1e-13))
+    o.pcg_max_iterations = int(getattr(options, "pcg_max_iterations", 2000))
+    return o
+
+
+class FlatProblem:
+    """numpy-backed `mm_ba_problem` (SURVEY.md §8a-a9 layout)."""
+
+    def __init__(self, poses, pose_const, img_cam, intr, cam_model, intr_const, pts, pt_const,
+                 obs_xy, obs_img, obs_pt, want_pt_err=False):
+        self.poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 6)
+        self.pose_const = np.ascontiguousarray(pose_const, dtype=np.uint8).reshape(-1, 4)
+        self.img_cam = np.ascontiguousarray(img_cam, dtype=np.int32)
+        self.intr = np.ascontiguousarray(intr, dtype=np.float64).reshape(-1, MM_INTR_STRIDE)
+        self.cam_model = np.ascontiguousarray(cam_model, dtype=np.int32)
+        self.intr_const = np.ascontiguousarray(intr_const, dtype=np.uint8)
+        self.pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+        self.pt_const = np.ascontiguousarray(pt_const, dtype=np.uint8)
+        self.obs_xy = np.ascontiguousarray(obs_xy, dtype=np.float64).reshape(-1, 2)
+        self.obs_img = np.ascontiguousarray(obs_img, dtype=np.int32)
+        self.obs_pt = np.ascontiguousarray(obs_pt, dtype=np.int32)
+        self.pt_err = np.zeros(len(self.pts), dtype=np.float64) if want_pt_err else None
+        assert len(self.poses) == len(self.pose_const) == len(self.img_cam)
+        assert len(self.intr) == len(self.cam_model) == len(self.intr_const)
+        assert len(self.pts) == len(self.pt_const)
+        assert len(self.obs_xy) == len(self.obs_img) == len(self.obs_pt)
+
+    @property
+    def n_img(self): return len(self.poses)
+    @property
+    def n_cam(self): return len(self.intr)
+    @property
+    def n_pt(self): return len(self.pts)
+    @property
+    def n_obs(self): return len(self.obs_xy)
+
+    def copy(self):
+        return FlatProblem(self.poses.copy(), self.pose_const, self.img_cam, self.intr.copy(),
+                           self.cam_model, self.intr_const, self.pts.copy(), self.pt_const,
+                           self.obs_xy, self.obs_img, self.obs_pt, self.pt_err is not None)
+
+    def to_c(self):
+        p = BAProblem()
+        p.n_img, p.n_cam, p.n_pt, p.n_obs = self.n_img, self.n_cam, self.n_pt, self.n_obs
+        p.poses = as_ptr(self.poses, p_f64)
+        p.pose_const = as_ptr(self.pose_const, p_u8)
+        p.img_cam = as_ptr(self.img_cam, p_i32)
+        p.intr = as_ptr(self.intr, p_f64)
+        p.cam_model = as_ptr(self.cam_model, p_i32)
+        p.intr_const = as_ptr(self.intr_const, p_u8)
+        p.pts = as_ptr(self.pts, p_f64)
+        p.pt_const = as_ptr(self.pt_const, p_u8)
+        p.obs_xy = as_ptr(self.obs_xy, p_f64)
+        p.obs_img = as_ptr(self.obs_img, p_i32)
+        p.obs_pt = as_ptr(self.obs_pt, p_i32)
+        p.pt_err = as_ptr(self.pt_err, p_f64) if self.pt_err is not None else None
+        return p
+
+
+_DATUM_MSG = ("At least 7 parameters should be set as fixed to avoid datum defects "
+              "resulting in a singular Jacobian.")
+_TRACK_MSG = ("Minimum track length must be >= 2 in order build valid bundle adjustment "
+              "problem.")
+
+
+def flatten(feature_manager, free_image_ids, fixed_image_ids, fixed_x_image_ids, options,
+            gcp_ids=()):
+    """FeatureManager subset -> (FlatProblem, image_ids, camera_ids, point3D_ids).
+
+    Mirrors bundle_adjustment.cc:459-549."""
+    fm = feature_manager
+    gcp_ids = set(gcp_ids)
+    num_fixed = len(fixed_image_ids) * 6 + len(fixed_x_image_ids) + len(gcp_ids) * 3
+    if num_fixed < 7:
+        raise ValueError(_DATUM_MSG)                       # .cc:462-466
+    if options.min_track_len < 2:
+        raise ValueError(_TRACK_MSG)                       # .cc:468-471
+
+    # _bundle_adjustment_extract_data (.cc:228-286): free, fixed_x, fixed
+    per_image = {}
+    count = {}
+    for ids in (free_image_ids, fixed_x_image_ids, fixed_image_ids):
+        for image_id in ids:
+            obs = []
+            for p2 in fm.image_to_points2D[image_id]:
+                p3 = fm.point2D_to_point3D.get(p2)
+                if p3 is None:
+                    continue
+                obs.append((p2, p3))
+                count[p3] = count.get(p3, 0) + 1
+            per_image[image_id] = obs
+
+    image_ids, img_index = [], {}
+    for ids in (free_image_ids, fixed_image_ids, fixed_x_image_ids):
+        for image_id in ids:
+            if image_id not in img_index:
+                img_index[image_id] = len(image_ids)
+                image_ids.append(image_id)
+    camera_ids, cam_index = [], {}
+    for image_id in image_ids:
+        cid = fm.image_to_camera[image_id]
+        if cid not in cam_index:
+            cam_index[cid] = len(camera_ids)
+            camera_ids.append(cid)
+
+    n_img = len(image_ids)
+    pose_const = np.zeros((n_img, 4), dtype=np.uint8)
+    intr_const = np.zeros(len(camera_ids), dtype=np.uint8)
+    point3D_ids, pt_index = [], {}
+    obs_xy, obs_img, obs_pt = [], [], []
+
+    # _bundle_adjustment_fill_problem (.cc:289-387): free, fixed, fixed_x
+    for state, ids in ((BA_POSE_FREE, free_image_ids), (BA_POSE_FIXED, fixed_image_ids),
+                       (BA_POSE_FIXED_X, fixed_x_image_ids)):
+        for image_id in ids:
+            ii = img_index[image_id]
+            num_residuals = 0
+            for p2, p3 in per_image[image_id]:
+                if count[p3] < options.min_track_len:      # .cc:326-332
+                    continue
+                if p3 not in pt_index:
+                    pt_index[p3] = len(point3D_ids)
+                    point3D_ids.append(p3)
+                obs_xy.append(fm.points2D[p2])
+                obs_img.append(ii)
+                obs_pt.append(pt_index[p3])
+                num_residuals += 1
+            if num_residuals > 1:                          # .cc:361
+                ci = cam_index[fm.image_to_camera[image_id]]
+                if state == BA_POSE_FIXED:
+                    pose_const[ii, :] = 1
+                elif state == BA_POSE_FIXED_X:
+                    pose_const[ii, 1] = 1
+                if not options.refine_camera_params:
+                    intr_const[ci] = 1
+
+    poses = np.array([np.concatenate([fm.rvecs[i], fm.tvecs[i]]) for i in image_ids],
+                     dtype=np.float64).reshape(-1, 6)
+    intr = np.zeros((len(camera_ids), MM_INTR_STRIDE))
+    cam_model = np.zeros(len(camera_ids), dtype=np.int32)
+    for k, cid in enumerate(camera_ids):
+        params = fm.camera_params[cid]
+        code = int(params[-1])                             # .cc:339
+        if code not in MODEL_NUM_PARAMS:
+            raise ValueError("unknown camera model code %d" % code)
+        cam_model[k] = code
+        intr[k, :MODEL_NUM_PARAMS[code]] = params[:MODEL_NUM_PARAMS[code]]
+    pts = np.array([fm.points3D[p] for p in point3D_ids], dtype=np.float64).reshape(-1, 3)
+    pt_const = np.array([1 if p in gcp_ids else 0 for p in point3D_ids], dtype=np.uint8)  # .cc:545-549
+    img_cam = np.array([cam_index[fm.image_to_camera[i]] for i in image_ids], dtype=np.int32)
+    flat = FlatProblem(poses, pose_const, img_cam, intr, cam_model, intr_const, pts, pt_const,
+                       np.array(obs_xy, dtype=np.float64).reshape(-1, 2),
+                       np.array(obs_img, dtype=np.int32), np.array(obs_pt, dtype=np.int32),
+                       want_pt_err=bool(options.update_point3D_errors))
+    return flat, image_ids, camera_ids, point3D_ids
+
+
+def unflatten(feature_manager, flat, image_ids, camera_ids, point3D_ids, options,
+              point3D_errors):
+    fm = feature_manager
+    for k, image_id in enumerate(image_ids):
+        fm.rvecs[image_id][:] = flat.poses[k, :3]
+        fm.tvecs[image_id][:] = flat.poses[k, 3:]
+    for k, cid in enumerate(camera_ids):
+        n = MODEL_NUM_PARAMS[int(flat.cam_model[k])]
+        fm.camera_params[cid][:n] = [float(v) for v in flat.intr[k, :n]]
+    for k, p3 in enumerate(point3D_ids):
+        fm.points3D[p3][:] = flat.pts[k]
+    if options.update_point3D_errors and flat.pt_err is not None:
+        for k, p3 in enumerate(point3D_ids):
+            point3D_errors[p3] = float(flat.pt_err[k])
+
+
+def _print_report(title, flat, summary):
+    """_print_report (bundle_adjustment.cc:114-136)."""
+    act_pose = flat.pose_const == 0
+    n_res = 2 * flat.n_obs
+    n_par = int(act_pose[:, 0].sum() * 3 + act_pose[:, 1:].sum())
+    n_par += int(sum(MODEL_NUM_PARAMS[int(m)] for m, c in zip(flat.cam_model, flat.intr_const) if not c))
+    n_par += int((flat.pt_const == 0).sum() * 3)
+    print(title)
+    print("-" * len(title))
+    print("%18s%d" % ("Residuals : ", n_res))
+    print("%18s%d" % ("Parameters : ", n_par))
+    print("%18s%d" % ("Iterations : ", summary.num_successful_steps + summary.num_unsuccessful_steps))
+    nr = max(summary.num_residuals, 1)
+    print("%18s%.6g [px]" % ("Initial cost : ", math.sqrt(summary.initial_cost / nr)))
+    print("%18s%.6g [px]" % ("Final cost : ", math.sqrt(summary.final_cost / nr)))
+    print()
+
+
+def solve_flat(flat, c_options, solve_fn=None):
+    """Run the engine on a FlatProblem in place; returns the BASummary."""
+    if solve_fn is None:
+        from ._lib import lib, check
+        solve_fn = lambda p, o, s: check(lib().mm_ba_solve(p, o, s))
+    cp = flat.to_c()
+    summary = BASummary()
+    solve_fn(C.byref(cp), C.byref(c_options), C.byref(summary))
+    return summary
+
+
+def bundle_adjustment(feature_manager, free_image_ids, fixed_image_ids, fixed_x_image_ids,
+                      options, point3D_errors, rotation_constraints=None, gcp_ids=(),
+                      _solve_fn=None):
+    """Drop-in for bundle_adjustment() (bundle_adjustment.cc:449-613); returns
+    sqrt(final_cost / num_residuals) (.cc:610).  Raises ValueError where the reference
+    throws std::invalid_argument (.cc:462-471)."""
+    if options.constrain_rotation:
+        raise NotImplementedError("constrain_rotation (bundle_adjustment.cc:390-446) is not "
+                                  "built yet; off by default in the reference (mapper.cc:869-873)")
+    flat, image_ids, camera_ids, point3D_ids = flatten(
+        feature_manager, free_image_ids, fixed_image_ids, fixed_x_image_ids, options, gcp_ids)
+    if flat.n_obs == 0:
+        print("No observations in bundle adjustment. Consider relaxing the constraints.")  # .cc:571-573
+    summary = solve_flat(flat, to_c_options(options), _solve_fn)
+    unflatten(feature_manager, flat, image_ids, camera_ids, point3D_ids, options, point3D_errors)
+    if options.print_progress:
+        print()
+    if options.print_summary:
+        _print_report("Bundle Adjustment Report", flat, summary)
+    return summary.return_value
+
+
+def pose_refinement(rvec, tvec, camera_params, points2D, points3D, inlier_mask, options,
+                    _refine_fn=None):
+    """Drop-in for pose_refinement() (bundle_adjustment.cc:139-225): rvec/tvec updated in
+    place, returns sqrt(final_cost / num_residuals)."""
+    code = int(camera_params[-1])
+    if code not in MODEL_NUM_PARAMS:
+        raise ValueError("unknown camera model code %d" % code)
+    params = np.zeros(MM_INTR_STRIDE)
+    params[:MODEL_NUM_PARAMS[code]] = camera_params[:MODEL_NUM_PARAMS[code]]
+    p2 = np.ascontiguousarray(points2D, dtype=np.float64).reshape(-1, 2)
+    p3 = np.ascontiguousarray(points3D, dtype=np.float64).reshape(-1, 3)
+    mask = None if inlier_mask is None else np.ascontiguousarray(inlier_mask, dtype=np.uint8)
+    rv = np.ascontiguousarray(rvec, dtype=np.float64).copy()
+    tv = np.ascontiguousarray(tvec, dtype=np.float64).copy()
+    if _refine_fn is None:
+        from ._lib import lib, check
+        _refine_fn = lambda *a: check(lib().mm_pose_refine(*a))
+    summary = BASummary()
+    ret = C.c_double(0.0)
+    co = to_c_options(options)
+    _refine_fn(as_ptr(rv, p_f64), as_ptr(tv, p_f64), code, as_ptr(params, p_f64), len(p2),
+               as_ptr(p2, p_f64), as_ptr(p3, p_f64), as_ptr(mask, p_u8), C.byref(co),
+               C.byref(summary), C.byref(ret))
+    rvec[:] = rv
+    tvec[:] = tv
+    if options.print_summary:
+        print("Pose Refinement Report")
+        print("----------------------")
+        nr = max(summary.num_residuals, 1)
+        print("%18s%d" % ("Residuals : ", summary.num_residuals))
+        print("%18s%d" % ("Parameters : ", 6))
+        print("%18s%d" % ("Iterations : ", summary.num_successful_steps + summary.num_unsuccessful_steps))
+        print("%18s%.6g [px]" % ("Initial cost : ", math.sqrt(summary.initial_cost / nr)))
+        print("%18s%.6g [px]" % ("Final cost : ", math.sqrt(summary.final_cost / nr)))
+        print()
+    return ret.value

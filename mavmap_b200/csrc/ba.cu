@@ -1,0 +1,636 @@
+// ba.cu — bundle-adjustment session: structure setup on the device (CUB sorts/scans), the
+// Levenberg-Marquardt driver and the C ABI (mm_ba_*, mm_pose_refine).
+//
+// Replaces (mavmap/mavmap):  bundle_adjustment()  src/base3d/bundle_adjustment.cc:449-613 and
+// pose_refinement() :139-225 — i.e. the ceres::Problem construction + ceres::Solve(SPARSE_SCHUR).
+// The LM control flow restates Ceres 1.8 (trust_region_minimizer.cc,
+// levenberg_marquardt_strategy.cc; rules listed in SURVEY.md §8a-a3' and oracle/orc_ba.c); the
+// linear solve is block-Jacobi PCG on the explicitly assembled reduced camera system.
+// The host only sequences kernels and reads a handful of scalars per LM iteration.
+#include <cub/cub.cuh>
+#include <math.h>
+#include <vector>
+#include <algorithm>
+#include "ba_kernels.cuh"
+
+namespace mm {
+
+// ------------------------------------------------------------------ setup kernels
+__global__ void k_iota(int n, int* out) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = i; }
+__global__ void k_hist(int64_t n, const int* __restrict__ keys, int* __restrict__ cnt) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) atomicAdd(cnt + keys[i], 1);
+}
+__global__ void k_gather_obs(int64_t n, const int* __restrict__ perm, const double2* __restrict__ xy_in, const int* __restrict__ img_in,
+                             double2* __restrict__ xy, int* __restrict__ img) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) { const int s = perm[i]; xy[i] = xy_in[s]; img[i] = img_in[s]; }
+}
+__global__ void k_pair_count(int n_pt, const int* __restrict__ pt_start, int64_t* __restrict__ cnt) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n_pt) { const int64_t k = pt_start[p + 1] - pt_start[p]; cnt[p] = k * (k - 1) / 2; }
+}
+__global__ void k_pair_keys(int n_pt, int n_img, const int* __restrict__ pt_start, const int* __restrict__ obs_img,
+                            const int64_t* __restrict__ pair_off, unsigned long long* __restrict__ keys) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pt) return;
+  int64_t slot = pair_off[p];
+  const int o0 = pt_start[p], o1 = pt_start[p + 1];
+  for (int i = o0; i < o1 - 1; ++i) {
+    const int a = obs_img[i];
+    for (int j = i + 1; j < o1; ++j, ++slot) {
+      const int b = obs_img[j];
+      const unsigned long long lo = a < b ? a : b, hi = a < b ? b : a;
+      keys[slot] = lo * (unsigned long long)n_img + hi;
+    }
+  }
+}
+// head flag of every run of equal off-diagonal keys
+__global__ void k_pair_heads(int64_t n, int n_img, const unsigned long long* __restrict__ keys, int* __restrict__ head) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned long long k = keys[i];
+    const bool diag = (k / n_img) == (k % n_img);
+    head[i] = (!diag && (i == 0 || keys[i - 1] != k)) ? 1 : 0;
+  }
+}
+__global__ void k_pair_assign(int64_t n, int n_img, const unsigned long long* __restrict__ keys, const int* __restrict__ incl,
+                              const int* __restrict__ head, const int* __restrict__ slot, int* __restrict__ pair_blk,
+                              int* __restrict__ blk_a, int* __restrict__ blk_b) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned long long k = keys[i];
+    const int a = (int)(k / n_img), b = (int)(k % n_img);
+    if (a == b) { pair_blk[slot[i]] = a; continue; }
+    const int id = incl[i] - 1;
+    pair_blk[slot[i]] = n_img + id;
+    if (head[i]) { blk_a[id] = a; blk_b[id] = b; }
+  }
+}
+// CSR entries: key = row * n_img + col, value = signed block reference (negative = transposed)
+__global__ void k_csr_entries(int n_img, int n_off, const int* __restrict__ blk_a, const int* __restrict__ blk_b,
+                              unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_img) { keys[i] = (unsigned long long)i * n_img + i; vals[i] = i; }
+  if (i < n_off) {
+    const int a = blk_a[i], b = blk_b[i], id = n_img + i;
+    keys[n_img + 2 * (size_t)i] = (unsigned long long)a * n_img + b; vals[n_img + 2 * (size_t)i] = id;
+    keys[n_img + 2 * (size_t)i + 1] = (unsigned long long)b * n_img + a; vals[n_img + 2 * (size_t)i + 1] = -id - 1;
+  }
+}
+__global__ void k_csr_rows(int64_t n, int n_img, const unsigned long long* __restrict__ keys, int* __restrict__ col, int* __restrict__ cnt) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned long long k = keys[i];
+    col[i] = (int)(k % n_img);
+    atomicAdd(cnt + (int)(k / n_img), 1);
+  }
+}
+__global__ void k_fill(int64_t n, double* p, double v) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+static inline int blocks_for(int64_t n, int block) { int64_t g = (n + block - 1) / block; return (int)(g < 1 ? 1 : g); }
+static inline int grid_stride(int64_t n, int block) { int64_t g = (n + block - 1) / block; const int cap = num_sms() * 8; return (int)(g < 1 ? 1 : (g > cap ? cap : g)); }
+
+}  // namespace mm
+
+using namespace mm;
+
+// ------------------------------------------------------------------ session
+struct mm_ba_session {
+  cudaStream_t stream = nullptr;
+  mm_ba_options opt;
+  int n_img = 0, n_cam = 0, n_pt = 0; int64_t n_obs = 0;
+  int n_off = 0; int64_t nblk = 0, n_pairs = 0, n_ent = 0;
+  std::vector<double> h_poses0, h_intr0, h_pts0;
+  DevBuf<double2> obs_xy; DevBuf<int> obs_img, obs_pt, pt_start, cam_perm, cam_start, img_cam, cam_model;
+  DevBuf<int64_t> pair_off; DevBuf<int> pair_blk, row_start, row_col, row_blk;
+  DevBuf<double> S, Minv, poses, intr, pts, poses2, pts2, aux, aux2, rec;
+  DevBuf<double> pose_mask, pt_mask, scale_c, scale_p, Vinv, gp, dp, gc, dc, rhs;
+  DevBuf<double> vx, vr, vz, vp0, vp1, vAp, pcg_sc; DevBuf<int> pcg_ic;
+  DevBuf<double> part_cost, part_pt, part_cam, part_x, red;   // red: [0]=cost [1]=new_cost [2]=gmax [3]=step_norm2 [4]=mcc [5]=xnorm2
+  DevBuf<int> fail;
+  int grid_obs = 1, grid_pt = 1, grid_cam6 = 1, grid_x = 1;
+  // LM state (host)
+  double cost = 0, radius = 0, decrease_factor = 2, x_norm = 0, abs_gtol = 0, gmax = 0;
+  int iter = 0, n_invalid = 0; bool started = false, finished = false, scaled = false;
+  int last_pcg_iters = 0;
+  mm_ba_summary sum;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+struct Timer {
+  mm_ba_session* s; double* acc;
+  Timer(mm_ba_session* s_, double* a) : s(s_), acc(a) { cudaEventRecord(s->ev0, s->stream); }
+  ~Timer() { cudaEventRecord(s->ev1, s->stream); cudaEventSynchronize(s->ev1); float ms = 0; cudaEventElapsedTime(&ms, s->ev0, s->ev1); *acc += ms; }
+};
+
+int validate_problem(const mm_ba_problem* P) {
+  if (!P || P->n_img < 0 || P->n_cam < 0 || P->n_pt < 0 || P->n_obs < 0) { set_error("invalid problem sizes"); return MM_ERR_INVALID_ARG; }
+  if (P->n_obs >= (int64_t)1 << 31) { set_error("n_obs >= 2^31 not supported"); return MM_ERR_UNSUPPORTED; }
+  if (P->n_obs > 0 && (!P->poses || !P->pose_const || !P->img_cam || !P->intr || !P->cam_model || !P->intr_const || !P->pts || !P->pt_const || !P->obs_xy || !P->obs_img || !P->obs_pt)) { set_error("null array in problem"); return MM_ERR_INVALID_ARG; }
+  for (int c = 0; c < P->n_cam; ++c) if (model_num_params(P->cam_model[c]) < 0) { set_error("unknown camera model code %d", P->cam_model[c]); return MM_ERR_INVALID_ARG; }
+  for (int i = 0; i < P->n_img; ++i) if (P->img_cam[i] < 0 || P->img_cam[i] >= P->n_cam) { set_error("img_cam out of range"); return MM_ERR_INVALID_ARG; }
+  for (int64_t o = 0; o < P->n_obs; ++o)
+    if (P->obs_img[o] < 0 || P->obs_img[o] >= P->n_img || P->obs_pt[o] < 0 || P->obs_pt[o] >= P->n_pt) { set_error("observation index out of range"); return MM_ERR_INVALID_ARG; }
+  return MM_OK;
+}
+
+template <typename K, typename V>
+int sort_pairs(cudaStream_t st, const K* kin, K* kout, const V* vin, V* vout, int64_t n, int end_bit) {
+  size_t bytes = 0;
+  MM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)n, 0, end_bit, st));
+  DevBuf<char> tmp; MM_CUDA(tmp.alloc(bytes));
+  MM_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, kin, kout, vin, vout, (int)n, 0, end_bit, st));
+  count_launch(4);
+  MM_CUDA(cudaStreamSynchronize(st));
+  return MM_OK;
+}
+template <typename T>
+int exclusive_sum(cudaStream_t st, const T* in, T* out, int64_t n) {
+  size_t bytes = 0;
+  MM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int)n, st));
+  DevBuf<char> tmp; MM_CUDA(tmp.alloc(bytes));
+  MM_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, in, out, (int)n, st));
+  count_launch(2);
+  MM_CUDA(cudaStreamSynchronize(st));
+  return MM_OK;
+}
+template <typename T>
+int inclusive_sum(cudaStream_t st, const T* in, T* out, int64_t n) {
+  size_t bytes = 0;
+  MM_CUDA(cub::DeviceScan::InclusiveSum(nullptr, bytes, in, out, (int)n, st));
+  DevBuf<char> tmp; MM_CUDA(tmp.alloc(bytes));
+  MM_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, bytes, in, out, (int)n, st));
+  count_launch(2);
+  MM_CUDA(cudaStreamSynchronize(st));
+  return MM_OK;
+}
+static int bits_for(unsigned long long maxval) { int b = 1; while (b < 64 && (maxval >> b)) ++b; return b; }
+
+int build_structure(mm_ba_session* s, const mm_ba_problem* P) {
+  cudaStream_t st = s->stream;
+  const int64_t n = s->n_obs; const int n_img = s->n_img, n_pt = s->n_pt;
+  const int B = 256;
+  // upload observations in caller order
+  DevBuf<double2> xy_in; DevBuf<int> img_in, pt_in, perm, iota;
+  MM_CUDA(xy_in.alloc(n)); MM_CUDA(img_in.alloc(n)); MM_CUDA(pt_in.alloc(n)); MM_CUDA(perm.alloc(n)); MM_CUDA(iota.alloc(n));
+  MM_CUDA(cudaMemcpyAsync(xy_in.p, P->obs_xy, sizeof(double2) * n, cudaMemcpyHostToDevice, st));
+  MM_CUDA(cudaMemcpyAsync(img_in.p, P->obs_img, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  MM_CUDA(cudaMemcpyAsync(pt_in.p, P->obs_pt, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  MM_CUDA(s->obs_xy.alloc(n)); MM_CUDA(s->obs_img.alloc(n)); MM_CUDA(s->obs_pt.alloc(n));
+  MM_CUDA(s->pt_start.alloc((size_t)n_pt + 1)); MM_CUDA(s->cam_start.alloc((size_t)n_img + 1)); MM_CUDA(s->cam_perm.alloc(n));
+  if (n > 0) {
+    k_iota<<<blocks_for(n, B), B, 0, st>>>((int)n, iota.p); MM_LAUNCH_CHECK();
+    // 1. stable sort by point (keeps the caller's order inside a track)
+    int rc = sort_pairs<int, int>(st, pt_in.p, s->obs_pt.p, iota.p, perm.p, n, bits_for((unsigned long long)std::max(n_pt, 1))); if (rc) return rc;
+    k_gather_obs<<<grid_stride(n, B), B, 0, st>>>(n, perm.p, xy_in.p, img_in.p, s->obs_xy.p, s->obs_img.p); MM_LAUNCH_CHECK();
+  }
+  // 2. point -> observation CSR
+  { DevBuf<int> cnt; MM_CUDA(cnt.alloc((size_t)n_pt + 1)); MM_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(int) * ((size_t)n_pt + 1), st));
+    if (n > 0) { k_hist<<<grid_stride(n, B), B, 0, st>>>(n, s->obs_pt.p, cnt.p); MM_LAUNCH_CHECK(); }
+    int rc = exclusive_sum<int>(st, cnt.p, s->pt_start.p, (int64_t)n_pt + 1); if (rc) return rc; }
+  // 3. camera-sorted permutation of the (point-sorted) observation positions
+  { DevBuf<int> cnt, keys_out; MM_CUDA(cnt.alloc((size_t)n_img + 1)); MM_CUDA(keys_out.alloc(n));
+    MM_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(int) * ((size_t)n_img + 1), st));
+    if (n > 0) {
+      k_hist<<<grid_stride(n, B), B, 0, st>>>(n, s->obs_img.p, cnt.p); MM_LAUNCH_CHECK();
+      int rc = sort_pairs<int, int>(st, s->obs_img.p, keys_out.p, iota.p, s->cam_perm.p, n, bits_for((unsigned long long)std::max(n_img, 1))); if (rc) return rc;
+    }
+    int rc = exclusive_sum<int>(st, cnt.p, s->cam_start.p, (int64_t)n_img + 1); if (rc) return rc; }
+  // 4. pairs of observations of one point -> blocks of the reduced camera system
+  MM_CUDA(s->pair_off.alloc((size_t)n_pt + 1));
+  { DevBuf<int64_t> cnt; MM_CUDA(cnt.alloc((size_t)n_pt + 1)); MM_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(int64_t) * ((size_t)n_pt + 1), st));
+    if (n_pt > 0) { k_pair_count<<<blocks_for(n_pt, B), B, 0, st>>>(n_pt, s->pt_start.p, cnt.p); MM_LAUNCH_CHECK(); }
+    int rc = exclusive_sum<int64_t>(st, cnt.p, s->pair_off.p, (int64_t)n_pt + 1); if (rc) return rc; }
+  int64_t n_pairs = 0;
+  MM_CUDA(cudaMemcpy(&n_pairs, s->pair_off.p + n_pt, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  if (n_pairs >= ((int64_t)1 << 31)) { set_error("too many observation pairs (%lld)", (long long)n_pairs); return MM_ERR_UNSUPPORTED; }
+  s->n_pairs = n_pairs;
+  MM_CUDA(s->pair_blk.alloc((size_t)n_pairs));
+  DevBuf<int> blk_a, blk_b;
+  int n_off = 0;
+  if (n_pairs > 0) {
+    DevBuf<unsigned long long> keys, keys_s; DevBuf<int> slot, slot_s, head, incl;
+    MM_CUDA(keys.alloc(n_pairs)); MM_CUDA(keys_s.alloc(n_pairs)); MM_CUDA(slot.alloc(n_pairs)); MM_CUDA(slot_s.alloc(n_pairs));
+    MM_CUDA(head.alloc(n_pairs)); MM_CUDA(incl.alloc(n_pairs));
+    k_pair_keys<<<blocks_for(n_pt, B), B, 0, st>>>(n_pt, n_img, s->pt_start.p, s->obs_img.p, s->pair_off.p, keys.p); MM_LAUNCH_CHECK();
+    k_iota<<<blocks_for(n_pairs, B), B, 0, st>>>((int)n_pairs, slot.p); MM_LAUNCH_CHECK();
+    int rc = sort_pairs<unsigned long long, int>(st, keys.p, keys_s.p, slot.p, slot_s.p, n_pairs, bits_for((unsigned long long)n_img * (unsigned long long)n_img)); if (rc) return rc;
+    k_pair_heads<<<grid_stride(n_pairs, B), B, 0, st>>>(n_pairs, n_img, keys_s.p, head.p); MM_LAUNCH_CHECK();
+    rc = inclusive_sum<int>(st, head.p, incl.p, n_pairs); if (rc) return rc;
+    MM_CUDA(cudaMemcpy(&n_off, incl.p + (n_pairs - 1), sizeof(int), cudaMemcpyDeviceToHost));
+    MM_CUDA(blk_a.alloc((size_t)n_off)); MM_CUDA(blk_b.alloc((size_t)n_off));
+    k_pair_assign<<<grid_stride(n_pairs, B), B, 0, st>>>(n_pairs, n_img, keys_s.p, incl.p, head.p, slot_s.p, s->pair_blk.p, blk_a.p, blk_b.p); MM_LAUNCH_CHECK();
+    MM_CUDA(cudaStreamSynchronize(st));
+  }
+  s->n_off = n_off; s->nblk = (int64_t)n_img + n_off;
+  // 5. block-CSR rows for the SpMV (each off-diagonal block referenced from both rows)
+  const int64_t n_ent = (int64_t)n_img + 2 * (int64_t)n_off; s->n_ent = n_ent;
+  MM_CUDA(s->row_start.alloc((size_t)n_img + 1)); MM_CUDA(s->row_col.alloc((size_t)n_ent)); MM_CUDA(s->row_blk.alloc((size_t)n_ent));
+  if (n_ent > 0) {
+    DevBuf<unsigned long long> keys, keys_s; DevBuf<int> vals, cnt;
+    MM_CUDA(keys.alloc(n_ent)); MM_CUDA(keys_s.alloc(n_ent)); MM_CUDA(vals.alloc(n_ent)); MM_CUDA(cnt.alloc((size_t)n_img + 1));
+    MM_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(int) * ((size_t)n_img + 1), st));
+    k_csr_entries<<<blocks_for(std::max(n_img, n_off), B), B, 0, st>>>(n_img, n_off, blk_a.p, blk_b.p, keys.p, vals.p); MM_LAUNCH_CHECK();
+    int rc = sort_pairs<unsigned long long, int>(st, keys.p, keys_s.p, vals.p, s->row_blk.p, n_ent, bits_for((unsigned long long)n_img * (unsigned long long)n_img)); if (rc) return rc;
+    k_csr_rows<<<grid_stride(n_ent, B), B, 0, st>>>(n_ent, n_img, keys_s.p, s->row_col.p, cnt.p); MM_LAUNCH_CHECK();
+    rc = exclusive_sum<int>(st, cnt.p, s->row_start.p, (int64_t)n_img + 1); if (rc) return rc;
+  } else {
+    MM_CUDA(cudaMemsetAsync(s->row_start.p, 0, sizeof(int) * ((size_t)n_img + 1), st));
+  }
+  MM_CUDA(cudaStreamSynchronize(st));
+  return MM_OK;
+}
+
+int upload_params(mm_ba_session* s) {
+  cudaStream_t st = s->stream;
+  MM_CUDA(cudaMemcpyAsync(s->poses.p, s->h_poses0.data(), sizeof(double) * 6 * (size_t)s->n_img, cudaMemcpyHostToDevice, st));
+  MM_CUDA(cudaMemcpyAsync(s->intr.p, s->h_intr0.data(), sizeof(double) * MM_INTR_STRIDE * (size_t)s->n_cam, cudaMemcpyHostToDevice, st));
+  MM_CUDA(cudaMemcpyAsync(s->pts.p, s->h_pts0.data(), sizeof(double) * 3 * (size_t)s->n_pt, cudaMemcpyHostToDevice, st));
+  return MM_OK;
+}
+
+LossParams loss_of(const mm_ba_options& o) {
+  LossParams L; L.type = o.loss_type; L.b = o.loss_scale * o.loss_scale; L.c = 1.0 / L.b; return L;
+}
+LMDiag lm_of(const mm_ba_session* s) { LMDiag d; d.radius = s->radius; d.min_diag = s->opt.min_lm_diagonal; d.max_diag = s->opt.max_lm_diagonal; return d; }
+
+// K1 at the current iterate: records + cost -> red[0]
+int launch_linearize(mm_ba_session* s) {
+  cudaStream_t st = s->stream;
+  k_pose_aux<<<blocks_for(s->n_img, 128), 128, 0, st>>>(s->n_img, s->poses.p, s->aux.p); MM_LAUNCH_CHECK();
+  k_residual_jacobian<true><<<s->grid_obs, 256, 0, st>>>(s->n_obs, s->obs_xy.p, s->obs_img.p, s->obs_pt.p, s->aux.p, s->pts.p, s->intr.p,
+      s->img_cam.p, s->cam_model.p, s->pose_mask.p, s->pt_mask.p, loss_of(s->opt), s->rec.p, s->part_cost.p); MM_LAUNCH_CHECK();
+  k_reduce_sum<<<1, 256, 0, st>>>(s->part_cost.p, s->grid_obs, s->red.p + 0); MM_LAUNCH_CHECK();
+  return MM_OK;
+}
+// K4: cost at the candidate (poses2/pts2) -> red[1]
+int launch_cost_candidate(mm_ba_session* s) {
+  cudaStream_t st = s->stream;
+  k_pose_aux<<<blocks_for(s->n_img, 128), 128, 0, st>>>(s->n_img, s->poses2.p, s->aux2.p); MM_LAUNCH_CHECK();
+  k_residual_jacobian<false><<<s->grid_obs, 256, 0, st>>>(s->n_obs, s->obs_xy.p, s->obs_img.p, s->obs_pt.p, s->aux2.p, s->pts2.p, s->intr.p,
+      s->img_cam.p, s->cam_model.p, s->pose_mask.p, s->pt_mask.p, loss_of(s->opt), nullptr, s->part_cost.p); MM_LAUNCH_CHECK();
+  k_reduce_sum<<<1, 256, 0, st>>>(s->part_cost.p, s->grid_obs, s->red.p + 1); MM_LAUNCH_CHECK();
+  return MM_OK;
+}
+int launch_scale(mm_ba_session* s) {
+  cudaStream_t st = s->stream;
+  if (s->opt.jacobi_scaling) {
+    k_colnorm_point<<<blocks_for(s->n_pt, 128), 128, 0, st>>>(s->n_pt, s->pt_start.p, s->rec.p, s->scale_p.p); MM_LAUNCH_CHECK();
+    k_colnorm_cam<<<blocks_for((int64_t)s->n_img * 32, 128), 128, 0, st>>>(s->n_img, s->cam_start.p, s->cam_perm.p, s->rec.p, s->scale_c.p); MM_LAUNCH_CHECK();
+  }
+  return MM_OK;
+}
+// K2: reduced camera system at the current radius (+ gradient max-norm -> red[2])
+int launch_schur(mm_ba_session* s) {
+  cudaStream_t st = s->stream;
+  MM_CUDA(cudaMemsetAsync(s->S.p, 0, sizeof(double) * 36 * (size_t)s->nblk, st));
+  MM_CUDA(cudaMemsetAsync(s->red.p + 2, 0, sizeof(double), st));
+  const LMDiag lm = lm_of(s);
+  k_schur_point<<<blocks_for(s->n_pt, 128), 128, 0, st>>>(s->n_pt, s->pt_start.p, s->obs_img.p, s->rec.p, s->scale_c.p, s->scale_p.p, lm,
+      s->pair_off.p, s->pair_blk.p, s->S.p, s->Vinv.p, s->gp.p, s->dp.p, s->red.p + 2, s->fail.p); MM_LAUNCH_CHECK();
+  k_schur_cam<<<blocks_for((int64_t)s->n_img * 32, 128), 128, 0, st>>>(s->n_img, s->cam_start.p, s->cam_perm.p, s->obs_pt.p, s->rec.p,
+      s->scale_c.p, s->scale_p.p, s->Vinv.p, s->gp.p, lm, s->S.p, s->rhs.p, s->gc.p, s->dc.p, s->red.p + 2); MM_LAUNCH_CHECK();
+  k_precond<<<blocks_for(s->n_img, 64), 64, 0, st>>>(s->n_img, s->S.p, s->Minv.p, s->fail.p); MM_LAUNCH_CHECK();
+  return MM_OK;
+}
+int launch_pcg_iteration(mm_ba_session* s, int it) {
+  cudaStream_t st = s->stream;
+  double* p_old = (it & 1) ? s->vp1.p : s->vp0.p; double* p_new = (it & 1) ? s->vp0.p : s->vp1.p;
+  k_pcg_spmv<<<blocks_for((int64_t)s->n_img * 32, 128), 128, 0, st>>>(s->n_img, s->row_start.p, s->row_col.p, s->row_blk.p, s->S.p,
+      s->vz.p, p_old, p_new, s->vAp.p, s->pcg_sc.p, s->pcg_ic.p, it == 0); MM_LAUNCH_CHECK();
+  const double tol = s->opt.pcg_tolerance;
+  k_pcg_update<<<blocks_for(s->n_img, 128), 128, 0, st>>>(s->n_img, s->Minv.p, p_new, s->vAp.p, s->vx.p, s->vr.p, s->vz.p,
+      s->pcg_sc.p, s->pcg_ic.p, tol * tol, s->opt.pcg_max_iterations); MM_LAUNCH_CHECK();
+  return MM_OK;
+}
+// K3: solve S y = rhs; returns iteration count
+int run_pcg(mm_ba_session* s, int* iters) {
+  cudaStream_t st = s->stream;
+  MM_CUDA(cudaMemsetAsync(s->pcg_sc.p, 0, sizeof(double) * 8, st));
+  MM_CUDA(cudaMemsetAsync(s->pcg_ic.p, 0, sizeof(int) * 4, st));
+  PcgVecs v = { s->vx.p, s->vr.p, s->vz.p, s->vp0.p, s->vp1.p, s->vAp.p };
+  k_pcg_init<<<blocks_for(s->n_img, 128), 128, 0, st>>>(s->n_img, s->rhs.p, s->Minv.p, v, s->pcg_sc.p, s->pcg_ic.p); MM_LAUNCH_CHECK();
+  int it = 0; int ic[2] = {0, 0};
+  const int batch = 16;
+  while (true) {
+    for (int b = 0; b < batch; ++b, ++it) { int rc = launch_pcg_iteration(s, it); if (rc) return rc; }
+    MM_CUDA(cudaMemcpyAsync(ic, s->pcg_ic.p, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+    MM_CUDA(cudaStreamSynchronize(st));
+    if (ic[0]) break;
+  }
+  *iters = ic[1];
+  return MM_OK;
+}
+// K4: back-substitution, candidate parameters, step norm and model cost change -> red[3], red[4]
+int launch_update(mm_ba_session* s) {
+  cudaStream_t st = s->stream;
+  const int gp_ = blocks_for(s->n_pt, 128), gc_ = blocks_for((int64_t)6 * s->n_img, 128);
+  k_backsub<<<gp_, 128, 0, st>>>(s->n_pt, s->pt_start.p, s->obs_img.p, s->rec.p, s->scale_c.p, s->scale_p.p, s->Vinv.p, s->gp.p, s->dp.p,
+      s->vx.p, s->pts.p, s->pts2.p, s->part_pt.p); MM_LAUNCH_CHECK();
+  k_update_cam<<<gc_, 128, 0, st>>>(6 * s->n_img, s->vx.p, s->scale_c.p, s->gc.p, s->dc.p, s->poses.p, s->poses2.p, s->part_cam.p); MM_LAUNCH_CHECK();
+  k_reduce_pairs<<<1, 256, 0, st>>>(s->part_pt.p, gp_, s->part_cam.p, gc_, s->red.p + 3); MM_LAUNCH_CHECK();
+  return MM_OK;
+}
+int launch_xnorm(mm_ba_session* s) {
+  cudaStream_t st = s->stream;
+  k_xnorm<<<s->grid_x, 256, 0, st>>>(6 * s->n_img, s->poses.p, s->pose_mask.p, s->n_pt, s->pts.p, s->pt_mask.p, s->part_x.p); MM_LAUNCH_CHECK();
+  k_reduce_sum<<<1, 256, 0, st>>>(s->part_x.p, s->grid_x, s->red.p + 5); MM_LAUNCH_CHECK();
+  return MM_OK;
+}
+int read_red(mm_ba_session* s, double* out8) {
+  MM_CUDA(cudaMemcpyAsync(out8, s->red.p, sizeof(double) * 8, cudaMemcpyDeviceToHost, s->stream));
+  MM_CUDA(cudaStreamSynchronize(s->stream));
+  return MM_OK;
+}
+int read_fail(mm_ba_session* s, int* f) {
+  MM_CUDA(cudaMemcpyAsync(f, s->fail.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  MM_CUDA(cudaStreamSynchronize(s->stream));
+  if (*f) MM_CUDA(cudaMemsetAsync(s->fail.p, 0, sizeof(int), s->stream));
+  return MM_OK;
+}
+
+void trace_push(mm_ba_session* s, int accepted, int lin) {
+  mm_ba_summary& S = s->sum; const int i = S.num_iterations;
+  if (i < MM_BA_TRACE_MAX) { S.trace_cost[i] = s->cost; S.trace_radius[i] = s->radius; S.trace_gradient_max_norm[i] = s->gmax; S.trace_accepted[i] = accepted; S.trace_linear_iterations[i] = lin; }
+  S.num_iterations = i + 1;
+  if (s->cost < S.final_cost) S.final_cost = s->cost;     // SetSummaryFinalCost: min over the recorded iterations
+}
+
+// initial evaluation (iteration 0 of Ceres' minimizer)
+int lm_start(mm_ba_session* s) {
+  mm_ba_summary& S = s->sum;
+  memset(&S, 0, sizeof S);
+  S.num_residuals = 2 * s->n_obs; S.final_cost = INFINITY; S.termination = MM_TERM_NO_CONVERGENCE;
+  s->radius = s->opt.initial_trust_region_radius; s->decrease_factor = 2.0; s->iter = 0; s->n_invalid = 0;
+  s->finished = false; s->started = true; s->scaled = false;
+  if (s->n_obs == 0) { S.termination = MM_TERM_EMPTY; S.initial_cost = S.final_cost = 0.0; S.return_value = NAN; s->finished = true; return MM_OK; }
+  int rc;
+  { Timer t(s, &S.ms_linearize);
+    if ((rc = launch_linearize(s))) return rc;
+    k_fill<<<grid_stride(6 * (int64_t)s->n_img, 256), 256, 0, s->stream>>>(6 * (int64_t)s->n_img, s->scale_c.p, 1.0); MM_LAUNCH_CHECK();
+    k_fill<<<grid_stride(3 * (int64_t)s->n_pt, 256), 256, 0, s->stream>>>(3 * (int64_t)s->n_pt, s->scale_p.p, 1.0); MM_LAUNCH_CHECK();
+    if ((rc = launch_scale(s))) return rc; }
+  { Timer t(s, &S.ms_schur); if ((rc = launch_schur(s))) return rc; }
+  if ((rc = launch_xnorm(s))) return rc;
+  double red[8]; if ((rc = read_red(s, red))) return rc;
+  s->cost = red[0]; s->gmax = red[2]; s->x_norm = sqrt(red[5]);
+  S.initial_cost = s->cost;
+  trace_push(s, 1, 0);
+  s->abs_gtol = s->opt.gradient_tolerance * fmax(s->gmax, 1e-12);
+  if (!isfinite(s->cost)) { S.termination = MM_TERM_NUMERICAL_FAILURE; s->finished = true; set_error("non-finite initial cost"); return MM_ERR_NUMERICAL; }
+  if (s->gmax <= s->abs_gtol) { S.termination = MM_TERM_GRADIENT_TOLERANCE; s->finished = true; }
+  // the iterate at which we stand is the best one so far: poses/pts already hold it (x_min == x)
+  return MM_OK;
+}
+
+// one LM iteration (one linear solve + candidate evaluation + accept/reject)
+int lm_iterate(mm_ba_session* s) {
+  mm_ba_summary& S = s->sum; const mm_ba_options& O = s->opt;
+  if (s->iter >= O.max_num_iterations) { S.termination = MM_TERM_NO_CONVERGENCE; s->finished = true; return MM_OK; }
+  s->iter++;
+  int rc, pcg_it = 0, fail = 0;
+  { Timer t(s, &S.ms_pcg); if ((rc = run_pcg(s, &pcg_it))) return rc; }
+  s->last_pcg_iters = pcg_it;
+  { Timer t(s, &S.ms_update); if ((rc = launch_update(s))) return rc; if ((rc = launch_cost_candidate(s))) return rc; }
+  double red[8]; if ((rc = read_red(s, red))) return rc;
+  if ((rc = read_fail(s, &fail))) return rc;
+  const double new_cost = red[1], step_norm = sqrt(red[3]), mcc = red[4];
+  bool valid = !fail && isfinite(step_norm) && isfinite(mcc) && isfinite(new_cost) && !(mcc < 0.0);
+  bool successful = false; double rel_dec = 0.0;
+  if (!valid) {
+    if (++s->n_invalid >= O.max_num_consecutive_invalid_steps) { S.termination = MM_TERM_NUMERICAL_FAILURE; s->finished = true; return MM_OK; }
+  } else {
+    s->n_invalid = 0;
+    if (step_norm <= O.parameter_tolerance * (s->x_norm + O.parameter_tolerance)) { S.termination = MM_TERM_PARAMETER_TOLERANCE; s->finished = true; return MM_OK; }
+    const double cost_change = s->cost - new_cost;
+    if (fabs(cost_change) < O.function_tolerance * s->cost) { S.termination = MM_TERM_FUNCTION_TOLERANCE; s->finished = true; return MM_OK; }
+    rel_dec = cost_change / mcc;
+    successful = rel_dec > O.min_relative_decrease;
+  }
+  if (successful) {
+    S.num_successful_steps++;
+    s->radius = s->radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * rel_dec - 1.0, 3));
+    s->radius = fmin(O.max_trust_region_radius, s->radius);
+    s->decrease_factor = 2.0;
+    // keep the previous iterate in poses2/pts2 until the gradient test has passed (Ceres 1.8 commits
+    // x_min only after it)
+    std::swap(s->poses.p, s->poses2.p); std::swap(s->pts.p, s->pts2.p); std::swap(s->aux.p, s->aux2.p);
+    { Timer t(s, &S.ms_linearize); if ((rc = launch_linearize(s))) return rc; }
+    { Timer t(s, &S.ms_schur); if ((rc = launch_schur(s))) return rc; }
+    if ((rc = launch_xnorm(s))) return rc;
+    if ((rc = read_red(s, red))) return rc;
+    s->cost = red[0]; s->gmax = red[2]; s->x_norm = sqrt(red[5]);
+    if (s->gmax <= s->abs_gtol) {
+      std::swap(s->poses.p, s->poses2.p); std::swap(s->pts.p, s->pts2.p); std::swap(s->aux.p, s->aux2.p);   // discard, as Ceres 1.8 does
+      S.termination = MM_TERM_GRADIENT_TOLERANCE; s->finished = true; return MM_OK;
+    }
+  } else {
+    S.num_unsuccessful_steps++;
+    s->radius = s->radius / s->decrease_factor; s->decrease_factor *= 2.0;
+    if (s->radius >= O.min_trust_region_radius) { Timer t(s, &S.ms_schur); if ((rc = launch_schur(s))) return rc; }
+  }
+  if (s->radius < O.min_trust_region_radius) { S.termination = MM_TERM_PARAMETER_TOLERANCE; s->finished = true; return MM_OK; }
+  trace_push(s, successful ? 1 : 0, pcg_it);
+  if (O.print_progress)
+    printf("% 4d: f:% 8e new:% 8e g:% 3.2e rho:% 3.2e mu:% 3.2e li:% 3d ok:%d\n", s->iter, s->cost, new_cost, s->gmax, rel_dec, s->radius, pcg_it, (int)successful);
+  return MM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void mm_ba_options_default(mm_ba_options* o) {
+  if (!o) return;
+  memset(o, 0, sizeof *o);
+  o->max_num_iterations = 100; o->function_tolerance = 1e-4; o->gradient_tolerance = 1e-8;   // bundle_adjustment.h:40-42
+  o->loss_type = MM_LOSS_CAUCHY; o->loss_scale = 1.0;                                          // :45
+  o->parameter_tolerance = 1e-8; o->initial_trust_region_radius = 1e4; o->max_trust_region_radius = 1e16;
+  o->min_trust_region_radius = 1e-32; o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32;
+  o->jacobi_scaling = 1; o->max_num_consecutive_invalid_steps = 10;
+  o->linear_solver = MM_SOLVER_PCG; o->pcg_tolerance = 1e-13; o->pcg_max_iterations = 2000; o->print_progress = 0;
+}
+
+void mm_ba_session_destroy(mm_ba_session* s) {
+  if (!s) return;
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
+  delete s;
+}
+
+int mm_ba_session_create(const mm_ba_problem* P, const mm_ba_options* opt, void* stream, mm_ba_session** out) {
+  if (!out || !opt) { set_error("null argument"); return MM_ERR_INVALID_ARG; }
+  *out = nullptr;
+  int rc = validate_problem(P); if (rc) return rc;
+  if (opt->linear_solver != MM_SOLVER_PCG) { set_error("the device engine solves the reduced system with PCG only"); return MM_ERR_UNSUPPORTED; }
+  for (int c = 0; c < P->n_cam; ++c) if (!P->intr_const[c]) {
+    bool used = false; for (int i = 0; i < P->n_img; ++i) if (P->img_cam[i] == c) used = true;
+    if (used) { set_error("refine_camera_params (free intrinsics) is not built into the device engine yet"); return MM_ERR_UNSUPPORTED; }
+  }
+  rc = ensure_device(); if (rc) return rc;
+  mm_ba_session* s = new mm_ba_session();
+  s->stream = (cudaStream_t)stream; s->opt = *opt;
+  s->n_img = P->n_img; s->n_cam = P->n_cam; s->n_pt = P->n_pt; s->n_obs = P->n_obs;
+  auto fail_out = [&](int code) { mm_ba_session_destroy(s); return code; };
+  if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) { set_error("cudaEventCreate failed"); return fail_out(MM_ERR_CUDA); }
+  float ms = 0; cudaEventRecord(s->ev0, s->stream);
+  s->h_poses0.assign(P->poses, P->poses + 6 * (size_t)P->n_img);
+  s->h_intr0.assign(P->intr, P->intr + MM_INTR_STRIDE * (size_t)P->n_cam);
+  s->h_pts0.assign(P->pts, P->pts + 3 * (size_t)P->n_pt);
+  const size_t n_img = (size_t)std::max(P->n_img, 1), n_pt = (size_t)std::max(P->n_pt, 1), n_cam = (size_t)std::max(P->n_cam, 1);
+#define A(buf, count) do { if ((buf).alloc(count) != cudaSuccess) { set_error("cudaMalloc failed for " #buf); cudaGetLastError(); return fail_out(MM_ERR_ALLOC); } } while (0)
+  A(s->poses, 6 * n_img); A(s->poses2, 6 * n_img); A(s->intr, MM_INTR_STRIDE * n_cam); A(s->pts, 3 * n_pt); A(s->pts2, 3 * n_pt);
+  A(s->aux, AUX * n_img); A(s->aux2, AUX * n_img); A(s->rec, (size_t)REC * (size_t)std::max<int64_t>(P->n_obs, 1));
+  A(s->pose_mask, 6 * n_img); A(s->pt_mask, n_pt); A(s->scale_c, 6 * n_img); A(s->scale_p, 3 * n_pt);
+  A(s->Vinv, 6 * n_pt); A(s->gp, 3 * n_pt); A(s->dp, 3 * n_pt); A(s->gc, 6 * n_img); A(s->dc, 6 * n_img); A(s->rhs, 6 * n_img);
+  A(s->vx, 6 * n_img); A(s->vr, 6 * n_img); A(s->vz, 6 * n_img); A(s->vp0, 6 * n_img); A(s->vp1, 6 * n_img); A(s->vAp, 6 * n_img);
+  A(s->pcg_sc, 16); A(s->pcg_ic, 4); A(s->red, 8); A(s->fail, 1); A(s->img_cam, n_img); A(s->cam_model, n_cam); A(s->Minv, 36 * n_img);
+  s->grid_obs = grid_stride(std::max<int64_t>(P->n_obs, 1), 256);
+  s->grid_x = grid_stride(std::max<int64_t>(3 * (int64_t)P->n_pt, 1), 256);
+  A(s->part_cost, (size_t)s->grid_obs); A(s->part_pt, 2 * (size_t)blocks_for(P->n_pt, 128)); A(s->part_cam, 2 * (size_t)blocks_for(6 * (int64_t)P->n_img, 128));
+  A(s->part_x, (size_t)s->grid_x);
+  // masks: 1.0 = free and present in at least one residual block
+  { std::vector<int> img_n(n_img, 0), pt_n(n_pt, 0);
+    for (int64_t o = 0; o < P->n_obs; ++o) { img_n[P->obs_img[o]]++; pt_n[P->obs_pt[o]]++; }
+    std::vector<double> pm(6 * n_img, 0.0), tm(n_pt, 0.0);
+    for (int i = 0; i < P->n_img; ++i) if (img_n[i]) {
+      for (int k = 0; k < 3; ++k) pm[6 * (size_t)i + k] = P->pose_const[4 * (size_t)i] ? 0.0 : 1.0;
+      for (int k = 0; k < 3; ++k) pm[6 * (size_t)i + 3 + k] = P->pose_const[4 * (size_t)i + 1 + k] ? 0.0 : 1.0;
+    }
+    for (int p = 0; p < P->n_pt; ++p) if (pt_n[p] && !P->pt_const[p]) tm[p] = 1.0;
+    if (cudaMemcpy(s->pose_mask.p, pm.data(), sizeof(double) * pm.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(s->pt_mask.p, tm.data(), sizeof(double) * tm.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(s->img_cam.p, P->img_cam, sizeof(int) * (size_t)P->n_img, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(s->cam_model.p, P->cam_model, sizeof(int) * (size_t)P->n_cam, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("mask upload failed"); return fail_out(MM_ERR_CUDA); } }
+  cudaMemsetAsync(s->fail.p, 0, sizeof(int), s->stream);
+  cudaMemsetAsync(s->red.p, 0, sizeof(double) * 8, s->stream);
+  rc = build_structure(s, P); if (rc) return fail_out(rc);
+  A(s->S, 36 * (size_t)std::max<int64_t>(s->nblk, 1));
+#undef A
+  rc = upload_params(s); if (rc) return fail_out(rc);
+  memset(&s->sum, 0, sizeof s->sum);
+  cudaEventRecord(s->ev1, s->stream); cudaEventSynchronize(s->ev1); cudaEventElapsedTime(&ms, s->ev0, s->ev1);
+  rc = lm_start(s); if (rc) return fail_out(rc);
+  s->sum.ms_setup = ms;
+  *out = s;
+  return MM_OK;
+}
+
+int mm_ba_session_reset(mm_ba_session* s) {
+  if (!s) return MM_ERR_INVALID_ARG;
+  int rc = upload_params(s); if (rc) return rc;
+  const double setup = s->sum.ms_setup;
+  rc = lm_start(s);
+  s->sum.ms_setup = setup;
+  return rc;
+}
+
+int mm_ba_session_iterate(mm_ba_session* s, int32_t n, int32_t* n_done) {
+  if (!s) return MM_ERR_INVALID_ARG;
+  int done = 0;
+  for (int i = 0; i < n && !s->finished; ++i) {
+    const int before = s->iter;
+    int rc = lm_iterate(s); if (rc) { if (n_done) *n_done = done; return rc; }
+    if (s->iter > before) ++done;
+  }
+  s->sum.return_value = sqrt(s->sum.final_cost / (double)std::max<int64_t>(s->sum.num_residuals, 1));
+  if (s->sum.num_residuals == 0) s->sum.return_value = NAN;
+  s->sum.ms_total = s->sum.ms_setup + s->sum.ms_linearize + s->sum.ms_schur + s->sum.ms_pcg + s->sum.ms_update;
+  if (n_done) *n_done = done;
+  return MM_OK;
+}
+
+int mm_ba_session_summary(mm_ba_session* s, mm_ba_summary* out) {
+  if (!s || !out) return MM_ERR_INVALID_ARG;
+  *out = s->sum;
+  return MM_OK;
+}
+
+int64_t mm_ba_session_num_blocks(mm_ba_session* s) { return s ? s->nblk : -1; }
+
+int mm_ba_session_download(mm_ba_session* s, double* poses, double* intr, double* pts, double* pt_err) {
+  if (!s) return MM_ERR_INVALID_ARG;
+  cudaStream_t st = s->stream;
+  if (poses) MM_CUDA(cudaMemcpyAsync(poses, s->poses.p, sizeof(double) * 6 * (size_t)s->n_img, cudaMemcpyDeviceToHost, st));
+  if (intr) MM_CUDA(cudaMemcpyAsync(intr, s->intr.p, sizeof(double) * MM_INTR_STRIDE * (size_t)s->n_cam, cudaMemcpyDeviceToHost, st));
+  if (pts) MM_CUDA(cudaMemcpyAsync(pts, s->pts.p, sizeof(double) * 3 * (size_t)s->n_pt, cudaMemcpyDeviceToHost, st));
+  if (pt_err && s->n_pt > 0 && s->n_obs > 0) {
+    // Vinv is free between LM iterations: reuse it as the staging buffer for the per-point errors
+    std::vector<double> host(pt_err, pt_err + s->n_pt);
+    MM_CUDA(cudaMemcpyAsync(s->Vinv.p, host.data(), sizeof(double) * (size_t)s->n_pt, cudaMemcpyHostToDevice, st));
+    k_pose_aux<<<blocks_for(s->n_img, 128), 128, 0, st>>>(s->n_img, s->poses.p, s->aux.p); MM_LAUNCH_CHECK();
+    k_point_errors<<<blocks_for(s->n_pt, 128), 128, 0, st>>>(s->n_pt, s->pt_start.p, s->obs_xy.p, s->obs_img.p, s->aux.p, s->pts.p, s->intr.p,
+        s->img_cam.p, s->cam_model.p, s->Vinv.p); MM_LAUNCH_CHECK();
+    MM_CUDA(cudaMemcpyAsync(pt_err, s->Vinv.p, sizeof(double) * (size_t)s->n_pt, cudaMemcpyDeviceToHost, st));
+    MM_CUDA(cudaStreamSynchronize(st));
+    // the Schur data must be rebuilt if the session continues
+    if (!s->finished) { int rc = launch_schur(s); if (rc) return rc; }
+  }
+  MM_CUDA(cudaStreamSynchronize(st));
+  return MM_OK;
+}
+
+int mm_ba_session_time_kernel(mm_ba_session* s, int32_t which, int32_t reps, double* ms_out) {
+  if (!s || !ms_out || reps <= 0 || s->n_obs == 0) return MM_ERR_INVALID_ARG;
+  cudaStream_t st = s->stream; int rc = MM_OK;
+  // warm-up
+  for (int r = -1; r < reps; ++r) {
+    if (r == 0) MM_CUDA(cudaEventRecord(s->ev0, st));
+    switch (which) {
+      case 0: k_residual_jacobian<true><<<s->grid_obs, 256, 0, st>>>(s->n_obs, s->obs_xy.p, s->obs_img.p, s->obs_pt.p, s->aux.p, s->pts.p, s->intr.p,
+                  s->img_cam.p, s->cam_model.p, s->pose_mask.p, s->pt_mask.p, loss_of(s->opt), s->rec.p, s->part_cost.p); count_launch(); break;
+      case 1: rc = launch_schur(s); break;
+      case 2: k_residual_jacobian<false><<<s->grid_obs, 256, 0, st>>>(s->n_obs, s->obs_xy.p, s->obs_img.p, s->obs_pt.p, s->aux.p, s->pts.p, s->intr.p,
+                  s->img_cam.p, s->cam_model.p, s->pose_mask.p, s->pt_mask.p, loss_of(s->opt), nullptr, s->part_cost.p); count_launch(); break;
+      case 3: {
+        MM_CUDA(cudaMemsetAsync(s->pcg_ic.p, 0, sizeof(int) * 4, st));
+        k_pcg_spmv<<<blocks_for((int64_t)s->n_img * 32, 128), 128, 0, st>>>(s->n_img, s->row_start.p, s->row_col.p, s->row_blk.p, s->S.p,
+            s->vz.p, s->vp0.p, s->vp1.p, s->vAp.p, s->pcg_sc.p + 8, s->pcg_ic.p, 1); count_launch(); break; }
+      default: return MM_ERR_INVALID_ARG;
+    }
+    if (rc) return rc;
+  }
+  MM_CUDA(cudaEventRecord(s->ev1, st)); MM_CUDA(cudaEventSynchronize(s->ev1));
+  float ms = 0; MM_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+  *ms_out = ms / reps;
+  if (which == 3) { MM_CUDA(cudaMemsetAsync(s->pcg_sc.p, 0, sizeof(double) * 8, st)); }
+  return MM_OK;
+}
+
+int mm_ba_solve(mm_ba_problem* P, const mm_ba_options* opt, mm_ba_summary* summary) {
+  if (!P || !opt) { set_error("null argument"); return MM_ERR_INVALID_ARG; }
+  mm_ba_session* s = nullptr;
+  int rc = mm_ba_session_create(P, opt, nullptr, &s); if (rc) return rc;
+  int32_t done = 0;
+  rc = mm_ba_session_iterate(s, opt->max_num_iterations + 1, &done);
+  if (rc == MM_OK) rc = mm_ba_session_download(s, P->poses, P->intr, P->pts, P->pt_err);
+  if (summary) *summary = s->sum;
+  mm_ba_session_destroy(s);
+  return rc;
+}
+
+int mm_pose_refine(double* rvec, double* tvec, int model_code, const double* params, int64_t n, const double* points2D,
+                   const double* points3D, const uint8_t* inlier_mask, const mm_ba_options* opt, mm_ba_summary* summary, double* ret) {
+  // bundle_adjustment.cc:139-225: one free pose; points (:187) and intrinsics (:193) constant
+  if (!rvec || !tvec || !params || n < 0 || model_num_params(model_code) < 0 || !opt || (n > 0 && (!points2D || !points3D))) { set_error("invalid argument"); return MM_ERR_INVALID_ARG; }
+  std::vector<double> pts, obs; std::vector<int32_t> oi, op; std::vector<uint8_t> pc;
+  for (int64_t i = 0; i < n; ++i) if (!inlier_mask || inlier_mask[i]) {
+    op.push_back((int32_t)pc.size()); oi.push_back(0); pc.push_back(1);
+    pts.insert(pts.end(), points3D + 3 * i, points3D + 3 * i + 3); obs.insert(obs.end(), points2D + 2 * i, points2D + 2 * i + 2);
+  }
+  double poses[6] = { rvec[0], rvec[1], rvec[2], tvec[0], tvec[1], tvec[2] };
+  uint8_t pose_const[4] = {0, 0, 0, 0}; int32_t img_cam[1] = {0}; double intr[MM_INTR_STRIDE] = {0};
+  memcpy(intr, params, sizeof(double) * (size_t)model_num_params(model_code));
+  int32_t cam_model[1] = { model_code }; uint8_t intr_const[1] = {1};
+  mm_ba_problem P; memset(&P, 0, sizeof P);
+  P.n_img = 1; P.n_cam = 1; P.n_pt = (int32_t)pc.size(); P.n_obs = (int64_t)pc.size();
+  double dummy3[3] = {0, 0, 0}, dummy2[2] = {0, 0}; int32_t dummyi[1] = {0}; uint8_t dummyc[1] = {1};
+  P.poses = poses; P.pose_const = pose_const; P.img_cam = img_cam; P.intr = intr; P.cam_model = cam_model; P.intr_const = intr_const;
+  P.pts = pts.empty() ? dummy3 : pts.data(); P.pt_const = pc.empty() ? dummyc : pc.data();
+  P.obs_xy = obs.empty() ? dummy2 : obs.data(); P.obs_img = oi.empty() ? dummyi : oi.data(); P.obs_pt = op.empty() ? dummyi : op.data();
+  mm_ba_summary S; int rc = mm_ba_solve(&P, opt, &S);
+  if (rc == MM_OK) { for (int k = 0; k < 3; ++k) { rvec[k] = poses[k]; tvec[k] = poses[3 + k]; } if (ret) *ret = S.return_value; if (summary) *summary = S; }
+  return rc;
+}
+
+}  // extern "C"

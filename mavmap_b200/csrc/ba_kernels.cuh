@@ -1,0 +1,645 @@
+// ba_kernels.cuh — device kernels of the bundle-adjustment inner loop (fp64, HBM-bound).
+//
+// What they replace in the reference (mavmap/mavmap) + Ceres:
+//   K1 k_residual_jacobian   Ceres autodiff of BACostFunction<M>::operator()
+//                            (src/base3d/bundle_adjustment.h:131-159) + Corrector for
+//                            CauchyLoss (bundle_adjustment.cc:477-478)
+//   K2 k_schur_point/_cam    Ceres SchurEliminator::Eliminate behind SPARSE_SCHUR
+//                            (bundle_adjustment.cc:555)
+//   K3 k_pcg_*               the reduced-camera-system solve (Ceres: sparse Cholesky)
+//   K4 k_backsub / k_cost    SchurEliminator::BackSubstitute + the candidate-cost Evaluate
+// Layout (DESIGN.md §Data layout): observations sorted by 3-D point; one 160-byte record per
+// observation  [r0 r1 | Jc row0 (w0 w1 w2 tx ty tz) | Jc row1 | Jp row0 | Jp row1]  so that the
+// point pass streams records and the camera pass gathers whole 32-byte sectors.
+#pragma once
+#include "common.cuh"
+#include "camera.cuh"
+
+namespace mm {
+
+constexpr int REC = 20;     // doubles per observation record (160 B = 5 sectors)
+constexpr int AUX = 24;     // doubles per image: R(9) Jl(9) t(3) pad(3) = 192 B
+
+struct LossParams { int type; double b; double c; };   // Cauchy: b = a^2, c = 1/b
+
+__device__ __forceinline__ void loss_eval(const LossParams& L, double s, double& rho0, double& sqrt_rho1) {
+  if (L.type == MM_LOSS_CAUCHY) {
+    const double sum = 1.0 + s * L.c, inv = 1.0 / sum;
+    rho0 = L.b * log(sum);
+    sqrt_rho1 = sqrt(fmax(inv, 2.2250738585072014e-308));
+  } else { rho0 = s; sqrt_rho1 = 1.0; }
+}
+
+// ---- per-image rotation data ---------------------------------------------------------
+__global__ void k_pose_aux(int n_img, const double* __restrict__ poses, double* __restrict__ aux) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_img) return;
+  double R[9], Jl[9];
+  const double* p = poses + 6 * (size_t)i;
+  rotation_and_left_jacobian(p, R, Jl);
+  double* a = aux + AUX * (size_t)i;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { a[k] = R[k]; a[9 + k] = Jl[k]; }
+  a[18] = p[3]; a[19] = p[4]; a[20] = p[5]; a[21] = 0; a[22] = 0; a[23] = 0;
+}
+
+// ---- K1: residual + Jacobian per observation -------------------------------------------
+// reads 24 B/obs (xy, img, pt) + gathered parameters, writes one 160 B record.
+// cost partial per block -> cost_part[blockIdx.x] (reduced deterministically afterwards).
+template <bool WITH_J>
+__global__ void __launch_bounds__(256) k_residual_jacobian(
+    int64_t n_obs, const double2* __restrict__ obs_xy, const int* __restrict__ obs_img, const int* __restrict__ obs_pt,
+    const double* __restrict__ aux, const double* __restrict__ pts, const double* __restrict__ intr,
+    const int* __restrict__ img_cam, const int* __restrict__ cam_model,
+    const double* __restrict__ pose_mask, const double* __restrict__ pt_mask,
+    LossParams L, double* __restrict__ rec, double* __restrict__ cost_part) {
+  __shared__ double red[32];
+  double cost = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_obs; i += (int64_t)gridDim.x * blockDim.x) {
+    const int img = obs_img[i], pt = obs_pt[i];
+    const double2 xy = obs_xy[i];
+    const double* a = aux + AUX * (size_t)img;
+    const double X0 = pts[3 * (size_t)pt], X1 = pts[3 * (size_t)pt + 1], X2 = pts[3 * (size_t)pt + 2];
+    double R[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[k] = a[k];
+    const double Y0 = R[0] * X0 + R[1] * X1 + R[2] * X2;
+    const double Y1 = R[3] * X0 + R[4] * X1 + R[5] * X2;
+    const double Y2 = R[6] * X0 + R[7] * X1 + R[8] * X2;
+    const double xc = Y0 + a[18], yc = Y1 + a[19], zc = Y2 + a[20];
+    const int cam = img_cam[img];
+    const int model = cam_model[cam];
+    double u, v, dX[2][3];
+    world2image<WITH_J>(model, intr + MM_INTR_STRIDE * (size_t)cam, xc, yc, zc, u, v, dX, nullptr);
+    double r0 = u - xy.x, r1 = v - xy.y;
+    double rho0, sr;
+    loss_eval(L, r0 * r0 + r1 * r1, rho0, sr);
+    cost += 0.5 * rho0;
+    if (WITH_J) {
+      double* out = rec + REC * (size_t)i;
+      const double* pm = pose_mask + 6 * (size_t)img;
+      const double mp = pt_mask[pt] * sr;
+      const double mw = pm[0] * sr, mx = pm[3] * sr, my = pm[4] * sr, mz = pm[5] * sr;
+      // d(Xc)/d(w) = -[Y]x Jl : column k = Jl[:,k] x Y
+      double M[3][3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double c0 = a[9 + k], c1 = a[12 + k], c2 = a[15 + k];
+        M[0][k] = c1 * Y2 - c2 * Y1; M[1][k] = c2 * Y0 - c0 * Y2; M[2][k] = c0 * Y1 - c1 * Y0;
+      }
+      double2* o2 = reinterpret_cast<double2*>(out);
+      o2[0] = make_double2(sr * r0, sr * r1);
+#pragma unroll
+      for (int row = 0; row < 2; ++row) {
+        const double d0 = dX[row][0], d1 = dX[row][1], d2 = dX[row][2];
+        const double jw0 = (d0 * M[0][0] + d1 * M[1][0] + d2 * M[2][0]) * mw;
+        const double jw1 = (d0 * M[0][1] + d1 * M[1][1] + d2 * M[2][1]) * mw;
+        const double jw2 = (d0 * M[0][2] + d1 * M[1][2] + d2 * M[2][2]) * mw;
+        o2[1 + 3 * row] = make_double2(jw0, jw1);
+        o2[2 + 3 * row] = make_double2(jw2, d0 * mx);
+        o2[3 + 3 * row] = make_double2(d1 * my, d2 * mz);
+      }
+      const double p00 = (dX[0][0] * R[0] + dX[0][1] * R[3] + dX[0][2] * R[6]) * mp;
+      const double p01 = (dX[0][0] * R[1] + dX[0][1] * R[4] + dX[0][2] * R[7]) * mp;
+      const double p02 = (dX[0][0] * R[2] + dX[0][1] * R[5] + dX[0][2] * R[8]) * mp;
+      const double p10 = (dX[1][0] * R[0] + dX[1][1] * R[3] + dX[1][2] * R[6]) * mp;
+      const double p11 = (dX[1][0] * R[1] + dX[1][1] * R[4] + dX[1][2] * R[7]) * mp;
+      const double p12 = (dX[1][0] * R[2] + dX[1][1] * R[5] + dX[1][2] * R[8]) * mp;
+      o2[7] = make_double2(p00, p01);
+      o2[8] = make_double2(p02, p10);
+      o2[9] = make_double2(p11, p12);
+    }
+  }
+  cost = block_sum(cost, red);
+  if (threadIdx.x == 0) cost_part[blockIdx.x] = cost;
+}
+
+// deterministic final reduction of per-block partials: out[0] = sum(part[0..n))
+__global__ void k_reduce_sum(const double* __restrict__ part, int n, double* __restrict__ out) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += part[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[0] = s;
+}
+
+// ---- Jacobi column scaling (estimated once, trust_region_minimizer.cc EstimateScale) ----
+__global__ void k_colnorm_point(int n_pt, const int* __restrict__ pt_start, const double* __restrict__ rec, double* __restrict__ scale_p) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pt) return;
+  double s0 = 0, s1 = 0, s2 = 0;
+  for (int o = pt_start[p]; o < pt_start[p + 1]; ++o) {
+    const double* r = rec + REC * (size_t)o + 14;
+    s0 += r[0] * r[0] + r[3] * r[3]; s1 += r[1] * r[1] + r[4] * r[4]; s2 += r[2] * r[2] + r[5] * r[5];
+  }
+  scale_p[3 * (size_t)p] = 1.0 / (1.0 + sqrt(s0));
+  scale_p[3 * (size_t)p + 1] = 1.0 / (1.0 + sqrt(s1));
+  scale_p[3 * (size_t)p + 2] = 1.0 / (1.0 + sqrt(s2));
+}
+
+// one warp per image
+__global__ void k_colnorm_cam(int n_img, const int* __restrict__ cam_start, const int* __restrict__ cam_perm,
+                              const double* __restrict__ rec, double* __restrict__ scale_c) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n_img) return;
+  double s[6] = {0, 0, 0, 0, 0, 0};
+  for (int q = cam_start[w] + lane; q < cam_start[w + 1]; q += 32) {
+    const double* r = rec + REC * (size_t)cam_perm[q] + 2;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s[k] += r[k] * r[k] + r[6 + k] * r[6 + k];
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) s[k] = warp_sum(s[k]);
+  if (lane < 6) {
+    double v = s[0];
+#pragma unroll
+    for (int k = 1; k < 6; ++k) if (lane == k) v = s[k];
+    scale_c[6 * (size_t)w + lane] = 1.0 / (1.0 + sqrt(v));
+  }
+}
+
+// ---- K2a: per-point blocks and the off-diagonal Schur updates ----------------------------
+// thread per point: V' = s_p (sum Jp'Jp) s_p + D_p^2, inverse, g_p'; then for every pair (i<j) of its
+// observations S(img_i,img_j) -= Y_i W_j' with Y_i = W_i V'^-1, W = Jc' Jp (scaled).
+struct LMDiag { double radius, min_diag, max_diag; };
+
+__device__ __forceinline__ bool sym3_inverse(const double* V /*xx xy xz yy yz zz*/, double* I) {
+  const double a = V[0], b = V[1], c = V[2], d = V[3], e = V[4], f = V[5];
+  const double A = d * f - e * e, B = -(b * f - c * e), C = b * e - c * d;
+  const double det = a * A + b * B + c * C;
+  if (!(det > 0.0) || !isfinite(det)) return false;
+  const double id = 1.0 / det;
+  I[0] = A * id; I[1] = B * id; I[2] = C * id;
+  I[3] = (a * f - c * c) * id; I[4] = -(a * e - b * c) * id; I[5] = (a * d - b * b) * id;
+  return true;
+}
+
+__device__ __forceinline__ void load_scaled(const double* __restrict__ rec, int64_t o, const double* __restrict__ sc /*6*/,
+                                            const double* sp /*3*/, double (&Jc)[2][6], double (&Jp)[2][3]) {
+  const double2* r2 = reinterpret_cast<const double2*>(rec + REC * (size_t)o);
+  double t[18];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { const double2 v = r2[1 + k]; t[2 * k] = v.x; t[2 * k + 1] = v.y; }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { const double s = sc[k]; Jc[0][k] = t[k] * s; Jc[1][k] = t[6 + k] * s; }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { Jp[0][k] = t[12 + k] * sp[k]; Jp[1][k] = t[15 + k] * sp[k]; }
+}
+
+__global__ void __launch_bounds__(128) k_schur_point(
+    int n_pt, const int* __restrict__ pt_start, const int* __restrict__ obs_img, const double* __restrict__ rec,
+    const double* __restrict__ scale_c, const double* __restrict__ scale_p, LMDiag lm,
+    const int64_t* __restrict__ pair_off, const int* __restrict__ pair_blk,
+    double* __restrict__ S, double* __restrict__ Vinv, double* __restrict__ gp_out, double* __restrict__ dp_out,
+    double* __restrict__ gmax, int* __restrict__ fail) {
+  __shared__ double red[32];
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  double gm = 0.0;
+  if (p < n_pt) {
+    const int o0 = pt_start[p], o1 = pt_start[p + 1];
+    const double sp[3] = { scale_p[3 * (size_t)p], scale_p[3 * (size_t)p + 1], scale_p[3 * (size_t)p + 2] };
+    double V[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
+    for (int o = o0; o < o1; ++o) {
+      const double2* r2 = reinterpret_cast<const double2*>(rec + REC * (size_t)o);
+      const double2 rr = r2[0], a = r2[7], b = r2[8], c = r2[9];
+      const double j00 = a.x * sp[0], j01 = a.y * sp[1], j02 = b.x * sp[2];
+      const double j10 = b.y * sp[0], j11 = c.x * sp[1], j12 = c.y * sp[2];
+      V[0] += j00 * j00 + j10 * j10; V[1] += j00 * j01 + j10 * j11; V[2] += j00 * j02 + j10 * j12;
+      V[3] += j01 * j01 + j11 * j11; V[4] += j01 * j02 + j11 * j12; V[5] += j02 * j02 + j12 * j12;
+      g[0] += j00 * rr.x + j10 * rr.y; g[1] += j01 * rr.x + j11 * rr.y; g[2] += j02 * rr.x + j12 * rr.y;
+    }
+    const double d0 = fmin(fmax(V[0], lm.min_diag), lm.max_diag) / lm.radius;
+    const double d1 = fmin(fmax(V[3], lm.min_diag), lm.max_diag) / lm.radius;
+    const double d2 = fmin(fmax(V[5], lm.min_diag), lm.max_diag) / lm.radius;
+    V[0] += d0; V[3] += d1; V[5] += d2;
+    double I[6];
+    if (!sym3_inverse(V, I)) { *fail = 1; I[0] = I[3] = I[5] = 0; I[1] = I[2] = I[4] = 0; }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) Vinv[6 * (size_t)p + k] = I[k];
+    gp_out[3 * (size_t)p] = g[0]; gp_out[3 * (size_t)p + 1] = g[1]; gp_out[3 * (size_t)p + 2] = g[2];
+    dp_out[3 * (size_t)p] = d0; dp_out[3 * (size_t)p + 1] = d1; dp_out[3 * (size_t)p + 2] = d2;
+    gm = fmax(fmax(fabs(g[0] / sp[0]), fabs(g[1] / sp[1])), fabs(g[2] / sp[2]));
+    if (o1 - o0 > 1) {
+      int64_t slot = pair_off[p];
+      for (int oi = o0; oi < o1 - 1; ++oi) {
+        const int ia = obs_img[oi];
+        double Jc[2][6], Jp[2][3];
+        load_scaled(rec, oi, scale_c + 6 * (size_t)ia, sp, Jc, Jp);
+        double Y[6][3];
+        bool nz = false;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+          const double w0 = Jc[0][a] * Jp[0][0] + Jc[1][a] * Jp[1][0];
+          const double w1 = Jc[0][a] * Jp[0][1] + Jc[1][a] * Jp[1][1];
+          const double w2 = Jc[0][a] * Jp[0][2] + Jc[1][a] * Jp[1][2];
+          Y[a][0] = w0 * I[0] + w1 * I[1] + w2 * I[2];
+          Y[a][1] = w0 * I[1] + w1 * I[3] + w2 * I[4];
+          Y[a][2] = w0 * I[2] + w1 * I[4] + w2 * I[5];
+          nz |= (w0 != 0.0) | (w1 != 0.0) | (w2 != 0.0);
+        }
+        for (int oj = oi + 1; oj < o1; ++oj, ++slot) {
+          if (!nz) continue;
+          const int ib = obs_img[oj];
+          double Kc[2][6], Kp[2][3];
+          load_scaled(rec, oj, scale_c + 6 * (size_t)ib, sp, Kc, Kp);
+          double* dst = S + 36 * (size_t)pair_blk[slot];
+          double T[6][2];
+#pragma unroll
+          for (int a = 0; a < 6; ++a) {
+            T[a][0] = Y[a][0] * Kp[0][0] + Y[a][1] * Kp[0][1] + Y[a][2] * Kp[0][2];
+            T[a][1] = Y[a][0] * Kp[1][0] + Y[a][1] * Kp[1][1] + Y[a][2] * Kp[1][2];
+          }
+          if (ia == ib) {
+            double Bm[6][6];
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+              for (int c = 0; c < 6; ++c) Bm[a][c] = T[a][0] * Kc[0][c] + T[a][1] * Kc[1][c];
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+              for (int c = 0; c < 6; ++c) { const double v = Bm[a][c] + Bm[c][a]; if (v != 0.0) atomicAdd(dst + 6 * a + c, -v); }
+          } else {
+            const bool fwd = ia < ib;
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+              for (int c = 0; c < 6; ++c) {
+                const double v = T[a][0] * Kc[0][c] + T[a][1] * Kc[1][c];
+                if (v != 0.0) atomicAdd(dst + (fwd ? 6 * a + c : 6 * c + a), -v);
+              }
+          }
+        }
+      }
+    }
+  }
+  gm = block_max(gm, red);
+  if (threadIdx.x == 0 && gm > 0.0) atomic_max_nonneg(gmax, gm);
+}
+
+// ---- K2b: per-image diagonal block, reduced right-hand side, gradient, LM diagonal ----------
+// one warp per image over its observations (camera-sorted permutation, 160 B record gathers).
+__global__ void __launch_bounds__(128) k_schur_cam(
+    int n_img, const int* __restrict__ cam_start, const int* __restrict__ cam_perm, const int* __restrict__ obs_pt,
+    const double* __restrict__ rec, const double* __restrict__ scale_c, const double* __restrict__ scale_p,
+    const double* __restrict__ Vinv, const double* __restrict__ gp, LMDiag lm,
+    double* __restrict__ S, double* __restrict__ rhs, double* __restrict__ gc_out, double* __restrict__ dc_out,
+    double* __restrict__ gmax) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n_img) return;
+  double sc[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) sc[k] = scale_c[6 * (size_t)w + k];
+  double Q[21], h[6], gc[6], ud[6];
+#pragma unroll
+  for (int k = 0; k < 21; ++k) Q[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { h[k] = 0.0; gc[k] = 0.0; ud[k] = 0.0; }
+  for (int q = cam_start[w] + lane; q < cam_start[w + 1]; q += 32) {
+    const int o = cam_perm[q];
+    const int p = obs_pt[o];
+    const double sp[3] = { scale_p[3 * (size_t)p], scale_p[3 * (size_t)p + 1], scale_p[3 * (size_t)p + 2] };
+    double Jc[2][6], Jp[2][3];
+    load_scaled(rec, o, sc, sp, Jc, Jp);
+    const double2 rr = *reinterpret_cast<const double2*>(rec + REC * (size_t)o);
+    double I[6], g3[3];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) I[k] = Vinv[6 * (size_t)p + k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) g3[k] = gp[3 * (size_t)p + k];
+    double W[6][3], Y[6][3];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      W[a][0] = Jc[0][a] * Jp[0][0] + Jc[1][a] * Jp[1][0];
+      W[a][1] = Jc[0][a] * Jp[0][1] + Jc[1][a] * Jp[1][1];
+      W[a][2] = Jc[0][a] * Jp[0][2] + Jc[1][a] * Jp[1][2];
+      Y[a][0] = W[a][0] * I[0] + W[a][1] * I[1] + W[a][2] * I[2];
+      Y[a][1] = W[a][0] * I[1] + W[a][1] * I[3] + W[a][2] * I[4];
+      Y[a][2] = W[a][0] * I[2] + W[a][1] * I[4] + W[a][2] * I[5];
+      const double ga = Jc[0][a] * rr.x + Jc[1][a] * rr.y;
+      gc[a] += ga;
+      h[a] += ga - (Y[a][0] * g3[0] + Y[a][1] * g3[1] + Y[a][2] * g3[2]);
+      ud[a] += Jc[0][a] * Jc[0][a] + Jc[1][a] * Jc[1][a];
+    }
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int c = a; c < 6; ++c, ++k)
+        Q[k] += Jc[0][a] * Jc[0][c] + Jc[1][a] * Jc[1][c] - (Y[a][0] * W[c][0] + Y[a][1] * W[c][1] + Y[a][2] * W[c][2]);
+  }
+#pragma unroll
+  for (int k = 0; k < 21; ++k) Q[k] = warp_sum(Q[k]);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { h[k] = warp_sum(h[k]); gc[k] = warp_sum(gc[k]); ud[k] = warp_sum(ud[k]); }
+  if (lane == 0) {
+    double* dst = S + 36 * (size_t)w;      // diagonal block id == image index
+    double gm = 0.0;
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      const double d = fmin(fmax(ud[a], lm.min_diag), lm.max_diag) / lm.radius;
+      dc_out[6 * (size_t)w + a] = d;
+      gc_out[6 * (size_t)w + a] = gc[a];
+      rhs[6 * (size_t)w + a] = h[a];
+      gm = fmax(gm, fabs(gc[a] / sc[a]));
+#pragma unroll
+      for (int c = a; c < 6; ++c, ++k) {
+        if (c == a) dst[6 * a + a] += Q[k] + d;
+        else { dst[6 * a + c] += Q[k]; dst[6 * c + a] += Q[k]; }
+      }
+    }
+    if (gm > 0.0) atomic_max_nonneg(gmax, gm);
+  }
+}
+
+// ---- block-Jacobi preconditioner: inverse of each 6x6 diagonal block --------------------
+__global__ void k_precond(int n_img, const double* __restrict__ S, double* __restrict__ Minv, int* __restrict__ fail) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_img) return;
+  double L[6][6];
+  const double* A = S + 36 * (size_t)i;
+  bool ok = true;
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) L[r][c] = A[6 * r + c];
+  // Cholesky
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double d = L[j][j];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) if (k < j) d -= L[j][k] * L[j][k];
+    if (!(d > 0.0)) { ok = false; d = 1.0; }
+    const double ljj = sqrt(d);
+    L[j][j] = ljj;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) if (r > j) {
+      double s = L[r][j];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) if (k < j) s -= L[r][k] * L[j][k];
+      L[r][j] = s / ljj;
+    }
+  }
+  // invert via solving L L' X = I column by column
+  double* out = Minv + 36 * (size_t)i;
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    double y[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      double s = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) if (k < r) s -= L[r][k] * y[k];
+      y[r] = s / L[r][r];
+    }
+#pragma unroll
+    for (int r = 5; r >= 0; --r) {
+      double s = y[r];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) if (k > r) s -= L[k][r] * y[k];
+      y[r] = s / L[r][r];
+    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r) out[6 * r + c] = y[r];
+  }
+  if (!ok) *fail = 1;
+}
+
+// ---- K3: PCG on the reduced camera system (block-CSR with transposed references) -----------
+// scalars layout (double): [0]=rz  [1]=pAp  [2]=rz_new  [3]=rr  [4]=bb   ; ints: [0]=done [1]=iters
+struct PcgVecs { double *x, *r, *z, *p0, *p1, *Ap; };
+
+// init: x = 0, r = b, z = Minv r, p0 = z; rz = r.z, bb = b.b (single block handles reduction per block + atomics)
+__global__ void k_pcg_init(int n_img, const double* __restrict__ b, const double* __restrict__ Minv, PcgVecs v,
+                           double* __restrict__ sc, int* __restrict__ ic) {
+  __shared__ double red[32];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double rz = 0.0, bb = 0.0;
+  if (i < n_img) {
+    double r[6], z[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) r[k] = b[6 * (size_t)i + k];
+    const double* M = Minv + 36 * (size_t)i;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      double s = 0.0;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) s += M[6 * a + c] * r[c];
+      z[a] = s;
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      v.x[6 * (size_t)i + k] = 0.0; v.r[6 * (size_t)i + k] = r[k]; v.z[6 * (size_t)i + k] = z[k]; v.p0[6 * (size_t)i + k] = 0.0; v.p1[6 * (size_t)i + k] = 0.0;
+      rz += r[k] * z[k]; bb += r[k] * r[k];
+    }
+  }
+  rz = block_sum(rz, red); bb = block_sum(bb, red);
+  if (threadIdx.x == 0) { atomicAdd(sc + 2, rz); atomicAdd(sc + 4, bb); atomicAdd(sc + 3, bb); }
+  (void)ic;
+}
+
+// A: p_new = z + beta p_old (beta = rz_new/rz, 0 on the first iteration); Ap = S p_new; pAp += p_new.Ap
+// one warp per block-row; lanes split the row's blocks.
+__global__ void __launch_bounds__(128) k_pcg_spmv(
+    int n_img, const int* __restrict__ row_start, const int* __restrict__ row_col, const int* __restrict__ row_blk,
+    const double* __restrict__ S, const double* __restrict__ z, const double* __restrict__ p_old, double* __restrict__ p_new,
+    double* __restrict__ Ap, double* __restrict__ sc, const int* __restrict__ ic, int first) {
+  if (ic[0]) return;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n_img) return;
+  const double beta = first ? 0.0 : sc[2] / sc[0];
+  double y[6] = {0, 0, 0, 0, 0, 0};
+  for (int e = row_start[w] + lane; e < row_start[w + 1]; e += 32) {
+    const int col = row_col[e]; const int bid = row_blk[e];
+    const bool tr = bid < 0;
+    const double* B = S + 36 * (size_t)(tr ? -bid - 1 : bid);
+    double pv[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) pv[k] = z[6 * (size_t)col + k] + beta * p_old[6 * (size_t)col + k];
+    double Bv[36];
+    const double2* B2 = reinterpret_cast<const double2*>(B);
+#pragma unroll
+    for (int k = 0; k < 18; ++k) { const double2 t = B2[k]; Bv[2 * k] = t.x; Bv[2 * k + 1] = t.y; }
+    if (!tr) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) y[a] += Bv[6 * a + c] * pv[c];
+    } else {
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) y[a] += Bv[6 * c + a] * pv[c];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) y[k] = warp_sum(y[k]);
+  if (lane == 0) {
+    double dot = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const double pn = z[6 * (size_t)w + k] + beta * p_old[6 * (size_t)w + k];
+      p_new[6 * (size_t)w + k] = pn; Ap[6 * (size_t)w + k] = y[k];
+      dot += pn * y[k];
+    }
+    atomicAdd(sc + 1, dot);
+  }
+}
+
+// B: alpha = rz_new_prev / pAp ; x += alpha p ; r -= alpha Ap ; z = Minv r ; accumulate rz_next, rr.
+// The last block to finish rotates the scalars and tests convergence.
+__global__ void __launch_bounds__(128) k_pcg_update(
+    int n_img, const double* __restrict__ Minv, const double* __restrict__ p, const double* __restrict__ Ap,
+    double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
+    double* __restrict__ sc, int* __restrict__ ic, double tol2, int max_iter) {
+  if (ic[0]) return;
+  __shared__ double red[32];
+  __shared__ int last;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const double alpha = sc[2] / sc[1];
+  double rz = 0.0, rr = 0.0;
+  if (i < n_img) {
+    double rv[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      x[6 * (size_t)i + k] += alpha * p[6 * (size_t)i + k];
+      rv[k] = r[6 * (size_t)i + k] - alpha * Ap[6 * (size_t)i + k];
+      r[6 * (size_t)i + k] = rv[k];
+      rr += rv[k] * rv[k];
+    }
+    const double* M = Minv + 36 * (size_t)i;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      double s = 0.0;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) s += M[6 * a + c] * rv[c];
+      z[6 * (size_t)i + a] = s; rz += rv[a] * s;
+    }
+  }
+  rz = block_sum(rz, red); rr = block_sum(rr, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(sc + 5, rz); atomicAdd(sc + 6, rr);
+    __threadfence();
+    last = (atomicAdd(ic + 2, 1) == (int)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    const double rz_next = atomicAdd(sc + 5, 0.0), rr_now = atomicAdd(sc + 6, 0.0);
+    sc[0] = sc[2];          // rz <- rz_new (the one used for alpha)
+    sc[2] = rz_next;        // rz_new <- r.z of this iteration (beta = sc[2]/sc[0] next time)
+    sc[3] = rr_now; sc[1] = 0.0; sc[5] = 0.0; sc[6] = 0.0;
+    ic[2] = 0;
+    const int it = ic[1] + 1; ic[1] = it;
+    if (rr_now <= tol2 * sc[4] || it >= max_iter || !(rr_now == rr_now)) ic[0] = 1;
+    __threadfence();
+  }
+}
+
+// ---- K4a: back-substitution for the points + candidate point parameters --------------------
+// y_p = V'^-1 (g_p - sum_i W_i' y_c[img_i]); delta = -y_p * s_p.  Partials: [0] step_norm2,
+// [1] model cost change 1/2 y (g + D y)  (valid because the linear system is solved to pcg_tolerance).
+__global__ void __launch_bounds__(128) k_backsub(
+    int n_pt, const int* __restrict__ pt_start, const int* __restrict__ obs_img, const double* __restrict__ rec,
+    const double* __restrict__ scale_c, const double* __restrict__ scale_p, const double* __restrict__ Vinv,
+    const double* __restrict__ gp, const double* __restrict__ dp, const double* __restrict__ yc,
+    const double* __restrict__ pts, double* __restrict__ pts2, double* __restrict__ part /*[2*grid]*/) {
+  __shared__ double red[32];
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  double sn = 0.0, mc = 0.0;
+  if (p < n_pt) {
+    const double sp[3] = { scale_p[3 * (size_t)p], scale_p[3 * (size_t)p + 1], scale_p[3 * (size_t)p + 2] };
+    double t[3] = { gp[3 * (size_t)p], gp[3 * (size_t)p + 1], gp[3 * (size_t)p + 2] };
+    const double g0 = t[0], g1 = t[1], g2 = t[2];
+    for (int o = pt_start[p]; o < pt_start[p + 1]; ++o) {
+      const int ia = obs_img[o];
+      double Jc[2][6], Jp[2][3];
+      load_scaled(rec, o, scale_c + 6 * (size_t)ia, sp, Jc, Jp);
+      double q0 = 0.0, q1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { const double y = yc[6 * (size_t)ia + k]; q0 += Jc[0][k] * y; q1 += Jc[1][k] * y; }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) t[k] -= Jp[0][k] * q0 + Jp[1][k] * q1;
+    }
+    const double* I = Vinv + 6 * (size_t)p;
+    const double y0 = I[0] * t[0] + I[1] * t[1] + I[2] * t[2];
+    const double y1 = I[1] * t[0] + I[3] * t[1] + I[4] * t[2];
+    const double y2 = I[2] * t[0] + I[4] * t[1] + I[5] * t[2];
+    const double e0 = -y0 * sp[0], e1 = -y1 * sp[1], e2 = -y2 * sp[2];
+    pts2[3 * (size_t)p] = pts[3 * (size_t)p] + e0; pts2[3 * (size_t)p + 1] = pts[3 * (size_t)p + 1] + e1; pts2[3 * (size_t)p + 2] = pts[3 * (size_t)p + 2] + e2;
+    sn = e0 * e0 + e1 * e1 + e2 * e2;
+    mc = 0.5 * (y0 * (g0 + dp[3 * (size_t)p] * y0) + y1 * (g1 + dp[3 * (size_t)p + 1] * y1) + y2 * (g2 + dp[3 * (size_t)p + 2] * y2));
+  }
+  sn = block_sum(sn, red); mc = block_sum(mc, red);
+  if (threadIdx.x == 0) { part[2 * blockIdx.x] = sn; part[2 * blockIdx.x + 1] = mc; }
+}
+
+// ---- K4b: candidate camera parameters -------------------------------------------------------
+__global__ void k_update_cam(int n, const double* __restrict__ yc, const double* __restrict__ scale_c,
+                             const double* __restrict__ gc, const double* __restrict__ dc,
+                             const double* __restrict__ poses, double* __restrict__ poses2, double* __restrict__ part) {
+  __shared__ double red[32];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double sn = 0.0, mc = 0.0;
+  if (i < n) {
+    const double y = yc[i];
+    const double e = -y * scale_c[i];
+    poses2[i] = poses[i] + e;
+    sn = e * e;
+    mc = 0.5 * y * (gc[i] + dc[i] * y);
+  }
+  sn = block_sum(sn, red); mc = block_sum(mc, red);
+  if (threadIdx.x == 0) { part[2 * blockIdx.x] = sn; part[2 * blockIdx.x + 1] = mc; }
+}
+
+__global__ void k_reduce_pairs(const double* __restrict__ partA, int nA, const double* __restrict__ partB, int nB,
+                               double* __restrict__ out /*[2]*/) {
+  __shared__ double red[32];
+  double s0 = 0.0, s1 = 0.0;
+  for (int i = threadIdx.x; i < nA; i += blockDim.x) { s0 += partA[2 * i]; s1 += partA[2 * i + 1]; }
+  for (int i = threadIdx.x; i < nB; i += blockDim.x) { s0 += partB[2 * i]; s1 += partB[2 * i + 1]; }
+  s0 = block_sum(s0, red); s1 = block_sum(s1, red);
+  if (threadIdx.x == 0) { out[0] = s0; out[1] = s1; }
+}
+
+// sum of squares of the active parameters (x_norm of the reduced program)
+__global__ void k_xnorm(int n_c, const double* __restrict__ poses, const double* __restrict__ pose_mask,
+                        int n_pt, const double* __restrict__ pts, const double* __restrict__ pt_mask, double* __restrict__ part) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_c; i += (int64_t)gridDim.x * blockDim.x)
+    s += pose_mask[i] * poses[i] * poses[i];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < 3 * (int64_t)n_pt; i += (int64_t)gridDim.x * blockDim.x)
+    s += pt_mask[i / 3] * pts[i] * pts[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+
+// mean raw residual norm per point (bundle_adjustment.cc:575-598)
+__global__ void k_point_errors(int n_pt, const int* __restrict__ pt_start, const double2* __restrict__ obs_xy,
+                               const int* __restrict__ obs_img, const double* __restrict__ aux, const double* __restrict__ pts,
+                               const double* __restrict__ intr, const int* __restrict__ img_cam, const int* __restrict__ cam_model,
+                               double* __restrict__ pt_err) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pt) return;
+  const int o0 = pt_start[p], o1 = pt_start[p + 1];
+  if (o1 == o0) return;
+  const double X0 = pts[3 * (size_t)p], X1 = pts[3 * (size_t)p + 1], X2 = pts[3 * (size_t)p + 2];
+  double s = 0.0;
+  for (int o = o0; o < o1; ++o) {
+    const int img = obs_img[o];
+    const double* a = aux + AUX * (size_t)img;
+    const double xc = a[0] * X0 + a[1] * X1 + a[2] * X2 + a[18];
+    const double yc = a[3] * X0 + a[4] * X1 + a[5] * X2 + a[19];
+    const double zc = a[6] * X0 + a[7] * X1 + a[8] * X2 + a[20];
+    const int cam = img_cam[img];
+    double u, v;
+    world2image<false>(cam_model[cam], intr + MM_INTR_STRIDE * (size_t)cam, xc, yc, zc, u, v, nullptr, nullptr);
+    const double2 xy = obs_xy[o];
+    s += sqrt((u - xy.x) * (u - xy.x) + (v - xy.y) * (v - xy.y)) / (double)(o1 - o0);
+  }
+  pt_err[p] = s;
+}
+
+}  // namespace mm

@@ -1,0 +1,252 @@
+// geometry.cu — library globals, batched camera-model kernels (K7) and the fused two-view
+// triangulation kernel (K6).
+//
+// Replaces (mavmap/mavmap):
+//   camera_model_world2image / image2world      src/base3d/camera_models.h:375-423
+//   camera_model_image2world (vector overload)  src/base3d/camera_models.cc:24-44
+//   camera_model_name_to_code                   src/base3d/camera_models.cc:12-21
+//   camera_model_image2world_threshold          src/base3d/camera_models.cc:47-52
+//   triangulate_point(s)                        src/base3d/triangulation.cc:12-74
+//   calc_tri_angles                             src/base3d/triangulation.cc:101-147
+//   calc_reproj_errors / calc_depth             src/base3d/projection.cc:107-149
+// These are latency-bound (<= a few thousand items per call): one thread per item, grid sized
+// to the SM count, P matrices and intrinsics passed by value in the launch parameters.
+#include <stdarg.h>
+#include <mutex>
+#include "common.cuh"
+#include "camera.cuh"
+
+namespace mm {
+
+static thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+}
+
+int ensure_device() {
+  static std::once_flag once; static int status = MM_ERR_NO_DEVICE;
+  std::call_once(once, [] {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) { cudaGetLastError(); return; }
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { cudaGetLastError(); return; }
+    if (prop.major != 10) { set_error("device %s is sm_%d%d; this library carries sm_100a code only", prop.name, prop.major, prop.minor); return; }
+    status = MM_OK;
+  });
+  if (status != MM_OK && !g_err[0]) set_error("no usable CUDA device (sm_100a required; there is no CPU fallback)");
+  return status;
+}
+
+struct Params9 { double p[9]; };
+struct Proj { double P[12]; };
+
+__global__ void k_world2image(int model, Params9 prm, int64_t n, const double* __restrict__ xyz, double* __restrict__ uv) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double u, v;
+    world2image<false>(model, prm.p, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], u, v, nullptr, nullptr);
+    uv[2 * i] = u; uv[2 * i + 1] = v;
+  }
+}
+
+__global__ void k_image2world(int model, Params9 prm, int64_t n, const double* __restrict__ uv, double* __restrict__ out, int normalized) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double x, y, z;
+    image2world(model, prm.p, uv[2 * i], uv[2 * i + 1], x, y, z);
+    if (normalized) { out[2 * i] = x / z; out[2 * i + 1] = y / z; }       // camera_models.cc:41-42
+    else { out[3 * i] = x; out[3 * i + 1] = y; out[3 * i + 2] = z; }
+  }
+}
+
+// One-sided Jacobi SVD of the 6x4 DLT matrix, all in registers; the null vector is the column
+// of V that belongs to the smallest singular value (triangulation.cc:40-41).
+__device__ __forceinline__ void null_vector_6x4(double (&A)[6][4], double* h) {
+  double V[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) V[r][c] = r == c ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    double off = 0.0;
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+      for (int q = p + 1; q < 4; ++q) {
+        double app = 0, aqq = 0, apq = 0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) { app += A[r][p] * A[r][p]; aqq += A[r][q] * A[r][q]; apq += A[r][p] * A[r][q]; }
+        const double denom = sqrt(app * aqq);
+        if (apq != 0.0 && denom != 0.0 && fabs(apq) > 1e-300) {
+          off = fmax(off, fabs(apq) / denom);
+          const double zeta = (aqq - app) / (2.0 * apq);
+          const double tt = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double c = 1.0 / sqrt(1.0 + tt * tt), s = c * tt;
+#pragma unroll
+          for (int r = 0; r < 6; ++r) { const double x = A[r][p], y = A[r][q]; A[r][p] = c * x - s * y; A[r][q] = s * x + c * y; }
+#pragma unroll
+          for (int r = 0; r < 4; ++r) { const double x = V[r][p], y = V[r][q]; V[r][p] = c * x - s * y; V[r][q] = s * x + c * y; }
+        }
+      }
+    if (off < 1e-17) break;
+  }
+  double bn = INFINITY; int best = 0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    double nn = 0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) nn += A[r][c] * A[r][c];
+    if (nn < bn) { bn = nn; best = c; }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) h[r] = best == 0 ? V[r][0] : (best == 1 ? V[r][1] : (best == 2 ? V[r][2] : V[r][3]));
+}
+
+__device__ __forceinline__ double reproj_err(const double* P, const double* X, double x, double y) {
+  const double q0 = P[0] * X[0] + P[1] * X[1] + P[2] * X[2] + P[3];
+  const double q1 = P[4] * X[0] + P[5] * X[1] + P[6] * X[2] + P[7];
+  const double q2 = P[8] * X[0] + P[9] * X[1] + P[10] * X[2] + P[11];
+  const double dx = q0 / q2 - x, dy = q1 / q2 - y;
+  return sqrt(dx * dx + dy * dy);
+}
+
+__global__ void k_triangulate(Proj p1, Proj p2, double c1x, double c1y, double c1z, double c2x, double c2y, double c2z,
+                              double baseline2, int64_t n, const double* __restrict__ x1, const double* __restrict__ x2,
+                              double* __restrict__ X, double* __restrict__ rp1, double* __restrict__ rp2,
+                              double* __restrict__ dp1, double* __restrict__ dp2, double* __restrict__ ang) {
+  const double* P1 = p1.P; const double* P2 = p2.P;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double xa = x1[2 * i], ya = x1[2 * i + 1], xb = x2[2 * i], yb = x2[2 * i + 1];
+    double A[6][4], h[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {                       // triangulation.cc:26-35
+      A[0][k] = xa * P1[8 + k] - P1[k];
+      A[1][k] = ya * P1[8 + k] - P1[4 + k];
+      A[2][k] = xa * P1[4 + k] - ya * P1[k];
+      A[3][k] = xb * P2[8 + k] - P2[k];
+      A[4][k] = yb * P2[8 + k] - P2[4 + k];
+      A[5][k] = xb * P2[4 + k] - yb * P2[k];
+    }
+    null_vector_6x4(A, h);
+    double Xi[3] = { h[0] / h[3], h[1] / h[3], h[2] / h[3] };
+    X[3 * i] = Xi[0]; X[3 * i + 1] = Xi[1]; X[3 * i + 2] = Xi[2];
+    if (rp1) rp1[i] = reproj_err(P1, Xi, xa, ya);
+    if (rp2) rp2[i] = reproj_err(P2, Xi, xb, yb);
+    if (dp1) dp1[i] = (P1[8] * Xi[0] + P1[9] * Xi[1] + P1[10] * Xi[2] + P1[11]) * sqrt(P1[2] * P1[2] + P1[6] * P1[6] + P1[10] * P1[10]);
+    if (dp2) dp2[i] = (P2[8] * Xi[0] + P2[9] * Xi[1] + P2[10] * Xi[2] + P2[11]) * sqrt(P2[2] * P2[2] + P2[6] * P2[6] + P2[10] * P2[10]);
+    if (ang) {
+      const double r1 = sqrt((Xi[0] - c1x) * (Xi[0] - c1x) + (Xi[1] - c1y) * (Xi[1] - c1y) + (Xi[2] - c1z) * (Xi[2] - c1z));
+      const double r2 = sqrt((Xi[0] - c2x) * (Xi[0] - c2x) + (Xi[1] - c2y) * (Xi[1] - c2y) + (Xi[2] - c2z) * (Xi[2] - c2z));
+      const double a = acos((r1 * r1 + r2 * r2 - baseline2) / (2.0 * r1 * r2));
+      ang[i] = isnan(a) ? 0.0 : a;                       // triangulation.cc:134-140
+    }
+  }
+}
+
+static void camera_center(const double* P, double* C) {       // projection.cc:82-88 translation column
+  const double a = P[0], b = P[1], c = P[2], d = P[4], e = P[5], f = P[6], g = P[8], h = P[9], i = P[10];
+  const double A = e * i - f * h, B = -(d * i - f * g), Cc = d * h - e * g;
+  const double det = a * A + b * B + c * Cc;
+  const double inv[9] = { A / det, (c * h - b * i) / det, (b * f - c * e) / det,
+                          B / det, (a * i - c * g) / det, (c * d - a * f) / det,
+                          Cc / det, (b * g - a * h) / det, (a * e - b * d) / det };
+  const double t[3] = { P[3], P[7], P[11] };
+  for (int r = 0; r < 3; ++r) C[r] = -(inv[3 * r] * t[0] + inv[3 * r + 1] * t[1] + inv[3 * r + 2] * t[2]);
+}
+
+static int grid_for(int64_t n, int block) {
+  int64_t g = (n + block - 1) / block;
+  const int cap = num_sms() * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+static int camera_batch(int which, int model, const double* params, int64_t n, const double* in, double* out) {
+  if (n < 0 || !params || model_num_params(model) < 0 || (n > 0 && (!in || !out))) { set_error("invalid argument"); return MM_ERR_INVALID_ARG; }
+  int rc = ensure_device(); if (rc != MM_OK) return rc;
+  if (n == 0) return MM_OK;
+  const int in_w = which == 0 ? 3 : 2, out_w = which == 0 ? 2 : (which == 1 ? 3 : 2);
+  DevBuf<double> din, dout;
+  MM_CUDA(din.alloc((size_t)n * in_w)); MM_CUDA(dout.alloc((size_t)n * out_w));
+  MM_CUDA(cudaMemcpy(din.p, in, sizeof(double) * (size_t)n * in_w, cudaMemcpyHostToDevice));
+  Params9 prm; memset(&prm, 0, sizeof prm);
+  memcpy(prm.p, params, sizeof(double) * (size_t)model_num_params(model));
+  const int block = 128, grid = grid_for(n, block);
+  if (which == 0) k_world2image<<<grid, block>>>(model, prm, n, din.p, dout.p);
+  else k_image2world<<<grid, block>>>(model, prm, n, din.p, dout.p, which == 2);
+  MM_LAUNCH_CHECK();
+  MM_CUDA(cudaMemcpy(out, dout.p, sizeof(double) * (size_t)n * out_w, cudaMemcpyDeviceToHost));
+  return MM_OK;
+}
+
+}  // namespace mm
+
+using namespace mm;
+
+extern "C" {
+
+int mm_abi_version(void) { return MM_ABI_VERSION; }
+const char* mm_last_error(void) { return g_err; }
+uint64_t mm_kernel_launch_count(void) { return g_launches.load(); }
+
+int mm_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int mm_camera_model_name_to_code(const char* name) {
+  if (!name) return -1;
+  if (!strcmp(name, "PINHOLE")) return MM_MODEL_PINHOLE;
+  if (!strcmp(name, "OPENCV")) return MM_MODEL_OPENCV;
+  if (!strcmp(name, "CATA")) return MM_MODEL_CATA;
+  return -1;
+}
+
+int mm_camera_model_num_params(int model_code) { return model_num_params(model_code); }
+
+double mm_camera_image2world_threshold(double threshold, int model_code, const double* params) {
+  (void)model_code;
+  return threshold / ((params[0] + params[1]) / 2);
+}
+
+int mm_camera_world2image(int model, const double* params, int64_t n, const double* xyz, double* uv) {
+  return camera_batch(0, model, params, n, xyz, uv);
+}
+int mm_camera_image2world(int model, const double* params, int64_t n, const double* uv, double* xyz) {
+  return camera_batch(1, model, params, n, uv, xyz);
+}
+int mm_camera_image2world_normalized(int model, const double* params, int64_t n, const double* uv, double* xy) {
+  return camera_batch(2, model, params, n, uv, xy);
+}
+
+int mm_triangulate_two_view(const double* P1, const double* P2, int64_t n, const double* x1, const double* x2,
+                            double* X, double* reproj1, double* reproj2, double* depth1, double* depth2, double* angle) {
+  if (n < 0 || !P1 || !P2 || (n > 0 && (!x1 || !x2 || !X))) { set_error("invalid argument"); return MM_ERR_INVALID_ARG; }
+  int rc = ensure_device(); if (rc != MM_OK) return rc;
+  if (n == 0) return MM_OK;
+  Proj p1, p2; memcpy(p1.P, P1, sizeof p1.P); memcpy(p2.P, P2, sizeof p2.P);
+  double C1[3], C2[3]; camera_center(P1, C1); camera_center(P2, C2);
+  const double bl = sqrt((C1[0] - C2[0]) * (C1[0] - C2[0]) + (C1[1] - C2[1]) * (C1[1] - C2[1]) + (C1[2] - C2[2]) * (C1[2] - C2[2]));
+  // one staging buffer: [x1 | x2 | X | 5 optional outputs]
+  DevBuf<double> buf;
+  MM_CUDA(buf.alloc((size_t)n * (2 + 2 + 3 + 5)));
+  double* dx1 = buf.p; double* dx2 = dx1 + 2 * n; double* dX = dx2 + 2 * n; double* dout = dX + 3 * n;
+  MM_CUDA(cudaMemcpy(dx1, x1, sizeof(double) * 2 * (size_t)n, cudaMemcpyHostToDevice));
+  MM_CUDA(cudaMemcpy(dx2, x2, sizeof(double) * 2 * (size_t)n, cudaMemcpyHostToDevice));
+  double* host_out[5] = { reproj1, reproj2, depth1, depth2, angle };
+  double* dev_out[5];
+  for (int k = 0; k < 5; ++k) dev_out[k] = host_out[k] ? dout + (size_t)k * n : nullptr;
+  const int block = 128, grid = grid_for(n, block);
+  k_triangulate<<<grid, block>>>(p1, p2, C1[0], C1[1], C1[2], C2[0], C2[1], C2[2], bl * bl, n, dx1, dx2, dX,
+                                 dev_out[0], dev_out[1], dev_out[2], dev_out[3], dev_out[4]);
+  MM_LAUNCH_CHECK();
+  MM_CUDA(cudaMemcpy(X, dX, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 5; ++k) if (host_out[k]) MM_CUDA(cudaMemcpy(host_out[k], dev_out[k], sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+  return MM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+"""GPU parity tests (through the C ABI): bundle adjustment / pose refinement against the oracle.
+
+Tolerance (north_star): cost and every pose/point parameter within 1e-6 relative after the
+same iteration count, denominators max(|x|, 1)."""
+import numpy as np
+import pytest
+
+from mavmap_b200 import synthetic
+from mavmap_b200.ba import default_c_options, solve_flat
+
+pytestmark = pytest.mark.gpu
+REL = 1e-6
+
+
+def _both(orc, flat, iters, **kw):
+    og = default_c_options(); og.max_num_iterations = iters; og.function_tolerance = 0; og.gradient_tolerance = 0
+    oo = orc.default_options(); oo.max_num_iterations = iters; oo.function_tolerance = 0; oo.gradient_tolerance = 0
+    for k, v in kw.items():
+        setattr(og, k, v); setattr(oo, k, v)
+    g, c = flat.copy(), flat.copy()
+    sg = solve_flat(g, og).as_dict(); so = orc.solve_flat(c, oo).as_dict()
+    return g, c, sg, so
+
+
+def _assert_parity(g, c, sg, so):
+    assert sg["trace_accepted"] == so["trace_accepted"]
+    np.testing.assert_allclose(sg["trace_cost"], so["trace_cost"], rtol=REL)
+    np.testing.assert_allclose(sg["trace_radius"], so["trace_radius"], rtol=1e-5)
+    assert abs(sg["return_value"] - so["return_value"]) <= REL * so["return_value"]
+    for a, b in ((g.poses, c.poses), (g.pts, c.pts), (g.intr, c.intr)):
+        assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1.0)) < REL
+
+
+@pytest.mark.parametrize("model", [1, 2, 3])
+def test_small_problem_parity_per_camera_model(mm, orc, model):
+    flat, _ = synthetic.make_ba_problem(model=model, **synthetic.BA_CONFIGS["tiny"])
+    _assert_parity(*_both(orc, flat, 10))
+
+
+def test_cfg1_parity(mm, orc):
+    # BASELINE.json configs[0]: 20-image PINHOLE sequence
+    flat, _ = synthetic.make_ba_problem(**synthetic.BA_CONFIGS["cfg1"])
+    g, c, sg, so = _both(orc, flat, 15)
+    _assert_parity(g, c, sg, so)
+    assert sg["final_cost"] < 0.2 * sg["initial_cost"]
+
+
+def test_medium_problem_parity_and_rejected_steps(mm, orc):
+    flat, _ = synthetic.make_ba_problem(**synthetic.BA_CONFIGS["small"])
+    # a tiny initial radius forces the first steps to be heavily damped; a huge one provokes rejections
+    for radius in (1e4, 1e12):
+        g, c, sg, so = _both(orc, flat, 12, initial_trust_region_radius=radius)
+        _assert_parity(g, c, sg, so)
+
+
+def test_trivial_loss_and_termination_parity(mm, orc):
+    flat, _ = synthetic.make_ba_problem(outlier_frac=0.0, **synthetic.BA_CONFIGS["tiny"])
+    g, c, sg, so = _both(orc, flat, 50, loss_type=0, function_tolerance=1e-6, gradient_tolerance=1e-10)
+    assert sg["termination"] == so["termination"] and sg["num_iterations"] == so["num_iterations"]
+    _assert_parity(g, c, sg, so)
+
+
+def test_point_errors_and_constant_points(mm, orc):
+    flat, _ = synthetic.make_ba_problem(**synthetic.BA_CONFIGS["tiny"])
+    flat.pt_const[::5] = 1                       # GCP-style constant points (bundle_adjustment.cc:545-549)
+    flat.pt_err = np.zeros(flat.n_pt)
+    g, c, sg, so = _both(orc, flat, 8)
+    _assert_parity(g, c, sg, so)
+    assert np.array_equal(g.pts[::5], flat.pts[::5])
+    np.testing.assert_allclose(g.pt_err, c.pt_err, rtol=1e-6, atol=1e-9)
+
+
+def test_empty_and_invalid_problems(mm):
+    flat, _ = synthetic.make_ba_problem(**synthetic.BA_CONFIGS["tiny"])
+    empty = type(flat)(flat.poses, flat.pose_const, flat.img_cam, flat.intr, flat.cam_model, flat.intr_const, flat.pts, flat.pt_const,
+                       np.zeros((0, 2)), np.zeros(0, np.int32), np.zeros(0, np.int32))
+    s = solve_flat(empty, default_c_options()).as_dict()
+    assert s["termination"] == "EMPTY" and np.isnan(s["return_value"])     # bundle_adjustment.cc:571-573 -> 0/0
+    bad = flat.copy(); bad.obs_img = bad.obs_img.copy(); bad.obs_img[0] = 10 ** 6
+    with pytest.raises(ValueError):
+        solve_flat(bad, default_c_options())
+
+
+def test_call_surface_bundle_adjustment_and_pose_refinement(mm, orc):
+    from test_oracle_ba import _scene
+    fm_g, ids = _scene(seed=3); fm_o, _ = _scene(seed=3)
+    opt = mm.BundleAdjustmentOptions(update_point3D_errors=True, print_summary=False, max_num_iterations=10,
+                                     function_tolerance=0, gradient_tolerance=0)
+    eg, eo = {}, {}
+    rg = mm.bundle_adjustment(fm_g, ids[2:], ids[:1], ids[1:2], opt, eg)
+    ro = orc.bundle_adjustment(fm_o, ids[2:], ids[:1], ids[1:2], opt, eo)
+    assert abs(rg - ro) <= REL * ro
+    for i in ids:
+        np.testing.assert_allclose(fm_g.rvecs[i], fm_o.rvecs[i], atol=REL); np.testing.assert_allclose(fm_g.tvecs[i], fm_o.tvecs[i], atol=REL)
+    for p in eo:
+        assert abs(eg[p] - eo[p]) < 1e-6
+    with pytest.raises(ValueError, match="At least 7 parameters"):
+        mm.bundle_adjustment(fm_g, ids[1:], ids[:1], [], opt, eg)
+    # pose_refinement
+    rng = np.random.default_rng(2)
+    X = rng.uniform([-2, -2, 6], [2, 2, 10], (200, 3))
+    from mavmap_b200.synthetic import _rodrigues, project
+    rvec, tvec = np.array([0.05, -0.1, 0.02]), np.array([0.3, -0.2, 0.5])
+    params = synthetic.INTRINSICS[2] + [2]
+    uv = project(2, np.array(params[:8]), X @ _rodrigues(rvec)[0].T + tvec) + rng.normal(0, 0.3, (200, 2))
+    mask = np.ones(200, bool); mask[::9] = False
+    o2 = mm.BundleAdjustmentOptions(print_summary=False, max_num_iterations=10, function_tolerance=0, gradient_tolerance=0)
+    rg_, tg_ = rvec + 0.02, tvec - 0.05; ro_, to_ = rg_.copy(), tg_.copy()
+    a = mm.pose_refinement(rg_, tg_, params, uv, X, mask, o2); b = orc.pose_refinement(ro_, to_, params, uv, X, mask, o2)
+    assert abs(a - b) <= REL * b
+    np.testing.assert_allclose(rg_, ro_, atol=REL); np.testing.assert_allclose(tg_, to_, atol=REL)
+
+
+def test_cfg2_scale_properties(mm):
+    """BASELINE.json configs[1] at full size: monotone cost, PCG converges, repeatable."""
+    flat, truth = synthetic.make_ba_problem(**synthetic.BA_CONFIGS["cfg2"])
+    assert flat.n_img == 500 and 0.9e6 < flat.n_obs < 1.1e6
+    o = default_c_options(); o.max_num_iterations = 6; o.function_tolerance = 0; o.gradient_tolerance = 0
+    a, b = flat.copy(), flat.copy()
+    sa = solve_flat(a, o).as_dict(); sb = solve_flat(b, o).as_dict()
+    costs = [c for c, ok in zip(sa["trace_cost"], sa["trace_accepted"]) if ok]
+    assert all(y <= x for x, y in zip(costs, costs[1:])) and costs[-1] < 0.05 * costs[0]
+    assert max(sa["trace_linear_iterations"]) < o.pcg_max_iterations
+    np.testing.assert_allclose(sa["trace_cost"], sb["trace_cost"], rtol=1e-9)     # atomics reorder sums, nothing more
+    assert np.abs(a.poses - truth["poses"]).max() < 0.05

@@ -1,0 +1,128 @@
+"""CPU tests: the BA oracle (Ceres-1.8-semantics LM + Schur) and the host-side flattening of
+the FeatureManager (bundle_adjustment.cc:228-387, 459-471)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import mavmap_b200 as mm
+from conftest import GOLDEN
+from mavmap_b200 import synthetic
+from mavmap_b200.ba import flatten
+
+
+def _opts(orc, iters=8):
+    o = orc.default_options(); o.max_num_iterations = iters; o.function_tolerance = 0; o.gradient_tolerance = 0
+    return o
+
+
+def test_oracle_reproduces_committed_traces(orc):
+    with open(os.path.join(GOLDEN, "ba_trace.json")) as f:
+        gold = json.load(f)
+    for name, kw, model, refine in [("tiny_pinhole", synthetic.BA_CONFIGS["tiny"], 1, False),
+                                    ("tiny_opencv", dict(synthetic.BA_CONFIGS["tiny"], seed=77), 2, False),
+                                    ("tiny_cata_refine", dict(synthetic.BA_CONFIGS["tiny"], seed=78), 3, True)]:
+        flat, _ = synthetic.make_ba_problem(model=model, refine_camera_params=refine, **kw)
+        s = orc.solve_flat(flat, _opts(orc)).as_dict()
+        np.testing.assert_allclose(s["trace_cost"], gold[name]["trace_cost"], rtol=1e-9)
+        np.testing.assert_allclose(s["trace_radius"], gold[name]["trace_radius"], rtol=1e-7)
+        assert s["trace_accepted"] == gold[name]["trace_accepted"]
+        np.testing.assert_allclose(np.abs(flat.poses).sum(), gold[name]["poses_sum"], rtol=1e-9)
+
+
+def test_lm_decreases_cost_and_recovers_truth(orc):
+    flat, truth = synthetic.make_ba_problem(n_img=10, n_obs_target=3000, track_len=4, seed=5, outlier_frac=0.0, noise_px=0.0)
+    c0 = orc.ba_cost(flat, _opts(orc))
+    s = orc.solve_flat(flat, _opts(orc, 30)).as_dict()
+    costs = [c for c, a in zip(s["trace_cost"], s["trace_accepted"]) if a]
+    assert all(b <= a for a, b in zip(costs, costs[1:]))
+    assert abs(s["initial_cost"] - c0) < 1e-9 * c0
+    assert s["final_cost"] < 1e-12 * c0          # noise-free: exact minimum is zero
+    # gauge fixed by image 0 (FIXED) and tx of image 1 (FIXED_X): truth is recovered
+    np.testing.assert_allclose(flat.poses, truth["poses"], atol=1e-6)
+    np.testing.assert_allclose(flat.pts, truth["pts"], atol=1e-5)
+
+
+def test_termination_rules(orc):
+    flat, _ = synthetic.make_ba_problem(**synthetic.BA_CONFIGS["tiny"])
+    o = orc.default_options()       # function_tolerance 1e-4 as BundleAdjustmentOptions default
+    s = orc.solve_flat(flat.copy(), o).as_dict()
+    assert s["termination"] == "FUNCTION_TOLERANCE"
+    assert s["return_value"] == pytest.approx(np.sqrt(s["final_cost"] / s["num_residuals"]))
+    o.max_num_iterations = 2
+    s2 = orc.solve_flat(flat.copy(), o).as_dict()
+    assert s2["termination"] == "NO_CONVERGENCE" and s2["num_successful_steps"] + s2["num_unsuccessful_steps"] == 2
+
+
+def _scene(n_img=4, n_pt=60, seed=0):
+    rng = np.random.default_rng(seed)
+    fm = mm.FeatureManager()
+    cam = fm.add_camera([1000.0, 1000.0, 640.0, 480.0, 1])
+    X = rng.uniform([-2, -2, 8], [2, 2, 12], (n_pt, 3))
+    ids = []
+    for i in range(n_img):
+        rvec = rng.normal(0, 0.02, 3); tvec = np.array([0.5 * i, 0.0, 0.0]) + rng.normal(0, 0.01, 3)
+        from mavmap_b200.synthetic import _rodrigues
+        Xc = X @ _rodrigues(rvec)[0].T + tvec
+        uv = np.stack([1000 * Xc[:, 0] / Xc[:, 2] + 640, 1000 * Xc[:, 1] / Xc[:, 2] + 480], axis=1)
+        iid = fm.add_image(cam, uv + rng.normal(0, 0.3, uv.shape))
+        fm.set_pose(iid, rvec + rng.normal(0, 0.005, 3), tvec + rng.normal(0, 0.02, 3))
+        ids.append(iid)
+    for p in range(n_pt):
+        # the last 10 points are seen by only one image (filtered by min_track_len)
+        obs = [(i, p) for i in ids] if p < n_pt - 10 else [(ids[0], p)]
+        fm.add_track(X[p] + rng.normal(0, 0.05, 3), obs)
+    return fm, ids
+
+
+def test_flatten_follows_reference_rules():
+    fm, ids = _scene()
+    opt = mm.BundleAdjustmentOptions(min_track_len=2, print_summary=False)
+    flat, image_ids, camera_ids, point_ids = flatten(fm, ids[2:], ids[:1], ids[1:2], opt)
+    # residual-block order: free, fixed, fixed_x (bundle_adjustment.cc:511-533)
+    assert image_ids == [ids[2], ids[3], ids[0], ids[1]]
+    assert flat.n_obs == 4 * 50 and flat.n_pt == 50            # single-view points dropped (count < min_track_len)
+    assert np.all(np.diff(flat.obs_img) >= 0)
+    assert flat.pose_const.tolist() == [[0, 0, 0, 0], [0, 0, 0, 0], [1, 1, 1, 1], [0, 1, 0, 0]]
+    assert flat.intr_const.tolist() == [1]
+    opt.refine_camera_params = True
+    assert flatten(fm, ids[2:], ids[:1], ids[1:2], opt)[0].intr_const.tolist() == [0]
+    with pytest.raises(ValueError, match="At least 7 parameters"):
+        flatten(fm, ids[1:], ids[:1], [], opt)                  # 6 fixed dof < 7
+    opt.min_track_len = 1
+    with pytest.raises(ValueError, match="Minimum track length"):
+        flatten(fm, ids[2:], ids[:1], ids[1:2], opt)
+    # GCP ids count 3 dof each and become constant points (bundle_adjustment.cc:459-461, 545-549)
+    opt.min_track_len = 2
+    gcp = {fm.point2D_to_point3D[fm.image_to_points2D[ids[0]][0]], fm.point2D_to_point3D[fm.image_to_points2D[ids[0]][1]],
+           fm.point2D_to_point3D[fm.image_to_points2D[ids[0]][2]]}
+    flat = flatten(fm, ids, [], [], opt, gcp_ids=gcp)[0]
+    assert int(flat.pt_const.sum()) == 3 and not flat.pose_const.any()
+
+
+def test_bundle_adjustment_call_surface_with_oracle_engine(orc):
+    fm, ids = _scene(seed=3)
+    errs = {}
+    opt = mm.BundleAdjustmentOptions(update_point3D_errors=True, print_summary=False, max_num_iterations=20)
+    before = {i: fm.rvecs[i].copy() for i in ids}
+    ret = orc.bundle_adjustment(fm, ids[2:], ids[:1], ids[1:2], opt, errs)
+    assert 0 < ret < 1.0                                         # ~0.3 px noise
+    assert np.array_equal(fm.rvecs[ids[0]], before[ids[0]])      # FIXED pose untouched
+    assert not np.array_equal(fm.rvecs[ids[2]], before[ids[2]])
+    assert len(errs) == 50 and all(e >= 0 for e in errs.values())
+
+
+def test_pose_refinement_oracle(orc):
+    rng = np.random.default_rng(2)
+    X = rng.uniform([-2, -2, 6], [2, 2, 10], (80, 3))
+    from mavmap_b200.synthetic import _rodrigues, project
+    rvec, tvec = np.array([0.05, -0.1, 0.02]), np.array([0.3, -0.2, 0.5])
+    params = synthetic.INTRINSICS[2] + [2]
+    uv = project(2, np.array(params[:8]), X @ _rodrigues(rvec)[0].T + tvec)
+    mask = np.ones(80, bool); mask[::7] = False
+    uv[~mask] += 50.0                                            # outliers excluded by the mask
+    r0, t0 = rvec + 0.02, tvec - 0.05
+    ret = orc.pose_refinement(r0, t0, params, uv, X, mask, mm.BundleAdjustmentOptions(print_summary=False, function_tolerance=1e-12))
+    np.testing.assert_allclose(r0, rvec, atol=1e-6); np.testing.assert_allclose(t0, tvec, atol=1e-6)
+    assert ret < 1e-6

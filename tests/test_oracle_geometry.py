@@ -1,0 +1,144 @@
+"""CPU tests: the oracle restatement of the camera models and triangulation against the
+reference's own test vectors (camera_models_test.cc, triangulation_test.cc) and against the
+reference code itself (tests/golden/camera_ref.npz, made from oracle/_ref)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from mavmap_b200 import synthetic
+
+CAMERA_SETS = [   # src/base3d/camera_models_test.cc:59-82
+    (1, [651.123, 655.123, 386.123, 511.123]),
+    (3, [651.123, 655.123, 386.123, 511.123, -0.471, 0.223, -0.001, 0.001, 0]),
+    (3, [651.123, 655.123, 386.123, 511.123, -0.471, 0.223, -0.001, 0.001, 1]),
+    (3, [651.123, 655.123, 386.123, 511.123, -0.471, 0.223, -0.001, 0.001, 0.5]),
+    (2, [651.123, 655.123, 386.123, 511.123, -0.471, 0.223, -0.001, 0.001]),
+]
+
+
+@pytest.mark.parametrize("code,params", CAMERA_SETS)
+def test_camera_round_trips_like_reference_test(orc, code, params):
+    # test_model<CameraModel>() of camera_models_test.cc:16-55, same tolerances
+    uv = orc.camera_world2image(code, params, [[0.5, 0.23, 1.0]])
+    xyz = orc.camera_image2world(code, params, uv)[0]
+    assert abs(xyz[0] / xyz[2] - 0.5) < 1e-5 and abs(xyz[1] / xyz[2] - 0.23) < 1e-5
+    xyz = orc.camera_image2world(code, params, [[200.0, 100.0]])
+    uv = orc.camera_world2image(code, params, xyz)[0]
+    assert abs(uv[0] - 200) < 1e-1 and abs(uv[1] - 100) < 1e-1
+    uv = orc.camera_world2image(code, params, [[0.0, 0.0, 1.0]])[0]
+    assert abs(uv[0] - params[2]) < 1e-6 and abs(uv[1] - params[3]) < 1e-6
+    xyz = orc.camera_image2world(code, params, [[params[2], params[3]]])[0]
+    assert abs(xyz[0] / xyz[2]) < 1e-4 and abs(xyz[1] / xyz[2]) < 1e-4
+
+
+def test_camera_oracle_equals_reference_code(orc):
+    g = np.load(os.path.join(GOLDEN, "camera_ref.npz"))
+    for k in range(int(g["n"])):
+        code = int(g["code%d" % k]); prm = g["params%d" % k]
+        np.testing.assert_array_equal(orc.camera_world2image(code, prm, g["xyz%d" % k]), g["uv%d" % k])
+        np.testing.assert_array_equal(orc.camera_image2world(code, prm, g["uv_in%d" % k]), g["xyz_out%d" % k])
+        np.testing.assert_array_equal(orc.camera_image2world_normalized(code, prm, g["uv_in%d" % k]), g["xy_norm%d" % k])
+
+
+def test_camera_oracle_equals_live_reference_build(orc):
+    import ctypes as C
+    path = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref", "libref_camera.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref not built here")
+    ref = C.CDLL(path)
+    p = C.POINTER(C.c_double)
+    rng = np.random.default_rng(3)
+    for code, params in CAMERA_SETS:
+        prm = np.zeros(9); prm[:len(params)] = params
+        xyz = rng.uniform([-0.5, -0.5, 0.9], [0.5, 0.5, 2.0], (200, 3)); uv = np.empty((200, 2))
+        ref.ref_world2image(code, prm.ctypes.data_as(p), C.c_long(200), xyz.ctypes.data_as(p), uv.ctypes.data_as(p))
+        np.testing.assert_array_equal(orc.camera_world2image(code, prm, xyz), uv)
+
+
+@pytest.mark.parametrize("model", [1, 2, 3])
+def test_ba_residual_jets_match_finite_differences(orc, model):
+    rng = np.random.default_rng(model)
+    intr = np.zeros(9); intr[:len(synthetic.INTRINSICS[model])] = synthetic.INTRINSICS[model]
+    for trial in range(5):
+        pose = np.concatenate([rng.normal(0, 0.5, 3), rng.normal(0, 0.3, 3) + [0, 0, 2.0]])
+        if trial == 4:
+            pose[:3] = 0.0          # theta == 0: first-order branch of AngleAxisRotatePoint
+        X = rng.uniform([-1, -1, 4], [1, 1, 8]); obs = rng.uniform(300, 700, 2)
+        r, J = orc.ba_residual_jet(model, pose, X, intr, obs)
+        x0 = np.concatenate([pose, X, intr])
+        Jn = np.zeros((2, 18))
+        for k in range(18):
+            h = 1e-6 * max(1.0, abs(x0[k]))
+            xp, xm = x0.copy(), x0.copy(); xp[k] += h; xm[k] -= h
+            rp, _ = orc.ba_residual_jet(model, xp[:6], xp[6:9], xp[9:], obs)
+            rm, _ = orc.ba_residual_jet(model, xm[:6], xm[6:9], xm[9:], obs)
+            Jn[:, k] = (rp - rm) / (2 * h)
+        Jn[:, 9 + len(synthetic.INTRINSICS[model]):] = 0
+        if trial == 4:
+            # at theta == 0 the Jet derivative is that of pt + w x pt; FD crosses into the Rodrigues branch (same to O(h))
+            np.testing.assert_allclose(J[:, :3], Jn[:, :3], rtol=0, atol=1e-4 * np.abs(J).max())
+            J[:, :3] = Jn[:, :3] = 0
+        np.testing.assert_allclose(J, Jn, rtol=0, atol=2e-7 * np.abs(J).max())
+
+
+def _rodrigues(rvec):
+    th = np.linalg.norm(rvec)
+    if th < np.finfo(float).eps:
+        return np.eye(3)
+    k = rvec / th
+    K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * K @ K
+
+
+def reference_triangulation_vectors():
+    """The cases of test_triangulate_point (src/base3d/triangulation_test.cc:16-60)."""
+    pts = np.array([[0, 0.1, 0.1], [0, 1, 3], [0, 1, 2], [0.01, 0.2, 3], [-1, 0.1, 1], [0.1, 0.1, 0.2]], dtype=float)
+    P1 = np.hstack([np.eye(3), np.zeros((3, 1))])
+    cases = []
+    rx = 0.0
+    while rx < 1:
+        tx = 0.0
+        while tx < 10:
+            # SimilarityTransform3D(1, rx, 0.2, 0.3, tx, 2, 3) (similarity_transform.cc:61-75) = [R(rvec) | t]
+            P2 = np.hstack([_rodrigues(np.array([rx, 0.2, 0.3])), np.array([[tx], [2.0], [3.0]])])
+            cases.append((P1, P2, pts))
+            tx += 2
+        rx += 0.2
+    return cases
+
+
+def test_triangulation_reference_vectors(orc):
+    cases = reference_triangulation_vectors()
+    assert len(cases) == 25
+    for P1, P2, pts in cases:
+        h = np.hstack([pts, np.ones((len(pts), 1))])
+        a = (P1 @ h.T).T; b = (P2 @ h.T).T
+        x1 = a[:, :2] / a[:, 2:]; x2 = b[:, :2] / b[:, 2:]
+        out = orc.triangulate_two_view(P1, P2, x1, x2)
+        assert np.linalg.norm(out["X"] - pts, axis=1).max() < 1e-10       # ASSERT_ALMOST_EQUAL(..., 1e-10)
+
+
+def test_triangulation_matches_numpy_svd_and_filters(orc):
+    rng = np.random.default_rng(5)
+    P1 = np.hstack([_rodrigues(rng.normal(0, 0.1, 3)), rng.normal(0, 0.2, (3, 1))])
+    P2 = np.hstack([_rodrigues(rng.normal(0, 0.2, 3)), np.array([[1.0], [0.1], [-0.1]])])
+    X = rng.uniform([-2, -2, 4], [2, 2, 9], (300, 3))
+    h = np.hstack([X, np.ones((300, 1))])
+    a = (P1 @ h.T).T; b = (P2 @ h.T).T
+    x1 = a[:, :2] / a[:, 2:] + rng.normal(0, 1e-3, (300, 2)); x2 = b[:, :2] / b[:, 2:] + rng.normal(0, 1e-3, (300, 2))
+    out = orc.triangulate_two_view(P1, P2, x1, x2)
+    for i in range(300):
+        A = np.array([x1[i, 0] * P1[2] - P1[0], x1[i, 1] * P1[2] - P1[1], x1[i, 0] * P1[1] - x1[i, 1] * P1[0],
+                      x2[i, 0] * P2[2] - P2[0], x2[i, 1] * P2[2] - P2[1], x2[i, 0] * P2[1] - x2[i, 1] * P2[0]])
+        v = np.linalg.svd(A)[2][3]
+        np.testing.assert_allclose(out["X"][i], v[:3] / v[3], rtol=1e-9, atol=1e-9)
+    Xh = np.hstack([out["X"], np.ones((300, 1))])
+    q = (P2 @ Xh.T).T
+    np.testing.assert_allclose(out["reproj2"], np.linalg.norm(q[:, :2] / q[:, 2:] - x2, axis=1), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(out["depth2"], q[:, 2] * np.linalg.norm(P2[:, 2]), rtol=1e-12)
+    C1 = -np.linalg.inv(P1[:, :3]) @ P1[:, 3]; C2 = -np.linalg.inv(P2[:, :3]) @ P2[:, 3]
+    r1 = np.linalg.norm(out["X"] - C1, axis=1); r2 = np.linalg.norm(out["X"] - C2, axis=1)
+    ang = np.arccos((r1 ** 2 + r2 ** 2 - np.linalg.norm(C1 - C2) ** 2) / (2 * r1 * r2))
+    np.testing.assert_allclose(out["angle"], ang, rtol=1e-9)
