@@ -336,3 +336,56 @@ def pose_refinement(rvec, tvec, camera_params, points2D, points3D, inlier_mask, 
         print("%18s%.6g [px]" % ("Final cost : ", math.sqrt(summary.final_cost / nr)))
         print()
     return ret.value
+
+
+class BASession:
+    """Resident BA session (inputs stay in HBM between calls) — what bench.py times."""
+
+    def __init__(self, flat, c_options, stream=0):
+        from ._lib import check, lib
+        self._lib, self._check = lib(), check
+        self.flat = flat
+        self._cp = flat.to_c()
+        self._h = C.c_void_p()
+        self._opt = c_options
+        check(self._lib.mm_ba_session_create(C.byref(self._cp), C.byref(c_options), C.c_void_p(stream), C.byref(self._h)))
+
+    def reset(self):
+        self._check(self._lib.mm_ba_session_reset(self._h))
+
+    def iterate(self, n=1):
+        done = C.c_int32(0)
+        self._check(self._lib.mm_ba_session_iterate(self._h, int(n), C.byref(done)))
+        return done.value
+
+    def summary(self):
+        s = BASummary()
+        self._check(self._lib.mm_ba_session_summary(self._h, C.byref(s)))
+        return s
+
+    def download(self, want_pt_err=False):
+        f = self.flat
+        if want_pt_err and f.pt_err is None:
+            f.pt_err = np.zeros(f.n_pt)
+        self._check(self._lib.mm_ba_session_download(self._h, as_ptr(f.poses, p_f64), as_ptr(f.intr, p_f64), as_ptr(f.pts, p_f64),
+                                                     as_ptr(f.pt_err, p_f64) if want_pt_err else None))
+        return f
+
+    def time_kernel(self, which, reps=10):
+        ms = C.c_double(0.0)
+        self._check(self._lib.mm_ba_session_time_kernel(self._h, int(which), int(reps), C.byref(ms)))
+        return ms.value
+
+    def num_blocks(self):
+        return int(self._lib.mm_ba_session_num_blocks(self._h))
+
+    def close(self):
+        if self._h:
+            self._lib.mm_ba_session_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -56,7 +56,7 @@ def test_full_size_pair_properties(mm, orc):
     # the cross-checked relation is symmetric: swapping the images transposes the match set
     assert sorted(zip(q.tolist(), t.tolist())) == sorted(zip(t2.tolist(), q2.tolist()))
     assert np.all(np.diff(q) > 0) and len(set(t.tolist())) == len(t)
-    assert 2000 < len(q) <= 3000                                     # 60 % shared descriptors
+    assert 2500 < len(q) <= 3100                                     # 60 % shared descriptors (+ a few chance matches)
     qo, to, do = orc.match_pair(desc[0], desc[1], ratio_test=True, max_ratio=0.9)
     assert np.array_equal(q, qo) and np.array_equal(t, to) and np.array_equal(d, do)
 
