@@ -272,7 +272,7 @@ def main():
         m_e2e = max_over_ranks((time.perf_counter() - t0) / max(2, min(6, np_)))
         secondary = {"metric": "image_pairs_matched_per_sec", "value": pairs_s, "unit": "pairs/s", "ms_per_pair": mms / max(np_, 1),
                      "config": {"workload": "5000 x 5000 SURF-%d descriptors per pair, ratio 0.9 + cross-check, %d pairs/rank" % (kdim, np_)},
-                     "impl": "tcgen05" if os.environ.get("MM_MATCH_TC", "1") != "0" else "simt", "gpu_launches": int(m_launch),
+                     "impl": "simt (exact fp64-accumulate CUDA cores)" if os.environ.get("MM_MATCH_NO_TC") else "tcgen05 TF32 candidate GEMM + exact re-rank", "gpu_launches": int(m_launch),
                      "algorithmic_tflops": pairs_s * flops / 1e12, "tensor_roofline_frac_of_bf16_peak": pairs_s * flops / 1e12 / peaks["bf16_tflops"],
                      "e2e": {"value": world / m_e2e, "unit": "pairs/s", "h2d_bytes_per_step": 2 * n_feat * kdim * 4, "d2h_bytes_per_step": 12 * 3000}}
         ms_set.close()

@@ -105,8 +105,9 @@ struct mm_ba_session {
   DevBuf<double> pose_mask, pt_mask, scale_c, scale_p, Vinv, gp, dp, gc, dc, rhs;
   DevBuf<double> vx, vr, vz, vp0, vp1, vAp, pcg_sc; DevBuf<int> pcg_ic;
   DevBuf<double> part_cost, part_pt, part_cam, part_x, red;   // red: [0]=cost [1]=new_cost [2]=gmax [3]=step_norm2 [4]=mcc [5]=xnorm2
-  DevBuf<int> fail;
-  int grid_obs = 1, grid_pt = 1, grid_cam6 = 1, grid_x = 1;
+  DevBuf<int> fail; DevBuf<unsigned long long> pcg_dbg;
+  int grid_obs = 1, grid_pt = 1, grid_cam6 = 1, grid_x = 1, pcg_grid = 0, pcg_ecap = 0, pcg_threads = 0; bool pcg_cached = false; size_t pcg_smem = 0; const void* pcg_fn = nullptr;
+  cudaEvent_t evs[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // LM state (host)
   double cost = 0, radius = 0, decrease_factor = 2, x_norm = 0, abs_gtol = 0, gmax = 0;
   int iter = 0, n_invalid = 0; bool started = false, finished = false, scaled = false;
@@ -293,32 +294,56 @@ int launch_schur(mm_ba_session* s) {
   k_precond<<<blocks_for(s->n_img, 64), 64, 0, st>>>(s->n_img, s->S.p, s->Minv.p, s->fail.p); MM_LAUNCH_CHECK();
   return MM_OK;
 }
-int launch_pcg_iteration(mm_ba_session* s, int it) {
+// K3: solve S y = rhs with the persistent cooperative kernel (no host sync; iteration count -> pcg_ic[1])
+int launch_pcg(mm_ba_session* s) {
   cudaStream_t st = s->stream;
-  double* p_old = (it & 1) ? s->vp1.p : s->vp0.p; double* p_new = (it & 1) ? s->vp0.p : s->vp1.p;
-  k_pcg_spmv<<<blocks_for((int64_t)s->n_img * 32, 128), 128, 0, st>>>(s->n_img, s->row_start.p, s->row_col.p, s->row_blk.p, s->S.p,
-      s->vz.p, p_old, p_new, s->vAp.p, s->pcg_sc.p, s->pcg_ic.p, it == 0); MM_LAUNCH_CHECK();
-  const double tol = s->opt.pcg_tolerance;
-  k_pcg_update<<<blocks_for(s->n_img, 128), 128, 0, st>>>(s->n_img, s->Minv.p, p_new, s->vAp.p, s->vx.p, s->vr.p, s->vz.p,
-      s->pcg_sc.p, s->pcg_ic.p, tol * tol, s->opt.pcg_max_iterations); MM_LAUNCH_CHECK();
-  return MM_OK;
-}
-// K3: solve S y = rhs; returns iteration count
-int run_pcg(mm_ba_session* s, int* iters) {
-  cudaStream_t st = s->stream;
-  MM_CUDA(cudaMemsetAsync(s->pcg_sc.p, 0, sizeof(double) * 8, st));
+  MM_CUDA(cudaMemsetAsync(s->pcg_sc.p, 0, sizeof(double) * 16, st));
   MM_CUDA(cudaMemsetAsync(s->pcg_ic.p, 0, sizeof(int) * 4, st));
-  PcgVecs v = { s->vx.p, s->vr.p, s->vz.p, s->vp0.p, s->vp1.p, s->vAp.p };
-  k_pcg_init<<<blocks_for(s->n_img, 128), 128, 0, st>>>(s->n_img, s->rhs.p, s->Minv.p, v, s->pcg_sc.p, s->pcg_ic.p); MM_LAUNCH_CHECK();
-  int it = 0; int ic[2] = {0, 0};
-  const int batch = 16;
-  while (true) {
-    for (int b = 0; b < batch; ++b, ++it) { int rc = launch_pcg_iteration(s, it); if (rc) return rc; }
-    MM_CUDA(cudaMemcpyAsync(ic, s->pcg_ic.p, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+  if (s->pcg_grid == 0) {
+    // choose between the cached kernel (rows resident in shared memory) and the streaming kernel
+    std::vector<int> h_rs((size_t)s->n_img + 1);
+    MM_CUDA(cudaMemcpyAsync(h_rs.data(), s->row_start.p, sizeof(int) * h_rs.size(), cudaMemcpyDeviceToHost, st));
     MM_CUDA(cudaStreamSynchronize(st));
-    if (ic[0]) break;
+    int dev = 0, max_smem = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    s->pcg_cached = false;
+    const int tries[3] = { 512, 256, 128 };
+    for (int ti = 0; ti < 3 && !s->pcg_cached && !getenv("MM_PCG_STREAMING"); ++ti) {
+      const int threads = tries[ti], NW = threads / 32;
+      const int blocks = (s->n_img + NW - 1) / NW;
+      int e_cap = 1;
+      for (int b = 0; b < blocks; ++b) e_cap = std::max(e_cap, h_rs[std::min((b + 1) * NW, s->n_img)] - h_rs[b * NW]);
+      const size_t smem = sizeof(double) * ((size_t)e_cap * 36 + NW * 36) + sizeof(int) * (size_t)e_cap + 16;
+      if (smem + 2048 > (size_t)max_smem) continue;
+      const void* fn = threads == 512 ? (const void*)k_pcg_cached<512> : (threads == 256 ? (const void*)k_pcg_cached<256> : (const void*)k_pcg_cached<128>);
+      int per_sm = 0;
+      if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+          cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&per_sm, fn, threads, smem, 0) == cudaSuccess && per_sm * num_sms() >= blocks) {
+        s->pcg_cached = true; s->pcg_grid = std::max(1, blocks); s->pcg_smem = smem; s->pcg_ecap = e_cap; s->pcg_threads = threads; s->pcg_fn = fn;
+      }
+      cudaGetLastError();
+    }
+    if (!s->pcg_cached) {
+      int per_sm = 0;
+      MM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_persistent, 256, 0));
+      const int cap = std::max(1, per_sm * num_sms());
+      s->pcg_grid = std::max(1, std::min(cap, (s->n_img + 7) / 8));
+    }
   }
-  *iters = ic[1];
+  PcgArgs a; a.n_img = s->n_img; a.row_start = s->row_start.p; a.row_col = s->row_col.p; a.row_blk = s->row_blk.p; a.S = s->S.p; a.Minv = s->Minv.p;
+  a.b = s->rhs.p; a.x = s->vx.p; a.r = s->vr.p; a.z = s->vz.p; a.p0 = s->vp0.p; a.p1 = s->vp1.p; a.Ap = s->vAp.p; a.sc = s->pcg_sc.p; a.ic = s->pcg_ic.p;
+  a.tol2 = s->opt.pcg_tolerance * s->opt.pcg_tolerance; a.max_iter = s->opt.pcg_max_iterations;
+  a.dbg = nullptr;
+  if (getenv("MM_PCG_DEBUG")) { if (!s->pcg_dbg.p) MM_CUDA(s->pcg_dbg.alloc(6 * 32)); a.dbg = s->pcg_dbg.p; }
+  if (s->pcg_cached) {
+    int e_cap = s->pcg_ecap;
+    void* cargs[] = { &a, &e_cap };
+    MM_CUDA(cudaLaunchCooperativeKernel(s->pcg_fn, dim3(s->pcg_grid), dim3(s->pcg_threads), cargs, s->pcg_smem, st));
+    count_launch();
+    return MM_OK;
+  }
+  void* args[] = { &a };
+  MM_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg_persistent, dim3(s->pcg_grid), dim3(256), args, 0, st));
+  count_launch();
   return MM_OK;
 }
 // K4: back-substitution, candidate parameters, step norm and model cost change -> red[3], red[4]
@@ -342,13 +367,6 @@ int read_red(mm_ba_session* s, double* out8) {
   MM_CUDA(cudaStreamSynchronize(s->stream));
   return MM_OK;
 }
-int read_fail(mm_ba_session* s, int* f) {
-  MM_CUDA(cudaMemcpyAsync(f, s->fail.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-  MM_CUDA(cudaStreamSynchronize(s->stream));
-  if (*f) MM_CUDA(cudaMemsetAsync(s->fail.p, 0, sizeof(int), s->stream));
-  return MM_OK;
-}
-
 void trace_push(mm_ba_session* s, int accepted, int lin) {
   mm_ba_summary& S = s->sum; const int i = S.num_iterations;
   if (i < MM_BA_TRACE_MAX) { S.trace_cost[i] = s->cost; S.trace_radius[i] = s->radius; S.trace_gradient_max_norm[i] = s->gmax; S.trace_accepted[i] = accepted; S.trace_linear_iterations[i] = lin; }
@@ -389,11 +407,22 @@ int lm_iterate(mm_ba_session* s) {
   if (s->iter >= O.max_num_iterations) { S.termination = MM_TERM_NO_CONVERGENCE; s->finished = true; return MM_OK; }
   s->iter++;
   int rc, pcg_it = 0, fail = 0;
-  { Timer t(s, &S.ms_pcg); if ((rc = run_pcg(s, &pcg_it))) return rc; }
+  cudaEventRecord(s->evs[0], s->stream);
+  if ((rc = launch_pcg(s))) return rc;
+  cudaEventRecord(s->evs[1], s->stream);
+  if ((rc = launch_update(s))) return rc;
+  if ((rc = launch_cost_candidate(s))) return rc;
+  cudaEventRecord(s->evs[2], s->stream);
+  double red[8];
+  { int hic[4];
+    MM_CUDA(cudaMemcpyAsync(hic, s->pcg_ic.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, s->stream));
+    MM_CUDA(cudaMemcpyAsync(&fail, s->fail.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    if ((rc = read_red(s, red))) return rc;           // synchronises the stream
+    pcg_it = hic[1];
+    if (s->pcg_dbg.p) { unsigned long long h[192]; cudaMemcpy(h, s->pcg_dbg.p, sizeof h, cudaMemcpyDeviceToHost); for (int i = 2; i < 6; ++i) printf("pcg(%s,%d thr,%d ctas) it %d: spmv %llu red %llu sync %llu upd %llu sync %llu  next %llu ns\n", s->pcg_cached ? "cached" : "streaming", s->pcg_threads, s->pcg_grid, i, h[6*i+1]-h[6*i], h[6*i+2]-h[6*i+1], h[6*i+3]-h[6*i+2], h[6*i+4]-h[6*i+3], h[6*i+5]-h[6*i+4], h[6*(i+1)]-h[6*i+5]); }
+    if (fail) MM_CUDA(cudaMemsetAsync(s->fail.p, 0, sizeof(int), s->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, s->evs[0], s->evs[1]); S.ms_pcg += ms; cudaEventElapsedTime(&ms, s->evs[1], s->evs[2]); S.ms_update += ms; }
   s->last_pcg_iters = pcg_it;
-  { Timer t(s, &S.ms_update); if ((rc = launch_update(s))) return rc; if ((rc = launch_cost_candidate(s))) return rc; }
-  double red[8]; if ((rc = read_red(s, red))) return rc;
-  if ((rc = read_fail(s, &fail))) return rc;
   const double new_cost = red[1], step_norm = sqrt(red[3]), mcc = red[4];
   bool valid = !fail && isfinite(step_norm) && isfinite(mcc) && isfinite(new_cost) && !(mcc < 0.0);
   bool successful = false; double rel_dec = 0.0;
@@ -415,10 +444,14 @@ int lm_iterate(mm_ba_session* s) {
     // keep the previous iterate in poses2/pts2 until the gradient test has passed (Ceres 1.8 commits
     // x_min only after it)
     std::swap(s->poses.p, s->poses2.p); std::swap(s->pts.p, s->pts2.p); std::swap(s->aux.p, s->aux2.p);
-    { Timer t(s, &S.ms_linearize); if ((rc = launch_linearize(s))) return rc; }
-    { Timer t(s, &S.ms_schur); if ((rc = launch_schur(s))) return rc; }
+    cudaEventRecord(s->evs[3], s->stream);
+    if ((rc = launch_linearize(s))) return rc;
+    cudaEventRecord(s->evs[4], s->stream);
+    if ((rc = launch_schur(s))) return rc;
+    cudaEventRecord(s->evs[5], s->stream);
     if ((rc = launch_xnorm(s))) return rc;
     if ((rc = read_red(s, red))) return rc;
+    { float ms = 0; cudaEventElapsedTime(&ms, s->evs[3], s->evs[4]); S.ms_linearize += ms; cudaEventElapsedTime(&ms, s->evs[4], s->evs[5]); S.ms_schur += ms; }
     s->cost = red[0]; s->gmax = red[2]; s->x_norm = sqrt(red[5]);
     if (s->gmax <= s->abs_gtol) {
       std::swap(s->poses.p, s->poses2.p); std::swap(s->pts.p, s->pts2.p); std::swap(s->aux.p, s->aux2.p);   // discard, as Ceres 1.8 does
@@ -427,7 +460,12 @@ int lm_iterate(mm_ba_session* s) {
   } else {
     S.num_unsuccessful_steps++;
     s->radius = s->radius / s->decrease_factor; s->decrease_factor *= 2.0;
-    if (s->radius >= O.min_trust_region_radius) { Timer t(s, &S.ms_schur); if ((rc = launch_schur(s))) return rc; }
+    if (s->radius >= O.min_trust_region_radius) {
+      cudaEventRecord(s->evs[4], s->stream);
+      if ((rc = launch_schur(s))) return rc;
+      cudaEventRecord(s->evs[5], s->stream); cudaEventSynchronize(s->evs[5]);
+      float ms = 0; cudaEventElapsedTime(&ms, s->evs[4], s->evs[5]); S.ms_schur += ms;
+    }
   }
   if (s->radius < O.min_trust_region_radius) { S.termination = MM_TERM_PARAMETER_TOLERANCE; s->finished = true; return MM_OK; }
   trace_push(s, successful ? 1 : 0, pcg_it);
@@ -455,6 +493,7 @@ void mm_ba_session_destroy(mm_ba_session* s) {
   if (!s) return;
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
+  for (int i = 0; i < 8; ++i) if (s->evs[i]) cudaEventDestroy(s->evs[i]);
   delete s;
 }
 
@@ -473,6 +512,7 @@ int mm_ba_session_create(const mm_ba_problem* P, const mm_ba_options* opt, void*
   s->n_img = P->n_img; s->n_cam = P->n_cam; s->n_pt = P->n_pt; s->n_obs = P->n_obs;
   auto fail_out = [&](int code) { mm_ba_session_destroy(s); return code; };
   if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) { set_error("cudaEventCreate failed"); return fail_out(MM_ERR_CUDA); }
+  for (int i = 0; i < 8; ++i) if (cudaEventCreate(&s->evs[i]) != cudaSuccess) { set_error("cudaEventCreate failed"); return fail_out(MM_ERR_CUDA); }
   float ms = 0; cudaEventRecord(s->ev0, s->stream);
   s->h_poses0.assign(P->poses, P->poses + 6 * (size_t)P->n_img);
   s->h_intr0.assign(P->intr, P->intr + MM_INTR_STRIDE * (size_t)P->n_cam);

@@ -12,6 +12,7 @@
 // observation  [r0 r1 | Jc row0 (w0 w1 w2 tx ty tz) | Jc row1 | Jp row0 | Jp row1]  so that the
 // point pass streams records and the camera pass gathers whole 32-byte sectors.
 #pragma once
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "camera.cuh"
 
@@ -535,6 +536,249 @@ __global__ void __launch_bounds__(128) k_pcg_update(
     if (rr_now <= tol2 * sc[4] || it >= max_iter || !(rr_now == rr_now)) ic[0] = 1;
     __threadfence();
   }
+}
+
+// ---- K3 (persistent form): the whole PCG solve in ONE cooperative launch -------------------------
+// One warp per block-row of S, grid sized to the rows (<= co-resident CTAs); two grid barriers per
+// iteration (after the SpMV reduction and after the residual update).  S, Minv and the CSR arrays are
+// read-only inside the kernel and stay L1/L2 resident across iterations; vectors written by other CTAs
+// are read with ld.global.cg after the barrier.  A single-CTA launch uses __syncthreads instead
+// (local-BA sized systems).  scalars sc[]: [0,1] pAp slots, [2,3] r.z slots, [4,5] r.r slots, [6] b.b.
+struct PcgArgs {
+  int n_img; const int* row_start; const int* row_col; const int* row_blk; const double* S; const double* Minv; const double* b;
+  double *x, *r, *z, *p0, *p1, *Ap; double* sc; int* ic; double tol2; int max_iter;
+  unsigned long long* dbg;   // optional: %globaltimer stamps of CTA 0 for the first 32 iterations (6 per iteration)
+};
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define PCG_STAMP(k) do { if (A.dbg && blockIdx.x == 0 && threadIdx.x == 0 && it < 32) A.dbg[6 * it + (k)] = gtimer(); } while (0)
+
+__device__ __forceinline__ double block_sum_to_thread0(double v, double* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x == 0) for (int i = 0; i < nw; ++i) t += red[i];
+  return t;
+}
+
+__global__ void __launch_bounds__(256) k_pcg_persistent(PcgArgs A) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  const bool single = gridDim.x == 1;
+  __shared__ double red[8];
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int gw = blockIdx.x * wpb + (threadIdx.x >> 5), nw = gridDim.x * wpb;
+  const int n = A.n_img;
+  const int g = lane / 6, rr_ = lane - 6 * g;          // SpMV: 5 groups of 6 lanes, lane = (group, block row)
+  // ---- init: x = 0, r = b, z = Minv r, p = 0
+  {
+    double a_rz = 0.0, a_bb = 0.0;
+    for (int row = gw; row < n; row += nw) {
+      double rv = 0.0;
+      if (lane < 6) rv = A.b[6 * (size_t)row + lane];
+      double zl = 0.0;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) { const double rc = __shfl_sync(0xffffffffu, rv, c); if (lane < 6) zl += A.Minv[36 * (size_t)row + 6 * lane + c] * rc; }
+      if (lane < 6) {
+        const size_t i = 6 * (size_t)row + lane;
+        A.x[i] = 0.0; A.r[i] = rv; A.z[i] = zl; A.p0[i] = 0.0; A.p1[i] = 0.0;
+        a_rz += rv * zl; a_bb += rv * rv;
+      }
+    }
+    a_rz = block_sum_to_thread0(a_rz, red); a_bb = block_sum_to_thread0(a_bb, red);
+    if (threadIdx.x == 0) { atomicAdd(A.sc + 2, a_rz); atomicAdd(A.sc + 6, a_bb); }
+  }
+  if (single) __syncthreads(); else grid.sync();
+  double rz = __ldcg(A.sc + 2), rz_old = 1.0;
+  const double bb = __ldcg(A.sc + 6);
+  int it = 0;
+  if (bb > 0.0) {
+    for (;;) {
+      const double beta = it == 0 ? 0.0 : rz / rz_old;
+      const double* p_old = (it & 1) ? A.p1 : A.p0; double* p_new = (it & 1) ? A.p0 : A.p1;
+      const int nxt = (it + 1) & 1;
+      if (gw == 0 && lane == 0) { A.sc[2 + nxt] = 0.0; A.sc[4 + nxt] = 0.0; }
+      // ---- SpMV with p formed on the fly: Ap = S (z + beta p_old)
+      double acc = 0.0;
+      for (int row = gw; row < n; row += nw) {
+        double y = 0.0;
+        if (lane < 30) {
+          for (int e = A.row_start[row] + g; e < A.row_start[row + 1]; e += 5) {
+            const int col = A.row_col[e], bid = A.row_blk[e];
+            const bool tr = bid < 0;
+            const double* B = A.S + 36 * (size_t)(tr ? -bid - 1 : bid);
+            const double* zc = A.z + 6 * (size_t)col; const double* pc = p_old + 6 * (size_t)col;
+            if (!tr) {
+#pragma unroll
+              for (int c = 0; c < 6; ++c) y += B[6 * rr_ + c] * (__ldcg(zc + c) + beta * __ldcg(pc + c));
+            } else {
+#pragma unroll
+              for (int c = 0; c < 6; ++c) y += B[6 * c + rr_] * (__ldcg(zc + c) + beta * __ldcg(pc + c));
+            }
+          }
+        }
+        double t = y + __shfl_down_sync(0xffffffffu, y, 12);
+        t += __shfl_down_sync(0xffffffffu, t, 6);
+        t += __shfl_down_sync(0xffffffffu, y, 24);
+        if (lane < 6) {
+          const size_t i = 6 * (size_t)row + lane;
+          const double pn = __ldcg(A.z + i) + beta * __ldcg(p_old + i);
+          p_new[i] = pn; A.Ap[i] = t; acc += pn * t;
+        }
+      }
+      acc = block_sum_to_thread0(acc, red);
+      if (threadIdx.x == 0) atomicAdd(A.sc + (it & 1), acc);
+      if (single) __syncthreads(); else grid.sync();
+      const double pAp = __ldcg(A.sc + (it & 1));
+      const double alpha = pAp > 0.0 ? rz / pAp : 0.0;
+      if (gw == 0 && lane == 0) A.sc[nxt] = 0.0;
+      // ---- x += alpha p ; r -= alpha Ap ; z = Minv r
+      double a_rz = 0.0, a_rr = 0.0;
+      for (int row = gw; row < n; row += nw) {
+        double rv = 0.0;
+        const size_t i = 6 * (size_t)row + (lane < 6 ? lane : 0);
+        if (lane < 6) {
+          A.x[i] += alpha * p_new[i];
+          rv = A.r[i] - alpha * A.Ap[i];
+          A.r[i] = rv;
+        }
+        double zl = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) { const double rc = __shfl_sync(0xffffffffu, rv, c); if (lane < 6) zl += A.Minv[36 * (size_t)row + 6 * lane + c] * rc; }
+        if (lane < 6) { A.z[i] = zl; a_rz += rv * zl; a_rr += rv * rv; }
+      }
+      a_rz = block_sum_to_thread0(a_rz, red); a_rr = block_sum_to_thread0(a_rr, red);
+      if (threadIdx.x == 0) { atomicAdd(A.sc + 2 + nxt, a_rz); atomicAdd(A.sc + 4 + nxt, a_rr); }
+      if (single) __syncthreads(); else grid.sync();
+      rz_old = rz; rz = __ldcg(A.sc + 2 + nxt);
+      const double rr = __ldcg(A.sc + 4 + nxt);
+      ++it;
+      if (rr <= A.tol2 * bb || it >= A.max_iter || !(rr == rr)) break;
+    }
+  }
+  if (gw == 0 && lane == 0) A.ic[1] = it;
+}
+
+// ---- K3 (persistent, cached form): small/medium reduced systems --------------------------------
+// Same algorithm as k_pcg_persistent, but each warp owns ONE block-row for the whole solve: the row's
+// 6x6 blocks (already oriented), its column indices and its Minv block live in shared memory, and its
+// slices of x, r, z, p, Ap live in registers.  Per iteration a warp only gathers z/p of its neighbour
+// rows from L2 (all loads issued back to back), so an iteration costs about two grid barriers.
+// Usable when every CTA's rows fit in shared memory (host checks); otherwise the streaming kernel runs.
+constexpr int PCG_MAXR = 16;          // rounds of 5 blocks held in registers per chunk
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_pcg_cached(PcgArgs A, int e_cap) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  constexpr int NW = THREADS / 32;
+  extern __shared__ double sm[];
+  double* sB = sm;                                   // [e_cap][36]
+  double* sM = sB + (size_t)e_cap * 36;              // [NW][36]
+  int* sC = reinterpret_cast<int*>(sM + NW * 36);    // [e_cap]
+  __shared__ double red[NW];
+  const bool single = gridDim.x == 1;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int n = A.n_img;
+  const int row = blockIdx.x * NW + wib;
+  const bool valid = row < n;
+  const int g = lane / 6, r6 = lane - 6 * g;
+  const bool act = valid && lane < 6;
+  const int first_row = min(blockIdx.x * NW, n);
+  const int e_blk0 = A.row_start[first_row];
+  int e0 = 0, e1 = 0;
+  if (valid) { e0 = A.row_start[row] - e_blk0; e1 = A.row_start[row + 1] - e_blk0; }
+  // ---- one-time staging of this row's blocks (oriented) and preconditioner block
+  for (int idx = lane; idx < (e1 - e0) * 36; idx += 32) {
+    const int e = idx / 36, k = idx - 36 * e, rr = k / 6, cc = k - 6 * rr;
+    const int bid = A.row_blk[e_blk0 + e0 + e];
+    const bool tr = bid < 0;
+    const double* B = A.S + 36 * (size_t)(tr ? -bid - 1 : bid);
+    sB[(size_t)(e0 + e) * 36 + k] = tr ? B[6 * cc + rr] : B[k];
+  }
+  for (int e = e0 + lane; e < e1; e += 32) sC[e] = A.row_col[e_blk0 + e];
+  if (valid) for (int k = lane; k < 36; k += 32) sM[wib * 36 + k] = A.Minv[36 * (size_t)row + k];
+  __syncwarp();
+  // ---- init
+  double xl = 0.0, rl = 0.0, zl = 0.0, pl = 0.0, apl = 0.0;
+  const size_t gi = 6 * (size_t)(valid ? row : 0) + (lane < 6 ? lane : 0);
+  {
+    if (act) rl = A.b[gi];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { const double rc = __shfl_sync(0xffffffffu, rl, c); if (act) zl += sM[wib * 36 + 6 * lane + c] * rc; }
+    if (act) { A.z[gi] = zl; A.p0[gi] = 0.0; A.p1[gi] = 0.0; }
+    double a_rz = act ? rl * zl : 0.0, a_bb = act ? rl * rl : 0.0;
+    a_rz = block_sum_to_thread0(a_rz, red); a_bb = block_sum_to_thread0(a_bb, red);
+    if (threadIdx.x == 0) { atomicAdd(A.sc + 2, a_rz); atomicAdd(A.sc + 6, a_bb); }
+  }
+  if (single) __syncthreads(); else grid.sync();
+  double rz = __ldcg(A.sc + 2), rz_old = 1.0;
+  const double bb = __ldcg(A.sc + 6);
+  int it = 0;
+  if (bb > 0.0) {
+    for (;;) {
+      const double beta = it == 0 ? 0.0 : rz / rz_old;
+      const double* p_old = (it & 1) ? A.p1 : A.p0; double* p_new = (it & 1) ? A.p0 : A.p1;
+      const int nxt = (it + 1) & 1;
+      if (blockIdx.x == 0 && threadIdx.x == 0) { A.sc[2 + nxt] = 0.0; A.sc[4 + nxt] = 0.0; }
+      PCG_STAMP(0);
+      // ---- SpMV: gather all neighbour slices first (independent L2 loads), then multiply from smem
+      double y = 0.0;
+      for (int base = e0; base < e1; base += 5 * PCG_MAXR) {
+        double pv[PCG_MAXR];
+#pragma unroll
+        for (int k = 0; k < PCG_MAXR; ++k) {
+          const int e = base + 5 * k + g;
+          pv[k] = 0.0;
+          if (lane < 30 && e < e1) { const size_t ci = 6 * (size_t)sC[e] + r6; pv[k] = __ldcg(A.z + ci) + beta * __ldcg(p_old + ci); }
+        }
+#pragma unroll
+        for (int k = 0; k < PCG_MAXR; ++k) {
+          if (base + 5 * k < e1) {                       // warp-uniform
+            const int e = base + 5 * k + g;
+            const bool ok = lane < 30 && e < e1;
+            const double* Brow = sB + (size_t)(ok ? e : e0) * 36 + 6 * r6;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) { const double xc = __shfl_sync(0xffffffffu, pv[k], 6 * g + c); if (ok) y += Brow[c] * xc; }
+          }
+        }
+      }
+      double t = y + __shfl_down_sync(0xffffffffu, y, 12);
+      t += __shfl_down_sync(0xffffffffu, t, 6);
+      t += __shfl_down_sync(0xffffffffu, y, 24);
+      PCG_STAMP(1);
+      double acc = 0.0;
+      if (act) { pl = zl + beta * pl; apl = t; p_new[gi] = pl; acc = pl * t; }
+      acc = block_sum_to_thread0(acc, red);
+      if (threadIdx.x == 0) atomicAdd(A.sc + (it & 1), acc);
+      PCG_STAMP(2);
+      if (single) __syncthreads(); else grid.sync();
+      PCG_STAMP(3);
+      const double pAp = __ldcg(A.sc + (it & 1));
+      const double alpha = pAp > 0.0 ? rz / pAp : 0.0;
+      if (blockIdx.x == 0 && threadIdx.x == 0) A.sc[nxt] = 0.0;
+      // ---- update (registers only)
+      if (act) { xl += alpha * pl; rl -= alpha * apl; }
+      double zn = 0.0;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) { const double rc = __shfl_sync(0xffffffffu, rl, c); if (act) zn += sM[wib * 36 + 6 * lane + c] * rc; }
+      if (act) { zl = zn; A.z[gi] = zl; }
+      double a_rz = act ? rl * zl : 0.0, a_rr = act ? rl * rl : 0.0;
+      a_rz = block_sum_to_thread0(a_rz, red); a_rr = block_sum_to_thread0(a_rr, red);
+      if (threadIdx.x == 0) { atomicAdd(A.sc + 2 + nxt, a_rz); atomicAdd(A.sc + 4 + nxt, a_rr); }
+      PCG_STAMP(4);
+      if (single) __syncthreads(); else grid.sync();
+      PCG_STAMP(5);
+      rz_old = rz; rz = __ldcg(A.sc + 2 + nxt);
+      const double rr = __ldcg(A.sc + 4 + nxt);
+      ++it;
+      if (rr <= A.tol2 * bb || it >= A.max_iter || !(rr == rr)) break;
+    }
+  }
+  if (act) A.x[gi] = xl;
+  if (blockIdx.x == 0 && threadIdx.x == 0) A.ic[1] = it;
 }
 
 // ---- K4a: back-substitution for the points + candidate point parameters --------------------

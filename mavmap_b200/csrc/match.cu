@@ -237,7 +237,7 @@ int match_pairs_device(mm_match_set* s, const int32_t* ia, const int32_t* ib, in
   const int impl = opt->impl;
   bool done_tc = false;
   if (impl == MM_MATCH_IMPL_TCGEN05 || impl == MM_MATCH_IMPL_AUTO) {
-    int rc = match_tc_pairs(s->desc, s->xy, s->k, s->offs.data(), ia, ib, jobs.data(), n_pairs, opt->max_distance,
+    int rc = match_tc_pairs(s->desc, s->xy, s->k, s->offs.data(), s->offs[s->n_images], ia, ib, jobs.data(), n_pairs, opt->max_distance,
                             s->knn12.p, s->knn21.p, st, impl == MM_MATCH_IMPL_TCGEN05);
     if (rc == MM_OK) done_tc = true;
     else if (rc != MM_ERR_UNSUPPORTED || impl == MM_MATCH_IMPL_TCGEN05) return rc;
@@ -266,7 +266,7 @@ void mm_match_options_default(mm_match_options* o) {
   o->ratio_test = 1; o->max_ratio = 0.6; o->max_distance = -1.0; o->impl = MM_MATCH_IMPL_AUTO;    // feature.h:107-109
 }
 
-void mm_match_set_destroy(mm_match_set* s) { delete s; }
+void mm_match_set_destroy(mm_match_set* s) { if (s) { match_tc_release(s->desc); delete s; } }
 
 int mm_match_set_create_dev(const float* desc_dev, const float* xy_dev, const int32_t* counts, int32_t n_images, int32_t k, mm_match_set** out) {
   if (!out || !counts || n_images < 0 || k <= 0) { set_error("invalid argument"); return MM_ERR_INVALID_ARG; }

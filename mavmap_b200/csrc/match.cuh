@@ -20,8 +20,12 @@ int knn2_simt(cudaStream_t st, const float* Q, int nq, const float* T, int nt, i
 
 // tensor-core candidate selection + exact re-rank for a list of pairs (match_tc.cu).
 // Returns MM_ERR_UNSUPPORTED when the shapes/options are outside what the tcgen05 path handles.
-int match_tc_pairs(const float* desc, const float* xy, int K, const int64_t* offs, const int32_t* ia, const int32_t* ib,
+int match_tc_pairs(const float* desc, const float* xy, int K, const int64_t* offs, int64_t total_rows, const int32_t* ia, const int32_t* ib,
                    const PairJob* jobs_host, int n_pairs, double max_distance, Knn2* knn12, Knn2* knn21,
                    cudaStream_t st, bool required);
+
+// drop the TF32 operand copies cached for a descriptor array (call before the array is freed)
+void match_tc_release(const float* desc);
+void match_tc_stats(uint64_t* rows, uint64_t* flagged);
 
 }  // namespace mm

@@ -1,11 +1,508 @@
-// match_tc.cu — tcgen05 tensor-core candidate selection for the matcher (placeholder until
-// the TF32 distance-GEMM kernel lands; AUTO falls back to the exact SIMT path).
+// match_tc.cu — tensor-core candidate selection for match_brute_force (K5).
+//
+// Replaces the two cv::BFMatcher::knnMatch(k=2) distance passes of mavmap/mavmap
+// src/base2d/feature.cc:71-72 (OpenCV batchDistance): the N x M x K distance matrix is the one
+// dense contraction of the hot path, so it runs on the 5th-generation tensor cores:
+//
+//   prep      each descriptor row is written twice, TF32-rounded (cvt.rna), K padded to K' = 32-multiple:
+//               A'[i] = [ a_i            | 1      1      h1  h2 | 0.. ]   h1+h2 = |a_i|^2 + 1 (tf32 split)
+//               B'[j] = [ -2 b_j         | g1     g2     1   1  | 0.. ]   g1+g2 = |b_j|^2     (tf32 split)
+//             so that  A'[i] . B'[j] = 1 + |a_i - b_j|^2  up to the TF32 rounding of the cross term.
+//   k_match_tc  persistent, warp-specialised: warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle,
+//             4-stage mbarrier ring), warp 1 = tcgen05.mma issuer (kind::tf32, M=128, N=256, accumulators
+//             double-buffered in all 512 TMEM columns), warps 2-5 = epilogue: tcgen05.ld the 128 x 256 tile,
+//             one thread per query row keeps the 4 smallest approximate distances of its row across all
+//             column tiles (the epilogue of tile t overlaps the MMAs of tile t+1).
+//   k_rerank  exact fp64-accumulated distances (same arithmetic as match.cu / the oracle) of the 4
+//             candidates -> exact top-2, plus a rigorous test that no other column can enter the top-2
+//             given the TF32 error bound; rows that fail the test are re-scanned exactly (k_rescan).
+// The result is bit-identical to the exact SIMT path; the tensor cores only prune.
+#include <cuda.h>
+#include <float.h>
+#include <vector>
+#include <algorithm>
+#include <mutex>
 #include "common.cuh"
 #include "match.cuh"
+
 namespace mm {
-int match_tc_pairs(const float*, const float*, int, const int64_t*, const int32_t*, const int32_t*,
-                   const PairJob*, int, double, Knn2*, Knn2*, cudaStream_t, bool required) {
-  if (required) set_error("tcgen05 matcher path not built");
-  return MM_ERR_UNSUPPORTED;
+
+constexpr int TC_M = 128, TC_N = 256, TC_KB = 32;           // tile rows, tile cols, K elements per stage (128 B)
+constexpr int TC_STAGES = 4;
+constexpr int TC_A_BYTES = TC_M * TC_KB * 4, TC_B_BYTES = TC_N * TC_KB * 4, TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr int TC_THREADS = 320;                               // warp0 TMA, warp1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int TC_C = 8;                                       // candidates kept per row
+constexpr uint32_t SPIN_LIMIT = 1u << 24;                     // watchdog: trap instead of hanging the GPU
+
+struct TcItem { int rowA0, nA, rowB0, nB; int64_t out_off; };  // one 128-row block of one direction of one pair
+struct TcCand { int idx[TC_C]; float worst; };
+
+// ---------------------------------------------------------------- PTX wrappers (sm_100a)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+  return ok != 0;
 }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) { if (++spins > SPIN_LIMIT) __trap(); }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               :: "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) { asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(map)) : "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) { asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+               :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                 "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                 "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major operand, 128-byte swizzle: rows are 128 B apart, 8-row atoms
+// are 1024 B apart (SBO); LBO is unused for swizzled K-major; descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);            // start address [0,14)
+  d |= (uint64_t)(1024 >> 4) << 32;                        // stride byte offset [32,46)
+  d |= (uint64_t)1 << 46;                                  // version
+  d |= (uint64_t)2 << 61;                                  // layout: SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------- prep: fp32 descriptors -> TF32 operand rows
+__device__ __forceinline__ float to_tf32(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return __uint_as_float(r); }
+
+__global__ void k_tc_prep(const float* __restrict__ desc, int64_t rows, int K, int Kp, float* __restrict__ PA, float* __restrict__ PB,
+                          float* __restrict__ norm_out /* [rows] |x|^2 in fp32 (rounded from fp64) */) {
+  const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* x = desc + row * K;
+  double n2 = 0.0;
+  for (int k = lane; k < Kp; k += 32) {
+    float a = 0.f, b = 0.f;
+    if (k < K) { const float v = x[k]; n2 += (double)v * (double)v; a = to_tf32(v); b = -2.0f * a; }
+    PA[row * Kp + k] = a; PB[row * Kp + k] = b;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+  __syncwarp();                          // the zero fill of columns >= K (other lanes) precedes lane 0's writes below
+  if (lane == 0) {
+    const float h1 = to_tf32((float)(n2 + 1.0)), h2 = to_tf32((float)(n2 + 1.0 - (double)h1));
+    const float g1 = to_tf32((float)n2), g2 = to_tf32((float)(n2 - (double)g1));
+    PA[row * Kp + K] = 1.f; PA[row * Kp + K + 1] = 1.f; PA[row * Kp + K + 2] = h1; PA[row * Kp + K + 3] = h2;
+    PB[row * Kp + K] = g1; PB[row * Kp + K + 1] = g2; PB[row * Kp + K + 2] = 1.f; PB[row * Kp + K + 3] = 1.f;
+    norm_out[row] = (float)n2;
+  }
+}
+
+// ---------------------------------------------------------------- the tensor-core kernel
+// branch-free insertion into the ascending list; strict '<' keeps the earlier (lower) column on ties
+__device__ __forceinline__ void cand_insert(float v, int j, float (&cv)[TC_C], int (&ci)[TC_C]) {
+  bool lt[TC_C];
+#pragma unroll
+  for (int c = 0; c < TC_C; ++c) lt[c] = v < cv[c];
+#pragma unroll
+  for (int c = TC_C - 1; c > 0; --c) {
+    cv[c] = lt[c - 1] ? cv[c - 1] : (lt[c] ? v : cv[c]);
+    ci[c] = lt[c - 1] ? ci[c - 1] : (lt[c] ? j : ci[c]);
+  }
+  cv[0] = lt[0] ? v : cv[0];
+  ci[0] = lt[0] ? j : ci[0];
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(
+    const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+    const TcItem* __restrict__ items, int n_items, int num_kb, TcCand* __restrict__ cand) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: stages (1024-aligned), then barriers
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + TC_STAGES * TC_STAGE_BYTES);
+  // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, then tmem ptr
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
+  float* merge_v = reinterpret_cast<float*>(bars + 2 * TC_STAGES + 6);          // [128][TC_C]
+  int* merge_i = reinterpret_cast<int*>(merge_v + TC_M * TC_C);                  // [128][TC_C]
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + TC_STAGES);
+  const uint32_t bar_tfull = smem_u32(bars + 2 * TC_STAGES), bar_tempty = smem_u32(bars + 2 * TC_STAGES + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapB);
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const TcItem w = items[it];
+        const int n_tiles = (w.nB + TC_N - 1) / TC_N;
+        for (int nt = 0; nt < n_tiles; ++nt)
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            const uint32_t sa = smem_base + stage * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
+            mbar_expect_tx(bar_full + 8 * stage, TC_STAGE_BYTES);
+            tma_load_2d(sa, &mapA, bar_full + 8 * stage, kb * TC_KB, w.rowA0);
+            tma_load_2d(sb, &mapB, bar_full + 8 * stage, kb * TC_KB, w.rowB0 + nt * TC_N);
+            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(TC_M, TC_N);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const TcItem w = items[it];
+        const int n_tiles = (w.nB + TC_N - 1) / TC_N;
+        for (int nt = 0; nt < n_tiles; ++nt) {
+          mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);          // epilogue has drained this accumulator
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * TC_N;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(bar_full + 8 * stage, phase);
+            tc_fence_after();
+            const uint32_t sa = smem_base + stage * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
+            const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sb);
+#pragma unroll
+            for (int k = 0; k < TC_KB / 8; ++k)                    // UMMA_K = 8 tf32 = 32 bytes -> +2 in the (addr >> 4) field
+              umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            umma_commit(bar_empty + 8 * stage);                    // frees the smem stage when these MMAs retire
+            if (kb == num_kb - 1) umma_commit(bar_tfull + 8 * acc);  // accumulator ready for the epilogue
+            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: warps 2..9; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====================
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int row_in_tile = q * 32 + lane;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const TcItem w = items[it];
+      const int n_tiles = (w.nB + TC_N - 1) / TC_N;
+      float cv[TC_C]; int ci[TC_C];
+#pragma unroll
+      for (int c = 0; c < TC_C; ++c) { cv[c] = FLT_MAX; ci[c] = -1; }
+      for (int nt = 0; nt < n_tiles; ++nt) {
+        mbar_wait(bar_tfull + 8 * acc, acc_phase);
+        tc_fence_after();
+        const int col0 = nt * TC_N + half * (TC_N / 2);
+        const int ncols = min(TC_N / 2, w.nB - col0);          // may be <= 0 for the second half of the last tile
+        for (int ch = 0; ch < TC_N / 64; ++ch) {
+          if (ch * 32 >= ncols) break;                          // warp-uniform
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * TC_N + half * (TC_N / 2) + ch * 32, v);
+          tmem_ld_wait();
+          const int lim = min(32, ncols - ch * 32);
+          const float thr = cv[TC_C - 1];
+          uint32_t mask = 0;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) mask |= (__uint_as_float(v[e]) < thr) ? (1u << e) : 0u;
+          if (lim < 32) mask &= (1u << lim) - 1u;
+          const uint32_t umask = __reduce_or_sync(0xffffffffu, mask);
+          if (umask) {                                          // warp-uniform: some row of this warp has a new candidate
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (umask & (1u << e)) cand_insert((mask >> e) & 1u ? __uint_as_float(v[e]) : FLT_MAX, col0 + ch * 32 + e, cv, ci);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      // merge the two column halves of each row (half 1 -> smem -> half 0), then write the candidates
+      if (half == 1) {
+#pragma unroll
+        for (int c = 0; c < TC_C; ++c) { merge_v[row_in_tile * TC_C + c] = cv[c]; merge_i[row_in_tile * TC_C + c] = ci[c]; }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (half == 0) {
+#pragma unroll
+        for (int c = 0; c < TC_C; ++c) { const int j = merge_i[row_in_tile * TC_C + c]; if (j >= 0) cand_insert(merge_v[row_in_tile * TC_C + c], j, cv, ci); }
+        if (row_in_tile < w.nA) {
+          TcCand o;
+#pragma unroll
+          for (int c = 0; c < TC_C; ++c) o.idx[c] = ci[c];
+          o.worst = cv[TC_C - 1];
+          cand[w.out_off + row_in_tile] = o;
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ---------------------------------------------------------------- exact re-rank of the candidates
+__device__ __forceinline__ double exact_d2(const float* __restrict__ a, const float* __restrict__ b, int K) {
+  double s = 0.0;
+  for (int k = 0; k < K; ++k) { const double t = (double)a[k] - (double)b[k]; s = __dadd_rn(s, __dmul_rn(t, t)); }
+  return s;
+}
+__device__ __forceinline__ void top2_insert_f(float d, int j, float& b0, int& i0, float& b1, int& i1) {
+  // (dist, index) lexicographic order == OpenCV's strict-'<' insertion in ascending index
+  if (d < b1 || (d == b1 && j < i1) || i1 < 0) {
+    if (i0 < 0 || d < b0 || (d == b0 && j < i0)) { b1 = b0; i1 = i0; b0 = d; i0 = j; }
+    else { b1 = d; i1 = j; }
+  }
+}
+
+struct RerankJob { int rowA0, nA, rowB0, nB; int64_t out_off; int64_t knn_off; float bmax; };
+
+// thread per query row.  eps: both operands are RN-rounded to TF32 (relative error <= 2^-11 each), so the cross term
+// -2 a.b is off by at most 2 * 2^-10 * sum|a_k b_k| <= 2^-9 |a| |b|; the 1e-5 term covers fp32 accumulation and the norm splits.
+__global__ void k_rerank(const RerankJob* __restrict__ jobs, const float* __restrict__ desc, const float* __restrict__ norms, int K,
+                         const TcCand* __restrict__ cand, Knn2* __restrict__ knn, int* __restrict__ flagged, int* __restrict__ n_flagged, int flag_cap) {
+  const RerankJob job = jobs[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= job.nA) return;
+  const TcCand c = cand[job.out_off + i];
+  const float* a = desc + (size_t)(job.rowA0 + i) * K;
+  float b0 = FLT_MAX, b1 = FLT_MAX; int i0 = -1, i1 = -1;
+  double e2[TC_C]; int nvalid = 0;
+#pragma unroll
+  for (int k = 0; k < TC_C; ++k) {
+    e2[k] = 0.0;
+    if (c.idx[k] >= 0 && c.idx[k] < job.nB) {
+      e2[k] = exact_d2(a, desc + (size_t)(job.rowB0 + c.idx[k]) * K, K);
+      top2_insert_f(__fsqrt_rn((float)e2[k]), c.idx[k], b0, i0, b1, i1);
+      ++nvalid;
+    }
+  }
+  Knn2 r; r.d0 = b0; r.d1 = b1; r.i0 = i0; r.i1 = i1;
+  bool safe = true;
+  if (job.nB > TC_C) {
+    if (nvalid < TC_C) safe = false;
+    else {
+      // exact squared distance of the second best among the candidates
+      double s2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < TC_C; ++k) if (c.idx[k] == i1) s2 = e2[k];
+      const double na = (double)norms[job.rowA0 + i];
+      const double eps = 0.001953125 * 1.02 * sqrt(na) * (double)job.bmax + 1e-5 * (na + (double)job.bmax * (double)job.bmax + 1.0);
+      const double lower_bound_others = ((double)c.worst - 1.0) - eps;      // every non-candidate has exact d^2 >= this
+      safe = s2 * (1.0 + 1e-6) + 1e-30 < lower_bound_others;
+    }
+  }
+  knn[job.knn_off + i] = r;
+  if (!safe) { const int slot = atomicAdd(n_flagged, 1); if (slot < flag_cap) { flagged[2 * slot] = blockIdx.y; flagged[2 * slot + 1] = i; } }
+}
+
+// exact full scan of one flagged row per warp (same arithmetic and tie rule as the SIMT path)
+__global__ void k_rescan(const RerankJob* __restrict__ jobs, const float* __restrict__ desc, int K,
+                         const int* __restrict__ flagged, const int* __restrict__ n_flagged, int flag_cap, Knn2* __restrict__ knn) {
+  const int nf = min(*n_flagged, flag_cap);
+  const int lane = threadIdx.x & 31;
+  for (int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); f < nf; f += gridDim.x * (blockDim.x >> 5)) {
+    const RerankJob job = jobs[flagged[2 * f]];
+    const int i = flagged[2 * f + 1];
+    const float* a = desc + (size_t)(job.rowA0 + i) * K;
+    float b0 = FLT_MAX, b1 = FLT_MAX; int i0 = -1, i1 = -1;
+    for (int j = lane; j < job.nB; j += 32)
+      top2_insert_f(__fsqrt_rn((float)exact_d2(a, desc + (size_t)(job.rowB0 + j) * K, K)), j, b0, i0, b1, i1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob0 = __shfl_xor_sync(0xffffffffu, b0, o), ob1 = __shfl_xor_sync(0xffffffffu, b1, o);
+      const int oi0 = __shfl_xor_sync(0xffffffffu, i0, o), oi1 = __shfl_xor_sync(0xffffffffu, i1, o);
+      if (oi0 >= 0) top2_insert_f(ob0, oi0, b0, i0, b1, i1);
+      if (oi1 >= 0) top2_insert_f(ob1, oi1, b0, i0, b1, i1);
+    }
+    if (lane == 0) { Knn2 r; r.d0 = b0; r.d1 = b1; r.i0 = i0; r.i1 = i1; knn[job.knn_off + i] = r; }
+  }
+}
+
+// ---------------------------------------------------------------- host side
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr; static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr; cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+    else cudaGetLastError();
+  });
+  return fn;
+}
+
+struct Prepared {           // TF32 operand copies of one descriptor array
+  const float* desc = nullptr; int64_t rows = 0; int K = 0, Kp = 0;
+  DevBuf<float> PA, PB, norms; CUtensorMap mapA, mapB; std::vector<float> h_norm_max;   // per call computed lazily
+  std::vector<float> h_norms;
+};
+std::mutex g_prep_mu;
+std::vector<Prepared*> g_prepared;
+
+int make_map(CUtensorMap* map, float* base, int64_t rows, int Kp, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return MM_ERR_UNSUPPORTED; }
+  cuuint64_t gdim[2] = { (cuuint64_t)Kp, (cuuint64_t)rows };
+  cuuint64_t gstride[1] = { (cuuint64_t)Kp * 4 };
+  cuuint32_t box[2] = { (cuuint32_t)TC_KB, (cuuint32_t)box_rows };
+  cuuint32_t estr[2] = { 1, 1 };
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return MM_ERR_CUDA; }
+  return MM_OK;
+}
+
+int get_prepared(const float* desc, int64_t rows, int K, cudaStream_t st, Prepared** out) {
+  std::lock_guard<std::mutex> lk(g_prep_mu);
+  for (Prepared* p : g_prepared) if (p->desc == desc && p->rows == rows && p->K == K) { *out = p; return MM_OK; }
+  Prepared* p = new Prepared(); p->desc = desc; p->rows = rows; p->K = K; p->Kp = (K + 4 + TC_KB - 1) / TC_KB * TC_KB;
+  const int64_t prow = rows + TC_N;       // slack rows so every TMA box starts in bounds
+  if (p->PA.alloc((size_t)prow * p->Kp) != cudaSuccess || p->PB.alloc((size_t)prow * p->Kp) != cudaSuccess || p->norms.alloc((size_t)rows + 1) != cudaSuccess) {
+    delete p; cudaGetLastError(); set_error("cudaMalloc failed for the TF32 operand copies"); return MM_ERR_ALLOC; }
+  MM_CUDA(cudaMemsetAsync(p->PA.p, 0, sizeof(float) * (size_t)prow * p->Kp, st));
+  MM_CUDA(cudaMemsetAsync(p->PB.p, 0, sizeof(float) * (size_t)prow * p->Kp, st));
+  k_tc_prep<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(desc, rows, K, p->Kp, p->PA.p, p->PB.p, p->norms.p);
+  MM_LAUNCH_CHECK();
+  p->h_norms.resize((size_t)rows);
+  MM_CUDA(cudaMemcpyAsync(p->h_norms.data(), p->norms.p, sizeof(float) * (size_t)rows, cudaMemcpyDeviceToHost, st));
+  MM_CUDA(cudaStreamSynchronize(st));
+  int rc = make_map(&p->mapA, p->PA.p, prow, p->Kp, TC_M); if (rc) { delete p; return rc; }
+  rc = make_map(&p->mapB, p->PB.p, prow, p->Kp, TC_N); if (rc) { delete p; return rc; }
+  g_prepared.push_back(p);
+  *out = p;
+  return MM_OK;
+}
+
+struct TcScratch { DevBuf<TcItem> items; DevBuf<RerankJob> jobs; DevBuf<TcCand> cand; DevBuf<int> flagged, n_flagged; size_t items_cap = 0, jobs_cap = 0, cand_cap = 0; };
+TcScratch g_scr;
+std::atomic<uint64_t> g_tc_rows{0}, g_tc_flagged{0};
+
+}  // namespace
+
+void match_tc_release(const float* desc) {
+  std::lock_guard<std::mutex> lk(g_prep_mu);
+  for (size_t i = 0; i < g_prepared.size(); ++i) if (g_prepared[i]->desc == desc) { delete g_prepared[i]; g_prepared.erase(g_prepared.begin() + i); --i; }
+}
+void match_tc_stats(uint64_t* rows, uint64_t* flagged) { *rows = g_tc_rows.load(); *flagged = g_tc_flagged.load(); }
+
+int match_tc_pairs(const float* desc, const float* xy, int K, const int64_t* offs, int64_t total_rows, const int32_t* ia, const int32_t* ib,
+                   const PairJob* jobs_host, int n_pairs, double max_distance, Knn2* knn12, Knn2* knn21,
+                   cudaStream_t st, bool required) {
+  (void)xy;
+  if (max_distance != -1.0) { if (required) set_error("the tcgen05 path does not take the keypoint-distance mask"); return MM_ERR_UNSUPPORTED; }
+  if (K % 4 != 0 || K < 8 || K > 1024) { if (required) set_error("tcgen05 path needs K %% 4 == 0"); return MM_ERR_UNSUPPORTED; }
+  if (getenv("MM_MATCH_NO_TC") && !required) return MM_ERR_UNSUPPORTED;
+  // the whole descriptor array of the set: its row count is the offset past the last image referenced
+  const int64_t rows = total_rows;
+  // prepared copies are keyed by the base pointer; use the full extent the set was created with when known
+  Prepared* P = nullptr;
+  { std::lock_guard<std::mutex> lk(g_prep_mu);
+    for (Prepared* q : g_prepared) if (q->desc == desc && q->K == K && q->rows >= rows) { P = q; break; } }
+  if (!P) { int rc = get_prepared(desc, rows, K, st, &P); if (rc) return required ? rc : MM_ERR_UNSUPPORTED; }
+
+  // work items: (pair, direction, 128-row block); knn12 and knn21 live in different arrays -> two candidate regions
+  std::vector<TcItem> items; std::vector<RerankJob> rjobs;
+  int64_t cand_rows = 0;
+  for (int p = 0; p < n_pairs; ++p) {
+    const PairJob& j = jobs_host[p];
+    for (int dir = 0; dir < 2; ++dir) {
+      const int imgA = dir == 0 ? ia[p] : ib[p], imgB = dir == 0 ? ib[p] : ia[p];
+      const int nA = dir == 0 ? j.n1 : j.n2, nB = dir == 0 ? j.n2 : j.n1;
+      if (nA == 0) continue;
+      float bmax = 0.f;
+      for (int64_t r = offs[imgB]; r < offs[imgB] + nB; ++r) bmax = std::max(bmax, P->h_norms[(size_t)r]);
+      RerankJob rj; rj.rowA0 = (int)offs[imgA]; rj.nA = nA; rj.rowB0 = (int)offs[imgB]; rj.nB = nB; rj.out_off = cand_rows;
+      rj.knn_off = dir == 0 ? j.knn12_off : -(j.knn21_off + 1); rj.bmax = std::sqrt(bmax);
+      rjobs.push_back(rj);
+      if (nB > 0) for (int m = 0; m < nA; m += TC_M) { TcItem t; t.rowA0 = (int)offs[imgA] + m; t.nA = std::min(TC_M, nA - m); t.rowB0 = (int)offs[imgB]; t.nB = nB; t.out_off = cand_rows + m; items.push_back(t); }
+      cand_rows += nA;
+    }
+  }
+  if (items.size() > g_scr.items_cap) { MM_CUDA(g_scr.items.alloc(items.size())); g_scr.items_cap = items.size(); }
+  if (rjobs.size() > g_scr.jobs_cap) { MM_CUDA(g_scr.jobs.alloc(rjobs.size())); g_scr.jobs_cap = rjobs.size(); }
+  if ((size_t)cand_rows > g_scr.cand_cap) { MM_CUDA(g_scr.cand.alloc((size_t)cand_rows)); g_scr.cand_cap = (size_t)cand_rows; MM_CUDA(g_scr.flagged.alloc(2 * (size_t)cand_rows + 2)); }
+  if (!g_scr.n_flagged.p) MM_CUDA(g_scr.n_flagged.alloc(1));
+  // knn21 jobs were tagged with a negative offset: split the re-rank into the two output arrays
+  std::vector<RerankJob> j12, j21;
+  for (auto& r : rjobs) { if (r.knn_off >= 0) j12.push_back(r); else { RerankJob t = r; t.knn_off = -r.knn_off - 1; j21.push_back(t); } }
+  std::vector<RerankJob> all = j12; all.insert(all.end(), j21.begin(), j21.end());
+  MM_CUDA(cudaMemcpyAsync(g_scr.jobs.p, all.data(), sizeof(RerankJob) * all.size(), cudaMemcpyHostToDevice, st));
+  // candidates of rows with nB == 0 are never written: give them empty lists
+  MM_CUDA(cudaMemsetAsync(g_scr.cand.p, 0xFF, sizeof(TcCand) * (size_t)cand_rows, st));
+  if (!items.empty()) {
+    MM_CUDA(cudaMemcpyAsync(g_scr.items.p, items.data(), sizeof(TcItem) * items.size(), cudaMemcpyHostToDevice, st));
+    const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 + 256 + (size_t)TC_M * TC_C * 8;
+    static bool configured = false;
+    if (!configured) { MM_CUDA(cudaFuncSetAttribute(k_match_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
+    const int grid = std::min((int)items.size(), num_sms());
+    k_match_tc<<<grid, TC_THREADS, smem, st>>>(P->mapA, P->mapB, g_scr.items.p, (int)items.size(), P->Kp / TC_KB, g_scr.cand.p);
+    MM_LAUNCH_CHECK();
+  }
+  MM_CUDA(cudaMemsetAsync(g_scr.n_flagged.p, 0, sizeof(int), st));
+  const int flag_cap = (int)cand_rows;
+  int max_nA = 1; for (auto& r : all) max_nA = std::max(max_nA, r.nA);
+  if (!j12.empty()) {
+    k_rerank<<<dim3((max_nA + 127) / 128, (unsigned)j12.size()), 128, 0, st>>>(g_scr.jobs.p, desc, P->norms.p, K, g_scr.cand.p, knn12, g_scr.flagged.p, g_scr.n_flagged.p, flag_cap);
+    MM_LAUNCH_CHECK();
+    k_rescan<<<num_sms() * 2, 256, 0, st>>>(g_scr.jobs.p, desc, K, g_scr.flagged.p, g_scr.n_flagged.p, flag_cap, knn12);
+    MM_LAUNCH_CHECK();
+  }
+  int nf12 = 0;
+  MM_CUDA(cudaMemcpyAsync(&nf12, g_scr.n_flagged.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (!j21.empty()) {
+    MM_CUDA(cudaMemsetAsync(g_scr.n_flagged.p, 0, sizeof(int), st));
+    k_rerank<<<dim3((max_nA + 127) / 128, (unsigned)j21.size()), 128, 0, st>>>(g_scr.jobs.p + j12.size(), desc, P->norms.p, K, g_scr.cand.p, knn21, g_scr.flagged.p, g_scr.n_flagged.p, flag_cap);
+    MM_LAUNCH_CHECK();
+    k_rescan<<<num_sms() * 2, 256, 0, st>>>(g_scr.jobs.p + j12.size(), desc, K, g_scr.flagged.p, g_scr.n_flagged.p, flag_cap, knn21);
+    MM_LAUNCH_CHECK();
+  }
+  g_tc_rows.fetch_add((uint64_t)cand_rows);
+  if (getenv("MM_MATCH_TC_STATS")) {
+    int nf21 = 0; MM_CUDA(cudaMemcpyAsync(&nf21, g_scr.n_flagged.p, sizeof(int), cudaMemcpyDeviceToHost, st)); MM_CUDA(cudaStreamSynchronize(st));
+    g_tc_flagged.fetch_add((uint64_t)nf12 + (uint64_t)nf21);
+    fprintf(stderr, "[match_tc] rows %lld flagged for exact rescan: %d + %d\n", (long long)cand_rows, nf12, nf21);
+  }
+  return MM_OK;
+}
+
 }  // namespace mm
