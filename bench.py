@@ -252,16 +252,19 @@ def main():
         np_ = len(mine)
         cnt = torch.zeros(np_, dtype=torch.int32, device="cuda"); qd = torch.empty(np_ * n_feat, dtype=torch.int32, device="cuda")
         td = torch.empty_like(qd); dd = torch.empty(np_ * n_feat, dtype=torch.float32, device="cuda")
-        run = lambda: ms_set.match_pairs_device(mine, cnt.data_ptr(), qd.data_ptr(), td.data_ptr(), dd.data_ptr(), n_feat, stream, True, 0.9, -1)
+        def run():
+            ms_set.match_pairs_device(mine, cnt.data_ptr(), qd.data_ptr(), td.data_ptr(), dd.data_ptr(), n_feat, stream, True, 0.9, -1)
+            if world > 1:        # the one exchange step of the sharded path: gather counts + packed match lists over NCCL/NVLink
+                dist.all_gather_into_tensor(g_cnt, cnt)
+                dist.all_gather_into_tensor(g_q, qd); dist.all_gather_into_tensor(g_t, td); dist.all_gather_into_tensor(g_d, dd)
+        if world > 1:
+            g_cnt = torch.empty(world * np_, dtype=torch.int32, device="cuda"); g_q = torch.empty(world * qd.numel(), dtype=torch.int32, device="cuda")
+            g_t = torch.empty_like(g_q); g_d = torch.empty(world * dd.numel(), dtype=torch.float32, device="cuda")
         run(); barrier()
         lm0 = _lib.kernel_launch_count()
         e0.record(); run(); e1.record(); barrier()
         mms = max_over_ranks(e0.elapsed_time(e1))
         m_launch = _lib.kernel_launch_count() - lm0
-        # gather of the match lists (counts + packed lists) over NCCL/NVLink
-        if world > 1:
-            counts = [torch.zeros_like(cnt) for _ in range(world)]
-            dist.all_gather(counts, cnt)
         pairs_s = len(pairs_all) / (mms * 1e-3)
         flops = 2.0 * n_feat * n_feat * kdim
         # e2e: host descriptors per pair (H2D 2 x n x k x 4 B, D2H the match list)

@@ -93,6 +93,11 @@ int mm_triangulate_two_view(const double* P1, const double* P2, int64_t n,
                             double* reproj1, double* reproj2,
                             double* depth1, double* depth2, double* angle);
 
+/* calc_reproj_errors (projection.cc:107-130) and calc_depth (projection.cc:133-149) for given 3-D points
+ * (the continued-track filter of sequential_mapper.cc:767-777).  x2d [n*2] normalised coordinates, X [n*3];
+ * err and depth are [n]; either output may be NULL.  Host buffers. */
+int mm_reproj_errors(const double* P, int64_t n, const double* x2d, const double* X, double* err, double* depth);
+
 /* ---- brute-force descriptor matching (feature.cc:52-133) ------------------ */
 #define MM_MATCH_IMPL_AUTO    0   /* tcgen05 tensor-core path when shapes allow */
 #define MM_MATCH_IMPL_SIMT    1   /* exact CUDA-core path (verification mode)   */

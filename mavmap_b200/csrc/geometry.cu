@@ -145,6 +145,15 @@ __global__ void k_triangulate(Proj p1, Proj p2, double c1x, double c1y, double c
   }
 }
 
+__global__ void k_reproj(Proj p, int64_t n, const double* __restrict__ x, const double* __restrict__ X, double* __restrict__ err, double* __restrict__ depth) {
+  const double* P = p.P;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double Xi[3] = { X[3 * i], X[3 * i + 1], X[3 * i + 2] };
+    if (err) err[i] = reproj_err(P, Xi, x[2 * i], x[2 * i + 1]);
+    if (depth) depth[i] = (P[8] * Xi[0] + P[9] * Xi[1] + P[10] * Xi[2] + P[11]) * sqrt(P[2] * P[2] + P[6] * P[6] + P[10] * P[10]);
+  }
+}
+
 static void camera_center(const double* P, double* C) {       // projection.cc:82-88 translation column
   const double a = P[0], b = P[1], c = P[2], d = P[4], e = P[5], f = P[6], g = P[8], h = P[9], i = P[10];
   const double A = e * i - f * h, B = -(d * i - f * g), Cc = d * h - e * g;
@@ -246,6 +255,22 @@ int mm_triangulate_two_view(const double* P1, const double* P2, int64_t n, const
   MM_LAUNCH_CHECK();
   MM_CUDA(cudaMemcpy(X, dX, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost));
   for (int k = 0; k < 5; ++k) if (host_out[k]) MM_CUDA(cudaMemcpy(host_out[k], dev_out[k], sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+  return MM_OK;
+}
+
+int mm_reproj_errors(const double* P, int64_t n, const double* x2d, const double* X, double* err, double* depth) {
+  if (n < 0 || !P || (n > 0 && (!X || (err && !x2d)))) { set_error("invalid argument"); return MM_ERR_INVALID_ARG; }
+  int rc = ensure_device(); if (rc != MM_OK) return rc;
+  if (n == 0 || (!err && !depth)) return MM_OK;
+  Proj p; memcpy(p.P, P, sizeof p.P);
+  DevBuf<double> buf; MM_CUDA(buf.alloc((size_t)n * 7));
+  double* dx = buf.p; double* dX = dx + 2 * n; double* de = dX + 3 * n; double* dd = de + n;
+  if (err) MM_CUDA(cudaMemcpy(dx, x2d, sizeof(double) * 2 * (size_t)n, cudaMemcpyHostToDevice));
+  MM_CUDA(cudaMemcpy(dX, X, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice));
+  k_reproj<<<grid_for(n, 128), 128>>>(p, n, dx, dX, err ? de : nullptr, depth ? dd : nullptr);
+  MM_LAUNCH_CHECK();
+  if (err) MM_CUDA(cudaMemcpy(err, de, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+  if (depth) MM_CUDA(cudaMemcpy(depth, dd, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
   return MM_OK;
 }
 

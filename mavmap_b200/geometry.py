@@ -77,3 +77,22 @@ def triangulate_points(proj_matrix1, proj_matrix2, points1, points2):
 
 def calc_tri_angles(proj_matrix1, proj_matrix2, points1, points2):
     return triangulate_two_view(proj_matrix1, proj_matrix2, points1, points2)["angle"]
+
+
+def calc_reproj_errors(points2D, points3D, proj_matrix):
+    """calc_reproj_errors (projection.cc:107-130): ||pi(P X) - x|| on the normalised plane."""
+    P = np.ascontiguousarray(proj_matrix, dtype=np.float64).reshape(3, 4)
+    x = np.ascontiguousarray(points2D, dtype=np.float64).reshape(-1, 2)
+    X = np.ascontiguousarray(points3D, dtype=np.float64).reshape(-1, 3)
+    err = np.empty(len(X))
+    check(lib().mm_reproj_errors(as_ptr(P, p_f64), len(X), as_ptr(x, p_f64), as_ptr(X, p_f64), as_ptr(err, p_f64), None))
+    return err
+
+
+def calc_depth(proj_matrix, points3D):
+    """calc_depth (projection.cc:133-149), batched over points."""
+    P = np.ascontiguousarray(proj_matrix, dtype=np.float64).reshape(3, 4)
+    X = np.ascontiguousarray(points3D, dtype=np.float64).reshape(-1, 3)
+    d = np.empty(len(X))
+    check(lib().mm_reproj_errors(as_ptr(P, p_f64), len(X), None, as_ptr(X, p_f64), None, as_ptr(d, p_f64)))
+    return d

@@ -1,0 +1,88 @@
+// Exercises the C++ drop-in shim (mavmap_b200/shim) exactly as sequential_mapper.cc calls the reference:
+// bundle_adjustment(), pose_refinement(), match_brute_force(), triangulate_points(), calc_*.
+// Prints one line per check; exit code 0 iff all pass.  Built by tests/test_shim.py.
+#include <cmath>
+#include <cstdio>
+#include <random>
+#include <set>
+#include <stdexcept>
+#include "base3d/bundle_adjustment.h"
+#include <opencv2/core/core.hpp>
+
+void match_brute_force(const std::vector<cv::KeyPoint>&, const cv::Mat&, const std::vector<cv::KeyPoint>&, const cv::Mat&,
+                       std::vector<cv::DMatch>&, const bool ratio_test = true, const double max_ratio = 0.6,
+                       const double max_distance = -1, const int norm_type = cv::NORM_L2);
+std::vector<Eigen::Vector3d> triangulate_points(const Eigen::Matrix<double, 3, 4>&, const Eigen::Matrix<double, 3, 4>&,
+                                                const std::vector<Eigen::Vector2d>&, const std::vector<Eigen::Vector2d>&);
+std::vector<double> calc_reproj_errors(const std::vector<Eigen::Vector2d>&, const std::vector<Eigen::Vector3d>&, const Eigen::Matrix<double, 3, 4>&);
+double calc_depth(const Eigen::Matrix<double, 3, 4>&, const Eigen::Vector3d&);
+
+static int fails = 0;
+#define CHECK(cond, what) do { const bool ok_ = (cond); std::printf("%s %s\n", ok_ ? "ok  " : "FAIL", what); if (!ok_) ++fails; } while (0)
+
+int main() {
+  std::mt19937 rng(7); std::normal_distribution<double> N(0.0, 1.0); std::uniform_real_distribution<double> U(-1.0, 1.0);
+  // ---- a 4-image scene, pinhole, exact observations + 0.3 px noise
+  FeatureManager fm;
+  const size_t cam = fm.add_camera({1000.0, 1000.0, 640.0, 480.0, 1});
+  const int n_pt = 80, n_img = 4;
+  std::vector<Eigen::Vector3d> X(n_pt);
+  for (auto& x : X) x = Eigen::Vector3d(2 * U(rng), 2 * U(rng), 10 + 2 * U(rng));
+  std::vector<size_t> ids;
+  for (int i = 0; i < n_img; ++i) {
+    const double tx = 0.5 * i;
+    std::vector<Eigen::Vector2d> uv(n_pt);
+    for (int p = 0; p < n_pt; ++p) uv[p] = Eigen::Vector2d(1000 * (X[p](0) + tx) / X[p](2) + 640 + 0.3 * N(rng), 1000 * X[p](1) / X[p](2) + 480 + 0.3 * N(rng));
+    const size_t id = fm.add_image(cam, uv);
+    fm.rvecs[id] = Eigen::Vector3d(0.003 * N(rng), 0.003 * N(rng), 0.003 * N(rng));
+    fm.tvecs[id] = Eigen::Vector3d(tx + 0.02 * N(rng), 0.02 * N(rng), 0.02 * N(rng));
+    ids.push_back(id);
+  }
+  for (int p = 0; p < n_pt; ++p) {
+    const size_t pid = fm.add_point3D();
+    fm.points3D[pid] = Eigen::Vector3d(X[p](0) + 0.05 * N(rng), X[p](1) + 0.05 * N(rng), X[p](2) + 0.05 * N(rng));
+    for (size_t id : ids) fm.point2D_to_point3D[fm.image_to_points2D[id][p]] = pid;
+  }
+  BundleAdjustmentOptions opt; opt.print_summary = false; opt.update_point3D_errors = true; opt.max_num_iterations = 30;
+  std::unordered_map<size_t, double> errs;
+  const Eigen::Vector3d r0 = fm.rvecs[ids[0]];
+  const double cost = bundle_adjustment(fm, {ids[2], ids[3]}, {ids[0]}, {ids[1]}, opt, errs);
+  CHECK(cost > 0.05 && cost < 0.6, "bundle_adjustment returns sqrt(final_cost/num_residuals) ~ noise level");
+  CHECK(fm.rvecs[ids[0]](0) == r0(0) && fm.rvecs[ids[0]](1) == r0(1), "FIXED pose untouched");
+  CHECK(errs.size() == (size_t)n_pt, "point3D_errors filled for every point in the problem");
+  bool threw = false;
+  try { bundle_adjustment(fm, {ids[1], ids[2], ids[3]}, {ids[0]}, {}, opt, errs); } catch (const std::invalid_argument&) { threw = true; }
+  CHECK(threw, "std::invalid_argument for < 7 fixed parameters (bundle_adjustment.cc:459-466)");
+  opt.min_track_len = 1; threw = false;
+  try { bundle_adjustment(fm, {ids[2], ids[3]}, {ids[0]}, {ids[1]}, opt, errs); } catch (const std::invalid_argument&) { threw = true; }
+  CHECK(threw, "std::invalid_argument for min_track_len < 2 (bundle_adjustment.cc:468-471)");
+  // ---- pose refinement
+  std::vector<Eigen::Vector2d> p2; std::vector<Eigen::Vector3d> p3; std::vector<bool> mask;
+  for (int p = 0; p < n_pt; ++p) { p2.push_back(Eigen::Vector2d(1000 * (X[p](0) + 0.7) / X[p](2) + 640, 1000 * (X[p](1) - 0.2) / X[p](2) + 480)); p3.push_back(X[p]); mask.push_back(p % 9 != 0); }
+  Eigen::Vector3d rv(0.01, -0.01, 0.005), tv(0.65, -0.15, 0.05);
+  std::vector<double> cp = {1000.0, 1000.0, 640.0, 480.0, 1};
+  BundleAdjustmentOptions po; po.print_summary = false; po.function_tolerance = 1e-12;
+  const double pc = pose_refinement(rv, tv, cp, p2, p3, mask, po);
+  CHECK(pc < 1e-6 && std::fabs(tv(0) - 0.7) < 1e-6 && std::fabs(tv(1) + 0.2) < 1e-6 && std::fabs(rv(0)) < 1e-7, "pose_refinement recovers the exact pose");
+  // ---- matching
+  const int nd = 300, kd = 64;
+  cv::Mat d1(nd, kd), d2(nd, kd);
+  for (int i = 0; i < nd; ++i) for (int k = 0; k < kd; ++k) { d1.ptr<float>(i)[k] = (float)N(rng); d2.ptr<float>((i * 7) % nd)[k] = d1.ptr<float>(i)[k] + 0.05f * (float)N(rng); }
+  std::vector<cv::KeyPoint> kp1(nd), kp2(nd); std::vector<cv::DMatch> matches;
+  match_brute_force(kp1, d1, kp2, d2, matches, true, 0.9, -1, cv::NORM_L2);
+  bool all_ok = matches.size() == (size_t)nd;
+  for (const auto& m : matches) all_ok = all_ok && m.trainIdx == (m.queryIdx * 7) % nd && m.imgIdx == 0;
+  CHECK(all_ok, "match_brute_force finds the planted permutation, ascending queryIdx");
+  // ---- triangulation + filters
+  Eigen::Matrix<double, 3, 4> P1, P2; for (int i = 0; i < 3; ++i) { P1(i, i) = 1; P2(i, i) = 1; } P2(0, 3) = -1.0;
+  std::vector<Eigen::Vector2d> x1, x2;
+  for (int p = 0; p < n_pt; ++p) { x1.push_back(Eigen::Vector2d(X[p](0) / X[p](2), X[p](1) / X[p](2))); x2.push_back(Eigen::Vector2d((X[p](0) - 1) / X[p](2), X[p](1) / X[p](2))); }
+  const std::vector<Eigen::Vector3d> T = triangulate_points(P1, P2, x1, x2);
+  double worst = 0; for (int p = 0; p < n_pt; ++p) for (int c = 0; c < 3; ++c) worst = std::fmax(worst, std::fabs(T[p](c) - X[p](c)));
+  CHECK(worst < 1e-9, "triangulate_points recovers the points (triangulation_test.cc tolerance class)");
+  const std::vector<double> re = calc_reproj_errors(x2, T, P2);
+  double wre = 0; for (double e : re) wre = std::fmax(wre, e);
+  CHECK(wre < 1e-10 && std::fabs(calc_depth(P2, T[0]) - X[0](2)) < 1e-9, "calc_reproj_errors / calc_depth");
+  std::printf("%d failure(s)\n", fails);
+  return fails ? 1 : 0;
+}

@@ -1,0 +1,36 @@
+"""The C++ drop-in shim (mavmap_b200/shim): compiles against stand-in Eigen/OpenCV/FeatureManager
+headers (none of the real ones are in the image) and, on a GPU, runs the reference-style calls."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+SHIM = os.path.join(ROOT, "mavmap_b200", "shim")
+EXE = os.path.join(ROOT, "build", "shim_test")
+
+
+def build_shim_test():
+    os.makedirs(os.path.dirname(EXE), exist_ok=True)
+    lib_dir = os.path.join(ROOT, "mavmap_b200")
+    cmd = ["/usr/bin/g++", "-std=c++11", "-O1", "-Wall", "-I" + os.path.join(ROOT, "tests", "stubs"), "-I" + SHIM, "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "shim_test.cc"), os.path.join(SHIM, "base3d", "bundle_adjustment.cc"),
+           os.path.join(SHIM, "base3d", "triangulation.cc"), os.path.join(SHIM, "base2d", "feature_match.cc"),
+           "-L" + lib_dir, "-lmavmap_b200", "-Wl,-rpath," + lib_dir, "-o", EXE]
+    subprocess.check_call(cmd)
+    return EXE
+
+
+def test_shim_compiles_and_links_against_the_c_abi():
+    exe = build_shim_test()
+    assert os.path.exists(exe)
+
+
+@pytest.mark.gpu
+def test_shim_runs_reference_style_calls(mm):
+    exe = build_shim_test()
+    out = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    print(out.stdout)
+    assert out.returncode == 0, out.stdout
+    assert out.stdout.count("ok  ") >= 9 and "FAIL" not in out.stdout
