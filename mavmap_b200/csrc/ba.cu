@@ -81,6 +81,21 @@ __global__ void k_csr_rows(int64_t n, int n_img, const unsigned long long* __res
     atomicAdd(cnt + (int)(k / n_img), 1);
   }
 }
+// spatial proxy key of a point: (smallest, largest) index of the images that see it — images follow the flight path
+__global__ void k_pt_minmax(int64_t n, const int* __restrict__ img, const int* __restrict__ pt, int* __restrict__ mn, int* __restrict__ mx) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) { atomicMin(mn + pt[i], img[i]); atomicMax(mx + pt[i], img[i]); }
+}
+__global__ void k_pt_key(int n_pt, int n_img, const int* __restrict__ mn, const int* __restrict__ mx, unsigned long long* __restrict__ key) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n_pt) key[p] = (unsigned long long)mn[p] * (unsigned long long)(n_img + 1) + (unsigned long long)(mx[p] < 0 ? n_img : mx[p]);
+}
+__global__ void k_invert_perm(int n, const int* __restrict__ new2old, int* __restrict__ old2new) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) old2new[new2old[i]] = i;
+}
+__global__ void k_remap(int64_t n, const int* __restrict__ old2new, int* __restrict__ pt) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) pt[i] = old2new[pt[i]];
+}
+__global__ void k_fill_int(int n, int* p, int v) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
 __global__ void k_fill(int64_t n, double* p, double v) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -99,6 +114,7 @@ struct mm_ba_session {
   int n_img = 0, n_cam = 0, n_pt = 0; int64_t n_obs = 0;
   int n_off = 0; int64_t nblk = 0, n_pairs = 0, n_ent = 0;
   std::vector<double> h_poses0, h_intr0, h_pts0;
+  std::vector<double> h_pt_mask; std::vector<int> h_pt_new2old; unsigned long long spread = 1;         // internal point order (spatially clustered) -> caller's order
   DevBuf<double2> obs_xy; DevBuf<int> obs_img, obs_pt, pt_start, cam_perm, cam_start, img_cam, cam_model;
   DevBuf<int64_t> pair_off; DevBuf<int> pair_blk, row_start, row_col, row_blk;
   DevBuf<double> S, Minv, poses, intr, pts, poses2, pts2, aux, aux2, rec;
@@ -179,6 +195,25 @@ int build_structure(mm_ba_session* s, const mm_ba_problem* P) {
   MM_CUDA(cudaMemcpyAsync(pt_in.p, P->obs_pt, sizeof(int) * n, cudaMemcpyHostToDevice, st));
   MM_CUDA(s->obs_xy.alloc(n)); MM_CUDA(s->obs_img.alloc(n)); MM_CUDA(s->obs_pt.alloc(n));
   MM_CUDA(s->pt_start.alloc((size_t)n_pt + 1)); MM_CUDA(s->cam_start.alloc((size_t)n_img + 1)); MM_CUDA(s->cam_perm.alloc(n));
+  // 0. renumber the points so that points seen by the same images are neighbours: gives the per-image gathers of
+  //    K1/K2b/K4 and the atomics of K2a cache locality.  The caller's numbering is restored on download.
+  s->h_pt_new2old.resize((size_t)n_pt);
+  if (n > 0 && n_pt > 1 && !getenv("MM_BA_NO_REORDER")) {
+    DevBuf<int> mn, mx, ids, new2old, old2new; DevBuf<unsigned long long> key, key_s;
+    MM_CUDA(mn.alloc(n_pt)); MM_CUDA(mx.alloc(n_pt)); MM_CUDA(ids.alloc(n_pt)); MM_CUDA(new2old.alloc(n_pt)); MM_CUDA(old2new.alloc(n_pt)); MM_CUDA(key.alloc(n_pt)); MM_CUDA(key_s.alloc(n_pt));
+    k_fill_int<<<blocks_for(n_pt, B), B, 0, st>>>(n_pt, mn.p, n_img); MM_LAUNCH_CHECK();
+    k_fill_int<<<blocks_for(n_pt, B), B, 0, st>>>(n_pt, mx.p, -1); MM_LAUNCH_CHECK();
+    k_pt_minmax<<<grid_stride(n, B), B, 0, st>>>(n, img_in.p, pt_in.p, mn.p, mx.p); MM_LAUNCH_CHECK();
+    k_pt_key<<<blocks_for(n_pt, B), B, 0, st>>>(n_pt, n_img, mn.p, mx.p, key.p); MM_LAUNCH_CHECK();
+    k_iota<<<blocks_for(n_pt, B), B, 0, st>>>(n_pt, ids.p); MM_LAUNCH_CHECK();
+    int rc = sort_pairs<unsigned long long, int>(st, key.p, key_s.p, ids.p, new2old.p, n_pt, bits_for((unsigned long long)(n_img + 1) * (unsigned long long)(n_img + 1))); if (rc) return rc;
+    k_invert_perm<<<blocks_for(n_pt, B), B, 0, st>>>(n_pt, new2old.p, old2new.p); MM_LAUNCH_CHECK();
+    k_remap<<<grid_stride(n, B), B, 0, st>>>(n, old2new.p, pt_in.p); MM_LAUNCH_CHECK();
+    MM_CUDA(cudaMemcpyAsync(s->h_pt_new2old.data(), new2old.p, sizeof(int) * (size_t)n_pt, cudaMemcpyDeviceToHost, st));
+    MM_CUDA(cudaStreamSynchronize(st));
+  } else {
+    for (int p = 0; p < n_pt; ++p) s->h_pt_new2old[p] = p;
+  }
   if (n > 0) {
     k_iota<<<blocks_for(n, B), B, 0, st>>>((int)n, iota.p); MM_LAUNCH_CHECK();
     // 1. stable sort by point (keeps the caller's order inside a track)
@@ -246,7 +281,9 @@ int upload_params(mm_ba_session* s) {
   cudaStream_t st = s->stream;
   MM_CUDA(cudaMemcpyAsync(s->poses.p, s->h_poses0.data(), sizeof(double) * 6 * (size_t)s->n_img, cudaMemcpyHostToDevice, st));
   MM_CUDA(cudaMemcpyAsync(s->intr.p, s->h_intr0.data(), sizeof(double) * MM_INTR_STRIDE * (size_t)s->n_cam, cudaMemcpyHostToDevice, st));
-  MM_CUDA(cudaMemcpyAsync(s->pts.p, s->h_pts0.data(), sizeof(double) * 3 * (size_t)s->n_pt, cudaMemcpyHostToDevice, st));
+  { std::vector<double> tmp(3 * (size_t)s->n_pt);
+    for (int p = 0; p < s->n_pt; ++p) { const size_t o = (size_t)s->h_pt_new2old[p]; tmp[3 * (size_t)p] = s->h_pts0[3 * o]; tmp[3 * (size_t)p + 1] = s->h_pts0[3 * o + 1]; tmp[3 * (size_t)p + 2] = s->h_pts0[3 * o + 2]; }
+    MM_CUDA(cudaMemcpy(s->pts.p, tmp.data(), sizeof(double) * 3 * (size_t)s->n_pt, cudaMemcpyHostToDevice)); }
   return MM_OK;
 }
 
@@ -258,7 +295,7 @@ LMDiag lm_of(const mm_ba_session* s) { LMDiag d; d.radius = s->radius; d.min_dia
 // K1 at the current iterate: records + cost -> red[0]
 int launch_linearize(mm_ba_session* s) {
   cudaStream_t st = s->stream;
-  k_pose_aux<<<blocks_for(s->n_img, 128), 128, 0, st>>>(s->n_img, s->poses.p, s->aux.p); MM_LAUNCH_CHECK();
+  k_pose_aux<<<blocks_for(s->n_img, 128), 128, 0, st>>>(s->n_img, s->poses.p, s->pose_mask.p, s->aux.p); MM_LAUNCH_CHECK();
   k_residual_jacobian<true><<<s->grid_obs, 256, 0, st>>>(s->n_obs, s->obs_xy.p, s->obs_img.p, s->obs_pt.p, s->aux.p, s->pts.p, s->intr.p,
       s->img_cam.p, s->cam_model.p, s->pose_mask.p, s->pt_mask.p, loss_of(s->opt), s->rec.p, s->part_cost.p); MM_LAUNCH_CHECK();
   k_reduce_sum<<<1, 256, 0, st>>>(s->part_cost.p, s->grid_obs, s->red.p + 0); MM_LAUNCH_CHECK();
@@ -267,7 +304,7 @@ int launch_linearize(mm_ba_session* s) {
 // K4: cost at the candidate (poses2/pts2) -> red[1]
 int launch_cost_candidate(mm_ba_session* s) {
   cudaStream_t st = s->stream;
-  k_pose_aux<<<blocks_for(s->n_img, 128), 128, 0, st>>>(s->n_img, s->poses2.p, s->aux2.p); MM_LAUNCH_CHECK();
+  k_pose_aux<<<blocks_for(s->n_img, 128), 128, 0, st>>>(s->n_img, s->poses2.p, s->pose_mask.p, s->aux2.p); MM_LAUNCH_CHECK();
   k_residual_jacobian<false><<<s->grid_obs, 256, 0, st>>>(s->n_obs, s->obs_xy.p, s->obs_img.p, s->obs_pt.p, s->aux2.p, s->pts2.p, s->intr.p,
       s->img_cam.p, s->cam_model.p, s->pose_mask.p, s->pt_mask.p, loss_of(s->opt), nullptr, s->part_cost.p); MM_LAUNCH_CHECK();
   k_reduce_sum<<<1, 256, 0, st>>>(s->part_cost.p, s->grid_obs, s->red.p + 1); MM_LAUNCH_CHECK();
@@ -288,7 +325,7 @@ int launch_schur(mm_ba_session* s) {
   MM_CUDA(cudaMemsetAsync(s->red.p + 2, 0, sizeof(double), st));
   const LMDiag lm = lm_of(s);
   k_schur_point<<<blocks_for(s->n_pt, 128), 128, 0, st>>>(s->n_pt, s->pt_start.p, s->obs_img.p, s->rec.p, s->scale_c.p, s->scale_p.p, lm,
-      s->pair_off.p, s->pair_blk.p, s->S.p, s->Vinv.p, s->gp.p, s->dp.p, s->red.p + 2, s->fail.p); MM_LAUNCH_CHECK();
+      s->pair_off.p, s->pair_blk.p, s->S.p, s->Vinv.p, s->gp.p, s->dp.p, s->red.p + 2, s->fail.p, s->spread); MM_LAUNCH_CHECK();
   k_schur_cam<<<blocks_for((int64_t)s->n_img * 32, 128), 128, 0, st>>>(s->n_img, s->cam_start.p, s->cam_perm.p, s->obs_pt.p, s->rec.p,
       s->scale_c.p, s->scale_p.p, s->Vinv.p, s->gp.p, lm, s->S.p, s->rhs.p, s->gc.p, s->dc.p, s->red.p + 2); MM_LAUNCH_CHECK();
   k_precond<<<blocks_for(s->n_img, 64), 64, 0, st>>>(s->n_img, s->S.p, s->Minv.p, s->fail.p); MM_LAUNCH_CHECK();
@@ -532,19 +569,25 @@ int mm_ba_session_create(const mm_ba_problem* P, const mm_ba_options* opt, void*
   // masks: 1.0 = free and present in at least one residual block
   { std::vector<int> img_n(n_img, 0), pt_n(n_pt, 0);
     for (int64_t o = 0; o < P->n_obs; ++o) { img_n[P->obs_img[o]]++; pt_n[P->obs_pt[o]]++; }
-    std::vector<double> pm(6 * n_img, 0.0), tm(n_pt, 0.0);
+    std::vector<double> pm(6 * n_img, 0.0); std::vector<double>& tm = s->h_pt_mask; tm.assign(n_pt, 0.0);
     for (int i = 0; i < P->n_img; ++i) if (img_n[i]) {
       for (int k = 0; k < 3; ++k) pm[6 * (size_t)i + k] = P->pose_const[4 * (size_t)i] ? 0.0 : 1.0;
       for (int k = 0; k < 3; ++k) pm[6 * (size_t)i + 3 + k] = P->pose_const[4 * (size_t)i + 1 + k] ? 0.0 : 1.0;
     }
     for (int p = 0; p < P->n_pt; ++p) if (pt_n[p] && !P->pt_const[p]) tm[p] = 1.0;
     if (cudaMemcpy(s->pose_mask.p, pm.data(), sizeof(double) * pm.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMemcpy(s->pt_mask.p, tm.data(), sizeof(double) * tm.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(s->img_cam.p, P->img_cam, sizeof(int) * (size_t)P->n_img, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(s->cam_model.p, P->cam_model, sizeof(int) * (size_t)P->n_cam, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("mask upload failed"); return fail_out(MM_ERR_CUDA); } }
   cudaMemsetAsync(s->fail.p, 0, sizeof(int), s->stream);
   cudaMemsetAsync(s->red.p, 0, sizeof(double) * 8, s->stream);
   rc = build_structure(s, P); if (rc) return fail_out(rc);
+  { // multiplier of the K2a point permutation: a prime near 0.38 * n_pt that does not divide n_pt
+    const unsigned long long primes[] = { 1000003ULL, 611953ULL, 382003ULL, 100003ULL, 38183ULL, 10007ULL, 3821ULL, 1009ULL, 383ULL, 101ULL, 37ULL, 7ULL, 1ULL };
+    s->spread = 1;
+    if (!getenv("MM_BA_NO_SPREAD")) for (unsigned long long q : primes) if (q < (unsigned long long)std::max(P->n_pt, 1) && (unsigned long long)P->n_pt % q != 0) { s->spread = q; break; } }
+  { std::vector<double> tmp((size_t)std::max(P->n_pt, 1), 0.0);
+    for (int p = 0; p < P->n_pt; ++p) tmp[p] = s->h_pt_mask[(size_t)s->h_pt_new2old[p]];
+    if (cudaMemcpy(s->pt_mask.p, tmp.data(), sizeof(double) * tmp.size(), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("mask upload failed"); return fail_out(MM_ERR_CUDA); } }
   A(s->S, 36 * (size_t)std::max<int64_t>(s->nblk, 1));
 #undef A
   rc = upload_params(s); if (rc) return fail_out(rc);
@@ -593,16 +636,23 @@ int mm_ba_session_download(mm_ba_session* s, double* poses, double* intr, double
   cudaStream_t st = s->stream;
   if (poses) MM_CUDA(cudaMemcpyAsync(poses, s->poses.p, sizeof(double) * 6 * (size_t)s->n_img, cudaMemcpyDeviceToHost, st));
   if (intr) MM_CUDA(cudaMemcpyAsync(intr, s->intr.p, sizeof(double) * MM_INTR_STRIDE * (size_t)s->n_cam, cudaMemcpyDeviceToHost, st));
-  if (pts) MM_CUDA(cudaMemcpyAsync(pts, s->pts.p, sizeof(double) * 3 * (size_t)s->n_pt, cudaMemcpyDeviceToHost, st));
+  if (pts && s->n_pt > 0) {
+    std::vector<double> tmp(3 * (size_t)s->n_pt);
+    MM_CUDA(cudaMemcpyAsync(tmp.data(), s->pts.p, sizeof(double) * 3 * (size_t)s->n_pt, cudaMemcpyDeviceToHost, st));
+    MM_CUDA(cudaStreamSynchronize(st));
+    for (int p = 0; p < s->n_pt; ++p) { const size_t o = (size_t)s->h_pt_new2old[p]; pts[3 * o] = tmp[3 * (size_t)p]; pts[3 * o + 1] = tmp[3 * (size_t)p + 1]; pts[3 * o + 2] = tmp[3 * (size_t)p + 2]; }
+  }
   if (pt_err && s->n_pt > 0 && s->n_obs > 0) {
     // Vinv is free between LM iterations: reuse it as the staging buffer for the per-point errors
-    std::vector<double> host(pt_err, pt_err + s->n_pt);
+    std::vector<double> host((size_t)s->n_pt);
+    for (int p = 0; p < s->n_pt; ++p) host[p] = pt_err[(size_t)s->h_pt_new2old[p]];
     MM_CUDA(cudaMemcpyAsync(s->Vinv.p, host.data(), sizeof(double) * (size_t)s->n_pt, cudaMemcpyHostToDevice, st));
-    k_pose_aux<<<blocks_for(s->n_img, 128), 128, 0, st>>>(s->n_img, s->poses.p, s->aux.p); MM_LAUNCH_CHECK();
+    k_pose_aux<<<blocks_for(s->n_img, 128), 128, 0, st>>>(s->n_img, s->poses.p, s->pose_mask.p, s->aux.p); MM_LAUNCH_CHECK();
     k_point_errors<<<blocks_for(s->n_pt, 128), 128, 0, st>>>(s->n_pt, s->pt_start.p, s->obs_xy.p, s->obs_img.p, s->aux.p, s->pts.p, s->intr.p,
         s->img_cam.p, s->cam_model.p, s->Vinv.p); MM_LAUNCH_CHECK();
-    MM_CUDA(cudaMemcpyAsync(pt_err, s->Vinv.p, sizeof(double) * (size_t)s->n_pt, cudaMemcpyDeviceToHost, st));
+    MM_CUDA(cudaMemcpyAsync(host.data(), s->Vinv.p, sizeof(double) * (size_t)s->n_pt, cudaMemcpyDeviceToHost, st));
     MM_CUDA(cudaStreamSynchronize(st));
+    for (int p = 0; p < s->n_pt; ++p) pt_err[(size_t)s->h_pt_new2old[p]] = host[p];
     // the Schur data must be rebuilt if the session continues
     if (!s->finished) { int rc = launch_schur(s); if (rc) return rc; }
   }

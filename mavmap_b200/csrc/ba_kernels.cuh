@@ -32,7 +32,7 @@ __device__ __forceinline__ void loss_eval(const LossParams& L, double s, double&
 }
 
 // ---- per-image rotation data ---------------------------------------------------------
-__global__ void k_pose_aux(int n_img, const double* __restrict__ poses, double* __restrict__ aux) {
+__global__ void k_pose_aux(int n_img, const double* __restrict__ poses, const double* __restrict__ pose_mask, double* __restrict__ aux) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_img) return;
   double R[9], Jl[9];
@@ -41,74 +41,105 @@ __global__ void k_pose_aux(int n_img, const double* __restrict__ poses, double* 
   double* a = aux + AUX * (size_t)i;
 #pragma unroll
   for (int k = 0; k < 9; ++k) { a[k] = R[k]; a[9 + k] = Jl[k]; }
-  a[18] = p[3]; a[19] = p[4]; a[20] = p[5]; a[21] = 0; a[22] = 0; a[23] = 0;
+  a[18] = p[3]; a[19] = p[4]; a[20] = p[5];
+  const double* m = pose_mask + 6 * (size_t)i;       // free-parameter masks ride along: [21] rvec, [22] tx + 2 ty + 4 tz
+  a[21] = m[0]; a[22] = m[3] + 2.0 * m[4] + 4.0 * m[5]; a[23] = 0;
 }
 
 // ---- K1: residual + Jacobian per observation -------------------------------------------
 // reads 24 B/obs (xy, img, pt) + gathered parameters, writes one 160 B record.
 // cost partial per block -> cost_part[blockIdx.x] (reduced deterministically afterwards).
 template <bool WITH_J>
-__global__ void __launch_bounds__(256) k_residual_jacobian(
+__global__ void __launch_bounds__(256, WITH_J ? 2 : 4) k_residual_jacobian(
     int64_t n_obs, const double2* __restrict__ obs_xy, const int* __restrict__ obs_img, const int* __restrict__ obs_pt,
     const double* __restrict__ aux, const double* __restrict__ pts, const double* __restrict__ intr,
     const int* __restrict__ img_cam, const int* __restrict__ cam_model,
     const double* __restrict__ pose_mask, const double* __restrict__ pt_mask,
     LossParams L, double* __restrict__ rec, double* __restrict__ cost_part) {
   __shared__ double red[32];
+  // records are staged per warp in shared memory (22-double pitch keeps 16-byte alignment) and written
+  // out as whole 512-byte runs: every store instruction of the warp covers contiguous global memory
+  constexpr int PITCH = 22;
+  __shared__ __align__(16) double stage[WITH_J ? 8 * 32 * PITCH : 2];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   double cost = 0.0;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_obs; i += (int64_t)gridDim.x * blockDim.x) {
-    const int img = obs_img[i], pt = obs_pt[i];
-    const double2 xy = obs_xy[i];
-    const double* a = aux + AUX * (size_t)img;
-    const double X0 = pts[3 * (size_t)pt], X1 = pts[3 * (size_t)pt + 1], X2 = pts[3 * (size_t)pt + 2];
-    double R[9];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + wib * 32; i0 < n_obs; i0 += stride) {
+    const int64_t i = i0 + lane;
+    const bool valid = i < n_obs;
+    if (valid) {
+      const int img = obs_img[i], pt = obs_pt[i];
+      const double2 xy = obs_xy[i];
+      // one 192-byte per-image record, fetched with 16-byte loads (R | Jl | t | masks)
+      const double2* a2 = reinterpret_cast<const double2*>(aux + AUX * (size_t)img);
+      double a[AUX];
+      if (WITH_J) {
 #pragma unroll
-    for (int k = 0; k < 9; ++k) R[k] = a[k];
-    const double Y0 = R[0] * X0 + R[1] * X1 + R[2] * X2;
-    const double Y1 = R[3] * X0 + R[4] * X1 + R[5] * X2;
-    const double Y2 = R[6] * X0 + R[7] * X1 + R[8] * X2;
-    const double xc = Y0 + a[18], yc = Y1 + a[19], zc = Y2 + a[20];
-    const int cam = img_cam[img];
-    const int model = cam_model[cam];
-    double u, v, dX[2][3];
-    world2image<WITH_J>(model, intr + MM_INTR_STRIDE * (size_t)cam, xc, yc, zc, u, v, dX, nullptr);
-    double r0 = u - xy.x, r1 = v - xy.y;
-    double rho0, sr;
-    loss_eval(L, r0 * r0 + r1 * r1, rho0, sr);
-    cost += 0.5 * rho0;
+        for (int k = 0; k < AUX / 2; ++k) { const double2 t = __ldg(a2 + k); a[2 * k] = t.x; a[2 * k + 1] = t.y; }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) { const double2 t = __ldg(a2 + k); a[2 * k] = t.x; a[2 * k + 1] = t.y; }
+#pragma unroll
+        for (int k = 9; k < 11; ++k) { const double2 t = __ldg(a2 + k); a[2 * k] = t.x; a[2 * k + 1] = t.y; }
+      }
+      const double X0 = pts[3 * (size_t)pt], X1 = pts[3 * (size_t)pt + 1], X2 = pts[3 * (size_t)pt + 2];
+      const double* R = a;
+      const double Y0 = R[0] * X0 + R[1] * X1 + R[2] * X2;
+      const double Y1 = R[3] * X0 + R[4] * X1 + R[5] * X2;
+      const double Y2 = R[6] * X0 + R[7] * X1 + R[8] * X2;
+      const double xc = Y0 + a[18], yc = Y1 + a[19], zc = Y2 + a[20];
+      const int cam = img_cam[img];
+      const int model = cam_model[cam];
+      double u, v, dX[2][3];
+      world2image<WITH_J>(model, intr + MM_INTR_STRIDE * (size_t)cam, xc, yc, zc, u, v, dX, nullptr);
+      const double r0 = u - xy.x, r1 = v - xy.y;
+      double rho0, sr;
+      loss_eval(L, r0 * r0 + r1 * r1, rho0, sr);
+      cost += 0.5 * rho0;
+      if (WITH_J) {
+        const double mp = pt_mask[pt] * sr;
+        const int mbits = (int)a[22];
+        const double mw = a[21] * sr, mx = (mbits & 1) ? sr : 0.0, my = (mbits & 2) ? sr : 0.0, mz = (mbits & 4) ? sr : 0.0;
+        double2* o2 = reinterpret_cast<double2*>(stage + (size_t)(wib * 32 + lane) * PITCH);
+        o2[0] = make_double2(sr * r0, sr * r1);
+        // d(Xc)/d(w) = -[Y]x Jl : column k = Jl[:,k] x Y
+        double M[3][3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double c0 = a[9 + k], c1 = a[12 + k], c2 = a[15 + k];
+          M[0][k] = c1 * Y2 - c2 * Y1; M[1][k] = c2 * Y0 - c0 * Y2; M[2][k] = c0 * Y1 - c1 * Y0;
+        }
+#pragma unroll
+        for (int row = 0; row < 2; ++row) {
+          const double d0 = dX[row][0], d1 = dX[row][1], d2 = dX[row][2];
+          const double jw0 = (d0 * M[0][0] + d1 * M[1][0] + d2 * M[2][0]) * mw;
+          const double jw1 = (d0 * M[0][1] + d1 * M[1][1] + d2 * M[2][1]) * mw;
+          const double jw2 = (d0 * M[0][2] + d1 * M[1][2] + d2 * M[2][2]) * mw;
+          o2[1 + 3 * row] = make_double2(jw0, jw1);
+          o2[2 + 3 * row] = make_double2(jw2, d0 * mx);
+          o2[3 + 3 * row] = make_double2(d1 * my, d2 * mz);
+        }
+        const double p00 = (dX[0][0] * R[0] + dX[0][1] * R[3] + dX[0][2] * R[6]) * mp;
+        const double p01 = (dX[0][0] * R[1] + dX[0][1] * R[4] + dX[0][2] * R[7]) * mp;
+        const double p02 = (dX[0][0] * R[2] + dX[0][1] * R[5] + dX[0][2] * R[8]) * mp;
+        const double p10 = (dX[1][0] * R[0] + dX[1][1] * R[3] + dX[1][2] * R[6]) * mp;
+        const double p11 = (dX[1][0] * R[1] + dX[1][1] * R[4] + dX[1][2] * R[7]) * mp;
+        const double p12 = (dX[1][0] * R[2] + dX[1][1] * R[5] + dX[1][2] * R[8]) * mp;
+        o2[7] = make_double2(p00, p01);
+        o2[8] = make_double2(p02, p10);
+        o2[9] = make_double2(p11, p12);
+      }
+    }
     if (WITH_J) {
-      double* out = rec + REC * (size_t)i;
-      const double* pm = pose_mask + 6 * (size_t)img;
-      const double mp = pt_mask[pt] * sr;
-      const double mw = pm[0] * sr, mx = pm[3] * sr, my = pm[4] * sr, mz = pm[5] * sr;
-      // d(Xc)/d(w) = -[Y]x Jl : column k = Jl[:,k] x Y
-      double M[3][3];
+      __syncwarp();
+      const int nvalid = (int)min((int64_t)32, n_obs - i0);
+      double2* g2 = reinterpret_cast<double2*>(rec + REC * (size_t)i0);
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const double c0 = a[9 + k], c1 = a[12 + k], c2 = a[15 + k];
-        M[0][k] = c1 * Y2 - c2 * Y1; M[1][k] = c2 * Y0 - c0 * Y2; M[2][k] = c0 * Y1 - c1 * Y0;
+      for (int k = 0; k < 10; ++k) {
+        const int c = k * 32 + lane, src = c / 10, part = c - 10 * src;
+        if (src < nvalid) g2[c] = *reinterpret_cast<const double2*>(stage + (size_t)(wib * 32 + src) * PITCH + 2 * part);
       }
-      double2* o2 = reinterpret_cast<double2*>(out);
-      o2[0] = make_double2(sr * r0, sr * r1);
-#pragma unroll
-      for (int row = 0; row < 2; ++row) {
-        const double d0 = dX[row][0], d1 = dX[row][1], d2 = dX[row][2];
-        const double jw0 = (d0 * M[0][0] + d1 * M[1][0] + d2 * M[2][0]) * mw;
-        const double jw1 = (d0 * M[0][1] + d1 * M[1][1] + d2 * M[2][1]) * mw;
-        const double jw2 = (d0 * M[0][2] + d1 * M[1][2] + d2 * M[2][2]) * mw;
-        o2[1 + 3 * row] = make_double2(jw0, jw1);
-        o2[2 + 3 * row] = make_double2(jw2, d0 * mx);
-        o2[3 + 3 * row] = make_double2(d1 * my, d2 * mz);
-      }
-      const double p00 = (dX[0][0] * R[0] + dX[0][1] * R[3] + dX[0][2] * R[6]) * mp;
-      const double p01 = (dX[0][0] * R[1] + dX[0][1] * R[4] + dX[0][2] * R[7]) * mp;
-      const double p02 = (dX[0][0] * R[2] + dX[0][1] * R[5] + dX[0][2] * R[8]) * mp;
-      const double p10 = (dX[1][0] * R[0] + dX[1][1] * R[3] + dX[1][2] * R[6]) * mp;
-      const double p11 = (dX[1][0] * R[1] + dX[1][1] * R[4] + dX[1][2] * R[7]) * mp;
-      const double p12 = (dX[1][0] * R[2] + dX[1][1] * R[5] + dX[1][2] * R[8]) * mp;
-      o2[7] = make_double2(p00, p01);
-      o2[8] = make_double2(p02, p10);
-      o2[9] = make_double2(p11, p12);
+      __syncwarp();
     }
   }
   cost = block_sum(cost, red);
@@ -192,9 +223,12 @@ __global__ void __launch_bounds__(128) k_schur_point(
     const double* __restrict__ scale_c, const double* __restrict__ scale_p, LMDiag lm,
     const int64_t* __restrict__ pair_off, const int* __restrict__ pair_blk,
     double* __restrict__ S, double* __restrict__ Vinv, double* __restrict__ gp_out, double* __restrict__ dp_out,
-    double* __restrict__ gmax, int* __restrict__ fail) {
+    double* __restrict__ gmax, int* __restrict__ fail, unsigned long long spread) {
   __shared__ double red[32];
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  // points are stored spatially clustered (good for the gathers elsewhere); here neighbouring threads take points that are
+  // far apart (multiplicative permutation, gcd(spread, n_pt) = 1) so that concurrent atomics hit different blocks of S
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = tid < n_pt ? (int)(((unsigned long long)tid * spread) % (unsigned long long)n_pt) : n_pt;
   double gm = 0.0;
   if (p < n_pt) {
     const int o0 = pt_start[p], o1 = pt_start[p + 1];
