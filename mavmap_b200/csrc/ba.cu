@@ -122,6 +122,9 @@ struct mm_ba_session {
   DevBuf<double> vx, vr, vz, vp0, vp1, vAp, pcg_sc; DevBuf<int> pcg_ic;
   DevBuf<double> part_cost, part_pt, part_cam, part_x, red;   // red: [0]=cost [1]=new_cost [2]=gmax [3]=step_norm2 [4]=mcc [5]=xnorm2
   DevBuf<int> fail; DevBuf<unsigned long long> pcg_dbg;
+  // refined intrinsics (single shared camera)
+  bool refine = false;
+  DevBuf<double> ji, intr2, intr_mask, scale_i, Apc, Bm, intr_acc, Cinv, gi, di, xi, zi, pi0, pi1, bt, sq9;
   int grid_obs = 1, grid_pt = 1, grid_cam6 = 1, grid_x = 1, pcg_grid = 0, pcg_ecap = 0, pcg_threads = 0; bool pcg_cached = false; size_t pcg_smem = 0; const void* pcg_fn = nullptr;
   cudaEvent_t evs[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // LM state (host)
@@ -281,6 +284,7 @@ int upload_params(mm_ba_session* s) {
   cudaStream_t st = s->stream;
   MM_CUDA(cudaMemcpyAsync(s->poses.p, s->h_poses0.data(), sizeof(double) * 6 * (size_t)s->n_img, cudaMemcpyHostToDevice, st));
   MM_CUDA(cudaMemcpyAsync(s->intr.p, s->h_intr0.data(), sizeof(double) * MM_INTR_STRIDE * (size_t)s->n_cam, cudaMemcpyHostToDevice, st));
+  MM_CUDA(cudaMemcpyAsync(s->intr2.p, s->h_intr0.data(), sizeof(double) * MM_INTR_STRIDE * (size_t)s->n_cam, cudaMemcpyHostToDevice, st));
   { std::vector<double> tmp(3 * (size_t)s->n_pt);
     for (int p = 0; p < s->n_pt; ++p) { const size_t o = (size_t)s->h_pt_new2old[p]; tmp[3 * (size_t)p] = s->h_pts0[3 * o]; tmp[3 * (size_t)p + 1] = s->h_pts0[3 * o + 1]; tmp[3 * (size_t)p + 2] = s->h_pts0[3 * o + 2]; }
     MM_CUDA(cudaMemcpy(s->pts.p, tmp.data(), sizeof(double) * 3 * (size_t)s->n_pt, cudaMemcpyHostToDevice)); }
@@ -296,8 +300,13 @@ LMDiag lm_of(const mm_ba_session* s) { LMDiag d; d.radius = s->radius; d.min_dia
 int launch_linearize(mm_ba_session* s) {
   cudaStream_t st = s->stream;
   k_pose_aux<<<blocks_for(s->n_img, 128), 128, 0, st>>>(s->n_img, s->poses.p, s->pose_mask.p, s->aux.p); MM_LAUNCH_CHECK();
-  k_residual_jacobian<true><<<s->grid_obs, 256, 0, st>>>(s->n_obs, s->obs_xy.p, s->obs_img.p, s->obs_pt.p, s->aux.p, s->pts.p, s->intr.p,
-      s->img_cam.p, s->cam_model.p, s->pose_mask.p, s->pt_mask.p, loss_of(s->opt), s->rec.p, s->part_cost.p); MM_LAUNCH_CHECK();
+  if (s->refine)
+    k_residual_jacobian<true, true><<<s->grid_obs, 256, 0, st>>>(s->n_obs, s->obs_xy.p, s->obs_img.p, s->obs_pt.p, s->aux.p, s->pts.p, s->intr.p,
+        s->img_cam.p, s->cam_model.p, s->pose_mask.p, s->pt_mask.p, loss_of(s->opt), s->rec.p, s->part_cost.p, s->ji.p, s->intr_mask.p);
+  else
+    k_residual_jacobian<true><<<s->grid_obs, 256, 0, st>>>(s->n_obs, s->obs_xy.p, s->obs_img.p, s->obs_pt.p, s->aux.p, s->pts.p, s->intr.p,
+        s->img_cam.p, s->cam_model.p, s->pose_mask.p, s->pt_mask.p, loss_of(s->opt), s->rec.p, s->part_cost.p);
+  MM_LAUNCH_CHECK();
   k_reduce_sum<<<1, 256, 0, st>>>(s->part_cost.p, s->grid_obs, s->red.p + 0); MM_LAUNCH_CHECK();
   return MM_OK;
 }
@@ -305,7 +314,7 @@ int launch_linearize(mm_ba_session* s) {
 int launch_cost_candidate(mm_ba_session* s) {
   cudaStream_t st = s->stream;
   k_pose_aux<<<blocks_for(s->n_img, 128), 128, 0, st>>>(s->n_img, s->poses2.p, s->pose_mask.p, s->aux2.p); MM_LAUNCH_CHECK();
-  k_residual_jacobian<false><<<s->grid_obs, 256, 0, st>>>(s->n_obs, s->obs_xy.p, s->obs_img.p, s->obs_pt.p, s->aux2.p, s->pts2.p, s->intr.p,
+  k_residual_jacobian<false><<<s->grid_obs, 256, 0, st>>>(s->n_obs, s->obs_xy.p, s->obs_img.p, s->obs_pt.p, s->aux2.p, s->pts2.p, s->refine ? s->intr2.p : s->intr.p,
       s->img_cam.p, s->cam_model.p, s->pose_mask.p, s->pt_mask.p, loss_of(s->opt), nullptr, s->part_cost.p); MM_LAUNCH_CHECK();
   k_reduce_sum<<<1, 256, 0, st>>>(s->part_cost.p, s->grid_obs, s->red.p + 1); MM_LAUNCH_CHECK();
   return MM_OK;
@@ -315,6 +324,11 @@ int launch_scale(mm_ba_session* s) {
   if (s->opt.jacobi_scaling) {
     k_colnorm_point<<<blocks_for(s->n_pt, 128), 128, 0, st>>>(s->n_pt, s->pt_start.p, s->rec.p, s->scale_p.p); MM_LAUNCH_CHECK();
     k_colnorm_cam<<<blocks_for((int64_t)s->n_img * 32, 128), 128, 0, st>>>(s->n_img, s->cam_start.p, s->cam_perm.p, s->rec.p, s->scale_c.p); MM_LAUNCH_CHECK();
+    if (s->refine) {
+      MM_CUDA(cudaMemsetAsync(s->sq9.p, 0, sizeof(double) * 9, st));
+      k_colnorm_intr<<<s->grid_obs, 256, 0, st>>>(s->n_obs, s->ji.p, s->sq9.p); MM_LAUNCH_CHECK();
+      k_intr_scale<<<1, 32, 0, st>>>(s->sq9.p, s->scale_i.p); MM_LAUNCH_CHECK();
+    }
   }
   return MM_OK;
 }
@@ -329,6 +343,13 @@ int launch_schur(mm_ba_session* s) {
   k_schur_cam<<<blocks_for((int64_t)s->n_img * 32, 128), 128, 0, st>>>(s->n_img, s->cam_start.p, s->cam_perm.p, s->obs_pt.p, s->rec.p,
       s->scale_c.p, s->scale_p.p, s->Vinv.p, s->gp.p, lm, s->S.p, s->rhs.p, s->gc.p, s->dc.p, s->red.p + 2); MM_LAUNCH_CHECK();
   k_precond<<<blocks_for(s->n_img, 64), 64, 0, st>>>(s->n_img, s->S.p, s->Minv.p, s->fail.p); MM_LAUNCH_CHECK();
+  if (s->refine) {
+    MM_CUDA(cudaMemsetAsync(s->intr_acc.p, 0, sizeof(double) * 108, st));
+    k_schur_intr_point<<<blocks_for(s->n_pt, 128), 128, 0, st>>>(s->n_pt, s->pt_start.p, s->rec.p, s->ji.p, s->scale_p.p, s->scale_i.p, s->Vinv.p, s->gp.p, s->Apc.p, s->intr_acc.p); MM_LAUNCH_CHECK();
+    k_schur_cam_intr<<<blocks_for((int64_t)s->n_img * 32, 128), 128, 0, st>>>(s->n_img, s->cam_start.p, s->cam_perm.p, s->obs_pt.p, s->rec.p, s->ji.p, s->scale_c.p, s->scale_p.p,
+        s->scale_i.p, s->Vinv.p, s->Apc.p, s->Bm.p); MM_LAUNCH_CHECK();
+    k_intr_finalize<<<1, 32, 0, st>>>(lm, s->scale_i.p, s->intr_acc.p, s->Cinv.p, s->gi.p, s->di.p, s->red.p + 2, s->fail.p); MM_LAUNCH_CHECK();
+  }
   return MM_OK;
 }
 // K3: solve S y = rhs with the persistent cooperative kernel (no host sync; iteration count -> pcg_ic[1])
@@ -344,7 +365,7 @@ int launch_pcg(mm_ba_session* s) {
     int dev = 0, max_smem = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     s->pcg_cached = false;
     const int tries[3] = { 512, 256, 128 };
-    for (int ti = 0; ti < 3 && !s->pcg_cached && !getenv("MM_PCG_STREAMING"); ++ti) {
+    for (int ti = 0; ti < 3 && !s->pcg_cached && !getenv("MM_PCG_STREAMING") && !s->refine; ++ti) {
       const int threads = tries[ti], NW = threads / 32;
       const int blocks = (s->n_img + NW - 1) / NW;
       int e_cap = 1;
@@ -370,6 +391,11 @@ int launch_pcg(mm_ba_session* s) {
   a.b = s->rhs.p; a.x = s->vx.p; a.r = s->vr.p; a.z = s->vz.p; a.p0 = s->vp0.p; a.p1 = s->vp1.p; a.Ap = s->vAp.p; a.sc = s->pcg_sc.p; a.ic = s->pcg_ic.p;
   a.tol2 = s->opt.pcg_tolerance * s->opt.pcg_tolerance; a.max_iter = s->opt.pcg_max_iterations;
   a.dbg = nullptr;
+  a.n_intr = 0; a.Bm = nullptr; a.Cm = nullptr; a.Cinv = nullptr; a.bi = nullptr; a.xi = a.zi = a.pi0 = a.pi1 = a.bt = nullptr;
+  if (s->refine) {
+    a.n_intr = 9; a.Bm = s->Bm.p; a.Cm = s->intr_acc.p; a.Cinv = s->Cinv.p; a.bi = s->intr_acc.p + 81; a.xi = s->xi.p; a.zi = s->zi.p; a.pi0 = s->pi0.p; a.pi1 = s->pi1.p; a.bt = s->bt.p;
+    MM_CUDA(cudaMemsetAsync(s->bt.p, 0, sizeof(double) * 18, st));
+  }
   if (getenv("MM_PCG_DEBUG")) { if (!s->pcg_dbg.p) MM_CUDA(s->pcg_dbg.alloc(6 * 32)); a.dbg = s->pcg_dbg.p; }
   if (s->pcg_cached) {
     int e_cap = s->pcg_ecap;
@@ -388,14 +414,15 @@ int launch_update(mm_ba_session* s) {
   cudaStream_t st = s->stream;
   const int gp_ = blocks_for(s->n_pt, 128), gc_ = blocks_for((int64_t)6 * s->n_img, 128);
   k_backsub<<<gp_, 128, 0, st>>>(s->n_pt, s->pt_start.p, s->obs_img.p, s->rec.p, s->scale_c.p, s->scale_p.p, s->Vinv.p, s->gp.p, s->dp.p,
-      s->vx.p, s->pts.p, s->pts2.p, s->part_pt.p); MM_LAUNCH_CHECK();
+      s->vx.p, s->pts.p, s->pts2.p, s->part_pt.p, s->refine ? s->Apc.p : nullptr, s->refine ? s->xi.p : nullptr); MM_LAUNCH_CHECK();
   k_update_cam<<<gc_, 128, 0, st>>>(6 * s->n_img, s->vx.p, s->scale_c.p, s->gc.p, s->dc.p, s->poses.p, s->poses2.p, s->part_cam.p); MM_LAUNCH_CHECK();
-  k_reduce_pairs<<<1, 256, 0, st>>>(s->part_pt.p, gp_, s->part_cam.p, gc_, s->red.p + 3); MM_LAUNCH_CHECK();
+  if (s->refine) { k_update_intr<<<1, 32, 0, st>>>(s->xi.p, s->scale_i.p, s->gi.p, s->di.p, s->intr.p, s->intr2.p, s->part_cam.p + 2 * (size_t)gc_); MM_LAUNCH_CHECK(); }
+  k_reduce_pairs<<<1, 256, 0, st>>>(s->part_pt.p, gp_, s->part_cam.p, gc_ + (s->refine ? 1 : 0), s->red.p + 3); MM_LAUNCH_CHECK();
   return MM_OK;
 }
 int launch_xnorm(mm_ba_session* s) {
   cudaStream_t st = s->stream;
-  k_xnorm<<<s->grid_x, 256, 0, st>>>(6 * s->n_img, s->poses.p, s->pose_mask.p, s->n_pt, s->pts.p, s->pt_mask.p, s->part_x.p); MM_LAUNCH_CHECK();
+  k_xnorm<<<s->grid_x, 256, 0, st>>>(6 * s->n_img, s->poses.p, s->pose_mask.p, s->n_pt, s->pts.p, s->pt_mask.p, s->part_x.p, s->refine ? s->intr.p : nullptr, s->intr_mask.p); MM_LAUNCH_CHECK();
   k_reduce_sum<<<1, 256, 0, st>>>(s->part_x.p, s->grid_x, s->red.p + 5); MM_LAUNCH_CHECK();
   return MM_OK;
 }
@@ -480,7 +507,7 @@ int lm_iterate(mm_ba_session* s) {
     s->decrease_factor = 2.0;
     // keep the previous iterate in poses2/pts2 until the gradient test has passed (Ceres 1.8 commits
     // x_min only after it)
-    std::swap(s->poses.p, s->poses2.p); std::swap(s->pts.p, s->pts2.p); std::swap(s->aux.p, s->aux2.p);
+    std::swap(s->poses.p, s->poses2.p); std::swap(s->pts.p, s->pts2.p); std::swap(s->aux.p, s->aux2.p); if (s->refine) std::swap(s->intr.p, s->intr2.p);
     cudaEventRecord(s->evs[3], s->stream);
     if ((rc = launch_linearize(s))) return rc;
     cudaEventRecord(s->evs[4], s->stream);
@@ -491,7 +518,7 @@ int lm_iterate(mm_ba_session* s) {
     { float ms = 0; cudaEventElapsedTime(&ms, s->evs[3], s->evs[4]); S.ms_linearize += ms; cudaEventElapsedTime(&ms, s->evs[4], s->evs[5]); S.ms_schur += ms; }
     s->cost = red[0]; s->gmax = red[2]; s->x_norm = sqrt(red[5]);
     if (s->gmax <= s->abs_gtol) {
-      std::swap(s->poses.p, s->poses2.p); std::swap(s->pts.p, s->pts2.p); std::swap(s->aux.p, s->aux2.p);   // discard, as Ceres 1.8 does
+      std::swap(s->poses.p, s->poses2.p); std::swap(s->pts.p, s->pts2.p); std::swap(s->aux.p, s->aux2.p); if (s->refine) std::swap(s->intr.p, s->intr2.p);   // discard, as Ceres 1.8 does
       S.termination = MM_TERM_GRADIENT_TOLERANCE; s->finished = true; return MM_OK;
     }
   } else {
@@ -539,14 +566,16 @@ int mm_ba_session_create(const mm_ba_problem* P, const mm_ba_options* opt, void*
   *out = nullptr;
   int rc = validate_problem(P); if (rc) return rc;
   if (opt->linear_solver != MM_SOLVER_PCG) { set_error("the device engine solves the reduced system with PCG only"); return MM_ERR_UNSUPPORTED; }
+  bool refine = false;
   for (int c = 0; c < P->n_cam; ++c) if (!P->intr_const[c]) {
     bool used = false; for (int i = 0; i < P->n_img; ++i) if (P->img_cam[i] == c) used = true;
-    if (used) { set_error("refine_camera_params (free intrinsics) is not built into the device engine yet"); return MM_ERR_UNSUPPORTED; }
+    if (used) refine = true;
   }
+  if (refine && P->n_cam != 1) { set_error("refine_camera_params on the device engine handles one shared camera (got %d)", P->n_cam); return MM_ERR_UNSUPPORTED; }
   rc = ensure_device(); if (rc) return rc;
   mm_ba_session* s = new mm_ba_session();
   s->stream = (cudaStream_t)stream; s->opt = *opt;
-  s->n_img = P->n_img; s->n_cam = P->n_cam; s->n_pt = P->n_pt; s->n_obs = P->n_obs;
+  s->n_img = P->n_img; s->n_cam = P->n_cam; s->n_pt = P->n_pt; s->n_obs = P->n_obs; s->refine = refine;
   auto fail_out = [&](int code) { mm_ba_session_destroy(s); return code; };
   if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) { set_error("cudaEventCreate failed"); return fail_out(MM_ERR_CUDA); }
   for (int i = 0; i < 8; ++i) if (cudaEventCreate(&s->evs[i]) != cudaSuccess) { set_error("cudaEventCreate failed"); return fail_out(MM_ERR_CUDA); }
@@ -564,8 +593,16 @@ int mm_ba_session_create(const mm_ba_problem* P, const mm_ba_options* opt, void*
   A(s->pcg_sc, 16); A(s->pcg_ic, 4); A(s->red, 8); A(s->fail, 1); A(s->img_cam, n_img); A(s->cam_model, n_cam); A(s->Minv, 36 * n_img);
   s->grid_obs = grid_stride(std::max<int64_t>(P->n_obs, 1), 256);
   s->grid_x = grid_stride(std::max<int64_t>(3 * (int64_t)P->n_pt, 1), 256);
-  A(s->part_cost, (size_t)s->grid_obs); A(s->part_pt, 2 * (size_t)blocks_for(P->n_pt, 128)); A(s->part_cam, 2 * (size_t)blocks_for(6 * (int64_t)P->n_img, 128));
+  A(s->part_cost, (size_t)s->grid_obs); A(s->part_pt, 2 * (size_t)blocks_for(P->n_pt, 128)); A(s->part_cam, 2 * (size_t)blocks_for(6 * (int64_t)P->n_img, 128) + 2);
   A(s->part_x, (size_t)s->grid_x);
+  A(s->intr2, MM_INTR_STRIDE * n_cam); A(s->intr_mask, 9); A(s->scale_i, 9);
+  if (refine) {
+    A(s->ji, 18 * (size_t)std::max<int64_t>(P->n_obs, 1)); A(s->Apc, 27 * n_pt); A(s->Bm, 54 * n_img); A(s->intr_acc, 108); A(s->Cinv, 81);
+    A(s->gi, 9); A(s->di, 9); A(s->xi, 9); A(s->zi, 9); A(s->pi0, 9); A(s->pi1, 9); A(s->bt, 18); A(s->sq9, 9);
+  }
+  { double im[9]; for (int k = 0; k < 9; ++k) im[k] = (refine && k < model_num_params(P->cam_model[0])) ? 1.0 : 0.0;
+    double ones[9]; for (int k = 0; k < 9; ++k) ones[k] = 1.0;
+    if (cudaMemcpy(s->intr_mask.p, im, sizeof im, cudaMemcpyHostToDevice) != cudaSuccess || cudaMemcpy(s->scale_i.p, ones, sizeof ones, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("mask upload failed"); return fail_out(MM_ERR_CUDA); } }
   // masks: 1.0 = free and present in at least one residual block
   { std::vector<int> img_n(n_img, 0), pt_n(n_pt, 0);
     for (int64_t o = 0; o < P->n_obs; ++o) { img_n[P->obs_img[o]]++; pt_n[P->obs_pt[o]]++; }

@@ -49,13 +49,14 @@ __global__ void k_pose_aux(int n_img, const double* __restrict__ poses, const do
 // ---- K1: residual + Jacobian per observation -------------------------------------------
 // reads 24 B/obs (xy, img, pt) + gathered parameters, writes one 160 B record.
 // cost partial per block -> cost_part[blockIdx.x] (reduced deterministically afterwards).
-template <bool WITH_J>
+template <bool WITH_J, bool WITH_JI = false>
 __global__ void __launch_bounds__(256, WITH_J ? 2 : 4) k_residual_jacobian(
     int64_t n_obs, const double2* __restrict__ obs_xy, const int* __restrict__ obs_img, const int* __restrict__ obs_pt,
     const double* __restrict__ aux, const double* __restrict__ pts, const double* __restrict__ intr,
     const int* __restrict__ img_cam, const int* __restrict__ cam_model,
     const double* __restrict__ pose_mask, const double* __restrict__ pt_mask,
-    LossParams L, double* __restrict__ rec, double* __restrict__ cost_part) {
+    LossParams L, double* __restrict__ rec, double* __restrict__ cost_part,
+    double* __restrict__ ji = nullptr, const double* __restrict__ intr_mask = nullptr) {
   __shared__ double red[32];
   // records are staged per warp in shared memory (22-double pitch keeps 16-byte alignment) and written
   // out as whole 512-byte runs: every store instruction of the warp covers contiguous global memory
@@ -90,12 +91,20 @@ __global__ void __launch_bounds__(256, WITH_J ? 2 : 4) k_residual_jacobian(
       const double xc = Y0 + a[18], yc = Y1 + a[19], zc = Y2 + a[20];
       const int cam = img_cam[img];
       const int model = cam_model[cam];
-      double u, v, dX[2][3];
-      world2image<WITH_J>(model, intr + MM_INTR_STRIDE * (size_t)cam, xc, yc, zc, u, v, dX, nullptr);
+      double u, v, dX[2][3], dP[2][9];
+      world2image<WITH_J>(model, intr + MM_INTR_STRIDE * (size_t)cam, xc, yc, zc, u, v, dX, WITH_JI ? dP : nullptr);
       const double r0 = u - xy.x, r1 = v - xy.y;
       double rho0, sr;
       loss_eval(L, r0 * r0 + r1 * r1, rho0, sr);
       cost += 0.5 * rho0;
+      if (WITH_JI) {        // d r / d intrinsics (2 x 9), robustified and masked; 144 B per observation
+        double2* j2 = reinterpret_cast<double2*>(ji + 18 * (size_t)i);
+        double t[18];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { const double m = intr_mask[k] * sr; t[k] = dP[0][k] * m; t[9 + k] = dP[1][k] * m; }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) j2[k] = make_double2(t[2 * k], t[2 * k + 1]);
+      }
       if (WITH_J) {
         const double mp = pt_mask[pt] * sr;
         const int mbits = (int)a[22];
@@ -582,6 +591,8 @@ struct PcgArgs {
   int n_img; const int* row_start; const int* row_col; const int* row_blk; const double* S; const double* Minv; const double* b;
   double *x, *r, *z, *p0, *p1, *Ap; double* sc; int* ic; double tol2; int max_iter;
   unsigned long long* dbg;   // optional: %globaltimer stamps of CTA 0 for the first 32 iterations (6 per iteration)
+  // dense border of the reduced system when the (single, shared) camera's intrinsics are refined: unknowns [poses | 9 intrinsics]
+  int n_intr; const double* Bm; const double* Cm; const double* Cinv; const double* bi; double *xi, *zi, *pi0, *pi1, *bt;
 };
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define PCG_STAMP(k) do { if (A.dbg && blockIdx.x == 0 && threadIdx.x == 0 && it < 32) A.dbg[6 * it + (k)] = gtimer(); } while (0)
@@ -602,10 +613,15 @@ __global__ void __launch_bounds__(256) k_pcg_persistent(PcgArgs A) {
   cg::grid_group grid = cg::this_grid();
   const bool single = gridDim.x == 1;
   __shared__ double red[8];
-  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  const int gw = blockIdx.x * wpb + (threadIdx.x >> 5), nw = gridDim.x * wpb;
+  __shared__ double bt_s[8][9];
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, wib = threadIdx.x >> 5;
+  const int gw = blockIdx.x * wpb + wib, nw = gridDim.x * wpb;
   const int n = A.n_img;
   const int g = lane / 6, rr_ = lane - 6 * g;          // SpMV: 5 groups of 6 lanes, lane = (group, block row)
+  const bool border = A.n_intr > 0;                     // 9 intrinsics unknowns owned by lanes 0..8 of warp 0 of CTA 0
+  const bool owner = border && gw == 0;
+  const bool olane = owner && lane < 9;
+  double xi = 0.0, ri = 0.0, zi_ = 0.0, pi_ = 0.0, cp = 0.0;    // owner-lane state of the intrinsics part
   // ---- init: x = 0, r = b, z = Minv r, p = 0
   {
     double a_rz = 0.0, a_bb = 0.0;
@@ -621,6 +637,12 @@ __global__ void __launch_bounds__(256) k_pcg_persistent(PcgArgs A) {
         a_rz += rv * zl; a_bb += rv * rv;
       }
     }
+    if (owner) {
+      if (olane) ri = A.bi[lane];
+#pragma unroll
+      for (int m = 0; m < 9; ++m) { const double rm = __shfl_sync(0xffffffffu, ri, m); if (olane) zi_ += A.Cinv[9 * lane + m] * rm; }
+      if (olane) { A.zi[lane] = zi_; A.pi0[lane] = 0.0; A.pi1[lane] = 0.0; a_rz += ri * zi_; a_bb += ri * ri; }
+    }
     a_rz = block_sum_to_thread0(a_rz, red); a_bb = block_sum_to_thread0(a_bb, red);
     if (threadIdx.x == 0) { atomicAdd(A.sc + 2, a_rz); atomicAdd(A.sc + 6, a_bb); }
   }
@@ -634,6 +656,10 @@ __global__ void __launch_bounds__(256) k_pcg_persistent(PcgArgs A) {
       const double* p_old = (it & 1) ? A.p1 : A.p0; double* p_new = (it & 1) ? A.p0 : A.p1;
       const int nxt = (it + 1) & 1;
       if (gw == 0 && lane == 0) { A.sc[2 + nxt] = 0.0; A.sc[4 + nxt] = 0.0; }
+      // intrinsics part of the search direction, formed on the fly by every warp: pin[m] in lane m
+      double pin = 0.0;
+      if (border && lane < 9) pin = __ldcg(A.zi + lane) + beta * __ldcg(((it & 1) ? A.pi1 : A.pi0) + lane);
+      double btl = 0.0;                                 // this warp's share of B' p (lane m < 9)
       // ---- SpMV with p formed on the fly: Ap = S (z + beta p_old)
       double acc = 0.0;
       for (int row = gw; row < n; row += nw) {
@@ -644,26 +670,46 @@ __global__ void __launch_bounds__(256) k_pcg_persistent(PcgArgs A) {
             const bool tr = bid < 0;
             const double* B = A.S + 36 * (size_t)(tr ? -bid - 1 : bid);
             const double* zc = A.z + 6 * (size_t)col; const double* pc = p_old + 6 * (size_t)col;
+            double pv[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) pv[c] = __ldcg(zc + c) + beta * __ldcg(pc + c);
             if (!tr) {
 #pragma unroll
-              for (int c = 0; c < 6; ++c) y += B[6 * rr_ + c] * (__ldcg(zc + c) + beta * __ldcg(pc + c));
+              for (int c = 0; c < 6; ++c) y += B[6 * rr_ + c] * pv[c];
             } else {
 #pragma unroll
-              for (int c = 0; c < 6; ++c) y += B[6 * c + rr_] * (__ldcg(zc + c) + beta * __ldcg(pc + c));
+              for (int c = 0; c < 6; ++c) y += B[6 * c + rr_] * pv[c];
             }
           }
         }
         double t = y + __shfl_down_sync(0xffffffffu, y, 12);
         t += __shfl_down_sync(0xffffffffu, t, 6);
         t += __shfl_down_sync(0xffffffffu, y, 24);
-        if (lane < 6) {
-          const size_t i = 6 * (size_t)row + lane;
-          const double pn = __ldcg(A.z + i) + beta * __ldcg(p_old + i);
-          p_new[i] = pn; A.Ap[i] = t; acc += pn * t;
+        double pn = 0.0, bp = 0.0;
+        const size_t i = 6 * (size_t)row + (lane < 6 ? lane : 0);
+        if (lane < 6) pn = __ldcg(A.z + i) + beta * __ldcg(p_old + i);
+        if (border) {
+          const double* Ba = A.Bm + 54 * (size_t)row;
+#pragma unroll
+          for (int m = 0; m < 9; ++m) { const double pm = __shfl_sync(0xffffffffu, pin, m); if (lane < 6) bp += Ba[9 * lane + m] * pm; }
+#pragma unroll
+          for (int r = 0; r < 6; ++r) { const double pr = __shfl_sync(0xffffffffu, pn, r); if (lane < 9) btl += Ba[9 * r + lane] * pr; }
+        }
+        if (lane < 6) { p_new[i] = pn; A.Ap[i] = t + bp; acc += pn * (t + bp) + pn * bp; }
+      }
+      if (border) {
+        // B' p: block-level reduction, then 9 atomics per CTA into the parity slot
+        if (lane < 9) bt_s[wib][lane] = btl;
+        if (owner) {      // C p_i and the intrinsics term of p'Ap
+          cp = 0.0;
+#pragma unroll
+          for (int m = 0; m < 9; ++m) { const double pm = __shfl_sync(0xffffffffu, pin, m); if (olane) cp += A.Cm[9 * lane + m] * pm; }
+          if (olane) { pi_ = pin; ((it & 1) ? A.pi0 : A.pi1)[lane] = pin; acc += pin * cp; }
         }
       }
-      acc = block_sum_to_thread0(acc, red);
+      acc = block_sum_to_thread0(acc, red);          // (contains __syncthreads: bt_s is complete afterwards)
       if (threadIdx.x == 0) atomicAdd(A.sc + (it & 1), acc);
+      if (border && threadIdx.x < 9) { double sb = 0.0; for (int w = 0; w < wpb; ++w) sb += bt_s[w][threadIdx.x]; atomicAdd(A.bt + 9 * (it & 1) + threadIdx.x, sb); }
       if (single) __syncthreads(); else grid.sync();
       const double pAp = __ldcg(A.sc + (it & 1));
       const double alpha = pAp > 0.0 ? rz / pAp : 0.0;
@@ -683,6 +729,13 @@ __global__ void __launch_bounds__(256) k_pcg_persistent(PcgArgs A) {
         for (int c = 0; c < 6; ++c) { const double rc = __shfl_sync(0xffffffffu, rv, c); if (lane < 6) zl += A.Minv[36 * (size_t)row + 6 * lane + c] * rc; }
         if (lane < 6) { A.z[i] = zl; a_rz += rv * zl; a_rr += rv * rv; }
       }
+      if (owner) {
+        if (olane) { const double api = __ldcg(A.bt + 9 * (it & 1) + lane) + cp; xi += alpha * pi_; ri -= alpha * api; A.bt[9 * nxt + lane] = 0.0; }
+        double zn = 0.0;
+#pragma unroll
+        for (int m = 0; m < 9; ++m) { const double rm = __shfl_sync(0xffffffffu, ri, m); if (olane) zn += A.Cinv[9 * lane + m] * rm; }
+        if (olane) { zi_ = zn; A.zi[lane] = zn; a_rz += ri * zn; a_rr += ri * ri; }
+      }
       a_rz = block_sum_to_thread0(a_rz, red); a_rr = block_sum_to_thread0(a_rr, red);
       if (threadIdx.x == 0) { atomicAdd(A.sc + 2 + nxt, a_rz); atomicAdd(A.sc + 4 + nxt, a_rr); }
       if (single) __syncthreads(); else grid.sync();
@@ -692,6 +745,7 @@ __global__ void __launch_bounds__(256) k_pcg_persistent(PcgArgs A) {
       if (rr <= A.tol2 * bb || it >= A.max_iter || !(rr == rr)) break;
     }
   }
+  if (olane) A.xi[lane] = xi;
   if (gw == 0 && lane == 0) A.ic[1] = it;
 }
 
@@ -815,6 +869,178 @@ __global__ void __launch_bounds__(THREADS, 1) k_pcg_cached(PcgArgs A, int e_cap)
   if (blockIdx.x == 0 && threadIdx.x == 0) A.ic[1] = it;
 }
 
+// ---- refined intrinsics (single shared camera): dense border of the reduced system ----------------------
+// Unknowns of the reduced system become [poses (6 n_img) | intrinsics (9)].  With E = d r / d intr (scaled):
+//   A_p  = sum_{obs of p} E' Jp                       (9 x 3, stored per point for the back-substitution)
+//   C    = sum_obs E'E + D_i^2 - sum_p A_p V_p^-1 A_p'   (9 x 9)
+//   b_i  = sum_obs E'r - sum_p A_p V_p^-1 g_p
+//   B_a  = sum_{obs of image a} (Jc'E - Y_obs A_p')       (6 x 9), Y_obs = Jc'Jp V_p^-1
+// intr_acc layout (doubles): [0,81) C   [81,90) b_i   [90,99) diag(E'E)   [99,108) E'r (unreduced gradient)
+__global__ void k_colnorm_intr(int64_t n_obs, const double* __restrict__ ji, double* __restrict__ out9) {
+  __shared__ double red[32];
+  double a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_obs; i += (int64_t)gridDim.x * blockDim.x) {
+    const double* j = ji + 18 * (size_t)i;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a[k] += j[k] * j[k] + j[9 + k] * j[9 + k];
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { const double v = block_sum(a[k], red); if (threadIdx.x == 0) atomicAdd(out9 + k, v); }
+}
+__global__ void k_intr_scale(const double* __restrict__ sq9, double* __restrict__ scale_i) {
+  if (threadIdx.x < 9) scale_i[threadIdx.x] = 1.0 / (1.0 + sqrt(sq9[threadIdx.x]));
+}
+
+__global__ void __launch_bounds__(128) k_schur_intr_point(
+    int n_pt, const int* __restrict__ pt_start, const double* __restrict__ rec, const double* __restrict__ ji,
+    const double* __restrict__ scale_p, const double* __restrict__ scale_i, const double* __restrict__ Vinv, const double* __restrict__ gp,
+    double* __restrict__ Apc, double* __restrict__ intr_acc) {
+  __shared__ double red[32];
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  double A[9][3], Cc[45], rh[9], ud[9], gu[9];
+#pragma unroll
+  for (int a = 0; a < 9; ++a) { A[a][0] = A[a][1] = A[a][2] = 0.0; rh[a] = 0.0; ud[a] = 0.0; gu[a] = 0.0; }
+#pragma unroll
+  for (int k = 0; k < 45; ++k) Cc[k] = 0.0;
+  if (p < n_pt) {
+    double si[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) si[k] = scale_i[k];
+    const double sp[3] = { scale_p[3 * (size_t)p], scale_p[3 * (size_t)p + 1], scale_p[3 * (size_t)p + 2] };
+    for (int o = pt_start[p]; o < pt_start[p + 1]; ++o) {
+      const double2* r2 = reinterpret_cast<const double2*>(rec + REC * (size_t)o);
+      const double2 rr = r2[0], q7 = r2[7], q8 = r2[8], q9 = r2[9];
+      const double jp0[3] = { q7.x * sp[0], q7.y * sp[1], q8.x * sp[2] }, jp1[3] = { q8.y * sp[0], q9.x * sp[1], q9.y * sp[2] };
+      const double* j = ji + 18 * (size_t)o;
+      int k = 0;
+#pragma unroll
+      for (int a = 0; a < 9; ++a) {
+        const double e0 = j[a] * si[a], e1 = j[9 + a] * si[a];
+        A[a][0] += e0 * jp0[0] + e1 * jp1[0]; A[a][1] += e0 * jp0[1] + e1 * jp1[1]; A[a][2] += e0 * jp0[2] + e1 * jp1[2];
+        const double ga = e0 * rr.x + e1 * rr.y;
+        gu[a] += ga; rh[a] += ga; ud[a] += e0 * e0 + e1 * e1;
+#pragma unroll
+        for (int b = a; b < 9; ++b, ++k) Cc[k] += e0 * (j[b] * si[b]) + e1 * (j[9 + b] * si[b]);
+      }
+    }
+    const double* I = Vinv + 6 * (size_t)p;
+    const double g0 = gp[3 * (size_t)p], g1 = gp[3 * (size_t)p + 1], g2 = gp[3 * (size_t)p + 2];
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < 9; ++a) {
+      const double t0 = A[a][0] * I[0] + A[a][1] * I[1] + A[a][2] * I[2];
+      const double t1 = A[a][0] * I[1] + A[a][1] * I[3] + A[a][2] * I[4];
+      const double t2 = A[a][0] * I[2] + A[a][1] * I[4] + A[a][2] * I[5];
+      rh[a] -= t0 * g0 + t1 * g1 + t2 * g2;
+#pragma unroll
+      for (int b = a; b < 9; ++b, ++k) Cc[k] -= t0 * A[b][0] + t1 * A[b][1] + t2 * A[b][2];
+      Apc[27 * (size_t)p + 3 * a] = A[a][0]; Apc[27 * (size_t)p + 3 * a + 1] = A[a][1]; Apc[27 * (size_t)p + 3 * a + 2] = A[a][2];
+    }
+  }
+  int k = 0;
+#pragma unroll
+  for (int a = 0; a < 9; ++a)
+#pragma unroll
+    for (int b = a; b < 9; ++b, ++k) {
+      const double v = block_sum(Cc[k], red);
+      if (threadIdx.x == 0 && v != 0.0) { atomicAdd(intr_acc + 9 * a + b, v); if (b != a) atomicAdd(intr_acc + 9 * b + a, v); }
+    }
+#pragma unroll
+  for (int a = 0; a < 9; ++a) {
+    const double v0 = block_sum(rh[a], red), v1 = block_sum(ud[a], red), v2 = block_sum(gu[a], red);
+    if (threadIdx.x == 0) { atomicAdd(intr_acc + 81 + a, v0); atomicAdd(intr_acc + 90 + a, v1); atomicAdd(intr_acc + 99 + a, v2); }
+  }
+}
+
+// warp per image: B_a (6 x 9)
+__global__ void __launch_bounds__(128) k_schur_cam_intr(
+    int n_img, const int* __restrict__ cam_start, const int* __restrict__ cam_perm, const int* __restrict__ obs_pt,
+    const double* __restrict__ rec, const double* __restrict__ ji, const double* __restrict__ scale_c, const double* __restrict__ scale_p,
+    const double* __restrict__ scale_i, const double* __restrict__ Vinv, const double* __restrict__ Apc, double* __restrict__ Bm) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n_img) return;
+  double sc[6], si[9], acc[6][9];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) sc[k] = scale_c[6 * (size_t)w + k];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) si[k] = scale_i[k];
+#pragma unroll
+  for (int a = 0; a < 6; ++a)
+#pragma unroll
+    for (int m = 0; m < 9; ++m) acc[a][m] = 0.0;
+  for (int q = cam_start[w] + lane; q < cam_start[w + 1]; q += 32) {
+    const int o = cam_perm[q], p = obs_pt[o];
+    const double sp[3] = { scale_p[3 * (size_t)p], scale_p[3 * (size_t)p + 1], scale_p[3 * (size_t)p + 2] };
+    double Jc[2][6], Jp[2][3];
+    load_scaled(rec, o, sc, sp, Jc, Jp);
+    double I[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) I[k] = Vinv[6 * (size_t)p + k];
+    const double* j = ji + 18 * (size_t)o;
+    const double* Ap = Apc + 27 * (size_t)p;
+    double e0[9], e1[9];
+#pragma unroll
+    for (int m = 0; m < 9; ++m) { e0[m] = j[m] * si[m]; e1[m] = j[9 + m] * si[m]; }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      const double w0 = Jc[0][a] * Jp[0][0] + Jc[1][a] * Jp[1][0];
+      const double w1 = Jc[0][a] * Jp[0][1] + Jc[1][a] * Jp[1][1];
+      const double w2 = Jc[0][a] * Jp[0][2] + Jc[1][a] * Jp[1][2];
+      const double y0 = w0 * I[0] + w1 * I[1] + w2 * I[2], y1 = w0 * I[1] + w1 * I[3] + w2 * I[4], y2 = w0 * I[2] + w1 * I[4] + w2 * I[5];
+#pragma unroll
+      for (int m = 0; m < 9; ++m)
+        acc[a][m] += Jc[0][a] * e0[m] + Jc[1][a] * e1[m] - (y0 * Ap[3 * m] + y1 * Ap[3 * m + 1] + y2 * Ap[3 * m + 2]);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 6; ++a)
+#pragma unroll
+    for (int m = 0; m < 9; ++m) { const double v = warp_sum(acc[a][m]); if (lane == 0) Bm[54 * (size_t)w + 9 * a + m] = v; }
+}
+
+// one warp: LM diagonal of the intrinsics, C^-1 (preconditioner block), gradient max-norm
+__global__ void k_intr_finalize(LMDiag lm, const double* __restrict__ scale_i, double* __restrict__ intr_acc, double* __restrict__ Cinv,
+                                double* __restrict__ gi_out, double* __restrict__ di_out, double* __restrict__ gmax, int* __restrict__ fail) {
+  if (threadIdx.x != 0) return;
+  double C[9][9], L[9][9];
+  double gm = 0.0;
+  for (int a = 0; a < 9; ++a) {
+    const double d = fmin(fmax(intr_acc[90 + a], lm.min_diag), lm.max_diag) / lm.radius;
+    di_out[a] = d; gi_out[a] = intr_acc[99 + a];
+    intr_acc[9 * a + a] += d;
+    gm = fmax(gm, fabs(intr_acc[99 + a] / scale_i[a]));
+  }
+  for (int a = 0; a < 9; ++a) for (int b = 0; b < 9; ++b) C[a][b] = intr_acc[9 * a + b];
+  bool ok = true;
+  for (int j = 0; j < 9; ++j) {
+    double d = C[j][j];
+    for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
+    if (!(d > 0.0)) { ok = false; d = 1.0; }
+    L[j][j] = sqrt(d);
+    for (int r = j + 1; r < 9; ++r) { double s = C[r][j]; for (int k = 0; k < j; ++k) s -= L[r][k] * L[j][k]; L[r][j] = s / L[j][j]; }
+  }
+  for (int c = 0; c < 9; ++c) {
+    double y[9];
+    for (int r = 0; r < 9; ++r) { double s = (r == c) ? 1.0 : 0.0; for (int k = 0; k < r; ++k) s -= L[r][k] * y[k]; y[r] = s / L[r][r]; }
+    for (int r = 8; r >= 0; --r) { double s = y[r]; for (int k = r + 1; k < 9; ++k) s -= L[k][r] * y[k]; y[r] = s / L[r][r]; }
+    for (int r = 0; r < 9; ++r) Cinv[9 * r + c] = y[r];
+  }
+  if (!ok) *fail = 1;
+  if (gm > 0.0) atomic_max_nonneg(gmax, gm);
+}
+
+// candidate intrinsics + their share of ||step||^2 and of the model cost change
+__global__ void k_update_intr(const double* __restrict__ yi, const double* __restrict__ scale_i, const double* __restrict__ gi, const double* __restrict__ di,
+                              const double* __restrict__ intr, double* __restrict__ intr2, double* __restrict__ part2) {
+  if (threadIdx.x != 0) return;
+  double sn = 0.0, mc = 0.0;
+  for (int k = 0; k < 9; ++k) {
+    const double y = yi[k], e = -y * scale_i[k];
+    intr2[k] = intr[k] + e; sn += e * e; mc += 0.5 * y * (gi[k] + di[k] * y);
+  }
+  part2[0] = sn; part2[1] = mc;
+}
+
 // ---- K4a: back-substitution for the points + candidate point parameters --------------------
 // y_p = V'^-1 (g_p - sum_i W_i' y_c[img_i]); delta = -y_p * s_p.  Partials: [0] step_norm2,
 // [1] model cost change 1/2 y (g + D y)  (valid because the linear system is solved to pcg_tolerance).
@@ -822,7 +1048,8 @@ __global__ void __launch_bounds__(128) k_backsub(
     int n_pt, const int* __restrict__ pt_start, const int* __restrict__ obs_img, const double* __restrict__ rec,
     const double* __restrict__ scale_c, const double* __restrict__ scale_p, const double* __restrict__ Vinv,
     const double* __restrict__ gp, const double* __restrict__ dp, const double* __restrict__ yc,
-    const double* __restrict__ pts, double* __restrict__ pts2, double* __restrict__ part /*[2*grid]*/) {
+    const double* __restrict__ pts, double* __restrict__ pts2, double* __restrict__ part /*[2*grid]*/,
+    const double* __restrict__ Apc = nullptr, const double* __restrict__ yi = nullptr) {
   __shared__ double red[32];
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   double sn = 0.0, mc = 0.0;
@@ -839,6 +1066,11 @@ __global__ void __launch_bounds__(128) k_backsub(
       for (int k = 0; k < 6; ++k) { const double y = yc[6 * (size_t)ia + k]; q0 += Jc[0][k] * y; q1 += Jc[1][k] * y; }
 #pragma unroll
       for (int k = 0; k < 3; ++k) t[k] -= Jp[0][k] * q0 + Jp[1][k] * q1;
+    }
+    if (Apc) {        // - A_p' y_i (refined intrinsics)
+      const double* Ap = Apc + 27 * (size_t)p;
+#pragma unroll
+      for (int a = 0; a < 9; ++a) { const double y = yi[a]; t[0] -= Ap[3 * a] * y; t[1] -= Ap[3 * a + 1] * y; t[2] -= Ap[3 * a + 2] * y; }
     }
     const double* I = Vinv + 6 * (size_t)p;
     const double y0 = I[0] * t[0] + I[1] * t[1] + I[2] * t[2];
@@ -883,9 +1115,11 @@ __global__ void k_reduce_pairs(const double* __restrict__ partA, int nA, const d
 
 // sum of squares of the active parameters (x_norm of the reduced program)
 __global__ void k_xnorm(int n_c, const double* __restrict__ poses, const double* __restrict__ pose_mask,
-                        int n_pt, const double* __restrict__ pts, const double* __restrict__ pt_mask, double* __restrict__ part) {
+                        int n_pt, const double* __restrict__ pts, const double* __restrict__ pt_mask, double* __restrict__ part,
+                        const double* __restrict__ intr = nullptr, const double* __restrict__ intr_mask = nullptr) {
   __shared__ double red[32];
   double s = 0.0;
+  if (intr && blockIdx.x == 0 && threadIdx.x < 9) s += intr_mask[threadIdx.x] * intr[threadIdx.x] * intr[threadIdx.x];
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_c; i += (int64_t)gridDim.x * blockDim.x)
     s += pose_mask[i] * poses[i] * poses[i];
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < 3 * (int64_t)n_pt; i += (int64_t)gridDim.x * blockDim.x)

@@ -37,6 +37,24 @@ def test_small_problem_parity_per_camera_model(mm, orc, model):
     _assert_parity(*_both(orc, flat, 10))
 
 
+@pytest.mark.parametrize("model", [1, 2, 3])
+def test_refine_camera_params_parity(mm, orc, model):
+    """refine_camera_params=true (the mapper's default, mapper.cc:878-886): one shared intrinsics block,
+    dense border of the reduced camera system."""
+    flat, truth = synthetic.make_ba_problem(model=model, refine_camera_params=True, **synthetic.BA_CONFIGS["tiny"])
+    flat.intr[0, :2] *= 1.01; flat.intr[0, 2:4] += 3.0          # start from a perturbed calibration
+    g, c, sg, so = _both(orc, flat, 10)
+    _assert_parity(g, c, sg, so)
+    assert not np.allclose(g.intr, flat.intr)                    # the intrinsics did move ...
+    assert abs(g.intr[0, 0] - truth["intr"][0, 0]) < abs(flat.intr[0, 0] - truth["intr"][0, 0])   # ... towards the truth
+
+
+def test_refine_camera_params_medium(mm, orc):
+    flat, _ = synthetic.make_ba_problem(outlier_frac=0.0, refine_camera_params=True, **synthetic.BA_CONFIGS["small"])
+    flat.intr[0, :2] *= 0.995
+    _assert_parity(*_both(orc, flat, 8))
+
+
 def test_cfg1_parity(mm, orc):
     # BASELINE.json configs[0]: 20-image PINHOLE sequence
     flat, _ = synthetic.make_ba_problem(**synthetic.BA_CONFIGS["cfg1"])
