@@ -28,7 +28,7 @@
 namespace mm {
 
 constexpr int TC_M = 128, TC_N = 256, TC_KB = 32;           // tile rows, tile cols, K elements per stage (128 B)
-constexpr int TC_STAGES = 4;
+constexpr int TC_STAGES = 3;
 constexpr int TC_A_BYTES = TC_M * TC_KB * 4, TC_B_BYTES = TC_N * TC_KB * 4, TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 constexpr int TC_THREADS = 320;                               // warp0 TMA, warp1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 constexpr int TC_C = 8;                                       // candidates kept per row
@@ -79,6 +79,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major operand, 128-byte swizzle: rows are 128 B apart, 8-row atoms
@@ -124,18 +129,15 @@ __global__ void k_tc_prep(const float* __restrict__ desc, int64_t rows, int K, i
 }
 
 // ---------------------------------------------------------------- the tensor-core kernel
-// branch-free insertion into the ascending list; strict '<' keeps the earlier (lower) column on ties
-__device__ __forceinline__ void cand_insert(float v, int j, float (&cv)[TC_C], int (&ci)[TC_C]) {
-  bool lt[TC_C];
+// Candidates are kept as packed 32-bit keys: the bit pattern of the (positive) approximate value with its low
+// TC_IDX_BITS mantissa bits replaced by the column index.  Unsigned integer order == (value, column) order, so a
+// sorted insertion is a min/max network (2 instructions per slot, no index bookkeeping, ties -> lower column).
+// The 2^-10 relative perturbation of the value is accounted for in k_rerank's bound.
+constexpr int TC_IDX_BITS = 13;                      // columns per direction <= 8192 on this path
+constexpr uint32_t TC_IDX_MASK = (1u << TC_IDX_BITS) - 1u;
+__device__ __forceinline__ void cand_insert(uint32_t key, uint32_t (&ck)[TC_C]) {
 #pragma unroll
-  for (int c = 0; c < TC_C; ++c) lt[c] = v < cv[c];
-#pragma unroll
-  for (int c = TC_C - 1; c > 0; --c) {
-    cv[c] = lt[c - 1] ? cv[c - 1] : (lt[c] ? v : cv[c]);
-    ci[c] = lt[c - 1] ? ci[c - 1] : (lt[c] ? j : ci[c]);
-  }
-  cv[0] = lt[0] ? v : cv[0];
-  ci[0] = lt[0] ? j : ci[0];
+  for (int c = 0; c < TC_C; ++c) { const uint32_t lo = min(ck[c], key); key = max(ck[c], key); ck[c] = lo; }
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(
@@ -148,8 +150,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + TC_STAGES * TC_STAGE_BYTES);
   // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, then tmem ptr
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
-  float* merge_v = reinterpret_cast<float*>(bars + 2 * TC_STAGES + 6);          // [128][TC_C]
-  int* merge_i = reinterpret_cast<int*>(merge_v + TC_M * TC_C);                  // [128][TC_C]
+  uint32_t* merge_k = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 6);   // [128][TC_C]
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + TC_STAGES);
   const uint32_t bar_tfull = smem_u32(bars + 2 * TC_STAGES), bar_tempty = smem_u32(bars + 2 * TC_STAGES + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -220,30 +221,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const TcItem w = items[it];
       const int n_tiles = (w.nB + TC_N - 1) / TC_N;
-      float cv[TC_C]; int ci[TC_C];
+      uint32_t ck[TC_C];
 #pragma unroll
-      for (int c = 0; c < TC_C; ++c) { cv[c] = FLT_MAX; ci[c] = -1; }
+      for (int c = 0; c < TC_C; ++c) ck[c] = 0xFFFFFFFFu;
       for (int nt = 0; nt < n_tiles; ++nt) {
         mbar_wait(bar_tfull + 8 * acc, acc_phase);
         tc_fence_after();
         const int col0 = nt * TC_N + half * (TC_N / 2);
         const int ncols = min(TC_N / 2, w.nB - col0);          // may be <= 0 for the second half of the last tile
+        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TC_N + half * (TC_N / 2);
+        // software pipeline over the 4 chunks of 32 columns: the TMEM load of chunk c+1 is in flight while chunk c is scanned
+        uint32_t va[32], vb[32];
+        if (ncols > 0) tmem_ld32(tbase, va);
+#pragma unroll
         for (int ch = 0; ch < TC_N / 64; ++ch) {
           if (ch * 32 >= ncols) break;                          // warp-uniform
-          uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * TC_N + half * (TC_N / 2) + ch * 32, v);
+          uint32_t (&v)[32] = (ch & 1) ? vb : va;
           tmem_ld_wait();
+          if ((ch + 1) * 32 < ncols && ch + 1 < TC_N / 64) tmem_ld32(tbase + (ch + 1) * 32, (ch & 1) ? va : vb);
           const int lim = min(32, ncols - ch * 32);
-          const float thr = cv[TC_C - 1];
+          const uint32_t thr = ck[TC_C - 1];              // values are positive floats: unsigned bit order == numeric order
           uint32_t mask = 0;
 #pragma unroll
-          for (int e = 0; e < 32; ++e) mask |= (__uint_as_float(v[e]) < thr) ? (1u << e) : 0u;
+          for (int e = 0; e < 32; ++e) mask |= (v[e] < thr) ? (1u << e) : 0u;
           if (lim < 32) mask &= (1u << lim) - 1u;
-          const uint32_t umask = __reduce_or_sync(0xffffffffu, mask);
-          if (umask) {                                          // warp-uniform: some row of this warp has a new candidate
-#pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (umask & (1u << e)) cand_insert((mask >> e) & 1u ? __uint_as_float(v[e]) : FLT_MAX, col0 + ch * 32 + e, cv, ci);
+          uint32_t umask = __reduce_or_sync(0xffffffffu, mask);
+          // warp-uniform loop over the columns in which some row of this warp has a new candidate; flagged columns are
+          // re-read from TMEM (uniform address, no dynamically indexed registers), four loads in flight per wait
+          const uint32_t tcol = tbase + ch * 32;
+          const int cbase = col0 + ch * 32;
+          while (umask) {
+            const int e0 = __ffs(umask) - 1; umask &= umask - 1;
+            const int e1 = umask ? __ffs(umask) - 1 : -1; if (e1 >= 0) umask &= umask - 1;
+            const int e2 = umask ? __ffs(umask) - 1 : -1; if (e2 >= 0) umask &= umask - 1;
+            const int e3 = umask ? __ffs(umask) - 1 : -1; if (e3 >= 0) umask &= umask - 1;
+            uint32_t w0 = tmem_ld1(tcol + e0), w1 = 0, w2 = 0, w3 = 0;
+            if (e1 >= 0) w1 = tmem_ld1(tcol + e1);
+            if (e2 >= 0) w2 = tmem_ld1(tcol + e2);
+            if (e3 >= 0) w3 = tmem_ld1(tcol + e3);
+            tmem_ld_wait();
+            cand_insert((mask >> e0) & 1u ? ((w0 & ~TC_IDX_MASK) | (uint32_t)(cbase + e0)) : 0xFFFFFFFFu, ck);
+            if (e1 >= 0) cand_insert((mask >> e1) & 1u ? ((w1 & ~TC_IDX_MASK) | (uint32_t)(cbase + e1)) : 0xFFFFFFFFu, ck);
+            if (e2 >= 0) cand_insert((mask >> e2) & 1u ? ((w2 & ~TC_IDX_MASK) | (uint32_t)(cbase + e2)) : 0xFFFFFFFFu, ck);
+            if (e3 >= 0) cand_insert((mask >> e3) & 1u ? ((w3 & ~TC_IDX_MASK) | (uint32_t)(cbase + e3)) : 0xFFFFFFFFu, ck);
           }
         }
         tc_fence_before();
@@ -254,17 +274,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(
       // merge the two column halves of each row (half 1 -> smem -> half 0), then write the candidates
       if (half == 1) {
 #pragma unroll
-        for (int c = 0; c < TC_C; ++c) { merge_v[row_in_tile * TC_C + c] = cv[c]; merge_i[row_in_tile * TC_C + c] = ci[c]; }
+        for (int c = 0; c < TC_C; ++c) merge_k[row_in_tile * TC_C + c] = ck[c];
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (half == 0) {
 #pragma unroll
-        for (int c = 0; c < TC_C; ++c) { const int j = merge_i[row_in_tile * TC_C + c]; if (j >= 0) cand_insert(merge_v[row_in_tile * TC_C + c], j, cv, ci); }
+        for (int c = 0; c < TC_C; ++c) cand_insert(merge_k[row_in_tile * TC_C + c], ck);
         if (row_in_tile < w.nA) {
           TcCand o;
 #pragma unroll
-          for (int c = 0; c < TC_C; ++c) o.idx[c] = ci[c];
-          o.worst = cv[TC_C - 1];
+          for (int c = 0; c < TC_C; ++c) o.idx[c] = ck[c] == 0xFFFFFFFFu ? -1 : (int)(ck[c] & TC_IDX_MASK);
+          o.worst = __uint_as_float(ck[TC_C - 1] & ~TC_IDX_MASK);      // floor of the 8th approximate value
           cand[w.out_off + row_in_tile] = o;
         }
       }
@@ -294,36 +314,52 @@ struct RerankJob { int rowA0, nA, rowB0, nB; int64_t out_off; int64_t knn_off; f
 
 // thread per query row.  eps: both operands are RN-rounded to TF32 (relative error <= 2^-11 each), so the cross term
 // -2 a.b is off by at most 2 * 2^-10 * sum|a_k b_k| <= 2^-9 |a| |b|; the 1e-5 term covers fp32 accumulation and the norm splits.
-__global__ void k_rerank(const RerankJob* __restrict__ jobs, const float* __restrict__ desc, const float* __restrict__ norms, int K,
+// The TC_C exact sums are accumulated side by side (independent chains), each still strictly in ascending k with
+// separate multiply and add, i.e. bit-identical to exact_d2().
+__global__ void __launch_bounds__(128) k_rerank(const RerankJob* __restrict__ jobs, const float* __restrict__ desc, const float* __restrict__ norms, int K,
                          const TcCand* __restrict__ cand, Knn2* __restrict__ knn, int* __restrict__ flagged, int* __restrict__ n_flagged, int flag_cap) {
   const RerankJob job = jobs[blockIdx.y];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= job.nA) return;
   const TcCand c = cand[job.out_off + i];
   const float* a = desc + (size_t)(job.rowA0 + i) * K;
-  float b0 = FLT_MAX, b1 = FLT_MAX; int i0 = -1, i1 = -1;
-  double e2[TC_C]; int nvalid = 0;
+  const float* bp[TC_C]; bool ok[TC_C]; double e2[TC_C];
+  int nvalid = 0;
 #pragma unroll
   for (int k = 0; k < TC_C; ++k) {
-    e2[k] = 0.0;
-    if (c.idx[k] >= 0 && c.idx[k] < job.nB) {
-      e2[k] = exact_d2(a, desc + (size_t)(job.rowB0 + c.idx[k]) * K, K);
-      top2_insert_f(__fsqrt_rn((float)e2[k]), c.idx[k], b0, i0, b1, i1);
-      ++nvalid;
+    ok[k] = c.idx[k] >= 0 && c.idx[k] < job.nB;
+    bp[k] = desc + (size_t)(job.rowB0 + (ok[k] ? c.idx[k] : 0)) * K;
+    e2[k] = 0.0; nvalid += ok[k];
+  }
+  for (int k0 = 0; k0 < K; k0 += 4) {           // K % 4 == 0 on this path
+    const float4 av = *reinterpret_cast<const float4*>(a + k0);
+    float4 bv[TC_C];
+#pragma unroll
+    for (int k = 0; k < TC_C; ++k) bv[k] = *reinterpret_cast<const float4*>(bp[k] + k0);
+#pragma unroll
+    for (int k = 0; k < TC_C; ++k) {
+      double t;
+      t = (double)av.x - (double)bv[k].x; e2[k] = __dadd_rn(e2[k], __dmul_rn(t, t));
+      t = (double)av.y - (double)bv[k].y; e2[k] = __dadd_rn(e2[k], __dmul_rn(t, t));
+      t = (double)av.z - (double)bv[k].z; e2[k] = __dadd_rn(e2[k], __dmul_rn(t, t));
+      t = (double)av.w - (double)bv[k].w; e2[k] = __dadd_rn(e2[k], __dmul_rn(t, t));
     }
   }
+  float b0 = FLT_MAX, b1 = FLT_MAX; int i0 = -1, i1 = -1;
+#pragma unroll
+  for (int k = 0; k < TC_C; ++k) if (ok[k]) top2_insert_f(__fsqrt_rn((float)e2[k]), c.idx[k], b0, i0, b1, i1);
   Knn2 r; r.d0 = b0; r.d1 = b1; r.i0 = i0; r.i1 = i1;
   bool safe = true;
   if (job.nB > TC_C) {
     if (nvalid < TC_C) safe = false;
     else {
-      // exact squared distance of the second best among the candidates
-      double s2 = 0.0;
+      double s2 = 0.0;              // exact squared distance of the second best among the candidates
 #pragma unroll
       for (int k = 0; k < TC_C; ++k) if (c.idx[k] == i1) s2 = e2[k];
       const double na = (double)norms[job.rowA0 + i];
       const double eps = 0.001953125 * 1.02 * sqrt(na) * (double)job.bmax + 1e-5 * (na + (double)job.bmax * (double)job.bmax + 1.0);
-      const double lower_bound_others = ((double)c.worst - 1.0) - eps;      // every non-candidate has exact d^2 >= this
+      // every non-candidate's packed key is >= the 8th key, so its approximate value exceeds worst (1 - 2^-10)
+      const double lower_bound_others = (double)c.worst * (1.0 - 0.0009765625) - 1.0 - eps;      // exact d^2 of any non-candidate >= this
       safe = s2 * (1.0 + 1e-6) + 1e-30 < lower_bound_others;
     }
   }
@@ -432,6 +468,9 @@ int match_tc_pairs(const float* desc, const float* xy, int K, const int64_t* off
   if (max_distance != -1.0) { if (required) set_error("the tcgen05 path does not take the keypoint-distance mask"); return MM_ERR_UNSUPPORTED; }
   if (K % 4 != 0 || K < 8 || K > 1024) { if (required) set_error("tcgen05 path needs K %% 4 == 0"); return MM_ERR_UNSUPPORTED; }
   if (getenv("MM_MATCH_NO_TC") && !required) return MM_ERR_UNSUPPORTED;
+  for (int p = 0; p < n_pairs; ++p) if (jobs_host[p].n1 > (1 << TC_IDX_BITS) || jobs_host[p].n2 > (1 << TC_IDX_BITS)) {
+    if (required) set_error("tcgen05 path packs the column index in %d bits: at most %d descriptors per image", TC_IDX_BITS, 1 << TC_IDX_BITS);
+    return MM_ERR_UNSUPPORTED; }
   // the whole descriptor array of the set: its row count is the offset past the last image referenced
   const int64_t rows = total_rows;
   // prepared copies are keyed by the base pointer; use the full extent the set was created with when known
@@ -471,7 +510,7 @@ int match_tc_pairs(const float* desc, const float* xy, int K, const int64_t* off
   MM_CUDA(cudaMemsetAsync(g_scr.cand.p, 0xFF, sizeof(TcCand) * (size_t)cand_rows, st));
   if (!items.empty()) {
     MM_CUDA(cudaMemcpyAsync(g_scr.items.p, items.data(), sizeof(TcItem) * items.size(), cudaMemcpyHostToDevice, st));
-    const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 + 256 + (size_t)TC_M * TC_C * 8;
+    const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 + 256 + (size_t)TC_M * TC_C * 4;
     static bool configured = false;
     if (!configured) { MM_CUDA(cudaFuncSetAttribute(k_match_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
     const int grid = std::min((int)items.size(), num_sms());

@@ -291,6 +291,12 @@ static int assemble_and_factor(ba_t* B) {
   }
   if (fail) return 0;
   for (int i = 0; i < nc; ++i) *S_at(B, i, i) += B->diag_c[i];
+  { const char* dump = getenv("ORC_DUMP_S");     /* debugging aid: reduced system in skyline form */
+    static int dump_count = 0;
+    if (dump && ++dump_count == (getenv("ORC_DUMP_AT") ? atoi(getenv("ORC_DUMP_AT")) : 3)) {
+      FILE* f = fopen(dump, "wb");
+      if (f) { fwrite(&nc, sizeof(int), 1, f); fwrite(B->first, sizeof(int), (size_t)nc, f); fwrite(B->rowptr, sizeof(int64_t), (size_t)nc + 1, f);
+               fwrite(B->S, sizeof(double), (size_t)B->rowptr[nc], f); fwrite(B->rhs, sizeof(double), (size_t)nc, f); fclose(f); } } }
   /* left-looking skyline Cholesky, rows stored contiguously */
   for (int j = 0; j < nc; ++j) {
     double* Lj = B->S + B->rowptr[j]; const int fj = B->first[j];
