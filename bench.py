@@ -165,7 +165,13 @@ def main():
     import torch.distributed as dist
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on stdout when the first communicator comes up: keep stdout for the JSON line only
+        sys.stdout.flush(); saved = os.dup(1); os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            warm = torch.zeros(1, device="cuda"); dist.all_reduce(warm); torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
     from mavmap_b200 import _lib, synthetic
     from mavmap_b200.ba import BASession, solve_flat
     from mavmap_b200.matching import MatchSet

@@ -17,6 +17,7 @@
 #include <float.h>
 #include <vector>
 #include <algorithm>
+#include <mutex>
 #include "common.cuh"
 #include "match.cuh"
 
@@ -345,6 +346,13 @@ int mm_match_set_pairs(mm_match_set* s, const int32_t* ia, const int32_t* ib, in
   return MM_OK;
 }
 
+// one-pair entry point: a process-wide workspace keeps every device buffer (descriptors, TF32 operand copies,
+// top-2 lists, outputs) alive between calls, so a call costs two H2D copies, the kernels and one D2H of the matches
+static mm_match_set* g_pair_set = nullptr;
+static DevBuf<float> g_pair_desc, g_pair_xy, g_pair_dist; static DevBuf<int32_t> g_pair_q, g_pair_t, g_pair_cnt;
+static size_t g_pair_desc_cap = 0, g_pair_xy_cap = 0, g_pair_out_cap = 0;
+static std::mutex g_pair_mu;
+
 int mm_match_pair(const float* d1, int32_t n1, const float* d2, int32_t n2, int32_t k, const float* xy1, const float* xy2,
                   const mm_match_options* opt, int32_t* q, int32_t* t, float* dist, int32_t* n_out) {
   if (!opt || !n_out || n1 < 0 || n2 < 0 || k <= 0) { set_error("invalid argument"); return MM_ERR_INVALID_ARG; }
@@ -353,17 +361,38 @@ int mm_match_pair(const float* d1, int32_t n1, const float* d2, int32_t n2, int3
   if (n1 == 0 || n2 == 0) return MM_OK;          // matches.clear() (feature.cc:62) and nothing to add
   if (!d1 || !d2 || !q || !t || !dist) { set_error("null buffer"); return MM_ERR_INVALID_ARG; }
   if (opt->max_distance != -1.0 && (!xy1 || !xy2)) { set_error("max_distance >= 0 needs keypoints"); return MM_ERR_INVALID_ARG; }
-  std::vector<float> desc((size_t)(n1 + n2) * k); std::vector<float> xy;
-  memcpy(desc.data(), d1, sizeof(float) * (size_t)n1 * k); memcpy(desc.data() + (size_t)n1 * k, d2, sizeof(float) * (size_t)n2 * k);
-  if (xy1 && xy2) { xy.resize(2 * (size_t)(n1 + n2)); memcpy(xy.data(), xy1, sizeof(float) * 2 * (size_t)n1); memcpy(xy.data() + 2 * (size_t)n1, xy2, sizeof(float) * 2 * (size_t)n2); }
+  std::lock_guard<std::mutex> lk(g_pair_mu);
+  const size_t rows = (size_t)n1 + (size_t)n2, need = (rows + 256) * (size_t)k;
+  if (need > g_pair_desc_cap) { match_tc_release(g_pair_desc.p); MM_CUDA(g_pair_desc.alloc(need + need / 2)); g_pair_desc_cap = need + need / 2; }
+  const bool use_xy = xy1 && xy2;
+  if (use_xy && 2 * rows > g_pair_xy_cap) { MM_CUDA(g_pair_xy.alloc(3 * rows)); g_pair_xy_cap = 3 * rows; }
+  const size_t cap = (size_t)std::min(n1, n2);
+  if (cap > g_pair_out_cap) { MM_CUDA(g_pair_q.alloc(2 * cap)); MM_CUDA(g_pair_t.alloc(2 * cap)); MM_CUDA(g_pair_dist.alloc(2 * cap)); g_pair_out_cap = 2 * cap; if (!g_pair_cnt.p) MM_CUDA(g_pair_cnt.alloc(1)); }
+  MM_CUDA(cudaMemcpyAsync(g_pair_desc.p, d1, sizeof(float) * (size_t)n1 * k, cudaMemcpyHostToDevice, nullptr));
+  MM_CUDA(cudaMemcpyAsync(g_pair_desc.p + (size_t)n1 * k, d2, sizeof(float) * (size_t)n2 * k, cudaMemcpyHostToDevice, nullptr));
+  if (use_xy) {
+    MM_CUDA(cudaMemcpyAsync(g_pair_xy.p, xy1, sizeof(float) * 2 * (size_t)n1, cudaMemcpyHostToDevice, nullptr));
+    MM_CUDA(cudaMemcpyAsync(g_pair_xy.p + 2 * (size_t)n1, xy2, sizeof(float) * 2 * (size_t)n2, cudaMemcpyHostToDevice, nullptr));
+  }
+  if (!g_pair_set) g_pair_set = new mm_match_set();
+  mm_match_set* s = g_pair_set;
   int32_t counts[2] = { n1, n2 };
-  mm_match_set* s = nullptr;
-  rc = mm_match_set_create(desc.data(), xy.empty() ? nullptr : xy.data(), counts, 2, k, &s); if (rc) return rc;
-  int32_t ia = 0, ib = 1; int64_t off[2] = {0, 0};
-  rc = mm_match_set_pairs(s, &ia, &ib, 1, opt, off, q, t, dist, std::min(n1, n2));
-  if (rc == MM_OK) *n_out = (int32_t)off[1];
-  mm_match_set_destroy(s);
-  return rc;
+  s->max_count = 0;
+  rc = set_init(s, counts, 2, k); if (rc) return rc;
+  s->desc = g_pair_desc.p; s->xy = use_xy ? g_pair_xy.p : nullptr;
+  match_tc_invalidate(s->desc);                 // same buffer, new contents: the TF32 operand copies must be refreshed
+  int32_t ia = 0, ib = 1;
+  rc = match_pairs_device(s, &ia, &ib, 1, opt, g_pair_cnt.p, g_pair_q.p, g_pair_t.p, g_pair_dist.p, (int)cap, nullptr); if (rc) return rc;
+  int32_t c = 0;
+  MM_CUDA(cudaMemcpy(&c, g_pair_cnt.p, sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (c > 0) {
+    MM_CUDA(cudaMemcpyAsync(q, g_pair_q.p, sizeof(int32_t) * (size_t)c, cudaMemcpyDeviceToHost, nullptr));
+    MM_CUDA(cudaMemcpyAsync(t, g_pair_t.p, sizeof(int32_t) * (size_t)c, cudaMemcpyDeviceToHost, nullptr));
+    MM_CUDA(cudaMemcpyAsync(dist, g_pair_dist.p, sizeof(float) * (size_t)c, cudaMemcpyDeviceToHost, nullptr));
+    MM_CUDA(cudaStreamSynchronize(nullptr));
+  }
+  *n_out = c;
+  return MM_OK;
 }
 
 }  // extern "C"

@@ -26,6 +26,8 @@ int match_tc_pairs(const float* desc, const float* xy, int K, const int64_t* off
 
 // drop the TF32 operand copies cached for a descriptor array (call before the array is freed)
 void match_tc_release(const float* desc);
+// the descriptor array at `desc` was overwritten: refresh the cached copies on next use (buffers are kept)
+void match_tc_invalidate(const float* desc);
 void match_tc_stats(uint64_t* rows, uint64_t* flagged);
 
 }  // namespace mm

@@ -408,7 +408,7 @@ EncodeTiledFn get_encode() {
 }
 
 struct Prepared {           // TF32 operand copies of one descriptor array
-  const float* desc = nullptr; int64_t rows = 0; int K = 0, Kp = 0;
+  const float* desc = nullptr; int64_t rows = 0; int K = 0, Kp = 0; bool valid = false; int64_t cap_rows = 0;
   DevBuf<float> PA, PB, norms; CUtensorMap mapA, mapB; std::vector<float> h_norm_max;   // per call computed lazily
   std::vector<float> h_norms;
 };
@@ -428,22 +428,35 @@ int make_map(CUtensorMap* map, float* base, int64_t rows, int Kp, int box_rows) 
   return MM_OK;
 }
 
-int get_prepared(const float* desc, int64_t rows, int K, cudaStream_t st, Prepared** out) {
-  std::lock_guard<std::mutex> lk(g_prep_mu);
-  for (Prepared* p : g_prepared) if (p->desc == desc && p->rows == rows && p->K == K) { *out = p; return MM_OK; }
-  Prepared* p = new Prepared(); p->desc = desc; p->rows = rows; p->K = K; p->Kp = (K + 4 + TC_KB - 1) / TC_KB * TC_KB;
+int fill_prepared(Prepared* p, int64_t rows, cudaStream_t st) {
   const int64_t prow = rows + TC_N;       // slack rows so every TMA box starts in bounds
-  if (p->PA.alloc((size_t)prow * p->Kp) != cudaSuccess || p->PB.alloc((size_t)prow * p->Kp) != cudaSuccess || p->norms.alloc((size_t)rows + 1) != cudaSuccess) {
-    delete p; cudaGetLastError(); set_error("cudaMalloc failed for the TF32 operand copies"); return MM_ERR_ALLOC; }
-  MM_CUDA(cudaMemsetAsync(p->PA.p, 0, sizeof(float) * (size_t)prow * p->Kp, st));
-  MM_CUDA(cudaMemsetAsync(p->PB.p, 0, sizeof(float) * (size_t)prow * p->Kp, st));
-  k_tc_prep<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(desc, rows, K, p->Kp, p->PA.p, p->PB.p, p->norms.p);
+  p->rows = rows;
+  MM_CUDA(cudaMemsetAsync(p->PA.p + (size_t)rows * p->Kp, 0, sizeof(float) * (size_t)TC_N * p->Kp, st));
+  MM_CUDA(cudaMemsetAsync(p->PB.p + (size_t)rows * p->Kp, 0, sizeof(float) * (size_t)TC_N * p->Kp, st));
+  k_tc_prep<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(p->desc, rows, p->K, p->Kp, p->PA.p, p->PB.p, p->norms.p);
   MM_LAUNCH_CHECK();
   p->h_norms.resize((size_t)rows);
   MM_CUDA(cudaMemcpyAsync(p->h_norms.data(), p->norms.p, sizeof(float) * (size_t)rows, cudaMemcpyDeviceToHost, st));
   MM_CUDA(cudaStreamSynchronize(st));
-  int rc = make_map(&p->mapA, p->PA.p, prow, p->Kp, TC_M); if (rc) { delete p; return rc; }
-  rc = make_map(&p->mapB, p->PB.p, prow, p->Kp, TC_N); if (rc) { delete p; return rc; }
+  int rc = make_map(&p->mapA, p->PA.p, prow, p->Kp, TC_M); if (rc) return rc;
+  rc = make_map(&p->mapB, p->PB.p, prow, p->Kp, TC_N); if (rc) return rc;
+  p->valid = true;
+  return MM_OK;
+}
+
+int get_prepared(const float* desc, int64_t rows, int K, cudaStream_t st, Prepared** out) {
+  std::lock_guard<std::mutex> lk(g_prep_mu);
+  for (Prepared* p : g_prepared) if (p->desc == desc && p->K == K) {
+    if (p->valid && p->rows >= rows) { *out = p; return MM_OK; }
+    if (p->cap_rows >= rows) { int rc = fill_prepared(p, rows, st); if (rc) return rc; *out = p; return MM_OK; }
+  }
+  for (size_t i = 0; i < g_prepared.size(); ++i) if (g_prepared[i]->desc == desc) { delete g_prepared[i]; g_prepared.erase(g_prepared.begin() + i); --i; }
+  Prepared* p = new Prepared(); p->desc = desc; p->K = K; p->Kp = (K + 4 + TC_KB - 1) / TC_KB * TC_KB;
+  p->cap_rows = rows + rows / 2;
+  const int64_t prow = p->cap_rows + TC_N;
+  if (p->PA.alloc((size_t)prow * p->Kp) != cudaSuccess || p->PB.alloc((size_t)prow * p->Kp) != cudaSuccess || p->norms.alloc((size_t)p->cap_rows + 1) != cudaSuccess) {
+    delete p; cudaGetLastError(); set_error("cudaMalloc failed for the TF32 operand copies"); return MM_ERR_ALLOC; }
+  int rc = fill_prepared(p, rows, st); if (rc) { delete p; return rc; }
   g_prepared.push_back(p);
   *out = p;
   return MM_OK;
@@ -458,6 +471,10 @@ std::atomic<uint64_t> g_tc_rows{0}, g_tc_flagged{0};
 void match_tc_release(const float* desc) {
   std::lock_guard<std::mutex> lk(g_prep_mu);
   for (size_t i = 0; i < g_prepared.size(); ++i) if (g_prepared[i]->desc == desc) { delete g_prepared[i]; g_prepared.erase(g_prepared.begin() + i); --i; }
+}
+void match_tc_invalidate(const float* desc) {
+  std::lock_guard<std::mutex> lk(g_prep_mu);
+  for (Prepared* p : g_prepared) if (p->desc == desc) p->valid = false;
 }
 void match_tc_stats(uint64_t* rows, uint64_t* flagged) { *rows = g_tc_rows.load(); *flagged = g_tc_flagged.load(); }
 
@@ -476,7 +493,7 @@ int match_tc_pairs(const float* desc, const float* xy, int K, const int64_t* off
   // prepared copies are keyed by the base pointer; use the full extent the set was created with when known
   Prepared* P = nullptr;
   { std::lock_guard<std::mutex> lk(g_prep_mu);
-    for (Prepared* q : g_prepared) if (q->desc == desc && q->K == K && q->rows >= rows) { P = q; break; } }
+    for (Prepared* q : g_prepared) if (q->desc == desc && q->K == K && q->valid && q->rows >= rows) { P = q; break; } }
   if (!P) { int rc = get_prepared(desc, rows, K, st, &P); if (rc) return required ? rc : MM_ERR_UNSUPPORTED; }
 
   // work items: (pair, direction, 128-row block); knn12 and knn21 live in different arrays -> two candidate regions
