@@ -664,21 +664,44 @@ __global__ void __launch_bounds__(256) k_pcg_persistent(PcgArgs A) {
       double acc = 0.0;
       for (int row = gw; row < n; row += nw) {
         double y = 0.0;
-        if (lane < 30) {
-          for (int e = A.row_start[row] + g; e < A.row_start[row + 1]; e += 5) {
-            const int col = A.row_col[e], bid = A.row_blk[e];
-            const bool tr = bid < 0;
-            const double* B = A.S + 36 * (size_t)(tr ? -bid - 1 : bid);
-            const double* zc = A.z + 6 * (size_t)col; const double* pc = p_old + 6 * (size_t)col;
-            double pv[6];
+        {
+          // four rounds of five blocks at a time: all index loads, then all gathers and block rows, are in flight together
+          const int e0r = A.row_start[row], e1r = A.row_start[row + 1];
+          for (int base = e0r; base < e1r; base += 20) {
+            int col[4], bid[4]; bool okk[4];
 #pragma unroll
-            for (int c = 0; c < 6; ++c) pv[c] = __ldcg(zc + c) + beta * __ldcg(pc + c);
-            if (!tr) {
+            for (int k = 0; k < 4; ++k) {
+              const int e = base + 5 * k + g;
+              okk[k] = lane < 30 && e < e1r;
+              col[k] = okk[k] ? A.row_col[e] : 0; bid[k] = okk[k] ? A.row_blk[e] : 0;
+            }
+            double pv1[4], bk[4][6];
 #pragma unroll
-              for (int c = 0; c < 6; ++c) y += B[6 * rr_ + c] * pv[c];
-            } else {
+            for (int k = 0; k < 4; ++k) {
+              pv1[k] = 0.0;
 #pragma unroll
-              for (int c = 0; c < 6; ++c) y += B[6 * c + rr_] * pv[c];
+              for (int c = 0; c < 6; ++c) bk[k][c] = 0.0;
+              if (okk[k]) {
+                const bool tr = bid[k] < 0;
+                const double* B = A.S + 36 * (size_t)(tr ? -bid[k] - 1 : bid[k]);
+                const size_t ci = 6 * (size_t)col[k] + rr_;
+                pv1[k] = __ldcg(A.z + ci) + beta * __ldcg(p_old + ci);
+                if (!tr) {
+                  const double2* B2 = reinterpret_cast<const double2*>(B + 6 * rr_);
+                  const double2 b0 = B2[0], b1 = B2[1], b2 = B2[2];
+                  bk[k][0] = b0.x; bk[k][1] = b0.y; bk[k][2] = b1.x; bk[k][3] = b1.y; bk[k][4] = b2.x; bk[k][5] = b2.y;
+                } else {
+#pragma unroll
+                  for (int c = 0; c < 6; ++c) bk[k][c] = B[6 * c + rr_];
+                }
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (base + 5 * k < e1r) {                        // warp-uniform
+#pragma unroll
+                for (int c = 0; c < 6; ++c) { const double xc = __shfl_sync(0xffffffffu, pv1[k], 6 * g + c); y += bk[k][c] * xc; }
+              }
             }
           }
         }
