@@ -28,14 +28,14 @@
 namespace mm {
 
 constexpr int TC_M = 128, TC_N = 256, TC_KB = 32;           // tile rows, tile cols, K elements per stage (128 B)
-constexpr int TC_STAGES = 3;
-constexpr int TC_A_BYTES = TC_M * TC_KB * 4, TC_B_BYTES = TC_N * TC_KB * 4, TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr int TC_STAGES = 3;                                  // B-operand ring (32 KB per stage)
+constexpr int TC_MAX_KB = 6;                                  // A tile stays resident for a whole item: K' <= 192
+constexpr int TC_A_BYTES = TC_M * TC_KB * 4, TC_B_BYTES = TC_N * TC_KB * 4;
+constexpr int TC_HCAP = 32;                                   // hit slots per (row, column half)
 constexpr int TC_THREADS = 320;                               // warp0 TMA, warp1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
-constexpr int TC_C = 8;                                       // candidates kept per row
 constexpr uint32_t SPIN_LIMIT = 1u << 24;                     // watchdog: trap instead of hanging the GPU
 
-struct TcItem { int rowA0, nA, rowB0, nB; int64_t out_off; };  // one 128-row block of one direction of one pair
-struct TcCand { int idx[TC_C]; float worst; };
+struct TcItem { int rowA0, nA, rowB0, nB; int64_t out_off; float bmax; int pad; };  // one 128-row block of one direction of one pair
 
 // ---------------------------------------------------------------- PTX wrappers (sm_100a)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -129,35 +129,38 @@ __global__ void k_tc_prep(const float* __restrict__ desc, int64_t rows, int K, i
 }
 
 // ---------------------------------------------------------------- the tensor-core kernel
-// Candidates are kept as packed 32-bit keys: the bit pattern of the (positive) approximate value with its low
-// TC_IDX_BITS mantissa bits replaced by the column index.  Unsigned integer order == (value, column) order, so a
-// sorted insertion is a min/max network (2 instructions per slot, no index bookkeeping, ties -> lower column).
-// The 2^-10 relative perturbation of the value is accounted for in k_rerank's bound.
-constexpr int TC_IDX_BITS = 13;                      // columns per direction <= 8192 on this path
-constexpr uint32_t TC_IDX_MASK = (1u << TC_IDX_BITS) - 1u;
-__device__ __forceinline__ void cand_insert(uint32_t key, uint32_t (&ck)[TC_C]) {
-#pragma unroll
-  for (int c = 0; c < TC_C; ++c) { const uint32_t lo = min(ck[c], key); key = max(ck[c], key); ck[c] = lo; }
+// TF32 error bound of the approximate value 1 + |a-b|^2 (see k_rerank): both operands RN-rounded to TF32
+__device__ __forceinline__ float tc_eps(float na, float bmax) {
+  return 0.001953125f * 1.02f * sqrtf(na) * bmax + 1e-5f * (na + bmax * bmax + 1.0f);
 }
 
+// MODE 0 ("bound"): only the first ~1/4 of the column tiles; every row keeps the two smallest approximate values seen
+//          -> bound[row] = 2nd smallest over that column subset, an upper bound of the row's true 2nd-nearest value.
+// MODE 1 ("collect"): all column tiles; the epilogue only compares against the per-row threshold
+//          T = bound + 2 eps (+ rounding slack) and appends the (rare) columns below it to the row's hit list.
+//          Every column that can be in the exact top-2 is below T, so the hit lists are complete by construction.
+template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(
     const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-    const TcItem* __restrict__ items, int n_items, int num_kb, TcCand* __restrict__ cand) {
+    const TcItem* __restrict__ items, int n_items, int num_kb, const float* __restrict__ norms,
+    float* __restrict__ bound, int* __restrict__ hits, int* __restrict__ hcnt) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: stages (1024-aligned), then barriers
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + TC_STAGES * TC_STAGE_BYTES);
-  // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, then tmem ptr
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
-  uint32_t* merge_k = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 6);   // [128][TC_C]
+  const uint32_t smem_a = smem_base, smem_b = smem_base + TC_MAX_KB * TC_A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + TC_MAX_KB * TC_A_BYTES + TC_STAGES * TC_B_BYTES);
+  // bars: [0..S) b_full, [S..2S) b_empty, 2S a_full, 2S+1 a_empty, [2S+2..2S+4) tmem_full, [2S+4..2S+6) tmem_empty
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 6);
+  float* merge_f = reinterpret_cast<float*>(bars + 2 * TC_STAGES + 8);           // [128][2]
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + TC_STAGES);
-  const uint32_t bar_tfull = smem_u32(bars + 2 * TC_STAGES), bar_tempty = smem_u32(bars + 2 * TC_STAGES + 2);
+  const uint32_t bar_afull = smem_u32(bars + 2 * TC_STAGES), bar_aempty = smem_u32(bars + 2 * TC_STAGES + 1);
+  const uint32_t bar_tfull = smem_u32(bars + 2 * TC_STAGES + 2), bar_tempty = smem_u32(bars + 2 * TC_STAGES + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapB);
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_afull, 1); mbar_init(bar_aempty, 1);
     for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 8); }
     fence_barrier_init();
   }
@@ -166,21 +169,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  auto tiles_of = [](int nB) { const int n = (nB + TC_N - 1) / TC_N; return MODE == 0 ? max(1, (n + 3) / 4) : n; };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
+      uint32_t stage = 0, phase = 0, aphase = 0;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const TcItem w = items[it];
-        const int n_tiles = (w.nB + TC_N - 1) / TC_N;
+        const int n_tiles = tiles_of(w.nB);
+        mbar_wait(bar_aempty, aphase ^ 1);                        // MMAs of the previous item have retired: A region is free
+        mbar_expect_tx(bar_afull, (uint32_t)num_kb * TC_A_BYTES);
+        for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(smem_a + kb * TC_A_BYTES, &mapA, bar_afull, kb * TC_KB, w.rowA0);
+        aphase ^= 1;
         for (int nt = 0; nt < n_tiles; ++nt)
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-            const uint32_t sa = smem_base + stage * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
-            mbar_expect_tx(bar_full + 8 * stage, TC_STAGE_BYTES);
-            tma_load_2d(sa, &mapA, bar_full + 8 * stage, kb * TC_KB, w.rowA0);
-            tma_load_2d(sb, &mapB, bar_full + 8 * stage, kb * TC_KB, w.rowB0 + nt * TC_N);
+            mbar_expect_tx(bar_full + 8 * stage, TC_B_BYTES);
+            tma_load_2d(smem_b + stage * TC_B_BYTES, &mapB, bar_full + 8 * stage, kb * TC_KB, w.rowB0 + nt * TC_N);
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           }
       }
@@ -189,10 +195,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_tf32(TC_M, TC_N);
-      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, aphase = 0;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const TcItem w = items[it];
-        const int n_tiles = (w.nB + TC_N - 1) / TC_N;
+        const int n_tiles = tiles_of(w.nB);
+        mbar_wait(bar_afull, aphase); aphase ^= 1;
+        tc_fence_after();
         for (int nt = 0; nt < n_tiles; ++nt) {
           mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);          // epilogue has drained this accumulator
           tc_fence_after();
@@ -200,17 +208,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(bar_full + 8 * stage, phase);
             tc_fence_after();
-            const uint32_t sa = smem_base + stage * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
-            const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sb);
+            const uint64_t da = umma_desc_sw128(smem_a + kb * TC_A_BYTES), db = umma_desc_sw128(smem_b + stage * TC_B_BYTES);
 #pragma unroll
             for (int k = 0; k < TC_KB / 8; ++k)                    // UMMA_K = 8 tf32 = 32 bytes -> +2 in the (addr >> 4) field
               umma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-            umma_commit(bar_empty + 8 * stage);                    // frees the smem stage when these MMAs retire
+            umma_commit(bar_empty + 8 * stage);                    // frees the B stage when these MMAs retire
             if (kb == num_kb - 1) umma_commit(bar_tfull + 8 * acc);  // accumulator ready for the epilogue
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           }
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        umma_commit(bar_aempty);                                   // A region reusable once every MMA of this item retired
       }
     }
   } else {
@@ -220,50 +228,50 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(
     uint32_t acc = 0, acc_phase = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const TcItem w = items[it];
-      const int n_tiles = (w.nB + TC_N - 1) / TC_N;
-      uint32_t ck[TC_C];
-#pragma unroll
-      for (int c = 0; c < TC_C; ++c) ck[c] = 0xFFFFFFFFu;
+      const int n_tiles = tiles_of(w.nB);
+      const bool row_ok = row_in_tile < w.nA;
+      float m1 = FLT_MAX, m2 = FLT_MAX;                            // MODE 0: two smallest values
+      float T = 0.f; int cnt = 0;                                   // MODE 1: threshold, hits so far
+      int* my_hits = nullptr;
+      if (MODE == 1) {
+        const int64_t r = w.out_off + (row_ok ? row_in_tile : 0);
+        const float bd = bound[r];
+        const float na = norms[w.rowA0 + (row_ok ? row_in_tile : 0)];
+        T = row_ok ? (bd + 2.0f * tc_eps(na, w.bmax)) * (1.0f + 4e-6f) : -1.f;    // FLT_MAX bound stays +inf
+        my_hits = hits + (r * 2 + half) * TC_HCAP;
+      }
       for (int nt = 0; nt < n_tiles; ++nt) {
         mbar_wait(bar_tfull + 8 * acc, acc_phase);
         tc_fence_after();
         const int col0 = nt * TC_N + half * (TC_N / 2);
-        const int ncols = min(TC_N / 2, w.nB - col0);          // may be <= 0 for the second half of the last tile
+        const int ncols = min(TC_N / 2, w.nB - col0);               // may be <= 0 for the second half of the last tile
         const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TC_N + half * (TC_N / 2);
-        // software pipeline over the 4 chunks of 32 columns: the TMEM load of chunk c+1 is in flight while chunk c is scanned
         uint32_t va[32], vb[32];
         if (ncols > 0) tmem_ld32(tbase, va);
 #pragma unroll
         for (int ch = 0; ch < TC_N / 64; ++ch) {
-          if (ch * 32 >= ncols) break;                          // warp-uniform
+          if (ch * 32 >= ncols) break;                              // warp-uniform
           uint32_t (&v)[32] = (ch & 1) ? vb : va;
           tmem_ld_wait();
           if ((ch + 1) * 32 < ncols && ch + 1 < TC_N / 64) tmem_ld32(tbase + (ch + 1) * 32, (ch & 1) ? va : vb);
           const int lim = min(32, ncols - ch * 32);
-          const uint32_t thr = ck[TC_C - 1];              // values are positive floats: unsigned bit order == numeric order
-          uint32_t mask = 0;
+          if (MODE == 0) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) mask |= (v[e] < thr) ? (1u << e) : 0u;
-          if (lim < 32) mask &= (1u << lim) - 1u;
-          uint32_t umask = __reduce_or_sync(0xffffffffu, mask);
-          // warp-uniform loop over the columns in which some row of this warp has a new candidate; flagged columns are
-          // re-read from TMEM (uniform address, no dynamically indexed registers), four loads in flight per wait
-          const uint32_t tcol = tbase + ch * 32;
-          const int cbase = col0 + ch * 32;
-          while (umask) {
-            const int e0 = __ffs(umask) - 1; umask &= umask - 1;
-            const int e1 = umask ? __ffs(umask) - 1 : -1; if (e1 >= 0) umask &= umask - 1;
-            const int e2 = umask ? __ffs(umask) - 1 : -1; if (e2 >= 0) umask &= umask - 1;
-            const int e3 = umask ? __ffs(umask) - 1 : -1; if (e3 >= 0) umask &= umask - 1;
-            uint32_t w0 = tmem_ld1(tcol + e0), w1 = 0, w2 = 0, w3 = 0;
-            if (e1 >= 0) w1 = tmem_ld1(tcol + e1);
-            if (e2 >= 0) w2 = tmem_ld1(tcol + e2);
-            if (e3 >= 0) w3 = tmem_ld1(tcol + e3);
-            tmem_ld_wait();
-            cand_insert((mask >> e0) & 1u ? ((w0 & ~TC_IDX_MASK) | (uint32_t)(cbase + e0)) : 0xFFFFFFFFu, ck);
-            if (e1 >= 0) cand_insert((mask >> e1) & 1u ? ((w1 & ~TC_IDX_MASK) | (uint32_t)(cbase + e1)) : 0xFFFFFFFFu, ck);
-            if (e2 >= 0) cand_insert((mask >> e2) & 1u ? ((w2 & ~TC_IDX_MASK) | (uint32_t)(cbase + e2)) : 0xFFFFFFFFu, ck);
-            if (e3 >= 0) cand_insert((mask >> e3) & 1u ? ((w3 & ~TC_IDX_MASK) | (uint32_t)(cbase + e3)) : 0xFFFFFFFFu, ck);
+            for (int e = 0; e < 32; ++e) {
+              const float x = e < lim ? __uint_as_float(v[e]) : FLT_MAX;
+              m2 = fminf(m2, fmaxf(m1, x)); m1 = fminf(m1, x);
+            }
+          } else {
+            uint32_t mask = 0;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) mask |= (__uint_as_float(v[e]) <= T) ? (1u << e) : 0u;
+            if (lim < 32) mask &= (1u << lim) - 1u;
+            uint32_t umask = __reduce_or_sync(0xffffffffu, mask);
+            const int cbase = col0 + ch * 32;
+            while (umask) {                                         // warp-uniform; a handful of columns per row in total
+              const int e = __ffs(umask) - 1; umask &= umask - 1;
+              if ((mask >> e) & 1u) { if (cnt < TC_HCAP) my_hits[cnt] = cbase + e; ++cnt; }
+            }
           }
         }
         tc_fence_before();
@@ -271,24 +279,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(
         if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      // merge the two column halves of each row (half 1 -> smem -> half 0), then write the candidates
-      if (half == 1) {
-#pragma unroll
-        for (int c = 0; c < TC_C; ++c) merge_k[row_in_tile * TC_C + c] = ck[c];
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (half == 0) {
-#pragma unroll
-        for (int c = 0; c < TC_C; ++c) cand_insert(merge_k[row_in_tile * TC_C + c], ck);
-        if (row_in_tile < w.nA) {
-          TcCand o;
-#pragma unroll
-          for (int c = 0; c < TC_C; ++c) o.idx[c] = ck[c] == 0xFFFFFFFFu ? -1 : (int)(ck[c] & TC_IDX_MASK);
-          o.worst = __uint_as_float(ck[TC_C - 1] & ~TC_IDX_MASK);      // floor of the 8th approximate value
-          cand[w.out_off + row_in_tile] = o;
+      if (MODE == 0) {
+        // merge the two column halves of each row (half 1 -> smem -> half 0)
+        if (half == 1) { merge_f[row_in_tile * 2] = m1; merge_f[row_in_tile * 2 + 1] = m2; }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (half == 0) {
+          const float o1 = merge_f[row_in_tile * 2], o2 = merge_f[row_in_tile * 2 + 1];
+          const float s2 = fminf(fmaxf(m1, o1), fminf(m2, o2));    // 2nd smallest of the union
+          if (row_ok) bound[w.out_off + row_in_tile] = s2;
         }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      } else {
+        if (row_ok) hcnt[(w.out_off + row_in_tile) * 2 + half] = cnt;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
   }
   tc_fence_before();
@@ -312,59 +315,52 @@ __device__ __forceinline__ void top2_insert_f(float d, int j, float& b0, int& i0
 
 struct RerankJob { int rowA0, nA, rowB0, nB; int64_t out_off; int64_t knn_off; float bmax; };
 
-// thread per query row.  eps: both operands are RN-rounded to TF32 (relative error <= 2^-11 each), so the cross term
-// -2 a.b is off by at most 2 * 2^-10 * sum|a_k b_k| <= 2^-9 |a| |b|; the 1e-5 term covers fp32 accumulation and the norm splits.
-// The TC_C exact sums are accumulated side by side (independent chains), each still strictly in ascending k with
-// separate multiply and add, i.e. bit-identical to exact_d2().
-__global__ void __launch_bounds__(128) k_rerank(const RerankJob* __restrict__ jobs, const float* __restrict__ desc, const float* __restrict__ norms, int K,
-                         const TcCand* __restrict__ cand, Knn2* __restrict__ knn, int* __restrict__ flagged, int* __restrict__ n_flagged, int flag_cap) {
+// thread per query row: exact fp64-accumulated distances (strictly ascending k, separate multiply and add — the same
+// arithmetic as match.cu and the oracle) of the row's hit columns, four independent chains at a time, then the exact
+// top-2 by (distance, index).  A row whose hit list overflowed is re-scanned exactly (k_rescan).
+__global__ void __launch_bounds__(128) k_rerank(const RerankJob* __restrict__ jobs, const float* __restrict__ desc, int K,
+                         const int* __restrict__ hits, const int* __restrict__ hcnt, Knn2* __restrict__ knn,
+                         int* __restrict__ flagged, int* __restrict__ n_flagged, int flag_cap) {
   const RerankJob job = jobs[blockIdx.y];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= job.nA) return;
-  const TcCand c = cand[job.out_off + i];
+  const int64_t r = job.out_off + i;
   const float* a = desc + (size_t)(job.rowA0 + i) * K;
-  const float* bp[TC_C]; bool ok[TC_C]; double e2[TC_C];
-  int nvalid = 0;
-#pragma unroll
-  for (int k = 0; k < TC_C; ++k) {
-    ok[k] = c.idx[k] >= 0 && c.idx[k] < job.nB;
-    bp[k] = desc + (size_t)(job.rowB0 + (ok[k] ? c.idx[k] : 0)) * K;
-    e2[k] = 0.0; nvalid += ok[k];
-  }
-  for (int k0 = 0; k0 < K; k0 += 4) {           // K % 4 == 0 on this path
-    const float4 av = *reinterpret_cast<const float4*>(a + k0);
-    float4 bv[TC_C];
-#pragma unroll
-    for (int k = 0; k < TC_C; ++k) bv[k] = *reinterpret_cast<const float4*>(bp[k] + k0);
-#pragma unroll
-    for (int k = 0; k < TC_C; ++k) {
-      double t;
-      t = (double)av.x - (double)bv[k].x; e2[k] = __dadd_rn(e2[k], __dmul_rn(t, t));
-      t = (double)av.y - (double)bv[k].y; e2[k] = __dadd_rn(e2[k], __dmul_rn(t, t));
-      t = (double)av.z - (double)bv[k].z; e2[k] = __dadd_rn(e2[k], __dmul_rn(t, t));
-      t = (double)av.w - (double)bv[k].w; e2[k] = __dadd_rn(e2[k], __dmul_rn(t, t));
-    }
-  }
   float b0 = FLT_MAX, b1 = FLT_MAX; int i0 = -1, i1 = -1;
+  bool overflow = false;
+  for (int half = 0; half < 2; ++half) {
+    const int n = hcnt[r * 2 + half];
+    if (n > TC_HCAP) overflow = true;
+    const int* h = hits + (r * 2 + half) * TC_HCAP;
+    for (int c0 = 0; c0 < min(n, TC_HCAP); c0 += 4) {
+      int col[4]; const float* bp[4]; double e2[4];
 #pragma unroll
-  for (int k = 0; k < TC_C; ++k) if (ok[k]) top2_insert_f(__fsqrt_rn((float)e2[k]), c.idx[k], b0, i0, b1, i1);
-  Knn2 r; r.d0 = b0; r.d1 = b1; r.i0 = i0; r.i1 = i1;
-  bool safe = true;
-  if (job.nB > TC_C) {
-    if (nvalid < TC_C) safe = false;
-    else {
-      double s2 = 0.0;              // exact squared distance of the second best among the candidates
+      for (int k = 0; k < 4; ++k) {
+        col[k] = (c0 + k < min(n, TC_HCAP)) ? h[c0 + k] : -1;
+        bp[k] = desc + (size_t)(job.rowB0 + (col[k] >= 0 && col[k] < job.nB ? col[k] : 0)) * K;
+        e2[k] = 0.0;
+      }
+      for (int k0 = 0; k0 < K; k0 += 4) {                           // K % 4 == 0 on this path
+        const float4 av = *reinterpret_cast<const float4*>(a + k0);
+        float4 bv[4];
 #pragma unroll
-      for (int k = 0; k < TC_C; ++k) if (c.idx[k] == i1) s2 = e2[k];
-      const double na = (double)norms[job.rowA0 + i];
-      const double eps = 0.001953125 * 1.02 * sqrt(na) * (double)job.bmax + 1e-5 * (na + (double)job.bmax * (double)job.bmax + 1.0);
-      // every non-candidate's packed key is >= the 8th key, so its approximate value exceeds worst (1 - 2^-10)
-      const double lower_bound_others = (double)c.worst * (1.0 - 0.0009765625) - 1.0 - eps;      // exact d^2 of any non-candidate >= this
-      safe = s2 * (1.0 + 1e-6) + 1e-30 < lower_bound_others;
+        for (int k = 0; k < 4; ++k) bv[k] = *reinterpret_cast<const float4*>(bp[k] + k0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          double t;
+          t = (double)av.x - (double)bv[k].x; e2[k] = __dadd_rn(e2[k], __dmul_rn(t, t));
+          t = (double)av.y - (double)bv[k].y; e2[k] = __dadd_rn(e2[k], __dmul_rn(t, t));
+          t = (double)av.z - (double)bv[k].z; e2[k] = __dadd_rn(e2[k], __dmul_rn(t, t));
+          t = (double)av.w - (double)bv[k].w; e2[k] = __dadd_rn(e2[k], __dmul_rn(t, t));
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (col[k] >= 0 && col[k] < job.nB) top2_insert_f(__fsqrt_rn((float)e2[k]), col[k], b0, i0, b1, i1);
     }
   }
-  knn[job.knn_off + i] = r;
-  if (!safe) { const int slot = atomicAdd(n_flagged, 1); if (slot < flag_cap) { flagged[2 * slot] = blockIdx.y; flagged[2 * slot + 1] = i; } }
+  Knn2 out; out.d0 = b0; out.d1 = b1; out.i0 = i0; out.i1 = i1;
+  knn[job.knn_off + i] = out;
+  if (overflow) { const int slot = atomicAdd(n_flagged, 1); if (slot < flag_cap) { flagged[2 * slot] = blockIdx.y; flagged[2 * slot + 1] = i; } }
 }
 
 // exact full scan of one flagged row per warp (same arithmetic and tie rule as the SIMT path)
@@ -462,7 +458,7 @@ int get_prepared(const float* desc, int64_t rows, int K, cudaStream_t st, Prepar
   return MM_OK;
 }
 
-struct TcScratch { DevBuf<TcItem> items; DevBuf<RerankJob> jobs; DevBuf<TcCand> cand; DevBuf<int> flagged, n_flagged; size_t items_cap = 0, jobs_cap = 0, cand_cap = 0; };
+struct TcScratch { DevBuf<TcItem> items; DevBuf<RerankJob> jobs; DevBuf<float> bound; DevBuf<int> hits, hcnt, flagged, n_flagged; size_t items_cap = 0, jobs_cap = 0, cand_cap = 0; };
 TcScratch g_scr;
 std::atomic<uint64_t> g_tc_rows{0}, g_tc_flagged{0};
 
@@ -483,11 +479,9 @@ int match_tc_pairs(const float* desc, const float* xy, int K, const int64_t* off
                    cudaStream_t st, bool required) {
   (void)xy;
   if (max_distance != -1.0) { if (required) set_error("the tcgen05 path does not take the keypoint-distance mask"); return MM_ERR_UNSUPPORTED; }
-  if (K % 4 != 0 || K < 8 || K > 1024) { if (required) set_error("tcgen05 path needs K %% 4 == 0"); return MM_ERR_UNSUPPORTED; }
+  if (K % 4 != 0 || K < 8 || (K + 4 + TC_KB - 1) / TC_KB > TC_MAX_KB) { if (required) set_error("tcgen05 path needs K %% 4 == 0 and K <= %d", TC_MAX_KB * TC_KB - 4); return MM_ERR_UNSUPPORTED; }
   if (getenv("MM_MATCH_NO_TC") && !required) return MM_ERR_UNSUPPORTED;
-  for (int p = 0; p < n_pairs; ++p) if (jobs_host[p].n1 > (1 << TC_IDX_BITS) || jobs_host[p].n2 > (1 << TC_IDX_BITS)) {
-    if (required) set_error("tcgen05 path packs the column index in %d bits: at most %d descriptors per image", TC_IDX_BITS, 1 << TC_IDX_BITS);
-    return MM_ERR_UNSUPPORTED; }
+
   // the whole descriptor array of the set: its row count is the offset past the last image referenced
   const int64_t rows = total_rows;
   // prepared copies are keyed by the base pointer; use the full extent the set was created with when known
@@ -510,13 +504,15 @@ int match_tc_pairs(const float* desc, const float* xy, int K, const int64_t* off
       RerankJob rj; rj.rowA0 = (int)offs[imgA]; rj.nA = nA; rj.rowB0 = (int)offs[imgB]; rj.nB = nB; rj.out_off = cand_rows;
       rj.knn_off = dir == 0 ? j.knn12_off : -(j.knn21_off + 1); rj.bmax = std::sqrt(bmax);
       rjobs.push_back(rj);
-      if (nB > 0) for (int m = 0; m < nA; m += TC_M) { TcItem t; t.rowA0 = (int)offs[imgA] + m; t.nA = std::min(TC_M, nA - m); t.rowB0 = (int)offs[imgB]; t.nB = nB; t.out_off = cand_rows + m; items.push_back(t); }
+      if (nB > 0) for (int m = 0; m < nA; m += TC_M) { TcItem t; t.rowA0 = (int)offs[imgA] + m; t.nA = std::min(TC_M, nA - m); t.rowB0 = (int)offs[imgB]; t.nB = nB; t.out_off = cand_rows + m; t.bmax = rj.bmax; t.pad = 0; items.push_back(t); }
       cand_rows += nA;
     }
   }
   if (items.size() > g_scr.items_cap) { MM_CUDA(g_scr.items.alloc(items.size())); g_scr.items_cap = items.size(); }
   if (rjobs.size() > g_scr.jobs_cap) { MM_CUDA(g_scr.jobs.alloc(rjobs.size())); g_scr.jobs_cap = rjobs.size(); }
-  if ((size_t)cand_rows > g_scr.cand_cap) { MM_CUDA(g_scr.cand.alloc((size_t)cand_rows)); g_scr.cand_cap = (size_t)cand_rows; MM_CUDA(g_scr.flagged.alloc(2 * (size_t)cand_rows + 2)); }
+  if ((size_t)cand_rows > g_scr.cand_cap) {
+    const size_t c = (size_t)cand_rows + (size_t)cand_rows / 4;
+    MM_CUDA(g_scr.bound.alloc(c)); MM_CUDA(g_scr.hits.alloc(c * 2 * TC_HCAP)); MM_CUDA(g_scr.hcnt.alloc(c * 2)); MM_CUDA(g_scr.flagged.alloc(2 * c + 2)); g_scr.cand_cap = c; }
   if (!g_scr.n_flagged.p) MM_CUDA(g_scr.n_flagged.alloc(1));
   // knn21 jobs were tagged with a negative offset: split the re-rank into the two output arrays
   std::vector<RerankJob> j12, j21;
@@ -524,21 +520,29 @@ int match_tc_pairs(const float* desc, const float* xy, int K, const int64_t* off
   std::vector<RerankJob> all = j12; all.insert(all.end(), j21.begin(), j21.end());
   MM_CUDA(cudaMemcpyAsync(g_scr.jobs.p, all.data(), sizeof(RerankJob) * all.size(), cudaMemcpyHostToDevice, st));
   // candidates of rows with nB == 0 are never written: give them empty lists
-  MM_CUDA(cudaMemsetAsync(g_scr.cand.p, 0xFF, sizeof(TcCand) * (size_t)cand_rows, st));
+  // rows of jobs with nB == 0 are never visited by the kernels: empty hit lists
+  MM_CUDA(cudaMemsetAsync(g_scr.hcnt.p, 0, sizeof(int) * 2 * (size_t)cand_rows, st));
   if (!items.empty()) {
     MM_CUDA(cudaMemcpyAsync(g_scr.items.p, items.data(), sizeof(TcItem) * items.size(), cudaMemcpyHostToDevice, st));
-    const size_t smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 + 256 + (size_t)TC_M * TC_C * 4;
+    const size_t smem = (size_t)TC_MAX_KB * TC_A_BYTES + (size_t)TC_STAGES * TC_B_BYTES + 1024 + 256 + (size_t)TC_M * 8;
     static bool configured = false;
-    if (!configured) { MM_CUDA(cudaFuncSetAttribute(k_match_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
+    if (!configured) {
+      MM_CUDA(cudaFuncSetAttribute(k_match_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      MM_CUDA(cudaFuncSetAttribute(k_match_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = true;
+    }
     const int grid = std::min((int)items.size(), num_sms());
-    k_match_tc<<<grid, TC_THREADS, smem, st>>>(P->mapA, P->mapB, g_scr.items.p, (int)items.size(), P->Kp / TC_KB, g_scr.cand.p);
+    const int num_kb = P->Kp / TC_KB;
+    k_match_tc<0><<<grid, TC_THREADS, smem, st>>>(P->mapA, P->mapB, g_scr.items.p, (int)items.size(), num_kb, P->norms.p, g_scr.bound.p, g_scr.hits.p, g_scr.hcnt.p);
+    MM_LAUNCH_CHECK();
+    k_match_tc<1><<<grid, TC_THREADS, smem, st>>>(P->mapA, P->mapB, g_scr.items.p, (int)items.size(), num_kb, P->norms.p, g_scr.bound.p, g_scr.hits.p, g_scr.hcnt.p);
     MM_LAUNCH_CHECK();
   }
   MM_CUDA(cudaMemsetAsync(g_scr.n_flagged.p, 0, sizeof(int), st));
   const int flag_cap = (int)cand_rows;
   int max_nA = 1; for (auto& r : all) max_nA = std::max(max_nA, r.nA);
   if (!j12.empty()) {
-    k_rerank<<<dim3((max_nA + 127) / 128, (unsigned)j12.size()), 128, 0, st>>>(g_scr.jobs.p, desc, P->norms.p, K, g_scr.cand.p, knn12, g_scr.flagged.p, g_scr.n_flagged.p, flag_cap);
+    k_rerank<<<dim3((max_nA + 127) / 128, (unsigned)j12.size()), 128, 0, st>>>(g_scr.jobs.p, desc, K, g_scr.hits.p, g_scr.hcnt.p, knn12, g_scr.flagged.p, g_scr.n_flagged.p, flag_cap);
     MM_LAUNCH_CHECK();
     k_rescan<<<num_sms() * 2, 256, 0, st>>>(g_scr.jobs.p, desc, K, g_scr.flagged.p, g_scr.n_flagged.p, flag_cap, knn12);
     MM_LAUNCH_CHECK();
@@ -547,7 +551,7 @@ int match_tc_pairs(const float* desc, const float* xy, int K, const int64_t* off
   MM_CUDA(cudaMemcpyAsync(&nf12, g_scr.n_flagged.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   if (!j21.empty()) {
     MM_CUDA(cudaMemsetAsync(g_scr.n_flagged.p, 0, sizeof(int), st));
-    k_rerank<<<dim3((max_nA + 127) / 128, (unsigned)j21.size()), 128, 0, st>>>(g_scr.jobs.p + j12.size(), desc, P->norms.p, K, g_scr.cand.p, knn21, g_scr.flagged.p, g_scr.n_flagged.p, flag_cap);
+    k_rerank<<<dim3((max_nA + 127) / 128, (unsigned)j21.size()), 128, 0, st>>>(g_scr.jobs.p + j12.size(), desc, K, g_scr.hits.p, g_scr.hcnt.p, knn21, g_scr.flagged.p, g_scr.n_flagged.p, flag_cap);
     MM_LAUNCH_CHECK();
     k_rescan<<<num_sms() * 2, 256, 0, st>>>(g_scr.jobs.p + j12.size(), desc, K, g_scr.flagged.p, g_scr.n_flagged.p, flag_cap, knn21);
     MM_LAUNCH_CHECK();
