@@ -250,10 +250,16 @@ int  mm_ba_session_download(mm_ba_session* s, double* poses, double* intr, doubl
 int  mm_ba_session_summary(mm_ba_session* s, mm_ba_summary* out);
 /* Time single hot kernels on the session's current state (bench/roofline):
  * which: 0 = residual+Jacobian (K1), 1 = Schur assembly (K2), 2 = cost-only evaluation (K4),
- * 3 = one PCG iteration.  Runs `reps` launches, returns mean ms via CUDA events. */
+ * 3 = one PCG iteration's SpMV, 4 = coarse-level setup (assembly + inverse).  Runs `reps` launches, returns mean ms via CUDA events. */
 int  mm_ba_session_time_kernel(mm_ba_session* s, int32_t which, int32_t reps, double* ms);
 /* Sizes of the reduced system: number of 6x6 blocks stored (upper triangle incl. diagonal). */
 int64_t mm_ba_session_num_blocks(mm_ba_session* s);
+/* Unknowns of the coarse level of the two-level PCG preconditioner (7 per aggregate of images;
+ * 0 = block-Jacobi only: small systems, refined intrinsics, or MM_PCG_NO_COARSE set). */
+int32_t mm_ba_session_coarse_dim(mm_ba_session* s);
+/* Test hook for the blocked Gauss-Jordan kernel that inverts the coarse matrix: a (m x m, row-major,
+ * symmetric positive definite, host memory) is replaced by its inverse. */
+int  mm_debug_spd_inverse(double* a, int32_t m);
 void mm_ba_session_destroy(mm_ba_session* s);
 
 /* pose_refinement (bundle_adjustment.cc:139-225): 6-dof refinement of one pose,

@@ -136,6 +136,8 @@ PROTOTYPES = {
     "mm_ba_session_summary": (C.c_int, [C.c_void_p, C.POINTER(BASummary)]),
     "mm_ba_session_time_kernel": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, p_f64]),
     "mm_ba_session_num_blocks": (C.c_int64, [C.c_void_p]),
+    "mm_ba_session_coarse_dim": (C.c_int32, [C.c_void_p]),
+    "mm_debug_spd_inverse": (C.c_int, [p_f64, C.c_int32]),
     "mm_ba_session_destroy": (None, [C.c_void_p]),
     "mm_pose_refine": (C.c_int, [p_f64, p_f64, C.c_int, p_f64, C.c_int64, p_f64, p_f64, p_u8,
                                  C.POINTER(BAOptions), C.POINTER(BASummary), p_f64]),

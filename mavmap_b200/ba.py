@@ -379,6 +379,10 @@ class BASession:
     def num_blocks(self):
         return int(self._lib.mm_ba_session_num_blocks(self._h))
 
+    def coarse_dim(self):
+        """Unknowns of the coarse level of the two-level PCG preconditioner (0 = block-Jacobi only)."""
+        return int(self._lib.mm_ba_session_coarse_dim(self._h))
+
     def close(self):
         if self._h:
             self._lib.mm_ba_session_destroy(self._h)

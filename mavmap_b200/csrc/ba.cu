@@ -122,6 +122,9 @@ struct mm_ba_session {
   DevBuf<double> vx, vr, vz, vp0, vp1, vAp, pcg_sc; DevBuf<int> pcg_ic;
   DevBuf<double> part_cost, part_pt, part_cam, part_x, red;   // red: [0]=cost [1]=new_cost [2]=gmax [3]=step_norm2 [4]=mcc [5]=xnorm2
   DevBuf<int> fail; DevBuf<unsigned long long> pcg_dbg;
+  // coarse level of the two-level preconditioner (ba_coarse.cuh)
+  int cm = 0, n_agg = 0; std::vector<int> h_agg; std::vector<double> h_pose_mask;
+  DevBuf<int> blk_a, blk_b, agg; DevBuf<double> Pc, Ac, gjC, gjR, crc, cqc, cyc; int gj_grid = 0;
   // refined intrinsics (single shared camera)
   bool refine = false;
   DevBuf<double> ji, intr2, intr_mask, scale_i, Apc, Bm, intr_acc, Cinv, gi, di, xi, zi, pi0, pi1, bt, sq9;
@@ -245,7 +248,7 @@ int build_structure(mm_ba_session* s, const mm_ba_problem* P) {
   if (n_pairs >= ((int64_t)1 << 31)) { set_error("too many observation pairs (%lld)", (long long)n_pairs); return MM_ERR_UNSUPPORTED; }
   s->n_pairs = n_pairs;
   MM_CUDA(s->pair_blk.alloc((size_t)n_pairs));
-  DevBuf<int> blk_a, blk_b;
+  DevBuf<int>& blk_a = s->blk_a; DevBuf<int>& blk_b = s->blk_b;
   int n_off = 0;
   if (n_pairs > 0) {
     DevBuf<unsigned long long> keys, keys_s; DevBuf<int> slot, slot_s, head, incl;
@@ -261,6 +264,7 @@ int build_structure(mm_ba_session* s, const mm_ba_problem* P) {
     k_pair_assign<<<grid_stride(n_pairs, B), B, 0, st>>>(n_pairs, n_img, keys_s.p, incl.p, head.p, slot_s.p, s->pair_blk.p, blk_a.p, blk_b.p); MM_LAUNCH_CHECK();
     MM_CUDA(cudaStreamSynchronize(st));
   }
+  if (!blk_a.p) { MM_CUDA(blk_a.alloc(1)); MM_CUDA(blk_b.alloc(1)); }
   s->n_off = n_off; s->nblk = (int64_t)n_img + n_off;
   // 5. block-CSR rows for the SpMV (each off-diagonal block referenced from both rows)
   const int64_t n_ent = (int64_t)n_img + 2 * (int64_t)n_off; s->n_ent = n_ent;
@@ -291,6 +295,122 @@ int upload_params(mm_ba_session* s) {
   return MM_OK;
 }
 
+// ---- coarse level: aggregates (host, greedy over the block graph of S) ------------------------------------------
+int build_aggregates(mm_ba_session* s) {
+  s->cm = 0; s->n_agg = 0;
+  const int n = s->n_img;
+  int target = getenv("MM_PCG_AGG") ? atoi(getenv("MM_PCG_AGG")) : 8;
+  if (getenv("MM_PCG_NO_COARSE") || s->refine || n < 64 || target < 2 || s->n_ent <= n) return MM_OK;
+  while ((int64_t)CM * ((n + target - 1) / target) > 2048) ++target;          // keeps the dense coarse inverse <= 32 MB
+  std::vector<int> rs((size_t)n + 1), col((size_t)s->n_ent);
+  MM_CUDA(cudaMemcpy(rs.data(), s->row_start.p, sizeof(int) * rs.size(), cudaMemcpyDeviceToHost));
+  MM_CUDA(cudaMemcpy(col.data(), s->row_col.p, sizeof(int) * col.size(), cudaMemcpyDeviceToHost));
+  std::vector<int> agg((size_t)n, -1);
+  std::vector<std::vector<int>> mem;
+  std::vector<int> front, nxt;
+  for (int seed = 0; seed < n; ++seed) {
+    if (agg[seed] >= 0) continue;
+    const int id = (int)mem.size(); mem.emplace_back();
+    std::vector<int>& g = mem.back();
+    g.push_back(seed); agg[seed] = id; front.assign(1, seed);
+    while ((int)g.size() < target && !front.empty()) {
+      nxt.clear();
+      for (int v : front)
+        for (int e = rs[v]; e < rs[v + 1] && (int)g.size() < target; ++e) {
+          const int u = col[e];
+          if (agg[u] < 0) { agg[u] = id; g.push_back(u); nxt.push_back(u); }
+        }
+      front.swap(nxt);
+    }
+  }
+  // left-over fragments join a neighbouring aggregate (a single image cannot carry 7 modes)
+  const int min_size = std::max(2, target / 2);
+  for (size_t a = 0; a < mem.size(); ++a) {
+    if (mem[a].empty() || (int)mem[a].size() >= min_size) continue;
+    int dst = -1;
+    for (int v : mem[a]) { for (int e = rs[v]; e < rs[v + 1]; ++e) if (agg[col[e]] != (int)a) { dst = agg[col[e]]; break; } if (dst >= 0) break; }
+    if (dst < 0) continue;
+    for (int v : mem[a]) { agg[v] = dst; mem[dst].push_back(v); }
+    mem[a].clear();
+  }
+  std::vector<int> remap(mem.size(), -1); int na = 0;
+  for (size_t a = 0; a < mem.size(); ++a) if (!mem[a].empty()) remap[a] = na++;
+  for (int i = 0; i < n; ++i) agg[i] = remap[agg[i]];
+  s->h_agg = agg; s->n_agg = na; s->cm = CM * na;
+  const size_t m = (size_t)s->cm;
+  MM_CUDA(s->agg.alloc((size_t)n)); MM_CUDA(s->Pc.alloc((size_t)PCS * n)); MM_CUDA(s->Ac.alloc(m * m));
+  MM_CUDA(s->gjC.alloc(m * GJ_NB)); MM_CUDA(s->gjR.alloc(m * GJ_NB)); MM_CUDA(s->crc.alloc(2 * m)); MM_CUDA(s->cqc.alloc(m)); MM_CUDA(s->cyc.alloc(m));
+  MM_CUDA(cudaMemcpy(s->agg.p, agg.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
+  int per_sm = 0;
+  MM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_spd_inverse, 256, 0));
+  const int tiles = (s->cm + 63) / 64;
+  s->gj_grid = std::max(1, std::min(std::max(1, per_sm) * num_sms(), std::max(tiles * tiles, (s->cm + 255) / 256)));
+  return MM_OK;
+}
+
+// prolongation blocks: the 7 similarity modes of each aggregate in the (scaled) pose parameters of its images.
+//   translation d:  d t = -R d          rotation a (about the world origin):  d w = -Jl^-1 R a, d t = 0
+//   scale about the aggregate centre c:  d t = -R (C - c),   C = -R' t the camera centre
+// (rotation about c differs from rotation about the origin by a translation, so the span is the same.)
+int build_coarse_basis(mm_ba_session* s) {
+  if (!s->cm) return MM_OK;
+  const int n = s->n_img;
+  std::vector<double> sc(6 * (size_t)n), P((size_t)PCS * n, 0.0), R(9 * (size_t)n), M(9 * (size_t)n), C(3 * (size_t)n), cen(3 * (size_t)s->n_agg, 0.0);
+  std::vector<int> cnt((size_t)s->n_agg, 0);
+  MM_CUDA(cudaMemcpyAsync(sc.data(), s->scale_c.p, sizeof(double) * sc.size(), cudaMemcpyDeviceToHost, s->stream));
+  MM_CUDA(cudaStreamSynchronize(s->stream));
+  for (int i = 0; i < n; ++i) {
+    const double* p = s->h_poses0.data() + 6 * (size_t)i;
+    double Jl[9]; double* Ri = R.data() + 9 * (size_t)i;
+    rotation_and_left_jacobian(p, Ri, Jl);
+    // M = Jl^-1 R  (adjugate inverse of the 3 x 3 left Jacobian)
+    const double a = Jl[0], b = Jl[1], c = Jl[2], d = Jl[3], e = Jl[4], f = Jl[5], g = Jl[6], h = Jl[7], k = Jl[8];
+    const double det = a * (e * k - f * h) - b * (d * k - f * g) + c * (d * h - e * g);
+    const double id = (fabs(det) > 1e-300) ? 1.0 / det : 0.0;
+    const double Ji[9] = { (e * k - f * h) * id, (c * h - b * k) * id, (b * f - c * e) * id,
+                           (f * g - d * k) * id, (a * k - c * g) * id, (c * d - a * f) * id,
+                           (d * h - e * g) * id, (b * g - a * h) * id, (a * e - b * d) * id };
+    double* Mi = M.data() + 9 * (size_t)i;
+    for (int r = 0; r < 3; ++r) for (int q = 0; q < 3; ++q) Mi[3 * r + q] = Ji[3 * r] * Ri[q] + Ji[3 * r + 1] * Ri[3 + q] + Ji[3 * r + 2] * Ri[6 + q];
+    for (int q = 0; q < 3; ++q) C[3 * (size_t)i + q] = -(Ri[q] * p[3] + Ri[3 + q] * p[4] + Ri[6 + q] * p[5]);
+    const int gidx = s->h_agg[i];
+    for (int q = 0; q < 3; ++q) cen[3 * (size_t)gidx + q] += C[3 * (size_t)i + q];
+    cnt[gidx]++;
+  }
+  for (int gi_ = 0; gi_ < s->n_agg; ++gi_) for (int q = 0; q < 3; ++q) cen[3 * (size_t)gi_ + q] /= std::max(cnt[gi_], 1);
+  for (int i = 0; i < n; ++i) {
+    const double* Ri = R.data() + 9 * (size_t)i; const double* Mi = M.data() + 9 * (size_t)i;
+    const double* c0 = cen.data() + 3 * (size_t)s->h_agg[i];
+    double* Pi = P.data() + (size_t)PCS * i;
+    double dc[3]; for (int q = 0; q < 3; ++q) dc[q] = C[3 * (size_t)i + q] - c0[q];
+    for (int r = 0; r < 3; ++r) {
+      for (int k = 0; k < 3; ++k) { Pi[CM * (3 + r) + k] = -Ri[3 * r + k]; Pi[CM * r + 3 + k] = -Mi[3 * r + k]; }
+      Pi[CM * (3 + r) + 6] = -(Ri[3 * r] * dc[0] + Ri[3 * r + 1] * dc[1] + Ri[3 * r + 2] * dc[2]);
+    }
+    for (int r = 0; r < 6; ++r) {
+      const double w = s->h_pose_mask[6 * (size_t)i + r] / sc[6 * (size_t)i + r];       // scaled coordinates, free parameters only
+      for (int k = 0; k < CM; ++k) Pi[CM * r + k] *= w;
+    }
+  }
+  MM_CUDA(cudaMemcpy(s->Pc.p, P.data(), sizeof(double) * P.size(), cudaMemcpyHostToDevice));
+  return MM_OK;
+}
+
+// Ac = P' S P and its explicit inverse (in place)
+int launch_coarse_setup(mm_ba_session* s) {
+  if (!s->cm) return MM_OK;
+  cudaStream_t st = s->stream;
+  int m = s->cm;
+  MM_CUDA(cudaMemsetAsync(s->Ac.p, 0, sizeof(double) * (size_t)m * m, st));
+  k_coarse_assemble<<<blocks_for(s->nblk * 32, 128), 128, 0, st>>>(s->n_img, s->nblk, s->blk_a.p, s->blk_b.p, s->S.p, s->agg.p, s->Pc.p, m, s->Ac.p); MM_LAUNCH_CHECK();
+  k_coarse_ridge<<<blocks_for(m, 128), 128, 0, st>>>(m, s->Ac.p); MM_LAUNCH_CHECK();
+  double* Ap = s->Ac.p; double* Ck = s->gjC.p; double* Rk = s->gjR.p;
+  void* args[] = { &m, &Ap, &Ck, &Rk };
+  MM_CUDA(cudaLaunchCooperativeKernel((const void*)k_spd_inverse, dim3(s->gj_grid), dim3(256), args, 0, st));
+  count_launch();
+  return MM_OK;
+}
+
 LossParams loss_of(const mm_ba_options& o) {
   LossParams L; L.type = o.loss_type; L.b = o.loss_scale * o.loss_scale; L.c = 1.0 / L.b; return L;
 }
@@ -301,10 +421,10 @@ int launch_linearize(mm_ba_session* s) {
   cudaStream_t st = s->stream;
   k_pose_aux<<<blocks_for(s->n_img, 128), 128, 0, st>>>(s->n_img, s->poses.p, s->pose_mask.p, s->aux.p); MM_LAUNCH_CHECK();
   if (s->refine)
-    k_residual_jacobian<true, true><<<s->grid_obs, 256, 0, st>>>(s->n_obs, s->obs_xy.p, s->obs_img.p, s->obs_pt.p, s->aux.p, s->pts.p, s->intr.p,
+    k_residual_jacobian<true, true><<<s->grid_obs, 256, K1_SMEM, st>>>(s->n_obs, s->obs_xy.p, s->obs_img.p, s->obs_pt.p, s->aux.p, s->pts.p, s->intr.p,
         s->img_cam.p, s->cam_model.p, s->pose_mask.p, s->pt_mask.p, loss_of(s->opt), s->rec.p, s->part_cost.p, s->ji.p, s->intr_mask.p);
   else
-    k_residual_jacobian<true><<<s->grid_obs, 256, 0, st>>>(s->n_obs, s->obs_xy.p, s->obs_img.p, s->obs_pt.p, s->aux.p, s->pts.p, s->intr.p,
+    k_residual_jacobian<true><<<s->grid_obs, 256, K1_SMEM, st>>>(s->n_obs, s->obs_xy.p, s->obs_img.p, s->obs_pt.p, s->aux.p, s->pts.p, s->intr.p,
         s->img_cam.p, s->cam_model.p, s->pose_mask.p, s->pt_mask.p, loss_of(s->opt), s->rec.p, s->part_cost.p);
   MM_LAUNCH_CHECK();
   k_reduce_sum<<<1, 256, 0, st>>>(s->part_cost.p, s->grid_obs, s->red.p + 0); MM_LAUNCH_CHECK();
@@ -314,7 +434,7 @@ int launch_linearize(mm_ba_session* s) {
 int launch_cost_candidate(mm_ba_session* s) {
   cudaStream_t st = s->stream;
   k_pose_aux<<<blocks_for(s->n_img, 128), 128, 0, st>>>(s->n_img, s->poses2.p, s->pose_mask.p, s->aux2.p); MM_LAUNCH_CHECK();
-  k_residual_jacobian<false><<<s->grid_obs, 256, 0, st>>>(s->n_obs, s->obs_xy.p, s->obs_img.p, s->obs_pt.p, s->aux2.p, s->pts2.p, s->refine ? s->intr2.p : s->intr.p,
+  k_residual_jacobian<false><<<s->grid_obs, 256, K1_SMEM, st>>>(s->n_obs, s->obs_xy.p, s->obs_img.p, s->obs_pt.p, s->aux2.p, s->pts2.p, s->refine ? s->intr2.p : s->intr.p,
       s->img_cam.p, s->cam_model.p, s->pose_mask.p, s->pt_mask.p, loss_of(s->opt), nullptr, s->part_cost.p); MM_LAUNCH_CHECK();
   k_reduce_sum<<<1, 256, 0, st>>>(s->part_cost.p, s->grid_obs, s->red.p + 1); MM_LAUNCH_CHECK();
   return MM_OK;
@@ -333,7 +453,7 @@ int launch_scale(mm_ba_session* s) {
   return MM_OK;
 }
 // K2: reduced camera system at the current radius (+ gradient max-norm -> red[2])
-int launch_schur(mm_ba_session* s) {
+int launch_schur(mm_ba_session* s, bool with_coarse = true) {
   cudaStream_t st = s->stream;
   MM_CUDA(cudaMemsetAsync(s->S.p, 0, sizeof(double) * 36 * (size_t)s->nblk, st));
   MM_CUDA(cudaMemsetAsync(s->red.p + 2, 0, sizeof(double), st));
@@ -343,6 +463,7 @@ int launch_schur(mm_ba_session* s) {
   k_schur_cam<<<blocks_for((int64_t)s->n_img * 32, 128), 128, 0, st>>>(s->n_img, s->cam_start.p, s->cam_perm.p, s->obs_pt.p, s->rec.p,
       s->scale_c.p, s->scale_p.p, s->Vinv.p, s->gp.p, lm, s->S.p, s->rhs.p, s->gc.p, s->dc.p, s->red.p + 2); MM_LAUNCH_CHECK();
   k_precond<<<blocks_for(s->n_img, 64), 64, 0, st>>>(s->n_img, s->S.p, s->Minv.p, s->fail.p); MM_LAUNCH_CHECK();
+  if (with_coarse) { const int rc = launch_coarse_setup(s); if (rc) return rc; }
   if (s->refine) {
     MM_CUDA(cudaMemsetAsync(s->intr_acc.p, 0, sizeof(double) * 108, st));
     k_schur_intr_point<<<blocks_for(s->n_pt, 128), 128, 0, st>>>(s->n_pt, s->pt_start.p, s->rec.p, s->ji.p, s->scale_p.p, s->scale_i.p, s->Vinv.p, s->gp.p, s->Apc.p, s->intr_acc.p); MM_LAUNCH_CHECK();
@@ -396,6 +517,8 @@ int launch_pcg(mm_ba_session* s) {
     a.n_intr = 9; a.Bm = s->Bm.p; a.Cm = s->intr_acc.p; a.Cinv = s->Cinv.p; a.bi = s->intr_acc.p + 81; a.xi = s->xi.p; a.zi = s->zi.p; a.pi0 = s->pi0.p; a.pi1 = s->pi1.p; a.bt = s->bt.p;
     MM_CUDA(cudaMemsetAsync(s->bt.p, 0, sizeof(double) * 18, st));
   }
+  a.cm = s->cm; a.agg = s->agg.p; a.Pc = s->Pc.p; a.Ainv = s->Ac.p; a.rc = s->crc.p; a.qc = s->cqc.p; a.yc = s->cyc.p;
+  if (s->cm) { MM_CUDA(cudaMemsetAsync(s->crc.p, 0, sizeof(double) * 2 * (size_t)s->cm, st)); MM_CUDA(cudaMemsetAsync(s->cqc.p, 0, sizeof(double) * (size_t)s->cm, st)); }
   if (getenv("MM_PCG_DEBUG")) { if (!s->pcg_dbg.p) MM_CUDA(s->pcg_dbg.alloc(6 * 32)); a.dbg = s->pcg_dbg.p; }
   if (s->pcg_cached) {
     int e_cap = s->pcg_ecap;
@@ -452,6 +575,7 @@ int lm_start(mm_ba_session* s) {
     k_fill<<<grid_stride(6 * (int64_t)s->n_img, 256), 256, 0, s->stream>>>(6 * (int64_t)s->n_img, s->scale_c.p, 1.0); MM_LAUNCH_CHECK();
     k_fill<<<grid_stride(3 * (int64_t)s->n_pt, 256), 256, 0, s->stream>>>(3 * (int64_t)s->n_pt, s->scale_p.p, 1.0); MM_LAUNCH_CHECK();
     if ((rc = launch_scale(s))) return rc; }
+  if ((rc = build_coarse_basis(s))) return rc;
   { Timer t(s, &S.ms_schur); if ((rc = launch_schur(s))) return rc; }
   if ((rc = launch_xnorm(s))) return rc;
   double red[8]; if ((rc = read_red(s, red))) return rc;
@@ -592,6 +716,9 @@ int mm_ba_session_create(const mm_ba_problem* P, const mm_ba_options* opt, void*
   A(s->vx, 6 * n_img); A(s->vr, 6 * n_img); A(s->vz, 6 * n_img); A(s->vp0, 6 * n_img); A(s->vp1, 6 * n_img); A(s->vAp, 6 * n_img);
   A(s->pcg_sc, 16); A(s->pcg_ic, 4); A(s->red, 8); A(s->fail, 1); A(s->img_cam, n_img); A(s->cam_model, n_cam); A(s->Minv, 36 * n_img);
   s->grid_obs = grid_stride(std::max<int64_t>(P->n_obs, 1), 256);
+  MM_CUDA(cudaFuncSetAttribute((const void*)k_residual_jacobian<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM));
+  MM_CUDA(cudaFuncSetAttribute((const void*)k_residual_jacobian<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM));
+  MM_CUDA(cudaFuncSetAttribute((const void*)k_residual_jacobian<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM));
   s->grid_x = grid_stride(std::max<int64_t>(3 * (int64_t)P->n_pt, 1), 256);
   A(s->part_cost, (size_t)s->grid_obs); A(s->part_pt, 2 * (size_t)blocks_for(P->n_pt, 128)); A(s->part_cam, 2 * (size_t)blocks_for(6 * (int64_t)P->n_img, 128) + 2);
   A(s->part_x, (size_t)s->grid_x);
@@ -612,12 +739,14 @@ int mm_ba_session_create(const mm_ba_problem* P, const mm_ba_options* opt, void*
       for (int k = 0; k < 3; ++k) pm[6 * (size_t)i + 3 + k] = P->pose_const[4 * (size_t)i + 1 + k] ? 0.0 : 1.0;
     }
     for (int p = 0; p < P->n_pt; ++p) if (pt_n[p] && !P->pt_const[p]) tm[p] = 1.0;
+    s->h_pose_mask = pm;
     if (cudaMemcpy(s->pose_mask.p, pm.data(), sizeof(double) * pm.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(s->img_cam.p, P->img_cam, sizeof(int) * (size_t)P->n_img, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(s->cam_model.p, P->cam_model, sizeof(int) * (size_t)P->n_cam, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("mask upload failed"); return fail_out(MM_ERR_CUDA); } }
   cudaMemsetAsync(s->fail.p, 0, sizeof(int), s->stream);
   cudaMemsetAsync(s->red.p, 0, sizeof(double) * 8, s->stream);
   rc = build_structure(s, P); if (rc) return fail_out(rc);
+  rc = build_aggregates(s); if (rc) return fail_out(rc);
   { // multiplier of the K2a point permutation: a prime near 0.38 * n_pt that does not divide n_pt
     const unsigned long long primes[] = { 1000003ULL, 611953ULL, 382003ULL, 100003ULL, 38183ULL, 10007ULL, 3821ULL, 1009ULL, 383ULL, 101ULL, 37ULL, 7ULL, 1ULL };
     s->spread = 1;
@@ -667,6 +796,26 @@ int mm_ba_session_summary(mm_ba_session* s, mm_ba_summary* out) {
 }
 
 int64_t mm_ba_session_num_blocks(mm_ba_session* s) { return s ? s->nblk : -1; }
+int32_t mm_ba_session_coarse_dim(mm_ba_session* s) { return s ? s->cm : -1; }
+
+int mm_debug_spd_inverse(double* a, int32_t m) {
+  if (!a || m <= 0) { set_error("invalid argument"); return MM_ERR_INVALID_ARG; }
+  int rc = ensure_device(); if (rc) return rc;
+  DevBuf<double> A, Ck, Rk;
+  MM_CUDA(A.alloc((size_t)m * m)); MM_CUDA(Ck.alloc((size_t)m * GJ_NB)); MM_CUDA(Rk.alloc((size_t)m * GJ_NB));
+  MM_CUDA(cudaMemcpy(A.p, a, sizeof(double) * (size_t)m * m, cudaMemcpyHostToDevice));
+  int per_sm = 0;
+  MM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_spd_inverse, 256, 0));
+  const int tiles = (m + 63) / 64;
+  const int grid = std::max(1, std::min(std::max(1, per_sm) * num_sms(), std::max(tiles * tiles, (m + 255) / 256)));
+  int mm_ = m; double* Ap = A.p; double* Cp = Ck.p; double* Rp = Rk.p;
+  void* args[] = { &mm_, &Ap, &Cp, &Rp };
+  MM_CUDA(cudaLaunchCooperativeKernel((const void*)k_spd_inverse, dim3(grid), dim3(256), args, 0, nullptr));
+  count_launch();
+  MM_CUDA(cudaDeviceSynchronize());
+  MM_CUDA(cudaMemcpy(a, A.p, sizeof(double) * (size_t)m * m, cudaMemcpyDeviceToHost));
+  return MM_OK;
+}
 
 int mm_ba_session_download(mm_ba_session* s, double* poses, double* intr, double* pts, double* pt_err) {
   if (!s) return MM_ERR_INVALID_ARG;
@@ -704,10 +853,11 @@ int mm_ba_session_time_kernel(mm_ba_session* s, int32_t which, int32_t reps, dou
   for (int r = -1; r < reps; ++r) {
     if (r == 0) MM_CUDA(cudaEventRecord(s->ev0, st));
     switch (which) {
-      case 0: k_residual_jacobian<true><<<s->grid_obs, 256, 0, st>>>(s->n_obs, s->obs_xy.p, s->obs_img.p, s->obs_pt.p, s->aux.p, s->pts.p, s->intr.p,
+      case 0: k_residual_jacobian<true><<<s->grid_obs, 256, K1_SMEM, st>>>(s->n_obs, s->obs_xy.p, s->obs_img.p, s->obs_pt.p, s->aux.p, s->pts.p, s->intr.p,
                   s->img_cam.p, s->cam_model.p, s->pose_mask.p, s->pt_mask.p, loss_of(s->opt), s->rec.p, s->part_cost.p); count_launch(); break;
-      case 1: rc = launch_schur(s); break;
-      case 2: k_residual_jacobian<false><<<s->grid_obs, 256, 0, st>>>(s->n_obs, s->obs_xy.p, s->obs_img.p, s->obs_pt.p, s->aux.p, s->pts.p, s->intr.p,
+      case 1: rc = launch_schur(s, false); break;
+      case 4: rc = launch_coarse_setup(s); break;
+      case 2: k_residual_jacobian<false><<<s->grid_obs, 256, K1_SMEM, st>>>(s->n_obs, s->obs_xy.p, s->obs_img.p, s->obs_pt.p, s->aux.p, s->pts.p, s->intr.p,
                   s->img_cam.p, s->cam_model.p, s->pose_mask.p, s->pt_mask.p, loss_of(s->opt), nullptr, s->part_cost.p); count_launch(); break;
       case 3: {
         MM_CUDA(cudaMemsetAsync(s->pcg_ic.p, 0, sizeof(int) * 4, st));
@@ -721,6 +871,7 @@ int mm_ba_session_time_kernel(mm_ba_session* s, int32_t which, int32_t reps, dou
   float ms = 0; MM_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
   *ms_out = ms / reps;
   if (which == 3) { MM_CUDA(cudaMemsetAsync(s->pcg_sc.p, 0, sizeof(double) * 8, st)); }
+  if (which == 1) { rc = launch_coarse_setup(s); if (rc) return rc; }      // leave the session consistent
   return MM_OK;
 }
 

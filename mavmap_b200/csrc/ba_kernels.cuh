@@ -15,11 +15,12 @@
 #include <cooperative_groups.h>
 #include "common.cuh"
 #include "camera.cuh"
+#include "ba_coarse.cuh"
 
 namespace mm {
 
 constexpr int REC = 20;     // doubles per observation record (160 B = 5 sectors)
-constexpr int AUX = 24;     // doubles per image: R(9) Jl(9) t(3) pad(3) = 192 B
+constexpr int AUX = 24;     // doubles per image: R(9) t(3) Jl(9) masks(2) pad = 192 B
 
 struct LossParams { int type; double b; double c; };   // Cauchy: b = a^2, c = 1/b
 
@@ -32,6 +33,7 @@ __device__ __forceinline__ void loss_eval(const LossParams& L, double s, double&
 }
 
 // ---- per-image rotation data ---------------------------------------------------------
+// aux[img] = [R (9) | t (3) | Jl (9) | rvec mask, tvec mask bits | pad]: the first 96 bytes are all the cost-only pass needs
 __global__ void k_pose_aux(int n_img, const double* __restrict__ poses, const double* __restrict__ pose_mask, double* __restrict__ aux) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_img) return;
@@ -40,8 +42,8 @@ __global__ void k_pose_aux(int n_img, const double* __restrict__ poses, const do
   rotation_and_left_jacobian(p, R, Jl);
   double* a = aux + AUX * (size_t)i;
 #pragma unroll
-  for (int k = 0; k < 9; ++k) { a[k] = R[k]; a[9 + k] = Jl[k]; }
-  a[18] = p[3]; a[19] = p[4]; a[20] = p[5];
+  for (int k = 0; k < 9; ++k) { a[k] = R[k]; a[12 + k] = Jl[k]; }
+  a[9] = p[3]; a[10] = p[4]; a[11] = p[5];
   const double* m = pose_mask + 6 * (size_t)i;       // free-parameter masks ride along: [21] rvec, [22] tx + 2 ty + 4 tz
   a[21] = m[0]; a[22] = m[3] + 2.0 * m[4] + 4.0 * m[5]; a[23] = 0;
 }
@@ -49,104 +51,125 @@ __global__ void k_pose_aux(int n_img, const double* __restrict__ poses, const do
 // ---- K1: residual + Jacobian per observation -------------------------------------------
 // reads 24 B/obs (xy, img, pt) + gathered parameters, writes one 160 B record.
 // cost partial per block -> cost_part[blockIdx.x] (reduced deterministically afterwards).
+//
+// Observations are sorted by point, so the 32 observations of a warp see only a handful of distinct images.  A per-lane
+// gather of the 192-byte image record costs 12 x 32 L1 tag look-ups per warp and made the kernel L1-bound (ncu r1d: l1tex 72 %,
+// DRAM 38 %).  Instead the warp finds its distinct images (__match_any_sync), fetches each record ONCE with coalesced 16-byte
+// loads into a shared-memory slot, and every lane reads its slot (conflict-free 208-byte pitch).  The same shared-memory area
+// then stages the output records so that every store instruction of the warp covers one contiguous 512-byte run.
+constexpr int K1_SLOT = 26;                                   // doubles per image slot (208 B pitch: 16-byte aligned, bank-conflict-free)
+constexpr int K1_PITCH = 22;                                  // doubles per staged record
+constexpr int K1_WARP_DOUBLES = 32 * K1_SLOT;                 // >= 32 * K1_PITCH
+constexpr size_t K1_SMEM = sizeof(double) * 8 * K1_WARP_DOUBLES + sizeof(int) * 8 * 32 + sizeof(double) * 32;
+
 template <bool WITH_J, bool WITH_JI = false>
-__global__ void __launch_bounds__(256, WITH_J ? 2 : 4) k_residual_jacobian(
+__global__ void __launch_bounds__(256, WITH_J ? 2 : 3) k_residual_jacobian(
     int64_t n_obs, const double2* __restrict__ obs_xy, const int* __restrict__ obs_img, const int* __restrict__ obs_pt,
     const double* __restrict__ aux, const double* __restrict__ pts, const double* __restrict__ intr,
     const int* __restrict__ img_cam, const int* __restrict__ cam_model,
     const double* __restrict__ pose_mask, const double* __restrict__ pt_mask,
     LossParams L, double* __restrict__ rec, double* __restrict__ cost_part,
     double* __restrict__ ji = nullptr, const double* __restrict__ intr_mask = nullptr) {
-  __shared__ double red[32];
-  // records are staged per warp in shared memory (22-double pitch keeps 16-byte alignment) and written
-  // out as whole 512-byte runs: every store instruction of the warp covers contiguous global memory
-  constexpr int PITCH = 22;
-  __shared__ __align__(16) double stage[WITH_J ? 8 * 32 * PITCH : 2];
+  extern __shared__ __align__(16) unsigned char k1_smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* wbuf = reinterpret_cast<double*>(k1_smem) + (size_t)wib * K1_WARP_DOUBLES;       // image slots, then staged records
+  int* wimg = reinterpret_cast<int*>(k1_smem + sizeof(double) * 8 * K1_WARP_DOUBLES) + wib * 32;
+  double* red = reinterpret_cast<double*>(k1_smem + sizeof(double) * 8 * K1_WARP_DOUBLES + sizeof(int) * 8 * 32);
+  constexpr int NCH = WITH_J ? 12 : 6;                        // 16-byte chunks of the image record that this pass needs
   double cost = 0.0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + wib * 32; i0 < n_obs; i0 += stride) {
-    const int64_t i = i0 + lane;
-    const bool valid = i < n_obs;
-    if (valid) {
-      const int img = obs_img[i], pt = obs_pt[i];
-      const double2 xy = obs_xy[i];
-      // one 192-byte per-image record, fetched with 16-byte loads (R | Jl | t | masks)
-      const double2* a2 = reinterpret_cast<const double2*>(aux + AUX * (size_t)img);
-      double a[AUX];
-      if (WITH_J) {
+  int64_t i0 = blockIdx.x * (int64_t)blockDim.x + wib * 32;
+  // software pipeline: the indices / observation of the next round are in flight while this one is computed
+  int img_n = 0, pt_n = 0; double2 xy_n = make_double2(0.0, 0.0);
+  if (i0 < n_obs) { const int64_t i = min(i0 + lane, n_obs - 1); img_n = obs_img[i]; pt_n = obs_pt[i]; xy_n = obs_xy[i]; }
+  for (; i0 < n_obs; i0 += stride) {
+    const bool valid = i0 + lane < n_obs;                     // lanes past the end recompute the last observation and are masked out
+    const int img = img_n, pt = pt_n; const double2 xy = xy_n;
+    if (i0 + stride < n_obs) { const int64_t i = min(i0 + stride + lane, n_obs - 1); img_n = obs_img[i]; pt_n = obs_pt[i]; xy_n = obs_xy[i]; }
+    const double X0 = pts[3 * (size_t)pt], X1 = pts[3 * (size_t)pt + 1], X2 = pts[3 * (size_t)pt + 2];
+    // distinct images of this warp -> shared-memory slots
+    const unsigned grp = __match_any_sync(0xffffffffu, img);
+    const int leader = __ffs(grp) - 1;
+    const unsigned lead_mask = __ballot_sync(0xffffffffu, lane == leader);
+    const int slot = __popc(lead_mask & ((1u << leader) - 1u));
+    const int total = __popc(lead_mask) * NCH;
+    if (lane == leader) wimg[slot] = img;
+    __syncwarp();
+    for (int it = lane; it < total; it += 32) {
+      const int k = it / NCH, c = it - k * NCH;
+      const double2 v = __ldg(reinterpret_cast<const double2*>(aux + AUX * (size_t)wimg[k]) + c);
+      *reinterpret_cast<double2*>(wbuf + k * K1_SLOT + 2 * c) = v;
+    }
+    __syncwarp();
+    double a[AUX];
+    {
+      const double2* s2 = reinterpret_cast<const double2*>(wbuf + slot * K1_SLOT);
 #pragma unroll
-        for (int k = 0; k < AUX / 2; ++k) { const double2 t = __ldg(a2 + k); a[2 * k] = t.x; a[2 * k + 1] = t.y; }
-      } else {
-#pragma unroll
-        for (int k = 0; k < 5; ++k) { const double2 t = __ldg(a2 + k); a[2 * k] = t.x; a[2 * k + 1] = t.y; }
-#pragma unroll
-        for (int k = 9; k < 11; ++k) { const double2 t = __ldg(a2 + k); a[2 * k] = t.x; a[2 * k + 1] = t.y; }
-      }
-      const double X0 = pts[3 * (size_t)pt], X1 = pts[3 * (size_t)pt + 1], X2 = pts[3 * (size_t)pt + 2];
-      const double* R = a;
-      const double Y0 = R[0] * X0 + R[1] * X1 + R[2] * X2;
-      const double Y1 = R[3] * X0 + R[4] * X1 + R[5] * X2;
-      const double Y2 = R[6] * X0 + R[7] * X1 + R[8] * X2;
-      const double xc = Y0 + a[18], yc = Y1 + a[19], zc = Y2 + a[20];
-      const int cam = img_cam[img];
-      const int model = cam_model[cam];
-      double u, v, dX[2][3], dP[2][9];
-      world2image<WITH_J>(model, intr + MM_INTR_STRIDE * (size_t)cam, xc, yc, zc, u, v, dX, WITH_JI ? dP : nullptr);
-      const double r0 = u - xy.x, r1 = v - xy.y;
-      double rho0, sr;
-      loss_eval(L, r0 * r0 + r1 * r1, rho0, sr);
-      cost += 0.5 * rho0;
-      if (WITH_JI) {        // d r / d intrinsics (2 x 9), robustified and masked; 144 B per observation
-        double2* j2 = reinterpret_cast<double2*>(ji + 18 * (size_t)i);
+      for (int k = 0; k < NCH; ++k) { const double2 t = s2[k]; a[2 * k] = t.x; a[2 * k + 1] = t.y; }
+    }
+    __syncwarp();                                             // slots are free again: the same area stages the records below
+    const double* R = a;
+    const double Y0 = R[0] * X0 + R[1] * X1 + R[2] * X2;
+    const double Y1 = R[3] * X0 + R[4] * X1 + R[5] * X2;
+    const double Y2 = R[6] * X0 + R[7] * X1 + R[8] * X2;
+    const double xc = Y0 + a[9], yc = Y1 + a[10], zc = Y2 + a[11];
+    const int cam = img_cam[img];
+    const int model = cam_model[cam];
+    double u, v, dX[2][3], dP[2][9];
+    world2image<WITH_J>(model, intr + MM_INTR_STRIDE * (size_t)cam, xc, yc, zc, u, v, dX, WITH_JI ? dP : nullptr);
+    const double r0 = u - xy.x, r1 = v - xy.y;
+    double rho0, sr;
+    loss_eval(L, r0 * r0 + r1 * r1, rho0, sr);
+    if (valid) cost += 0.5 * rho0;
+    if (WITH_JI) {        // d r / d intrinsics (2 x 9), robustified and masked; 144 B per observation
+      if (valid) {
+        double2* j2 = reinterpret_cast<double2*>(ji + 18 * (size_t)(i0 + lane));
         double t[18];
 #pragma unroll
         for (int k = 0; k < 9; ++k) { const double m = intr_mask[k] * sr; t[k] = dP[0][k] * m; t[9 + k] = dP[1][k] * m; }
 #pragma unroll
         for (int k = 0; k < 9; ++k) j2[k] = make_double2(t[2 * k], t[2 * k + 1]);
       }
-      if (WITH_J) {
-        const double mp = pt_mask[pt] * sr;
-        const int mbits = (int)a[22];
-        const double mw = a[21] * sr, mx = (mbits & 1) ? sr : 0.0, my = (mbits & 2) ? sr : 0.0, mz = (mbits & 4) ? sr : 0.0;
-        double2* o2 = reinterpret_cast<double2*>(stage + (size_t)(wib * 32 + lane) * PITCH);
-        o2[0] = make_double2(sr * r0, sr * r1);
-        // d(Xc)/d(w) = -[Y]x Jl : column k = Jl[:,k] x Y
-        double M[3][3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const double c0 = a[9 + k], c1 = a[12 + k], c2 = a[15 + k];
-          M[0][k] = c1 * Y2 - c2 * Y1; M[1][k] = c2 * Y0 - c0 * Y2; M[2][k] = c0 * Y1 - c1 * Y0;
-        }
-#pragma unroll
-        for (int row = 0; row < 2; ++row) {
-          const double d0 = dX[row][0], d1 = dX[row][1], d2 = dX[row][2];
-          const double jw0 = (d0 * M[0][0] + d1 * M[1][0] + d2 * M[2][0]) * mw;
-          const double jw1 = (d0 * M[0][1] + d1 * M[1][1] + d2 * M[2][1]) * mw;
-          const double jw2 = (d0 * M[0][2] + d1 * M[1][2] + d2 * M[2][2]) * mw;
-          o2[1 + 3 * row] = make_double2(jw0, jw1);
-          o2[2 + 3 * row] = make_double2(jw2, d0 * mx);
-          o2[3 + 3 * row] = make_double2(d1 * my, d2 * mz);
-        }
-        const double p00 = (dX[0][0] * R[0] + dX[0][1] * R[3] + dX[0][2] * R[6]) * mp;
-        const double p01 = (dX[0][0] * R[1] + dX[0][1] * R[4] + dX[0][2] * R[7]) * mp;
-        const double p02 = (dX[0][0] * R[2] + dX[0][1] * R[5] + dX[0][2] * R[8]) * mp;
-        const double p10 = (dX[1][0] * R[0] + dX[1][1] * R[3] + dX[1][2] * R[6]) * mp;
-        const double p11 = (dX[1][0] * R[1] + dX[1][1] * R[4] + dX[1][2] * R[7]) * mp;
-        const double p12 = (dX[1][0] * R[2] + dX[1][1] * R[5] + dX[1][2] * R[8]) * mp;
-        o2[7] = make_double2(p00, p01);
-        o2[8] = make_double2(p02, p10);
-        o2[9] = make_double2(p11, p12);
-      }
     }
     if (WITH_J) {
+      const double mp = pt_mask[pt] * sr;
+      const int mbits = (int)a[22];
+      const double mw = a[21] * sr, mx = (mbits & 1) ? sr : 0.0, my = (mbits & 2) ? sr : 0.0, mz = (mbits & 4) ? sr : 0.0;
+      double2* o2 = reinterpret_cast<double2*>(wbuf + (size_t)lane * K1_PITCH);
+      o2[0] = make_double2(sr * r0, sr * r1);
+      // d(Xc)/d(w) = -[Y]x Jl : column k = Jl[:,k] x Y
+      double M[3][3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double c0 = a[12 + k], c1 = a[15 + k], c2 = a[18 + k];
+        M[0][k] = c1 * Y2 - c2 * Y1; M[1][k] = c2 * Y0 - c0 * Y2; M[2][k] = c0 * Y1 - c1 * Y0;
+      }
+#pragma unroll
+      for (int row = 0; row < 2; ++row) {
+        const double d0 = dX[row][0], d1 = dX[row][1], d2 = dX[row][2];
+        const double jw0 = (d0 * M[0][0] + d1 * M[1][0] + d2 * M[2][0]) * mw;
+        const double jw1 = (d0 * M[0][1] + d1 * M[1][1] + d2 * M[2][1]) * mw;
+        const double jw2 = (d0 * M[0][2] + d1 * M[1][2] + d2 * M[2][2]) * mw;
+        o2[1 + 3 * row] = make_double2(jw0, jw1);
+        o2[2 + 3 * row] = make_double2(jw2, d0 * mx);
+        o2[3 + 3 * row] = make_double2(d1 * my, d2 * mz);
+      }
+      const double p00 = (dX[0][0] * R[0] + dX[0][1] * R[3] + dX[0][2] * R[6]) * mp;
+      const double p01 = (dX[0][0] * R[1] + dX[0][1] * R[4] + dX[0][2] * R[7]) * mp;
+      const double p02 = (dX[0][0] * R[2] + dX[0][1] * R[5] + dX[0][2] * R[8]) * mp;
+      const double p10 = (dX[1][0] * R[0] + dX[1][1] * R[3] + dX[1][2] * R[6]) * mp;
+      const double p11 = (dX[1][0] * R[1] + dX[1][1] * R[4] + dX[1][2] * R[7]) * mp;
+      const double p12 = (dX[1][0] * R[2] + dX[1][1] * R[5] + dX[1][2] * R[8]) * mp;
+      o2[7] = make_double2(p00, p01);
+      o2[8] = make_double2(p02, p10);
+      o2[9] = make_double2(p11, p12);
       __syncwarp();
       const int nvalid = (int)min((int64_t)32, n_obs - i0);
       double2* g2 = reinterpret_cast<double2*>(rec + REC * (size_t)i0);
 #pragma unroll
       for (int k = 0; k < 10; ++k) {
         const int c = k * 32 + lane, src = c / 10, part = c - 10 * src;
-        if (src < nvalid) g2[c] = *reinterpret_cast<const double2*>(stage + (size_t)(wib * 32 + src) * PITCH + 2 * part);
+        if (src < nvalid) g2[c] = *reinterpret_cast<const double2*>(wbuf + (size_t)src * K1_PITCH + 2 * part);
       }
       __syncwarp();
     }
@@ -593,7 +616,36 @@ struct PcgArgs {
   unsigned long long* dbg;   // optional: %globaltimer stamps of CTA 0 for the first 32 iterations (6 per iteration)
   // dense border of the reduced system when the (single, shared) camera's intrinsics are refined: unknowns [poses | 9 intrinsics]
   int n_intr; const double* Bm; const double* Cm; const double* Cinv; const double* bi; double *xi, *zi, *pi0, *pi1, *bt;
+  // coarse level of the two-level preconditioner (ba_coarse.cuh): cm = 7 * aggregates (0 = block-Jacobi only)
+  int cm; const int* agg; const double* Pc; const double* Ainv; double* rc /*[2][cm]*/; double* qc; double* yc;
 };
+
+// P_i' v added into a coarse vector: lane r < 6 holds row r of the image's 6 x 7 prolongation block (Pl) and v[r]
+__device__ __forceinline__ void coarse_restrict_add(const double (&Pl)[CM], double v, int lane, bool valid, double* dst) {
+  double t[CM];
+#pragma unroll
+  for (int k = 0; k < CM; ++k) {
+    t[k] = Pl[k] * v;
+    t[k] += __shfl_xor_sync(0xffffffffu, t[k], 1);
+    t[k] += __shfl_xor_sync(0xffffffffu, t[k], 2);
+    t[k] += __shfl_xor_sync(0xffffffffu, t[k], 4);
+  }
+  double mine = t[0];
+#pragma unroll
+  for (int k = 1; k < CM; ++k) if (lane == k) mine = t[k];
+  if (valid && lane < CM && mine != 0.0) atomicAdd(dst + lane, mine);
+}
+// yc = Ainv (rc_old - alpha qc), rows spread over all warps of the grid; rc_new = rc_old - alpha qc (residual recursion)
+__device__ __forceinline__ void coarse_solve(const PcgArgs& A, double alpha, const double* rc_old, double* rc_new, int gw, int nwt, int lane) {
+  const int cm = A.cm;
+  for (int j = gw; j < cm; j += nwt) {
+    const double* row = A.Ainv + (size_t)j * cm;
+    double s = 0.0;
+    for (int k = lane; k < cm; k += 32) s += row[k] * (__ldcg(rc_old + k) - alpha * __ldcg(A.qc + k));
+    s = warp_sum(s);
+    if (lane == 0) { __stcg(A.yc + j, s); if (rc_new) __stcg(rc_new + j, __ldcg(rc_old + j) - alpha * __ldcg(A.qc + j)); }
+  }
+}
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define PCG_STAMP(k) do { if (A.dbg && blockIdx.x == 0 && threadIdx.x == 0 && it < 32) A.dbg[6 * it + (k)] = gtimer(); } while (0)
 
@@ -622,7 +674,19 @@ __global__ void __launch_bounds__(256) k_pcg_persistent(PcgArgs A) {
   const bool owner = border && gw == 0;
   const bool olane = owner && lane < 9;
   double xi = 0.0, ri = 0.0, zi_ = 0.0, pi_ = 0.0, cp = 0.0;    // owner-lane state of the intrinsics part
-  // ---- init: x = 0, r = b, z = Minv r, p = 0
+  const bool coarse = A.cm > 0;
+  // ---- init: x = 0, r = b, z = M^-1 r, p = 0
+  if (coarse) {       // coarse residual rc = P' b, then yc = Ainv rc
+    for (int row = gw; row < n; row += nw) {
+      double Pl[CM];
+#pragma unroll
+      for (int k = 0; k < CM; ++k) Pl[k] = lane < 6 ? A.Pc[PCS * (size_t)row + CM * lane + k] : 0.0;
+      coarse_restrict_add(Pl, lane < 6 ? A.b[6 * (size_t)row + lane] : 0.0, lane, true, A.rc + CM * A.agg[row]);
+    }
+    grid.sync();
+    coarse_solve(A, 0.0, A.rc, nullptr, gw, nw, lane);
+    grid.sync();
+  }
   {
     double a_rz = 0.0, a_bb = 0.0;
     for (int row = gw; row < n; row += nw) {
@@ -631,6 +695,11 @@ __global__ void __launch_bounds__(256) k_pcg_persistent(PcgArgs A) {
       double zl = 0.0;
 #pragma unroll
       for (int c = 0; c < 6; ++c) { const double rc = __shfl_sync(0xffffffffu, rv, c); if (lane < 6) zl += A.Minv[36 * (size_t)row + 6 * lane + c] * rc; }
+      if (coarse && lane < 6) {
+        const double* yc = A.yc + CM * A.agg[row];
+#pragma unroll
+        for (int k = 0; k < CM; ++k) zl += A.Pc[PCS * (size_t)row + CM * lane + k] * __ldcg(yc + k);
+      }
       if (lane < 6) {
         const size_t i = 6 * (size_t)row + lane;
         A.x[i] = 0.0; A.r[i] = rv; A.z[i] = zl; A.p0[i] = 0.0; A.p1[i] = 0.0;
@@ -719,6 +788,12 @@ __global__ void __launch_bounds__(256) k_pcg_persistent(PcgArgs A) {
           for (int r = 0; r < 6; ++r) { const double pr = __shfl_sync(0xffffffffu, pn, r); if (lane < 9) btl += Ba[9 * r + lane] * pr; }
         }
         if (lane < 6) { p_new[i] = pn; A.Ap[i] = t + bp; acc += pn * (t + bp) + pn * bp; }
+        if (coarse) {     // qc += P' (A p): the coarse residual follows the recursion r -= alpha A p without another pass
+          double Pl[CM];
+#pragma unroll
+          for (int k = 0; k < CM; ++k) Pl[k] = lane < 6 ? A.Pc[PCS * (size_t)row + CM * lane + k] : 0.0;
+          coarse_restrict_add(Pl, lane < 6 ? t : 0.0, lane, true, A.qc + CM * A.agg[row]);
+        }
       }
       if (border) {
         // B' p: block-level reduction, then 9 atomics per CTA into the parity slot
@@ -747,10 +822,29 @@ __global__ void __launch_bounds__(256) k_pcg_persistent(PcgArgs A) {
           rv = A.r[i] - alpha * A.Ap[i];
           A.r[i] = rv;
         }
+        if (coarse) continue;                           // z needs the coarse correction: second pass below
         double zl = 0.0;
 #pragma unroll
         for (int c = 0; c < 6; ++c) { const double rc = __shfl_sync(0xffffffffu, rv, c); if (lane < 6) zl += A.Minv[36 * (size_t)row + 6 * lane + c] * rc; }
         if (lane < 6) { A.z[i] = zl; a_rz += rv * zl; a_rr += rv * rv; }
+      }
+      if (coarse) {
+        coarse_solve(A, alpha, A.rc + (size_t)(it & 1) * A.cm, A.rc + (size_t)nxt * A.cm, gw, nw, lane);
+        grid.sync();
+        for (int j = gw * 32 + lane; j < A.cm; j += nw * 32) A.qc[j] = 0.0;       // next accumulation starts after the barrier below
+        for (int row = gw; row < n; row += nw) {
+          const size_t i = 6 * (size_t)row + (lane < 6 ? lane : 0);
+          const double rv = lane < 6 ? A.r[i] : 0.0;
+          double zl = 0.0;
+#pragma unroll
+          for (int c = 0; c < 6; ++c) { const double rc = __shfl_sync(0xffffffffu, rv, c); if (lane < 6) zl += A.Minv[36 * (size_t)row + 6 * lane + c] * rc; }
+          if (lane < 6) {
+            const double* yc = A.yc + CM * A.agg[row];
+#pragma unroll
+            for (int k = 0; k < CM; ++k) zl += A.Pc[PCS * (size_t)row + CM * lane + k] * __ldcg(yc + k);
+            A.z[i] = zl; a_rz += rv * zl; a_rr += rv * rv;
+          }
+        }
       }
       if (owner) {
         if (olane) { const double api = __ldcg(A.bt + 9 * (it & 1) + lane) + cp; xi += alpha * pi_; ri -= alpha * api; A.bt[9 * nxt + lane] = 0.0; }
@@ -815,10 +909,26 @@ __global__ void __launch_bounds__(THREADS, 1) k_pcg_cached(PcgArgs A, int e_cap)
   // ---- init
   double xl = 0.0, rl = 0.0, zl = 0.0, pl = 0.0, apl = 0.0;
   const size_t gi = 6 * (size_t)(valid ? row : 0) + (lane < 6 ? lane : 0);
+  const bool coarse = A.cm > 0;
+  const int gw = blockIdx.x * NW + wib, nwt = gridDim.x * NW;
+  double Pl[CM]; int ga = 0;                          // this row of the prolongation block, aggregate offset
+#pragma unroll
+  for (int k = 0; k < CM; ++k) Pl[k] = (coarse && act) ? A.Pc[PCS * (size_t)row + CM * lane + k] : 0.0;
+  if (coarse && valid) ga = CM * A.agg[row];
   {
     if (act) rl = A.b[gi];
+    if (coarse) {
+      coarse_restrict_add(Pl, rl, lane, valid, A.rc + ga);
+      grid.sync();
+      coarse_solve(A, 0.0, A.rc, nullptr, gw, nwt, lane);
+      grid.sync();
+    }
 #pragma unroll
     for (int c = 0; c < 6; ++c) { const double rc = __shfl_sync(0xffffffffu, rl, c); if (act) zl += sM[wib * 36 + 6 * lane + c] * rc; }
+    if (coarse && act) {
+#pragma unroll
+      for (int k = 0; k < CM; ++k) zl += Pl[k] * __ldcg(A.yc + ga + k);
+    }
     if (act) { A.z[gi] = zl; A.p0[gi] = 0.0; A.p1[gi] = 0.0; }
     double a_rz = act ? rl * zl : 0.0, a_bb = act ? rl * rl : 0.0;
     a_rz = block_sum_to_thread0(a_rz, red); a_bb = block_sum_to_thread0(a_bb, red);
@@ -862,6 +972,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_pcg_cached(PcgArgs A, int e_cap)
       PCG_STAMP(1);
       double acc = 0.0;
       if (act) { pl = zl + beta * pl; apl = t; p_new[gi] = pl; acc = pl * t; }
+      if (coarse) coarse_restrict_add(Pl, act ? t : 0.0, lane, valid, A.qc + ga);
       acc = block_sum_to_thread0(acc, red);
       if (threadIdx.x == 0) atomicAdd(A.sc + (it & 1), acc);
       PCG_STAMP(2);
@@ -872,9 +983,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_pcg_cached(PcgArgs A, int e_cap)
       if (blockIdx.x == 0 && threadIdx.x == 0) A.sc[nxt] = 0.0;
       // ---- update (registers only)
       if (act) { xl += alpha * pl; rl -= alpha * apl; }
+      if (coarse) {
+        coarse_solve(A, alpha, A.rc + (size_t)(it & 1) * A.cm, A.rc + (size_t)nxt * A.cm, gw, nwt, lane);
+        grid.sync();
+        for (int j = gw * 32 + lane; j < A.cm; j += nwt * 32) A.qc[j] = 0.0;     // next accumulation starts after the barrier below
+      }
       double zn = 0.0;
 #pragma unroll
       for (int c = 0; c < 6; ++c) { const double rc = __shfl_sync(0xffffffffu, rl, c); if (act) zn += sM[wib * 36 + 6 * lane + c] * rc; }
+      if (coarse && act) {
+#pragma unroll
+        for (int k = 0; k < CM; ++k) zn += Pl[k] * __ldcg(A.yc + ga + k);
+      }
       if (act) { zl = zn; A.z[gi] = zl; }
       double a_rz = act ? rl * zl : 0.0, a_rr = act ? rl * rl : 0.0;
       a_rz = block_sum_to_thread0(a_rz, red); a_rr = block_sum_to_thread0(a_rr, red);
@@ -1165,9 +1285,9 @@ __global__ void k_point_errors(int n_pt, const int* __restrict__ pt_start, const
   for (int o = o0; o < o1; ++o) {
     const int img = obs_img[o];
     const double* a = aux + AUX * (size_t)img;
-    const double xc = a[0] * X0 + a[1] * X1 + a[2] * X2 + a[18];
-    const double yc = a[3] * X0 + a[4] * X1 + a[5] * X2 + a[19];
-    const double zc = a[6] * X0 + a[7] * X1 + a[8] * X2 + a[20];
+    const double xc = a[0] * X0 + a[1] * X1 + a[2] * X2 + a[9];
+    const double yc = a[3] * X0 + a[4] * X1 + a[5] * X2 + a[10];
+    const double zc = a[6] * X0 + a[7] * X1 + a[8] * X2 + a[11];
     const int cam = img_cam[img];
     double u, v;
     world2image<false>(cam_model[cam], intr + MM_INTR_STRIDE * (size_t)cam, xc, yc, zc, u, v, nullptr, nullptr);

@@ -296,7 +296,8 @@ static int assemble_and_factor(ba_t* B) {
     if (dump && ++dump_count == (getenv("ORC_DUMP_AT") ? atoi(getenv("ORC_DUMP_AT")) : 3)) {
       FILE* f = fopen(dump, "wb");
       if (f) { fwrite(&nc, sizeof(int), 1, f); fwrite(B->first, sizeof(int), (size_t)nc, f); fwrite(B->rowptr, sizeof(int64_t), (size_t)nc + 1, f);
-               fwrite(B->S, sizeof(double), (size_t)B->rowptr[nc], f); fwrite(B->rhs, sizeof(double), (size_t)nc, f); fclose(f); } } }
+               fwrite(B->S, sizeof(double), (size_t)B->rowptr[nc], f); fwrite(B->rhs, sizeof(double), (size_t)nc, f);
+               fwrite(B->scale_c, sizeof(double), (size_t)nc, f); fwrite(B->poses, sizeof(double), 6*(size_t)n_img, f); fclose(f); } } }
   /* left-looking skyline Cholesky, rows stored contiguously */
   for (int j = 0; j < nc; ++j) {
     double* Lj = B->S + B->rowptr[j]; const int fj = B->first[j];

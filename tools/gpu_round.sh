@@ -1,0 +1,33 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, the bench lines, the ncu launch list and the --set full captures.
+# usage (under gpurun): bash tools/gpu_round.sh <tag> [stages...]   stages: test bench cfg4 launches full
+set -u
+TAG=${1:-r1}; shift || true
+STAGES=${*:-"test bench cfg4 launches full"}
+OUT=gpurun_out; mkdir -p $OUT
+has() { case " $STAGES " in *" $1 "*) return 0;; esac; return 1; }
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi_$TAG.txt 2>&1
+if has test; then
+  timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu_$TAG.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_gpu_$TAG.log
+  tail -3 $OUT/pytest_gpu_$TAG.log
+fi
+if has bench; then
+  timeout 600 python bench.py > $OUT/bench_${TAG}_cfg2.json 2> $OUT/bench_${TAG}_cfg2.err; tail -c 600 $OUT/bench_${TAG}_cfg2.json
+  timeout 300 python bench.py --impl reference --steps 3 > $OUT/bench_${TAG}_ref.json 2>> $OUT/bench_${TAG}_cfg2.err
+fi
+if has cfg4; then
+  timeout 900 python bench.py --workload ba_cfg4 --no-match --cpu-steps 2 > $OUT/bench_${TAG}_cfg4.json 2> $OUT/bench_${TAG}_cfg4.err; tail -c 600 $OUT/bench_${TAG}_cfg4.json
+fi
+if has launches; then
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/launches_$TAG.csv \
+      python bench.py --steps 2 --warmup 3 --no-cpu > $OUT/launches_$TAG.log 2>&1
+fi
+if has full; then
+  timeout 600 ncu --set full --clock-control none --import-source on \
+      -k regex:'k_residual_jacobian|k_schur_point|k_schur_cam|k_backsub' -s 8 -c 8 -f -o $OUT/prof_ba_$TAG \
+      python tools/time_ba.py cfg4 2 > $OUT/prof_ba_$TAG.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on \
+      -k regex:'k_match_tc|k_rerank|k_tc_prep' -s 3 -c 4 -f -o $OUT/prof_match_$TAG \
+      python tools/time_match.py 64 > $OUT/prof_match_$TAG.log 2>&1
+fi
+echo done
