@@ -29,7 +29,8 @@ __global__ void k_pair_count(int n_pt, const int* __restrict__ pt_start, int64_t
   if (p < n_pt) { const int64_t k = pt_start[p + 1] - pt_start[p]; cnt[p] = k * (k - 1) / 2; }
 }
 __global__ void k_pair_keys(int n_pt, int n_img, const int* __restrict__ pt_start, const int* __restrict__ obs_img,
-                            const int64_t* __restrict__ pair_off, unsigned long long* __restrict__ keys) {
+                            const int64_t* __restrict__ pair_off, unsigned long long* __restrict__ keys,
+                            int* __restrict__ pair_lo, int* __restrict__ pair_hi) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_pt) return;
   int64_t slot = pair_off[p];
@@ -40,6 +41,7 @@ __global__ void k_pair_keys(int n_pt, int n_img, const int* __restrict__ pt_star
       const int b = obs_img[j];
       const unsigned long long lo = a < b ? a : b, hi = a < b ? b : a;
       keys[slot] = lo * (unsigned long long)n_img + hi;
+      pair_lo[slot] = a <= b ? i : j; pair_hi[slot] = a <= b ? j : i;      // observation of the lower / higher image index
     }
   }
 }
@@ -51,16 +53,21 @@ __global__ void k_pair_heads(int64_t n, int n_img, const unsigned long long* __r
     head[i] = (!diag && (i == 0 || keys[i - 1] != k)) ? 1 : 0;
   }
 }
+// block id of every (sorted) pair; per block the contiguous range of its pairs in sorted order and the pairs themselves
 __global__ void k_pair_assign(int64_t n, int n_img, const unsigned long long* __restrict__ keys, const int* __restrict__ incl,
-                              const int* __restrict__ head, const int* __restrict__ slot, int* __restrict__ pair_blk,
-                              int* __restrict__ blk_a, int* __restrict__ blk_b) {
+                              const int* __restrict__ head, const int* __restrict__ slot,
+                              int* __restrict__ blk_a, int* __restrict__ blk_b,
+                              const int* __restrict__ pair_lo, const int* __restrict__ pair_hi, int* __restrict__ sp_lo, int* __restrict__ sp_hi,
+                              const int* __restrict__ obs_pt, int* __restrict__ sp_pt, int* __restrict__ bp_start, int* __restrict__ bp_end) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const unsigned long long k = keys[i];
     const int a = (int)(k / n_img), b = (int)(k % n_img);
-    if (a == b) { pair_blk[slot[i]] = a; continue; }
-    const int id = incl[i] - 1;
-    pair_blk[slot[i]] = n_img + id;
-    if (head[i]) { blk_a[id] = a; blk_b[id] = b; }
+    const int sl = slot[i];
+    const int id = (a == b) ? a : n_img + incl[i] - 1;
+    if (a != b && head[i]) { blk_a[incl[i] - 1] = a; blk_b[incl[i] - 1] = b; }
+    sp_lo[i] = pair_lo[sl]; sp_hi[i] = pair_hi[sl]; sp_pt[i] = obs_pt[pair_lo[sl]];
+    if (i == 0 || keys[i - 1] != k) bp_start[id] = (int)i;
+    if (i == n - 1 || keys[i + 1] != k) bp_end[id] = (int)(i + 1);
   }
 }
 // CSR entries: key = row * n_img + col, value = signed block reference (negative = transposed)
@@ -116,7 +123,7 @@ struct mm_ba_session {
   std::vector<double> h_poses0, h_intr0, h_pts0;
   std::vector<double> h_pt_mask; std::vector<int> h_pt_new2old; unsigned long long spread = 1;         // internal point order (spatially clustered) -> caller's order
   DevBuf<double2> obs_xy; DevBuf<int> obs_img, obs_pt, pt_start, cam_perm, cam_start, img_cam, cam_model;
-  DevBuf<int64_t> pair_off; DevBuf<int> pair_blk, row_start, row_col, row_blk;
+  DevBuf<int64_t> pair_off; DevBuf<int> row_start, row_col, row_blk, sp_lo, sp_hi, sp_pt, bp_start, bp_end; DevBuf<double> pinfo;
   DevBuf<double> S, Minv, poses, intr, pts, poses2, pts2, aux, aux2, rec;
   DevBuf<double> pose_mask, pt_mask, scale_c, scale_p, Vinv, gp, dp, gc, dc, rhs;
   DevBuf<double> vx, vr, vz, vp0, vp1, vAp, pcg_sc; DevBuf<int> pcg_ic;
@@ -247,23 +254,28 @@ int build_structure(mm_ba_session* s, const mm_ba_problem* P) {
   MM_CUDA(cudaMemcpy(&n_pairs, s->pair_off.p + n_pt, sizeof(int64_t), cudaMemcpyDeviceToHost));
   if (n_pairs >= ((int64_t)1 << 31)) { set_error("too many observation pairs (%lld)", (long long)n_pairs); return MM_ERR_UNSUPPORTED; }
   s->n_pairs = n_pairs;
-  MM_CUDA(s->pair_blk.alloc((size_t)n_pairs));
   DevBuf<int>& blk_a = s->blk_a; DevBuf<int>& blk_b = s->blk_b;
   int n_off = 0;
+  MM_CUDA(s->sp_lo.alloc((size_t)n_pairs)); MM_CUDA(s->sp_hi.alloc((size_t)n_pairs)); MM_CUDA(s->sp_pt.alloc((size_t)n_pairs));
   if (n_pairs > 0) {
-    DevBuf<unsigned long long> keys, keys_s; DevBuf<int> slot, slot_s, head, incl;
+    DevBuf<unsigned long long> keys, keys_s; DevBuf<int> slot, slot_s, head, incl, pair_lo, pair_hi;
     MM_CUDA(keys.alloc(n_pairs)); MM_CUDA(keys_s.alloc(n_pairs)); MM_CUDA(slot.alloc(n_pairs)); MM_CUDA(slot_s.alloc(n_pairs));
-    MM_CUDA(head.alloc(n_pairs)); MM_CUDA(incl.alloc(n_pairs));
-    k_pair_keys<<<blocks_for(n_pt, B), B, 0, st>>>(n_pt, n_img, s->pt_start.p, s->obs_img.p, s->pair_off.p, keys.p); MM_LAUNCH_CHECK();
+    MM_CUDA(head.alloc(n_pairs)); MM_CUDA(incl.alloc(n_pairs)); MM_CUDA(pair_lo.alloc(n_pairs)); MM_CUDA(pair_hi.alloc(n_pairs));
+    k_pair_keys<<<blocks_for(n_pt, B), B, 0, st>>>(n_pt, n_img, s->pt_start.p, s->obs_img.p, s->pair_off.p, keys.p, pair_lo.p, pair_hi.p); MM_LAUNCH_CHECK();
     k_iota<<<blocks_for(n_pairs, B), B, 0, st>>>((int)n_pairs, slot.p); MM_LAUNCH_CHECK();
     int rc = sort_pairs<unsigned long long, int>(st, keys.p, keys_s.p, slot.p, slot_s.p, n_pairs, bits_for((unsigned long long)n_img * (unsigned long long)n_img)); if (rc) return rc;
     k_pair_heads<<<grid_stride(n_pairs, B), B, 0, st>>>(n_pairs, n_img, keys_s.p, head.p); MM_LAUNCH_CHECK();
     rc = inclusive_sum<int>(st, head.p, incl.p, n_pairs); if (rc) return rc;
     MM_CUDA(cudaMemcpy(&n_off, incl.p + (n_pairs - 1), sizeof(int), cudaMemcpyDeviceToHost));
     MM_CUDA(blk_a.alloc((size_t)n_off)); MM_CUDA(blk_b.alloc((size_t)n_off));
-    k_pair_assign<<<grid_stride(n_pairs, B), B, 0, st>>>(n_pairs, n_img, keys_s.p, incl.p, head.p, slot_s.p, s->pair_blk.p, blk_a.p, blk_b.p); MM_LAUNCH_CHECK();
+    MM_CUDA(s->bp_start.alloc((size_t)n_img + n_off)); MM_CUDA(s->bp_end.alloc((size_t)n_img + n_off));
+    MM_CUDA(cudaMemsetAsync(s->bp_start.p, 0, sizeof(int) * ((size_t)n_img + n_off), st)); MM_CUDA(cudaMemsetAsync(s->bp_end.p, 0, sizeof(int) * ((size_t)n_img + n_off), st));
+    k_pair_assign<<<grid_stride(n_pairs, B), B, 0, st>>>(n_pairs, n_img, keys_s.p, incl.p, head.p, slot_s.p, blk_a.p, blk_b.p,
+        pair_lo.p, pair_hi.p, s->sp_lo.p, s->sp_hi.p, s->obs_pt.p, s->sp_pt.p, s->bp_start.p, s->bp_end.p); MM_LAUNCH_CHECK();
     MM_CUDA(cudaStreamSynchronize(st));
   }
+  if (!s->bp_start.p) { MM_CUDA(s->bp_start.alloc((size_t)std::max(n_img, 1))); MM_CUDA(s->bp_end.alloc((size_t)std::max(n_img, 1)));
+    MM_CUDA(cudaMemsetAsync(s->bp_start.p, 0, sizeof(int) * (size_t)std::max(n_img, 1), st)); MM_CUDA(cudaMemsetAsync(s->bp_end.p, 0, sizeof(int) * (size_t)std::max(n_img, 1), st)); }
   if (!blk_a.p) { MM_CUDA(blk_a.alloc(1)); MM_CUDA(blk_b.alloc(1)); }
   s->n_off = n_off; s->nblk = (int64_t)n_img + n_off;
   // 5. block-CSR rows for the SpMV (each off-diagonal block referenced from both rows)
@@ -404,8 +416,8 @@ int launch_coarse_setup(mm_ba_session* s) {
   MM_CUDA(cudaMemsetAsync(s->Ac.p, 0, sizeof(double) * (size_t)m * m, st));
   k_coarse_assemble<<<blocks_for(s->nblk * 32, 128), 128, 0, st>>>(s->n_img, s->nblk, s->blk_a.p, s->blk_b.p, s->S.p, s->agg.p, s->Pc.p, m, s->Ac.p); MM_LAUNCH_CHECK();
   k_coarse_ridge<<<blocks_for(m, 128), 128, 0, st>>>(m, s->Ac.p); MM_LAUNCH_CHECK();
-  double* Ap = s->Ac.p; double* Ck = s->gjC.p; double* Rk = s->gjR.p;
-  void* args[] = { &m, &Ap, &Ck, &Rk };
+  double* Ap = s->Ac.p; double* Ck = s->gjC.p; double* Rk = s->gjR.p; unsigned long long* dbg = nullptr;
+  void* args[] = { &m, &Ap, &Ck, &Rk, &dbg };
   MM_CUDA(cudaLaunchCooperativeKernel((const void*)k_spd_inverse, dim3(s->gj_grid), dim3(256), args, 0, st));
   count_launch();
   return MM_OK;
@@ -434,7 +446,7 @@ int launch_linearize(mm_ba_session* s) {
 int launch_cost_candidate(mm_ba_session* s) {
   cudaStream_t st = s->stream;
   k_pose_aux<<<blocks_for(s->n_img, 128), 128, 0, st>>>(s->n_img, s->poses2.p, s->pose_mask.p, s->aux2.p); MM_LAUNCH_CHECK();
-  k_residual_jacobian<false><<<s->grid_obs, 256, K1_SMEM, st>>>(s->n_obs, s->obs_xy.p, s->obs_img.p, s->obs_pt.p, s->aux2.p, s->pts2.p, s->refine ? s->intr2.p : s->intr.p,
+  k_residual_jacobian<false><<<s->grid_obs, 256, K1_SMEM_COST, st>>>(s->n_obs, s->obs_xy.p, s->obs_img.p, s->obs_pt.p, s->aux2.p, s->pts2.p, s->refine ? s->intr2.p : s->intr.p,
       s->img_cam.p, s->cam_model.p, s->pose_mask.p, s->pt_mask.p, loss_of(s->opt), nullptr, s->part_cost.p); MM_LAUNCH_CHECK();
   k_reduce_sum<<<1, 256, 0, st>>>(s->part_cost.p, s->grid_obs, s->red.p + 1); MM_LAUNCH_CHECK();
   return MM_OK;
@@ -455,11 +467,12 @@ int launch_scale(mm_ba_session* s) {
 // K2: reduced camera system at the current radius (+ gradient max-norm -> red[2])
 int launch_schur(mm_ba_session* s, bool with_coarse = true) {
   cudaStream_t st = s->stream;
-  MM_CUDA(cudaMemsetAsync(s->S.p, 0, sizeof(double) * 36 * (size_t)s->nblk, st));
   MM_CUDA(cudaMemsetAsync(s->red.p + 2, 0, sizeof(double), st));
   const LMDiag lm = lm_of(s);
-  k_schur_point<<<blocks_for(s->n_pt, 128), 128, 0, st>>>(s->n_pt, s->pt_start.p, s->obs_img.p, s->rec.p, s->scale_c.p, s->scale_p.p, lm,
-      s->pair_off.p, s->pair_blk.p, s->S.p, s->Vinv.p, s->gp.p, s->dp.p, s->red.p + 2, s->fail.p, s->spread); MM_LAUNCH_CHECK();
+  k_schur_point<<<blocks_for(s->n_pt, 128), 128, 0, st>>>(s->n_pt, s->pt_start.p, s->rec.p, s->scale_p.p, lm,
+      s->Vinv.p, s->gp.p, s->dp.p, s->red.p + 2, s->fail.p, s->pinfo.p); MM_LAUNCH_CHECK();
+  k_schur_blocks<<<blocks_for(s->nblk * 32, 128), 128, 0, st>>>(s->n_img, s->nblk, s->blk_a.p, s->blk_b.p, s->bp_start.p, s->bp_end.p, s->sp_lo.p, s->sp_hi.p,
+      s->sp_pt.p, s->rec.p, s->scale_c.p, s->pinfo.p, s->S.p); MM_LAUNCH_CHECK();
   k_schur_cam<<<blocks_for((int64_t)s->n_img * 32, 128), 128, 0, st>>>(s->n_img, s->cam_start.p, s->cam_perm.p, s->obs_pt.p, s->rec.p,
       s->scale_c.p, s->scale_p.p, s->Vinv.p, s->gp.p, lm, s->S.p, s->rhs.p, s->gc.p, s->dc.p, s->red.p + 2); MM_LAUNCH_CHECK();
   k_precond<<<blocks_for(s->n_img, 64), 64, 0, st>>>(s->n_img, s->S.p, s->Minv.p, s->fail.p); MM_LAUNCH_CHECK();
@@ -712,13 +725,13 @@ int mm_ba_session_create(const mm_ba_problem* P, const mm_ba_options* opt, void*
   A(s->poses, 6 * n_img); A(s->poses2, 6 * n_img); A(s->intr, MM_INTR_STRIDE * n_cam); A(s->pts, 3 * n_pt); A(s->pts2, 3 * n_pt);
   A(s->aux, AUX * n_img); A(s->aux2, AUX * n_img); A(s->rec, (size_t)REC * (size_t)std::max<int64_t>(P->n_obs, 1));
   A(s->pose_mask, 6 * n_img); A(s->pt_mask, n_pt); A(s->scale_c, 6 * n_img); A(s->scale_p, 3 * n_pt);
-  A(s->Vinv, 6 * n_pt); A(s->gp, 3 * n_pt); A(s->dp, 3 * n_pt); A(s->gc, 6 * n_img); A(s->dc, 6 * n_img); A(s->rhs, 6 * n_img);
+  A(s->Vinv, 6 * n_pt); A(s->pinfo, PINFO * n_pt); A(s->gp, 3 * n_pt); A(s->dp, 3 * n_pt); A(s->gc, 6 * n_img); A(s->dc, 6 * n_img); A(s->rhs, 6 * n_img);
   A(s->vx, 6 * n_img); A(s->vr, 6 * n_img); A(s->vz, 6 * n_img); A(s->vp0, 6 * n_img); A(s->vp1, 6 * n_img); A(s->vAp, 6 * n_img);
   A(s->pcg_sc, 16); A(s->pcg_ic, 4); A(s->red, 8); A(s->fail, 1); A(s->img_cam, n_img); A(s->cam_model, n_cam); A(s->Minv, 36 * n_img);
   s->grid_obs = grid_stride(std::max<int64_t>(P->n_obs, 1), 256);
   MM_CUDA(cudaFuncSetAttribute((const void*)k_residual_jacobian<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM));
   MM_CUDA(cudaFuncSetAttribute((const void*)k_residual_jacobian<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM));
-  MM_CUDA(cudaFuncSetAttribute((const void*)k_residual_jacobian<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM));
+  MM_CUDA(cudaFuncSetAttribute((const void*)k_residual_jacobian<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM_COST));
   s->grid_x = grid_stride(std::max<int64_t>(3 * (int64_t)P->n_pt, 1), 256);
   A(s->part_cost, (size_t)s->grid_obs); A(s->part_pt, 2 * (size_t)blocks_for(P->n_pt, 128)); A(s->part_cam, 2 * (size_t)blocks_for(6 * (int64_t)P->n_img, 128) + 2);
   A(s->part_x, (size_t)s->grid_x);
@@ -808,11 +821,23 @@ int mm_debug_spd_inverse(double* a, int32_t m) {
   MM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_spd_inverse, 256, 0));
   const int tiles = (m + 63) / 64;
   const int grid = std::max(1, std::min(std::max(1, per_sm) * num_sms(), std::max(tiles * tiles, (m + 255) / 256)));
+  DevBuf<unsigned long long> dbgb; unsigned long long* dbg = nullptr;
+  if (getenv("MM_GJ_DEBUG")) { MM_CUDA(dbgb.alloc(64)); MM_CUDA(cudaMemset(dbgb.p, 0, 64 * sizeof(unsigned long long))); dbg = dbgb.p; }
   int mm_ = m; double* Ap = A.p; double* Cp = Ck.p; double* Rp = Rk.p;
-  void* args[] = { &mm_, &Ap, &Cp, &Rp };
+  void* args[] = { &mm_, &Ap, &Cp, &Rp, &dbg };
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, nullptr);
   MM_CUDA(cudaLaunchCooperativeKernel((const void*)k_spd_inverse, dim3(grid), dim3(256), args, 0, nullptr));
+  cudaEventRecord(e1, nullptr);
   count_launch();
   MM_CUDA(cudaDeviceSynchronize());
+  if (dbg) {
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    unsigned long long h[64]; cudaMemcpy(h, dbg, sizeof h, cudaMemcpyDeviceToHost);
+    printf("spd_inverse m=%d grid=%d: %.3f ms\n", m, grid, ms);
+    for (int k = 1; k < 4 && 32 * k < m; ++k) printf("  step %d: pivot %llu panel %llu sync %llu tiles %llu sync %llu ns\n", k, h[6*k+1]-h[6*k], h[6*k+2]-h[6*k+1], h[6*k+3]-h[6*k+2], h[6*k+4]-h[6*k+3], h[6*k+5]-h[6*k+4]);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
   MM_CUDA(cudaMemcpy(a, A.p, sizeof(double) * (size_t)m * m, cudaMemcpyDeviceToHost));
   return MM_OK;
 }
@@ -857,7 +882,7 @@ int mm_ba_session_time_kernel(mm_ba_session* s, int32_t which, int32_t reps, dou
                   s->img_cam.p, s->cam_model.p, s->pose_mask.p, s->pt_mask.p, loss_of(s->opt), s->rec.p, s->part_cost.p); count_launch(); break;
       case 1: rc = launch_schur(s, false); break;
       case 4: rc = launch_coarse_setup(s); break;
-      case 2: k_residual_jacobian<false><<<s->grid_obs, 256, K1_SMEM, st>>>(s->n_obs, s->obs_xy.p, s->obs_img.p, s->obs_pt.p, s->aux.p, s->pts.p, s->intr.p,
+      case 2: k_residual_jacobian<false><<<s->grid_obs, 256, K1_SMEM_COST, st>>>(s->n_obs, s->obs_xy.p, s->obs_img.p, s->obs_pt.p, s->aux.p, s->pts.p, s->intr.p,
                   s->img_cam.p, s->cam_model.p, s->pose_mask.p, s->pt_mask.p, loss_of(s->opt), nullptr, s->part_cost.p); count_launch(); break;
       case 3: {
         MM_CUDA(cudaMemsetAsync(s->pcg_ic.p, 0, sizeof(int) * 4, st));

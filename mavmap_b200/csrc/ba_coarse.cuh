@@ -59,63 +59,69 @@ __global__ void k_coarse_ridge(int m, double* __restrict__ Ac) {
 }
 
 // In-place inverse of a symmetric positive definite m x m matrix (row-major) by blocked Gauss-Jordan, panel width 32.
-// Per panel:  (A) every CTA inverts the 32 x 32 pivot block in the registers of its first warp (lane = row, shuffles
-// broadcast the pivot row); the grid forms the scaled row panel Rk = inv * A[k,:] (with inv itself in the pivot columns) and
+// Per panel:  (A) every CTA inverts the 32 x 32 pivot block in shared memory (redundantly: cheaper than a barrier);
+// the grid forms the scaled row panel Rk = inv * A[k,:] (with inv itself in the pivot columns) and
 // copies the column panel Ck = A[:,k];  grid barrier;  (B) 64 x 64 tiles of A get  A -= Ck Rk  (pivot rows <- Rk, pivot
 // columns <- -Ck inv);  grid barrier.  2 m^3 flop, m/32 * 2 barriers.
 constexpr int GJ_NB = 32;
-__global__ void __launch_bounds__(256) k_spd_inverse(int m, double* __restrict__ A, double* __restrict__ Ck, double* __restrict__ Rk) {
+__global__ void __launch_bounds__(256, 2) k_spd_inverse(int m, double* __restrict__ A, double* __restrict__ Ck, double* __restrict__ Rk, unsigned long long* dbg) {
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
   __shared__ double s_inv[GJ_NB][GJ_NB + 1];
   __shared__ double s_c[64][GJ_NB + 1];
   __shared__ double s_r[GJ_NB][64 + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int gtid = blockIdx.x * blockDim.x + tid, gsize = gridDim.x * blockDim.x;
+  // warp-interleaved global thread index: consecutive warps of work land on different SMs
+  const int gtid = (warp * gridDim.x + blockIdx.x) * 32 + lane, gsize = gridDim.x * blockDim.x;
   const int nt = (m + 63) / 64;
+#define GJ_STAMP(k) do { if (dbg && blockIdx.x == 0 && tid == 0 && k0 < 8 * GJ_NB) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); dbg[6 * (k0 / GJ_NB) + (k)] = t_; } } while (0)
   for (int k0 = 0; k0 < m; k0 += GJ_NB) {
     const int kb = min(GJ_NB, m - k0);
-    if (warp == 0) {
-      double a[GJ_NB];
+    GJ_STAMP(0);
+    // pivot block -> shared memory (identity padding past the matrix edge), then 32 elimination steps with all threads
+    for (int idx = tid; idx < GJ_NB * GJ_NB; idx += 256) {
+      const int i = idx >> 5, j = idx & 31;
+      s_inv[i][j] = (i < kb && j < kb) ? __ldcg(A + (size_t)(k0 + i) * m + k0 + j) : (i == j ? 1.0 : 0.0);
+    }
+    for (int c = 0; c < GJ_NB; ++c) {
+      __syncthreads();
+      const double ip = 1.0 / s_inv[c][c];
+      double nv[4];
 #pragma unroll
-      for (int j = 0; j < GJ_NB; ++j) a[j] = (lane < kb && j < kb) ? __ldcg(A + (size_t)(k0 + lane) * m + k0 + j) : (lane == j ? 1.0 : 0.0);
-#pragma unroll
-      for (int c = 0; c < GJ_NB; ++c) {
-        const double ip = 1.0 / __shfl_sync(0xffffffffu, a[c], c);
-        const double f = a[c];
-#pragma unroll
-        for (int j = 0; j < GJ_NB; ++j) {
-          const double rcj = __shfl_sync(0xffffffffu, a[j], c) * ip;      // pivot row, scaled
-          if (j != c) a[j] = (lane == c) ? rcj : a[j] - f * rcj;
-        }
-        a[c] = (lane == c) ? ip : -f * ip;
+      for (int e = 0; e < 4; ++e) {
+        const int idx = tid + 256 * e, i = idx >> 5, j = idx & 31;
+        const double own = s_inv[i][j], f = s_inv[i][c], r = s_inv[c][j];
+        nv[e] = (i == c) ? (j == c ? ip : r * ip) : (j == c ? -f * ip : own - f * (r * ip));
       }
+      __syncthreads();
 #pragma unroll
-      for (int j = 0; j < GJ_NB; ++j) s_inv[lane][j] = a[j];
+      for (int e = 0; e < 4; ++e) { const int idx = tid + 256 * e; s_inv[idx >> 5][idx & 31] = nv[e]; }
     }
     __syncthreads();
-    // ---- (A) row panel and column panel
-    for (int j = gtid; j < m; j += gsize) {
+    GJ_STAMP(1);
+    // ---- (A) row panel (thread = column j x group of 4 panel rows) and column panel
+    for (int idx = gtid; idx < 8 * m; idx += gsize) {
+      const int cg8 = idx / m, j = idx - cg8 * m, c0 = 4 * cg8;
       if (j >= k0 && j < k0 + kb) {
-#pragma unroll 4
-        for (int c = 0; c < GJ_NB; ++c) Rk[(size_t)c * m + j] = s_inv[c][j - k0];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) Rk[(size_t)(c0 + c) * m + j] = s_inv[c0 + c][j - k0];
       } else {
-        double col[GJ_NB];
-#pragma unroll
-        for (int q = 0; q < GJ_NB; ++q) col[q] = q < kb ? __ldcg(A + (size_t)(k0 + q) * m + j) : 0.0;
-        for (int c = 0; c < GJ_NB; ++c) {
-          double s = 0.0;
-#pragma unroll
-          for (int q = 0; q < GJ_NB; ++q) s += s_inv[c][q] * col[q];
-          Rk[(size_t)c * m + j] = s;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 8
+        for (int q = 0; q < GJ_NB; ++q) {
+          const double v = q < kb ? __ldcg(A + (size_t)(k0 + q) * m + j) : 0.0;
+          s0 += s_inv[c0][q] * v; s1 += s_inv[c0 + 1][q] * v; s2 += s_inv[c0 + 2][q] * v; s3 += s_inv[c0 + 3][q] * v;
         }
+        Rk[(size_t)c0 * m + j] = s0; Rk[(size_t)(c0 + 1) * m + j] = s1; Rk[(size_t)(c0 + 2) * m + j] = s2; Rk[(size_t)(c0 + 3) * m + j] = s3;
       }
     }
     for (int64_t idx = gtid; idx < (int64_t)m * GJ_NB; idx += gsize) {
       const int i = (int)(idx >> 5), c = (int)(idx & 31);
       Ck[idx] = c < kb ? __ldcg(A + (size_t)i * m + k0 + c) : 0.0;
     }
+    GJ_STAMP(2);
     grid.sync();
+    GJ_STAMP(3);
     // ---- (B) rank-32 update of every tile
     for (int t = blockIdx.x; t < nt * nt; t += gridDim.x) {
       const int i0 = (t / nt) * 64, j0 = (t % nt) * 64;
@@ -123,11 +129,15 @@ __global__ void __launch_bounds__(256) k_spd_inverse(int m, double* __restrict__
       for (int idx = tid; idx < GJ_NB * 64; idx += 256) { const int c = idx >> 6, j = idx & 63; s_r[c][j] = (j0 + j < m) ? __ldcg(Rk + (size_t)c * m + j0 + j) : 0.0; }
       __syncthreads();
       const int tr = tid >> 4, tc = tid & 15;
-      double acc[4][4];
+      double acc[4][4], old[4][4];
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+        for (int b = 0; b < 4; ++b) {         // the tile's current values are in flight while the product is formed
+          const int i = i0 + tr + 16 * a, j = j0 + tc + 16 * b;
+          acc[a][b] = 0.0;
+          old[a][b] = (i < m && j < m) ? __ldcg(A + (size_t)i * m + j) : 0.0;
+        }
 #pragma unroll 8
       for (int c = 0; c < GJ_NB; ++c) {
         double ca[4], rb[4];
@@ -150,17 +160,19 @@ __global__ void __launch_bounds__(256) k_spd_inverse(int m, double* __restrict__
           const int j = j0 + tc + 16 * b;
           if (j >= m) continue;
           const bool pcol = j >= k0 && j < k0 + kb;
-          double* dst = A + (size_t)i * m + j;
           double v;
           if (prow) v = s_r[i - k0][tc + 16 * b];
-          else v = (pcol ? 0.0 : __ldcg(dst)) - acc[a][b];
-          __stcg(dst, v);
+          else v = (pcol ? 0.0 : old[a][b]) - acc[a][b];
+          __stcg(A + (size_t)i * m + j, v);
         }
       }
       __syncthreads();
     }
+    GJ_STAMP(4);
     grid.sync();
+    GJ_STAMP(5);
   }
+#undef GJ_STAMP
 }
 
 }  // namespace mm

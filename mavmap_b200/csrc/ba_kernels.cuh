@@ -61,6 +61,8 @@ constexpr int K1_SLOT = 26;                                   // doubles per ima
 constexpr int K1_PITCH = 22;                                  // doubles per staged record
 constexpr int K1_WARP_DOUBLES = 32 * K1_SLOT;                 // >= 32 * K1_PITCH
 constexpr size_t K1_SMEM = sizeof(double) * 8 * K1_WARP_DOUBLES + sizeof(int) * 8 * 32 + sizeof(double) * 32;
+constexpr size_t K1_SMEM_COST = K1_SMEM;
+
 
 template <bool WITH_J, bool WITH_JI = false>
 __global__ void __launch_bounds__(256, WITH_J ? 2 : 3) k_residual_jacobian(
@@ -178,6 +180,13 @@ __global__ void __launch_bounds__(256, WITH_J ? 2 : 3) k_residual_jacobian(
   if (threadIdx.x == 0) cost_part[blockIdx.x] = cost;
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
 // deterministic final reduction of per-block partials: out[0] = sum(part[0..n))
 __global__ void k_reduce_sum(const double* __restrict__ part, int n, double* __restrict__ out) {
   __shared__ double red[32];
@@ -222,9 +231,8 @@ __global__ void k_colnorm_cam(int n_img, const int* __restrict__ cam_start, cons
   }
 }
 
-// ---- K2a: per-point blocks and the off-diagonal Schur updates ----------------------------
-// thread per point: V' = s_p (sum Jp'Jp) s_p + D_p^2, inverse, g_p'; then for every pair (i<j) of its
-// observations S(img_i,img_j) -= Y_i W_j' with Y_i = W_i V'^-1, W = Jc' Jp (scaled).
+// ---- K2a: per-point blocks ------------------------------------------------------------------
+// thread per point (streams its records): V' = s_p (sum Jp'Jp) s_p + D_p^2, inverse, g_p'.
 struct LMDiag { double radius, min_diag, max_diag; };
 
 __device__ __forceinline__ bool sym3_inverse(const double* V /*xx xy xz yy yz zz*/, double* I) {
@@ -251,16 +259,11 @@ __device__ __forceinline__ void load_scaled(const double* __restrict__ rec, int6
 }
 
 __global__ void __launch_bounds__(128) k_schur_point(
-    int n_pt, const int* __restrict__ pt_start, const int* __restrict__ obs_img, const double* __restrict__ rec,
-    const double* __restrict__ scale_c, const double* __restrict__ scale_p, LMDiag lm,
-    const int64_t* __restrict__ pair_off, const int* __restrict__ pair_blk,
-    double* __restrict__ S, double* __restrict__ Vinv, double* __restrict__ gp_out, double* __restrict__ dp_out,
-    double* __restrict__ gmax, int* __restrict__ fail, unsigned long long spread) {
+    int n_pt, const int* __restrict__ pt_start, const double* __restrict__ rec, const double* __restrict__ scale_p, LMDiag lm,
+    double* __restrict__ Vinv, double* __restrict__ gp_out, double* __restrict__ dp_out, double* __restrict__ gmax, int* __restrict__ fail,
+    double* __restrict__ pinfo) {
   __shared__ double red[32];
-  // points are stored spatially clustered (good for the gathers elsewhere); here neighbouring threads take points that are
-  // far apart (multiplicative permutation, gcd(spread, n_pt) = 1) so that concurrent atomics hit different blocks of S
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int p = tid < n_pt ? (int)(((unsigned long long)tid * spread) % (unsigned long long)n_pt) : n_pt;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
   double gm = 0.0;
   if (p < n_pt) {
     const int o0 = pt_start[p], o1 = pt_start[p + 1];
@@ -283,65 +286,98 @@ __global__ void __launch_bounds__(128) k_schur_point(
     if (!sym3_inverse(V, I)) { *fail = 1; I[0] = I[3] = I[5] = 0; I[1] = I[2] = I[4] = 0; }
 #pragma unroll
     for (int k = 0; k < 6; ++k) Vinv[6 * (size_t)p + k] = I[k];
+    {     // the same data as one 80-byte record per point for the block pass (5 whole 16-byte chunks)
+      double2* pi = reinterpret_cast<double2*>(pinfo + 10 * (size_t)p);
+      pi[0] = make_double2(I[0], I[1]); pi[1] = make_double2(I[2], I[3]); pi[2] = make_double2(I[4], I[5]);
+      pi[3] = make_double2(sp[0], sp[1]); pi[4] = make_double2(sp[2], 0.0);
+    }
     gp_out[3 * (size_t)p] = g[0]; gp_out[3 * (size_t)p + 1] = g[1]; gp_out[3 * (size_t)p + 2] = g[2];
     dp_out[3 * (size_t)p] = d0; dp_out[3 * (size_t)p + 1] = d1; dp_out[3 * (size_t)p + 2] = d2;
     gm = fmax(fmax(fabs(g[0] / sp[0]), fabs(g[1] / sp[1])), fabs(g[2] / sp[2]));
-    if (o1 - o0 > 1) {
-      int64_t slot = pair_off[p];
-      for (int oi = o0; oi < o1 - 1; ++oi) {
-        const int ia = obs_img[oi];
-        double Jc[2][6], Jp[2][3];
-        load_scaled(rec, oi, scale_c + 6 * (size_t)ia, sp, Jc, Jp);
-        double Y[6][3];
-        bool nz = false;
-#pragma unroll
-        for (int a = 0; a < 6; ++a) {
-          const double w0 = Jc[0][a] * Jp[0][0] + Jc[1][a] * Jp[1][0];
-          const double w1 = Jc[0][a] * Jp[0][1] + Jc[1][a] * Jp[1][1];
-          const double w2 = Jc[0][a] * Jp[0][2] + Jc[1][a] * Jp[1][2];
-          Y[a][0] = w0 * I[0] + w1 * I[1] + w2 * I[2];
-          Y[a][1] = w0 * I[1] + w1 * I[3] + w2 * I[4];
-          Y[a][2] = w0 * I[2] + w1 * I[4] + w2 * I[5];
-          nz |= (w0 != 0.0) | (w1 != 0.0) | (w2 != 0.0);
-        }
-        for (int oj = oi + 1; oj < o1; ++oj, ++slot) {
-          if (!nz) continue;
-          const int ib = obs_img[oj];
-          double Kc[2][6], Kp[2][3];
-          load_scaled(rec, oj, scale_c + 6 * (size_t)ib, sp, Kc, Kp);
-          double* dst = S + 36 * (size_t)pair_blk[slot];
-          double T[6][2];
-#pragma unroll
-          for (int a = 0; a < 6; ++a) {
-            T[a][0] = Y[a][0] * Kp[0][0] + Y[a][1] * Kp[0][1] + Y[a][2] * Kp[0][2];
-            T[a][1] = Y[a][0] * Kp[1][0] + Y[a][1] * Kp[1][1] + Y[a][2] * Kp[1][2];
-          }
-          if (ia == ib) {
-            double Bm[6][6];
-#pragma unroll
-            for (int a = 0; a < 6; ++a)
-#pragma unroll
-              for (int c = 0; c < 6; ++c) Bm[a][c] = T[a][0] * Kc[0][c] + T[a][1] * Kc[1][c];
-#pragma unroll
-            for (int a = 0; a < 6; ++a)
-#pragma unroll
-              for (int c = 0; c < 6; ++c) { const double v = Bm[a][c] + Bm[c][a]; if (v != 0.0) atomicAdd(dst + 6 * a + c, -v); }
-          } else {
-            const bool fwd = ia < ib;
-#pragma unroll
-            for (int a = 0; a < 6; ++a)
-#pragma unroll
-              for (int c = 0; c < 6; ++c) {
-                const double v = T[a][0] * Kc[0][c] + T[a][1] * Kc[1][c];
-                if (v != 0.0) atomicAdd(dst + (fwd ? 6 * a + c : 6 * c + a), -v);
-              }
-          }
-        }
-      }
-    }
   }
   gm = block_max(gm, red);
   if (threadIdx.x == 0 && gm > 0.0) atomic_max_nonneg(gmax, gm);
+}
+
+// ---- K2a': the blocks of the reduced camera system, one warp per stored block, no atomics ----------------
+// Block (a, b), a <= b, is  - sum over the points p seen by both images of  Y_a W_b'  with  W = Jc' Jp (scaled),
+// Y_a = W_a V_p^-1.  The (observation in a, observation in b, point) triples of every block were listed at setup (sorted
+// by block, blocks in row-major order so that a row's records stay in L2).  Lanes take pairs round-robin with all of a
+// pair's loads in flight at once (two 144-byte Jacobian records, one 80-byte point record), accumulate the 6 x 6 product
+// in registers, and one shuffle reduction per block ends it: deterministic, no memset, no atomics.
+// (Tried and measured slower on B200, cfg4: staging the records through shared memory with cp.async so that consecutive
+// lanes read consecutive 16-byte chunks — single-buffered 2.1 ms, double-buffered 2.3 ms against 1.9 ms for this form:
+// the gather is L1-tag bound, the staged forms are latency bound at the occupancy their buffers allow.)
+// Diagonal blocks only receive the (rare) pairs of one point observed twice by the same image; K2b adds U - sum Y W'.
+constexpr int PINFO = 10;                // doubles per point record: V^-1 (6) | scale_p (3) | pad
+
+__global__ void __launch_bounds__(128, 3) k_schur_blocks(
+    int n_img, int64_t nblk, const int* __restrict__ blk_a, const int* __restrict__ blk_b,
+    const int* __restrict__ bp_start, const int* __restrict__ bp_end, const int* __restrict__ sp_lo, const int* __restrict__ sp_hi,
+    const int* __restrict__ sp_pt, const double* __restrict__ rec, const double* __restrict__ scale_c,
+    const double* __restrict__ pinfo, double* __restrict__ S) {
+  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= nblk) return;
+  const bool diag = b < n_img;
+  const int ia = diag ? (int)b : blk_a[b - n_img], ib = diag ? (int)b : blk_b[b - n_img];
+  const int q0 = bp_start[b], q1 = bp_end[b];
+  double acc[36];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) acc[k] = 0.0;
+  if (q1 > q0) {
+    double sa[6], sb[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { sa[k] = scale_c[6 * (size_t)ia + k]; sb[k] = scale_c[6 * (size_t)ib + k]; }
+    for (int q = q0 + lane; q < q1; q += 32) {
+      const int oi = sp_lo[q], oj = sp_hi[q], p = sp_pt[q];
+      double I[6], sp[3];
+      {
+        const double2* p2 = reinterpret_cast<const double2*>(pinfo + PINFO * (size_t)p);
+        const double2 v0 = p2[0], v1 = p2[1], v2 = p2[2], v3 = p2[3], v4 = p2[4];
+        I[0] = v0.x; I[1] = v0.y; I[2] = v1.x; I[3] = v1.y; I[4] = v2.x; I[5] = v2.y; sp[0] = v3.x; sp[1] = v3.y; sp[2] = v4.x;
+      }
+      double Jc[2][6], Jp[2][3], Kc[2][6], Kp[2][3];
+      load_scaled(rec, oi, sa, sp, Jc, Jp);
+      load_scaled(rec, oj, sb, sp, Kc, Kp);
+      double T[6][2];
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        const double w0 = Jc[0][a] * Jp[0][0] + Jc[1][a] * Jp[1][0];
+        const double w1 = Jc[0][a] * Jp[0][1] + Jc[1][a] * Jp[1][1];
+        const double w2 = Jc[0][a] * Jp[0][2] + Jc[1][a] * Jp[1][2];
+        const double y0 = w0 * I[0] + w1 * I[1] + w2 * I[2];
+        const double y1 = w0 * I[1] + w1 * I[3] + w2 * I[4];
+        const double y2 = w0 * I[2] + w1 * I[4] + w2 * I[5];
+        T[a][0] = y0 * Kp[0][0] + y1 * Kp[0][1] + y2 * Kp[0][2];
+        T[a][1] = y0 * Kp[1][0] + y1 * Kp[1][1] + y2 * Kp[1][2];
+      }
+      if (!diag) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+          for (int c = 0; c < 6; ++c) acc[6 * a + c] -= T[a][0] * Kc[0][c] + T[a][1] * Kc[1][c];
+      } else {
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+          for (int c = 0; c < 6; ++c) { const double v = T[a][0] * Kc[0][c] + T[a][1] * Kc[1][c]; acc[6 * a + c] -= v; acc[6 * c + a] -= v; }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 36; ++k) acc[k] = warp_sum(acc[k]);
+  }
+  double* dst = S + 36 * (size_t)b;
+  double mine = acc[0];
+#pragma unroll
+  for (int k = 1; k < 32; ++k) if (lane == k) mine = acc[k];
+  dst[lane] = mine;
+  if (lane < 4) {
+    double m2 = acc[32];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) if (lane == k) m2 = acc[32 + k];
+    dst[32 + lane] = m2;
+  }
 }
 
 // ---- K2b: per-image diagonal block, reduced right-hand side, gradient, LM diagonal ----------
