@@ -214,16 +214,22 @@ def main():
 
     # per-kernel timings on the resident state (live, CUDA events inside the library)
     k1_ms = sess.time_kernel(0, 20); k2_ms = sess.time_kernel(1, 10); k4_ms = sess.time_kernel(2, 20); spmv_ms = sess.time_kernel(3, 50)
+    coarse_dim = sess.coarse_dim()
+    coarse_ms = sess.time_kernel(4, 10) if coarse_dim else 0.0
     n_obs, n_pt, n_img = flat.n_obs, flat.n_pt, flat.n_img
     k1_bytes = 184.0 * n_obs + 48.0 * n_img + 24.0 * n_pt            # K1 algorithmic bytes
     k2_bytes = 168.0 * n_obs + 72.0 * n_pt + 216.0 * n_img + 288.0 * n_blocks
     k3_bytes = 288.0 * (2 * n_blocks - n_img) + 5 * 48.0 * n_img      # both triangles are read through the CSR
     pcg_iters = sum(summ["trace_linear_iterations"][W + 1:W + 1 + K])
     lin_ms = summ["ms"]
+    traffic = None                       # dram bytes per launch of K1 from the committed `ncu --set full` capture of this workload
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(name, {}).get("k_residual_jacobian<1,0>")
     roof_k1 = {"kernel": "k_residual_jacobian (K1)", "bound": "hbm", "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
-               "unit": "GB/s", "traffic": None, "ms": k1_ms, "peak_source": peaks["source"]}
+               "unit": "GB/s", "traffic": traffic, "ms": k1_ms, "peak_source": peaks["source"], "algorithmic_bytes": k1_bytes}
     roof_k1["frac"] = roof_k1["achieved"] / roof_k1["peak"]
-    roof_k2 = {"kernel": "k_schur_point + k_schur_cam (K2)", "bound": "hbm", "achieved": k2_bytes / (k2_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+    roof_k2 = {"kernel": "k_schur_point + k_schur_blocks + k_schur_cam (K2)", "bound": "hbm", "achieved": k2_bytes / (k2_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                "unit": "GB/s", "traffic": None, "ms": k2_ms}
     roof_k2["frac"] = roof_k2["achieved"] / roof_k2["peak"]
     roof_k3 = {"kernel": "k_pcg_spmv (K3, one PCG iteration's SpMV)", "bound": "hbm", "achieved": k3_bytes / (spmv_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
@@ -306,12 +312,14 @@ def main():
                 "config": {"workload": "%s: %d images, %d points, %d observations, PINHOLE fx=fy=1000, fixed intrinsics, Cauchy loss, image0 FIXED / image1 FIXED_X" % (name, n_img, n_pt, n_obs),
                            "parallelism": "replicas only (one independent BA per GPU)" if world > 1 else "single GPU",
                            "l2_policy": "inputs larger than L2: %.0f MB of Jacobian records + %.0f MB of observations per LM iteration" % (160.0 * n_obs / 1e6, 24.0 * n_obs / 1e6),
-                           "pcg_tolerance": 1e-13, "reduced_system_blocks": n_blocks},
+                           "pcg_tolerance": 1e-13, "reduced_system_blocks": n_blocks,
+                           "pcg_preconditioner": ("two-level: block-Jacobi + %d similarity-mode coarse unknowns" % coarse_dim) if coarse_dim else "block-Jacobi"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": dict(roof_k1, note="K1 is the kernel north_star names; share of the step is in `breakdown`"),
                 "roofline_other": [roof_k2, roof_k3],
                 "breakdown": {"ms_linearize_K1": lin_ms["linearize"], "ms_schur_K2": lin_ms["schur"], "ms_pcg_K3": lin_ms["pcg"], "ms_update_K4": lin_ms["update"],
                               "pcg_iterations_in_timed_steps": int(pcg_iters), "k1_ms": k1_ms, "k2_ms": k2_ms, "k4_cost_ms": k4_ms, "pcg_spmv_ms": spmv_ms,
+                              "coarse_setup_ms": coarse_ms, "ms_pcg_per_iteration": lin_ms["pcg"] / max(int(pcg_iters), 1),
                               "dominant_by_time": "K3 PCG" if lin_ms["pcg"] > max(lin_ms["schur"], lin_ms["linearize"]) else dominant["kernel"]},
                 "cpu_baseline": cpu, "secondary": secondary, "final_cost": summ["final_cost"]}
         print(json.dumps(line), flush=True)

@@ -239,6 +239,17 @@ int mm_ba_solve(mm_ba_problem* problem, const mm_ba_options* opt, mm_ba_summary*
 typedef struct mm_ba_session mm_ba_session;
 int  mm_ba_session_create(const mm_ba_problem* problem, const mm_ba_options* opt,
                           void* stream, mm_ba_session** out);
+/* Multi-GPU bundle adjustment: one process per GPU, every rank creates its session from the SAME full
+ * problem plus (rank, world).  The 3-D points - and with them the observations, the Jacobian records (160 B each, the
+ * large part of the footprint) and K1/K2/K4 - are partitioned across the ranks; poses, intrinsics and the reduced
+ * camera system are replicated.  `allreduce` must sum `count` doubles at device pointer `buf` over all ranks in place,
+ * ordered on `stream` (ncclAllReduce on that stream, or torch.distributed.all_reduce on a tensor that wraps the
+ * pointer); it is called once per Schur assembly (S | rhs | gradient | LM diagonal | scalars), once per step
+ * evaluation (4 doubles), once per solve for x, and at download.  Returns 0 on success. */
+typedef int (*mm_allreduce_fn)(void* user, double* buf, int64_t count, void* stream);
+int  mm_ba_session_create_sharded(const mm_ba_problem* problem, const mm_ba_options* opt, void* stream,
+                                  int32_t rank, int32_t world, mm_allreduce_fn allreduce, void* user,
+                                  mm_ba_session** out);
 /* Reset parameters to the values given at creation and restart the LM state. */
 int  mm_ba_session_reset(mm_ba_session* s);
 /* Run up to n LM iterations (each = linearize + Schur + PCG + candidate evaluation +

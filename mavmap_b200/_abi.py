@@ -98,6 +98,9 @@ class BASummary(C.Structure):
 
 
 # symbol -> (restype, argtypes) for every entry point include/mavmap_b200.h declares
+# int (*mm_allreduce_fn)(void* user, double* buf, int64_t count, void* stream)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
+
 PROTOTYPES = {
     "mm_abi_version": (C.c_int, []),
     "mm_last_error": (C.c_char_p, []),
@@ -130,6 +133,8 @@ PROTOTYPES = {
     "mm_ba_solve": (C.c_int, [C.POINTER(BAProblem), C.POINTER(BAOptions), C.POINTER(BASummary)]),
     "mm_ba_session_create": (C.c_int, [C.POINTER(BAProblem), C.POINTER(BAOptions), C.c_void_p,
                                        C.POINTER(C.c_void_p)]),
+    "mm_ba_session_create_sharded": (C.c_int, [C.POINTER(BAProblem), C.POINTER(BAOptions), C.c_void_p, C.c_int32, C.c_int32,
+                                               ALLREDUCE_FN, C.c_void_p, C.POINTER(C.c_void_p)]),
     "mm_ba_session_reset": (C.c_int, [C.c_void_p]),
     "mm_ba_session_iterate": (C.c_int, [C.c_void_p, C.c_int32, p_i32]),
     "mm_ba_session_download": (C.c_int, [C.c_void_p, p_f64, p_f64, p_f64, p_f64]),

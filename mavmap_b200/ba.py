@@ -341,14 +341,21 @@ def pose_refinement(rvec, tvec, camera_params, points2D, points3D, inlier_mask, 
 class BASession:
     """Resident BA session (inputs stay in HBM between calls) — what bench.py times."""
 
-    def __init__(self, flat, c_options, stream=0):
+    def __init__(self, flat, c_options, stream=0, rank=0, world=1, allreduce=None):
+        """rank/world/allreduce: multi-GPU session (points sharded across the ranks); `allreduce` is a callback made by
+        mavmap_b200.parallel.make_allreduce_callback and must stay alive as long as the session."""
         from ._lib import check, lib
         self._lib, self._check = lib(), check
         self.flat = flat
         self._cp = flat.to_c()
         self._h = C.c_void_p()
         self._opt = c_options
-        check(self._lib.mm_ba_session_create(C.byref(self._cp), C.byref(c_options), C.c_void_p(stream), C.byref(self._h)))
+        self._allreduce = allreduce
+        if world > 1:
+            check(self._lib.mm_ba_session_create_sharded(C.byref(self._cp), C.byref(c_options), C.c_void_p(stream), int(rank), int(world),
+                                                         allreduce, None, C.byref(self._h)))
+        else:
+            check(self._lib.mm_ba_session_create(C.byref(self._cp), C.byref(c_options), C.c_void_p(stream), C.byref(self._h)))
 
     def reset(self):
         self._check(self._lib.mm_ba_session_reset(self._h))

@@ -15,6 +15,41 @@
 
 namespace mm {
 
+// ------------------------------------------------------------------ multi-GPU shard ranges
+// both lists are sorted by point inside an image / a block (stable sorts of point-major data), so a rank's part is a
+// contiguous sub-range: found once at setup by bisection
+__global__ void k_shard_cam_ranges(int n_img, const int* __restrict__ cam_start, const int* __restrict__ cam_perm, int o_lo, int o_hi,
+                                   int* __restrict__ lo, int* __restrict__ hi) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_img) return;
+  const int b = cam_start[w], e = cam_start[w + 1];
+  int l = b, r = e;
+  while (l < r) { const int m = (l + r) >> 1; if (cam_perm[m] < o_lo) l = m + 1; else r = m; }
+  lo[w] = l; r = e;
+  while (l < r) { const int m = (l + r) >> 1; if (cam_perm[m] < o_hi) l = m + 1; else r = m; }
+  hi[w] = l;
+}
+__global__ void k_shard_blk_ranges(int64_t nblk, const int* __restrict__ bp_start, const int* __restrict__ bp_end, const int* __restrict__ sp_pt,
+                                   int p_lo, int p_hi, int* __restrict__ lo, int* __restrict__ hi) {
+  const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (b >= nblk) return;
+  int l = bp_start[b], r = bp_end[b]; const int e = r;
+  while (l < r) { const int m = (l + r) >> 1; if (sp_pt[m] < p_lo) l = m + 1; else r = m; }
+  lo[b] = l; r = e;
+  while (l < r) { const int m = (l + r) >> 1; if (sp_pt[m] < p_hi) l = m + 1; else r = m; }
+  hi[b] = l;
+}
+// scal[0] = local cost, scal[1] = local |x|^2, scal[2] = local failure flag (slots 3.. hold the per-rank gradient maxima)
+__global__ void k_pack_scal(const double* __restrict__ loc, const int* __restrict__ fail, double* __restrict__ scal) {
+  if (threadIdx.x == 0) { scal[0] = loc[0]; scal[1] = loc[5]; scal[2] = *fail ? 1.0 : 0.0; }
+}
+__global__ void k_pack_step(const double* __restrict__ loc, const int* __restrict__ fail, double* __restrict__ buf) {
+  if (threadIdx.x == 0) { buf[0] = loc[1]; buf[1] = loc[3]; buf[2] = loc[4]; buf[3] = *fail ? 1.0 : 0.0; }
+}
+__global__ void k_unpack_step(const double* __restrict__ buf, double* __restrict__ red, int* __restrict__ fail) {
+  if (threadIdx.x == 0) { red[1] = buf[0]; red[3] = buf[1]; red[4] = buf[2]; if (buf[3] > 0.0) *fail = 1; }
+}
+
 // ------------------------------------------------------------------ setup kernels
 __global__ void k_iota(int n, int* out) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = i; }
 __global__ void k_hist(int64_t n, const int* __restrict__ keys, int* __restrict__ cnt) {
@@ -129,6 +164,17 @@ struct mm_ba_session {
   DevBuf<double> vx, vr, vz, vp0, vp1, vAp, pcg_sc; DevBuf<int> pcg_ic;
   DevBuf<double> part_cost, part_pt, part_cam, part_x, red;   // red: [0]=cost [1]=new_cost [2]=gmax [3]=step_norm2 [4]=mcc [5]=xnorm2
   DevBuf<int> fail; DevBuf<unsigned long long> pcg_dbg;
+  // multi-GPU: the points [p_lo, p_hi) (internal order) and with them the observations [o_lo, o_hi) belong to this rank;
+  // poses, intrinsics and the reduced system are replicated; `ar` sums device doubles over the ranks (one exchange step
+  // per Schur assembly, one per step evaluation).  world == 1: everything is local and `ar` is never called.
+  int rank = 0, world = 1; mm_allreduce_fn ar = nullptr; void* ar_user = nullptr;
+  int p_lo = 0, p_hi = 0; int64_t o_lo = 0, o_hi = 0;
+  DevBuf<double> xch, loc, stepbuf, ud; size_t xch_count = 0, scal_off = 0;     // xch = [S | rhs | gc | ud | scal]: what the exchange step sums
+  DevBuf<int> cam_lo, cam_hi, bp_lo, bp_hi;                                      // this rank's part of every image's / block's list
+  int np_loc() const { return p_hi - p_lo; }
+  int64_t no_loc() const { return o_hi - o_lo; }
+  double* rec_base() const { return rec.p - (size_t)REC * (size_t)o_lo; }      // records are stored for the local observations only
+  double* scal() const { return xch.p + scal_off; }
   // coarse level of the two-level preconditioner (ba_coarse.cuh)
   int cm = 0, n_agg = 0; std::vector<int> h_agg; std::vector<double> h_pose_mask;
   DevBuf<int> blk_a, blk_b, agg; DevBuf<double> Pc, Ac, gjC, gjR, crc, cqc, cyc; int gj_grid = 0;
@@ -360,6 +406,28 @@ int build_aggregates(mm_ba_session* s) {
   return MM_OK;
 }
 
+// ---- multi-GPU: this rank's points / observations and its part of every per-image and per-block list -----------
+int build_shard(mm_ba_session* s) {
+  cudaStream_t st = s->stream;
+  const int n_pt = s->n_pt, n_img = s->n_img;
+  s->p_lo = (int)((int64_t)n_pt * s->rank / s->world); s->p_hi = (int)((int64_t)n_pt * (s->rank + 1) / s->world);
+  int o2[2] = {0, 0};
+  MM_CUDA(cudaMemcpy(&o2[0], s->pt_start.p + s->p_lo, sizeof(int), cudaMemcpyDeviceToHost));
+  MM_CUDA(cudaMemcpy(&o2[1], s->pt_start.p + s->p_hi, sizeof(int), cudaMemcpyDeviceToHost));
+  s->o_lo = o2[0]; s->o_hi = o2[1];
+  if (s->world == 1) {       // windows onto the full lists
+    s->cam_lo.view(s->cam_start.p, (size_t)n_img); s->cam_hi.view(s->cam_start.p + 1, (size_t)n_img);
+    s->bp_lo.view(s->bp_start.p, (size_t)s->nblk); s->bp_hi.view(s->bp_end.p, (size_t)s->nblk);
+    return MM_OK;
+  }
+  MM_CUDA(s->cam_lo.alloc((size_t)std::max(n_img, 1))); MM_CUDA(s->cam_hi.alloc((size_t)std::max(n_img, 1)));
+  MM_CUDA(s->bp_lo.alloc((size_t)std::max<int64_t>(s->nblk, 1))); MM_CUDA(s->bp_hi.alloc((size_t)std::max<int64_t>(s->nblk, 1)));
+  if (n_img > 0) { k_shard_cam_ranges<<<blocks_for(n_img, 128), 128, 0, st>>>(n_img, s->cam_start.p, s->cam_perm.p, (int)s->o_lo, (int)s->o_hi, s->cam_lo.p, s->cam_hi.p); MM_LAUNCH_CHECK(); }
+  if (s->nblk > 0) { k_shard_blk_ranges<<<blocks_for(s->nblk, 128), 128, 0, st>>>(s->nblk, s->bp_start.p, s->bp_end.p, s->sp_pt.p, s->p_lo, s->p_hi, s->bp_lo.p, s->bp_hi.p); MM_LAUNCH_CHECK(); }
+  MM_CUDA(cudaStreamSynchronize(st));
+  return MM_OK;
+}
+
 // prolongation blocks: the 7 similarity modes of each aggregate in the (scaled) pose parameters of its images.
 //   translation d:  d t = -R d          rotation a (about the world origin):  d w = -Jl^-1 R a, d t = 0
 //   scale about the aggregate centre c:  d t = -R (C - c),   C = -R' t the camera centre
@@ -423,6 +491,13 @@ int launch_coarse_setup(mm_ba_session* s) {
   return MM_OK;
 }
 
+int all_reduce(mm_ba_session* s, double* buf, size_t count) {
+  if (s->world <= 1) return MM_OK;
+  const int rc = s->ar(s->ar_user, buf, (int64_t)count, (void*)s->stream);
+  if (rc) { set_error("the all-reduce callback failed (%d)", rc); return MM_ERR_CUDA; }
+  return MM_OK;
+}
+
 LossParams loss_of(const mm_ba_options& o) {
   LossParams L; L.type = o.loss_type; L.b = o.loss_scale * o.loss_scale; L.c = 1.0 / L.b; return L;
 }
@@ -433,29 +508,35 @@ int launch_linearize(mm_ba_session* s) {
   cudaStream_t st = s->stream;
   k_pose_aux<<<blocks_for(s->n_img, 128), 128, 0, st>>>(s->n_img, s->poses.p, s->pose_mask.p, s->aux.p); MM_LAUNCH_CHECK();
   if (s->refine)
-    k_residual_jacobian<true, true><<<s->grid_obs, 256, K1_SMEM, st>>>(s->n_obs, s->obs_xy.p, s->obs_img.p, s->obs_pt.p, s->aux.p, s->pts.p, s->intr.p,
+    k_residual_jacobian<true, true><<<s->grid_obs, 256, K1_SMEM, st>>>(s->no_loc(), s->obs_xy.p + s->o_lo, s->obs_img.p + s->o_lo, s->obs_pt.p + s->o_lo, s->aux.p, s->pts.p, s->intr.p,
         s->img_cam.p, s->cam_model.p, s->pose_mask.p, s->pt_mask.p, loss_of(s->opt), s->rec.p, s->part_cost.p, s->ji.p, s->intr_mask.p);
   else
-    k_residual_jacobian<true><<<s->grid_obs, 256, K1_SMEM, st>>>(s->n_obs, s->obs_xy.p, s->obs_img.p, s->obs_pt.p, s->aux.p, s->pts.p, s->intr.p,
+    k_residual_jacobian<true><<<s->grid_obs, 256, K1_SMEM, st>>>(s->no_loc(), s->obs_xy.p + s->o_lo, s->obs_img.p + s->o_lo, s->obs_pt.p + s->o_lo, s->aux.p, s->pts.p, s->intr.p,
         s->img_cam.p, s->cam_model.p, s->pose_mask.p, s->pt_mask.p, loss_of(s->opt), s->rec.p, s->part_cost.p);
   MM_LAUNCH_CHECK();
-  k_reduce_sum<<<1, 256, 0, st>>>(s->part_cost.p, s->grid_obs, s->red.p + 0); MM_LAUNCH_CHECK();
+  k_reduce_sum<<<1, 256, 0, st>>>(s->part_cost.p, s->grid_obs, s->loc.p + 0); MM_LAUNCH_CHECK();
   return MM_OK;
 }
 // K4: cost at the candidate (poses2/pts2) -> red[1]
 int launch_cost_candidate(mm_ba_session* s) {
   cudaStream_t st = s->stream;
   k_pose_aux<<<blocks_for(s->n_img, 128), 128, 0, st>>>(s->n_img, s->poses2.p, s->pose_mask.p, s->aux2.p); MM_LAUNCH_CHECK();
-  k_residual_jacobian<false><<<s->grid_obs, 256, K1_SMEM_COST, st>>>(s->n_obs, s->obs_xy.p, s->obs_img.p, s->obs_pt.p, s->aux2.p, s->pts2.p, s->refine ? s->intr2.p : s->intr.p,
+  k_residual_jacobian<false><<<s->grid_obs, 256, K1_SMEM_COST, st>>>(s->no_loc(), s->obs_xy.p + s->o_lo, s->obs_img.p + s->o_lo, s->obs_pt.p + s->o_lo, s->aux2.p, s->pts2.p, s->refine ? s->intr2.p : s->intr.p,
       s->img_cam.p, s->cam_model.p, s->pose_mask.p, s->pt_mask.p, loss_of(s->opt), nullptr, s->part_cost.p); MM_LAUNCH_CHECK();
-  k_reduce_sum<<<1, 256, 0, st>>>(s->part_cost.p, s->grid_obs, s->red.p + 1); MM_LAUNCH_CHECK();
+  k_reduce_sum<<<1, 256, 0, st>>>(s->part_cost.p, s->grid_obs, s->loc.p + 1); MM_LAUNCH_CHECK();
+  // the step scalars (candidate cost, |step|^2, model cost change) summed over the ranks -> red[1], red[3], red[4]
+  k_pack_step<<<1, 32, 0, st>>>(s->loc.p, s->fail.p, s->stepbuf.p); MM_LAUNCH_CHECK();
+  { const int rc = all_reduce(s, s->stepbuf.p, 4); if (rc) return rc; }
+  k_unpack_step<<<1, 32, 0, st>>>(s->stepbuf.p, s->red.p, s->fail.p); MM_LAUNCH_CHECK();
   return MM_OK;
 }
 int launch_scale(mm_ba_session* s) {
   cudaStream_t st = s->stream;
   if (s->opt.jacobi_scaling) {
-    k_colnorm_point<<<blocks_for(s->n_pt, 128), 128, 0, st>>>(s->n_pt, s->pt_start.p, s->rec.p, s->scale_p.p); MM_LAUNCH_CHECK();
-    k_colnorm_cam<<<blocks_for((int64_t)s->n_img * 32, 128), 128, 0, st>>>(s->n_img, s->cam_start.p, s->cam_perm.p, s->rec.p, s->scale_c.p); MM_LAUNCH_CHECK();
+    k_colnorm_point<<<blocks_for(s->np_loc(), 128), 128, 0, st>>>(s->np_loc(), s->pt_start.p + s->p_lo, s->rec_base(), s->scale_p.p + 3 * (size_t)s->p_lo); MM_LAUNCH_CHECK();
+    k_colnorm_cam<<<blocks_for((int64_t)s->n_img * 32, 128), 128, 0, st>>>(s->n_img, s->cam_lo.p, s->cam_hi.p, s->cam_perm.p, s->rec_base(), s->ud.p); MM_LAUNCH_CHECK();
+    { const int rc = all_reduce(s, s->ud.p, 6 * (size_t)s->n_img); if (rc) return rc; }
+    k_scale_finish<<<blocks_for(6 * (int64_t)s->n_img, 256), 256, 0, st>>>(6 * s->n_img, s->ud.p, s->scale_c.p); MM_LAUNCH_CHECK();
     if (s->refine) {
       MM_CUDA(cudaMemsetAsync(s->sq9.p, 0, sizeof(double) * 9, st));
       k_colnorm_intr<<<s->grid_obs, 256, 0, st>>>(s->n_obs, s->ji.p, s->sq9.p); MM_LAUNCH_CHECK();
@@ -468,13 +549,20 @@ int launch_scale(mm_ba_session* s) {
 int launch_schur(mm_ba_session* s, bool with_coarse = true) {
   cudaStream_t st = s->stream;
   MM_CUDA(cudaMemsetAsync(s->red.p + 2, 0, sizeof(double), st));
+  MM_CUDA(cudaMemsetAsync(s->scal(), 0, sizeof(double) * (3 + (size_t)s->world), st));
   const LMDiag lm = lm_of(s);
-  k_schur_point<<<blocks_for(s->n_pt, 128), 128, 0, st>>>(s->n_pt, s->pt_start.p, s->rec.p, s->scale_p.p, lm,
-      s->Vinv.p, s->gp.p, s->dp.p, s->red.p + 2, s->fail.p, s->pinfo.p); MM_LAUNCH_CHECK();
-  k_schur_blocks<<<blocks_for(s->nblk * 32, 128), 128, 0, st>>>(s->n_img, s->nblk, s->blk_a.p, s->blk_b.p, s->bp_start.p, s->bp_end.p, s->sp_lo.p, s->sp_hi.p,
-      s->sp_pt.p, s->rec.p, s->scale_c.p, s->pinfo.p, s->S.p); MM_LAUNCH_CHECK();
-  k_schur_cam<<<blocks_for((int64_t)s->n_img * 32, 128), 128, 0, st>>>(s->n_img, s->cam_start.p, s->cam_perm.p, s->obs_pt.p, s->rec.p,
-      s->scale_c.p, s->scale_p.p, s->Vinv.p, s->gp.p, lm, s->S.p, s->rhs.p, s->gc.p, s->dc.p, s->red.p + 2); MM_LAUNCH_CHECK();
+  const int P0 = s->p_lo, NP = s->np_loc();
+  k_schur_point<<<blocks_for(NP, 128), 128, 0, st>>>(NP, s->pt_start.p + P0, s->rec_base(), s->scale_p.p + 3 * (size_t)P0, lm,
+      s->Vinv.p + 6 * (size_t)P0, s->gp.p + 3 * (size_t)P0, s->dp.p + 3 * (size_t)P0, s->scal() + 3 + s->rank, s->fail.p, s->pinfo.p + PINFO * (size_t)P0); MM_LAUNCH_CHECK();
+  k_schur_blocks<<<blocks_for(s->nblk * 32, 128), 128, 0, st>>>(s->n_img, s->nblk, s->blk_a.p, s->blk_b.p, s->bp_lo.p, s->bp_hi.p, s->sp_lo.p, s->sp_hi.p,
+      s->sp_pt.p, s->rec_base(), s->scale_c.p, s->pinfo.p, s->S.p); MM_LAUNCH_CHECK();
+  k_schur_cam<<<blocks_for((int64_t)s->n_img * 32, 128), 128, 0, st>>>(s->n_img, s->cam_lo.p, s->cam_hi.p, s->cam_perm.p, s->obs_pt.p, s->rec_base(),
+      s->scale_c.p, s->scale_p.p, s->Vinv.p, s->gp.p, s->S.p, s->rhs.p, s->gc.p, s->ud.p); MM_LAUNCH_CHECK();
+  // exchange step: S | rhs | gc | ud | scalars summed over the ranks (nothing to do on one GPU), then the LM diagonal
+  k_pack_scal<<<1, 32, 0, st>>>(s->loc.p, s->fail.p, s->scal()); MM_LAUNCH_CHECK();
+  { const int rc = all_reduce(s, s->xch.p, s->xch_count); if (rc) return rc; }
+  k_cam_finish<<<blocks_for(6 * (int64_t)s->n_img, 128), 128, 0, st>>>(6 * s->n_img, s->ud.p, s->gc.p, s->scale_c.p, lm, s->S.p, s->dc.p, s->scal(), s->world,
+      s->red.p, s->fail.p); MM_LAUNCH_CHECK();
   k_precond<<<blocks_for(s->n_img, 64), 64, 0, st>>>(s->n_img, s->S.p, s->Minv.p, s->fail.p); MM_LAUNCH_CHECK();
   if (with_coarse) { const int rc = launch_coarse_setup(s); if (rc) return rc; }
   if (s->refine) {
@@ -485,6 +573,13 @@ int launch_schur(mm_ba_session* s, bool with_coarse = true) {
     k_intr_finalize<<<1, 32, 0, st>>>(lm, s->scale_i.p, s->intr_acc.p, s->Cinv.p, s->gi.p, s->di.p, s->red.p + 2, s->fail.p); MM_LAUNCH_CHECK();
   }
   return MM_OK;
+}
+// every rank solved the same replicated system, but the dot products of the solve are accumulated with atomics whose
+// order differs from GPU to GPU: rank 0's solution is the one everybody continues with
+int pcg_broadcast(mm_ba_session* s) {
+  if (s->world <= 1) return MM_OK;
+  if (s->rank != 0) MM_CUDA(cudaMemsetAsync(s->vx.p, 0, sizeof(double) * 6 * (size_t)s->n_img, s->stream));
+  return all_reduce(s, s->vx.p, 6 * (size_t)s->n_img);
 }
 // K3: solve S y = rhs with the persistent cooperative kernel (no host sync; iteration count -> pcg_ic[1])
 int launch_pcg(mm_ba_session* s) {
@@ -538,28 +633,32 @@ int launch_pcg(mm_ba_session* s) {
     void* cargs[] = { &a, &e_cap };
     MM_CUDA(cudaLaunchCooperativeKernel(s->pcg_fn, dim3(s->pcg_grid), dim3(s->pcg_threads), cargs, s->pcg_smem, st));
     count_launch();
-    return MM_OK;
+    return pcg_broadcast(s);
   }
   void* args[] = { &a };
   MM_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg_persistent, dim3(s->pcg_grid), dim3(256), args, 0, st));
   count_launch();
-  return MM_OK;
+  return pcg_broadcast(s);
 }
 // K4: back-substitution, candidate parameters, step norm and model cost change -> red[3], red[4]
 int launch_update(mm_ba_session* s) {
   cudaStream_t st = s->stream;
-  const int gp_ = blocks_for(s->n_pt, 128), gc_ = blocks_for((int64_t)6 * s->n_img, 128);
-  k_backsub<<<gp_, 128, 0, st>>>(s->n_pt, s->pt_start.p, s->obs_img.p, s->rec.p, s->scale_c.p, s->scale_p.p, s->Vinv.p, s->gp.p, s->dp.p,
-      s->vx.p, s->pts.p, s->pts2.p, s->part_pt.p, s->refine ? s->Apc.p : nullptr, s->refine ? s->xi.p : nullptr); MM_LAUNCH_CHECK();
+  const int P0 = s->p_lo, NP = s->np_loc();
+  const int gp_ = blocks_for(NP, 128), gc_ = blocks_for((int64_t)6 * s->n_img, 128);
+  k_backsub<<<gp_, 128, 0, st>>>(NP, s->pt_start.p + P0, s->obs_img.p, s->rec_base(), s->scale_c.p, s->scale_p.p + 3 * (size_t)P0, s->Vinv.p + 6 * (size_t)P0,
+      s->gp.p + 3 * (size_t)P0, s->dp.p + 3 * (size_t)P0, s->vx.p, s->pts.p + 3 * (size_t)P0, s->pts2.p + 3 * (size_t)P0, s->part_pt.p,
+      s->refine ? s->Apc.p : nullptr, s->refine ? s->xi.p : nullptr); MM_LAUNCH_CHECK();
   k_update_cam<<<gc_, 128, 0, st>>>(6 * s->n_img, s->vx.p, s->scale_c.p, s->gc.p, s->dc.p, s->poses.p, s->poses2.p, s->part_cam.p); MM_LAUNCH_CHECK();
   if (s->refine) { k_update_intr<<<1, 32, 0, st>>>(s->xi.p, s->scale_i.p, s->gi.p, s->di.p, s->intr.p, s->intr2.p, s->part_cam.p + 2 * (size_t)gc_); MM_LAUNCH_CHECK(); }
-  k_reduce_pairs<<<1, 256, 0, st>>>(s->part_pt.p, gp_, s->part_cam.p, gc_ + (s->refine ? 1 : 0), s->red.p + 3); MM_LAUNCH_CHECK();
+  // the (replicated) camera part of |step|^2 and of the model cost change is counted on rank 0 only
+  k_reduce_pairs<<<1, 256, 0, st>>>(s->part_pt.p, gp_, s->part_cam.p, s->rank == 0 ? gc_ + (s->refine ? 1 : 0) : 0, s->loc.p + 3); MM_LAUNCH_CHECK();
   return MM_OK;
 }
 int launch_xnorm(mm_ba_session* s) {
   cudaStream_t st = s->stream;
-  k_xnorm<<<s->grid_x, 256, 0, st>>>(6 * s->n_img, s->poses.p, s->pose_mask.p, s->n_pt, s->pts.p, s->pt_mask.p, s->part_x.p, s->refine ? s->intr.p : nullptr, s->intr_mask.p); MM_LAUNCH_CHECK();
-  k_reduce_sum<<<1, 256, 0, st>>>(s->part_x.p, s->grid_x, s->red.p + 5); MM_LAUNCH_CHECK();
+  k_xnorm<<<s->grid_x, 256, 0, st>>>(s->rank == 0 ? 6 * s->n_img : 0, s->poses.p, s->pose_mask.p, s->np_loc(), s->pts.p + 3 * (size_t)s->p_lo, s->pt_mask.p + s->p_lo, s->part_x.p,
+      s->refine ? s->intr.p : nullptr, s->intr_mask.p); MM_LAUNCH_CHECK();
+  k_reduce_sum<<<1, 256, 0, st>>>(s->part_x.p, s->grid_x, s->loc.p + 5); MM_LAUNCH_CHECK();
   return MM_OK;
 }
 int read_red(mm_ba_session* s, double* out8) {
@@ -589,8 +688,8 @@ int lm_start(mm_ba_session* s) {
     k_fill<<<grid_stride(3 * (int64_t)s->n_pt, 256), 256, 0, s->stream>>>(3 * (int64_t)s->n_pt, s->scale_p.p, 1.0); MM_LAUNCH_CHECK();
     if ((rc = launch_scale(s))) return rc; }
   if ((rc = build_coarse_basis(s))) return rc;
+  if ((rc = launch_xnorm(s))) return rc;                     // before the Schur pass: its exchange step carries cost and |x|^2
   { Timer t(s, &S.ms_schur); if ((rc = launch_schur(s))) return rc; }
-  if ((rc = launch_xnorm(s))) return rc;
   double red[8]; if ((rc = read_red(s, red))) return rc;
   s->cost = red[0]; s->gmax = red[2]; s->x_norm = sqrt(red[5]);
   S.initial_cost = s->cost;
@@ -647,10 +746,10 @@ int lm_iterate(mm_ba_session* s) {
     std::swap(s->poses.p, s->poses2.p); std::swap(s->pts.p, s->pts2.p); std::swap(s->aux.p, s->aux2.p); if (s->refine) std::swap(s->intr.p, s->intr2.p);
     cudaEventRecord(s->evs[3], s->stream);
     if ((rc = launch_linearize(s))) return rc;
+    if ((rc = launch_xnorm(s))) return rc;
     cudaEventRecord(s->evs[4], s->stream);
     if ((rc = launch_schur(s))) return rc;
     cudaEventRecord(s->evs[5], s->stream);
-    if ((rc = launch_xnorm(s))) return rc;
     if ((rc = read_red(s, red))) return rc;
     { float ms = 0; cudaEventElapsedTime(&ms, s->evs[3], s->evs[4]); S.ms_linearize += ms; cudaEventElapsedTime(&ms, s->evs[4], s->evs[5]); S.ms_schur += ms; }
     s->cost = red[0]; s->gmax = red[2]; s->x_norm = sqrt(red[5]);
@@ -699,8 +798,14 @@ void mm_ba_session_destroy(mm_ba_session* s) {
 }
 
 int mm_ba_session_create(const mm_ba_problem* P, const mm_ba_options* opt, void* stream, mm_ba_session** out) {
+  return mm_ba_session_create_sharded(P, opt, stream, 0, 1, nullptr, nullptr, out);
+}
+
+int mm_ba_session_create_sharded(const mm_ba_problem* P, const mm_ba_options* opt, void* stream, int32_t rank, int32_t world,
+                                 mm_allreduce_fn allreduce, void* user, mm_ba_session** out) {
   if (!out || !opt) { set_error("null argument"); return MM_ERR_INVALID_ARG; }
   *out = nullptr;
+  if (world < 1 || rank < 0 || rank >= world || (world > 1 && !allreduce)) { set_error("invalid shard (rank %d of %d) or missing all-reduce callback", rank, world); return MM_ERR_INVALID_ARG; }
   int rc = validate_problem(P); if (rc) return rc;
   if (opt->linear_solver != MM_SOLVER_PCG) { set_error("the device engine solves the reduced system with PCG only"); return MM_ERR_UNSUPPORTED; }
   bool refine = false;
@@ -709,10 +814,12 @@ int mm_ba_session_create(const mm_ba_problem* P, const mm_ba_options* opt, void*
     if (used) refine = true;
   }
   if (refine && P->n_cam != 1) { set_error("refine_camera_params on the device engine handles one shared camera (got %d)", P->n_cam); return MM_ERR_UNSUPPORTED; }
+  if (refine && world > 1) { set_error("refine_camera_params is not available with a sharded session"); return MM_ERR_UNSUPPORTED; }
   rc = ensure_device(); if (rc) return rc;
   mm_ba_session* s = new mm_ba_session();
   s->stream = (cudaStream_t)stream; s->opt = *opt;
   s->n_img = P->n_img; s->n_cam = P->n_cam; s->n_pt = P->n_pt; s->n_obs = P->n_obs; s->refine = refine;
+  s->rank = rank; s->world = world; s->ar = allreduce; s->ar_user = user;
   auto fail_out = [&](int code) { mm_ba_session_destroy(s); return code; };
   if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) { set_error("cudaEventCreate failed"); return fail_out(MM_ERR_CUDA); }
   for (int i = 0; i < 8; ++i) if (cudaEventCreate(&s->evs[i]) != cudaSuccess) { set_error("cudaEventCreate failed"); return fail_out(MM_ERR_CUDA); }
@@ -723,21 +830,21 @@ int mm_ba_session_create(const mm_ba_problem* P, const mm_ba_options* opt, void*
   const size_t n_img = (size_t)std::max(P->n_img, 1), n_pt = (size_t)std::max(P->n_pt, 1), n_cam = (size_t)std::max(P->n_cam, 1);
 #define A(buf, count) do { if ((buf).alloc(count) != cudaSuccess) { set_error("cudaMalloc failed for " #buf); cudaGetLastError(); return fail_out(MM_ERR_ALLOC); } } while (0)
   A(s->poses, 6 * n_img); A(s->poses2, 6 * n_img); A(s->intr, MM_INTR_STRIDE * n_cam); A(s->pts, 3 * n_pt); A(s->pts2, 3 * n_pt);
-  A(s->aux, AUX * n_img); A(s->aux2, AUX * n_img); A(s->rec, (size_t)REC * (size_t)std::max<int64_t>(P->n_obs, 1));
+  A(s->aux, AUX * n_img); A(s->aux2, AUX * n_img);
   A(s->pose_mask, 6 * n_img); A(s->pt_mask, n_pt); A(s->scale_c, 6 * n_img); A(s->scale_p, 3 * n_pt);
-  A(s->Vinv, 6 * n_pt); A(s->pinfo, PINFO * n_pt); A(s->gp, 3 * n_pt); A(s->dp, 3 * n_pt); A(s->gc, 6 * n_img); A(s->dc, 6 * n_img); A(s->rhs, 6 * n_img);
+  A(s->Vinv, 6 * n_pt); A(s->pinfo, PINFO * n_pt); A(s->gp, 3 * n_pt); A(s->dp, 3 * n_pt); A(s->dc, 6 * n_img);
+  A(s->loc, 8); A(s->stepbuf, 8);
   A(s->vx, 6 * n_img); A(s->vr, 6 * n_img); A(s->vz, 6 * n_img); A(s->vp0, 6 * n_img); A(s->vp1, 6 * n_img); A(s->vAp, 6 * n_img);
   A(s->pcg_sc, 16); A(s->pcg_ic, 4); A(s->red, 8); A(s->fail, 1); A(s->img_cam, n_img); A(s->cam_model, n_cam); A(s->Minv, 36 * n_img);
-  s->grid_obs = grid_stride(std::max<int64_t>(P->n_obs, 1), 256);
   MM_CUDA(cudaFuncSetAttribute((const void*)k_residual_jacobian<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM));
   MM_CUDA(cudaFuncSetAttribute((const void*)k_residual_jacobian<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM));
   MM_CUDA(cudaFuncSetAttribute((const void*)k_residual_jacobian<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM_COST));
   s->grid_x = grid_stride(std::max<int64_t>(3 * (int64_t)P->n_pt, 1), 256);
-  A(s->part_cost, (size_t)s->grid_obs); A(s->part_pt, 2 * (size_t)blocks_for(P->n_pt, 128)); A(s->part_cam, 2 * (size_t)blocks_for(6 * (int64_t)P->n_img, 128) + 2);
+  A(s->part_cost, (size_t)grid_stride(std::max<int64_t>(P->n_obs, 1), 256)); A(s->part_pt, 2 * (size_t)blocks_for(P->n_pt, 128)); A(s->part_cam, 2 * (size_t)blocks_for(6 * (int64_t)P->n_img, 128) + 2);
   A(s->part_x, (size_t)s->grid_x);
   A(s->intr2, MM_INTR_STRIDE * n_cam); A(s->intr_mask, 9); A(s->scale_i, 9);
   if (refine) {
-    A(s->ji, 18 * (size_t)std::max<int64_t>(P->n_obs, 1)); A(s->Apc, 27 * n_pt); A(s->Bm, 54 * n_img); A(s->intr_acc, 108); A(s->Cinv, 81);
+    A(s->Apc, 27 * n_pt); A(s->Bm, 54 * n_img); A(s->intr_acc, 108); A(s->Cinv, 81);
     A(s->gi, 9); A(s->di, 9); A(s->xi, 9); A(s->zi, 9); A(s->pi0, 9); A(s->pi1, 9); A(s->bt, 18); A(s->sq9, 9);
   }
   { double im[9]; for (int k = 0; k < 9; ++k) im[k] = (refine && k < model_num_params(P->cam_model[0])) ? 1.0 : 0.0;
@@ -758,8 +865,19 @@ int mm_ba_session_create(const mm_ba_problem* P, const mm_ba_options* opt, void*
         cudaMemcpy(s->cam_model.p, P->cam_model, sizeof(int) * (size_t)P->n_cam, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("mask upload failed"); return fail_out(MM_ERR_CUDA); } }
   cudaMemsetAsync(s->fail.p, 0, sizeof(int), s->stream);
   cudaMemsetAsync(s->red.p, 0, sizeof(double) * 8, s->stream);
+  cudaMemsetAsync(s->loc.p, 0, sizeof(double) * 8, s->stream);
   rc = build_structure(s, P); if (rc) return fail_out(rc);
   rc = build_aggregates(s); if (rc) return fail_out(rc);
+  rc = build_shard(s); if (rc) return fail_out(rc);
+  A(s->rec, (size_t)REC * (size_t)std::max<int64_t>(s->no_loc(), 1));
+  if (refine) A(s->ji, 18 * (size_t)std::max<int64_t>(P->n_obs, 1));
+  s->grid_obs = grid_stride(std::max<int64_t>(s->no_loc(), 1), 256);
+  { // the exchange buffer: S | rhs | gc | ud | scalars, contiguous so that one all-reduce moves it
+    const size_t nS = 36 * (size_t)std::max<int64_t>(s->nblk, 1), nv = 6 * n_img;
+    s->scal_off = nS + 3 * nv; s->xch_count = s->scal_off + 3 + (size_t)world;
+    A(s->xch, s->xch_count);
+    s->S.view(s->xch.p, nS); s->rhs.view(s->xch.p + nS, nv); s->gc.view(s->xch.p + nS + nv, nv); s->ud.view(s->xch.p + nS + 2 * nv, nv);
+    cudaMemsetAsync(s->xch.p, 0, sizeof(double) * s->xch_count, s->stream); }
   { // multiplier of the K2a point permutation: a prime near 0.38 * n_pt that does not divide n_pt
     const unsigned long long primes[] = { 1000003ULL, 611953ULL, 382003ULL, 100003ULL, 38183ULL, 10007ULL, 3821ULL, 1009ULL, 383ULL, 101ULL, 37ULL, 7ULL, 1ULL };
     s->spread = 1;
@@ -767,7 +885,6 @@ int mm_ba_session_create(const mm_ba_problem* P, const mm_ba_options* opt, void*
   { std::vector<double> tmp((size_t)std::max(P->n_pt, 1), 0.0);
     for (int p = 0; p < P->n_pt; ++p) tmp[p] = s->h_pt_mask[(size_t)s->h_pt_new2old[p]];
     if (cudaMemcpy(s->pt_mask.p, tmp.data(), sizeof(double) * tmp.size(), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("mask upload failed"); return fail_out(MM_ERR_CUDA); } }
-  A(s->S, 36 * (size_t)std::max<int64_t>(s->nblk, 1));
 #undef A
   rc = upload_params(s); if (rc) return fail_out(rc);
   memset(&s->sum, 0, sizeof s->sum);
@@ -847,6 +964,11 @@ int mm_ba_session_download(mm_ba_session* s, double* poses, double* intr, double
   cudaStream_t st = s->stream;
   if (poses) MM_CUDA(cudaMemcpyAsync(poses, s->poses.p, sizeof(double) * 6 * (size_t)s->n_img, cudaMemcpyDeviceToHost, st));
   if (intr) MM_CUDA(cudaMemcpyAsync(intr, s->intr.p, sizeof(double) * MM_INTR_STRIDE * (size_t)s->n_cam, cudaMemcpyDeviceToHost, st));
+  if (s->world > 1 && s->n_pt > 0 && (pts || pt_err)) {      // every rank holds current values of its own points only
+    if (s->p_lo > 0) MM_CUDA(cudaMemsetAsync(s->pts.p, 0, sizeof(double) * 3 * (size_t)s->p_lo, st));
+    if (s->p_hi < s->n_pt) MM_CUDA(cudaMemsetAsync(s->pts.p + 3 * (size_t)s->p_hi, 0, sizeof(double) * 3 * (size_t)(s->n_pt - s->p_hi), st));
+    int rc = all_reduce(s, s->pts.p, 3 * (size_t)s->n_pt); if (rc) return rc;
+  }
   if (pts && s->n_pt > 0) {
     std::vector<double> tmp(3 * (size_t)s->n_pt);
     MM_CUDA(cudaMemcpyAsync(tmp.data(), s->pts.p, sizeof(double) * 3 * (size_t)s->n_pt, cudaMemcpyDeviceToHost, st));
@@ -860,7 +982,7 @@ int mm_ba_session_download(mm_ba_session* s, double* poses, double* intr, double
     MM_CUDA(cudaMemcpyAsync(s->Vinv.p, host.data(), sizeof(double) * (size_t)s->n_pt, cudaMemcpyHostToDevice, st));
     k_pose_aux<<<blocks_for(s->n_img, 128), 128, 0, st>>>(s->n_img, s->poses.p, s->pose_mask.p, s->aux.p); MM_LAUNCH_CHECK();
     k_point_errors<<<blocks_for(s->n_pt, 128), 128, 0, st>>>(s->n_pt, s->pt_start.p, s->obs_xy.p, s->obs_img.p, s->aux.p, s->pts.p, s->intr.p,
-        s->img_cam.p, s->cam_model.p, s->Vinv.p); MM_LAUNCH_CHECK();
+        s->img_cam.p, s->cam_model.p, s->Vinv.p); MM_LAUNCH_CHECK();     // (all points are current on every rank after the gather above)
     MM_CUDA(cudaMemcpyAsync(host.data(), s->Vinv.p, sizeof(double) * (size_t)s->n_pt, cudaMemcpyDeviceToHost, st));
     MM_CUDA(cudaStreamSynchronize(st));
     for (int p = 0; p < s->n_pt; ++p) pt_err[(size_t)s->h_pt_new2old[p]] = host[p];
@@ -878,11 +1000,11 @@ int mm_ba_session_time_kernel(mm_ba_session* s, int32_t which, int32_t reps, dou
   for (int r = -1; r < reps; ++r) {
     if (r == 0) MM_CUDA(cudaEventRecord(s->ev0, st));
     switch (which) {
-      case 0: k_residual_jacobian<true><<<s->grid_obs, 256, K1_SMEM, st>>>(s->n_obs, s->obs_xy.p, s->obs_img.p, s->obs_pt.p, s->aux.p, s->pts.p, s->intr.p,
+      case 0: k_residual_jacobian<true><<<s->grid_obs, 256, K1_SMEM, st>>>(s->no_loc(), s->obs_xy.p + s->o_lo, s->obs_img.p + s->o_lo, s->obs_pt.p + s->o_lo, s->aux.p, s->pts.p, s->intr.p,
                   s->img_cam.p, s->cam_model.p, s->pose_mask.p, s->pt_mask.p, loss_of(s->opt), s->rec.p, s->part_cost.p); count_launch(); break;
       case 1: rc = launch_schur(s, false); break;
       case 4: rc = launch_coarse_setup(s); break;
-      case 2: k_residual_jacobian<false><<<s->grid_obs, 256, K1_SMEM_COST, st>>>(s->n_obs, s->obs_xy.p, s->obs_img.p, s->obs_pt.p, s->aux.p, s->pts.p, s->intr.p,
+      case 2: k_residual_jacobian<false><<<s->grid_obs, 256, K1_SMEM_COST, st>>>(s->no_loc(), s->obs_xy.p + s->o_lo, s->obs_img.p + s->o_lo, s->obs_pt.p + s->o_lo, s->aux.p, s->pts.p, s->intr.p,
                   s->img_cam.p, s->cam_model.p, s->pose_mask.p, s->pt_mask.p, loss_of(s->opt), nullptr, s->part_cost.p); count_launch(); break;
       case 3: {
         MM_CUDA(cudaMemsetAsync(s->pcg_ic.p, 0, sizeof(int) * 4, st));

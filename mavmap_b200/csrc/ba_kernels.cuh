@@ -210,13 +210,14 @@ __global__ void k_colnorm_point(int n_pt, const int* __restrict__ pt_start, cons
   scale_p[3 * (size_t)p + 2] = 1.0 / (1.0 + sqrt(s2));
 }
 
-// one warp per image
-__global__ void k_colnorm_cam(int n_img, const int* __restrict__ cam_start, const int* __restrict__ cam_perm,
-                              const double* __restrict__ rec, double* __restrict__ scale_c) {
+// one warp per image over [cam_lo[w], cam_hi[w]) of the camera-sorted permutation (the whole image, or this rank's part
+// of it when the points are sharded): raw column sums of squares; k_scale_finish turns them into 1/(1+norm)
+__global__ void k_colnorm_cam(int n_img, const int* __restrict__ cam_lo, const int* __restrict__ cam_hi, const int* __restrict__ cam_perm,
+                              const double* __restrict__ rec, double* __restrict__ sums) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= n_img) return;
   double s[6] = {0, 0, 0, 0, 0, 0};
-  for (int q = cam_start[w] + lane; q < cam_start[w + 1]; q += 32) {
+  for (int q = cam_lo[w] + lane; q < cam_hi[w]; q += 32) {
     const double* r = rec + REC * (size_t)cam_perm[q] + 2;
 #pragma unroll
     for (int k = 0; k < 6; ++k) s[k] += r[k] * r[k] + r[6 + k] * r[6 + k];
@@ -227,8 +228,12 @@ __global__ void k_colnorm_cam(int n_img, const int* __restrict__ cam_start, cons
     double v = s[0];
 #pragma unroll
     for (int k = 1; k < 6; ++k) if (lane == k) v = s[k];
-    scale_c[6 * (size_t)w + lane] = 1.0 / (1.0 + sqrt(v));
+    sums[6 * (size_t)w + lane] = v;
   }
+}
+__global__ void k_scale_finish(int n, const double* __restrict__ sums, double* __restrict__ scale_c) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) scale_c[i] = 1.0 / (1.0 + sqrt(sums[i]));
 }
 
 // ---- K2a: per-point blocks ------------------------------------------------------------------
@@ -383,11 +388,10 @@ __global__ void __launch_bounds__(128, 3) k_schur_blocks(
 // ---- K2b: per-image diagonal block, reduced right-hand side, gradient, LM diagonal ----------
 // one warp per image over its observations (camera-sorted permutation, 160 B record gathers).
 __global__ void __launch_bounds__(128) k_schur_cam(
-    int n_img, const int* __restrict__ cam_start, const int* __restrict__ cam_perm, const int* __restrict__ obs_pt,
+    int n_img, const int* __restrict__ cam_lo, const int* __restrict__ cam_hi, const int* __restrict__ cam_perm, const int* __restrict__ obs_pt,
     const double* __restrict__ rec, const double* __restrict__ scale_c, const double* __restrict__ scale_p,
-    const double* __restrict__ Vinv, const double* __restrict__ gp, LMDiag lm,
-    double* __restrict__ S, double* __restrict__ rhs, double* __restrict__ gc_out, double* __restrict__ dc_out,
-    double* __restrict__ gmax) {
+    const double* __restrict__ Vinv, const double* __restrict__ gp,
+    double* __restrict__ S, double* __restrict__ rhs, double* __restrict__ gc_out, double* __restrict__ ud_out) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= n_img) return;
   double sc[6];
@@ -398,7 +402,7 @@ __global__ void __launch_bounds__(128) k_schur_cam(
   for (int k = 0; k < 21; ++k) Q[k] = 0.0;
 #pragma unroll
   for (int k = 0; k < 6; ++k) { h[k] = 0.0; gc[k] = 0.0; ud[k] = 0.0; }
-  for (int q = cam_start[w] + lane; q < cam_start[w + 1]; q += 32) {
+  for (int q = cam_lo[w] + lane; q < cam_hi[w]; q += 32) {
     const int o = cam_perm[q];
     const int p = obs_pt[o];
     const double sp[3] = { scale_p[3 * (size_t)p], scale_p[3 * (size_t)p + 1], scale_p[3 * (size_t)p + 2] };
@@ -437,23 +441,44 @@ __global__ void __launch_bounds__(128) k_schur_cam(
   for (int k = 0; k < 6; ++k) { h[k] = warp_sum(h[k]); gc[k] = warp_sum(gc[k]); ud[k] = warp_sum(ud[k]); }
   if (lane == 0) {
     double* dst = S + 36 * (size_t)w;      // diagonal block id == image index
-    double gm = 0.0;
     int k = 0;
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
-      const double d = fmin(fmax(ud[a], lm.min_diag), lm.max_diag) / lm.radius;
-      dc_out[6 * (size_t)w + a] = d;
+      ud_out[6 * (size_t)w + a] = ud[a];
       gc_out[6 * (size_t)w + a] = gc[a];
       rhs[6 * (size_t)w + a] = h[a];
-      gm = fmax(gm, fabs(gc[a] / sc[a]));
 #pragma unroll
       for (int c = a; c < 6; ++c, ++k) {
-        if (c == a) dst[6 * a + a] += Q[k] + d;
+        if (c == a) dst[6 * a + a] += Q[k];
         else { dst[6 * a + c] += Q[k]; dst[6 * c + a] += Q[k]; }
       }
     }
-    if (gm > 0.0) atomic_max_nonneg(gmax, gm);
   }
+}
+
+// after the camera pass (and, when the points are sharded across GPUs, after the all-reduce of S | rhs | gc | ud | scal):
+// LM diagonal of every pose parameter onto the diagonal blocks, gradient max-norm, and the reduced scalars.
+// scal: [0] cost  [1] |x|^2  [2] failure count  [3 .. 3 + world) per-rank max |g_point|
+__global__ void k_cam_finish(int n6, const double* __restrict__ ud, const double* __restrict__ gc, const double* __restrict__ scale_c, LMDiag lm,
+                             double* __restrict__ S, double* __restrict__ dc_out, const double* __restrict__ scal, int world,
+                             double* __restrict__ red, int* __restrict__ fail) {
+  __shared__ double sred[32];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double gm = 0.0;
+  if (i < n6) {
+    const int img = i / 6, a = i - 6 * img;
+    const double d = fmin(fmax(ud[i], lm.min_diag), lm.max_diag) / lm.radius;
+    dc_out[i] = d;
+    S[36 * (size_t)img + 7 * a] += d;
+    gm = fabs(gc[i] / scale_c[i]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (int r = 0; r < world; ++r) gm = fmax(gm, scal[3 + r]);
+    red[0] = scal[0]; red[5] = scal[1];
+    if (scal[2] > 0.0) *fail = 1;
+  }
+  gm = block_max(gm, sred);
+  if (threadIdx.x == 0 && gm > 0.0) atomic_max_nonneg(red + 2, gm);
 }
 
 // ---- block-Jacobi preconditioner: inverse of each 6x6 diagonal block --------------------

@@ -22,6 +22,7 @@
 #include <vector>
 #include <algorithm>
 #include <mutex>
+#include <unordered_map>
 #include "common.cuh"
 #include "match.cuh"
 
@@ -32,6 +33,7 @@ constexpr int TC_STAGES = 3;                                  // B-operand ring 
 constexpr int TC_MAX_KB = 6;                                  // A tile stays resident for a whole item: K' <= 192
 constexpr int TC_A_BYTES = TC_M * TC_KB * 4, TC_B_BYTES = TC_N * TC_KB * 4;
 constexpr int TC_HCAP = 32;                                   // hit slots per (row, column half)
+constexpr int TC_BOUND_DIV = 2;                               // the bound pass looks at 1/TC_BOUND_DIV of the column tiles
 constexpr int TC_THREADS = 320;                               // warp0 TMA, warp1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 constexpr uint32_t SPIN_LIMIT = 1u << 24;                     // watchdog: trap instead of hanging the GPU
 
@@ -151,7 +153,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + TC_MAX_KB * TC_A_BYTES + TC_STAGES * TC_B_BYTES);
   // bars: [0..S) b_full, [S..2S) b_empty, 2S a_full, 2S+1 a_empty, [2S+2..2S+4) tmem_full, [2S+4..2S+6) tmem_empty
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 6);
-  float* merge_f = reinterpret_cast<float*>(bars + 2 * TC_STAGES + 8);           // [128][2]
+  float* merge_f = reinterpret_cast<float*>(bars + 2 * TC_STAGES + 8);           // [128][4]
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + TC_STAGES);
   const uint32_t bar_afull = smem_u32(bars + 2 * TC_STAGES), bar_aempty = smem_u32(bars + 2 * TC_STAGES + 1);
   const uint32_t bar_tfull = smem_u32(bars + 2 * TC_STAGES + 2), bar_tempty = smem_u32(bars + 2 * TC_STAGES + 4);
@@ -169,7 +171,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  auto tiles_of = [](int nB) { const int n = (nB + TC_N - 1) / TC_N; return MODE == 0 ? max(1, (n + 3) / 4) : n; };
+  auto tiles_of = [](int nB) { const int n = (nB + TC_N - 1) / TC_N; return MODE == 0 ? max(1, (n + TC_BOUND_DIV - 1) / TC_BOUND_DIV) : n; };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -230,7 +232,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(
       const TcItem w = items[it];
       const int n_tiles = tiles_of(w.nB);
       const bool row_ok = row_in_tile < w.nA;
-      float m1 = FLT_MAX, m2 = FLT_MAX;                            // MODE 0: two smallest values
+      // MODE 0: minima of four disjoint column groups (chunk index within the tile half).  The 2nd smallest of the row's
+      // eight group minima (both halves) is >= the row's 2nd smallest value: a valid bound at one FMNMX3 per two columns.
+      float g0 = FLT_MAX, g1 = FLT_MAX, g2 = FLT_MAX, g3 = FLT_MAX;
       float T = 0.f; int cnt = 0;                                   // MODE 1: threshold, hits so far
       int* my_hits = nullptr;
       if (MODE == 1) {
@@ -255,22 +259,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(
           tmem_ld_wait();
           if ((ch + 1) * 32 < ncols && ch + 1 < TC_N / 64) tmem_ld32(tbase + (ch + 1) * 32, (ch & 1) ? va : vb);
           const int lim = min(32, ncols - ch * 32);
+          if (lim < 32) {                                           // ragged last chunk of an image: columns past the end read as FLT_MAX
+#pragma unroll
+            for (int e = 0; e < 32; ++e) if (e >= lim) v[e] = __float_as_uint(FLT_MAX);
+          }
+          // minima of the four 8-column groups of the chunk: 4 FMNMX3-class instructions each
+          float s[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float t1 = fminf(fminf(__uint_as_float(v[8 * k]), __uint_as_float(v[8 * k + 1])), __uint_as_float(v[8 * k + 2]));
+            const float t2 = fminf(fminf(__uint_as_float(v[8 * k + 3]), __uint_as_float(v[8 * k + 4])), __uint_as_float(v[8 * k + 5]));
+            s[k] = fminf(fminf(fminf(t1, t2), __uint_as_float(v[8 * k + 6])), __uint_as_float(v[8 * k + 7]));
+          }
+          const float m = fminf(fminf(fminf(s[0], s[1]), s[2]), s[3]);
           if (MODE == 0) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const float x = e < lim ? __uint_as_float(v[e]) : FLT_MAX;
-              m2 = fminf(m2, fmaxf(m1, x)); m1 = fminf(m1, x);
-            }
+            if (ch == 0) g0 = fminf(g0, m); else if (ch == 1) g1 = fminf(g1, m); else if (ch == 2) g2 = fminf(g2, m); else g3 = fminf(g3, m);
           } else {
-            uint32_t mask = 0;
+            if (__any_sync(0xffffffffu, m <= T)) {                  // a few columns per row in total: everything below is warp-uniform
+              const int cbase = col0 + ch * 32;
 #pragma unroll
-            for (int e = 0; e < 32; ++e) mask |= (__uint_as_float(v[e]) <= T) ? (1u << e) : 0u;
-            if (lim < 32) mask &= (1u << lim) - 1u;
-            uint32_t umask = __reduce_or_sync(0xffffffffu, mask);
-            const int cbase = col0 + ch * 32;
-            while (umask) {                                         // warp-uniform; a handful of columns per row in total
-              const int e = __ffs(umask) - 1; umask &= umask - 1;
-              if ((mask >> e) & 1u) { if (cnt < TC_HCAP) my_hits[cnt] = cbase + e; ++cnt; }
+              for (int k = 0; k < 4; ++k) {
+                if (!__any_sync(0xffffffffu, s[k] <= T)) continue;
+                uint32_t mask = 0;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) mask |= (__uint_as_float(v[8 * k + e]) <= T) ? (1u << e) : 0u;
+                uint32_t umask = __reduce_or_sync(0xffffffffu, mask);
+                while (umask) {
+                  const int e = __ffs(umask) - 1; umask &= umask - 1;
+                  if ((mask >> e) & 1u) { if (cnt < TC_HCAP) my_hits[cnt] = cbase + 8 * k + e; ++cnt; }
+                }
+              }
             }
           }
         }
@@ -280,13 +298,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       if (MODE == 0) {
-        // merge the two column halves of each row (half 1 -> smem -> half 0)
-        if (half == 1) { merge_f[row_in_tile * 2] = m1; merge_f[row_in_tile * 2 + 1] = m2; }
+        // merge the two column halves of each row (half 1 -> smem -> half 0): 2nd smallest of the eight group minima
+        if (half == 1) { merge_f[row_in_tile * 4] = g0; merge_f[row_in_tile * 4 + 1] = g1; merge_f[row_in_tile * 4 + 2] = g2; merge_f[row_in_tile * 4 + 3] = g3; }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (half == 0) {
-          const float o1 = merge_f[row_in_tile * 2], o2 = merge_f[row_in_tile * 2 + 1];
-          const float s2 = fminf(fmaxf(m1, o1), fminf(m2, o2));    // 2nd smallest of the union
-          if (row_ok) bound[w.out_off + row_in_tile] = s2;
+          float m1 = FLT_MAX, m2 = FLT_MAX;
+          const float x[8] = { g0, g1, g2, g3, merge_f[row_in_tile * 4], merge_f[row_in_tile * 4 + 1], merge_f[row_in_tile * 4 + 2], merge_f[row_in_tile * 4 + 3] };
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { m2 = fminf(m2, fmaxf(m1, x[e])); m1 = fminf(m1, x[e]); }
+          if (row_ok) bound[w.out_off + row_in_tile] = m2;
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
       } else {
@@ -407,6 +427,7 @@ struct Prepared {           // TF32 operand copies of one descriptor array
   const float* desc = nullptr; int64_t rows = 0; int K = 0, Kp = 0; bool valid = false; int64_t cap_rows = 0;
   DevBuf<float> PA, PB, norms; CUtensorMap mapA, mapB; std::vector<float> h_norm_max;   // per call computed lazily
   std::vector<float> h_norms;
+  std::unordered_map<uint64_t, float> bmax_cache;     // (first row, rows) of an image -> largest |b|^2
 };
 std::mutex g_prep_mu;
 std::vector<Prepared*> g_prepared;
@@ -431,7 +452,7 @@ int fill_prepared(Prepared* p, int64_t rows, cudaStream_t st) {
   MM_CUDA(cudaMemsetAsync(p->PB.p + (size_t)rows * p->Kp, 0, sizeof(float) * (size_t)TC_N * p->Kp, st));
   k_tc_prep<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(p->desc, rows, p->K, p->Kp, p->PA.p, p->PB.p, p->norms.p);
   MM_LAUNCH_CHECK();
-  p->h_norms.resize((size_t)rows);
+  p->h_norms.resize((size_t)rows); p->bmax_cache.clear();
   MM_CUDA(cudaMemcpyAsync(p->h_norms.data(), p->norms.p, sizeof(float) * (size_t)rows, cudaMemcpyDeviceToHost, st));
   MM_CUDA(cudaStreamSynchronize(st));
   int rc = make_map(&p->mapA, p->PA.p, prow, p->Kp, TC_M); if (rc) return rc;
@@ -500,7 +521,10 @@ int match_tc_pairs(const float* desc, const float* xy, int K, const int64_t* off
       const int nA = dir == 0 ? j.n1 : j.n2, nB = dir == 0 ? j.n2 : j.n1;
       if (nA == 0) continue;
       float bmax = 0.f;
-      for (int64_t r = offs[imgB]; r < offs[imgB] + nB; ++r) bmax = std::max(bmax, P->h_norms[(size_t)r]);
+      { const uint64_t key = ((uint64_t)offs[imgB] << 24) ^ (uint64_t)nB;
+        auto hit = P->bmax_cache.find(key);
+        if (hit != P->bmax_cache.end()) bmax = hit->second;
+        else { for (int64_t r = offs[imgB]; r < offs[imgB] + nB; ++r) bmax = std::max(bmax, P->h_norms[(size_t)r]); P->bmax_cache[key] = bmax; } }
       RerankJob rj; rj.rowA0 = (int)offs[imgA]; rj.nA = nA; rj.rowB0 = (int)offs[imgB]; rj.nB = nB; rj.out_off = cand_rows;
       rj.knn_off = dir == 0 ? j.knn12_off : -(j.knn21_off + 1); rj.bmax = std::sqrt(bmax);
       rjobs.push_back(rj);
@@ -524,7 +548,7 @@ int match_tc_pairs(const float* desc, const float* xy, int K, const int64_t* off
   MM_CUDA(cudaMemsetAsync(g_scr.hcnt.p, 0, sizeof(int) * 2 * (size_t)cand_rows, st));
   if (!items.empty()) {
     MM_CUDA(cudaMemcpyAsync(g_scr.items.p, items.data(), sizeof(TcItem) * items.size(), cudaMemcpyHostToDevice, st));
-    const size_t smem = (size_t)TC_MAX_KB * TC_A_BYTES + (size_t)TC_STAGES * TC_B_BYTES + 1024 + 256 + (size_t)TC_M * 8;
+    const size_t smem = (size_t)TC_MAX_KB * TC_A_BYTES + (size_t)TC_STAGES * TC_B_BYTES + 1024 + 256 + (size_t)TC_M * 16;
     static bool configured = false;
     if (!configured) {
       MM_CUDA(cudaFuncSetAttribute(k_match_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -548,7 +572,8 @@ int match_tc_pairs(const float* desc, const float* xy, int K, const int64_t* off
     MM_LAUNCH_CHECK();
   }
   int nf12 = 0;
-  MM_CUDA(cudaMemcpyAsync(&nf12, g_scr.n_flagged.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  const bool want_stats = getenv("MM_MATCH_TC_STATS") != nullptr;       // (a D2H copy into pageable memory would stall the launch queue here)
+  if (want_stats) MM_CUDA(cudaMemcpyAsync(&nf12, g_scr.n_flagged.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   if (!j21.empty()) {
     MM_CUDA(cudaMemsetAsync(g_scr.n_flagged.p, 0, sizeof(int), st));
     k_rerank<<<dim3((max_nA + 127) / 128, (unsigned)j21.size()), 128, 0, st>>>(g_scr.jobs.p + j12.size(), desc, K, g_scr.hits.p, g_scr.hcnt.p, knn21, g_scr.flagged.p, g_scr.n_flagged.p, flag_cap);
@@ -557,7 +582,7 @@ int match_tc_pairs(const float* desc, const float* xy, int K, const int64_t* off
     MM_LAUNCH_CHECK();
   }
   g_tc_rows.fetch_add((uint64_t)cand_rows);
-  if (getenv("MM_MATCH_TC_STATS")) {
+  if (want_stats) {
     int nf21 = 0; MM_CUDA(cudaMemcpyAsync(&nf21, g_scr.n_flagged.p, sizeof(int), cudaMemcpyDeviceToHost, st)); MM_CUDA(cudaStreamSynchronize(st));
     g_tc_flagged.fetch_add((uint64_t)nf12 + (uint64_t)nf21);
     fprintf(stderr, "[match_tc] rows %lld flagged for exact rescan: %d + %d\n", (long long)cand_rows, nf12, nf21);

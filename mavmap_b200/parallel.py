@@ -4,10 +4,49 @@ Pairs are independent units: every rank holds the descriptors, 
 slice of the pair list, matches it on its own GPU, and the variable-length match lists are
 gathered once at the end (two collectives: counts, then the packed lists) over NCCL/NVLink
 (`gloo` in the CPU tests).  There is no data-path collective inside the matching itself.
-BA does not shard in this round (north_star: single GPU unless the problem overflows HBM):
-`bench.py --gpus N` runs N independent replicas.
+Bundle adjustment shards by 3-D point (mm_ba_session_create_sharded): the library asks the host for ONE primitive, an
+in-place sum of doubles over the ranks, through a callback; `make_allreduce_callback` provides it on top of
+torch.distributed (NCCL over NVLink on the GPUs, `gloo` on host buffers in the CPU tests).
 """
+import ctypes as C
+
 import numpy as np
+
+
+class _DevF64:
+    """zero-copy view of `n` doubles at a device pointer for torch.as_tensor"""
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+def make_allreduce_callback(group=None, device=True):
+    """The `mm_allreduce_fn` of include/mavmap_b200.h: sums `count` doubles at `buf` over all ranks, in place, ordered on
+    `stream`.  device=False treats `buf` as a host pointer (CPU tests of the plumbing with gloo)."""
+    import torch
+    import torch.distributed as dist
+    from ._abi import ALLREDUCE_FN
+
+    def cb(user, buf, count, stream):
+        try:
+            if count <= 0:
+                return 0
+            if device:
+                t = torch.as_tensor(_DevF64(buf, count), device="cuda")
+                if stream:
+                    with torch.cuda.stream(torch.cuda.ExternalStream(int(stream))):
+                        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+                else:
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            else:
+                a = np.ctypeslib.as_array((C.c_double * int(count)).from_address(int(buf)))
+                t = torch.from_numpy(a)
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            return 0
+        except Exception as e:          # never unwind through the C frame
+            import sys
+            print("all-reduce callback failed: %r" % (e,), file=sys.stderr)
+            return 1
+    return ALLREDUCE_FN(cb)
 
 
 def shard_pairs(n_pairs, rank, world):

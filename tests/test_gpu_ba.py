@@ -197,3 +197,16 @@ def test_two_level_preconditioner_parity_and_iteration_count(mm, orc, monkeypatc
     np.testing.assert_allclose(s1["trace_cost"], sg["trace_cost"], rtol=REL)
     assert two_level * 2 < sum(s1["trace_linear_iterations"])
     assert max(sg["trace_linear_iterations"]) < o.pcg_max_iterations
+
+
+def test_sharded_ba_two_gpus_matches_single_gpu(mm):
+    """points sharded across two GPUs with one exchange step per Schur assembly reproduce the single-GPU solve
+    (needs two visible GPUs; tools/sharded_ba.py exits non-zero on any mismatch)."""
+    import os, subprocess, sys
+    from mavmap_b200 import _lib
+    if _lib.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29517", os.path.join(root, "tools", "sharded_ba.py"), "mid"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

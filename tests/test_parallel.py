@@ -55,3 +55,29 @@ def test_two_rank_gather_equals_single_process(tmp_path):
         g = np.load(os.path.join(str(tmp_path), "r%d.npz" % r))
         assert np.array_equal(g["off"], off1) and np.array_equal(g["q"], q1) and np.array_equal(g["t"], t1) and np.array_equal(g["d"], d1)
     assert off1[-1] > 100
+
+
+def _allreduce_cb_worker(rank, world, port, q):
+    import ctypes as C
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    from mavmap_b200.parallel import make_allreduce_callback
+    cb = make_allreduce_callback(device=False)          # the mm_allreduce_fn of the sharded BA session, on a host buffer
+    buf = np.arange(10, dtype=np.float64) * (rank + 1)
+    rc = cb(None, buf.ctypes.data_as(C.c_void_p), 10, None)
+    q.put((rank, rc, buf.copy()))
+    dist.destroy_process_group()
+
+
+def test_allreduce_callback_two_ranks_gloo():
+    """the one collective primitive the sharded BA session asks of the host (mm_allreduce_fn): in-place sum over the ranks"""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue(); port = _free_port()
+    ps = [ctx.Process(target=_allreduce_cb_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps: p.start()
+    out = [q.get(timeout=120) for _ in ps]
+    for p in ps: p.join(timeout=60)
+    for rank, rc, buf in out:
+        assert rc == 0
+        np.testing.assert_array_equal(buf, np.arange(10, dtype=np.float64) * 3)

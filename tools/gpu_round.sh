@@ -23,11 +23,19 @@ if has launches; then
       python bench.py --steps 2 --warmup 3 --no-cpu > $OUT/launches_$TAG.log 2>&1
 fi
 if has full; then
-  timeout 600 ncu --set full --clock-control none --import-source on \
-      -k regex:'k_residual_jacobian|k_schur_point|k_schur_cam|k_backsub' -s 8 -c 8 -f -o $OUT/prof_ba_$TAG \
-      python tools/time_ba.py cfg4 2 > $OUT/prof_ba_$TAG.log 2>&1
-  timeout 600 ncu --set full --clock-control none --import-source on \
+  # one instance of every BA kernel on the bench workload (cfg2) and on cfg4, and the matcher kernels.  The reports are
+  # converted to the raw-metric CSV on the box and dropped (gpurun brings back at most 64 MiB); K1's report is kept for
+  # the source page.
+  for cfg in cfg2 cfg4; do
+    MM_NO_TIME_KERNEL=1 timeout 900 ncu --set full --clock-control none \
+        -k regex:'k_residual_jacobian|k_schur_point|k_schur_blocks|k_schur_cam|k_backsub|k_spd_inverse|k_pcg|k_coarse_assemble' -c 9 -f -o $OUT/prof_ba_${cfg}_$TAG \
+        python tools/time_ba.py $cfg 1 > $OUT/prof_ba_${cfg}_$TAG.log 2>&1
+    ncu -i $OUT/prof_ba_${cfg}_$TAG.ncu-rep --page raw --csv > $OUT/prof_ba_${cfg}_$TAG.csv 2>/dev/null; rm -f $OUT/prof_ba_${cfg}_$TAG.ncu-rep
+  done
+  timeout 600 ncu --set full --clock-control none \
       -k regex:'k_match_tc|k_rerank|k_tc_prep' -s 3 -c 4 -f -o $OUT/prof_match_$TAG \
       python tools/time_match.py 64 > $OUT/prof_match_$TAG.log 2>&1
+  ncu -i $OUT/prof_match_$TAG.ncu-rep --page raw --csv > $OUT/prof_match_$TAG.csv 2>/dev/null; rm -f $OUT/prof_match_$TAG.ncu-rep
 fi
+du -sh $OUT
 echo done
