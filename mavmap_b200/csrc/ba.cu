@@ -12,6 +12,7 @@
 #include <vector>
 #include <algorithm>
 #include "ba_kernels.cuh"
+#include "ba_pose.cuh"
 
 namespace mm {
 
@@ -1044,6 +1045,31 @@ int mm_pose_refine(double* rvec, double* tvec, int model_code, const double* par
     pts.insert(pts.end(), points3D + 3 * i, points3D + 3 * i + 3); obs.insert(obs.end(), points2D + 2 * i, points2D + 2 * i + 2);
   }
   double poses[6] = { rvec[0], rvec[1], rvec[2], tvec[0], tvec[1], tvec[2] };
+  if (!pc.empty() && !getenv("MM_POSE_REFINE_GENERAL")) {
+    // latency path: the whole LM loop in one single-CTA kernel (ba_pose.cuh); one upload, one launch, one download
+    int rc = ensure_device(); if (rc) return rc;
+    const size_t m = pc.size();
+    DevBuf<double> d_in, d_pose; DevBuf<mm_ba_summary> d_sum;       // d_in = [uv (2m) | X (3m) | intr (9)]
+    MM_CUDA(d_in.alloc(5 * m + MM_INTR_STRIDE)); MM_CUDA(d_pose.alloc(6)); MM_CUDA(d_sum.alloc(1));
+    double intr9[MM_INTR_STRIDE] = {0};
+    memcpy(intr9, params, sizeof(double) * (size_t)model_num_params(model_code));
+    MM_CUDA(cudaMemcpyAsync(d_in.p, obs.data(), sizeof(double) * 2 * m, cudaMemcpyHostToDevice, nullptr));
+    MM_CUDA(cudaMemcpyAsync(d_in.p + 2 * m, pts.data(), sizeof(double) * 3 * m, cudaMemcpyHostToDevice, nullptr));
+    MM_CUDA(cudaMemcpyAsync(d_in.p + 5 * m, intr9, sizeof intr9, cudaMemcpyHostToDevice, nullptr));
+    MM_CUDA(cudaMemcpyAsync(d_pose.p, poses, sizeof poses, cudaMemcpyHostToDevice, nullptr));
+    k_pose_refine<<<1, 256, 0, nullptr>>>((int)m, reinterpret_cast<const double2*>(d_in.p), d_in.p + 2 * m, model_code, d_in.p + 5 * m, *opt, d_pose.p, d_sum.p);
+    MM_LAUNCH_CHECK();
+    mm_ba_summary S;
+    MM_CUDA(cudaMemcpyAsync(&S, d_sum.p, sizeof S, cudaMemcpyDeviceToHost, nullptr));
+    MM_CUDA(cudaMemcpyAsync(poses, d_pose.p, sizeof poses, cudaMemcpyDeviceToHost, nullptr));
+    MM_CUDA(cudaStreamSynchronize(nullptr));
+    S.return_value = sqrt(S.final_cost / (double)std::max<int64_t>(S.num_residuals, 1));
+    S.ms_setup = S.ms_linearize = S.ms_schur = S.ms_pcg = S.ms_update = S.ms_total = 0.0;
+    if (S.termination == MM_TERM_NUMERICAL_FAILURE && !isfinite(S.initial_cost)) { set_error("non-finite initial cost"); return MM_ERR_NUMERICAL; }
+    for (int k = 0; k < 3; ++k) { rvec[k] = poses[k]; tvec[k] = poses[3 + k]; }
+    if (ret) *ret = S.return_value; if (summary) *summary = S;
+    return MM_OK;
+  }
   uint8_t pose_const[4] = {0, 0, 0, 0}; int32_t img_cam[1] = {0}; double intr[MM_INTR_STRIDE] = {0};
   memcpy(intr, params, sizeof(double) * (size_t)model_num_params(model_code));
   int32_t cam_model[1] = { model_code }; uint8_t intr_const[1] = {1};

@@ -210,3 +210,41 @@ def test_sharded_ba_two_gpus_matches_single_gpu(mm):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29517", os.path.join(root, "tools", "sharded_ba.py"), "mid"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("model", [1, 2, 3])
+def test_pose_refinement_single_kernel_path(mm, orc, model, monkeypatch):
+    """pose_refinement (bundle_adjustment.cc:139-225) runs as one single-CTA kernel (ba_pose.cuh): same LM trace and pose as
+    the oracle and as the general session engine, including a tolerance-terminated run and an inlier mask."""
+    import time
+    from mavmap_b200.synthetic import _rodrigues, project
+    rng = np.random.default_rng(10 + model)
+    n = 1500
+    X = rng.uniform([-3, -3, 5], [3, 3, 12], (n, 3))
+    rvec, tvec = np.array([0.08, -0.05, 0.03]), np.array([0.2, -0.3, 0.4])
+    params = list(synthetic.INTRINSICS[model]) + [model]
+    uv = project(model, np.array(params[:-1]), X @ _rodrigues(rvec)[0].T + tvec) + rng.normal(0, 0.4, (n, 2))
+    uv[::50] += rng.uniform(-80, 80, (len(uv[::50]), 2))               # gross outliers for the Cauchy loss
+    mask = np.ones(n, bool); mask[::7] = False
+    for kw in (dict(max_num_iterations=12, function_tolerance=0, gradient_tolerance=0), dict(max_num_iterations=50)):
+        opt = mm.BundleAdjustmentOptions(print_summary=False, **kw)
+        out = {}
+        for name in ("fused", "general", "oracle"):
+            r, t = rvec + 0.03, tvec - 0.08
+            if name == "general":
+                monkeypatch.setenv("MM_POSE_REFINE_GENERAL", "1")
+            else:
+                monkeypatch.delenv("MM_POSE_REFINE_GENERAL", raising=False)
+            t0 = time.perf_counter()
+            ret = (orc if name == "oracle" else mm).pose_refinement(r, t, params, uv, X, mask, opt)
+            out[name] = (ret, r.copy(), t.copy(), time.perf_counter() - t0)
+        for name in ("fused", "general"):
+            assert abs(out[name][0] - out["oracle"][0]) <= REL * out["oracle"][0]
+            np.testing.assert_allclose(out[name][1], out["oracle"][1], atol=REL)
+            np.testing.assert_allclose(out[name][2], out["oracle"][2], atol=REL)
+    monkeypatch.delenv("MM_POSE_REFINE_GENERAL", raising=False)
+    r, t = rvec + 0.03, tvec - 0.08
+    t0 = time.perf_counter()
+    for _ in range(20):
+        mm.pose_refinement(r.copy(), t.copy(), params, uv, X, mask, opt)
+    print("pose_refinement latency: %.0f us per call (%d points)" % ((time.perf_counter() - t0) / 20 * 1e6, int(mask.sum())))
