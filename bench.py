@@ -148,11 +148,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ba_cfg2", choices=["ba_cfg2", "ba_cfg4", "ba_cfg1", "ba_small"])
-    ap.add_argument("--match-pairs", type=int, default=24)
+    ap.add_argument("--match-pairs", type=int, default=120)
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--ref-max-steps", type=int, default=12)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-match", action="store_true")
+    ap.add_argument("--ba-mode", default="replicas", choices=["replicas", "sharded"],
+                    help="N > 1: independent problems per GPU (default, north_star: BA stays on one GPU) or ONE problem with its points sharded")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -190,11 +192,18 @@ def main():
 
     # ------------------------------------------------------------------ BA, resident
     name, kw = ba_config(args.workload)
-    kw["seed"] = kw["seed"] + 1000 * rank                 # replicas: one independent problem per rank
+    sharded = args.ba_mode == "sharded" and world > 1
+    if not sharded:
+        kw["seed"] = kw["seed"] + 1000 * rank             # replicas: one independent problem per rank
     flat, _ = synthetic.make_ba_problem(**kw)
     W, K = args.warmup, args.steps
     stream = torch.cuda.current_stream().cuda_stream
-    sess = BASession(flat.copy(), options(W + K), stream=stream)
+    if sharded:
+        from mavmap_b200.parallel import make_allreduce_callback
+        ar_cb = make_allreduce_callback()
+        sess = BASession(flat.copy(), options(W + K), stream=stream, rank=rank, world=world, allreduce=ar_cb)
+    else:
+        sess = BASession(flat.copy(), options(W + K), stream=stream)
     n_blocks = sess.num_blocks()
     sess.iterate(W)
     sampler = ClockSampler(local); sampler.start()
@@ -210,7 +219,7 @@ def main():
     clocks = sampler.stop()
     summ = sess.summary().as_dict()
     assert done == K, "LM stopped early (%d of %d iterations)" % (done, K)
-    value = world * K / (ms * 1e-3)
+    value = (1 if sharded else world) * K / (ms * 1e-3)
 
     # per-kernel timings on the resident state (live, CUDA events inside the library)
     k1_ms = sess.time_kernel(0, 20); k2_ms = sess.time_kernel(1, 10); k4_ms = sess.time_kernel(2, 20); spmv_ms = sess.time_kernel(3, 50)
@@ -238,6 +247,10 @@ def main():
     sess.close()
 
     # ------------------------------------------------------------------ BA, end to end through mm_ba_solve (host buffers)
+    if sharded:
+        kw2 = dict(kw); kw2["seed"] = kw["seed"] + 1000 * rank
+        flat, _ = synthetic.make_ba_problem(**kw2)          # the host-buffer call is per GPU: one problem each
+        n_obs, n_pt, n_img = flat.n_obs, flat.n_pt, flat.n_img
     warm = flat.copy(); solve_flat(warm, options(1))          # load kernels / allocator warm-up, untimed
     barrier()
     f2 = flat.copy()
@@ -292,6 +305,24 @@ def main():
                      "e2e": {"value": world / m_e2e, "unit": "pairs/s", "h2d_bytes_per_step": 2 * n_feat * kdim * 4, "d2h_bytes_per_step": 12 * 3000}}
         ms_set.close()
 
+    # ------------------------------------------------------------------ pose_refinement latency, rank 0
+    pose_lat = None
+    if rank == 0:
+        import mavmap_b200 as mmod
+        from mavmap_b200.synthetic import _rodrigues, project
+        rng = np.random.default_rng(5); npts = 2000
+        Xp = rng.uniform([-3, -3, 5], [3, 3, 12], (npts, 3)); rv, tv = np.array([0.08, -0.05, 0.03]), np.array([0.2, -0.3, 0.4])
+        prm = list(synthetic.INTRINSICS[1]) + [1]
+        uvp = project(1, np.array(prm[:-1]), Xp @ _rodrigues(rv)[0].T + tv) + rng.normal(0, 0.4, (npts, 2))
+        po = mmod.BundleAdjustmentOptions(print_summary=False, max_num_iterations=10, function_tolerance=0, gradient_tolerance=0)
+        msk = np.ones(npts, bool)
+        mmod.pose_refinement(rv + 0.03, tv - 0.08, prm, uvp, Xp, msk, po)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            mmod.pose_refinement(rv + 0.03, tv - 0.08, prm, uvp, Xp, msk, po)
+        pose_lat = {"metric": "pose_refinement_latency", "value": (time.perf_counter() - t0) / 20 * 1e6, "unit": "us per call (host buffers in, pose out)",
+                    "config": {"workload": "%d 2D-3D pairs, PINHOLE, 10 LM iterations, single-CTA kernel" % npts}}
+
     # ------------------------------------------------------------------ CPU baseline beside it (rank 0, N = 1)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -308,9 +339,10 @@ def main():
     if rank == 0:
         dominant = max((roof_k1, roof_k2), key=lambda r: r["ms"])
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "%s: %d images, %d points, %d observations, PINHOLE fx=fy=1000, fixed intrinsics, Cauchy loss, image0 FIXED / image1 FIXED_X" % (name, n_img, n_pt, n_obs),
-                           "parallelism": "replicas only (one independent BA per GPU)" if world > 1 else "single GPU",
+                           "parallelism": ("one problem, points sharded across %d GPUs, all-reduce of the reduced system per Schur assembly" % world) if sharded else
+                                          ("replicas only (one independent BA per GPU)" if world > 1 else "single GPU"),
                            "l2_policy": "inputs larger than L2: %.0f MB of Jacobian records + %.0f MB of observations per LM iteration" % (160.0 * n_obs / 1e6, 24.0 * n_obs / 1e6),
                            "pcg_tolerance": 1e-13, "reduced_system_blocks": n_blocks,
                            "pcg_preconditioner": ("two-level: block-Jacobi + %d similarity-mode coarse unknowns" % coarse_dim) if coarse_dim else "block-Jacobi"},
@@ -321,7 +353,7 @@ def main():
                               "pcg_iterations_in_timed_steps": int(pcg_iters), "k1_ms": k1_ms, "k2_ms": k2_ms, "k4_cost_ms": k4_ms, "pcg_spmv_ms": spmv_ms,
                               "coarse_setup_ms": coarse_ms, "ms_pcg_per_iteration": lin_ms["pcg"] / max(int(pcg_iters), 1),
                               "dominant_by_time": "K3 PCG" if lin_ms["pcg"] > max(lin_ms["schur"], lin_ms["linearize"]) else dominant["kernel"]},
-                "cpu_baseline": cpu, "secondary": secondary, "final_cost": summ["final_cost"]}
+                "cpu_baseline": cpu, "secondary": secondary, "tertiary": pose_lat, "final_cost": summ["final_cost"]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
