@@ -557,8 +557,8 @@ int launch_schur(mm_ba_session* s, bool with_coarse = true) {
       s->Vinv.p + 6 * (size_t)P0, s->gp.p + 3 * (size_t)P0, s->dp.p + 3 * (size_t)P0, s->scal() + 3 + s->rank, s->fail.p, s->pinfo.p + PINFO * (size_t)P0); MM_LAUNCH_CHECK();
   k_schur_blocks<<<blocks_for(s->nblk * 32, 128), 128, 0, st>>>(s->n_img, s->nblk, s->blk_a.p, s->blk_b.p, s->bp_lo.p, s->bp_hi.p, s->sp_lo.p, s->sp_hi.p,
       s->sp_pt.p, s->rec_base(), s->scale_c.p, s->pinfo.p, s->S.p); MM_LAUNCH_CHECK();
-  k_schur_cam<<<blocks_for((int64_t)s->n_img * 32, 128), 128, 0, st>>>(s->n_img, s->cam_lo.p, s->cam_hi.p, s->cam_perm.p, s->obs_pt.p, s->rec_base(),
-      s->scale_c.p, s->scale_p.p, s->Vinv.p, s->gp.p, s->S.p, s->rhs.p, s->gc.p, s->ud.p); MM_LAUNCH_CHECK();
+  if (s->n_img > 0) { k_schur_cam<<<s->n_img, 128, 0, st>>>(s->n_img, s->cam_lo.p, s->cam_hi.p, s->cam_perm.p, s->obs_pt.p, s->rec_base(),
+      s->scale_c.p, s->pinfo.p, s->S.p, s->rhs.p, s->gc.p, s->ud.p); MM_LAUNCH_CHECK(); }
   // exchange step: S | rhs | gc | ud | scalars summed over the ranks (nothing to do on one GPU), then the LM diagonal
   k_pack_scal<<<1, 32, 0, st>>>(s->loc.p, s->fail.p, s->scal()); MM_LAUNCH_CHECK();
   { const int rc = all_reduce(s, s->xch.p, s->xch_count); if (rc) return rc; }

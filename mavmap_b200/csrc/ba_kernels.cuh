@@ -20,6 +20,7 @@
 namespace mm {
 
 constexpr int REC = 20;     // doubles per observation record (160 B = 5 sectors)
+constexpr int PINFO = 12;                // doubles per point record (96 B = 3 sectors): V^-1 (6) | scale_p (3) | g_p (3)
 constexpr int AUX = 24;     // doubles per image: R(9) t(3) Jl(9) masks(2) pad = 192 B
 
 struct LossParams { int type; double b; double c; };   // Cauchy: b = a^2, c = 1/b
@@ -291,10 +292,10 @@ __global__ void __launch_bounds__(128) k_schur_point(
     if (!sym3_inverse(V, I)) { *fail = 1; I[0] = I[3] = I[5] = 0; I[1] = I[2] = I[4] = 0; }
 #pragma unroll
     for (int k = 0; k < 6; ++k) Vinv[6 * (size_t)p + k] = I[k];
-    {     // the same data as one 80-byte record per point for the block pass (5 whole 16-byte chunks)
-      double2* pi = reinterpret_cast<double2*>(pinfo + 10 * (size_t)p);
+    {     // the same data as one 96-byte record per point for the block and camera passes (6 whole 16-byte chunks)
+      double2* pi = reinterpret_cast<double2*>(pinfo + PINFO * (size_t)p);
       pi[0] = make_double2(I[0], I[1]); pi[1] = make_double2(I[2], I[3]); pi[2] = make_double2(I[4], I[5]);
-      pi[3] = make_double2(sp[0], sp[1]); pi[4] = make_double2(sp[2], 0.0);
+      pi[3] = make_double2(sp[0], sp[1]); pi[4] = make_double2(sp[2], g[0]); pi[5] = make_double2(g[1], g[2]);
     }
     gp_out[3 * (size_t)p] = g[0]; gp_out[3 * (size_t)p + 1] = g[1]; gp_out[3 * (size_t)p + 2] = g[2];
     dp_out[3 * (size_t)p] = d0; dp_out[3 * (size_t)p + 1] = d1; dp_out[3 * (size_t)p + 2] = d2;
@@ -314,7 +315,6 @@ __global__ void __launch_bounds__(128) k_schur_point(
 // lanes read consecutive 16-byte chunks — single-buffered 2.1 ms, double-buffered 2.3 ms against 1.9 ms for this form:
 // the gather is L1-tag bound, the staged forms are latency bound at the occupancy their buffers allow.)
 // Diagonal blocks only receive the (rare) pairs of one point observed twice by the same image; K2b adds U - sum Y W'.
-constexpr int PINFO = 10;                // doubles per point record: V^-1 (6) | scale_p (3) | pad
 
 __global__ void __launch_bounds__(128, 3) k_schur_blocks(
     int n_img, int64_t nblk, const int* __restrict__ blk_a, const int* __restrict__ blk_b,
@@ -387,33 +387,32 @@ __global__ void __launch_bounds__(128, 3) k_schur_blocks(
 
 // ---- K2b: per-image diagonal block, reduced right-hand side, gradient, LM diagonal ----------
 // one warp per image over its observations (camera-sorted permutation, 160 B record gathers).
-__global__ void __launch_bounds__(128) k_schur_cam(
+__global__ void __launch_bounds__(128, 3) k_schur_cam(
     int n_img, const int* __restrict__ cam_lo, const int* __restrict__ cam_hi, const int* __restrict__ cam_perm, const int* __restrict__ obs_pt,
-    const double* __restrict__ rec, const double* __restrict__ scale_c, const double* __restrict__ scale_p,
-    const double* __restrict__ Vinv, const double* __restrict__ gp,
+    const double* __restrict__ rec, const double* __restrict__ scale_c, const double* __restrict__ pinfo,
     double* __restrict__ S, double* __restrict__ rhs, double* __restrict__ gc_out, double* __restrict__ ud_out) {
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (w >= n_img) return;
+  // one CTA (4 warps) per image: enough warps in flight for a 500-image problem too (one warp per image left 3 warps/SM)
+  __shared__ double part[4][40];
+  const int w = blockIdx.x, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   double sc[6];
 #pragma unroll
   for (int k = 0; k < 6; ++k) sc[k] = scale_c[6 * (size_t)w + k];
-  double Q[21], h[6], gc[6], ud[6];
+  double acc[39];                       // [0,21) Q upper triangle | [21,27) h | [27,33) gc | [33,39) ud
 #pragma unroll
-  for (int k = 0; k < 21; ++k) Q[k] = 0.0;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) { h[k] = 0.0; gc[k] = 0.0; ud[k] = 0.0; }
-  for (int q = cam_lo[w] + lane; q < cam_hi[w]; q += 32) {
+  for (int k = 0; k < 39; ++k) acc[k] = 0.0;
+  for (int q = cam_lo[w] + threadIdx.x; q < cam_hi[w]; q += 128) {
     const int o = cam_perm[q];
     const int p = obs_pt[o];
-    const double sp[3] = { scale_p[3 * (size_t)p], scale_p[3 * (size_t)p + 1], scale_p[3 * (size_t)p + 2] };
+    double I[6], sp[3], g3[3];
+    {
+      const double2* p2 = reinterpret_cast<const double2*>(pinfo + PINFO * (size_t)p);
+      const double2 v0 = p2[0], v1 = p2[1], v2 = p2[2], v3 = p2[3], v4 = p2[4], v5 = p2[5];
+      I[0] = v0.x; I[1] = v0.y; I[2] = v1.x; I[3] = v1.y; I[4] = v2.x; I[5] = v2.y; sp[0] = v3.x; sp[1] = v3.y; sp[2] = v4.x;
+      g3[0] = v4.y; g3[1] = v5.x; g3[2] = v5.y;
+    }
     double Jc[2][6], Jp[2][3];
     load_scaled(rec, o, sc, sp, Jc, Jp);
     const double2 rr = *reinterpret_cast<const double2*>(rec + REC * (size_t)o);
-    double I[6], g3[3];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) I[k] = Vinv[6 * (size_t)p + k];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) g3[k] = gp[3 * (size_t)p + k];
     double W[6][3], Y[6][3];
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
@@ -424,33 +423,33 @@ __global__ void __launch_bounds__(128) k_schur_cam(
       Y[a][1] = W[a][0] * I[1] + W[a][1] * I[3] + W[a][2] * I[4];
       Y[a][2] = W[a][0] * I[2] + W[a][1] * I[4] + W[a][2] * I[5];
       const double ga = Jc[0][a] * rr.x + Jc[1][a] * rr.y;
-      gc[a] += ga;
-      h[a] += ga - (Y[a][0] * g3[0] + Y[a][1] * g3[1] + Y[a][2] * g3[2]);
-      ud[a] += Jc[0][a] * Jc[0][a] + Jc[1][a] * Jc[1][a];
+      acc[27 + a] += ga;
+      acc[21 + a] += ga - (Y[a][0] * g3[0] + Y[a][1] * g3[1] + Y[a][2] * g3[2]);
+      acc[33 + a] += Jc[0][a] * Jc[0][a] + Jc[1][a] * Jc[1][a];
     }
     int k = 0;
 #pragma unroll
     for (int a = 0; a < 6; ++a)
 #pragma unroll
       for (int c = a; c < 6; ++c, ++k)
-        Q[k] += Jc[0][a] * Jc[0][c] + Jc[1][a] * Jc[1][c] - (Y[a][0] * W[c][0] + Y[a][1] * W[c][1] + Y[a][2] * W[c][2]);
+        acc[k] += Jc[0][a] * Jc[0][c] + Jc[1][a] * Jc[1][c] - (Y[a][0] * W[c][0] + Y[a][1] * W[c][1] + Y[a][2] * W[c][2]);
   }
 #pragma unroll
-  for (int k = 0; k < 21; ++k) Q[k] = warp_sum(Q[k]);
-#pragma unroll
-  for (int k = 0; k < 6; ++k) { h[k] = warp_sum(h[k]); gc[k] = warp_sum(gc[k]); ud[k] = warp_sum(ud[k]); }
-  if (lane == 0) {
+  for (int k = 0; k < 39; ++k) { const double v = warp_sum(acc[k]); if (lane == 0) part[wib][k] = v; }
+  __syncthreads();
+  if (threadIdx.x < 39) part[0][threadIdx.x] = part[0][threadIdx.x] + part[1][threadIdx.x] + part[2][threadIdx.x] + part[3][threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) {
     double* dst = S + 36 * (size_t)w;      // diagonal block id == image index
+    const double* t = part[0];
     int k = 0;
-#pragma unroll
     for (int a = 0; a < 6; ++a) {
-      ud_out[6 * (size_t)w + a] = ud[a];
-      gc_out[6 * (size_t)w + a] = gc[a];
-      rhs[6 * (size_t)w + a] = h[a];
-#pragma unroll
+      ud_out[6 * (size_t)w + a] = t[33 + a];
+      gc_out[6 * (size_t)w + a] = t[27 + a];
+      rhs[6 * (size_t)w + a] = t[21 + a];
       for (int c = a; c < 6; ++c, ++k) {
-        if (c == a) dst[6 * a + a] += Q[k];
-        else { dst[6 * a + c] += Q[k]; dst[6 * c + a] += Q[k]; }
+        if (c == a) dst[6 * a + a] += t[k];
+        else { dst[6 * a + c] += t[k]; dst[6 * c + a] += t[k]; }
       }
     }
   }
