@@ -180,6 +180,12 @@ typedef struct mm_ba_problem {
   const int32_t* obs_pt;      /* [n_obs]                                      */
   double*        pt_err;      /* optional [n_pt]: mean raw residual norm per
                                  point (.cc:575-598); NULL to skip            */
+  /* constrain_rotation (bundle_adjustment.cc:390-446, bundle_adjustment.h:191-209): one extra residual
+   * weight * ||R(rvec)' - R(rvec0)||_F per constrained image (with the reference's index quirk, .cc:103),
+   * no loss function.  NULL / weight 0 = no constraint.  The caller has already rotated the scene into the
+   * frame of the constraints (.cc:412-425; the shim does it). */
+  const double*  rot_prior;   /* optional [n_img*3] rvec0                     */
+  const double*  rot_prior_w; /* optional [n_img] weight (0 = unconstrained)  */
 } mm_ba_problem;
 
 typedef struct mm_ba_options {

@@ -46,7 +46,7 @@ class BAProblem(C.Structure):
                 ("intr", p_f64), ("cam_model", p_i32), ("intr_const", p_u8),
                 ("pts", p_f64), ("pt_const", p_u8),
                 ("obs_xy", p_f64), ("obs_img", p_i32), ("obs_pt", p_i32),
-                ("pt_err", p_f64)]
+                ("pt_err", p_f64), ("rot_prior", p_f64), ("rot_prior_w", p_f64)]
 
 
 class BAOptions(C.Structure):

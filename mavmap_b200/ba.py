@@ -98,6 +98,8 @@ class FlatProblem:
         self.obs_img = np.ascontiguousarray(obs_img, dtype=np.int32)
         self.obs_pt = np.ascontiguousarray(obs_pt, dtype=np.int32)
         self.pt_err = np.zeros(len(self.pts), dtype=np.float64) if want_pt_err else None
+        self.rot_prior = None        # [n_img, 3] rvec0 of the rotation constraints (constrain_rotation) or None
+        self.rot_prior_w = None      # [n_img] weights, 0 = unconstrained
         assert len(self.poses) == len(self.pose_const) == len(self.img_cam)
         assert len(self.intr) == len(self.cam_model) == len(self.intr_const)
         assert len(self.pts) == len(self.pt_const)
@@ -113,9 +115,16 @@ class FlatProblem:
     def n_obs(self): return len(self.obs_xy)
 
     def copy(self):
-        return FlatProblem(self.poses.copy(), self.pose_const, self.img_cam, self.intr.copy(),
-                           self.cam_model, self.intr_const, self.pts.copy(), self.pt_const,
-                           self.obs_xy, self.obs_img, self.obs_pt, self.pt_err is not None)
+        f = FlatProblem(self.poses.copy(), self.pose_const, self.img_cam, self.intr.copy(),
+                        self.cam_model, self.intr_const, self.pts.copy(), self.pt_const,
+                        self.obs_xy, self.obs_img, self.obs_pt, self.pt_err is not None)
+        f.rot_prior, f.rot_prior_w = self.rot_prior, self.rot_prior_w
+        return f
+
+    def set_rotation_constraints(self, rvec0, weight):
+        self.rot_prior = np.ascontiguousarray(rvec0, dtype=np.float64).reshape(-1, 3)
+        self.rot_prior_w = np.ascontiguousarray(weight, dtype=np.float64).reshape(-1)
+        assert len(self.rot_prior) == len(self.rot_prior_w) == self.n_img
 
     def to_c(self):
         p = BAProblem()
@@ -132,6 +141,8 @@ class FlatProblem:
         p.obs_img = as_ptr(self.obs_img, p_i32)
         p.obs_pt = as_ptr(self.obs_pt, p_i32)
         p.pt_err = as_ptr(self.pt_err, p_f64) if self.pt_err is not None else None
+        if self.rot_prior is not None:
+            p.rot_prior = as_ptr(self.rot_prior, p_f64); p.rot_prior_w = as_ptr(self.rot_prior_w, p_f64)
         return p
 
 
@@ -278,6 +289,24 @@ def solve_flat(flat, c_options, solve_fn=None):
     return summary
 
 
+def _rotate_into_constraint_frame(fm, fixed_image_ids, rotation_constraints):
+    """_bundle_adjustment_add_pose_constraints, first half (bundle_adjustment.cc:402-425): every pose and point of the
+    feature manager is rotated by M = R_FM' R_C taken at the first fixed image (SimilarityTransform3D(M|0):
+    transform_point X' = M X, transform_pose [R|t] -> [R M' | t], similarity_transform.cc:90-121)."""
+    from scipy.spatial.transform import Rotation
+    if not fixed_image_ids:
+        raise ValueError("constrain_rotation needs a fixed image")
+    iid = fixed_image_ids[0]
+    R_fm = Rotation.from_rotvec(np.asarray(fm.rvecs[iid], dtype=np.float64)).as_matrix()
+    R_c = Rotation.from_rotvec(np.asarray(rotation_constraints[iid], dtype=np.float64)).as_matrix()
+    M = R_fm.T @ R_c
+    for k in fm.rvecs:
+        R = Rotation.from_rotvec(np.asarray(fm.rvecs[k], dtype=np.float64)).as_matrix()
+        fm.rvecs[k][:] = Rotation.from_matrix(R @ M.T).as_rotvec()
+    for k in fm.points3D:
+        fm.points3D[k][:] = M @ np.asarray(fm.points3D[k], dtype=np.float64)
+
+
 def bundle_adjustment(feature_manager, free_image_ids, fixed_image_ids, fixed_x_image_ids,
                       options, point3D_errors, rotation_constraints=None, gcp_ids=(),
                       _solve_fn=None):
@@ -285,10 +314,16 @@ def bundle_adjustment(feature_manager, free_image_ids, fixed_image_ids, fixed_x_
     sqrt(final_cost / num_residuals) (.cc:610).  Raises ValueError where the reference
     throws std::invalid_argument (.cc:462-471)."""
     if options.constrain_rotation:
-        raise NotImplementedError("constrain_rotation (bundle_adjustment.cc:390-446) is not "
-                                  "built yet; off by default in the reference (mapper.cc:869-873)")
+        _rotate_into_constraint_frame(feature_manager, fixed_image_ids, rotation_constraints)
     flat, image_ids, camera_ids, point3D_ids = flatten(
         feature_manager, free_image_ids, fixed_image_ids, fixed_x_image_ids, options, gcp_ids)
+    if options.constrain_rotation:                         # .cc:427-443: one residual per FREE image, NULL loss
+        r0 = np.zeros((flat.n_img, 3)); w = np.zeros(flat.n_img)
+        index = {iid: k for k, iid in enumerate(image_ids)}
+        for iid in free_image_ids:
+            r0[index[iid]] = np.asarray(rotation_constraints[iid], dtype=np.float64)
+            w[index[iid]] = options.constrain_rotation_weight
+        flat.set_rotation_constraints(r0, w)
     if flat.n_obs == 0:
         print("No observations in bundle adjustment. Consider relaxing the constraints.")  # .cc:571-573
     summary = solve_flat(flat, to_c_options(options), _solve_fn)

@@ -47,8 +47,8 @@ __global__ void k_pack_scal(const double* __restrict__ loc, const int* __restric
 __global__ void k_pack_step(const double* __restrict__ loc, const int* __restrict__ fail, double* __restrict__ buf) {
   if (threadIdx.x == 0) { buf[0] = loc[1]; buf[1] = loc[3]; buf[2] = loc[4]; buf[3] = *fail ? 1.0 : 0.0; }
 }
-__global__ void k_unpack_step(const double* __restrict__ buf, double* __restrict__ red, int* __restrict__ fail) {
-  if (threadIdx.x == 0) { red[1] = buf[0]; red[3] = buf[1]; red[4] = buf[2]; if (buf[3] > 0.0) *fail = 1; }
+__global__ void k_unpack_step(const double* __restrict__ buf, double* __restrict__ red, int* __restrict__ fail, const double* __restrict__ prior_cost) {
+  if (threadIdx.x == 0) { red[1] = buf[0] + (prior_cost ? prior_cost[0] : 0.0); red[3] = buf[1]; red[4] = buf[2]; if (buf[3] > 0.0) *fail = 1; }
 }
 
 // ------------------------------------------------------------------ setup kernels
@@ -176,6 +176,8 @@ struct mm_ba_session {
   int64_t no_loc() const { return o_hi - o_lo; }
   double* rec_base() const { return rec.p - (size_t)REC * (size_t)o_lo; }      // records are stored for the local observations only
   double* scal() const { return xch.p + scal_off; }
+  // rotation constraints (constrain_rotation): rvec0 and weight per image, residual / Jacobian of the current iterate
+  int n_prior = 0; DevBuf<double> pr_rot0, pr_w, pr_r, pr_J;
   // coarse level of the two-level preconditioner (ba_coarse.cuh)
   int cm = 0, n_agg = 0; std::vector<int> h_agg; std::vector<double> h_pose_mask;
   DevBuf<int> blk_a, blk_b, agg; DevBuf<double> Pc, Ac, gjC, gjR, crc, cqc, cyc; int gj_grid = 0;
@@ -516,6 +518,7 @@ int launch_linearize(mm_ba_session* s) {
         s->img_cam.p, s->cam_model.p, s->pose_mask.p, s->pt_mask.p, loss_of(s->opt), s->rec.p, s->part_cost.p);
   MM_LAUNCH_CHECK();
   k_reduce_sum<<<1, 256, 0, st>>>(s->part_cost.p, s->grid_obs, s->loc.p + 0); MM_LAUNCH_CHECK();
+  if (s->n_prior) { k_rot_prior<<<1, 256, 0, st>>>(s->n_img, s->poses.p, s->pose_mask.p, s->pr_rot0.p, s->pr_w.p, s->pr_r.p, s->pr_J.p, s->loc.p + 6); MM_LAUNCH_CHECK(); }
   return MM_OK;
 }
 // K4: cost at the candidate (poses2/pts2) -> red[1]
@@ -526,9 +529,10 @@ int launch_cost_candidate(mm_ba_session* s) {
       s->img_cam.p, s->cam_model.p, s->pose_mask.p, s->pt_mask.p, loss_of(s->opt), nullptr, s->part_cost.p); MM_LAUNCH_CHECK();
   k_reduce_sum<<<1, 256, 0, st>>>(s->part_cost.p, s->grid_obs, s->loc.p + 1); MM_LAUNCH_CHECK();
   // the step scalars (candidate cost, |step|^2, model cost change) summed over the ranks -> red[1], red[3], red[4]
+  if (s->n_prior) { k_rot_prior<<<1, 256, 0, st>>>(s->n_img, s->poses2.p, s->pose_mask.p, s->pr_rot0.p, s->pr_w.p, nullptr, nullptr, s->loc.p + 7); MM_LAUNCH_CHECK(); }
   k_pack_step<<<1, 32, 0, st>>>(s->loc.p, s->fail.p, s->stepbuf.p); MM_LAUNCH_CHECK();
   { const int rc = all_reduce(s, s->stepbuf.p, 4); if (rc) return rc; }
-  k_unpack_step<<<1, 32, 0, st>>>(s->stepbuf.p, s->red.p, s->fail.p); MM_LAUNCH_CHECK();
+  k_unpack_step<<<1, 32, 0, st>>>(s->stepbuf.p, s->red.p, s->fail.p, s->n_prior ? s->loc.p + 7 : nullptr); MM_LAUNCH_CHECK();
   return MM_OK;
 }
 int launch_scale(mm_ba_session* s) {
@@ -537,7 +541,7 @@ int launch_scale(mm_ba_session* s) {
     k_colnorm_point<<<blocks_for(s->np_loc(), 128), 128, 0, st>>>(s->np_loc(), s->pt_start.p + s->p_lo, s->rec_base(), s->scale_p.p + 3 * (size_t)s->p_lo); MM_LAUNCH_CHECK();
     k_colnorm_cam<<<blocks_for((int64_t)s->n_img * 32, 128), 128, 0, st>>>(s->n_img, s->cam_lo.p, s->cam_hi.p, s->cam_perm.p, s->rec_base(), s->ud.p); MM_LAUNCH_CHECK();
     { const int rc = all_reduce(s, s->ud.p, 6 * (size_t)s->n_img); if (rc) return rc; }
-    k_scale_finish<<<blocks_for(6 * (int64_t)s->n_img, 256), 256, 0, st>>>(6 * s->n_img, s->ud.p, s->scale_c.p); MM_LAUNCH_CHECK();
+    k_scale_finish<<<blocks_for(6 * (int64_t)s->n_img, 256), 256, 0, st>>>(6 * s->n_img, s->ud.p, s->scale_c.p, s->n_prior ? s->pr_J.p : nullptr); MM_LAUNCH_CHECK();
     if (s->refine) {
       MM_CUDA(cudaMemsetAsync(s->sq9.p, 0, sizeof(double) * 9, st));
       k_colnorm_intr<<<s->grid_obs, 256, 0, st>>>(s->n_obs, s->ji.p, s->sq9.p); MM_LAUNCH_CHECK();
@@ -562,8 +566,8 @@ int launch_schur(mm_ba_session* s, bool with_coarse = true) {
   // exchange step: S | rhs | gc | ud | scalars summed over the ranks (nothing to do on one GPU), then the LM diagonal
   k_pack_scal<<<1, 32, 0, st>>>(s->loc.p, s->fail.p, s->scal()); MM_LAUNCH_CHECK();
   { const int rc = all_reduce(s, s->xch.p, s->xch_count); if (rc) return rc; }
-  k_cam_finish<<<blocks_for(6 * (int64_t)s->n_img, 128), 128, 0, st>>>(6 * s->n_img, s->ud.p, s->gc.p, s->scale_c.p, lm, s->S.p, s->dc.p, s->scal(), s->world,
-      s->red.p, s->fail.p); MM_LAUNCH_CHECK();
+  k_cam_finish<<<blocks_for(6 * (int64_t)s->n_img, 128), 128, 0, st>>>(6 * s->n_img, s->ud.p, s->gc.p, s->rhs.p, s->scale_c.p, lm, s->S.p, s->dc.p, s->scal(), s->world,
+      s->red.p, s->fail.p, s->n_prior ? s->pr_r.p : nullptr, s->n_prior ? s->pr_J.p : nullptr, s->n_prior ? s->loc.p + 6 : nullptr); MM_LAUNCH_CHECK();
   k_precond<<<blocks_for(s->n_img, 64), 64, 0, st>>>(s->n_img, s->S.p, s->Minv.p, s->fail.p); MM_LAUNCH_CHECK();
   if (with_coarse) { const int rc = launch_coarse_setup(s); if (rc) return rc; }
   if (s->refine) {
@@ -678,7 +682,7 @@ void trace_push(mm_ba_session* s, int accepted, int lin) {
 int lm_start(mm_ba_session* s) {
   mm_ba_summary& S = s->sum;
   memset(&S, 0, sizeof S);
-  S.num_residuals = 2 * s->n_obs; S.final_cost = INFINITY; S.termination = MM_TERM_NO_CONVERGENCE;
+  S.num_residuals = 2 * s->n_obs + s->n_prior; S.final_cost = INFINITY; S.termination = MM_TERM_NO_CONVERGENCE;
   s->radius = s->opt.initial_trust_region_radius; s->decrease_factor = 2.0; s->iter = 0; s->n_invalid = 0;
   s->finished = false; s->started = true; s->scaled = false;
   if (s->n_obs == 0) { S.termination = MM_TERM_EMPTY; S.initial_cost = S.final_cost = 0.0; S.return_value = NAN; s->finished = true; return MM_OK; }
@@ -864,6 +868,15 @@ int mm_ba_session_create_sharded(const mm_ba_problem* P, const mm_ba_options* op
     if (cudaMemcpy(s->pose_mask.p, pm.data(), sizeof(double) * pm.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(s->img_cam.p, P->img_cam, sizeof(int) * (size_t)P->n_img, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(s->cam_model.p, P->cam_model, sizeof(int) * (size_t)P->n_cam, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("mask upload failed"); return fail_out(MM_ERR_CUDA); } }
+  if (P->rot_prior && P->rot_prior_w) {
+    for (int i = 0; i < P->n_img; ++i) if (P->rot_prior_w[i] != 0.0) s->n_prior++;
+    if (s->n_prior) {
+      if (refine) { set_error("constrain_rotation together with refine_camera_params is not available on the device engine"); return fail_out(MM_ERR_UNSUPPORTED); }
+      A(s->pr_rot0, 3 * n_img); A(s->pr_w, n_img); A(s->pr_r, n_img); A(s->pr_J, 3 * n_img);
+      if (cudaMemcpy(s->pr_rot0.p, P->rot_prior, sizeof(double) * 3 * (size_t)P->n_img, cudaMemcpyHostToDevice) != cudaSuccess ||
+          cudaMemcpy(s->pr_w.p, P->rot_prior_w, sizeof(double) * (size_t)P->n_img, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("constraint upload failed"); return fail_out(MM_ERR_CUDA); }
+    }
+  }
   cudaMemsetAsync(s->fail.p, 0, sizeof(int), s->stream);
   cudaMemsetAsync(s->red.p, 0, sizeof(double) * 8, s->stream);
   cudaMemsetAsync(s->loc.p, 0, sizeof(double) * 8, s->stream);

@@ -232,9 +232,54 @@ __global__ void k_colnorm_cam(int n_img, const int* __restrict__ cam_lo, const i
     sums[6 * (size_t)w + lane] = v;
   }
 }
-__global__ void k_scale_finish(int n, const double* __restrict__ sums, double* __restrict__ scale_c) {
+__global__ void k_scale_finish(int n, const double* __restrict__ sums, double* __restrict__ scale_c, const double* __restrict__ pr_J) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) scale_c[i] = 1.0 / (1.0 + sqrt(sums[i]));
+  if (i >= n) return;
+  double v = sums[i];
+  const int img = i / 6, a = i - 6 * img;
+  if (pr_J && a < 3) { const double j = pr_J[3 * (size_t)img + a]; v += j * j; }       // rotation-constraint rows
+  scale_c[i] = 1.0 / (1.0 + sqrt(v));
+}
+
+// ---- rotation constraints (constrain_rotation, bundle_adjustment.cc:390-446; cost functor .cc:57-111) ----------
+// r = weight * sqrt(sum_i (R_a(i) - R0_b(i))^2) over the reference's nine index pairs (||R' - R0||_F with the index quirk
+// of .cc:103), no loss function; d r / d rvec in closed form with d R / d w_k = [Jl e_k]x R.  One residual per image.
+__device__ __forceinline__ double rot_prior_eval(const double* w, const double* w0, double weight, double* J) {
+  const int PA[9] = { 0, 1, 2, 3, 4, 5, 6, 2, 8 }, PB[9] = { 0, 3, 6, 1, 4, 7, 2, 5, 8 };
+  double R[9], Jl[9], R0[9], J0[9];
+  rotation_and_left_jacobian(w, R, Jl); rotation_and_left_jacobian(w0, R0, J0);
+  double q = 0.0, d[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { d[i] = R[PA[i]] - R0[PB[i]]; q += d[i] * d[i]; }
+  const double n = sqrt(q);
+  if (J) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double v0 = Jl[k], v1 = Jl[3 + k], v2 = Jl[6 + k];
+      double dR[9];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { dR[c] = v1 * R[6 + c] - v2 * R[3 + c]; dR[3 + c] = v2 * R[c] - v0 * R[6 + c]; dR[6 + c] = v0 * R[3 + c] - v1 * R[c]; }
+      double sdr = 0.0;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) sdr += d[i] * dR[PA[i]];
+      J[k] = n > 0.0 ? weight * sdr / n : 0.0;
+    }
+  }
+  return weight * n;
+}
+// one block: residual, masked Jacobian (unscaled) and the cost 1/2 sum r^2 of all rotation constraints
+__global__ void k_rot_prior(int n_img, const double* __restrict__ poses, const double* __restrict__ pose_mask, const double* __restrict__ rot0,
+                            const double* __restrict__ weight, double* __restrict__ r_out, double* __restrict__ J_out, double* __restrict__ cost_out) {
+  __shared__ double red[32];
+  double c = 0.0;
+  for (int i = threadIdx.x; i < n_img; i += blockDim.x) {
+    double r = 0.0, J[3] = {0, 0, 0};
+    if (weight[i] != 0.0) r = rot_prior_eval(poses + 6 * (size_t)i, rot0 + 3 * (size_t)i, weight[i], J_out ? J : nullptr);
+    c += 0.5 * r * r;
+    if (r_out) { r_out[i] = r; const double m = pose_mask[6 * (size_t)i]; J_out[3 * (size_t)i] = J[0] * m; J_out[3 * (size_t)i + 1] = J[1] * m; J_out[3 * (size_t)i + 2] = J[2] * m; }
+  }
+  c = block_sum(c, red);
+  if (threadIdx.x == 0) cost_out[0] = c;
 }
 
 // ---- K2a: per-point blocks ------------------------------------------------------------------
@@ -458,22 +503,30 @@ __global__ void __launch_bounds__(128, 3) k_schur_cam(
 // after the camera pass (and, when the points are sharded across GPUs, after the all-reduce of S | rhs | gc | ud | scal):
 // LM diagonal of every pose parameter onto the diagonal blocks, gradient max-norm, and the reduced scalars.
 // scal: [0] cost  [1] |x|^2  [2] failure count  [3 .. 3 + world) per-rank max |g_point|
-__global__ void k_cam_finish(int n6, const double* __restrict__ ud, const double* __restrict__ gc, const double* __restrict__ scale_c, LMDiag lm,
+__global__ void k_cam_finish(int n6, const double* __restrict__ ud, double* __restrict__ gc, double* __restrict__ rhs, const double* __restrict__ scale_c, LMDiag lm,
                              double* __restrict__ S, double* __restrict__ dc_out, const double* __restrict__ scal, int world,
-                             double* __restrict__ red, int* __restrict__ fail) {
+                             double* __restrict__ red, int* __restrict__ fail,
+                             const double* __restrict__ pr_r, const double* __restrict__ pr_J, const double* __restrict__ prior_cost) {
   __shared__ double sred[32];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double gm = 0.0;
   if (i < n6) {
     const int img = i / 6, a = i - 6 * img;
-    const double d = fmin(fmax(ud[i], lm.min_diag), lm.max_diag) / lm.radius;
+    double udv = ud[i], gcv = gc[i];
+    if (pr_J && a < 3) {          // the image's rotation-constraint row: J'J into the rvec block, J'r into gradient and rhs
+      const double ja = pr_J[3 * (size_t)img + a] * scale_c[i], r = pr_r[img];
+      udv += ja * ja; gcv += ja * r; gc[i] = gcv; rhs[i] += ja * r;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) S[36 * (size_t)img + 6 * a + c] += ja * pr_J[3 * (size_t)img + c] * scale_c[6 * (size_t)img + c];
+    }
+    const double d = fmin(fmax(udv, lm.min_diag), lm.max_diag) / lm.radius;
     dc_out[i] = d;
     S[36 * (size_t)img + 7 * a] += d;
-    gm = fabs(gc[i] / scale_c[i]);
+    gm = fabs(gcv / scale_c[i]);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     for (int r = 0; r < world; ++r) gm = fmax(gm, scal[3 + r]);
-    red[0] = scal[0]; red[5] = scal[1];
+    red[0] = scal[0] + (prior_cost ? prior_cost[0] : 0.0); red[5] = scal[1];
     if (scal[2] > 0.0) *fail = 1;
   }
   gm = block_max(gm, sred);

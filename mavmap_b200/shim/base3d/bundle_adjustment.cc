@@ -48,6 +48,31 @@ mm_ba_options to_options(const BundleAdjustmentOptions& o) {
 
 }  // namespace
 
+// angle-axis <-> rotation matrix (row-major), the conventions of Eigen::AngleAxisd used by the reference (util/math.h)
+static void rvec_to_matrix(const Eigen::Vector3d& r, double* R) {
+  const double x = r(0), y = r(1), z = r(2), t2 = x * x + y * y + z * z;
+  if (!(t2 > 0.0)) { for (int k = 0; k < 9; ++k) R[k] = (k % 4 == 0) ? 1.0 : 0.0; return; }
+  const double t = std::sqrt(t2), s = std::sin(t), c = std::cos(t), kx = x / t, ky = y / t, kz = z / t, v = 1.0 - c;
+  R[0] = c + kx * kx * v;      R[1] = kx * ky * v - kz * s; R[2] = kx * kz * v + ky * s;
+  R[3] = ky * kx * v + kz * s; R[4] = c + ky * ky * v;      R[5] = ky * kz * v - kx * s;
+  R[6] = kz * kx * v - ky * s; R[7] = kz * ky * v + kx * s; R[8] = c + kz * kz * v;
+}
+static void matrix_to_rvec(const double* R, Eigen::Vector3d& r) {
+  // via the unit quaternion (as Eigen::AngleAxis(Matrix3) does): angle in [0, pi]
+  double q[4];
+  const double tr = R[0] + R[4] + R[8];
+  if (tr > 0.0) { const double s = std::sqrt(tr + 1.0) * 2.0; q[0] = 0.25 * s; q[1] = (R[7] - R[5]) / s; q[2] = (R[2] - R[6]) / s; q[3] = (R[3] - R[1]) / s; }
+  else if (R[0] > R[4] && R[0] > R[8]) { const double s = std::sqrt(1.0 + R[0] - R[4] - R[8]) * 2.0; q[0] = (R[7] - R[5]) / s; q[1] = 0.25 * s; q[2] = (R[1] + R[3]) / s; q[3] = (R[2] + R[6]) / s; }
+  else if (R[4] > R[8]) { const double s = std::sqrt(1.0 + R[4] - R[0] - R[8]) * 2.0; q[0] = (R[2] - R[6]) / s; q[1] = (R[1] + R[3]) / s; q[2] = 0.25 * s; q[3] = (R[5] + R[7]) / s; }
+  else { const double s = std::sqrt(1.0 + R[8] - R[0] - R[4]) * 2.0; q[0] = (R[3] - R[1]) / s; q[1] = (R[2] + R[6]) / s; q[2] = (R[5] + R[7]) / s; q[3] = 0.25 * s; }
+  if (q[0] < 0.0) for (int k = 0; k < 4; ++k) q[k] = -q[k];
+  const double n = std::sqrt(q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  if (n < 1e-300) { r(0) = r(1) = r(2) = 0.0; return; }
+  const double angle = 2.0 * std::atan2(n, q[0]);
+  r(0) = angle * q[1] / n; r(1) = angle * q[2] / n; r(2) = angle * q[3] / n;
+}
+
+
 double pose_refinement(Eigen::Vector3d& rvec, Eigen::Vector3d& tvec, std::vector<double>& camera_params,
                        const std::vector<Eigen::Vector2d>& points2D, std::vector<Eigen::Vector3d>& points3D,
                        const std::vector<bool>& inlier_mask, const BundleAdjustmentOptions& options) {
@@ -74,14 +99,30 @@ double bundle_adjustment(FeatureManager& fm, const std::vector<size_t>& free_ima
                          const BundleAdjustmentOptions& options, std::unordered_map<size_t, double>& point3D_errors,
                          const std::unordered_map<size_t, Eigen::Vector3d>& rotation_constraints,
                          const std::set<size_t>& gcp_ids) {
-  (void)rotation_constraints;
   const size_t num_fixed_params = fixed_image_ids.size() * 6 + fixed_x_image_ids.size() + gcp_ids.size() * 3;
   if (num_fixed_params < 7)                                                   // .cc:459-466
     throw std::invalid_argument("At least 7 parameters should be set as fixed to avoid datum defects resulting in a singular Jacobian.");
   if (options.min_track_len < 2)                                              // .cc:468-471
     throw std::invalid_argument("Minimum track length must be >= 2 in order build valid bundle adjustment problem.");
-  if (options.constrain_rotation)
-    throw std::runtime_error("mavmap_b200: constrain_rotation (bundle_adjustment.cc:390-446) is not built yet");
+  if (options.constrain_rotation) {
+    // _bundle_adjustment_add_pose_constraints (.cc:390-446), first half: rotate EVERY pose and point of the feature manager
+    // into the frame of the constraints, M = R_FM' R_C taken at the first fixed image (.cc:402-425).
+    // SimilarityTransform3D(M|0): transform_point X' = M X; transform_pose [R|t] -> [R M' | t].
+    if (fixed_image_ids.empty()) throw std::invalid_argument("constrain_rotation needs a fixed image");
+    double Rf[9], Rc[9], M[9];
+    rvec_to_matrix(fm.rvecs[fixed_image_ids[0]], Rf); rvec_to_matrix(rotation_constraints.at(fixed_image_ids[0]), Rc);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) M[3 * i + j] = Rf[i] * Rc[j] + Rf[3 + i] * Rc[3 + j] + Rf[6 + i] * Rc[6 + j];
+    for (auto& kv : fm.rvecs) {
+      double R[9], R2[9];
+      rvec_to_matrix(kv.second, R);
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R2[3 * i + j] = R[3 * i] * M[3 * j] + R[3 * i + 1] * M[3 * j + 1] + R[3 * i + 2] * M[3 * j + 2];
+      matrix_to_rvec(R2, kv.second);
+    }
+    for (auto& kv : fm.points3D) {
+      const double x = kv.second(0), y = kv.second(1), z = kv.second(2);
+      kv.second(0) = M[0] * x + M[1] * y + M[2] * z; kv.second(1) = M[3] * x + M[4] * y + M[5] * z; kv.second(2) = M[6] * x + M[7] * y + M[8] * z;
+    }
+  }
 
   // _bundle_adjustment_extract_data (.cc:228-286): free, fixed_x, fixed
   struct Obs { size_t p2, p3; };
@@ -163,6 +204,16 @@ double bundle_adjustment(FeatureManager& fm, const std::vector<size_t>& free_ima
   P.pts = pts.empty() ? dummy_d : pts.data(); P.pt_const = pt_const.empty() ? dummy_u : pt_const.data();
   P.obs_xy = obs_xy.empty() ? dummy_d : obs_xy.data(); P.obs_img = obs_img.empty() ? dummy_i : obs_img.data(); P.obs_pt = obs_pt.empty() ? dummy_i : obs_pt.data();
   P.pt_err = options.update_point3D_errors && !pt_err.empty() ? pt_err.data() : nullptr;
+  std::vector<double> rot_prior(3 * n_img, 0.0), rot_prior_w(n_img, 0.0);
+  if (options.constrain_rotation) {                                           // .cc:427-443: one residual per FREE image
+    for (size_t image_id : free_image_ids) {
+      const Eigen::Vector3d& r0 = rotation_constraints.at(image_id);
+      const int32_t ii = img_index[image_id];
+      for (int cidx = 0; cidx < 3; ++cidx) rot_prior[3 * ii + cidx] = r0(cidx);
+      rot_prior_w[ii] = options.constrain_rotation_weight;
+    }
+    P.rot_prior = rot_prior.data(); P.rot_prior_w = rot_prior_w.data();
+  }
   if (P.n_obs == 0) std::cout << "No observations in bundle adjustment. Consider relaxing the constraints." << std::endl;   // .cc:571-573
 
   mm_ba_options c = to_options(options); mm_ba_summary s;

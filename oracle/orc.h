@@ -67,6 +67,8 @@ int orc_pose_refine(double* rvec, double* tvec, int model_code, const double* pa
                     mm_ba_summary* summary, double* ret);
 /* cost only: 1/2 sum rho(|r|^2) at the problem's current parameters */
 double orc_ba_cost(const mm_ba_problem* problem, const mm_ba_options* opt);
+/* BARotationConstraintCostFunction (bundle_adjustment.cc:57-111): residual and d r / d rvec (J may be NULL) */
+double orc_rot_prior(const double* rvec, const double* rvec0, double weight, double* J);
 void orc_ba_options_default(mm_ba_options* o);
 int  orc_num_threads(void);
 

@@ -35,6 +35,8 @@ def lib():
         L.orc_ba_options_default.argtypes = [C.POINTER(BAOptions)]
         L.orc_ba_solve.restype = C.c_int
         L.orc_ba_solve.argtypes = [C.POINTER(_abi.BAProblem), C.POINTER(BAOptions), C.POINTER(BASummary)]
+        L.orc_rot_prior.restype = C.c_double
+        L.orc_rot_prior.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_double)]
         L.orc_ba_cost.restype = C.c_double
         L.orc_ba_cost.argtypes = [C.POINTER(_abi.BAProblem), C.POINTER(BAOptions)]
         L.orc_pose_refine.restype = C.c_int
@@ -222,6 +224,14 @@ def solve_flat(flat, c_options):
 def ba_cost(flat, c_options):
     cp = flat.to_c()
     return lib().orc_ba_cost(C.byref(cp), C.byref(c_options))
+
+
+def rot_prior(rvec, rvec0, weight):
+    """BARotationConstraintCostFunction (bundle_adjustment.cc:57-111): (residual, d residual / d rvec [3])"""
+    a = np.ascontiguousarray(rvec, dtype=np.float64); b = np.ascontiguousarray(rvec0, dtype=np.float64); J = np.zeros(3)
+    p = lambda x: x.ctypes.data_as(C.POINTER(C.c_double))
+    r = lib().orc_rot_prior(p(a), p(b), float(weight), p(J))
+    return r, J
 
 
 def bundle_adjustment(fm, free, fixed, fixed_x, options, point3D_errors, rotation_constraints=None, gcp_ids=()):

@@ -85,7 +85,53 @@ typedef struct {
   double *step_c, *step_p;
   /* skyline storage of the reduced system */
   int64_t* rowptr; int* first; double* S; double* rhs; int* reach;
+  /* rotation constraints (bundle_adjustment.cc:390-446): residual and d r / d rvec per image (scaled with J) */
+  double *pr_r, *pr_J; int n_prior;
 } ba_t;
+
+/* ---- BARotationConstraintCostFunction (bundle_adjustment.cc:57-111, bundle_adjustment.h:191-209) --------------
+ * r = weight * sqrt(sum_i (R_a(i) - R0_b(i))^2) over the nine index pairs the reference uses: ||R' - R0||_F, except that
+ * the 8th term compares R[0][2] (not R[2][1]) with R0[1][2] (.cc:103).  Ceres differentiates it with Jets; the same
+ * derivative in closed form is  d R / d w_k = [Jl e_k]x R  (Jl = left Jacobian of SO(3)).  Row-major indices. */
+static const int PR_A[9] = { 0, 1, 2, 3, 4, 5, 6, 2, 8 }, PR_B[9] = { 0, 3, 6, 1, 4, 7, 2, 5, 8 };
+static void so3_R_Jl(const double* w, double* R, double* Jl) {
+  const double t2 = w[0]*w[0] + w[1]*w[1] + w[2]*w[2];
+  double A = 1.0, Bc = 0.5, Dd = 1.0/6.0;
+  if (t2 > 0.0) {
+    const double t = sqrt(t2), sh = sin(0.5*t);
+    A = sin(t)/t; Bc = 2.0*sh*sh/t2;
+    Dd = t < 0.05 ? 1.0/6.0 - t2/120.0 + t2*t2/5040.0 - t2*t2*t2/362880.0 : (t - sin(t))/(t2*t);
+  } else { A = 1.0; Bc = 0.0; Dd = 0.0; }
+  const double x = w[0], y = w[1], z = w[2];
+  R[0] = 1.0 - Bc*(y*y + z*z); R[1] = -A*z + Bc*x*y; R[2] = A*y + Bc*x*z;
+  R[3] = A*z + Bc*x*y; R[4] = 1.0 - Bc*(x*x + z*z); R[5] = -A*x + Bc*y*z;
+  R[6] = -A*y + Bc*x*z; R[7] = A*x + Bc*y*z; R[8] = 1.0 - Bc*(x*x + y*y);
+  Jl[0] = 1.0 - Dd*(y*y + z*z); Jl[1] = -Bc*z + Dd*x*y; Jl[2] = Bc*y + Dd*x*z;
+  Jl[3] = Bc*z + Dd*x*y; Jl[4] = 1.0 - Dd*(x*x + z*z); Jl[5] = -Bc*x + Dd*y*z;
+  Jl[6] = -Bc*y + Dd*x*z; Jl[7] = Bc*x + Dd*y*z; Jl[8] = 1.0 - Dd*(x*x + y*y);
+}
+double orc_rot_prior(const double* rvec, const double* rvec0, double weight, double* J /* [3] or NULL */) {
+  double R[9], Jl[9], R0[9], J0[9];
+  so3_R_Jl(rvec, R, Jl); so3_R_Jl(rvec0, R0, J0);
+  double q = 0.0, d[9];
+  for (int i = 0; i < 9; ++i) { d[i] = R[PR_A[i]] - R0[PR_B[i]]; q += d[i]*d[i]; }
+  const double n = sqrt(q);
+  if (J) for (int k = 0; k < 3; ++k) {
+    /* dR = [v]x R with v = Jl[:,k] */
+    const double v0 = Jl[k], v1 = Jl[3+k], v2 = Jl[6+k];
+    double dR[9];
+    for (int c = 0; c < 3; ++c) {
+      dR[c]     = v1*R[6+c] - v2*R[3+c];
+      dR[3 + c] = v2*R[c]   - v0*R[6+c];
+      dR[6 + c] = v0*R[3+c] - v1*R[c];
+    }
+    double s = 0.0;
+    for (int i = 0; i < 9; ++i) s += d[i] * dR[PR_A[i]];
+    J[k] = n > 0.0 ? weight * s / n : 0.0;
+  }
+  return weight * n;
+}
+static int has_prior(const mm_ba_problem* P, int i) { return P->rot_prior && P->rot_prior_w && P->rot_prior_w[i] != 0.0; }
 
 /* ---- loss (loss_function.cc CauchyLoss; corrector.cc) ---------------------- */
 static inline void loss_eval(const mm_ba_options* O, double s, double* rho0, double* sqrt_rho1) {
@@ -109,6 +155,10 @@ static double eval_cost(const ba_t* B, const double* poses, const double* intr, 
     double rho0, sr; loss_eval(B->O, r[0]*r[0] + r[1]*r[1], &rho0, &sr);
     cost += 0.5 * rho0;
   }
+  for (int i = 0; i < P->n_img; ++i) if (has_prior(P, i)) {          /* NULL loss (.cc:442) */
+    const double r = orc_rot_prior(poses + 6*(size_t)i, P->rot_prior + 3*(size_t)i, P->rot_prior_w[i], NULL);
+    cost += 0.5 * r * r;
+  }
   return cost;
 }
 
@@ -131,6 +181,14 @@ static double eval_full(ba_t* B) {        /* cost, robustified r and J (unscaled
     }
     B->r[2*o] = sr * r[0]; B->r[2*o+1] = sr * r[1];
   }
+  for (int i = 0; i < B->n_img && B->pr_r; ++i) {
+    B->pr_r[i] = 0.0; B->pr_J[3*(size_t)i] = B->pr_J[3*(size_t)i+1] = B->pr_J[3*(size_t)i+2] = 0.0;
+    if (!has_prior(P, i)) continue;
+    double J[3];
+    B->pr_r[i] = orc_rot_prior(B->poses + 6*(size_t)i, P->rot_prior + 3*(size_t)i, P->rot_prior_w[i], J);
+    for (int k = 0; k < 3; ++k) B->pr_J[3*(size_t)i + k] = B->act_c[6*(size_t)i + k] ? J[k] : 0.0;
+    cost += 0.5 * B->pr_r[i] * B->pr_r[i];
+  }
   return cost;
 }
 
@@ -150,6 +208,10 @@ static void column_sums(const ba_t* B, int squared, double* out_c, double* out_p
       for (int k = 0; k < 3; ++k) op[k] += squared ? j[15+k]*j[15+k] : j[15+k]*w;
     }
   }
+  for (int i = 0; i < B->n_img && B->pr_r; ++i) for (int k = 0; k < 3; ++k) {
+    const double j = B->pr_J[3*(size_t)i + k];
+    out_c[6*(size_t)i + k] += squared ? j*j : j*B->pr_r[i];
+  }
 }
 
 static void scale_jacobian(ba_t* B) {      /* jacobian->ScaleColumns(scale) */
@@ -165,6 +227,7 @@ static void scale_jacobian(ba_t* B) {      /* jacobian->ScaleColumns(scale) */
       for (int k = 0; k < 3; ++k) j[15+k] *= B->scale_p[3*(size_t)pt + k];
     }
   }
+  for (int i = 0; i < B->n_img && B->pr_r; ++i) for (int k = 0; k < 3; ++k) B->pr_J[3*(size_t)i + k] *= B->scale_c[6*(size_t)i + k];
 }
 
 /* ---- skyline reduced system -------------------------------------------------- */
@@ -290,6 +353,10 @@ static int assemble_and_factor(ba_t* B) {
     free(W); free(Y); free(cols);
   }
   if (fail) return 0;
+  for (int i = 0; i < n_img && B->pr_r; ++i) {      /* rotation-constraint rows touch one rvec block only */
+    const double* j = B->pr_J + 3*(size_t)i;
+    for (int a = 0; a < 3; ++a) { B->rhs[6*i + a] += j[a] * B->pr_r[i]; for (int b = 0; b <= a; ++b) *S_at(B, 6*i + a, 6*i + b) += j[a] * j[b]; }
+  }
   for (int i = 0; i < nc; ++i) *S_at(B, i, i) += B->diag_c[i];
   { const char* dump = getenv("ORC_DUMP_S");     /* debugging aid: reduced system in skyline form */
     static int dump_count = 0;
@@ -407,6 +474,11 @@ static int compute_step(ba_t* B, double radius, int reuse_diagonal, double* mode
       mcc -= m * (B->r[2*o + row] + m / 2.0);
     }
   }
+  for (int i = 0; i < n_img && B->pr_r; ++i) {
+    double m = 0.0;
+    for (int k = 0; k < 3; ++k) m += B->pr_J[3*(size_t)i + k] * B->step_c[6*(size_t)i + k];
+    mcc -= m * (B->pr_r[i] + m / 2.0);
+  }
   *model_cost_change = mcc;
   return 1;
 }
@@ -488,6 +560,8 @@ int orc_ba_solve(mm_ba_problem* P, const mm_ba_options* O, mm_ba_summary* S) {
   B->diag_c = malloc(sizeof(double)*(size_t)nc);  B->diag_p = malloc(sizeof(double)*np3 + 8);
   B->g_c = malloc(sizeof(double)*(size_t)nc);     B->g_p = malloc(sizeof(double)*np3 + 8);
   B->step_c = malloc(sizeof(double)*(size_t)nc);  B->step_p = malloc(sizeof(double)*np3 + 8);
+  for (int i = 0; i < P->n_img; ++i) if (has_prior(P, i)) B->n_prior++;
+  if (B->n_prior) { B->pr_r = calloc((size_t)P->n_img, sizeof(double)); B->pr_J = calloc(3*(size_t)P->n_img, sizeof(double)); S->num_residuals += B->n_prior; }
   rc = build_structure(B);
   if (rc != MM_OK || !B->J) { rc = MM_ERR_ALLOC; goto done; }
 
@@ -576,7 +650,7 @@ done:
   free(B->poses); free(B->poses2); free(B->intr); free(B->intr2); free(B->pts); free(B->pts2);
   free(B->J); free(B->r); free(B->scale_c); free(B->scale_p); free(B->diag_c); free(B->diag_p);
   free(B->g_c); free(B->g_p); free(B->step_c); free(B->step_p);
-  free(B->rowptr); free(B->first); free(B->S); free(B->rhs); free(B->reach);
+  free(B->rowptr); free(B->first); free(B->S); free(B->rhs); free(B->reach); free(B->pr_r); free(B->pr_J);
   return rc;
 }
 

@@ -248,3 +248,30 @@ def test_pose_refinement_single_kernel_path(mm, orc, model, monkeypatch):
     for _ in range(20):
         mm.pose_refinement(r.copy(), t.copy(), params, uv, X, mask, opt)
     print("pose_refinement latency: %.0f us per call (%d points)" % ((time.perf_counter() - t0) / 20 * 1e6, int(mask.sum())))
+
+
+def test_rotation_constraints_parity(mm, orc):
+    """constrain_rotation (bundle_adjustment.cc:390-446, functor .cc:57-111 with its index quirk): device engine against the
+    oracle, flat problem and reference call surface (which first rotates the whole feature manager)."""
+    from test_oracle_ba import _constraint_scene
+    flat, _ = synthetic.make_ba_problem(outlier_frac=0.0, **synthetic.BA_CONFIGS["small"])
+    rng = np.random.default_rng(3)
+    from scipy.spatial.transform import Rotation
+    r0 = np.stack([(Rotation.from_rotvec(p[:3]).inv() * Rotation.from_rotvec(rng.normal(0, 0.01, 3))).as_rotvec() for p in flat.poses])
+    w = np.full(flat.n_img, 30.0); w[:2] = 0.0                       # the two gauge images carry no constraint (.cc:428: free images only)
+    flat.set_rotation_constraints(r0, w)
+    g, c, sg, so = _both(orc, flat, 10)
+    _assert_parity(g, c, sg, so)
+    assert sg["num_residuals"] == 2 * flat.n_obs + flat.n_img - 2
+    plain = flat.copy(); plain.rot_prior = plain.rot_prior_w = None
+    assert abs(solve_flat(plain, default_c_options()).as_dict()["initial_cost"] - sg["initial_cost"]) > 1e-6 * sg["initial_cost"]
+    # call surface
+    fm_g, ids, cons = _constraint_scene(); fm_o, _, _ = _constraint_scene()
+    opt = mm.BundleAdjustmentOptions(print_summary=False, max_num_iterations=12, function_tolerance=0, gradient_tolerance=0,
+                                     constrain_rotation=True, constrain_rotation_weight=50.0)
+    cons[ids[0]] = np.array([0.2, -0.1, 0.3])                        # a real change of frame this time
+    rg = mm.bundle_adjustment(fm_g, ids[2:], ids[:1], ids[1:2], opt, {}, cons)
+    ro = orc.bundle_adjustment(fm_o, ids[2:], ids[:1], ids[1:2], opt, {}, cons)
+    assert abs(rg - ro) <= REL * ro
+    for i in ids:
+        np.testing.assert_allclose(fm_g.rvecs[i], fm_o.rvecs[i], atol=2e-6); np.testing.assert_allclose(fm_g.tvecs[i], fm_o.tvecs[i], atol=2e-6)

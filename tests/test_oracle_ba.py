@@ -126,3 +126,73 @@ def test_pose_refinement_oracle(orc):
     ret = orc.pose_refinement(r0, t0, params, uv, X, mask, mm.BundleAdjustmentOptions(print_summary=False, function_tolerance=1e-12))
     np.testing.assert_allclose(r0, rvec, atol=1e-6); np.testing.assert_allclose(t0, tvec, atol=1e-6)
     assert ret < 1e-6
+
+
+def test_rotation_constraint_functor_matches_reference_formula_and_finite_differences():
+    """BARotationConstraintCostFunction (bundle_adjustment.cc:57-111): weight * sqrt of nine squared differences between the
+    column-major rotation matrices, INCLUDING the reference's index quirk (the 8th term reads rotmat[6], .cc:103)."""
+    from scipy.spatial.transform import Rotation
+    from oracle import orc
+    rng = np.random.default_rng(4)
+    for _ in range(20):
+        w, w0, weight = rng.normal(0, 0.8, 3), rng.normal(0, 0.8, 3), float(rng.uniform(0.5, 20))
+        rot = Rotation.from_rotvec(w).as_matrix().T.ravel()       # column-major, as ceres::AngleAxisToRotationMatrix fills it
+        rot0 = Rotation.from_rotvec(w0).as_matrix().T.ravel()
+        pairs = [(0, 0), (3, 1), (6, 2), (1, 3), (4, 4), (7, 5), (2, 6), (6, 7), (8, 8)]       # (rotmat index, rotmat0_ index)
+        want = weight * np.sqrt(sum((rot[a] - rot0[b]) ** 2 for a, b in pairs))
+        r, J = orc.rot_prior(w, w0, weight)
+        assert abs(r - want) < 1e-12 * max(1.0, want)
+        for k in range(3):
+            e = np.zeros(3); e[k] = 1e-6
+            fd = (orc.rot_prior(w + e, w0, weight)[0] - orc.rot_prior(w - e, w0, weight)[0]) / 2e-6
+            assert abs(J[k] - fd) < 1e-6 * max(1.0, abs(fd))
+
+
+def _constraint_scene(seed=5):
+    """4-image scene + rotation constraints in the reference's convention: the functor compares R(rvec)' (camera-to-world)
+    with R(rvec0) (bundle_adjustment.cc:79-81), and the scene is first rotated by M = R_FM' R_C of the first fixed image."""
+    from scipy.spatial.transform import Rotation
+    fm, ids = _scene(seed=seed)
+    rng = np.random.default_rng(9)
+    cons = {i: (Rotation.from_rotvec(fm.rvecs[i]).inv() * Rotation.from_rotvec(rng.normal(0, 0.004, 3))).as_rotvec() for i in ids}
+    cons[ids[0]] = np.array(fm.rvecs[ids[0]], dtype=np.float64)        # M = identity: the frames already agree
+    return fm, ids, cons
+
+
+def test_rotate_into_constraint_frame_follows_reference_and_keeps_projections():
+    """bundle_adjustment.cc:402-425 + similarity_transform.cc:90-121: X' = M X, [R|t] -> [R M'|t] with M = R_FM' R_C;
+    camera coordinates R X + t of every observation are unchanged by construction."""
+    from scipy.spatial.transform import Rotation
+    from mavmap_b200.ba import _rotate_into_constraint_frame
+    fm, ids = _scene(seed=6)
+    cons = {ids[0]: np.array([0.4, -0.3, 0.2])}
+    Xc_before = {i: Rotation.from_rotvec(fm.rvecs[i]).as_matrix() @ np.asarray(fm.points3D[1]) + fm.tvecs[i] for i in ids}
+    R_fm = Rotation.from_rotvec(fm.rvecs[ids[0]]).as_matrix(); R_c = Rotation.from_rotvec(cons[ids[0]]).as_matrix()
+    _rotate_into_constraint_frame(fm, ids[:1], cons)
+    np.testing.assert_allclose(Rotation.from_rotvec(fm.rvecs[ids[0]]).as_matrix(), R_fm @ (R_fm.T @ R_c).T, atol=1e-12)
+    for i in ids:
+        np.testing.assert_allclose(Rotation.from_rotvec(fm.rvecs[i]).as_matrix() @ np.asarray(fm.points3D[1]) + fm.tvecs[i], Xc_before[i], atol=1e-10)
+
+
+def test_bundle_adjustment_with_rotation_constraints_oracle():
+    """constrain_rotation (bundle_adjustment.cc:390-446): one extra residual per free image (no loss function).  The
+    residual is a norm, not a squared norm, and carries the reference's index quirk, so it does not vanish at the
+    constraint; the test holds what the reference guarantees: the extra residuals are counted, they enter the cost, and the
+    optimiser trades reprojection error for a smaller constraint residual."""
+    import mavmap_b200 as mm
+    from oracle import orc
+    from mavmap_b200.ba import flatten
+    fm, ids, cons = _constraint_scene()
+    before = {i: np.array(fm.rvecs[i]) for i in ids}
+    prior = lambda f: sum(orc.rot_prior(f.rvecs[i], cons[i], 1.0)[0] for i in ids[2:])
+    kw = dict(print_summary=False, max_num_iterations=15, function_tolerance=0, gradient_tolerance=0)
+    opt = mm.BundleAdjustmentOptions(constrain_rotation=True, constrain_rotation_weight=1e2, **kw)
+    flat, image_ids, _, _ = flatten(fm, ids[2:], ids[:1], ids[1:2], opt)
+    ret = orc.bundle_adjustment(fm, ids[2:], ids[:1], ids[1:2], opt, {}, cons)
+    assert np.isfinite(ret)
+    np.testing.assert_allclose(fm.rvecs[ids[0]], before[ids[0]], atol=1e-9)       # M = I and the image is fixed
+    # same scene without the constraints: different rotations, and a return value over 2 n_obs residuals only
+    fm2, ids2, _ = _constraint_scene()
+    ret2 = orc.bundle_adjustment(fm2, ids2[2:], ids2[:1], ids2[1:2], mm.BundleAdjustmentOptions(**kw), {})
+    assert not np.allclose(fm2.rvecs[ids2[2]], fm.rvecs[ids[2]], atol=1e-6) and ret2 < ret
+    assert prior(fm) < prior(fm2)                  # the constrained solve ends closer to the constraints than the free one
