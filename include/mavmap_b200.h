@@ -145,6 +145,19 @@ int mm_match_set_pairs_dev(mm_match_set* s, const int32_t* img_a_host, const int
                            int32_t* cnt_dev, int32_t* q_dev, int32_t* t_dev, float* dist_dev,
                            int32_t stride, void* stream);
 
+/* ---- feature cache files of the reference (src/base2d/feature_cache.cc:126-163) ----
+ * "<image>.keypoints" / "<image>.descriptors" as the reference mapper writes them, read without OpenCV (only
+ * KeyPoint::pt and CV_32F descriptor matrices are used by match_brute_force).  The 8-byte rows/cols fields of the
+ * descriptor header carry their value in the low 32 bits (feature_cache.cc:140-141 writes ints with sizeof(size_t)). */
+int mm_feature_cache_info(const char* keypoints_path, const char* descriptors_path,
+                          int32_t* n_keypoints, int32_t* rows, int32_t* cols, int32_t* cv_type);
+int mm_feature_cache_read(const char* keypoints_path, const char* descriptors_path,
+                          float* xy /* [2*rows] or NULL */, float* desc /* [rows*cols] or NULL */,
+                          int32_t cap_rows, int32_t cols_expected);
+/* All images of a sequence from their cache files into one resident match set (upload included). */
+int mm_match_set_create_from_cache(const char* const* keypoints_paths, const char* const* descriptors_paths,
+                                   int32_t n_images, mm_match_set** out);
+
 /* ---- bundle adjustment (bundle_adjustment.h / .cc) ------------------------ */
 #define MM_POSE_FREE    0     /* BA_POSE_FREE    bundle_adjustment.h:33       */
 #define MM_POSE_FIXED   1     /* BA_POSE_FIXED   :34                          */

@@ -47,8 +47,54 @@ def match_brute_force(keypoints1, descriptors1, keypoints2, descriptors2, ratio_
     return q[:m].copy(), t[:m].copy(), dist[:m].copy()
 
 
+def read_feature_cache(keypoints_path, descriptors_path):
+    """One image of the reference's feature cache (feature_cache.cc:126-163) -> (xy [n,2] float32, descriptors [n,k] float32)."""
+    n_kp, rows, cols, typ = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_int32(0)
+    kp, dp = str(keypoints_path).encode(), str(descriptors_path).encode()
+    check(lib().mm_feature_cache_info(kp, dp, C.byref(n_kp), C.byref(rows), C.byref(cols), C.byref(typ)))
+    xy = np.empty((rows.value, 2), np.float32); desc = np.empty((rows.value, cols.value), np.float32)
+    check(lib().mm_feature_cache_read(kp, dp, as_ptr(xy, p_f32), as_ptr(desc, p_f32), rows.value, cols.value))
+    return xy, desc
+
+
+def write_feature_cache(keypoints_path, descriptors_path, xy, desc, junk=0x7f3a9c10):
+    """Writes the two files byte-for-byte as feature_cache.cc:126-147 does (test fixtures / interchange): 28-byte
+    cv::KeyPoint records, and the descriptor header whose 8-byte rows/cols fields carry cols / pointer bits in their high
+    halves (`junk` stands in for the low half of cv::Mat::data)."""
+    xy = np.ascontiguousarray(xy, dtype=np.float32).reshape(-1, 2); desc = np.ascontiguousarray(desc, dtype=np.float32)
+    n = len(xy)
+    kp = np.zeros(n, dtype=np.dtype([("pt", "<f4", (2,)), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")]))
+    kp["pt"] = xy; kp["size"] = 7.0; kp["angle"] = -1.0; kp["class_id"] = -1
+    assert kp.dtype.itemsize == 28
+    with open(keypoints_path, "wb") as f:
+        f.write(np.uint64(n * 28).tobytes()); f.write(kp.tobytes())
+    rows, cols = (desc.shape if desc.ndim == 2 else (0, 0))
+    with open(descriptors_path, "wb") as f:
+        f.write(np.uint64(desc.nbytes).tobytes())
+        f.write(np.array([rows, cols], dtype="<i4").tobytes())           # &rows read as 8 bytes: rows | cols
+        f.write(np.array([cols, junk], dtype="<i4").tobytes())           # &cols read as 8 bytes: cols | low half of the data pointer
+        f.write(np.int32(5).tobytes())                                   # CV_32FC1
+        f.write(desc.tobytes())
+
+
 class MatchSet:
     """Descriptors of a whole sequence resident in HBM (BASELINE.json configs[2]: all pairs)."""
+
+    @classmethod
+    def from_cache(cls, keypoints_paths, descriptors_paths):
+        """All images straight from the reference's cache files (no cv::Mat in between)."""
+        self = cls.__new__(cls)
+        n = len(keypoints_paths)
+        kp = (C.c_char_p * n)(*[str(p).encode() for p in keypoints_paths]); dp = (C.c_char_p * n)(*[str(p).encode() for p in descriptors_paths])
+        counts, k = [], 0
+        for a, b in zip(keypoints_paths, descriptors_paths):
+            nk, r, c, t = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_int32(0)
+            check(lib().mm_feature_cache_info(str(a).encode(), str(b).encode(), C.byref(nk), C.byref(r), C.byref(c), C.byref(t)))
+            counts.append(r.value); k = k or c.value
+        self.counts = np.array(counts, dtype=np.int32); self.k = k or 64
+        self._h = C.c_void_p()
+        check(lib().mm_match_set_create_from_cache(kp, dp, n, C.byref(self._h)))
+        return self
 
     def __init__(self, descriptors, keypoints=None):
         """descriptors: list of [n_i,k] arrays or one [n_images,n,k] array."""
