@@ -859,6 +859,7 @@ __global__ void __launch_bounds__(256) k_pcg_persistent(PcgArgs A) {
       if (border && lane < 9) pin = __ldcg(A.zi + lane) + beta * __ldcg(((it & 1) ? A.pi1 : A.pi0) + lane);
       double btl = 0.0;                                 // this warp's share of B' p (lane m < 9)
       // ---- SpMV with p formed on the fly: Ap = S (z + beta p_old)
+      PCG_STAMP(0);
       double acc = 0.0;
       for (int row = gw; row < n; row += nw) {
         double y = 0.0;
@@ -934,10 +935,13 @@ __global__ void __launch_bounds__(256) k_pcg_persistent(PcgArgs A) {
           if (olane) { pi_ = pin; ((it & 1) ? A.pi0 : A.pi1)[lane] = pin; acc += pin * cp; }
         }
       }
+      PCG_STAMP(1);
       acc = block_sum_to_thread0(acc, red);          // (contains __syncthreads: bt_s is complete afterwards)
       if (threadIdx.x == 0) atomicAdd(A.sc + (it & 1), acc);
       if (border && threadIdx.x < 9) { double sb = 0.0; for (int w = 0; w < wpb; ++w) sb += bt_s[w][threadIdx.x]; atomicAdd(A.bt + 9 * (it & 1) + threadIdx.x, sb); }
+      PCG_STAMP(2);
       if (single) __syncthreads(); else grid_barrier(bar_ctr, bar_target);
+      PCG_STAMP(3);
       const double pAp = __ldcg(A.sc + (it & 1));
       const double alpha = pAp > 0.0 ? rz / pAp : 0.0;
       if (gw == 0 && lane == 0) A.sc[nxt] = 0.0;
@@ -984,7 +988,9 @@ __global__ void __launch_bounds__(256) k_pcg_persistent(PcgArgs A) {
       }
       a_rz = block_sum_to_thread0(a_rz, red); a_rr = block_sum_to_thread0(a_rr, red);
       if (threadIdx.x == 0) { atomicAdd(A.sc + 2 + nxt, a_rz); atomicAdd(A.sc + 4 + nxt, a_rr); }
+      PCG_STAMP(4);
       if (single) __syncthreads(); else grid_barrier(bar_ctr, bar_target);
+      PCG_STAMP(5);
       rz_old = rz; rz = __ldcg(A.sc + 2 + nxt);
       const double rr = __ldcg(A.sc + 4 + nxt);
       ++it;
