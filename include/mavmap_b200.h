@@ -98,6 +98,20 @@ int mm_triangulate_two_view(const double* P1, const double* P2, int64_t n,
  * err and depth are [n]; either output may be NULL.  Host buffers. */
 int mm_reproj_errors(const double* P, int64_t n, const double* x2d, const double* X, double* err, double* depth);
 
+/* RANSAC hypothesis scoring (util/estimation.cc:83-126): for every model the number of inliers |r| <= threshold and
+ * the sum of |r| over the inliers, with the residual of
+ *   kind 0  P3PEstimator::residuals (p3p.cc:172-199):  x = points2D [n*2], y = points3D [n*3], model = [R|t] 3x4 row-major
+ *   kind 1  ProjectiveTransformEstimator::residuals (projective_transform.cc:48-74): x = src [n*2], y = dst [n*2], model = H 3x3
+ *   kind 2  EssentialMatrixEstimator::residuals (essential_matrix.cc:131-162, signed Sampson distance): x, y [n*2], model = E 3x3
+ * `best` = index the reference's rule selects (most inliers, then smallest residual sum); best_residuals [n] and
+ * best_mask [n] (optional) are evaluated for that model.  Hypotheses are generated by the caller.  Host buffers. */
+#define MM_RANSAC_P3P 0
+#define MM_RANSAC_HOMOGRAPHY 1
+#define MM_RANSAC_ESSENTIAL 2
+int mm_ransac_score(int32_t kind, const double* models, int32_t n_models, int64_t n, const double* x, const double* y,
+                    double threshold, int32_t* num_inliers, double* residual_sum, int32_t* best,
+                    double* best_residuals, uint8_t* best_mask);
+
 /* ---- brute-force descriptor matching (feature.cc:52-133) ------------------ */
 #define MM_MATCH_IMPL_AUTO    0   /* tcgen05 tensor-core path when shapes allow */
 #define MM_MATCH_IMPL_SIMT    1   /* exact CUDA-core path (verification mode)   */

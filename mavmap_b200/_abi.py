@@ -129,6 +129,7 @@ PROTOTYPES = {
     "mm_match_set_pairs_dev": (C.c_int, [C.c_void_p, p_i32, p_i32, C.c_int32,
                                          C.POINTER(MatchOptions), C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "mm_ransac_score": (C.c_int, [C.c_int32, p_f64, C.c_int32, C.c_int64, p_f64, p_f64, C.c_double, p_i32, p_f64, p_i32, p_f64, p_u8]),
     "mm_feature_cache_info": (C.c_int, [C.c_char_p, C.c_char_p, p_i32, p_i32, p_i32, p_i32]),
     "mm_feature_cache_read": (C.c_int, [C.c_char_p, C.c_char_p, p_f32, p_f32, C.c_int32, C.c_int32]),
     "mm_match_set_create_from_cache": (C.c_int, [C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_int32, C.POINTER(C.c_void_p)]),

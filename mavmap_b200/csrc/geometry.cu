@@ -13,6 +13,7 @@
 // to the SM count, P matrices and intrinsics passed by value in the launch parameters.
 #include <stdarg.h>
 #include <mutex>
+#include <vector>
 #include "common.cuh"
 #include "camera.cuh"
 
@@ -195,6 +196,77 @@ static int camera_batch(int which, int model, const double* params, int64_t n, c
 
 using namespace mm;
 
+
+// ---- RANSAC hypothesis scoring ------------------------------------------------------------------
+// The reference scores every hypothesis with an OpenMP loop over all correspondences (util/estimation.cc:83-116 calling
+// P3PEstimator::residuals p3p.cc:172-199, ProjectiveTransformEstimator::residuals projective_transform.cc:48-74,
+// EssentialMatrixEstimator::residuals essential_matrix.cc:131-162).  Here: one CTA per hypothesis, threads stride over the
+// correspondences, inlier test |r| <= threshold, block reduction of (inlier count, sum of |r| over inliers).
+// Arithmetic is written without FMA contraction and in the reference's operation order, so residuals - and with them the
+// inlier masks - are bit-identical to the CPU oracle.
+#define MM_RANSAC_P3P 0
+#define MM_RANSAC_HOMOGRAPHY 1
+#define MM_RANSAC_ESSENTIAL 2
+__device__ __forceinline__ double dot3_rn(double a0, double a1, double a2, double b0, double b1, double b2) {
+  return __dadd_rn(__dadd_rn(__dmul_rn(a0, b0), __dmul_rn(a1, b1)), __dmul_rn(a2, b2));
+}
+__device__ __forceinline__ double ransac_residual(int kind, const double* m, const double* x, const double* y, int64_t i) {
+  if (kind == MM_RANSAC_P3P) {            // x = points2D [n,2], y = points3D [n,3], m = [R | t] 3x4 row-major
+    const double X0 = y[3 * i], X1 = y[3 * i + 1], X2 = y[3 * i + 2];
+    double p0 = __dadd_rn(dot3_rn(m[0], m[1], m[2], X0, X1, X2), m[3]);
+    double p1 = __dadd_rn(dot3_rn(m[4], m[5], m[6], X0, X1, X2), m[7]);
+    const double p2 = __dadd_rn(dot3_rn(m[8], m[9], m[10], X0, X1, X2), m[11]);
+    p0 = __ddiv_rn(p0, p2); p1 = __ddiv_rn(p1, p2);
+    const double dx = __dadd_rn(p0, -x[2 * i]), dy = __dadd_rn(p1, -x[2 * i + 1]);
+    return __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+  } else if (kind == MM_RANSAC_HOMOGRAPHY) {   // x = src [n,2], y = dst [n,2], m = H 3x3 row-major
+    const double s0 = x[2 * i], s1 = x[2 * i + 1];
+    const double t0 = dot3_rn(m[0], m[1], m[2], s0, s1, 1.0), t1 = dot3_rn(m[3], m[4], m[5], s0, s1, 1.0), t2 = dot3_rn(m[6], m[7], m[8], s0, s1, 1.0);
+    const double dx = __dadd_rn(__ddiv_rn(t0, t2), -y[2 * i]), dy = __dadd_rn(__ddiv_rn(t1, t2), -y[2 * i + 1]);
+    return __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+  } else {                                      // Sampson distance; x = points1, y = points2, m = E 3x3 row-major
+    const double a0 = x[2 * i], a1 = x[2 * i + 1], b0 = y[2 * i], b1 = y[2 * i + 1];
+    const double e0 = dot3_rn(m[0], m[1], m[2], a0, a1, 1.0), e1 = dot3_rn(m[3], m[4], m[5], a0, a1, 1.0), e2 = dot3_rn(m[6], m[7], m[8], a0, a1, 1.0);
+    const double f0 = dot3_rn(m[0], m[3], m[6], b0, b1, 1.0), f1 = dot3_rn(m[1], m[4], m[7], b0, b1, 1.0);
+    const double num = dot3_rn(b0, b1, 1.0, e0, e1, e2);
+    const double den = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(e0, e0), __dmul_rn(e1, e1)), __dmul_rn(f0, f0)), __dmul_rn(f1, f1));
+    return __ddiv_rn(num, __dsqrt_rn(den));
+  }
+}
+__global__ void __launch_bounds__(256) k_ransac_score(int kind, int msize, const double* __restrict__ models, int64_t n,
+                                                      const double* __restrict__ x, const double* __restrict__ y, double threshold,
+                                                      int* __restrict__ num_inliers, double* __restrict__ residual_sum) {
+  __shared__ double sm_m[12]; __shared__ double sred[32]; __shared__ int cred[32];
+  if (threadIdx.x < msize) sm_m[threadIdx.x] = models[(size_t)blockIdx.x * msize + threadIdx.x];
+  __syncthreads();
+  int cnt = 0; double sum = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double a = fabs(ransac_residual(kind, sm_m, x, y, i));
+    if (a <= threshold) { ++cnt; sum += a; }
+  }
+  sum = mm::warp_sum(sum);
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { sred[w] = sum; cred[w] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0; int c = 0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { s += sred[k]; c += cred[k]; }
+    num_inliers[blockIdx.x] = c; residual_sum[blockIdx.x] = s;
+  }
+}
+__global__ void k_ransac_residuals(int kind, int msize, const double* __restrict__ model, int64_t n, const double* __restrict__ x,
+                                   const double* __restrict__ y, double threshold, double* __restrict__ res, unsigned char* __restrict__ mask) {
+  __shared__ double sm_m[12];
+  if (threadIdx.x < msize) sm_m[threadIdx.x] = model[threadIdx.x];
+  __syncthreads();
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double r = ransac_residual(kind, sm_m, x, y, i);
+  if (res) res[i] = r;
+  if (mask) mask[i] = fabs(r) <= threshold ? 1 : 0;
+}
+
 extern "C" {
 
 int mm_abi_version(void) { return MM_ABI_VERSION; }
@@ -271,6 +343,42 @@ int mm_reproj_errors(const double* P, int64_t n, const double* x2d, const double
   MM_LAUNCH_CHECK();
   if (err) MM_CUDA(cudaMemcpy(err, de, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
   if (depth) MM_CUDA(cudaMemcpy(depth, dd, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+  return MM_OK;
+}
+
+int mm_ransac_score(int32_t kind, const double* models, int32_t n_models, int64_t n, const double* x, const double* y, double threshold,
+                    int32_t* num_inliers, double* residual_sum, int32_t* best, double* best_residuals, uint8_t* best_mask) {
+  if (kind < 0 || kind > 2 || n_models < 0 || n < 0 || (n_models > 0 && !models) || (n > 0 && (!x || !y))) { set_error("invalid argument"); return MM_ERR_INVALID_ARG; }
+  int rc = ensure_device(); if (rc != MM_OK) return rc;
+  if (best) *best = -1;
+  if (n_models == 0) return MM_OK;
+  const int msize = kind == MM_RANSAC_P3P ? 12 : 9, xd = 2, yd = kind == MM_RANSAC_P3P ? 3 : 2;
+  DevBuf<double> d_m, d_x, d_y, d_sum, d_res; DevBuf<int> d_cnt; DevBuf<unsigned char> d_mask;
+  MM_CUDA(d_m.alloc((size_t)n_models * msize)); MM_CUDA(d_x.alloc((size_t)n * xd)); MM_CUDA(d_y.alloc((size_t)n * yd));
+  MM_CUDA(d_sum.alloc((size_t)n_models)); MM_CUDA(d_cnt.alloc((size_t)n_models));
+  MM_CUDA(cudaMemcpyAsync(d_m.p, models, sizeof(double) * (size_t)n_models * msize, cudaMemcpyHostToDevice, nullptr));
+  if (n) { MM_CUDA(cudaMemcpyAsync(d_x.p, x, sizeof(double) * (size_t)n * xd, cudaMemcpyHostToDevice, nullptr));
+           MM_CUDA(cudaMemcpyAsync(d_y.p, y, sizeof(double) * (size_t)n * yd, cudaMemcpyHostToDevice, nullptr)); }
+  k_ransac_score<<<n_models, 256>>>(kind, msize, d_m.p, n, d_x.p, d_y.p, threshold, d_cnt.p, d_sum.p);
+  MM_LAUNCH_CHECK();
+  std::vector<int> h_cnt((size_t)n_models); std::vector<double> h_sum((size_t)n_models);
+  MM_CUDA(cudaMemcpy(h_cnt.data(), d_cnt.p, sizeof(int) * (size_t)n_models, cudaMemcpyDeviceToHost));
+  MM_CUDA(cudaMemcpy(h_sum.data(), d_sum.p, sizeof(double) * (size_t)n_models, cudaMemcpyDeviceToHost));
+  // util/estimation.cc:118-126: more inliers wins, ties go to the smaller residual sum (first hypothesis wins exact ties)
+  int b = -1;
+  for (int h = 0; h < n_models; ++h) {
+    if (num_inliers) num_inliers[h] = h_cnt[h];
+    if (residual_sum) residual_sum[h] = h_sum[h];
+    if (b < 0 || h_cnt[h] > h_cnt[b] || (h_cnt[h] == h_cnt[b] && h_sum[h] < h_sum[b])) b = h;
+  }
+  if (best) *best = b;
+  if (b >= 0 && n > 0 && (best_residuals || best_mask)) {
+    MM_CUDA(d_res.alloc((size_t)n)); MM_CUDA(d_mask.alloc((size_t)n));
+    k_ransac_residuals<<<grid_for(n, 256), 256>>>(kind, msize, d_m.p + (size_t)b * msize, n, d_x.p, d_y.p, threshold, d_res.p, d_mask.p);
+    MM_LAUNCH_CHECK();
+    if (best_residuals) MM_CUDA(cudaMemcpy(best_residuals, d_res.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+    if (best_mask) MM_CUDA(cudaMemcpy(best_mask, d_mask.p, (size_t)n, cudaMemcpyDeviceToHost));
+  }
   return MM_OK;
 }
 

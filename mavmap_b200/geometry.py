@@ -96,3 +96,28 @@ def calc_depth(proj_matrix, points3D):
     d = np.empty(len(X))
     check(lib().mm_reproj_errors(as_ptr(P, p_f64), len(X), None, as_ptr(X, p_f64), None, as_ptr(d, p_f64)))
     return d
+
+
+RANSAC_P3P, RANSAC_HOMOGRAPHY, RANSAC_ESSENTIAL = 0, 1, 2
+
+
+def ransac_score(kind, models, x, y, threshold, _fn=None):
+    """Scores RANSAC hypotheses as util/estimation.cc:83-126 does (inliers |r| <= threshold, sum of |r| over them) with the
+    residuals of p3p.cc:172-199 (kind 0: x = points2D, y = points3D, models [h,3,4]), projective_transform.cc:48-74 (kind 1:
+    src, dst, models [h,3,3]) or essential_matrix.cc:131-162 (kind 2).  Returns a dict: num_inliers [h], residual_sum [h],
+    best (index by the reference's rule), residuals [n] and inlier_mask [n] of the best model."""
+    import ctypes as C
+    from ._abi import p_i32, p_u8
+    msize = 12 if kind == RANSAC_P3P else 9
+    M = np.ascontiguousarray(models, dtype=np.float64).reshape(-1, msize)
+    x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 2)
+    y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1, 3 if kind == RANSAC_P3P else 2)
+    assert len(x) == len(y)
+    cnt = np.zeros(len(M), np.int32); rs = np.zeros(len(M)); best = C.c_int32(-1)
+    res = np.zeros(len(x)); mask = np.zeros(len(x), np.uint8)
+    fn = _fn or lib().mm_ransac_score
+    rc = fn(int(kind), as_ptr(M, p_f64), len(M), len(x), as_ptr(x, p_f64), as_ptr(y, p_f64), float(threshold),
+            as_ptr(cnt, p_i32), as_ptr(rs, p_f64), C.byref(best), as_ptr(res, p_f64), as_ptr(mask, p_u8))
+    if _fn is None:
+        check(rc)
+    return {"num_inliers": cnt, "residual_sum": rs, "best": best.value, "residuals": res, "inlier_mask": mask.astype(bool)}

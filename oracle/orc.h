@@ -66,6 +66,8 @@ int orc_pose_refine(double* rvec, double* tvec, int model_code, const double* pa
                     const uint8_t* inlier_mask, const mm_ba_options* opt,
                     mm_ba_summary* summary, double* ret);
 /* cost only: 1/2 sum rho(|r|^2) at the problem's current parameters */
+int orc_ransac_score(int kind, const double* models, int n_models, int64_t n, const double* x, const double* y, double threshold,
+                     int32_t* num_inliers, double* residual_sum, int32_t* best, double* best_residuals, uint8_t* best_mask);
 double orc_ba_cost(const mm_ba_problem* problem, const mm_ba_options* opt);
 /* BARotationConstraintCostFunction (bundle_adjustment.cc:57-111): residual and d r / d rvec (J may be NULL) */
 double orc_rot_prior(const double* rvec, const double* rvec0, double weight, double* J);

@@ -226,6 +226,15 @@ def ba_cost(flat, c_options):
     return lib().orc_ba_cost(C.byref(cp), C.byref(c_options))
 
 
+def ransac_score(kind, models, x, y, threshold):
+    from mavmap_b200.geometry import ransac_score as _rs
+    L = lib()
+    L.orc_ransac_score.restype = C.c_int
+    L.orc_ransac_score.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double,
+                                   C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_uint8)]
+    return _rs(kind, models, x, y, threshold, _fn=L.orc_ransac_score)
+
+
 def rot_prior(rvec, rvec0, weight):
     """BARotationConstraintCostFunction (bundle_adjustment.cc:57-111): (residual, d residual / d rvec [3])"""
     a = np.ascontiguousarray(rvec, dtype=np.float64); b = np.ascontiguousarray(rvec0, dtype=np.float64); J = np.zeros(3)

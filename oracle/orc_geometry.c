@@ -107,3 +107,47 @@ int orc_triangulate_two_view(const double* P1, const double* P2, int64_t n,
   }
   return MM_OK;
 }
+
+
+/* ---- RANSAC hypothesis scoring: util/estimation.cc:83-126 with the residuals of p3p.cc:172-199 (kind 0),
+ * projective_transform.cc:48-74 (kind 1) and essential_matrix.cc:131-162 (kind 2).  Row-major models. */
+static double ransac_residual(int kind, const double* m, const double* x, const double* y, int64_t i) {
+  if (kind == 0) {
+    const double X0 = y[3*i], X1 = y[3*i+1], X2 = y[3*i+2];
+    double p0 = (m[0]*X0 + m[1]*X1 + m[2]*X2) + m[3];
+    double p1 = (m[4]*X0 + m[5]*X1 + m[6]*X2) + m[7];
+    const double p2 = (m[8]*X0 + m[9]*X1 + m[10]*X2) + m[11];
+    p0 /= p2; p1 /= p2;
+    const double dx = p0 - x[2*i], dy = p1 - x[2*i+1];
+    return sqrt(dx*dx + dy*dy);
+  } else if (kind == 1) {
+    const double s0 = x[2*i], s1 = x[2*i+1];
+    const double t0 = m[0]*s0 + m[1]*s1 + m[2]*1.0, t1 = m[3]*s0 + m[4]*s1 + m[5]*1.0, t2 = m[6]*s0 + m[7]*s1 + m[8]*1.0;
+    const double dx = t0 / t2 - y[2*i], dy = t1 / t2 - y[2*i+1];
+    return sqrt(dx*dx + dy*dy);
+  } else {
+    const double a0 = x[2*i], a1 = x[2*i+1], b0 = y[2*i], b1 = y[2*i+1];
+    const double e0 = m[0]*a0 + m[1]*a1 + m[2]*1.0, e1 = m[3]*a0 + m[4]*a1 + m[5]*1.0, e2 = m[6]*a0 + m[7]*a1 + m[8]*1.0;
+    const double f0 = m[0]*b0 + m[3]*b1 + m[6]*1.0, f1 = m[1]*b0 + m[4]*b1 + m[7]*1.0;
+    const double num = b0*e0 + b1*e1 + 1.0*e2;
+    return num / sqrt(e0*e0 + e1*e1 + f0*f0 + f1*f1);
+  }
+}
+int orc_ransac_score(int kind, const double* models, int n_models, int64_t n, const double* x, const double* y, double threshold,
+                     int32_t* num_inliers, double* residual_sum, int32_t* best, double* best_residuals, uint8_t* best_mask) {
+  const int msize = kind == 0 ? 12 : 9; int b = -1; int bc = 0; double bs = 0.0;
+  for (int h = 0; h < n_models; ++h) {
+    int c = 0; double s = 0.0;
+    for (int64_t i = 0; i < n; ++i) { const double a = fabs(ransac_residual(kind, models + (size_t)h*msize, x, y, i)); if (a <= threshold) { ++c; s += a; } }
+    if (num_inliers) num_inliers[h] = c;
+    if (residual_sum) residual_sum[h] = s;
+    if (b < 0 || c > bc || (c == bc && s < bs)) { b = h; bc = c; bs = s; }
+  }
+  if (best) *best = b;
+  if (b >= 0) for (int64_t i = 0; i < n; ++i) {
+    const double r = ransac_residual(kind, models + (size_t)b*msize, x, y, i);
+    if (best_residuals) best_residuals[i] = r;
+    if (best_mask) best_mask[i] = fabs(r) <= threshold;
+  }
+  return 0;
+}

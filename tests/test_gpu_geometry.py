@@ -61,3 +61,20 @@ def test_triangulation_batch_vs_oracle(mm, orc):
     for k in ("reproj1", "reproj2", "depth1", "depth2", "angle"):
         np.testing.assert_allclose(g[k], o[k], rtol=1e-8, atol=1e-10)
     assert mm.triangulate_points(P1, P2, np.zeros((0, 2)), np.zeros((0, 2))).shape == (0, 3)
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_ransac_score_bit_exact_against_oracle(mm, orc, kind):
+    """hypothesis scoring on the device; residuals are computed without FMA contraction in the reference's
+    operation order, so residuals, inlier masks and counts are identical to the oracle and the same model wins."""
+    from test_oracle_geometry import _ransac_case
+    from mavmap_b200.geometry import ransac_score
+    models, x, y, thr = _ransac_case(kind, n=20000, h=64, seed=3)
+    g = ransac_score(kind, models, x, y, thr); o = orc.ransac_score(kind, models, x, y, thr)
+    np.testing.assert_array_equal(g["num_inliers"], o["num_inliers"])
+    np.testing.assert_allclose(g["residual_sum"], o["residual_sum"], rtol=1e-12)
+    assert g["best"] == o["best"] == 0
+    np.testing.assert_array_equal(g["residuals"], o["residuals"])
+    np.testing.assert_array_equal(g["inlier_mask"], o["inlier_mask"])
+    e = ransac_score(kind, models[:0], x, y, thr)
+    assert e["best"] == -1

@@ -142,3 +142,49 @@ def test_triangulation_matches_numpy_svd_and_filters(orc):
     r1 = np.linalg.norm(out["X"] - C1, axis=1); r2 = np.linalg.norm(out["X"] - C2, axis=1)
     ang = np.arccos((r1 ** 2 + r2 ** 2 - np.linalg.norm(C1 - C2) ** 2) / (2 * r1 * r2))
     np.testing.assert_allclose(out["angle"], ang, rtol=1e-9)
+
+
+def _ransac_case(kind, n=3000, h=40, seed=0):
+    """correspondences consistent with model 0 (+ noise + 30 % outliers) and h-1 perturbed hypotheses"""
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(seed + kind)
+    if kind == 0:
+        R = Rotation.from_rotvec([0.1, -0.2, 0.05]).as_matrix(); t = np.array([0.3, -0.1, 0.5])
+        X = rng.uniform([-2, -2, 4], [2, 2, 9], (n, 3)); Xc = X @ R.T + t
+        x = Xc[:, :2] / Xc[:, 2:] + rng.normal(0, 1e-3, (n, 2)); y = X
+        models = [np.hstack([R, t[:, None]])] + [np.hstack([Rotation.from_rotvec(rng.normal(0, 0.01, 3)).as_matrix() @ R, (t + rng.normal(0, 0.02, 3))[:, None]]) for _ in range(h - 1)]
+    elif kind == 1:
+        H = np.array([[1.1, 0.02, 5.0], [-0.03, 0.95, -3.0], [1e-4, -2e-4, 1.0]])
+        x = rng.uniform(0, 1000, (n, 2)); xh = np.hstack([x, np.ones((n, 1))]) @ H.T
+        y = xh[:, :2] / xh[:, 2:] + rng.normal(0, 0.5, (n, 2))
+        models = [H] + [H + rng.normal(0, 1e-3, (3, 3)) * np.array([[1, 1, 100], [1, 1, 100], [1e-4, 1e-4, 0]]) for _ in range(h - 1)]
+    else:
+        R = Rotation.from_rotvec([0.02, 0.1, -0.03]).as_matrix(); t = np.array([1.0, 0.1, 0.05])
+        X = rng.uniform([-2, -2, 4], [2, 2, 9], (n, 3)); X2 = X @ R.T + t
+        x = X[:, :2] / X[:, 2:] + rng.normal(0, 1e-3, (n, 2)); y = X2[:, :2] / X2[:, 2:] + rng.normal(0, 1e-3, (n, 2))
+        tx = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]]); E = tx @ R
+        models = [E] + [E + rng.normal(0, 0.01, (3, 3)) for _ in range(h - 1)]
+    out = rng.random(n) < 0.3
+    y = y.copy(); y[out] += rng.normal(0, 50.0 if kind == 1 else (1.0 if kind == 0 else 0.3), (out.sum(), y.shape[1]))
+    return np.array(models), x, y, (2.0 if kind == 1 else 4e-3)
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_ransac_score_oracle_matches_numpy(kind):
+    """oracle restatement of util/estimation.cc:83-126 + the three residual functions against plain numpy"""
+    from oracle import orc
+    models, x, y, thr = _ransac_case(kind)
+    o = orc.ransac_score(kind, models, x, y, thr)
+    for h in (0, 7):
+        M = models[h]
+        if kind == 0:
+            p = y @ M[:, :3].T + M[:, 3]; r = np.linalg.norm(p[:, :2] / p[:, 2:] - x, axis=1)
+        elif kind == 1:
+            p = np.hstack([x, np.ones((len(x), 1))]) @ M.T; r = np.linalg.norm(p[:, :2] / p[:, 2:] - y, axis=1)
+        else:
+            x1 = np.hstack([x, np.ones((len(x), 1))]); x2 = np.hstack([y, np.ones((len(y), 1))])
+            Ex1 = x1 @ M.T; Etx2 = x2 @ M; r = np.abs(np.sum(x2 * Ex1, axis=1) / np.sqrt(Ex1[:, 0] ** 2 + Ex1[:, 1] ** 2 + Etx2[:, 0] ** 2 + Etx2[:, 1] ** 2))
+        inl = r <= thr
+        assert abs(int(inl.sum()) - int(o["num_inliers"][h])) <= 1            # a residual within an ulp of the threshold may flip
+        assert abs(r[inl].sum() - o["residual_sum"][h]) < 1e-6 * max(1.0, r[inl].sum())
+    assert o["best"] == 0 and o["inlier_mask"].sum() == o["num_inliers"][0] > 0.6 * len(x)
