@@ -591,6 +591,15 @@ int launch_pcg(mm_ba_session* s) {
   cudaStream_t st = s->stream;
   MM_CUDA(cudaMemsetAsync(s->pcg_sc.p, 0, sizeof(double) * 16, st));
   MM_CUDA(cudaMemsetAsync(s->pcg_ic.p, 0, sizeof(int) * 4, st));
+  if (!s->refine && s->n_img <= DENSE_MAX_IMG && s->n_img > 0 && !getenv("MM_PCG_ONLY")) {
+    // local-BA sized system: dense Cholesky in one CTA (ba_coarse.cuh); reported as 0 linear iterations
+    const int n = 6 * s->n_img;
+    const size_t smem = sizeof(double) * ((size_t)n * (n + 1) + n);
+    static bool configured = false;
+    if (!configured) { MM_CUDA(cudaFuncSetAttribute(k_dense_chol_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ((size_t)6 * DENSE_MAX_IMG * (6 * DENSE_MAX_IMG + 1) + 6 * DENSE_MAX_IMG)))); configured = true; }
+    k_dense_chol_solve<<<1, 512, smem, st>>>(s->n_img, s->nblk, s->blk_a.p, s->blk_b.p, s->S.p, s->rhs.p, s->vx.p, s->fail.p); MM_LAUNCH_CHECK();
+    return pcg_broadcast(s);
+  }
   if (s->pcg_grid == 0) {
     // choose between the cached kernel (rows resident in shared memory) and the streaming kernel
     std::vector<int> h_rs((size_t)s->n_img + 1);

@@ -175,4 +175,72 @@ __global__ void __launch_bounds__(256, 2) k_spd_inverse(int m, double* __restric
 #undef GJ_STAMP
 }
 
+
+// ---- small reduced systems (local BA): direct solve in ONE CTA ------------------------------------------
+// Up to 26 images (156 unknowns) the whole reduced camera system fits in shared memory as a dense matrix.  A local-BA sized
+// solve took 30-90 PCG iterations of 4-9 us each (latency of the vector exchange through L2); the dense Cholesky below takes
+// tens of microseconds and is what the reference does anyway (SPARSE_SCHUR = Cholesky, bundle_adjustment.cc:555).
+// Block pass: stored 6 x 6 blocks -> dense lower triangle; right-looking Cholesky with all threads (2 barriers per column);
+// forward / backward substitution by one warp (no block barriers).
+constexpr int DENSE_MAX_IMG = 26;
+__global__ void __launch_bounds__(512, 1) k_dense_chol_solve(int n_img, int64_t nblk, const int* __restrict__ blk_a, const int* __restrict__ blk_b,
+                                                             const double* __restrict__ S, const double* __restrict__ rhs, double* __restrict__ x,
+                                                             int* __restrict__ fail) {
+  extern __shared__ double dsm[];
+  const int n = 6 * n_img, ld = n + 1;
+  double* L = dsm;                 // [n][ld], lower triangle used
+  double* v = dsm + (size_t)n * ld;   // [n]
+  __shared__ int bad;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid == 0) bad = 0;
+  for (int i = tid; i < n * ld; i += nt) L[i] = 0.0;
+  __syncthreads();
+  for (int64_t e = tid; e < nblk * 36; e += nt) {
+    const int64_t b = e / 36; const int k = (int)(e - 36 * b), r = k / 6, c = k - 6 * r;
+    const int ia = b < n_img ? (int)b : blk_a[b - n_img], ib = b < n_img ? (int)b : blk_b[b - n_img];      // ia <= ib: block (ia, ib) of the upper triangle
+    const double val = S[36 * (size_t)b + k];
+    const int gi = 6 * ia + r, gj = 6 * ib + c;
+    if (gi >= gj) L[gi * ld + gj] = val;            // diagonal blocks: their lower half
+    if (ia != ib) L[gj * ld + gi] = val;            // off-diagonal block, transposed into the lower triangle
+  }
+  for (int i = tid; i < n; i += nt) v[i] = rhs[i];
+  __syncthreads();
+  for (int j = 0; j < n; ++j) {
+    const double d = L[j * ld + j];
+    if (!(d > 0.0) || !isfinite(d)) { if (tid == 0) bad = 1; break; }      // uniform: every thread reads the same value
+    const double l = sqrt(d), il = 1.0 / l;
+    __syncthreads();
+    for (int i = j + tid; i < n; i += nt) L[i * ld + j] = (i == j) ? l : L[i * ld + j] * il;
+    __syncthreads();
+    // trailing update of the lower triangle: A[i][k] -= L[i][j] L[k][j], j < k <= i
+    const int m = n - j - 1;
+    for (int a = tid >> 5; a < m; a += (nt >> 5)) {       // warp per row, lanes along the row: no integer division, conflict-free
+      const int i = j + 1 + a;
+      const double lij = L[i * ld + j];
+      for (int c = tid & 31; c <= a; c += 32) L[i * ld + j + 1 + c] -= lij * L[(j + 1 + c) * ld + j];
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (bad) { if (tid == 0) *fail = 1; for (int i = tid; i < n; i += nt) x[i] = 0.0; return; }
+  if (tid < 32) {                   // L y = b, then L' x = y; lane-strided rows, the pivot value is broadcast through shared memory
+    for (int j = 0; j < n; ++j) {
+      if (tid == 0) v[j] = v[j] / L[j * ld + j];
+      __syncwarp();
+      const double yj = v[j];
+      for (int i = j + 1 + tid; i < n; i += 32) v[i] -= L[i * ld + j] * yj;
+      __syncwarp();
+    }
+    for (int j = n - 1; j >= 0; --j) {
+      if (tid == 0) v[j] = v[j] / L[j * ld + j];
+      __syncwarp();
+      const double xj = v[j];
+      for (int i = tid; i < j; i += 32) v[i] -= L[j * ld + i] * xj;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += nt) x[i] = v[i];
+}
+
 }  // namespace mm
