@@ -52,7 +52,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
         except Exception:
@@ -60,9 +60,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.time()] + [c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """samples taken between t0 and t1 (the warm-up + timed region); the nearest ones if the window caught none"""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -71,7 +72,11 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        rows = [r[1:] for r in self.rows if (t0 is None or r[0] >= t0) and (t1 is None or r[0] <= t1 + 0.05)]
+        if not rows and self.rows:
+            mid = 0.5 * ((t0 or 0) + (t1 or 0))
+            rows = [r[1:] for r in sorted(self.rows, key=lambda r: abs(r[0] - mid))[:3]]
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except Exception:
@@ -205,8 +210,10 @@ def main():
     else:
         sess = BASession(flat.copy(), options(W + K), stream=stream)
     n_blocks = sess.num_blocks()
-    sess.iterate(W)
     sampler = ClockSampler(local); sampler.start()
+    time.sleep(0.25)                                       # nvidia-smi needs a moment to produce its first sample
+    t_load0 = time.time()
+    sess.iterate(W)
     barrier()
     l0 = _lib.kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -216,7 +223,7 @@ def main():
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = _lib.kernel_launch_count() - l0
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_load0, time.time())
     summ = sess.summary().as_dict()
     assert done == K, "LM stopped early (%d of %d iterations)" % (done, K)
     value = (1 if sharded else world) * K / (ms * 1e-3)

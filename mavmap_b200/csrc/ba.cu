@@ -157,7 +157,7 @@ struct mm_ba_session {
   int n_img = 0, n_cam = 0, n_pt = 0; int64_t n_obs = 0;
   int n_off = 0; int64_t nblk = 0, n_pairs = 0, n_ent = 0;
   std::vector<double> h_poses0, h_intr0, h_pts0;
-  std::vector<double> h_pt_mask; std::vector<int> h_pt_new2old; unsigned long long spread = 1;         // internal point order (spatially clustered) -> caller's order
+  std::vector<double> h_pt_mask; std::vector<int> h_pt_new2old;         // internal point order (spatially clustered) -> caller's order
   DevBuf<double2> obs_xy; DevBuf<int> obs_img, obs_pt, pt_start, cam_perm, cam_start, img_cam, cam_model;
   DevBuf<int64_t> pair_off; DevBuf<int> row_start, row_col, row_blk, sp_lo, sp_hi, sp_pt, bp_start, bp_end; DevBuf<double> pinfo;
   DevBuf<double> S, Minv, poses, intr, pts, poses2, pts2, aux, aux2, rec;
@@ -901,10 +901,6 @@ int mm_ba_session_create_sharded(const mm_ba_problem* P, const mm_ba_options* op
     A(s->xch, s->xch_count);
     s->S.view(s->xch.p, nS); s->rhs.view(s->xch.p + nS, nv); s->gc.view(s->xch.p + nS + nv, nv); s->ud.view(s->xch.p + nS + 2 * nv, nv);
     cudaMemsetAsync(s->xch.p, 0, sizeof(double) * s->xch_count, s->stream); }
-  { // multiplier of the K2a point permutation: a prime near 0.38 * n_pt that does not divide n_pt
-    const unsigned long long primes[] = { 1000003ULL, 611953ULL, 382003ULL, 100003ULL, 38183ULL, 10007ULL, 3821ULL, 1009ULL, 383ULL, 101ULL, 37ULL, 7ULL, 1ULL };
-    s->spread = 1;
-    if (!getenv("MM_BA_NO_SPREAD")) for (unsigned long long q : primes) if (q < (unsigned long long)std::max(P->n_pt, 1) && (unsigned long long)P->n_pt % q != 0) { s->spread = q; break; } }
   { std::vector<double> tmp((size_t)std::max(P->n_pt, 1), 0.0);
     for (int p = 0; p < P->n_pt; ++p) tmp[p] = s->h_pt_mask[(size_t)s->h_pt_new2old[p]];
     if (cudaMemcpy(s->pt_mask.p, tmp.data(), sizeof(double) * tmp.size(), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("mask upload failed"); return fail_out(MM_ERR_CUDA); } }

@@ -587,40 +587,9 @@ __global__ void k_precond(int n_img, const double* __restrict__ S, double* __res
 }
 
 // ---- K3: PCG on the reduced camera system (block-CSR with transposed references) -----------
-// scalars layout (double): [0]=rz  [1]=pAp  [2]=rz_new  [3]=rr  [4]=bb   ; ints: [0]=done [1]=iters
-struct PcgVecs { double *x, *r, *z, *p0, *p1, *Ap; };
 
-// init: x = 0, r = b, z = Minv r, p0 = z; rz = r.z, bb = b.b (single block handles reduction per block + atomics)
-__global__ void k_pcg_init(int n_img, const double* __restrict__ b, const double* __restrict__ Minv, PcgVecs v,
-                           double* __restrict__ sc, int* __restrict__ ic) {
-  __shared__ double red[32];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  double rz = 0.0, bb = 0.0;
-  if (i < n_img) {
-    double r[6], z[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) r[k] = b[6 * (size_t)i + k];
-    const double* M = Minv + 36 * (size_t)i;
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
-      double s = 0.0;
-#pragma unroll
-      for (int c = 0; c < 6; ++c) s += M[6 * a + c] * r[c];
-      z[a] = s;
-    }
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      v.x[6 * (size_t)i + k] = 0.0; v.r[6 * (size_t)i + k] = r[k]; v.z[6 * (size_t)i + k] = z[k]; v.p0[6 * (size_t)i + k] = 0.0; v.p1[6 * (size_t)i + k] = 0.0;
-      rz += r[k] * z[k]; bb += r[k] * r[k];
-    }
-  }
-  rz = block_sum(rz, red); bb = block_sum(bb, red);
-  if (threadIdx.x == 0) { atomicAdd(sc + 2, rz); atomicAdd(sc + 4, bb); atomicAdd(sc + 3, bb); }
-  (void)ic;
-}
-
-// A: p_new = z + beta p_old (beta = rz_new/rz, 0 on the first iteration); Ap = S p_new; pAp += p_new.Ap
-// one warp per block-row; lanes split the row's blocks.
+// stand-alone block-row SpMV (one warp per block-row; lanes split the row's blocks): p_new = z + beta p_old, Ap = S p_new.
+// Only used to time one SpMV in isolation (mm_ba_session_time_kernel); the solves run in the persistent kernels below.
 __global__ void __launch_bounds__(128) k_pcg_spmv(
     int n_img, const int* __restrict__ row_start, const int* __restrict__ row_col, const int* __restrict__ row_blk,
     const double* __restrict__ S, const double* __restrict__ z, const double* __restrict__ p_old, double* __restrict__ p_new,
@@ -664,56 +633,6 @@ __global__ void __launch_bounds__(128) k_pcg_spmv(
       dot += pn * y[k];
     }
     atomicAdd(sc + 1, dot);
-  }
-}
-
-// B: alpha = rz_new_prev / pAp ; x += alpha p ; r -= alpha Ap ; z = Minv r ; accumulate rz_next, rr.
-// The last block to finish rotates the scalars and tests convergence.
-__global__ void __launch_bounds__(128) k_pcg_update(
-    int n_img, const double* __restrict__ Minv, const double* __restrict__ p, const double* __restrict__ Ap,
-    double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
-    double* __restrict__ sc, int* __restrict__ ic, double tol2, int max_iter) {
-  if (ic[0]) return;
-  __shared__ double red[32];
-  __shared__ int last;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const double alpha = sc[2] / sc[1];
-  double rz = 0.0, rr = 0.0;
-  if (i < n_img) {
-    double rv[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      x[6 * (size_t)i + k] += alpha * p[6 * (size_t)i + k];
-      rv[k] = r[6 * (size_t)i + k] - alpha * Ap[6 * (size_t)i + k];
-      r[6 * (size_t)i + k] = rv[k];
-      rr += rv[k] * rv[k];
-    }
-    const double* M = Minv + 36 * (size_t)i;
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
-      double s = 0.0;
-#pragma unroll
-      for (int c = 0; c < 6; ++c) s += M[6 * a + c] * rv[c];
-      z[6 * (size_t)i + a] = s; rz += rv[a] * s;
-    }
-  }
-  rz = block_sum(rz, red); rr = block_sum(rr, red);
-  if (threadIdx.x == 0) {
-    atomicAdd(sc + 5, rz); atomicAdd(sc + 6, rr);
-    __threadfence();
-    last = (atomicAdd(ic + 2, 1) == (int)gridDim.x - 1);
-  }
-  __syncthreads();
-  if (last && threadIdx.x == 0) {
-    __threadfence();
-    const double rz_next = atomicAdd(sc + 5, 0.0), rr_now = atomicAdd(sc + 6, 0.0);
-    sc[0] = sc[2];          // rz <- rz_new (the one used for alpha)
-    sc[2] = rz_next;        // rz_new <- r.z of this iteration (beta = sc[2]/sc[0] next time)
-    sc[3] = rr_now; sc[1] = 0.0; sc[5] = 0.0; sc[6] = 0.0;
-    ic[2] = 0;
-    const int it = ic[1] + 1; ic[1] = it;
-    if (rr_now <= tol2 * sc[4] || it >= max_iter || !(rr_now == rr_now)) ic[0] = 1;
-    __threadfence();
   }
 }
 

@@ -3,13 +3,16 @@
 # usage (under gpurun): bash tools/gpu_round.sh <tag> [stages...]   stages: test bench cfg4 launches full
 set -u
 TAG=${1:-r1}; shift || true
-STAGES=${*:-"test bench cfg4 launches full"}
+STAGES=${*:-"test smoke bench cfg4 launches full"}
 OUT=gpurun_out; mkdir -p $OUT
 has() { case " $STAGES " in *" $1 "*) return 0;; esac; return 1; }
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi_$TAG.txt 2>&1
 if has test; then
   timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu_$TAG.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_gpu_$TAG.log
   tail -3 $OUT/pytest_gpu_$TAG.log
+fi
+if has smoke; then
+  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke_$TAG.log 2>&1; tail -2 $OUT/smoke_$TAG.log
 fi
 if has bench; then
   timeout 600 python bench.py > $OUT/bench_${TAG}_cfg2.json 2> $OUT/bench_${TAG}_cfg2.err; tail -c 600 $OUT/bench_${TAG}_cfg2.json
