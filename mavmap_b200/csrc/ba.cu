@@ -361,7 +361,7 @@ int build_aggregates(mm_ba_session* s) {
   s->cm = 0; s->n_agg = 0;
   const int n = s->n_img;
   int target = getenv("MM_PCG_AGG") ? atoi(getenv("MM_PCG_AGG")) : 8;
-  if (getenv("MM_PCG_NO_COARSE") || s->refine || n < 64 || target < 2 || s->n_ent <= n) return MM_OK;
+  if (getenv("MM_PCG_NO_COARSE") || n < 64 || target < 2 || s->n_ent <= n) return MM_OK;
   while ((int64_t)CM * ((n + target - 1) / target) > 2048) ++target;          // keeps the dense coarse inverse <= 32 MB
   std::vector<int> rs((size_t)n + 1), col((size_t)s->n_ent);
   MM_CUDA(cudaMemcpy(rs.data(), s->row_start.p, sizeof(int) * rs.size(), cudaMemcpyDeviceToHost));

@@ -841,7 +841,7 @@ __global__ void __launch_bounds__(256) k_pcg_persistent(PcgArgs A) {
           double Pl[CM];
 #pragma unroll
           for (int k = 0; k < CM; ++k) Pl[k] = lane < 6 ? A.Pc[PCS * (size_t)row + CM * lane + k] : 0.0;
-          coarse_restrict_add(Pl, lane < 6 ? t : 0.0, lane, true, A.qc + CM * A.agg[row]);
+          coarse_restrict_add(Pl, lane < 6 ? t + bp : 0.0, lane, true, A.qc + CM * A.agg[row]);      // (bp: border term, 0 without refined intrinsics)
         }
       }
       if (border) {

@@ -22,6 +22,11 @@ def _both(orc, flat, iters, **kw):
     return g, c, sg, so
 
 
+def _opts(iters):
+    o = default_c_options(); o.max_num_iterations = iters; o.function_tolerance = 0; o.gradient_tolerance = 0
+    return o
+
+
 def _assert_parity(g, c, sg, so, param_rel=REL):
     assert sg["trace_accepted"] == so["trace_accepted"]
     np.testing.assert_allclose(sg["trace_cost"], so["trace_cost"], rtol=REL)
@@ -275,3 +280,18 @@ def test_rotation_constraints_parity(mm, orc):
     assert abs(rg - ro) <= REL * ro
     for i in ids:
         np.testing.assert_allclose(fm_g.rvecs[i], fm_o.rvecs[i], atol=2e-6); np.testing.assert_allclose(fm_g.tvecs[i], fm_o.tvecs[i], atol=2e-6)
+
+
+def test_two_level_preconditioner_with_refined_intrinsics(mm, orc, monkeypatch):
+    """refine_camera_params=true is the mapper's default (mapper.cc:878-886): the coarse level also works on the pose block of
+    the bordered system (intrinsics keep their own 9 x 9 block)."""
+    cfg = dict(n_img=120, n_obs_target=120000, track_len=4, seed=778)
+    flat, _ = synthetic.make_ba_problem(outlier_frac=0.0, refine_camera_params=True, **cfg)
+    flat.intr[0, :2] *= 0.997
+    g, c, sg, so = _both(orc, flat, 8)
+    _assert_parity(g, c, sg, so, param_rel=4e-6)
+    two_level = sum(sg["trace_linear_iterations"])
+    monkeypatch.setenv("MM_PCG_NO_COARSE", "1")
+    s1 = solve_flat(flat.copy(), _opts(8)).as_dict()
+    assert s1["trace_accepted"] == sg["trace_accepted"]
+    assert two_level * 2 < sum(s1["trace_linear_iterations"])
