@@ -179,7 +179,7 @@ struct mm_ba_session {
   // rotation constraints (constrain_rotation): rvec0 and weight per image, residual / Jacobian of the current iterate
   int n_prior = 0; DevBuf<double> pr_rot0, pr_w, pr_r, pr_J;
   // coarse level of the two-level preconditioner (ba_coarse.cuh)
-  int cm = 0, n_agg = 0; std::vector<int> h_agg; std::vector<double> h_pose_mask;
+  int cm = 0, n_agg = 0; std::vector<int> h_agg; std::vector<double> h_pose_mask; int coarse_iter = -1; double coarse_radius = 0.0;
   DevBuf<int> blk_a, blk_b, agg; DevBuf<double> Pc, Ac, gjC, gjR, crc, cqc, cyc; int gj_grid = 0;
   // refined intrinsics (single shared camera)
   bool refine = false;
@@ -569,7 +569,13 @@ int launch_schur(mm_ba_session* s, bool with_coarse = true) {
   k_cam_finish<<<blocks_for(6 * (int64_t)s->n_img, 128), 128, 0, st>>>(6 * s->n_img, s->ud.p, s->gc.p, s->rhs.p, s->scale_c.p, lm, s->S.p, s->dc.p, s->scal(), s->world,
       s->red.p, s->fail.p, s->n_prior ? s->pr_r.p : nullptr, s->n_prior ? s->pr_J.p : nullptr, s->n_prior ? s->loc.p + 6 : nullptr); MM_LAUNCH_CHECK();
   k_precond<<<blocks_for(s->n_img, 64), 64, 0, st>>>(s->n_img, s->S.p, s->Minv.p, s->fail.p); MM_LAUNCH_CHECK();
-  if (with_coarse) { const int rc = launch_coarse_setup(s); if (rc) return rc; }
+  if (with_coarse && s->cm) {
+    // The coarse inverse is only a preconditioner: once the iteration has settled (S changes little from one LM step to the
+    // next) it is refreshed every third step, or when the trust-region radius - the damping inside S - moved by more than 30x.
+    const double rr = s->coarse_radius > 0.0 ? s->radius / s->coarse_radius : 0.0;
+    const bool refresh = s->iter <= 3 || s->coarse_iter < 0 || s->iter - s->coarse_iter >= 3 || rr > 30.0 || rr < 1.0 / 30.0 || getenv("MM_PCG_COARSE_EVERY");
+    if (refresh) { const int rc = launch_coarse_setup(s); if (rc) return rc; s->coarse_iter = s->iter; s->coarse_radius = s->radius; }
+  }
   if (s->refine) {
     MM_CUDA(cudaMemsetAsync(s->intr_acc.p, 0, sizeof(double) * 108, st));
     k_schur_intr_point<<<blocks_for(s->n_pt, 128), 128, 0, st>>>(s->n_pt, s->pt_start.p, s->rec.p, s->ji.p, s->scale_p.p, s->scale_i.p, s->Vinv.p, s->gp.p, s->Apc.p, s->intr_acc.p); MM_LAUNCH_CHECK();
@@ -693,7 +699,7 @@ int lm_start(mm_ba_session* s) {
   memset(&S, 0, sizeof S);
   S.num_residuals = 2 * s->n_obs + s->n_prior; S.final_cost = INFINITY; S.termination = MM_TERM_NO_CONVERGENCE;
   s->radius = s->opt.initial_trust_region_radius; s->decrease_factor = 2.0; s->iter = 0; s->n_invalid = 0;
-  s->finished = false; s->started = true; s->scaled = false;
+  s->finished = false; s->started = true; s->scaled = false; s->coarse_iter = -1; s->coarse_radius = 0.0;
   if (s->n_obs == 0) { S.termination = MM_TERM_EMPTY; S.initial_cost = S.final_cost = 0.0; S.return_value = NAN; s->finished = true; return MM_OK; }
   int rc;
   { Timer t(s, &S.ms_linearize);

@@ -7,7 +7,10 @@ from mavmap_b200.ba import BASession, default_c_options
 
 cfg = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 8
-t = time.time(); flat, _ = synthetic.make_ba_problem(**synthetic.BA_CONFIGS[cfg]); print("gen %.1fs n_img %d n_pt %d n_obs %d" % (time.time() - t, flat.n_img, flat.n_pt, flat.n_obs))
+refine = os.environ.get("MM_TIME_REFINE") == "1"
+t = time.time(); flat, _ = synthetic.make_ba_problem(refine_camera_params=refine, **synthetic.BA_CONFIGS[cfg]);
+if refine: flat.intr[0, :2] *= 0.998
+print("gen %.1fs n_img %d n_pt %d n_obs %d" % (time.time() - t, flat.n_img, flat.n_pt, flat.n_obs))
 o = default_c_options(); o.max_num_iterations = iters; o.function_tolerance = 0; o.gradient_tolerance = 0
 if len(sys.argv) > 3: o.pcg_tolerance = float(sys.argv[3])
 t = time.time(); s = BASession(flat, o); print("create %.3fs blocks %d coarse dim %d" % (time.time() - t, s.num_blocks(), s.coarse_dim()))
