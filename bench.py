@@ -158,6 +158,7 @@ def main():
     ap.add_argument("--ref-max-steps", type=int, default=12)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-match", action="store_true")
+    ap.add_argument("--no-cfg4", action="store_true", help="skip the extra 5000-image / 10 M observation measurement (N = 1 only)")
     ap.add_argument("--ba-mode", default="replicas", choices=["replicas", "sharded"],
                     help="N > 1: independent problems per GPU (default, north_star: BA stays on one GPU) or ONE problem with its points sharded")
     args = ap.parse_args()
@@ -312,6 +313,32 @@ def main():
                      "e2e": {"value": world / m_e2e, "unit": "pairs/s", "h2d_bytes_per_step": 2 * n_feat * kdim * 4, "d2h_bytes_per_step": 12 * 3000}}
         ms_set.close()
 
+    # ------------------------------------------------------------------ the north_star problem (configs[3]: 5000 cams / 10 M obs), N = 1
+    big = None
+    if rank == 0 and world == 1 and not args.no_cfg4 and args.workload == "ba_cfg2":
+        try:
+            fbig, _ = synthetic.make_ba_problem(**dict(synthetic.BA_CONFIGS["cfg4"]))
+            sb = BASession(fbig.copy(), options(W + K), stream=stream)
+            sb.iterate(W); torch.cuda.synchronize()
+            e0.record(); nb = sb.iterate(K); e1.record(); torch.cuda.synchronize()
+            msb = e0.elapsed_time(e1)
+            k1b = sb.time_kernel(0, 20); k2b = sb.time_kernel(1, 5)
+            sumb = sb.summary().as_dict(); nblk_b = sb.num_blocks(); cdim_b = sb.coarse_dim(); sb.close()
+            k1b_bytes = 184.0 * fbig.n_obs + 48.0 * fbig.n_img + 24.0 * fbig.n_pt
+            k2b_bytes = 168.0 * fbig.n_obs + 72.0 * fbig.n_pt + 216.0 * fbig.n_img + 288.0 * nblk_b
+            big = {"workload": "cfg4: %d images, %d points, %d observations" % (fbig.n_img, fbig.n_pt, fbig.n_obs), "value": nb / (msb * 1e-3), "unit": UNIT,
+                   "ms_per_step": msb / max(nb, 1), "steps": nb, "pcg_iterations": int(sum(sumb["trace_linear_iterations"][W + 1:W + 1 + K])), "coarse_unknowns": cdim_b,
+                   "roofline_K1": {"bound": "hbm", "ms": k1b, "achieved": k1b_bytes / (k1b * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                   "frac": k1b_bytes / (k1b * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+                   "roofline_K2": {"bound": "hbm", "ms": k2b, "achieved": k2b_bytes / (k2b * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                   "frac": k2b_bytes / (k2b * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
+            if not args.no_cpu:
+                ips_b, dt_b, n_b, cores_b, _ = cpu_ba_iterations(fbig, 2)
+                big["cpu_baseline"] = {"value": ips_b, "unit": UNIT, "cores": cores_b, "kind": "port", "sample": "full cfg4 problem, %d LM iterations of the oracle, %.1f s" % (n_b, dt_b)}
+            del fbig
+        except Exception as e:          # the headline line must not depend on the extra measurement
+            big = {"error": repr(e)}
+
     # ------------------------------------------------------------------ pose_refinement latency, rank 0
     pose_lat = None
     if rank == 0:
@@ -360,7 +387,7 @@ def main():
                               "pcg_iterations_in_timed_steps": int(pcg_iters), "k1_ms": k1_ms, "k2_ms": k2_ms, "k4_cost_ms": k4_ms, "pcg_spmv_ms": spmv_ms,
                               "coarse_setup_ms": coarse_ms, "ms_pcg_per_iteration": lin_ms["pcg"] / max(int(pcg_iters), 1),
                               "dominant_by_time": "K3 PCG" if lin_ms["pcg"] > max(lin_ms["schur"], lin_ms["linearize"]) else dominant["kernel"]},
-                "cpu_baseline": cpu, "secondary": secondary, "tertiary": pose_lat, "final_cost": summ["final_cost"]}
+                "cpu_baseline": cpu, "secondary": secondary, "tertiary": pose_lat, "north_star_cfg4": big, "final_cost": summ["final_cost"]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -15,7 +15,7 @@ if has smoke; then
   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke_$TAG.log 2>&1; tail -2 $OUT/smoke_$TAG.log
 fi
 if has bench; then
-  timeout 600 python bench.py > $OUT/bench_${TAG}_cfg2.json 2> $OUT/bench_${TAG}_cfg2.err; tail -c 600 $OUT/bench_${TAG}_cfg2.json
+  timeout 900 python bench.py > $OUT/bench_${TAG}_cfg2.json 2> $OUT/bench_${TAG}_cfg2.err; tail -c 600 $OUT/bench_${TAG}_cfg2.json
   timeout 300 python bench.py --impl reference --steps 3 > $OUT/bench_${TAG}_ref.json 2>> $OUT/bench_${TAG}_cfg2.err
 fi
 if has cfg4; then

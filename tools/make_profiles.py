@@ -31,8 +31,9 @@ for name in ("prof_ba_cfg2", "prof_ba_cfg4", "prof_match"):
             rd = to_bytes(r[hdr.index("dram__bytes_read.sum")], units[hdr.index("dram__bytes_read.sum")]); wr = to_bytes(r[hdr.index("dram__bytes_write.sum")], units[hdr.index("dram__bytes_write.sum")])
             traffic.setdefault(cfg, {})[k.replace(" ", "")] = rd + wr
     out.append("")
-open(os.path.join(P, "ncu_full_%s.txt" % tag), "w").write("\n".join(out))
-json.dump(traffic, open(os.path.join(P, "ncu_traffic.json"), "w"), indent=1, sort_keys=True)
+if traffic:            # only when this round has `--set full` captures
+    open(os.path.join(P, "ncu_full_%s.txt" % tag), "w").write("\n".join(out))
+    json.dump(traffic, open(os.path.join(P, "ncu_traffic.json"), "w"), indent=1, sort_keys=True)
 # launch list: aggregate by kernel
 fn = os.path.join(G, "launches_%s.csv" % tag)
 if os.path.exists(fn):
