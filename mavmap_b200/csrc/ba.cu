@@ -613,9 +613,10 @@ int launch_pcg(mm_ba_session* s) {
     MM_CUDA(cudaStreamSynchronize(st));
     int dev = 0, max_smem = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     s->pcg_cached = false;
-    const int tries[3] = { 512, 256, 128 };
+    const int tries[3] = { 128, 256, 512 };       // smallest CTA whose grid is still co-resident: more SMs share the rows (cfg2: 406 / 392 / 341 LM it/s)
     for (int ti = 0; ti < 3 && !s->pcg_cached && !getenv("MM_PCG_STREAMING") && !s->refine; ++ti) {
       const int threads = tries[ti], NW = threads / 32;
+      if (getenv("MM_PCG_THREADS") && atoi(getenv("MM_PCG_THREADS")) != threads) continue;
       const int blocks = (s->n_img + NW - 1) / NW;
       int e_cap = 1;
       for (int b = 0; b < blocks; ++b) e_cap = std::max(e_cap, h_rs[std::min((b + 1) * NW, s->n_img)] - h_rs[b * NW]);
