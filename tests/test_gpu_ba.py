@@ -295,3 +295,14 @@ def test_two_level_preconditioner_with_refined_intrinsics(mm, orc, monkeypatch):
     s1 = solve_flat(flat.copy(), _opts(8)).as_dict()
     assert s1["trace_accepted"] == sg["trace_accepted"]
     assert two_level * 2 < sum(s1["trace_linear_iterations"])
+
+
+def test_mixed_camera_rig_parity(mm, orc):
+    """BASELINE.json configs[4]: a rig of two different cameras (PINHOLE + OPENCV) in one sequence, intrinsics fixed
+    (bundle_adjustment.cc:339: the model code travels with each camera's parameter vector)."""
+    flat, _ = synthetic.make_ba_problem(outlier_frac=0.0, models=[1, 2], **synthetic.BA_CONFIGS["small"])
+    assert flat.n_cam == 2 and sorted(set(flat.img_cam.tolist())) == [0, 1]
+    _assert_parity(*_both(orc, flat, 10))
+    # three cameras incl. CATA, with the two-level preconditioner switched on (>= 64 images)
+    flat3, _ = synthetic.make_ba_problem(outlier_frac=0.0, models=[1, 2, 3], n_img=90, n_obs_target=60000, track_len=4, seed=31)
+    _assert_parity(*_both(orc, flat3, 8))
