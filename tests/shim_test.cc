@@ -56,6 +56,31 @@ int main() {
   opt.min_track_len = 1; threw = false;
   try { bundle_adjustment(fm, {ids[2], ids[3]}, {ids[0]}, {ids[1]}, opt, errs); } catch (const std::invalid_argument&) { threw = true; }
   CHECK(threw, "std::invalid_argument for min_track_len < 2 (bundle_adjustment.cc:468-471)");
+  // ---- constrain_rotation (bundle_adjustment.cc:390-446): the shim rotates the whole feature manager by M = R_FM' R_C, which turns
+  // the first fixed image's rotation into R_FM R_C' R_FM, keeps every camera-frame point R X + t, and adds one residual per free image
+  {
+    opt.min_track_len = 2; opt.constrain_rotation = true; opt.constrain_rotation_weight = 5.0; opt.max_num_iterations = 8;
+    std::unordered_map<size_t, Eigen::Vector3d> cons;
+    for (size_t id : ids) cons[id] = Eigen::Vector3d(-fm.rvecs[id](0) + 0.001, -fm.rvecs[id](1), -fm.rvecs[id](2));   // ~ camera-to-world rotations
+    cons[ids[0]] = Eigen::Vector3d(0.0, 0.0, 0.3);                                                                       // a real change of frame
+    auto rot = [](const Eigen::Vector3d& r, const Eigen::Vector3d& x) {      // Rodrigues: R(r) x
+      const double t = std::sqrt(r(0) * r(0) + r(1) * r(1) + r(2) * r(2));
+      if (t < 1e-14) return Eigen::Vector3d(x(0), x(1), x(2));
+      const double k0 = r(0) / t, k1 = r(1) / t, k2 = r(2) / t, c = std::cos(t), s_ = std::sin(t), d = (k0 * x(0) + k1 * x(1) + k2 * x(2)) * (1 - c);
+      return Eigen::Vector3d(x(0) * c + (k1 * x(2) - k2 * x(1)) * s_ + k0 * d, x(1) * c + (k2 * x(0) - k0 * x(2)) * s_ + k1 * d, x(2) * c + (k0 * x(1) - k1 * x(0)) * s_ + k2 * d);
+    };
+    const size_t pid0 = fm.point2D_to_point3D[fm.image_to_points2D[ids[0]][0]];
+    const Eigen::Vector3d before = rot(fm.rvecs[ids[0]], fm.points3D[pid0]);      // camera-frame direction of a point in the FIXED image
+    const double c2 = bundle_adjustment(fm, {ids[2], ids[3]}, {ids[0]}, {ids[1]}, opt, errs, cons);
+    const Eigen::Vector3d ez(0, 0, 1), rz = rot(fm.rvecs[ids[0]], ez);
+    // R_FM ~ I here, so the fixed image's new rotation is ~ R_C' = rotation by -0.3 about z: it leaves e_z in place
+    CHECK(std::isfinite(c2) && c2 > 0.0, "bundle_adjustment with constrain_rotation runs");
+    CHECK(std::fabs(rz(2) - 1.0) < 1e-3 && std::fabs(std::fabs(fm.rvecs[ids[0]](2)) - 0.3) < 2e-2, "scene rotated into the frame of the constraints (R' = R M')");
+    // the point moved with the scene (X' = M X) and the fixed pose is not optimised: same camera-frame coordinates up to the BA update of X
+    const Eigen::Vector3d after = rot(fm.rvecs[ids[0]], fm.points3D[pid0]);
+    CHECK(std::fabs(after(0) - before(0)) < 0.1 && std::fabs(after(1) - before(1)) < 0.1 && std::fabs(after(2) - before(2)) < 0.3, "camera-frame geometry kept by the pre-rotation");
+    opt.constrain_rotation = false;
+  }
   // ---- pose refinement
   std::vector<Eigen::Vector2d> p2; std::vector<Eigen::Vector3d> p3; std::vector<bool> mask;
   for (int p = 0; p < n_pt; ++p) { p2.push_back(Eigen::Vector2d(1000 * (X[p](0) + 0.7) / X[p](2) + 640, 1000 * (X[p](1) - 0.2) / X[p](2) + 480)); p3.push_back(X[p]); mask.push_back(p % 9 != 0); }
