@@ -21,6 +21,8 @@ struct File {
   explicit File(const char* path) { f = path ? fopen(path, "rb") : nullptr; }
   ~File() { if (f) fclose(f); }
   bool read(void* dst, size_t n) { return f && fread(dst, 1, n, f) == n; }
+  // bytes left between the current position and the end of the file (headers announce payload sizes: check before allocating)
+  uint64_t remaining() { if (!f) return 0; const long pos = ftell(f); fseek(f, 0, SEEK_END); const long end = ftell(f); fseek(f, pos, SEEK_SET); return end > pos ? (uint64_t)(end - pos) : 0; }
 };
 
 int read_desc_header(File& d, const char* path, uint64_t* nbytes, int32_t* rows, int32_t* cols, int32_t* type) {
@@ -54,6 +56,7 @@ int mm_feature_cache_read(const char* keypoints_path, const char* descriptors_pa
   if (nbytes != (uint64_t)rows * (uint64_t)cols * 4u) { mm::set_error("%s: %llu data bytes for a %d x %d float matrix", descriptors_path, (unsigned long long)nbytes, rows, cols); return MM_ERR_INVALID_ARG; }
   if (n_kp != rows) { mm::set_error("%lld keypoints but %d descriptor rows", (long long)n_kp, rows); return MM_ERR_INVALID_ARG; }
   if (rows > cap_rows || (rows > 0 && cols != cols_expected)) { mm::set_error("buffer too small or descriptor length mismatch (%d x %d)", rows, cols); return MM_ERR_INVALID_ARG; }
+  if (kb > k.remaining() || nbytes > d.remaining()) { mm::set_error("truncated feature cache file (%s / %s)", keypoints_path, descriptors_path); return MM_ERR_INVALID_ARG; }
   std::vector<unsigned char> raw((size_t)kb);
   if (kb && !k.read(raw.data(), (size_t)kb)) { mm::set_error("truncated %s", keypoints_path); return MM_ERR_INVALID_ARG; }
   if (xy) for (int64_t i = 0; i < n_kp; ++i) memcpy(xy + 2 * i, raw.data() + (size_t)i * KEYPOINT_BYTES, 8);      // KeyPoint::pt

@@ -50,3 +50,11 @@ def test_match_set_from_cache_equals_match_set_from_arrays(tmp_path, mm):
         for u, v in zip(ra, rb):
             np.testing.assert_array_equal(u, v)
     a.close(); b.close()
+
+
+def test_header_that_announces_more_than_the_file_holds(tmp_path):
+    """a corrupt size field must be rejected before anything is allocated from it"""
+    desc, xy, kps, dps = _files(tmp_path, n_img=1)
+    raw = bytearray(open(kps[0], "rb").read()); raw[0:8] = np.uint64(28 * 10 ** 9).tobytes(); open(kps[0], "wb").write(bytes(raw))
+    with pytest.raises(Exception):
+        matching.read_feature_cache(kps[0], dps[0])
