@@ -306,3 +306,28 @@ def test_mixed_camera_rig_parity(mm, orc):
     # three cameras incl. CATA, with the two-level preconditioner switched on (>= 64 images)
     flat3, _ = synthetic.make_ba_problem(outlier_frac=0.0, models=[1, 2, 3], n_img=90, n_obs_target=60000, track_len=4, seed=31)
     _assert_parity(*_both(orc, flat3, 8))
+
+
+def test_device_reproduces_committed_golden_traces(mm):
+    """the CUDA path against the committed fixtures directly (tests/golden/ba_trace.json, extra.json): LM cost / radius traces,
+    step pattern and parameter checksums of the seeded tiny problems, and the rotation-constrained trace"""
+    import json, os, sys
+    from conftest import GOLDEN
+    gold = json.load(open(os.path.join(GOLDEN, "ba_trace.json")))
+    for name, kw, model, refine in [("tiny_pinhole", synthetic.BA_CONFIGS["tiny"], 1, False),
+                                    ("tiny_opencv", dict(synthetic.BA_CONFIGS["tiny"], seed=77), 2, False),
+                                    ("tiny_cata_refine", dict(synthetic.BA_CONFIGS["tiny"], seed=78), 3, True)]:
+        flat, _ = synthetic.make_ba_problem(model=model, refine_camera_params=refine, **kw)
+        s = solve_flat(flat, _opts(8)).as_dict()
+        np.testing.assert_allclose(s["trace_cost"], gold[name]["trace_cost"], rtol=REL)
+        np.testing.assert_allclose(s["trace_radius"], gold[name]["trace_radius"], rtol=1e-5)
+        assert s["trace_accepted"] == gold[name]["trace_accepted"]
+        np.testing.assert_allclose(np.abs(flat.poses).sum(), gold[name]["poses_sum"], rtol=1e-5 if refine else REL)   # (refine: see the oracle's own spread above)
+    sys.path.insert(0, GOLDEN)
+    import make_golden_extra as mg
+    g = json.load(open(os.path.join(GOLDEN, "extra.json")))["ba_rotation_constraints"]
+    flat = mg.constrained_problem()
+    s = solve_flat(flat, _opts(8)).as_dict()
+    np.testing.assert_allclose(s["trace_cost"], g["trace_cost"], rtol=REL)
+    assert s["trace_accepted"] == g["trace_accepted"] and s["num_residuals"] == g["num_residuals"]
+    np.testing.assert_allclose(np.abs(flat.poses).sum(), g["poses_sum"], rtol=REL)

@@ -2,6 +2,7 @@
 the FeatureManager (bundle_adjustment.cc:228-387, 459-471)."""
 import json
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -196,3 +197,19 @@ def test_bundle_adjustment_with_rotation_constraints_oracle():
     ret2 = orc.bundle_adjustment(fm2, ids2[2:], ids2[:1], ids2[1:2], mm.BundleAdjustmentOptions(**kw), {})
     assert not np.allclose(fm2.rvecs[ids2[2]], fm.rvecs[ids[2]], atol=1e-6) and ret2 < ret
     assert prior(fm) < prior(fm2)                  # the constrained solve ends closer to the constraints than the free one
+
+
+def test_oracle_reproduces_extra_goldens(orc):
+    """tests/golden/extra.json (made by make_golden_extra.py): rotation-constraint functor and a constrained LM trace"""
+    sys.path.insert(0, GOLDEN)
+    import make_golden_extra as mg
+    gold = json.load(open(os.path.join(GOLDEN, "extra.json")))
+    for case in gold["rot_prior"]:
+        r, J = orc.rot_prior(case["rvec"], case["rvec0"], case["weight"])
+        assert abs(r - case["r"]) <= 1e-12 * max(1.0, abs(case["r"]))
+        np.testing.assert_allclose(J, case["J"], rtol=1e-10, atol=1e-12)
+    flat = mg.constrained_problem()
+    s = orc.solve_flat(flat, _opts(orc)).as_dict()
+    g = gold["ba_rotation_constraints"]
+    np.testing.assert_allclose(s["trace_cost"], g["trace_cost"], rtol=1e-9)
+    assert s["trace_accepted"] == g["trace_accepted"] and s["num_residuals"] == g["num_residuals"]

@@ -188,3 +188,15 @@ def test_ransac_score_oracle_matches_numpy(kind):
         assert abs(int(inl.sum()) - int(o["num_inliers"][h])) <= 1            # a residual within an ulp of the threshold may flip
         assert abs(r[inl].sum() - o["residual_sum"][h]) < 1e-6 * max(1.0, r[inl].sum())
     assert o["best"] == 0 and o["inlier_mask"].sum() == o["num_inliers"][0] > 0.6 * len(x)
+
+
+def test_ransac_score_oracle_reproduces_golden():
+    import json, os, sys
+    from conftest import GOLDEN
+    from oracle import orc
+    gold = json.load(open(os.path.join(GOLDEN, "extra.json")))["ransac"]
+    for kind in (0, 1, 2):
+        models, x, y, thr = _ransac_case(kind, n=2000, h=16, seed=21)
+        r = orc.ransac_score(kind, models, x, y, thr)
+        assert r["num_inliers"].tolist() == gold[str(kind)]["num_inliers"] and r["best"] == gold[str(kind)]["best"]
+        np.testing.assert_allclose(r["residual_sum"], gold[str(kind)]["residual_sum"], rtol=1e-12)
