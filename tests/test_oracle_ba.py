@@ -213,3 +213,45 @@ def test_oracle_reproduces_extra_goldens(orc):
     g = gold["ba_rotation_constraints"]
     np.testing.assert_allclose(s["trace_cost"], g["trace_cost"], rtol=1e-9)
     assert s["trace_accepted"] == g["trace_accepted"] and s["num_residuals"] == g["num_residuals"]
+
+
+def test_oracle_objective_and_minimum_against_independent_numpy(orc):
+    """Independent cross-check of WHAT the oracle minimises (residual of bundle_adjustment.h:131-159 for the OPENCV model,
+    Cauchy loss of bundle_adjustment.cc:477-478, gauge by constant parameters): a numpy objective written from
+    mavmap_b200.synthetic's own camera-model code must (1) equal the oracle's cost at the start, (2) equal it at the oracle's
+    final iterate, and (3) be stationary there (central-difference gradient ~ 0 against its size at the start).
+    Pins the objective and the optimum, not the LM trajectory (Ceres is not available: DESIGN.md section 2)."""
+    from mavmap_b200.synthetic import _rodrigues, project
+    flat, _ = synthetic.make_ba_problem(n_img=5, n_obs_target=500, track_len=4, seed=91, model=2, outlier_frac=0.02)
+    o = orc.default_options(); o.max_num_iterations = 100; o.function_tolerance = 1e-16; o.gradient_tolerance = 1e-14; o.parameter_tolerance = 1e-14
+    f = flat.copy(); s = orc.solve_flat(f, o).as_dict()
+    free_pose = np.ones((flat.n_img, 6), bool)
+    for i in range(flat.n_img):
+        c = flat.pose_const[i]
+        free_pose[i, :3] = not c[0]; free_pose[i, 3] = not c[1]; free_pose[i, 4] = not c[2]; free_pose[i, 5] = not c[3]
+    nfp = int(free_pose.sum())
+
+    def objective(z):
+        poses = flat.poses.copy(); poses[free_pose] = z[:nfp]
+        pts = z[nfp:].reshape(-1, 3)
+        c = 0.0
+        for i in range(flat.n_img):
+            sel = flat.obs_img == i
+            Xc = pts[flat.obs_pt[sel]] @ _rodrigues(poses[i, :3])[0].T + poses[i, 3:]
+            r = project(2, flat.intr[0], Xc) - flat.obs_xy[sel]
+            c += 0.5 * np.sum(np.log1p(np.sum(r * r, axis=1)))       # rho(s) = a^2 log(1 + s / a^2), a = loss_scale_factor = 1
+        return c
+
+    def gradient(z, h=1e-6):
+        g = np.empty_like(z)
+        for k in range(len(z)):
+            e = np.zeros_like(z); e[k] = h
+            g[k] = (objective(z + e) - objective(z - e)) / (2 * h)
+        return g
+    z0 = np.concatenate([flat.poses[free_pose], flat.pts.ravel()])
+    z1 = np.concatenate([f.poses[free_pose], f.pts.ravel()])
+    assert abs(objective(z0) - s["initial_cost"]) < 1e-9 * s["initial_cost"]
+    assert abs(objective(z1) - s["final_cost"]) < 1e-9 * s["final_cost"]
+    assert s["final_cost"] < 0.5 * s["initial_cost"]
+    g0, g1 = gradient(z0), gradient(z1)
+    assert np.abs(g1).max() < 1e-5 * np.abs(g0).max()
