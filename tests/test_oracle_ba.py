@@ -255,3 +255,46 @@ def test_oracle_objective_and_minimum_against_independent_numpy(orc):
     assert s["final_cost"] < 0.5 * s["initial_cost"]
     g0, g1 = gradient(z0), gradient(z1)
     assert np.abs(g1).max() < 1e-5 * np.abs(g0).max()
+
+
+def test_oracle_first_lm_step_against_dense_numpy(orc):
+    """One Levenberg-Marquardt step restated densely in numpy with a NUMERICAL Jacobian (independent of the oracle's dual
+    numbers and of its Schur elimination): Triggs-corrected Cauchy residuals (sqrt(rho') scaling, rho'' < 0), Jacobi column
+    scaling 1/(1 + ||col||), D^2 = clamp(diag J'J, 1e-6, 1e32) / radius with the initial radius 1e4, step = -scale * y from
+    (J'J + D^2) y = J'r.  The cost after that step must equal the oracle's trace entry 1 (SURVEY 8a-a3')."""
+    from mavmap_b200.synthetic import _rodrigues, project
+    flat, _ = synthetic.make_ba_problem(n_img=5, n_obs_target=500, track_len=4, seed=92, model=2, outlier_frac=0.02)
+    s = orc.solve_flat(flat.copy(), _opts(orc, 1)).as_dict()
+    assert s["trace_accepted"][1] == 1
+    free_pose = np.ones((flat.n_img, 6), bool)
+    for i in range(flat.n_img):
+        c = flat.pose_const[i]
+        free_pose[i, :3] = not c[0]; free_pose[i, 3] = not c[1]; free_pose[i, 4] = not c[2]; free_pose[i, 5] = not c[3]
+    nfp = int(free_pose.sum())
+
+    def raw(z):
+        poses = flat.poses.copy(); poses[free_pose] = z[:nfp]
+        pts = z[nfp:].reshape(-1, 3)
+        r = np.empty((flat.n_obs, 2))
+        for i in range(flat.n_img):
+            sel = flat.obs_img == i
+            Xc = pts[flat.obs_pt[sel]] @ _rodrigues(poses[i, :3])[0].T + poses[i, 3:]
+            r[sel] = project(2, flat.intr[0], Xc) - flat.obs_xy[sel]
+        return r
+    cost = lambda z: 0.5 * np.sum(np.log1p(np.sum(raw(z) ** 2, axis=1)))
+    z0 = np.concatenate([flat.poses[free_pose], flat.pts.ravel()])
+    r0 = raw(z0); n = len(z0)
+    J = np.empty((2 * flat.n_obs, n)); h = 1e-6
+    for k in range(n):
+        e = np.zeros(n); e[k] = h
+        J[:, k] = ((raw(z0 + e) - raw(z0 - e)) / (2 * h)).ravel()
+    w = np.sqrt(1.0 / (1.0 + np.sum(r0 ** 2, axis=1)))               # sqrt(rho'), one per observation
+    rt = (r0 * w[:, None]).ravel(); Jt = J * np.repeat(w, 2)[:, None]
+    scale = 1.0 / (1.0 + np.linalg.norm(Jt, axis=0))
+    Js = Jt * scale
+    A = Js.T @ Js
+    D2 = np.clip(np.diag(A), 1e-6, 1e32) / 1e4
+    y = np.linalg.solve(A + np.diag(D2), Js.T @ rt)
+    z1 = z0 - scale * y
+    assert abs(cost(z0) - s["trace_cost"][0]) < 1e-9 * s["trace_cost"][0]
+    assert abs(cost(z1) - s["trace_cost"][1]) < 1e-7 * s["trace_cost"][1], (cost(z1), s["trace_cost"][1])
