@@ -4,9 +4,11 @@
 // mm_ba_solve / mm_pose_refine (include/mavmap_b200.h).
 #include "base3d/bundle_adjustment.h"
 
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <iomanip>
 #include <iostream>
@@ -99,6 +101,7 @@ double bundle_adjustment(FeatureManager& fm, const std::vector<size_t>& free_ima
                          const BundleAdjustmentOptions& options, std::unordered_map<size_t, double>& point3D_errors,
                          const std::unordered_map<size_t, Eigen::Vector3d>& rotation_constraints,
                          const std::set<size_t>& gcp_ids) {
+  const auto t_enter = std::chrono::steady_clock::now();
   const size_t num_fixed_params = fixed_image_ids.size() * 6 + fixed_x_image_ids.size() + gcp_ids.size() * 3;
   if (num_fixed_params < 7)                                                   // .cc:459-466
     throw std::invalid_argument("At least 7 parameters should be set as fixed to avoid datum defects resulting in a singular Jacobian.");
@@ -217,7 +220,9 @@ double bundle_adjustment(FeatureManager& fm, const std::vector<size_t>& free_ima
   if (P.n_obs == 0) std::cout << "No observations in bundle adjustment. Consider relaxing the constraints." << std::endl;   // .cc:571-573
 
   mm_ba_options c = to_options(options); mm_ba_summary s;
+  const auto t_flat = std::chrono::steady_clock::now();
   throw_for(mm_ba_solve(&P, &c, &s));
+  const auto t_solved = std::chrono::steady_clock::now();
 
   // the reference optimises the FeatureManager storage in place (.cc:243-247, 269-270)
   for (size_t k = 0; k < n_img; ++k) {
@@ -234,6 +239,12 @@ double bundle_adjustment(FeatureManager& fm, const std::vector<size_t>& free_ima
   }
   if (options.update_point3D_errors)                                         // .cc:575-598
     for (size_t k = 0; k < point_ids.size(); ++k) point3D_errors[point_ids[k]] = pt_err[k];
+  if (std::getenv("MM_SHIM_TIMING")) {       // FeatureManager walk (hash maps) vs the device call, SURVEY 8a-a9
+    const auto t_done = std::chrono::steady_clock::now();
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    std::printf("[mavmap_b200 shim] %zu images, %zu points, %zu observations: flatten %.3f ms, mm_ba_solve %.3f ms (device %.3f ms), write-back %.3f ms\n",
+                n_img, point_ids.size(), obs_img.size(), ms(t_enter, t_flat), ms(t_flat, t_solved), s.ms_total, ms(t_solved, t_done));
+  }
   if (options.print_progress) std::cout << std::endl;
   if (options.print_summary) {
     long long npar = 0;

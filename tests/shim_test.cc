@@ -108,6 +108,34 @@ int main() {
   const std::vector<double> re = calc_reproj_errors(x2, T, P2);
   double wre = 0; for (double e : re) wre = std::fmax(wre, e);
   CHECK(wre < 1e-10 && std::fabs(calc_depth(P2, T[0]) - X[0](2)) < 1e-9, "calc_reproj_errors / calc_depth");
+  // ---- a larger feature manager: what the marshalling costs next to the device call (printed with MM_SHIM_TIMING=1)
+  {
+    FeatureManager big;
+    const size_t cam2 = big.add_camera({1000.0, 1000.0, 640.0, 480.0, 1});
+    const int NI = 60, NP = 6000;
+    std::vector<Eigen::Vector3d> XB(NP);
+    for (auto& x : XB) x = Eigen::Vector3d(30 * U(rng) + 30, 4 * U(rng), 40 + 4 * U(rng));
+    std::vector<size_t> bid;
+    for (int i = 0; i < NI; ++i) {
+      const double tx = -1.0 * i;
+      std::vector<Eigen::Vector2d> uv(NP);
+      for (int p = 0; p < NP; ++p) uv[p] = Eigen::Vector2d(1000 * (XB[p](0) + tx) / XB[p](2) + 640 + 0.3 * N(rng), 1000 * XB[p](1) / XB[p](2) + 480 + 0.3 * N(rng));
+      const size_t id = big.add_image(cam2, uv);
+      big.rvecs[id] = Eigen::Vector3d(0.002 * N(rng), 0.002 * N(rng), 0.002 * N(rng));
+      big.tvecs[id] = Eigen::Vector3d(tx + 0.02 * N(rng), 0.02 * N(rng), 0.02 * N(rng));
+      bid.push_back(id);
+    }
+    for (int p = 0; p < NP; ++p) {
+      const size_t pid = big.add_point3D();
+      big.points3D[pid] = Eigen::Vector3d(XB[p](0) + 0.05 * N(rng), XB[p](1) + 0.05 * N(rng), XB[p](2) + 0.05 * N(rng));
+      for (int i = p % 7; i < NI; i += 7) big.point2D_to_point3D[big.image_to_points2D[bid[i]][p]] = pid;      // ~8 observations per point
+    }
+    BundleAdjustmentOptions bo; bo.print_summary = false; bo.max_num_iterations = 5;
+    std::unordered_map<size_t, double> e2;
+    std::vector<size_t> free_ids(bid.begin() + 2, bid.end());
+    const double cb = bundle_adjustment(big, free_ids, {bid[0]}, {bid[1]}, bo, e2);
+    CHECK(std::isfinite(cb) && cb < 1.0, "bundle_adjustment on a 60-image feature manager (timing: MM_SHIM_TIMING=1)");
+  }
   std::printf("%d failure(s)\n", fails);
   return fails ? 1 : 0;
 }
