@@ -211,9 +211,11 @@ def test_sharded_ba_two_gpus_matches_single_gpu(mm):
     from mavmap_b200 import _lib
     if _lib.device_count() < 2:
         pytest.skip("needs 2 GPUs")
+    import socket
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sk = socket.socket(); sk.bind(("127.0.0.1", 0)); port = sk.getsockname()[1]; sk.close()
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29517", os.path.join(root, "tools", "sharded_ba.py"), "mid"], capture_output=True, text=True, timeout=600)
+                        "--master-port", str(port), os.path.join(root, "tools", "sharded_ba.py"), "mid"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
