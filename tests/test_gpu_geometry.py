@@ -78,3 +78,4 @@ def test_ransac_score_bit_exact_against_oracle(mm, orc, kind):
     np.testing.assert_array_equal(g["inlier_mask"], o["inlier_mask"])
     e = ransac_score(kind, models[:0], x, y, thr)
     assert e["best"] == -1
+

@@ -200,3 +200,32 @@ def test_ransac_score_oracle_reproduces_golden():
         r = orc.ransac_score(kind, models, x, y, thr)
         assert r["num_inliers"].tolist() == gold[str(kind)]["num_inliers"] and r["best"] == gold[str(kind)]["best"]
         np.testing.assert_allclose(r["residual_sum"], gold[str(kind)]["residual_sum"], rtol=1e-12)
+
+
+def _ransac_homography(score_fn, seed=5, n=1000, n_out=400, trials=60, thr=1.0):
+    """RANSAC as util/estimation.cc:26-146 runs it, with the SCORING step delegated to `score_fn` (all hypotheses of a batch at
+    once): the data layout of estimation_test.cc:19-66 (first 400 of 1000 correspondences are gross outliers), for a homography."""
+    rng = np.random.default_rng(seed)
+    H = np.array([[1.05, 0.03, 12.0], [-0.02, 0.97, -7.0], [2e-5, -1e-5, 1.0]])
+    src = np.stack([np.arange(n, dtype=float), np.sqrt(np.arange(n)) * 20 + 2], axis=1)
+    d = np.hstack([src, np.ones((n, 1))]) @ H.T; dst = d[:, :2] / d[:, 2:]
+    dst[:n_out] = rng.uniform(-6000, -2000, (n_out, 2))
+    models = []
+    for _ in range(trials):                       # 4-point DLT hypotheses on the host
+        idx = rng.choice(n, 4, replace=False)
+        A = []
+        for (x, y), (u, v) in zip(src[idx], dst[idx]):
+            A.append([-x, -y, -1, 0, 0, 0, u * x, u * y, u]); A.append([0, 0, 0, -x, -y, -1, v * x, v * y, v])
+        h = np.linalg.svd(np.array(A))[2][-1]
+        models.append((h / h[8]).reshape(3, 3) if abs(h[8]) > 1e-12 else np.eye(3))
+    r = score_fn(1, np.array(models), src, dst, thr)
+    return r, models, H, n, n_out
+
+
+def test_ransac_loop_separates_outliers_like_estimation_test():
+    """mirror of estimation_test.cc:19-66 (400 gross outliers of 1000 must be rejected exactly) with the oracle scorer"""
+    from oracle import orc
+    r, models, H, n, n_out = _ransac_homography(orc.ransac_score)
+    assert r["num_inliers"][r["best"]] == n - n_out
+    assert not r["inlier_mask"][:n_out].any() and r["inlier_mask"][n_out:].all()
+    assert np.abs(models[r["best"]] - H).max() < 1e-6 * np.abs(H).max()
