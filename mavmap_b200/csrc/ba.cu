@@ -1110,8 +1110,3 @@ int mm_pose_refine(double* rvec, double* tvec, int model_code, const double* par
 }
 
 }  // extern "C"
-
-// register probe (not launched)
-template __global__ void mm::k_residual_jacobian<true, false, 1, 2>(int64_t, const double2*, const int*, const int*, const double*, const double*, const double*, const int*, const int*, const double*, const double*, mm::LossParams, double*, double*, double*, const double*);
-template __global__ void mm::k_residual_jacobian<true, false, 1, 3>(int64_t, const double2*, const int*, const int*, const double*, const double*, const double*, const int*, const int*, const double*, const double*, mm::LossParams, double*, double*, double*, const double*);
-template __global__ void mm::k_residual_jacobian<true, false, 2, 3>(int64_t, const double2*, const int*, const int*, const double*, const double*, const double*, const int*, const int*, const double*, const double*, mm::LossParams, double*, double*, double*, const double*);

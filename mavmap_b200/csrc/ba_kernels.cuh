@@ -65,8 +65,8 @@ constexpr size_t K1_SMEM = sizeof(double) * 8 * K1_WARP_DOUBLES + sizeof(int) * 
 constexpr size_t K1_SMEM_COST = K1_SMEM;
 
 
-template <bool WITH_J, bool WITH_JI = false, int MODEL = 0, int MINB = (WITH_J ? 2 : 3)>
-__global__ void __launch_bounds__(256, MINB) k_residual_jacobian(
+template <bool WITH_J, bool WITH_JI = false>
+__global__ void __launch_bounds__(256, WITH_J ? 2 : 3) k_residual_jacobian(
     int64_t n_obs, const double2* __restrict__ obs_xy, const int* __restrict__ obs_img, const int* __restrict__ obs_pt,
     const double* __restrict__ aux, const double* __restrict__ pts, const double* __restrict__ intr,
     const int* __restrict__ img_cam, const int* __restrict__ cam_model,
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256, MINB) k_residual_jacobian(
     const double Y2 = R[6] * X0 + R[7] * X1 + R[8] * X2;
     const double xc = Y0 + a[9], yc = Y1 + a[10], zc = Y2 + a[11];
     const int cam = img_cam[img];
-    const int model = MODEL ? MODEL : cam_model[cam];
+    const int model = cam_model[cam];
     double u, v, dX[2][3], dP[2][9];
     world2image<WITH_J>(model, intr + MM_INTR_STRIDE * (size_t)cam, xc, yc, zc, u, v, dX, WITH_JI ? dP : nullptr);
     const double r0 = u - xy.x, r1 = v - xy.y;
