@@ -34,3 +34,22 @@ def test_shim_runs_reference_style_calls(mm):
     print(out.stdout)
     assert out.returncode == 0, out.stdout
     assert out.stdout.count("ok  ") >= 9 and "FAIL" not in out.stdout
+
+
+def test_shim_compiles_against_the_reference_feature_manager_header():
+    """the BA shim against the REFERENCE's own src/fm/feature_management.h (with the small Eigen stand-in
+    that also builds oracle/_ref), not the test stub: the members it walks (rvecs, tvecs, points2D, points3D,
+    image_to_points2D, point2D_to_point3D, image_to_camera, camera_params) exist there with the types it assumes.
+    Only possible where the reference tree is mounted (build container)."""
+    ref = "/root/reference/src"
+    if not os.path.exists(os.path.join(ref, "fm", "feature_management.h")):
+        pytest.skip("reference tree not present")
+    obj = os.path.join(ROOT, "build", "shim_ba_vs_reference_fm.o")
+    os.makedirs(os.path.dirname(obj), exist_ok=True)
+    # shim include path first: "base3d/bundle_adjustment.h" is the drop-in header, "fm/feature_management.h" the reference's
+    subprocess.check_call(["/usr/bin/g++", "-std=c++11", "-Wall", "-c", "-I" + SHIM, "-I" + os.path.join(ROOT, "oracle", "ref_wrap"), "-I" + ref,
+                           "-I" + os.path.join(ROOT, "include"), os.path.join(SHIM, "base3d", "bundle_adjustment.cc"), "-o", obj])
+    # and the reference's own FeatureManager implementation builds next to it with the same stand-in
+    subprocess.check_call(["/usr/bin/g++", "-std=c++11", "-c", "-I" + os.path.join(ROOT, "oracle", "ref_wrap"), "-I" + ref,
+                           os.path.join(ref, "fm", "feature_management.cc"), "-o", os.path.join(ROOT, "build", "ref_feature_management.o")])
+    assert os.path.getsize(obj) > 0
