@@ -252,6 +252,17 @@ def main():
     roof_k3 = {"kernel": "k_pcg_spmv (K3, one PCG iteration's SpMV)", "bound": "hbm", "achieved": k3_bytes / (spmv_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                "unit": "GB/s", "traffic": None, "ms": spmv_ms}
     roof_k3["frac"] = roof_k3["achieved"] / roof_k3["peak"]
+    # the persistent solver as it runs inside the step: bytes one PCG iteration touches (blocks through both row references, five
+    # vectors, the dense coarse inverse) over the measured time per iteration; S and the inverse are L2 / shared-memory resident,
+    # so this is a bandwidth figure for orientation, not an HBM-bound kernel
+    try:
+        per_it_ms = lin_ms["pcg"] / max(int(pcg_iters), 1)
+        k3_it_bytes = k3_bytes + 8.0 * coarse_dim * coarse_dim
+        roof_k3p = {"kernel": "persistent PCG kernel, one iteration (K3; dominant by time)", "bound": "hbm", "achieved": k3_it_bytes / (per_it_ms * 1e-3) / 1e9 if per_it_ms > 0 else 0.0,
+                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "traffic": None, "ms": per_it_ms, "note": "operands resident in L2 / shared memory: latency- and barrier-bound (3 grid barriers per iteration)"}
+        roof_k3p["frac"] = roof_k3p["achieved"] / roof_k3p["peak"]
+    except Exception as e:      # orientation figure only: never let it take the headline line down
+        roof_k3p = {"kernel": "persistent PCG kernel", "error": repr(e)}
     sess.close()
 
     # ------------------------------------------------------------------ BA, end to end through mm_ba_solve (host buffers)
@@ -382,7 +393,7 @@ def main():
                            "pcg_preconditioner": ("two-level: block-Jacobi + %d similarity-mode coarse unknowns" % coarse_dim) if coarse_dim else "block-Jacobi"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": dict(roof_k1, note="K1 is the kernel north_star names; share of the step is in `breakdown`"),
-                "roofline_other": [roof_k2, roof_k3],
+                "roofline_other": [roof_k2, roof_k3, roof_k3p],
                 "breakdown": {"ms_linearize_K1": lin_ms["linearize"], "ms_schur_K2": lin_ms["schur"], "ms_pcg_K3": lin_ms["pcg"], "ms_update_K4": lin_ms["update"],
                               "pcg_iterations_in_timed_steps": int(pcg_iters), "k1_ms": k1_ms, "k2_ms": k2_ms, "k4_cost_ms": k4_ms, "pcg_spmv_ms": spmv_ms,
                               "coarse_setup_ms": coarse_ms, "ms_pcg_per_iteration": lin_ms["pcg"] / max(int(pcg_iters), 1),
