@@ -180,8 +180,13 @@ int mm_match_set_create_from_cache(const char* const* keypoints_paths, const cha
 #define MM_LOSS_TRIVIAL 0
 #define MM_LOSS_CAUCHY  1     /* ceres::CauchyLoss(loss_scale) bundle_adjustment.cc:477-478 */
 
-#define MM_SOLVER_PCG      0  /* block-Jacobi PCG on the reduced camera system (device)     */
+#define MM_SOLVER_PCG      0  /* preconditioned CG on the reduced camera system (device)    */
 #define MM_SOLVER_CHOLESKY 1  /* direct Cholesky of the reduced system (oracle; = SPARSE_SCHUR) */
+
+/* preconditioner of the device PCG */
+#define MM_PRECOND_AUTO          0  /* sparse tile Cholesky where its tiles fit in memory, else two-level   */
+#define MM_PRECOND_TWO_LEVEL     1  /* block-Jacobi + similarity-mode aggregates (fixed intrinsics only)    */
+#define MM_PRECOND_TILE_CHOLESKY 2  /* exact sparse tile Cholesky of the reduced system (1-2 PCG iterations) */
 
 /* Flat SoA view of the FeatureManager subset that takes part in one BA
  * (feature_management.h:189-230 flattened per SURVEY.md §8a-a9).
@@ -237,6 +242,7 @@ typedef struct mm_ba_options {
   double  pcg_tolerance;        /* relative residual ||S y - b|| / ||b||, 1e-13 */
   int32_t pcg_max_iterations;   /* 2000 */
   int32_t print_progress;       /* 0 */
+  int32_t pcg_preconditioner;   /* MM_PRECOND_AUTO */
 } mm_ba_options;
 
 void mm_ba_options_default(mm_ba_options* o);
@@ -304,6 +310,25 @@ int32_t mm_ba_session_coarse_dim(mm_ba_session* s);
 /* Test hook for the blocked Gauss-Jordan kernel that inverts the coarse matrix: a (m x m, row-major,
  * symmetric positive definite, host memory) is replaced by its inverse. */
 int  mm_debug_spd_inverse(double* a, int32_t m);
+/* Test hooks of the sparse tile Cholesky that preconditions the PCG (csrc/tilechol_plan.h, tilechol.cuh).
+ * plan_create runs the host-side symbolic analysis (nested dissection, tile structure, task lists) for a block graph given by
+ * its off-diagonal blocks (blk_a[e], blk_b[e]); pos = optional camera centres [3 n_img]; n_cam_border = cameras whose 9
+ * intrinsics form the dense border.  plan_array copies one of the plan's integer arrays (widened to int64) and returns its
+ * length (out may be NULL): 0 scalars {nt_pose, nt, n_l, n_upd, n_nodes, max_height, flops, T, TI, n_w, n_wtask, n_slots,
+ * n_stasks, n_tnodes}, 1 img_tile, 2 img_slot, 3 tile_nunk, 4 col_ptr, 5 row_idx, 6 col_idx, 7 has_a, 8 upd_ptr, 9 upd_a,
+ * 10 upd_b, 11 rowp_ptr, 12 rowp_tile, 13 rowp_col, 14 unk_of, 15 sc_tile, 16 sc_off, 17 tile_height, 18 tile_node,
+ * 19 node_first, 20 node_nt, 21 w_row_ptr, 22 wt_row, 23 wt_col, 24 wt_store, 25 wupd_ptr, 26 wupd_l, 27 wupd_w, 28 wupd_flag,
+ * 29 task_order, 30 st_kind, 31 st_out, 32 st_base, 33 st_tile, 34 st_item_ptr, 35 it_mat, 36 it_src (see
+ * csrc/tilechol_plan.h for their meaning).  No device needed.
+ * tilechol_solve factorises on the device and returns z = M^-1 rhs (needs a device). */
+typedef struct mm_tilechol_plan mm_tilechol_plan;
+int  mm_debug_tilechol_plan_create(int32_t n_img, int32_t n_off, const int32_t* blk_a, const int32_t* blk_b, const double* pos,
+                                   int32_t n_cam_border, mm_tilechol_plan** out);
+int64_t mm_debug_tilechol_plan_array(mm_tilechol_plan* plan, int32_t which, int64_t* out, int64_t cap);
+void mm_debug_tilechol_plan_destroy(mm_tilechol_plan* plan);
+int  mm_debug_tilechol_solve(int32_t n_img, int32_t n_off, const int32_t* blk_a, const int32_t* blk_b, const double* pos, const double* S,
+                             int32_t n_cam_border, const double* Bm, const double* Cm, const double* rhs, double* z, int32_t reps,
+                             double* ms_factor, double* ms_apply);
 void mm_ba_session_destroy(mm_ba_session* s);
 
 /* pose_refinement (bundle_adjustment.cc:139-225): 6-dof refinement of one pose,

@@ -23,6 +23,7 @@ MM_MATCH_IMPL_AUTO, MM_MATCH_IMPL_SIMT, MM_MATCH_IMPL_TCGEN05 = 0, 1, 2
 MM_POSE_FREE, MM_POSE_FIXED, MM_POSE_FIXED_X = 0, 1, 2
 MM_LOSS_TRIVIAL, MM_LOSS_CAUCHY = 0, 1
 MM_SOLVER_PCG, MM_SOLVER_CHOLESKY = 0, 1
+MM_PRECOND_AUTO, MM_PRECOND_TWO_LEVEL, MM_PRECOND_TILE_CHOLESKY = 0, 1, 2
 MM_BA_TRACE_MAX = 512
 TERMINATION = {0: "NO_CONVERGENCE", 1: "FUNCTION_TOLERANCE", 2: "GRADIENT_TOLERANCE",
                3: "PARAMETER_TOLERANCE", 4: "NUMERICAL_FAILURE", 5: "EMPTY"}
@@ -61,7 +62,8 @@ class BAOptions(C.Structure):
                 ("jacobi_scaling", C.c_int32),
                 ("max_num_consecutive_invalid_steps", C.c_int32),
                 ("linear_solver", C.c_int32), ("pcg_tolerance", C.c_double),
-                ("pcg_max_iterations", C.c_int32), ("print_progress", C.c_int32)]
+                ("pcg_max_iterations", C.c_int32), ("print_progress", C.c_int32),
+                ("pcg_preconditioner", C.c_int32)]
 
 
 class BASummary(C.Structure):
@@ -147,6 +149,10 @@ PROTOTYPES = {
     "mm_ba_session_num_blocks": (C.c_int64, [C.c_void_p]),
     "mm_ba_session_coarse_dim": (C.c_int32, [C.c_void_p]),
     "mm_debug_spd_inverse": (C.c_int, [p_f64, C.c_int32]),
+    "mm_debug_tilechol_plan_create": (C.c_int, [C.c_int32, C.c_int32, p_i32, p_i32, p_f64, C.c_int32, C.POINTER(C.c_void_p)]),
+    "mm_debug_tilechol_plan_array": (C.c_int64, [C.c_void_p, C.c_int32, p_i64, C.c_int64]),
+    "mm_debug_tilechol_plan_destroy": (None, [C.c_void_p]),
+    "mm_debug_tilechol_solve": (C.c_int, [C.c_int32, C.c_int32, p_i32, p_i32, p_f64, p_f64, C.c_int32, p_f64, p_f64, p_f64, p_f64, C.c_int32, p_f64, p_f64]),
     "mm_ba_session_destroy": (None, [C.c_void_p]),
     "mm_pose_refine": (C.c_int, [p_f64, p_f64, C.c_int, p_f64, C.c_int64, p_f64, p_f64, p_u8,
                                  C.POINTER(BAOptions), C.POINTER(BASummary), p_f64]),

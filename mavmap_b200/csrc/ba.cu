@@ -10,9 +10,11 @@
 #include <cub/cub.cuh>
 #include <math.h>
 #include <vector>
+#include <string>
 #include <algorithm>
 #include "ba_kernels.cuh"
 #include "ba_pose.cuh"
+#include "tilechol.cuh"
 
 namespace mm {
 
@@ -184,6 +186,14 @@ struct mm_ba_session {
   // refined intrinsics (single shared camera)
   bool refine = false;
   DevBuf<double> ji, intr2, intr_mask, scale_i, Apc, Bm, intr_acc, Cinv, gi, di, xi, zi, pi0, pi1, bt, sq9;
+  // sparse tile Cholesky preconditioner of the PCG solve (tilechol.cuh): plan (host), its device copy, tiles, PCG vectors
+  bool tc_on = false; int tc_epoch = 0, tc_sepoch = 0, tc_grid_f = 0, tc_grid_s = 0, n_unk = 0, ncb = 0;
+  TileCholPlan tc_plan; TcDev tc;
+  DevBuf<int> tc_unk_of, tc_sc_tile, tc_sc_off, tc_a_tiles, tc_img_tile, tc_img_slot, tc_sched, tc_sdesc;
+  DevBuf<int4> tc_upd; DevBuf<int2> tc_items;
+  DevBuf<int> tc_ready, tc_sflag, tc_counters;
+  DevBuf<int64_t> tc_col_ptr;
+  DevBuf<double> tc_L, tc_WC, tc_WR, tc_slots, dv_b, dv_r, dv_z, dv_p, dv_Ap;
   int grid_obs = 1, grid_pt = 1, grid_cam6 = 1, grid_x = 1, pcg_grid = 0, pcg_ecap = 0, pcg_threads = 0; bool pcg_cached = false; size_t pcg_smem = 0; const void* pcg_fn = nullptr;
   cudaEvent_t evs[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // LM state (host)
@@ -568,7 +578,7 @@ int launch_schur(mm_ba_session* s, bool with_coarse = true) {
   { const int rc = all_reduce(s, s->xch.p, s->xch_count); if (rc) return rc; }
   k_cam_finish<<<blocks_for(6 * (int64_t)s->n_img, 128), 128, 0, st>>>(6 * s->n_img, s->ud.p, s->gc.p, s->rhs.p, s->scale_c.p, lm, s->S.p, s->dc.p, s->scal(), s->world,
       s->red.p, s->fail.p, s->n_prior ? s->pr_r.p : nullptr, s->n_prior ? s->pr_J.p : nullptr, s->n_prior ? s->loc.p + 6 : nullptr); MM_LAUNCH_CHECK();
-  k_precond<<<blocks_for(s->n_img, 64), 64, 0, st>>>(s->n_img, s->S.p, s->Minv.p, s->fail.p); MM_LAUNCH_CHECK();
+  if (!s->tc_on) { k_precond<<<blocks_for(s->n_img, 64), 64, 0, st>>>(s->n_img, s->S.p, s->Minv.p, s->fail.p); MM_LAUNCH_CHECK(); }   // (the tile factorisation checks definiteness itself)
   if (with_coarse && s->cm) {
     // The coarse inverse is only a preconditioner: once the iteration has settled (S changes little from one LM step to the
     // next) it is refreshed every third step, or when the trust-region radius - the damping inside S - moved by more than 30x.
@@ -585,6 +595,151 @@ int launch_schur(mm_ba_session* s, bool with_coarse = true) {
   }
   return MM_OK;
 }
+
+// ---- sparse tile Cholesky (tilechol_plan.h / tilechol.cuh): plan at session creation, factorisation per Schur assembly ------
+template <typename T, typename U>
+int tc_upload(DevBuf<T>& d, const std::vector<U>& h) {
+  static_assert(sizeof(T) == sizeof(U), "element size");
+  MM_CUDA(d.alloc(std::max<size_t>(h.size(), 1)));
+  if (!h.empty()) MM_CUDA(cudaMemcpy(d.p, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice));
+  return MM_OK;
+}
+int build_tilechol(mm_ba_session* s) {
+  s->tc_on = false;
+  const int pre = s->opt.pcg_preconditioner;
+  const char* env = getenv("MM_PCG_PRECOND");               // "twolevel" | "tilechol" overrides the option (experiments)
+  const bool force_two = (env && !strcmp(env, "twolevel")) || (!env && pre == MM_PRECOND_TWO_LEVEL);
+  const bool force_tc = (env && !strcmp(env, "tilechol")) || (!env && pre == MM_PRECOND_TILE_CHOLESKY);
+  if (s->n_img <= 0 || s->n_obs == 0) return MM_OK;
+  if (force_two && !s->refine) return MM_OK;
+  if (!s->refine && !force_tc && s->n_img <= DENSE_MAX_IMG) return MM_OK;          // dense Cholesky in one CTA
+  const int n = s->n_img;
+  std::vector<int> ha((size_t)std::max(s->n_off, 1)), hb((size_t)std::max(s->n_off, 1));
+  if (s->n_off > 0) {
+    MM_CUDA(cudaMemcpy(ha.data(), s->blk_a.p, sizeof(int) * (size_t)s->n_off, cudaMemcpyDeviceToHost));
+    MM_CUDA(cudaMemcpy(hb.data(), s->blk_b.p, sizeof(int) * (size_t)s->n_off, cudaMemcpyDeviceToHost));
+  }
+  // camera centres C = -R' t guide the dissection
+  std::vector<double> pos(3 * (size_t)n);
+  for (int i = 0; i < n; ++i) {
+    const double* p = s->h_poses0.data() + 6 * (size_t)i; double R[9], Jl[9];
+    rotation_and_left_jacobian(p, R, Jl);
+    for (int q = 0; q < 3; ++q) pos[3 * (size_t)i + q] = -(R[q] * p[3] + R[3 + q] * p[4] + R[6 + q] * p[5]);
+  }
+  s->ncb = s->refine ? s->n_cam : 0;
+  TileCholPlan& P = s->tc_plan;
+  const int prc = build_tilechol_plan(n, s->n_off, ha.data(), hb.data(), getenv("MM_TC_NO_GEOMETRY") ? nullptr : pos.data(), s->ncb, P);
+  if (prc != 0) { set_error("tile Cholesky plan failed (%d)", prc); return MM_ERR_UNSUPPORTED; }
+  // memory: the tiles of L must fit comfortably beside the Jacobian records
+  size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
+  const size_t need = sizeof(double) * TC_TT * ((size_t)P.n_l + 2 * (size_t)P.n_w);
+  if (need > free_b / 2 && !force_tc && !s->refine) { P = TileCholPlan(); return MM_OK; }          // falls back to the two-level PCG
+  // packed device copies (layouts: TcDev in tilechol.cuh)
+  const size_t n_tasks = (size_t)(P.n_l + P.n_wtask);
+  if (P.n_upd + P.n_wupd >= ((int64_t)1 << 31) || (int64_t)P.it_mat.size() >= ((int64_t)1 << 31)) { set_error("tile Cholesky plan too large"); return MM_ERR_UNSUPPORTED; }
+  std::vector<int> sched(8 * n_tasks), sdesc(16 * (size_t)P.n_stasks, 0);
+  std::vector<int4> upd((size_t)(P.n_upd + P.n_wupd)); std::vector<int2> items(P.it_mat.size());
+  for (int64_t u = 0; u < P.n_upd; ++u) upd[u] = make_int4(P.upd_a[u], P.upd_b[u], P.upd_a[u], P.upd_b[u]);
+  for (int64_t u = 0; u < P.n_wupd; ++u) upd[P.n_upd + u] = make_int4(P.wupd_l[u], P.wupd_w[u], P.wupd_l[u], P.wupd_flag[u] | (1 << 30));
+  for (size_t slot = 0; slot < n_tasks; ++slot) {
+    const int t = P.task_order[slot]; int* d = sched.data() + 8 * slot;
+    d[0] = t;
+    if (t < P.n_l) {
+      const int j = P.col_idx[t]; const bool diag = P.row_idx[t] == j;
+      d[1] = diag ? 1 : 0; d[2] = (int)P.upd_ptr[t]; d[3] = (int)(P.upd_ptr[t + 1] - P.upd_ptr[t]);
+      d[4] = (int)(P.w_row_ptr[j + 1] - 1); d[5] = (int)P.col_ptr[j]; d[6] = P.has_a[t]; d[7] = diag ? P.tile_nunk[j] : 0;
+    } else {
+      const int w = t - (int)P.n_l; const int i = P.wt_row[w];
+      d[1] = 2; d[2] = (int)(P.n_upd + P.wupd_ptr[w]); d[3] = (int)(P.wupd_ptr[w + 1] - P.wupd_ptr[w]);
+      d[4] = (int)(P.w_row_ptr[i + 1] - 1); d[5] = (int)P.col_ptr[i]; d[6] = 0; d[7] = P.wt_store[w];
+    }
+  }
+  for (int k = 0; k < P.n_stasks; ++k) {
+    int* d = sdesc.data() + 16 * (size_t)k;
+    const int64_t b = P.st_item_ptr[k], e = P.st_item_ptr[k + 1];
+    d[0] = P.st_kind[k]; d[1] = P.st_out[k]; d[2] = P.st_base[k]; d[3] = P.st_tile[k]; d[4] = (int)b; d[5] = (int)(e - b);
+    for (int q = 0; q < 4 && b + q < e; ++q) { d[8 + 2 * q] = P.it_mat[b + q]; d[9 + 2 * q] = P.it_src[b + q]; }
+  }
+  for (size_t q = 0; q < items.size(); ++q) items[q] = make_int2(P.it_mat[q], P.it_src[q]);
+  int rc;
+  if ((rc = tc_upload(s->tc_unk_of, P.unk_of)) || (rc = tc_upload(s->tc_sc_tile, P.sc_tile)) || (rc = tc_upload(s->tc_sc_off, P.sc_off)) || (rc = tc_upload(s->tc_a_tiles, P.a_tiles)) ||
+      (rc = tc_upload(s->tc_img_tile, P.img_tile)) || (rc = tc_upload(s->tc_img_slot, P.img_slot)) || (rc = tc_upload(s->tc_col_ptr, P.col_ptr)) ||
+      (rc = tc_upload(s->tc_sched, sched)) || (rc = tc_upload(s->tc_sdesc, sdesc)) || (rc = tc_upload(s->tc_upd, upd)) || (rc = tc_upload(s->tc_items, items))) return rc;
+  MM_CUDA(s->tc_L.alloc((size_t)TC_TT * (size_t)P.n_l)); MM_CUDA(s->tc_WC.alloc((size_t)TC_TT * (size_t)P.n_w)); MM_CUDA(s->tc_WR.alloc((size_t)TC_TT * (size_t)P.n_w));
+  MM_CUDA(s->tc_slots.alloc((size_t)TC_T * (size_t)P.n_slots));
+  MM_CUDA(s->tc_ready.alloc(n_tasks)); MM_CUDA(s->tc_sflag.alloc((size_t)P.n_slots)); MM_CUDA(s->tc_counters.alloc(4));
+  MM_CUDA(cudaMemset(s->tc_ready.p, 0, sizeof(int) * n_tasks)); MM_CUDA(cudaMemset(s->tc_sflag.p, 0, sizeof(int) * (size_t)P.n_slots));
+  s->n_unk = 6 * n + 9 * s->ncb;
+  MM_CUDA(s->dv_b.alloc((size_t)s->n_unk)); MM_CUDA(s->dv_r.alloc((size_t)s->n_unk)); MM_CUDA(s->dv_z.alloc((size_t)s->n_unk)); MM_CUDA(s->dv_p.alloc((size_t)s->n_unk)); MM_CUDA(s->dv_Ap.alloc((size_t)s->n_unk));
+  TcDev& D = s->tc;
+  D.nt = P.nt; D.nt_pose = P.nt_pose; D.nt_border = P.nt - P.nt_pose; D.n_img = n; D.n_cam_border = s->ncb; D.n_l = (int)P.n_l; D.n_a_tiles = (int)P.a_tiles.size();
+  D.n_tasks = (int)n_tasks; D.n_stasks = P.n_stasks; D.n_slots = P.n_slots;
+  D.unk_of = s->tc_unk_of.p; D.sc_tile = s->tc_sc_tile.p; D.sc_off = s->tc_sc_off.p; D.a_tiles = s->tc_a_tiles.p; D.img_tile = s->tc_img_tile.p; D.img_slot = s->tc_img_slot.p;
+  D.col_ptr = s->tc_col_ptr.p; D.sched = s->tc_sched.p; D.upd = s->tc_upd.p; D.sdesc = s->tc_sdesc.p; D.items = s->tc_items.p;
+  D.L = s->tc_L.p; D.WC = s->tc_WC.p; D.WR = s->tc_WR.p; D.slots = s->tc_slots.p;
+  D.ready = s->tc_ready.p; D.sflag = s->tc_sflag.p; D.counters = s->tc_counters.p; D.trace = nullptr; D.trace_diag = nullptr;
+  MM_CUDA(cudaFuncSetAttribute((const void*)k_tc_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_FACTOR_SMEM));
+  int per_sm = 0;
+  MM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tc_factor, TC_FACTOR_THREADS, TC_FACTOR_SMEM));
+  s->tc_grid_f = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)std::max(1, per_sm) * num_sms(), (int64_t)n_tasks));
+  int per_sm_s = 0;
+  MM_CUDA(cudaFuncSetAttribute((const void*)k_tc_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_APPLY_SMEM));
+  MM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, k_tc_apply, TC_APPLY_THREADS, TC_APPLY_SMEM));
+  // few CTAs per SM: a CTA that has taken a task polls the flags of its operands, and thousands of pollers saturate the L2
+  const int apply_per_sm = getenv("MM_TC_APPLY_CTAS") ? std::max(1, atoi(getenv("MM_TC_APPLY_CTAS"))) : 4;
+  s->tc_grid_s = std::max(1, std::min(std::min(std::max(1, per_sm_s), apply_per_sm) * num_sms(), P.n_stasks));
+  s->tc_on = true; s->tc_epoch = 0; s->tc_sepoch = 0;
+  return MM_OK;
+}
+// assembly of S (and the intrinsics border) into the tiles + numeric factorisation
+int launch_tc_factor(mm_ba_session* s) {
+  cudaStream_t st = s->stream; TcDev D = s->tc;
+  MM_CUDA(cudaMemsetAsync(D.counters, 0, sizeof(int) * 4, st));
+  k_tc_zero_tiles<<<std::min(D.n_a_tiles, 8 * num_sms()), 256, 0, st>>>(D.n_a_tiles, D.a_tiles, D.L); MM_LAUNCH_CHECK();
+  k_tc_scatter_blocks<<<grid_stride(36 * s->nblk, 256), 256, 0, st>>>(s->nblk, D.sc_tile, D.sc_off, s->S.p, D.L); MM_LAUNCH_CHECK();
+  if (s->ncb) { k_tc_scatter_border<<<grid_stride((int64_t)s->n_img * s->ncb * 54 + 81 * s->ncb * s->ncb, 256), 256, 0, st>>>(D, s->Bm.p, s->intr_acc.p); MM_LAUNCH_CHECK(); }
+  int epoch = ++s->tc_epoch; int* fail = s->fail.p;
+  void* args[] = { &D, &epoch, &fail };
+  MM_CUDA(cudaLaunchCooperativeKernel((const void*)k_tc_factor, dim3(s->tc_grid_f), dim3(TC_FACTOR_THREADS), args, TC_FACTOR_SMEM, st));
+  count_launch();
+  return MM_OK;
+}
+// z = M^-1 r with the factorisation (both substitutions); skipped on the device once the solve has converged
+int launch_tc_apply(mm_ba_session* s, const double* r, double* z, const int* done) {
+  cudaStream_t st = s->stream; TcDev D = s->tc;
+  MM_CUDA(cudaMemsetAsync(D.counters + 1, 0, sizeof(int), st));
+  int epoch = ++s->tc_sepoch;
+  void* args[] = { &D, &epoch, &r, &z, &done };
+  MM_CUDA(cudaLaunchCooperativeKernel((const void*)k_tc_apply, dim3(s->tc_grid_s), dim3(TC_APPLY_THREADS), args, TC_APPLY_SMEM, st)); count_launch();
+  return MM_OK;
+}
+// PCG on the reduced system [poses | intrinsics] preconditioned by the exact tile factorisation
+int launch_dpcg(mm_ba_session* s) {
+  cudaStream_t st = s->stream;
+  int rc = launch_tc_factor(s); if (rc) return rc;
+  const size_t n6 = 6 * (size_t)s->n_img;
+  MM_CUDA(cudaMemcpyAsync(s->dv_b.p, s->rhs.p, sizeof(double) * n6, cudaMemcpyDeviceToDevice, st));
+  if (s->ncb) MM_CUDA(cudaMemcpyAsync(s->dv_b.p + n6, s->intr_acc.p + 81 * (size_t)s->ncb * s->ncb, sizeof(double) * 9 * (size_t)s->ncb, cudaMemcpyDeviceToDevice, st));
+  DpcgVec V; V.n = s->n_unk; V.x = s->vx.p; V.r = s->dv_r.p; V.z = s->dv_z.p; V.p = s->dv_p.p; V.Ap = s->dv_Ap.p; V.b = s->dv_b.p; V.sc = s->pcg_sc.p; V.ic = s->pcg_ic.p;
+  V.tol2 = s->opt.pcg_tolerance * s->opt.pcg_tolerance; V.max_iter = s->opt.pcg_max_iterations;
+  k_dpcg_init<<<1, 1024, 0, st>>>(V); MM_LAUNCH_CHECK();
+  int done_it = 0;
+  while (done_it < V.max_iter) {
+    for (int k = 0; k < 2; ++k, ++done_it) {
+      if ((rc = launch_tc_apply(s, V.r, V.z, V.ic))) return rc;
+      k_dpcg_direction<<<1, 1024, 0, st>>>(V); MM_LAUNCH_CHECK();
+      k_dpcg_spmv<<<blocks_for((int64_t)s->n_img * 32, 128), 128, 0, st>>>(s->n_img, s->row_start.p, s->row_col.p, s->row_blk.p, s->S.p, V.p, V.Ap, s->ncb, s->ncb ? s->Bm.p : nullptr, V.ic); MM_LAUNCH_CHECK();
+      if (s->ncb) { k_dpcg_spmv_border<<<s->ncb, 256, 0, st>>>(s->n_img, s->ncb, s->Bm.p, s->intr_acc.p, V.p, V.Ap, V.ic); MM_LAUNCH_CHECK(); }
+      k_dpcg_update<<<1, 1024, 0, st>>>(V); MM_LAUNCH_CHECK();
+    }
+    int hic[2] = {0, 0};
+    MM_CUDA(cudaMemcpyAsync(hic, s->pcg_ic.p, sizeof hic, cudaMemcpyDeviceToHost, st));
+    MM_CUDA(cudaStreamSynchronize(st));
+    if (hic[0]) break;
+  }
+  return MM_OK;
+}
+
 // every rank solved the same replicated system, but the dot products of the solve are accumulated with atomics whose
 // order differs from GPU to GPU: rank 0's solution is the one everybody continues with
 int pcg_broadcast(mm_ba_session* s) {
@@ -597,6 +752,7 @@ int launch_pcg(mm_ba_session* s) {
   cudaStream_t st = s->stream;
   MM_CUDA(cudaMemsetAsync(s->pcg_sc.p, 0, sizeof(double) * 16, st));
   MM_CUDA(cudaMemsetAsync(s->pcg_ic.p, 0, sizeof(int) * 4, st));
+  if (s->tc_on) return launch_dpcg(s);          // deterministic: every rank of a sharded session computes the same bits
   if (!s->refine && s->n_img <= DENSE_MAX_IMG && s->n_img > 0 && !getenv("MM_PCG_ONLY")) {
     // local-BA sized system: dense Cholesky in one CTA (ba_coarse.cuh); reported as 0 linear iterations
     const int n = 6 * s->n_img;
@@ -808,6 +964,7 @@ void mm_ba_options_default(mm_ba_options* o) {
   o->min_trust_region_radius = 1e-32; o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32;
   o->jacobi_scaling = 1; o->max_num_consecutive_invalid_steps = 10;
   o->linear_solver = MM_SOLVER_PCG; o->pcg_tolerance = 1e-13; o->pcg_max_iterations = 2000; o->print_progress = 0;
+  o->pcg_preconditioner = MM_PRECOND_AUTO;
 }
 
 void mm_ba_session_destroy(mm_ba_session* s) {
@@ -855,7 +1012,7 @@ int mm_ba_session_create_sharded(const mm_ba_problem* P, const mm_ba_options* op
   A(s->pose_mask, 6 * n_img); A(s->pt_mask, n_pt); A(s->scale_c, 6 * n_img); A(s->scale_p, 3 * n_pt);
   A(s->Vinv, 6 * n_pt); A(s->pinfo, PINFO * n_pt); A(s->gp, 3 * n_pt); A(s->dp, 3 * n_pt); A(s->dc, 6 * n_img);
   A(s->loc, 8); A(s->stepbuf, 8);
-  A(s->vx, 6 * n_img); A(s->vr, 6 * n_img); A(s->vz, 6 * n_img); A(s->vp0, 6 * n_img); A(s->vp1, 6 * n_img); A(s->vAp, 6 * n_img);
+  A(s->vx, 6 * n_img + 9 * n_cam); A(s->vr, 6 * n_img); A(s->vz, 6 * n_img); A(s->vp0, 6 * n_img); A(s->vp1, 6 * n_img); A(s->vAp, 6 * n_img);
   A(s->pcg_sc, 16); A(s->pcg_ic, 4); A(s->red, 8); A(s->fail, 1); A(s->img_cam, n_img); A(s->cam_model, n_cam); A(s->Minv, 36 * n_img);
   MM_CUDA(cudaFuncSetAttribute((const void*)k_residual_jacobian<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM));
   MM_CUDA(cudaFuncSetAttribute((const void*)k_residual_jacobian<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM));
@@ -866,7 +1023,7 @@ int mm_ba_session_create_sharded(const mm_ba_problem* P, const mm_ba_options* op
   A(s->intr2, MM_INTR_STRIDE * n_cam); A(s->intr_mask, 9); A(s->scale_i, 9);
   if (refine) {
     A(s->Apc, 27 * n_pt); A(s->Bm, 54 * n_img); A(s->intr_acc, 108); A(s->Cinv, 81);
-    A(s->gi, 9); A(s->di, 9); A(s->xi, 9); A(s->zi, 9); A(s->pi0, 9); A(s->pi1, 9); A(s->bt, 18); A(s->sq9, 9);
+    A(s->gi, 9); A(s->di, 9); s->xi.view(s->vx.p + 6 * n_img, 9 * n_cam); A(s->zi, 9); A(s->pi0, 9); A(s->pi1, 9); A(s->bt, 18); A(s->sq9, 9);
   }
   { double im[9]; for (int k = 0; k < 9; ++k) im[k] = (refine && k < model_num_params(P->cam_model[0])) ? 1.0 : 0.0;
     double ones[9]; for (int k = 0; k < 9; ++k) ones[k] = 1.0;
@@ -897,7 +1054,8 @@ int mm_ba_session_create_sharded(const mm_ba_problem* P, const mm_ba_options* op
   cudaMemsetAsync(s->red.p, 0, sizeof(double) * 8, s->stream);
   cudaMemsetAsync(s->loc.p, 0, sizeof(double) * 8, s->stream);
   rc = build_structure(s, P); if (rc) return fail_out(rc);
-  rc = build_aggregates(s); if (rc) return fail_out(rc);
+  rc = build_tilechol(s); if (rc) return fail_out(rc);
+  rc = s->tc_on ? MM_OK : build_aggregates(s); if (rc) return fail_out(rc);
   rc = build_shard(s); if (rc) return fail_out(rc);
   A(s->rec, (size_t)REC * (size_t)std::max<int64_t>(s->no_loc(), 1));
   if (refine) A(s->ji, 18 * (size_t)std::max<int64_t>(P->n_obs, 1));
@@ -982,6 +1140,96 @@ int mm_debug_spd_inverse(double* a, int32_t m) {
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   MM_CUDA(cudaMemcpy(a, A.p, sizeof(double) * (size_t)m * m, cudaMemcpyDeviceToHost));
+  return MM_OK;
+}
+
+
+/* ---- test hooks of the sparse tile Cholesky ---------------------------------------------------------------- */
+struct mm_tilechol_plan { mm::TileCholPlan P; };
+
+int mm_debug_tilechol_plan_create(int32_t n_img, int32_t n_off, const int32_t* blk_a, const int32_t* blk_b, const double* pos,
+                                  int32_t n_cam_border, mm_tilechol_plan** out) {
+  if (!out || n_img <= 0 || n_off < 0 || (n_off > 0 && (!blk_a || !blk_b))) { set_error("invalid argument"); return MM_ERR_INVALID_ARG; }
+  for (int e = 0; e < n_off; ++e) if (blk_a[e] < 0 || blk_a[e] >= n_img || blk_b[e] < 0 || blk_b[e] >= n_img) { set_error("block index out of range"); return MM_ERR_INVALID_ARG; }
+  mm_tilechol_plan* h = new mm_tilechol_plan();
+  const int rc = build_tilechol_plan(n_img, n_off, blk_a, blk_b, pos, n_cam_border, h->P);
+  if (rc) { delete h; set_error("tile Cholesky plan failed (%d)", rc); return MM_ERR_UNSUPPORTED; }
+  *out = h;
+  return MM_OK;
+}
+void mm_debug_tilechol_plan_destroy(mm_tilechol_plan* h) { delete h; }
+int64_t mm_debug_tilechol_plan_array(mm_tilechol_plan* h, int32_t which, int64_t* out, int64_t cap) {
+  if (!h) return -1;
+  const TileCholPlan& P = h->P;
+  auto copy = [&](const auto& v) -> int64_t { const int64_t n = (int64_t)v.size(); if (out) for (int64_t i = 0; i < n && i < cap; ++i) out[i] = (int64_t)v[i]; return n; };
+  switch (which) {
+    case 0: { const std::vector<int64_t> sc = { P.nt_pose, P.nt, P.n_l, P.n_upd, P.n_nodes, P.max_height, (int64_t)P.flops, TC_T, TC_TI, P.n_w, P.n_wtask, P.n_slots, P.n_stasks, P.n_tnodes }; return copy(sc); }
+    case 1: return copy(P.img_tile);   case 2: return copy(P.img_slot);  case 3: return copy(P.tile_nunk); case 4: return copy(P.col_ptr);
+    case 5: return copy(P.row_idx);    case 6: return copy(P.col_idx);   case 7: return copy(P.has_a);     case 8: return copy(P.upd_ptr);
+    case 9: return copy(P.upd_a);      case 10: return copy(P.upd_b);    case 11: return copy(P.rowp_ptr); case 12: return copy(P.rowp_tile);
+    case 13: return copy(P.rowp_col);  case 14: return copy(P.unk_of);   case 15: return copy(P.sc_tile);  case 16: return copy(P.sc_off);
+    case 17: return copy(P.tile_height);
+    case 18: return copy(P.tile_node);  case 19: return copy(P.node_first); case 20: return copy(P.node_nt);   case 21: return copy(P.w_row_ptr);
+    case 22: return copy(P.wt_row);     case 23: return copy(P.wt_col);     case 24: return copy(P.wt_store);  case 25: return copy(P.wupd_ptr);
+    case 26: return copy(P.wupd_l);     case 27: return copy(P.wupd_w);     case 28: return copy(P.wupd_flag); case 29: return copy(P.task_order);
+    case 30: return copy(P.st_kind);    case 31: return copy(P.st_out);     case 32: return copy(P.st_base);   case 33: return copy(P.st_tile);
+    case 34: return copy(P.st_item_ptr); case 35: return copy(P.it_mat);    case 36: return copy(P.it_src);
+    default: return -1;
+  }
+}
+/* factorisation + one application z = M^-1 rhs on the device for a block-sparse SPD matrix given like the reduced system:
+ * S [(n_img + n_off) * 36] (diagonal blocks first, then the blocks (blk_a < blk_b) row-major), optional border Bm [n_img][ncb][6][9],
+ * Cm [(9 ncb)^2]; rhs and z have 6 n_img + 9 ncb entries.  Host buffers. */
+int mm_debug_tilechol_solve(int32_t n_img, int32_t n_off, const int32_t* blk_a, const int32_t* blk_b, const double* pos, const double* S,
+                            int32_t ncb, const double* Bm, const double* Cm, const double* rhs, double* z, int32_t reps, double* ms_factor, double* ms_apply) {
+  if (n_img <= 0 || n_off < 0 || !S || !rhs || !z || ncb < 0 || (ncb > 0 && (!Bm || !Cm))) { set_error("invalid argument"); return MM_ERR_INVALID_ARG; }
+  int rc = ensure_device(); if (rc) return rc;
+  mm_ba_session* s = new mm_ba_session();
+  struct Guard { mm_ba_session* s; ~Guard() { delete s; } } guard{ s };
+  mm_ba_options_default(&s->opt); s->opt.pcg_preconditioner = MM_PRECOND_TILE_CHOLESKY;
+  s->n_img = n_img; s->n_off = n_off; s->nblk = (int64_t)n_img + n_off; s->n_obs = 1; s->refine = ncb > 0; s->n_cam = ncb;
+  s->h_poses0.assign(6 * (size_t)n_img, 0.0);
+  if (pos) for (int i = 0; i < n_img; ++i) for (int q = 0; q < 3; ++q) s->h_poses0[6 * (size_t)i + 3 + q] = -pos[3 * (size_t)i + q];
+  MM_CUDA(s->blk_a.alloc((size_t)std::max(n_off, 1))); MM_CUDA(s->blk_b.alloc((size_t)std::max(n_off, 1))); MM_CUDA(s->S.alloc(36 * (size_t)s->nblk)); MM_CUDA(s->fail.alloc(1));
+  if (n_off) { MM_CUDA(cudaMemcpy(s->blk_a.p, blk_a, sizeof(int) * (size_t)n_off, cudaMemcpyHostToDevice)); MM_CUDA(cudaMemcpy(s->blk_b.p, blk_b, sizeof(int) * (size_t)n_off, cudaMemcpyHostToDevice)); }
+  MM_CUDA(cudaMemcpy(s->S.p, S, sizeof(double) * 36 * (size_t)s->nblk, cudaMemcpyHostToDevice));
+  MM_CUDA(cudaMemset(s->fail.p, 0, sizeof(int)));
+  if (ncb) {
+    MM_CUDA(s->Bm.alloc((size_t)54 * n_img * ncb)); MM_CUDA(s->intr_acc.alloc((size_t)81 * ncb * ncb + 27 * (size_t)ncb));
+    MM_CUDA(cudaMemcpy(s->Bm.p, Bm, sizeof(double) * 54 * (size_t)n_img * ncb, cudaMemcpyHostToDevice));
+    MM_CUDA(cudaMemcpy(s->intr_acc.p, Cm, sizeof(double) * 81 * (size_t)ncb * ncb, cudaMemcpyHostToDevice));
+  }
+  rc = build_tilechol(s); if (rc) return rc;
+  if (!s->tc_on) { set_error("tile Cholesky not enabled"); return MM_ERR_UNSUPPORTED; }
+  DevBuf<double> d_r, d_z; MM_CUDA(d_r.alloc((size_t)s->n_unk)); MM_CUDA(d_z.alloc((size_t)s->n_unk));
+  MM_CUDA(cudaMemcpy(d_r.p, rhs, sizeof(double) * (size_t)s->n_unk, cudaMemcpyHostToDevice));
+  cudaEvent_t e0, e1, e2; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+  if (reps < 1) reps = 1;
+  DevBuf<unsigned long long> trace; const size_t n_trace = 2 * ((size_t)s->tc.n_tasks + (size_t)s->tc.n_stasks);
+  DevBuf<unsigned long long> trace_d; const size_t n_trace_d = 8 * (size_t)s->tc_plan.n_w;
+  if (getenv("MM_TC_TRACE")) { MM_CUDA(trace.alloc(n_trace)); MM_CUDA(cudaMemset(trace.p, 0, sizeof(unsigned long long) * n_trace)); s->tc.trace = trace.p;
+    MM_CUDA(trace_d.alloc(n_trace_d)); MM_CUDA(cudaMemset(trace_d.p, 0, sizeof(unsigned long long) * n_trace_d)); s->tc.trace_diag = trace_d.p; }
+  for (int r = -1; r < reps && rc == MM_OK; ++r) { if (r == 0) cudaEventRecord(e0, nullptr); rc = launch_tc_factor(s); }
+  cudaEventRecord(e1, nullptr);
+  for (int r = 0; r < reps && rc == MM_OK; ++r) rc = launch_tc_apply(s, d_r.p, d_z.p, nullptr);
+  cudaEventRecord(e2, nullptr);
+  if (rc == MM_OK && cudaDeviceSynchronize() != cudaSuccess) { set_error("tile Cholesky kernels failed: %s", cudaGetErrorString(cudaGetLastError())); rc = MM_ERR_CUDA; }
+  float f0 = 0, f1 = 0; cudaEventElapsedTime(&f0, e0, e1); cudaEventElapsedTime(&f1, e1, e2);
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+  if (rc) return rc;
+  if (ms_factor) *ms_factor = f0 / reps; if (ms_apply) *ms_apply = f1 / reps;
+  if (trace.p) {        // time stamps of the last factorisation / application: {start, end} per task, raw uint64 ns
+    std::vector<unsigned long long> h(n_trace);
+    MM_CUDA(cudaMemcpy(h.data(), trace.p, sizeof(unsigned long long) * n_trace, cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen(getenv("MM_TC_TRACE"), "wb")) { fwrite(h.data(), sizeof(unsigned long long), n_trace, f); fclose(f); }
+    std::vector<unsigned long long> hd(n_trace_d);
+    MM_CUDA(cudaMemcpy(hd.data(), trace_d.p, sizeof(unsigned long long) * n_trace_d, cudaMemcpyDeviceToHost));
+    const std::string pd = std::string(getenv("MM_TC_TRACE")) + ".diag";
+    if (FILE* f = fopen(pd.c_str(), "wb")) { fwrite(hd.data(), sizeof(unsigned long long), n_trace_d, f); fclose(f); }
+  }
+  int fail = 0; MM_CUDA(cudaMemcpy(&fail, s->fail.p, sizeof(int), cudaMemcpyDeviceToHost));
+  MM_CUDA(cudaMemcpy(z, d_z.p, sizeof(double) * (size_t)s->n_unk, cudaMemcpyDeviceToHost));
+  if (fail) { set_error("the matrix is not positive definite"); return MM_ERR_NUMERICAL; }
   return MM_OK;
 }
 
