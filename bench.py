@@ -3,21 +3,24 @@
 
   python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
   python bench.py --impl reference ...                     (CPU arm: the oracle restatement of the
-                                                            reference's Ceres/OpenCV path, all host cores)
+                                                            reference's Ceres path, all host cores)
 
-Primary metric (BASELINE.json): bundle-adjustment LM iterations per second on configs[1]
-(500-image PINHOLE sequence, ~1 M observations).  A "step" is one LM iteration = residual+Jacobian
-(K1) + Schur assembly (K2) + PCG solve (K3) + back-substitution / candidate cost (K4) + accept/reject.
-The same JSON line carries the matching throughput (image pairs/s, 5k x 5k SURF-64) as `secondary`.
+Primary metric (BASELINE.json): bundle-adjustment LM iterations per second on the configuration the
+metric is quoted on, configs[3] = "cfg4": 5000 cameras / 2 M points / 10 M observations.  A "step" is one LM
+iteration = residual+Jacobian (K1) + Schur assembly (K2) + PCG solve preconditioned by the sparse tile Cholesky
+(K3) + back-substitution / candidate cost (K4) + accept/reject.  cfg2 (500 images) and the matching
+throughput (image pairs/s, 5k x 5k SURF-64) ride along as `secondary_cfg2` / `secondary`.
 
 value    : inputs resident in HBM (mm_ba_session_*), CUDA-event timed on the session's stream
 e2e      : same metric through mm_ba_solve with HOST buffers (upload + structure setup + K
            iterations + download inside the timed region)
-N > 1    : BA does not need to shard (north_star: single-GPU unless HBM overflows) -> N independent
-           replicas ("replicas only", weak scaling); matching shards by pair with one gather.
+parity   : computed in the run: cost, step pattern and parameters against the CPU oracle after the same
+           number of LM iterations on this very problem
+N > 1    : ONE cfg4 problem with its points sharded across the N GPUs (strong scaling; the reduced system is
+           all-reduced once per Schur assembly and solved on every rank); `replicas` (N independent
+           problems, what north_star prescribes for BA) is reported beside it.
 """
 import argparse
-import ctypes as C
 import json
 import os
 import subprocess
@@ -88,10 +91,21 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def ba_config(workload):
+WORKLOADS = {"ba_cfg2": "cfg2", "ba_cfg4": "cfg4", "ba_cfg1": "cfg1", "ba_small": "small"}
+
+
+def make_problem(name, seed_offset=0):
     from mavmap_b200 import synthetic
-    name = {"ba_cfg2": "cfg2", "ba_cfg4": "cfg4", "ba_cfg1": "cfg1", "ba_small": "small"}[workload]
-    return name, dict(synthetic.BA_CONFIGS[name])
+    kw = dict(synthetic.BA_CONFIGS[name])
+    kw["seed"] = kw["seed"] + seed_offset
+    flat, _ = synthetic.make_ba_problem(**kw)
+    return flat
+
+
+def workload_string(name, flat):
+    """identical in both arms (the driver compares it)"""
+    return ("%s: %d images, %d points, %d observations, PINHOLE fx=fy=1000, fixed intrinsics, Cauchy loss, image 0 FIXED / image 1 FIXED_X"
+            % (name, flat.n_img, flat.n_pt, flat.n_obs))
 
 
 def options(iters, oracle=False):
@@ -105,16 +119,28 @@ def options(iters, oracle=False):
     return o
 
 
-def cpu_ba_iterations(flat, iters):
-    """Oracle (restated Ceres-semantics LM + Schur + Cholesky, OpenMP) timed on the host cores."""
+def cpu_ba(flat, iters):
+    """Oracle (restated Ceres-semantics LM + Schur + Cholesky, OpenMP) on the host cores: returns (seconds, summary, solved copy)."""
     from oracle import orc
-    o = options(iters, oracle=True)
     f = flat.copy()
     t = time.perf_counter()
-    s = orc.solve_flat(f, o)
-    dt = time.perf_counter() - t
-    n = s.num_successful_steps + s.num_unsuccessful_steps
-    return n / dt, dt, n, orc.num_threads(), s
+    s = orc.solve_flat(f, options(iters, oracle=True))
+    return time.perf_counter() - t, s, f
+
+
+def parity_block(g, sg, c, sc, iters):
+    """GPU result (problem g, summary dict sg) against the oracle's (c, sc) after the same iteration count"""
+    def rel(a, b):
+        return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1.0))) if a.size else 0.0
+    n = min(len(sg["trace_cost"]), len(sc["trace_cost"]))
+    tc_g, tc_c = np.array(sg["trace_cost"][:n]), np.array(sc["trace_cost"][:n])
+    return {"against": "CPU oracle (oracle/orc_ba.c: restated Ceres LM + Schur + direct Cholesky), same problem, %d LM iterations" % iters,
+            "rel_final_cost_diff": float(abs(sg["final_cost"] - sc["final_cost"]) / sc["final_cost"]),
+            "max_rel_cost_trace_diff": float(np.max(np.abs(tc_g - tc_c) / tc_c)),
+            "same_step_pattern": sg["trace_accepted"][:n] == sc["trace_accepted"][:n],
+            "max_rel_pose_diff": rel(g.poses, c.poses), "max_rel_point_diff": rel(g.pts, c.pts),
+            "tolerance_north_star": 1e-6,
+            "max_pcg_iterations_per_solve": int(max(sg["trace_linear_iterations"]) if sg["trace_linear_iterations"] else 0)}
 
 
 def cpu_match_pairs(desc, n_pairs):
@@ -128,21 +154,31 @@ def cpu_match_pairs(desc, n_pairs):
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the CPU arm.  Real Ceres/OpenCV-C++ cannot be built here (not in the image),
-    so this is the oracle port of the reference path (BA) and cv2.BFMatcher (matching)."""
+    """--impl reference: the CPU arm.  Real Ceres/OpenCV-C++ cannot be built here (not in the image), so this is the
+    oracle port of the reference's BA path on all host cores, on the same problem, for W + K LM iterations; the rate is
+    taken over the last K."""
     if rank != 0:
         return
-    from mavmap_b200 import synthetic
-    name, kw = ba_config(args.workload)
-    flat, _ = synthetic.make_ba_problem(**kw)
-    steps = max(1, min(args.steps, args.ref_max_steps))
-    ips, dt, n, cores, s = cpu_ba_iterations(flat, steps)
-    line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": n, "warmup": 0,
-            "ms_per_step": 1e3 * dt / max(n, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": "%s: %d images, %d points, %d observations, PINHOLE, fixed intrinsics" % (name, flat.n_img, flat.n_pt, flat.n_obs)},
-            "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "full %s problem, %d LM iterations of the oracle (restated Ceres-semantics LM + Schur + skyline Cholesky, OpenMP; NOT Ceres)" % (name, n)},
-            "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)        # torchrun exports OMP_NUM_THREADS=1: undo it before libgomp loads
+    from oracle import orc
+    name = WORKLOADS[args.workload]
+    flat = make_problem(name)
+    W, K = args.warmup, args.steps
+    # two runs of the same deterministic trajectory: W iterations (untimed part), then W + K; the difference is K steps
+    t_w = 0.0
+    if W > 0:
+        t_w, _, _ = cpu_ba(flat, W)
+    t_all, s, _ = cpu_ba(flat, W + K)
+    n = s.num_successful_steps + s.num_unsuccessful_steps
+    dt = max(t_all - t_w, 1e-9)
+    ips = K / dt
+    line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 * dt / max(K, 1), "higher_is_better": True, "scaling": "weak" if args.gpus == 1 else "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": workload_string(name, flat)},
+            "cpu_baseline": {"value": ips, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+                             "sample": "full %s problem: %d LM iterations of the oracle timed as (run of %d) - (run of %d) (restated Ceres-semantics LM + Schur + skyline Cholesky, OpenMP; NOT Ceres: no Ceres in the image)" % (name, K, n, W)},
+            "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "final_cost": s.final_cost}
     print(json.dumps(line), flush=True)
 
 
@@ -152,15 +188,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="ba_cfg2", choices=["ba_cfg2", "ba_cfg4", "ba_cfg1", "ba_small"])
+    ap.add_argument("--workload", default="ba_cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--match-pairs", type=int, default=120)
-    ap.add_argument("--cpu-steps", type=int, default=3)
-    ap.add_argument("--ref-max-steps", type=int, default=12)
+    ap.add_argument("--cpu-steps", type=int, default=3, help="LM iterations of the CPU oracle for cpu_baseline and the parity block")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-match", action="store_true")
-    ap.add_argument("--no-cfg4", action="store_true", help="skip the extra 5000-image / 10 M observation measurement (N = 1 only)")
-    ap.add_argument("--ba-mode", default="replicas", choices=["replicas", "sharded"],
-                    help="N > 1: independent problems per GPU (default, north_star: BA stays on one GPU) or ONE problem with its points sharded")
+    ap.add_argument("--no-cfg2", action="store_true", help="skip the secondary 500-image measurement")
+    ap.add_argument("--ba-mode", default="auto", choices=["auto", "replicas", "sharded"],
+                    help="N > 1: ONE problem with its points sharded (auto / sharded: strong scaling) or independent problems per GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -196,93 +231,132 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ------------------------------------------------------------------ BA, resident
-    name, kw = ba_config(args.workload)
-    sharded = args.ba_mode == "sharded" and world > 1
-    if not sharded:
-        kw["seed"] = kw["seed"] + 1000 * rank             # replicas: one independent problem per rank
-    flat, _ = synthetic.make_ba_problem(**kw)
-    W, K = args.warmup, args.steps
     stream = torch.cuda.current_stream().cuda_stream
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    W, K = args.warmup, args.steps
+    name = WORKLOADS[args.workload]
+    sharded = world > 1 and args.ba_mode != "replicas"
+
+    def timed_session(flat, make_session):
+        """W warm-up + K timed LM iterations on a resident session; returns (ms over K, launches, summary dict, session)"""
+        sess = make_session(flat.copy())
+        sess.iterate(W)
+        barrier()
+        l0 = _lib.kernel_launch_count()
+        e0.record()
+        done = sess.iterate(K)
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        assert done == K, "LM stopped early (%d of %d iterations)" % (done, K)
+        return ms, _lib.kernel_launch_count() - l0, sess.summary().as_dict(), sess
+
+    # ------------------------------------------------------------------ headline BA problem, resident
+    flat = make_problem(name)                                       # the same problem on every rank
+    rep = flat if rank == 0 else (make_problem(name, 1000 * rank) if world > 1 else flat)     # one independent problem per rank (replicas, host-buffer call)
     if sharded:
         from mavmap_b200.parallel import make_allreduce_callback
         ar_cb = make_allreduce_callback()
-        sess = BASession(flat.copy(), options(W + K), stream=stream, rank=rank, world=world, allreduce=ar_cb)
+        mk = lambda f: BASession(f, options(W + K), stream=stream, rank=rank, world=world, allreduce=ar_cb)
     else:
-        sess = BASession(flat.copy(), options(W + K), stream=stream)
-    n_blocks = sess.num_blocks()
+        mk = lambda f: BASession(f, options(W + K), stream=stream)
     sampler = ClockSampler(local); sampler.start()
     time.sleep(0.25)                                       # nvidia-smi needs a moment to produce its first sample
     t_load0 = time.time()
-    sess.iterate(W)
-    barrier()
-    l0 = _lib.kernel_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    done = sess.iterate(K)
-    e1.record()
-    barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = _lib.kernel_launch_count() - l0
+    ms, launches, summ, sess = timed_session(flat if sharded else rep, mk)
     clocks = sampler.stop(t_load0, time.time())
-    summ = sess.summary().as_dict()
-    assert done == K, "LM stopped early (%d of %d iterations)" % (done, K)
     value = (1 if sharded else world) * K / (ms * 1e-3)
+    n_blocks = sess.num_blocks(); info = sess.solver_info()
 
     # per-kernel timings on the resident state (live, CUDA events inside the library)
-    k1_ms = sess.time_kernel(0, 20); k2_ms = sess.time_kernel(1, 10); k4_ms = sess.time_kernel(2, 20); spmv_ms = sess.time_kernel(3, 50)
-    coarse_dim = sess.coarse_dim()
-    coarse_ms = sess.time_kernel(4, 10) if coarse_dim else 0.0
     n_obs, n_pt, n_img = flat.n_obs, flat.n_pt, flat.n_img
-    k1_bytes = 184.0 * n_obs + 48.0 * n_img + 24.0 * n_pt            # K1 algorithmic bytes
-    k2_bytes = 168.0 * n_obs + 72.0 * n_pt + 216.0 * n_img + 288.0 * n_blocks
-    k3_bytes = 288.0 * (2 * n_blocks - n_img) + 5 * 48.0 * n_img      # both triangles are read through the CSR
-    pcg_iters = sum(summ["trace_linear_iterations"][W + 1:W + 1 + K])
-    lin_ms = summ["ms"]
-    traffic = None                       # dram bytes per launch of K1 from the committed `ncu --set full` capture of this workload
+    share = 1.0 / world if sharded else 1.0                                          # observations / points per rank
+    k1_ms = sess.time_kernel(0, 20); k2_ms = sess.time_kernel(1, 10); k4_ms = sess.time_kernel(2, 20)
+    k1_bytes = (184.0 * n_obs + 24.0 * n_pt) * share + 48.0 * n_img              # SURVEY §8d: K1 algorithmic bytes
+    k2_bytes = (168.0 * n_obs + 72.0 * n_pt) * share + 216.0 * n_img + 288.0 * n_blocks
+    traffic = None                       # dram bytes per launch of K1 from the committed `ncu --set full` capture of this workload (not measured in this run)
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and world == 1:
         traffic = json.load(open(tp)).get(name, {}).get("k_residual_jacobian<1,0>")
+    lin_ms = summ["ms"]
+    pcg_iters = summ["trace_linear_iterations"][W + 1:W + 1 + K]
     roof_k1 = {"kernel": "k_residual_jacobian (K1)", "bound": "hbm", "achieved": k1_bytes / (k1_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
-               "unit": "GB/s", "traffic": traffic, "ms": k1_ms, "peak_source": peaks["source"], "algorithmic_bytes": k1_bytes}
+               "unit": "GB/s", "traffic": traffic, "traffic_source": "profiles/ncu_traffic.json (ncu --set full of this workload, committed; not re-measured in this run)" if traffic else None,
+               "ms": k1_ms, "peak_source": peaks["source"], "algorithmic_bytes": k1_bytes,
+               "share_of_step": k1_ms / (ms / K)}
     roof_k1["frac"] = roof_k1["achieved"] / roof_k1["peak"]
-    roof_k2 = {"kernel": "k_schur_point + k_schur_blocks + k_schur_cam (K2)", "bound": "hbm", "achieved": k2_bytes / (k2_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
-               "unit": "GB/s", "traffic": None, "ms": k2_ms}
+    roof_k2 = {"kernel": "Schur assembly (K2: k_schur_point + k_schur_blocks + k_schur_cam)", "bound": "hbm", "achieved": k2_bytes / (k2_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+               "unit": "GB/s", "traffic": None, "ms": k2_ms, "share_of_step": k2_ms / (ms / K)}
     roof_k2["frac"] = roof_k2["achieved"] / roof_k2["peak"]
-    roof_k3 = {"kernel": "k_pcg_spmv (K3, one PCG iteration's SpMV)", "bound": "hbm", "achieved": k3_bytes / (spmv_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
-               "unit": "GB/s", "traffic": None, "ms": spmv_ms}
-    roof_k3["frac"] = roof_k3["achieved"] / roof_k3["peak"]
-    # the persistent solver as it runs inside the step: bytes one PCG iteration touches (blocks through both row references, five
-    # vectors, the dense coarse inverse) over the measured time per iteration; S and the inverse are L2 / shared-memory resident,
-    # so this is a bandwidth figure for orientation, not an HBM-bound kernel
-    try:
-        per_it_ms = lin_ms["pcg"] / max(int(pcg_iters), 1)
-        k3_it_bytes = k3_bytes + 8.0 * coarse_dim * coarse_dim
-        roof_k3p = {"kernel": "persistent PCG kernel, one iteration (K3; dominant by time)", "bound": "hbm", "achieved": k3_it_bytes / (per_it_ms * 1e-3) / 1e9 if per_it_ms > 0 else 0.0,
-                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "traffic": None, "ms": per_it_ms, "note": "operands resident in L2 / shared memory: latency- and barrier-bound (3 grid barriers per iteration)"}
-        roof_k3p["frac"] = roof_k3p["achieved"] / roof_k3p["peak"]
-    except Exception as e:      # orientation figure only: never let it take the headline line down
-        roof_k3p = {"kernel": "persistent PCG kernel", "error": repr(e)}
+    others = [roof_k2]
+    solver = {"preconditioner": info["preconditioner"], "pcg_iterations_per_solve": {"min": int(min(pcg_iters)), "max": int(max(pcg_iters)), "mean": float(np.mean(pcg_iters))}}
+    if info["preconditioner"] == "sparse tile Cholesky":
+        f_ms = sess.time_kernel(5, 5); a_ms = sess.time_kernel(6, 5)
+        sm_mhz = clocks.get("sm_max_mhz") or 1965.0
+        fp64_peak = 148 * 128 * sm_mhz * 1e6 / 1e12                                  # 64 FMA / clk / SM, nominal: no measured fp64 peak in MEASURED_PEAKS.json
+        solver.update({"tiles_of_L": info["tiles"], "tile_mb": info["tile_mb"], "tile_products": info["tile_products"], "gflop_per_factorisation": info["flops"] / 1e9,
+                       "ms_assembly_and_factorisation": f_ms, "ms_per_application": a_ms, "substitution_tasks": info["substitution_tasks"]})
+        others.append({"kernel": "k_tc_factor (K3: sparse tile Cholesky; dominant by time)", "bound": "fp64", "achieved": info["flops"] / (f_ms * 1e-3) / 1e12, "peak": fp64_peak,
+                       "unit": "TFLOP/s", "traffic": None, "ms": f_ms, "frac": info["flops"] / (f_ms * 1e-3) / 1e12 / fp64_peak, "share_of_step": f_ms / (ms / K),
+                       "note": "dependency-bound (critical path through the dense separator blocks), not pipe-bound; peak = 148 SMs x 64 fp64 FMA/clk x max SM clock (nominal)"})
     sess.close()
 
-    # ------------------------------------------------------------------ BA, end to end through mm_ba_solve (host buffers)
-    if sharded:
-        kw2 = dict(kw); kw2["seed"] = kw["seed"] + 1000 * rank
-        flat, _ = synthetic.make_ba_problem(**kw2)          # the host-buffer call is per GPU: one problem each
-        n_obs, n_pt, n_img = flat.n_obs, flat.n_pt, flat.n_img
-    warm = flat.copy(); solve_flat(warm, options(1))          # load kernels / allocator warm-up, untimed
+    # ------------------------------------------------------------------ same problem, end to end through mm_ba_solve (host buffers)
+    fe = rep                                                  # the host-buffer call is per GPU: one problem each
+    warm = fe.copy(); solve_flat(warm, options(1))            # load kernels / allocator warm-up, untimed
     barrier()
-    f2 = flat.copy()
+    f2 = fe.copy()
     t0 = time.perf_counter()
     s2 = solve_flat(f2, options(K))
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     n2 = s2.num_successful_steps + s2.num_unsuccessful_steps
-    h2d = 24 * n_obs + 48 * n_img + 24 * n_pt + 72 + 6 * n_img + n_pt
-    d2h = 48 * n_img + 24 * n_pt + 72
+    h2d = 24 * fe.n_obs + 48 * fe.n_img + 24 * fe.n_pt + 72 + 6 * fe.n_img + fe.n_pt
+    d2h = 48 * fe.n_img + 24 * fe.n_pt + 72
     e2e = {"value": world * n2 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d / max(n2, 1)), "d2h_bytes_per_step": int(d2h / max(n2, 1)),
            "total_ms": 1e3 * e2e_s, "setup_ms": s2.ms_setup, "steps": n2,
-           "note": "mm_ba_solve on host arrays: upload + device structure setup + %d LM iterations + download" % n2}
+           "note": "mm_ba_solve on host arrays%s: upload + device structure setup + host symbolic analysis of the tile Cholesky + %d LM iterations + download" % (" (one independent problem per GPU)" if world > 1 else "", n2)}
+
+    # ------------------------------------------------------------------ parity + CPU baseline on this very problem (rank 0, N = 1)
+    cpu = parity = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import orc
+        dt, sc, c = cpu_ba(flat, args.cpu_steps)
+        n = sc.num_successful_steps + sc.num_unsuccessful_steps
+        cpu = {"value": n / dt, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+               "sample": "full %s problem, %d LM iterations of the oracle (restated Ceres-semantics LM + Schur + skyline Cholesky, OpenMP; NOT Ceres), %.1f s" % (name, n, dt)}
+        g = flat.copy(); sg = solve_flat(g, options(args.cpu_steps)).as_dict()
+        parity = parity_block(g, sg, c, sc.as_dict(), args.cpu_steps)
+
+    # ------------------------------------------------------------------ replicas beside the sharded line (N > 1)
+    replicas = None
+    if sharded:
+        msr, _, _, sr = timed_session(rep, lambda f: BASession(f, options(W + K), stream=stream))
+        sr.close()
+        replicas = {"value": world * K / (msr * 1e-3), "unit": UNIT, "scaling": "weak", "ms_per_step": msr / K,
+                    "note": "N independent %s problems, one per GPU, no communication (what north_star prescribes for BA that fits one HBM)" % name}
+
+    # ------------------------------------------------------------------ secondary BA configuration: cfg2 (N = 1)
+    cfg2 = None
+    if rank == 0 and world == 1 and not args.no_cfg2 and name != "cfg2":
+        try:
+            f2c = make_problem("cfg2")
+            ms2, _, sum2, sb = timed_session(f2c, lambda f: BASession(f, options(W + K), stream=stream))
+            k1b = sb.time_kernel(0, 20); k2b = sb.time_kernel(1, 10); nblk2 = sb.num_blocks(); sb.close()
+            wb = f2c.copy(); solve_flat(wb, options(1))
+            fb = f2c.copy(); t0 = time.perf_counter(); s2b = solve_flat(fb, options(K)); torch.cuda.synchronize(); e2b = time.perf_counter() - t0
+            cfg2 = {"workload": workload_string("cfg2", f2c), "value": K / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / K, "steps": K,
+                    "e2e": {"value": (s2b.num_successful_steps + s2b.num_unsuccessful_steps) / e2b, "unit": UNIT, "total_ms": 1e3 * e2b, "setup_ms": s2b.ms_setup},
+                    "pcg_iterations": sum2["trace_linear_iterations"][W + 1:W + 1 + K], "breakdown_ms": sum2["ms"],
+                    "roofline_K1": {"bound": "hbm", "ms": k1b, "frac": (184.0 * f2c.n_obs + 48.0 * f2c.n_img + 24.0 * f2c.n_pt) / (k1b * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+                    "roofline_K2": {"bound": "hbm", "ms": k2b, "frac": (168.0 * f2c.n_obs + 72.0 * f2c.n_pt + 216.0 * f2c.n_img + 288.0 * nblk2) / (k2b * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
+            if not args.no_cpu:
+                dtc, scc, cc = cpu_ba(f2c, args.cpu_steps)
+                cfg2["cpu_baseline"] = {"value": (scc.num_successful_steps + scc.num_unsuccessful_steps) / dtc, "unit": UNIT, "kind": "port", "sample": "full cfg2 problem, %d LM iterations of the oracle, %.1f s" % (args.cpu_steps, dtc)}
+                gg = f2c.copy(); sgg = solve_flat(gg, options(args.cpu_steps)).as_dict()
+                cfg2["parity"] = parity_block(gg, sgg, cc, scc.as_dict(), args.cpu_steps)
+        except Exception as e:          # the headline line must not depend on the extra measurement
+            cfg2 = {"error": repr(e)}
 
     # ------------------------------------------------------------------ matching (secondary), sharded by pair
     secondary = None
@@ -320,35 +394,13 @@ def main():
         secondary = {"metric": "image_pairs_matched_per_sec", "value": pairs_s, "unit": "pairs/s", "ms_per_pair": mms / max(np_, 1),
                      "config": {"workload": "5000 x 5000 SURF-%d descriptors per pair, ratio 0.9 + cross-check, %d pairs/rank" % (kdim, np_)},
                      "impl": "simt (exact fp64-accumulate CUDA cores)" if os.environ.get("MM_MATCH_NO_TC") else "tcgen05 TF32 candidate GEMM + exact re-rank", "gpu_launches": int(m_launch),
-                     "algorithmic_tflops": pairs_s * flops / 1e12, "tensor_roofline_frac_of_bf16_peak": pairs_s * flops / 1e12 / peaks["bf16_tflops"],
+                     "algorithmic_tflops": pairs_s * flops / 1e12, "algorithmic_tflops_per_gpu": pairs_s * flops / 1e12 / world,
+                     "tensor_roofline_frac_of_bf16_peak_per_gpu": pairs_s * flops / 1e12 / world / peaks["bf16_tflops"],
                      "e2e": {"value": world / m_e2e, "unit": "pairs/s", "h2d_bytes_per_step": 2 * n_feat * kdim * 4, "d2h_bytes_per_step": 12 * 3000}}
+        if rank == 0 and world == 1 and not args.no_cpu:
+            secondary["cpu_baseline"] = {"value": cpu_match_pairs(desc, 3), "unit": "pairs/s", "cores": os.cpu_count(), "kind": "reference",
+                                         "sample": "3 pairs, cv2.BFMatcher knnMatch x2 + ratio + cross-check (OpenCV %s)" % __import__("cv2").__version__}
         ms_set.close()
-
-    # ------------------------------------------------------------------ the north_star problem (configs[3]: 5000 cams / 10 M obs), N = 1
-    big = None
-    if rank == 0 and world == 1 and not args.no_cfg4 and args.workload == "ba_cfg2":
-        try:
-            fbig, _ = synthetic.make_ba_problem(**dict(synthetic.BA_CONFIGS["cfg4"]))
-            sb = BASession(fbig.copy(), options(W + K), stream=stream)
-            sb.iterate(W); torch.cuda.synchronize()
-            e0.record(); nb = sb.iterate(K); e1.record(); torch.cuda.synchronize()
-            msb = e0.elapsed_time(e1)
-            k1b = sb.time_kernel(0, 20); k2b = sb.time_kernel(1, 5)
-            sumb = sb.summary().as_dict(); nblk_b = sb.num_blocks(); cdim_b = sb.coarse_dim(); sb.close()
-            k1b_bytes = 184.0 * fbig.n_obs + 48.0 * fbig.n_img + 24.0 * fbig.n_pt
-            k2b_bytes = 168.0 * fbig.n_obs + 72.0 * fbig.n_pt + 216.0 * fbig.n_img + 288.0 * nblk_b
-            big = {"workload": "cfg4: %d images, %d points, %d observations" % (fbig.n_img, fbig.n_pt, fbig.n_obs), "value": nb / (msb * 1e-3), "unit": UNIT,
-                   "ms_per_step": msb / max(nb, 1), "steps": nb, "pcg_iterations": int(sum(sumb["trace_linear_iterations"][W + 1:W + 1 + K])), "coarse_unknowns": cdim_b,
-                   "roofline_K1": {"bound": "hbm", "ms": k1b, "achieved": k1b_bytes / (k1b * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                   "frac": k1b_bytes / (k1b * 1e-3) / 1e9 / peaks["hbm_gbs"]},
-                   "roofline_K2": {"bound": "hbm", "ms": k2b, "achieved": k2b_bytes / (k2b * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                   "frac": k2b_bytes / (k2b * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
-            if not args.no_cpu:
-                ips_b, dt_b, n_b, cores_b, _ = cpu_ba_iterations(fbig, 2)
-                big["cpu_baseline"] = {"value": ips_b, "unit": UNIT, "cores": cores_b, "kind": "port", "sample": "full cfg4 problem, %d LM iterations of the oracle, %.1f s" % (n_b, dt_b)}
-            del fbig
-        except Exception as e:          # the headline line must not depend on the extra measurement
-            big = {"error": repr(e)}
 
     # ------------------------------------------------------------------ pose_refinement latency, rank 0
     pose_lat = None
@@ -368,37 +420,25 @@ def main():
         pose_lat = {"metric": "pose_refinement_latency", "value": (time.perf_counter() - t0) / 20 * 1e6, "unit": "us per call (host buffers in, pose out)",
                     "config": {"workload": "%d 2D-3D pairs, PINHOLE, 10 LM iterations, single-CTA kernel" % npts}}
 
-    # ------------------------------------------------------------------ CPU baseline beside it (rank 0, N = 1)
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        ips, dt, n, cores, s = cpu_ba_iterations(flat, args.cpu_steps)
-        cpu = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "full %s problem, %d LM iterations of the oracle (restated Ceres-semantics LM + Schur + skyline Cholesky, OpenMP; NOT Ceres), %.1f s" % (name, n, dt)}
-        # parity of the two engines on this very workload after the same iteration count
-        g = flat.copy(); sg = solve_flat(g, options(args.cpu_steps))
-        cpu["parity_rel_cost_diff_after_%d_iters" % n] = abs(sg.final_cost - s.final_cost) / s.final_cost
-        if secondary is not None:
-            secondary["cpu_baseline"] = {"value": cpu_match_pairs(desc, 3), "unit": "pairs/s", "cores": os.cpu_count(), "kind": "reference",
-                                         "sample": "3 pairs, cv2.BFMatcher knnMatch x2 + ratio + cross-check (OpenCV %s)" % __import__("cv2").__version__}
-
     if rank == 0:
-        dominant = max((roof_k1, roof_k2), key=lambda r: r["ms"])
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+        step_ms = ms / K
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": step_ms,
                 "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "%s: %d images, %d points, %d observations, PINHOLE fx=fy=1000, fixed intrinsics, Cauchy loss, image0 FIXED / image1 FIXED_X" % (name, n_img, n_pt, n_obs),
-                           "parallelism": ("one problem, points sharded across %d GPUs, all-reduce of the reduced system per Schur assembly" % world) if sharded else
+                "config": {"workload": workload_string(name, flat),
+                           "parallelism": ("one problem, points (and with them observations, Jacobian records, K1/K2/K4) sharded across %d GPUs; limiting collective: all-reduce of the reduced "
+                                           "system S | rhs | gradient (%.0f MB) once per Schur assembly over NCCL/NVLink; the reduced solve (tile Cholesky + PCG) is replicated" % (world, (36.0 * n_blocks + 18.0 * n_img) * 8 / 1e6)) if sharded else
                                           ("replicas only (one independent BA per GPU)" if world > 1 else "single GPU"),
-                           "l2_policy": "inputs larger than L2: %.0f MB of Jacobian records + %.0f MB of observations per LM iteration" % (160.0 * n_obs / 1e6, 24.0 * n_obs / 1e6),
-                           "pcg_tolerance": 1e-13, "reduced_system_blocks": n_blocks,
-                           "pcg_preconditioner": ("two-level: block-Jacobi + %d similarity-mode coarse unknowns" % coarse_dim) if coarse_dim else "block-Jacobi"},
+                           "l2_policy": "inputs larger than L2: %.0f MB of Jacobian records + %.0f MB of observations per LM iteration" % (160.0 * n_obs * share / 1e6, 24.0 * n_obs * share / 1e6),
+                           "pcg_tolerance": 1e-13, "reduced_system_blocks": n_blocks, "pcg_preconditioner": info["preconditioner"]},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": dict(roof_k1, note="K1 is the kernel north_star names; share of the step is in `breakdown`"),
-                "roofline_other": [roof_k2, roof_k3, roof_k3p],
-                "breakdown": {"ms_linearize_K1": lin_ms["linearize"], "ms_schur_K2": lin_ms["schur"], "ms_pcg_K3": lin_ms["pcg"], "ms_update_K4": lin_ms["update"],
-                              "pcg_iterations_in_timed_steps": int(pcg_iters), "k1_ms": k1_ms, "k2_ms": k2_ms, "k4_cost_ms": k4_ms, "pcg_spmv_ms": spmv_ms,
-                              "coarse_setup_ms": coarse_ms, "ms_pcg_per_iteration": lin_ms["pcg"] / max(int(pcg_iters), 1),
-                              "dominant_by_time": "K3 PCG" if lin_ms["pcg"] > max(lin_ms["schur"], lin_ms["linearize"]) else dominant["kernel"]},
-                "cpu_baseline": cpu, "secondary": secondary, "tertiary": pose_lat, "north_star_cfg4": big, "final_cost": summ["final_cost"]}
+                "roofline": dict(roof_k1, note="K1 is the HBM-bound kernel north_star names; the kernel that dominates the step by time is in roofline_other / breakdown"),
+                "roofline_other": others,
+                "solver": solver,
+                "breakdown": {"ms_linearize_K1": lin_ms["linearize"], "ms_schur_K2": lin_ms["schur"], "ms_solve_K3": lin_ms["pcg"], "ms_update_K4": lin_ms["update"],
+                              "note": "device ms accumulated over setup + all %d iterations of the session" % (W + K),
+                              "k1_ms": k1_ms, "k2_ms": k2_ms, "k4_cost_ms": k4_ms,
+                              "dominant_by_time": max((("K3 solve", lin_ms["pcg"]), ("K2 Schur assembly", lin_ms["schur"]), ("K1 linearize", lin_ms["linearize"]), ("K4 update", lin_ms["update"])), key=lambda kv: kv[1])[0]},
+                "parity": parity, "cpu_baseline": cpu, "secondary": secondary, "secondary_cfg2": cfg2, "replicas": replicas, "tertiary": pose_lat, "final_cost": summ["final_cost"]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -300,10 +300,15 @@ int  mm_ba_session_download(mm_ba_session* s, double* poses, double* intr, doubl
 int  mm_ba_session_summary(mm_ba_session* s, mm_ba_summary* out);
 /* Time single hot kernels on the session's current state (bench/roofline):
  * which: 0 = residual+Jacobian (K1), 1 = Schur assembly (K2), 2 = cost-only evaluation (K4),
- * 3 = one PCG iteration's SpMV, 4 = coarse-level setup (assembly + inverse).  Runs `reps` launches, returns mean ms via CUDA events. */
+ * 3 = one PCG iteration's SpMV, 4 = coarse-level setup (assembly + inverse), 5 = assembly + numeric factorisation of the sparse
+ * tile Cholesky, 6 = one application of it (both substitutions).  Runs `reps` launches, returns mean ms via CUDA events. */
 int  mm_ba_session_time_kernel(mm_ba_session* s, int32_t which, int32_t reps, double* ms);
 /* Sizes of the reduced system: number of 6x6 blocks stored (upper triangle incl. diagonal). */
 int64_t mm_ba_session_num_blocks(mm_ba_session* s);
+/* What preconditions the PCG of this session: out8 = {kind (0 block-Jacobi / dense Cholesky of a small system, 1 two-level,
+ * 2 sparse tile Cholesky), tiles of L, tile products per factorisation, flop per factorisation, tile rows, tiles of the
+ * node-block inverses, substitution tasks, MB of tile storage}. */
+int  mm_ba_session_solver_info(mm_ba_session* s, double* out8);
 /* Unknowns of the coarse level of the two-level PCG preconditioner (7 per aggregate of images;
  * 0 = block-Jacobi only: small systems, refined intrinsics, or MM_PCG_NO_COARSE set). */
 int32_t mm_ba_session_coarse_dim(mm_ba_session* s);

@@ -148,6 +148,7 @@ PROTOTYPES = {
     "mm_ba_session_time_kernel": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, p_f64]),
     "mm_ba_session_num_blocks": (C.c_int64, [C.c_void_p]),
     "mm_ba_session_coarse_dim": (C.c_int32, [C.c_void_p]),
+    "mm_ba_session_solver_info": (C.c_int, [C.c_void_p, p_f64]),
     "mm_debug_spd_inverse": (C.c_int, [p_f64, C.c_int32]),
     "mm_debug_tilechol_plan_create": (C.c_int, [C.c_int32, C.c_int32, p_i32, p_i32, p_f64, C.c_int32, C.POINTER(C.c_void_p)]),
     "mm_debug_tilechol_plan_array": (C.c_int64, [C.c_void_p, C.c_int32, p_i64, C.c_int64]),

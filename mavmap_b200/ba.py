@@ -425,6 +425,15 @@ class BASession:
         """Unknowns of the coarse level of the two-level PCG preconditioner (0 = block-Jacobi only)."""
         return int(self._lib.mm_ba_session_coarse_dim(self._h))
 
+    def solver_info(self):
+        """What preconditions the PCG: {"preconditioner", "tiles", "tile_products", "flops", "tile_rows", "inverse_tiles",
+        "substitution_tasks", "tile_mb"} (mm_ba_session_solver_info)."""
+        out = np.zeros(8)
+        self._check(self._lib.mm_ba_session_solver_info(self._h, as_ptr(out, _abi.p_f64)))
+        kind = {0: "block-Jacobi / dense", 1: "two-level aggregates", 2: "sparse tile Cholesky"}[int(out[0])]
+        return {"preconditioner": kind, "tiles": int(out[1]), "tile_products": int(out[2]), "flops": float(out[3]), "tile_rows": int(out[4]),
+                "inverse_tiles": int(out[5]), "substitution_tasks": int(out[6]), "tile_mb": float(out[7])}
+
     def close(self):
         if self._h:
             self._lib.mm_ba_session_destroy(self._h)

@@ -735,6 +735,7 @@ int launch_dpcg(mm_ba_session* s) {
     int hic[2] = {0, 0};
     MM_CUDA(cudaMemcpyAsync(hic, s->pcg_ic.p, sizeof hic, cudaMemcpyDeviceToHost, st));
     MM_CUDA(cudaStreamSynchronize(st));
+    if (getenv("MM_PCG_DEBUG")) { double sc[8]; cudaMemcpy(sc, s->pcg_sc.p, sizeof sc, cudaMemcpyDeviceToHost); printf("dpcg: %d iterations, |r|/|b| = %.3e (first iteration %.3e)\n", hic[1], sqrt(sc[4] / sc[0]), sqrt(sc[5] / sc[0])); }
     if (hic[0]) break;
   }
   return MM_OK;
@@ -1110,6 +1111,15 @@ int mm_ba_session_summary(mm_ba_session* s, mm_ba_summary* out) {
 }
 
 int64_t mm_ba_session_num_blocks(mm_ba_session* s) { return s ? s->nblk : -1; }
+int mm_ba_session_solver_info(mm_ba_session* s, double* out8) {
+  if (!s || !out8) return MM_ERR_INVALID_ARG;
+  for (int k = 0; k < 8; ++k) out8[k] = 0.0;
+  const TileCholPlan& P = s->tc_plan;
+  if (s->tc_on) { out8[0] = 2; out8[1] = (double)P.n_l; out8[2] = (double)(P.n_upd + P.n_wupd); out8[3] = P.flops; out8[4] = P.nt; out8[5] = (double)P.n_w; out8[6] = P.n_stasks;
+                  out8[7] = sizeof(double) * (double)TC_TT * ((double)P.n_l + 2.0 * (double)P.n_w) / 1e6; }
+  else if (s->cm) { out8[0] = 1; out8[4] = s->cm; }
+  return MM_OK;
+}
 int32_t mm_ba_session_coarse_dim(mm_ba_session* s) { return s ? s->cm : -1; }
 
 int mm_debug_spd_inverse(double* a, int32_t m) {
@@ -1278,6 +1288,8 @@ int mm_ba_session_time_kernel(mm_ba_session* s, int32_t which, int32_t reps, dou
                   s->img_cam.p, s->cam_model.p, s->pose_mask.p, s->pt_mask.p, loss_of(s->opt), s->rec.p, s->part_cost.p); count_launch(); break;
       case 1: rc = launch_schur(s, false); break;
       case 4: rc = launch_coarse_setup(s); break;
+      case 5: if (!s->tc_on) return MM_ERR_UNSUPPORTED; rc = launch_tc_factor(s); break;
+      case 6: if (!s->tc_on) return MM_ERR_UNSUPPORTED; rc = launch_tc_apply(s, s->dv_b.p, s->dv_z.p, nullptr); break;
       case 2: k_residual_jacobian<false><<<s->grid_obs, 256, K1_SMEM_COST, st>>>(s->no_loc(), s->obs_xy.p + s->o_lo, s->obs_img.p + s->o_lo, s->obs_pt.p + s->o_lo, s->aux.p, s->pts.p, s->intr.p,
                   s->img_cam.p, s->cam_model.p, s->pose_mask.p, s->pt_mask.p, loss_of(s->opt), nullptr, s->part_cost.p); count_launch(); break;
       case 3: {

@@ -153,9 +153,9 @@ __device__ __forceinline__ void tc_publish(int* flag, int epoch, int tid) {
 
 // 6 x 6 register fragment (64 threads cover a tile): 36 FMAs per six 16-byte shared-memory loads
 template <bool SUB>
-__device__ __forceinline__ void tc_frag_gemm66(double (&acc)[6][6], const double* A, const double* B, int r0, int c0) {
+__device__ __forceinline__ void tc_frag_gemm66(double (&acc)[6][6], const double* A, const double* B, int r0, int c0, int q0, int q1) {
 #pragma unroll 2
-  for (int q = 0; q < TC_T; ++q) {
+  for (int q = q0; q < q1; ++q) {
     const double2* a2 = reinterpret_cast<const double2*>(A + q * TC_T + r0);
     const double2* b2 = reinterpret_cast<const double2*>(B + q * TC_T + c0);
     const double2 a01 = a2[0], a23 = a2[1], a45 = a2[2], b01 = b2[0], b23 = b2[1], b45 = b2[2];
@@ -167,10 +167,11 @@ __device__ __forceinline__ void tc_frag_gemm66(double (&acc)[6][6], const double
   }
 }
 
-// Consumers: two groups of 64 threads.  The tile products of a task alternate between the groups (item n of the CTA's
-// stream goes to group n & 1), each group keeps its own partial sum in a 6 x 6 register fragment per thread, and the
-// finishing stage of the task adds the two partial sums (and the entries of A) in shared memory before all 128 threads
-// finish the tile (6 x 3 fragments).  Fixed assignment, fixed order: deterministic.
+// Consumers: two groups of 64 threads.  Every tile product is split along its inner dimension (group g takes k in
+// [24 g, 24 g + 24)), each group keeps its partial sum in a 6 x 6 register fragment per thread (36 FMAs per six 16-byte
+// shared-memory loads), and the finishing stage of the task adds the two partial sums to the entries of A - which the
+// producer has put into the free half of the stage by TMA - before all 128 threads finish the tile (6 x 3 fragments).
+// Fixed split, fixed order: deterministic.
 __global__ void __launch_bounds__(TC_FACTOR_THREADS, 2) k_tc_factor(TcDev P, int epoch, int* __restrict__ fail) {
   extern __shared__ __align__(128) unsigned char tc_smem[];
   double* bufs = reinterpret_cast<double*>(tc_smem);                                  // [stage][A | B][TC_TT]
@@ -232,14 +233,18 @@ __global__ void __launch_bounds__(TC_FACTOR_THREADS, 2) k_tc_factor(TcDev P, int
         }
       }
       if (lane == 0) {
+        // finishing stage: the entries of A(i,j) (what the assembly left in the tile's own storage) into the first half,
+        // the inverse of the diagonal tile into the second half
         tc_mbar_wait(bar0 + 8 * (TC_STAGES + stage), phase ^ 1);
-        if (kind == 1) { meta[stage] = make_int4(t, TC_KIND_FIN_DIAG | (has_a << 10), aux, fin_idx); tc_mbar_arrive(bar0 + 8 * stage); }
+        const uint32_t dstA = tc_smem_addr(bufs + (size_t)2 * TC_TT * stage);
+        if (kind != 1) { tc_wait_flag(P.ready + fin_flag, epoch); tc_fence_proxy_async_global(); }
+        meta[stage] = make_int4(t, (kind == 1 ? TC_KIND_FIN_DIAG : (kind == 2 ? TC_KIND_FIN_W : TC_KIND_FIN_OFF)) | (has_a << 10), aux, fin_idx);
+        const uint32_t bytes = TILE_BYTES * ((has_a ? 1 : 0) + (kind != 1 ? 1 : 0));
+        if (bytes == 0) tc_mbar_arrive(bar0 + 8 * stage);
         else {
-          tc_wait_flag(P.ready + fin_flag, epoch);
-          tc_fence_proxy_async_global();
-          meta[stage] = make_int4(t, (kind == 2 ? TC_KIND_FIN_W : TC_KIND_FIN_OFF) | (has_a << 10), aux, 0);
-          tc_mbar_expect_tx(bar0 + 8 * stage, TILE_BYTES);
-          tc_bulk_g2s(tc_smem_addr(bufs + (size_t)2 * TC_TT * stage + TC_TT), P.WC + (size_t)TC_TT * fin_idx, TILE_BYTES, bar0 + 8 * stage);      // inverse of the diagonal tile, column-major
+          tc_mbar_expect_tx(bar0 + 8 * stage, bytes);
+          if (has_a) tc_bulk_g2s(dstA, P.L + (size_t)TC_TT * t, TILE_BYTES, bar0 + 8 * stage);
+          if (kind != 1) tc_bulk_g2s(dstA + TILE_BYTES, P.WC + (size_t)TC_TT * fin_idx, TILE_BYTES, bar0 + 8 * stage);      // inverse of the diagonal tile, column-major
         }
       }
       if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
@@ -252,8 +257,8 @@ __global__ void __launch_bounds__(TC_FACTOR_THREADS, 2) k_tc_factor(TcDev P, int
   const int tr = tid >> 4, tcn = tid & 15, r0 = 6 * tr, c0 = 3 * tcn, lane = tid & 31;  // 6 x 3 fragment of the finishing steps
   double acc[6][6];
   int cur = -1;                                          // task whose partial sum `acc` holds
-  int stage = 0, item = 0; uint32_t phase = 0;
-  for (;; ++item) {
+  int stage = 0; uint32_t phase = 0;
+  for (;;) {
     tc_mbar_wait(bar0 + 8 * stage, phase);
     const int4 m = meta[stage];
     const int skind = m.y & 0xff;
@@ -261,38 +266,36 @@ __global__ void __launch_bounds__(TC_FACTOR_THREADS, 2) k_tc_factor(TcDev P, int
     const int t = m.x;
     double* A = bufs + (size_t)2 * TC_TT * stage; double* B = A + TC_TT;
     if (skind == TC_KIND_UPD || skind == TC_KIND_WUPD) {
-      if (grp == (item & 1)) {
-        if (cur != t) {
-          cur = t;
+      if (cur != t) {
+        cur = t;
 #pragma unroll
-          for (int a = 0; a < 6; ++a)
+        for (int a = 0; a < 6; ++a)
 #pragma unroll
-            for (int b = 0; b < 6; ++b) acc[a][b] = 0.0;
-        }
-        if (skind == TC_KIND_UPD) tc_frag_gemm66<true>(acc, A, ((m.y >> 9) & 1) ? A : B, R0, C0);
-        else tc_frag_gemm66<false>(acc, A, B, R0, C0);
+          for (int b = 0; b < 6; ++b) acc[a][b] = 0.0;
       }
+      const int q0 = grp * (TC_T / 2);
+      if (skind == TC_KIND_UPD) tc_frag_gemm66<true>(acc, A, ((m.y >> 9) & 1) ? A : B, R0, C0, q0, q0 + TC_T / 2);
+      else tc_frag_gemm66<false>(acc, A, B, R0, C0, q0, q0 + TC_T / 2);
     } else {
-      // ---- finishing stage: C = A(i,j) + partial sums, assembled in the free half of the stage.  Column-major for the tiles
-      // of L, row-major for W (there it is the second operand of the final product).
-      const bool rowmajor = skind == TC_KIND_FIN_W;
+      // ---- finishing stage: C = A(i,j) + partial sums, assembled in the first half of the stage.  Column-major for the tiles
+      // of L, row-major for W (there it is the second operand of the final product; W tiles have no entries of A).
+      const bool rowmajor = skind == TC_KIND_FIN_W, has_a = (m.y >> 10) & 1, mine = cur == t;
       if (P.trace_diag && tid == 0 && skind == TC_KIND_FIN_DIAG) P.trace_diag[8 * (size_t)m.w + 0] = tc_gtimer();
       if (grp == 0) {
-        const bool mine = cur == t, has_a = (m.y >> 10) & 1;
-        const double* src = P.L + (size_t)TC_TT * t;
 #pragma unroll
         for (int b = 0; b < 6; ++b)
 #pragma unroll
           for (int a = 0; a < 6; a += 2) {
-            double2 v = make_double2(0.0, 0.0);
-            if (has_a) v = __ldcg(reinterpret_cast<const double2*>(src + (C0 + b) * TC_T + R0 + a));
-            if (mine) { v.x += acc[a][b]; v.y += acc[a + 1][b]; }
-            if (!rowmajor) *reinterpret_cast<double2*>(A + (C0 + b) * TC_T + R0 + a) = v;
-            else { A[(R0 + a) * TC_T + C0 + b] = v.x; A[(R0 + a + 1) * TC_T + C0 + b] = v.y; }
+            if (!rowmajor) {
+              double2* e = reinterpret_cast<double2*>(A + (C0 + b) * TC_T + R0 + a);
+              double2 v = has_a ? *e : make_double2(0.0, 0.0);
+              if (mine) { v.x += acc[a][b]; v.y += acc[a + 1][b]; }
+              *e = v;
+            } else { A[(R0 + a) * TC_T + C0 + b] = mine ? acc[a][b] : 0.0; A[(R0 + a + 1) * TC_T + C0 + b] = mine ? acc[a + 1][b] : 0.0; }
           }
       }
       tc_bar_consumers();
-      if (grp == 1 && cur == t) {
+      if (grp == 1 && mine) {
 #pragma unroll
         for (int b = 0; b < 6; ++b)
 #pragma unroll
@@ -613,7 +616,7 @@ __global__ void __launch_bounds__(TC_APPLY_THREADS) k_tc_apply(TcDev P, int epoc
 // ---------------------------------------------------------------- PCG around the factorisation
 // Unknowns: [6 n_img pose parameters | 9 ncb intrinsics].  All dot products are reduced in a fixed order by ONE CTA, so the
 // solve is bit-reproducible (run to run, and between the ranks of a sharded session, which solve the same replicated system).
-// sc: [0] b.b  [1] r.z  [2] r.z of the previous iteration  [3] p.Ap  [4] r.r ;  ic: [0] converged flag, [1] iterations done
+// sc: [0] b.b  [1] r.z  [2] r.z of the previous iteration  [3] p.Ap  [4] r.r  [5] r.r after the first iteration ;  ic: [0] converged flag, [1] iterations done
 struct DpcgVec { int n; double *x, *r, *z, *p, *Ap; const double* b; double* sc; int* ic; double tol2; int max_iter; };
 
 __device__ __forceinline__ double dpcg_block_sum_all(double v, double* red) {      // 1024 threads; the sum, in every thread
@@ -658,7 +661,7 @@ __global__ void __launch_bounds__(1024) k_dpcg_update(DpcgVec V) {
   for (int i = threadIdx.x; i < V.n; i += blockDim.x) { V.x[i] += alpha * V.p[i]; const double r = V.r[i] - alpha * V.Ap[i]; V.r[i] = r; rr += r * r; }
   rr = dpcg_block_sum_all(rr, red);
   if (threadIdx.x == 0) {
-    V.sc[3] = pap; V.sc[4] = rr;
+    V.sc[3] = pap; V.sc[4] = rr; if (V.ic[1] == 0) V.sc[5] = rr;
     const int it = V.ic[1] + 1; V.ic[1] = it;
     if (rr <= V.tol2 * V.sc[0] || it >= V.max_iter || !(rr == rr) || !(pap > 0.0)) V.ic[0] = 1;
   }
