@@ -185,7 +185,8 @@ struct mm_ba_session {
   DevBuf<int> blk_a, blk_b, agg; DevBuf<double> Pc, Ac, gjC, gjR, crc, cqc, cyc; int gj_grid = 0;
   // refined intrinsics (single shared camera)
   bool refine = false;
-  DevBuf<double> ji, intr2, intr_mask, scale_i, Apc, Bm, intr_acc, Cinv, gi, di, xi, zi, pi0, pi1, bt, sq9;
+  DevBuf<double> ji, intr2, intr_mask, scale_i, Apc, Bm, intr_acc, xch2, gi, di, xi, img_sq; DevBuf<unsigned> pt_cam_mask; size_t xch2_count = 0;
+  double* ji_base() const { return ji.p - (size_t)18 * (size_t)o_lo; }      // like rec_base(): intrinsics Jacobians exist for the local observations only
   // sparse tile Cholesky preconditioner of the PCG solve (tilechol.cuh): plan (host), its device copy, tiles, PCG vectors
   bool tc_on = false; int tc_epoch = 0, tc_sepoch = 0, tc_grid_f = 0, tc_grid_s = 0, n_unk = 0, ncb = 0;
   TileCholPlan tc_plan; TcDev tc;
@@ -553,9 +554,9 @@ int launch_scale(mm_ba_session* s) {
     { const int rc = all_reduce(s, s->ud.p, 6 * (size_t)s->n_img); if (rc) return rc; }
     k_scale_finish<<<blocks_for(6 * (int64_t)s->n_img, 256), 256, 0, st>>>(6 * s->n_img, s->ud.p, s->scale_c.p, s->n_prior ? s->pr_J.p : nullptr); MM_LAUNCH_CHECK();
     if (s->refine) {
-      MM_CUDA(cudaMemsetAsync(s->sq9.p, 0, sizeof(double) * 9, st));
-      k_colnorm_intr<<<s->grid_obs, 256, 0, st>>>(s->n_obs, s->ji.p, s->sq9.p); MM_LAUNCH_CHECK();
-      k_intr_scale<<<1, 32, 0, st>>>(s->sq9.p, s->scale_i.p); MM_LAUNCH_CHECK();
+      k_colnorm_intr_img<<<blocks_for((int64_t)s->n_img * 32, 128), 128, 0, st>>>(s->n_img, s->cam_lo.p, s->cam_hi.p, s->cam_perm.p, s->ji_base(), s->img_sq.p); MM_LAUNCH_CHECK();
+      { const int rc = all_reduce(s, s->img_sq.p, 9 * (size_t)s->n_img); if (rc) return rc; }
+      k_intr_scale<<<s->n_cam, 256, 0, st>>>(s->n_img, s->img_cam.p, s->img_sq.p, s->scale_i.p); MM_LAUNCH_CHECK();
     }
   }
   return MM_OK;
@@ -587,11 +588,16 @@ int launch_schur(mm_ba_session* s, bool with_coarse = true) {
     if (refresh) { const int rc = launch_coarse_setup(s); if (rc) return rc; s->coarse_iter = s->iter; s->coarse_radius = s->radius; }
   }
   if (s->refine) {
-    MM_CUDA(cudaMemsetAsync(s->intr_acc.p, 0, sizeof(double) * 108, st));
-    k_schur_intr_point<<<blocks_for(s->n_pt, 128), 128, 0, st>>>(s->n_pt, s->pt_start.p, s->rec.p, s->ji.p, s->scale_p.p, s->scale_i.p, s->Vinv.p, s->gp.p, s->Apc.p, s->intr_acc.p); MM_LAUNCH_CHECK();
-    k_schur_cam_intr<<<blocks_for((int64_t)s->n_img * 32, 128), 128, 0, st>>>(s->n_img, s->cam_start.p, s->cam_perm.p, s->obs_pt.p, s->rec.p, s->ji.p, s->scale_c.p, s->scale_p.p,
-        s->scale_i.p, s->Vinv.p, s->Apc.p, s->Bm.p); MM_LAUNCH_CHECK();
-    k_intr_finalize<<<1, 32, 0, st>>>(lm, s->scale_i.p, s->intr_acc.p, s->Cinv.p, s->gi.p, s->di.p, s->red.p + 2, s->fail.p); MM_LAUNCH_CHECK();
+    // border of the reduced system: B (6 x 9 per image and camera) | C, b, diagonal, gradient of the intrinsics; summed over the
+    // ranks like S (one more exchange step), then the LM diagonal of the intrinsics
+    const int P0 = s->p_lo, NP = s->np_loc(); const int n9 = 9 * s->n_cam;
+    MM_CUDA(cudaMemsetAsync(s->intr_acc.p, 0, sizeof(double) * ((size_t)n9 * n9 + 3 * (size_t)n9), st));
+    k_schur_intr_point<<<blocks_for(NP, 128), 128, 0, st>>>(NP, s->n_cam, s->pt_start.p + P0, s->obs_img.p, s->img_cam.p, s->rec_base(), s->ji_base(),
+        s->scale_p.p + 3 * (size_t)P0, s->scale_i.p, s->Vinv.p + 6 * (size_t)P0, s->gp.p + 3 * (size_t)P0, s->Apc.p + 27 * (size_t)P0 * s->n_cam, s->pt_cam_mask.p + P0, s->intr_acc.p); MM_LAUNCH_CHECK();
+    k_schur_cam_intr<<<blocks_for((int64_t)s->n_img * 32, 128), 128, 0, st>>>(s->n_img, s->n_cam, s->cam_lo.p, s->cam_hi.p, s->cam_perm.p, s->obs_pt.p, s->img_cam.p, s->rec_base(), s->ji_base(),
+        s->scale_c.p, s->scale_p.p, s->scale_i.p, s->Vinv.p, s->Apc.p, s->pt_cam_mask.p, s->Bm.p); MM_LAUNCH_CHECK();
+    { const int rc = all_reduce(s, s->xch2.p, s->xch2_count); if (rc) return rc; }
+    k_intr_finalize<<<blocks_for(n9, 64), 64, 0, st>>>(n9, lm, s->scale_i.p, s->intr_acc.p, s->gi.p, s->di.p, s->red.p + 2); MM_LAUNCH_CHECK();
   }
   return MM_OK;
 }
@@ -798,11 +804,7 @@ int launch_pcg(mm_ba_session* s) {
   a.b = s->rhs.p; a.x = s->vx.p; a.r = s->vr.p; a.z = s->vz.p; a.p0 = s->vp0.p; a.p1 = s->vp1.p; a.Ap = s->vAp.p; a.sc = s->pcg_sc.p; a.ic = s->pcg_ic.p;
   a.tol2 = s->opt.pcg_tolerance * s->opt.pcg_tolerance; a.max_iter = s->opt.pcg_max_iterations;
   a.dbg = nullptr;
-  a.n_intr = 0; a.Bm = nullptr; a.Cm = nullptr; a.Cinv = nullptr; a.bi = nullptr; a.xi = a.zi = a.pi0 = a.pi1 = a.bt = nullptr;
-  if (s->refine) {
-    a.n_intr = 9; a.Bm = s->Bm.p; a.Cm = s->intr_acc.p; a.Cinv = s->Cinv.p; a.bi = s->intr_acc.p + 81; a.xi = s->xi.p; a.zi = s->zi.p; a.pi0 = s->pi0.p; a.pi1 = s->pi1.p; a.bt = s->bt.p;
-    MM_CUDA(cudaMemsetAsync(s->bt.p, 0, sizeof(double) * 18, st));
-  }
+  a.n_intr = 0; a.Bm = nullptr; a.Cm = nullptr; a.Cinv = nullptr; a.bi = nullptr; a.xi = a.zi = a.pi0 = a.pi1 = a.bt = nullptr;      // (refined intrinsics always go through the tile factorisation)
   a.cm = s->cm; a.agg = s->agg.p; a.Pc = s->Pc.p; a.Ainv = s->Ac.p; a.rc = s->crc.p; a.qc = s->cqc.p; a.yc = s->cyc.p;
   if (s->cm) { MM_CUDA(cudaMemsetAsync(s->crc.p, 0, sizeof(double) * 2 * (size_t)s->cm, st)); MM_CUDA(cudaMemsetAsync(s->cqc.p, 0, sizeof(double) * (size_t)s->cm, st)); }
   if (getenv("MM_PCG_DEBUG")) { if (!s->pcg_dbg.p) MM_CUDA(s->pcg_dbg.alloc(6 * 32)); a.dbg = s->pcg_dbg.p; }
@@ -825,9 +827,9 @@ int launch_update(mm_ba_session* s) {
   const int gp_ = blocks_for(NP, 128), gc_ = blocks_for((int64_t)6 * s->n_img, 128);
   k_backsub<<<gp_, 128, 0, st>>>(NP, s->pt_start.p + P0, s->obs_img.p, s->rec_base(), s->scale_c.p, s->scale_p.p + 3 * (size_t)P0, s->Vinv.p + 6 * (size_t)P0,
       s->gp.p + 3 * (size_t)P0, s->dp.p + 3 * (size_t)P0, s->vx.p, s->pts.p + 3 * (size_t)P0, s->pts2.p + 3 * (size_t)P0, s->part_pt.p,
-      s->refine ? s->Apc.p : nullptr, s->refine ? s->xi.p : nullptr); MM_LAUNCH_CHECK();
+      s->refine ? s->Apc.p + 27 * (size_t)P0 * s->n_cam : nullptr, s->refine ? s->xi.p : nullptr, s->n_cam, s->refine ? s->pt_cam_mask.p + P0 : nullptr); MM_LAUNCH_CHECK();
   k_update_cam<<<gc_, 128, 0, st>>>(6 * s->n_img, s->vx.p, s->scale_c.p, s->gc.p, s->dc.p, s->poses.p, s->poses2.p, s->part_cam.p); MM_LAUNCH_CHECK();
-  if (s->refine) { k_update_intr<<<1, 32, 0, st>>>(s->xi.p, s->scale_i.p, s->gi.p, s->di.p, s->intr.p, s->intr2.p, s->part_cam.p + 2 * (size_t)gc_); MM_LAUNCH_CHECK(); }
+  if (s->refine) { k_update_intr<<<1, 32, 0, st>>>(s->n_cam, s->xi.p, s->scale_i.p, s->gi.p, s->di.p, s->intr.p, s->intr2.p, s->part_cam.p + 2 * (size_t)gc_); MM_LAUNCH_CHECK(); }
   // the (replicated) camera part of |step|^2 and of the model cost change is counted on rank 0 only
   k_reduce_pairs<<<1, 256, 0, st>>>(s->part_pt.p, gp_, s->part_cam.p, s->rank == 0 ? gc_ + (s->refine ? 1 : 0) : 0, s->loc.p + 3); MM_LAUNCH_CHECK();
   return MM_OK;
@@ -835,7 +837,7 @@ int launch_update(mm_ba_session* s) {
 int launch_xnorm(mm_ba_session* s) {
   cudaStream_t st = s->stream;
   k_xnorm<<<s->grid_x, 256, 0, st>>>(s->rank == 0 ? 6 * s->n_img : 0, s->poses.p, s->pose_mask.p, s->np_loc(), s->pts.p + 3 * (size_t)s->p_lo, s->pt_mask.p + s->p_lo, s->part_x.p,
-      s->refine ? s->intr.p : nullptr, s->intr_mask.p); MM_LAUNCH_CHECK();
+      s->refine && s->rank == 0 ? s->intr.p : nullptr, s->intr_mask.p, s->n_cam); MM_LAUNCH_CHECK();
   k_reduce_sum<<<1, 256, 0, st>>>(s->part_x.p, s->grid_x, s->loc.p + 5); MM_LAUNCH_CHECK();
   return MM_OK;
 }
@@ -992,8 +994,7 @@ int mm_ba_session_create_sharded(const mm_ba_problem* P, const mm_ba_options* op
     bool used = false; for (int i = 0; i < P->n_img; ++i) if (P->img_cam[i] == c) used = true;
     if (used) refine = true;
   }
-  if (refine && P->n_cam != 1) { set_error("refine_camera_params on the device engine handles one shared camera (got %d)", P->n_cam); return MM_ERR_UNSUPPORTED; }
-  if (refine && world > 1) { set_error("refine_camera_params is not available with a sharded session"); return MM_ERR_UNSUPPORTED; }
+  if (refine && P->n_cam > 32) { set_error("refine_camera_params handles up to 32 cameras (got %d)", P->n_cam); return MM_ERR_UNSUPPORTED; }
   rc = ensure_device(); if (rc) return rc;
   mm_ba_session* s = new mm_ba_session();
   s->stream = (cudaStream_t)stream; s->opt = *opt;
@@ -1021,14 +1022,21 @@ int mm_ba_session_create_sharded(const mm_ba_problem* P, const mm_ba_options* op
   s->grid_x = grid_stride(std::max<int64_t>(3 * (int64_t)P->n_pt, 1), 256);
   A(s->part_cost, (size_t)grid_stride(std::max<int64_t>(P->n_obs, 1), 256)); A(s->part_pt, 2 * (size_t)blocks_for(P->n_pt, 128)); A(s->part_cam, 2 * (size_t)blocks_for(6 * (int64_t)P->n_img, 128) + 2);
   A(s->part_x, (size_t)s->grid_x);
-  A(s->intr2, MM_INTR_STRIDE * n_cam); A(s->intr_mask, 9); A(s->scale_i, 9);
+  A(s->intr2, MM_INTR_STRIDE * n_cam); A(s->intr_mask, 9 * n_cam); A(s->scale_i, 9 * n_cam);
   if (refine) {
-    A(s->Apc, 27 * n_pt); A(s->Bm, 54 * n_img); A(s->intr_acc, 108); A(s->Cinv, 81);
-    A(s->gi, 9); A(s->di, 9); s->xi.view(s->vx.p + 6 * n_img, 9 * n_cam); A(s->zi, 9); A(s->pi0, 9); A(s->pi1, 9); A(s->bt, 18); A(s->sq9, 9);
+    // exchange buffer of the border: B | C, b, diag, gradient  (contiguous: one all-reduce)
+    const size_t nB = 54 * n_img * n_cam, nA = 81 * n_cam * n_cam + 27 * n_cam;
+    s->xch2_count = nB + nA;
+    A(s->xch2, s->xch2_count); s->Bm.view(s->xch2.p, nB); s->intr_acc.view(s->xch2.p + nB, nA);
+    A(s->gi, 9 * n_cam); A(s->di, 9 * n_cam); s->xi.view(s->vx.p + 6 * n_img, 9 * n_cam); A(s->img_sq, 9 * n_img);
   }
-  { double im[9]; for (int k = 0; k < 9; ++k) im[k] = (refine && k < model_num_params(P->cam_model[0])) ? 1.0 : 0.0;
-    double ones[9]; for (int k = 0; k < 9; ++k) ones[k] = 1.0;
-    if (cudaMemcpy(s->intr_mask.p, im, sizeof im, cudaMemcpyHostToDevice) != cudaSuccess || cudaMemcpy(s->scale_i.p, ones, sizeof ones, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("mask upload failed"); return fail_out(MM_ERR_CUDA); } }
+  { // free intrinsics: the parameters of the camera's model, for cameras that are used and not held constant
+    std::vector<double> im(9 * n_cam, 0.0), ones(9 * n_cam, 1.0);
+    for (int c = 0; c < P->n_cam; ++c) {
+      bool used = false; for (int i = 0; i < P->n_img; ++i) if (P->img_cam[i] == c) used = true;
+      if (refine && used && !P->intr_const[c]) for (int k = 0; k < model_num_params(P->cam_model[c]); ++k) im[9 * (size_t)c + k] = 1.0;
+    }
+    if (cudaMemcpy(s->intr_mask.p, im.data(), sizeof(double) * im.size(), cudaMemcpyHostToDevice) != cudaSuccess || cudaMemcpy(s->scale_i.p, ones.data(), sizeof(double) * ones.size(), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("mask upload failed"); return fail_out(MM_ERR_CUDA); } }
   // masks: 1.0 = free and present in at least one residual block
   { std::vector<int> img_n(n_img, 0), pt_n(n_pt, 0);
     for (int64_t o = 0; o < P->n_obs; ++o) { img_n[P->obs_img[o]]++; pt_n[P->obs_pt[o]]++; }
@@ -1045,7 +1053,6 @@ int mm_ba_session_create_sharded(const mm_ba_problem* P, const mm_ba_options* op
   if (P->rot_prior && P->rot_prior_w) {
     for (int i = 0; i < P->n_img; ++i) if (P->rot_prior_w[i] != 0.0) s->n_prior++;
     if (s->n_prior) {
-      if (refine) { set_error("constrain_rotation together with refine_camera_params is not available on the device engine"); return fail_out(MM_ERR_UNSUPPORTED); }
       A(s->pr_rot0, 3 * n_img); A(s->pr_w, n_img); A(s->pr_r, n_img); A(s->pr_J, 3 * n_img);
       if (cudaMemcpy(s->pr_rot0.p, P->rot_prior, sizeof(double) * 3 * (size_t)P->n_img, cudaMemcpyHostToDevice) != cudaSuccess ||
           cudaMemcpy(s->pr_w.p, P->rot_prior_w, sizeof(double) * (size_t)P->n_img, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("constraint upload failed"); return fail_out(MM_ERR_CUDA); }
@@ -1059,7 +1066,7 @@ int mm_ba_session_create_sharded(const mm_ba_problem* P, const mm_ba_options* op
   rc = s->tc_on ? MM_OK : build_aggregates(s); if (rc) return fail_out(rc);
   rc = build_shard(s); if (rc) return fail_out(rc);
   A(s->rec, (size_t)REC * (size_t)std::max<int64_t>(s->no_loc(), 1));
-  if (refine) A(s->ji, 18 * (size_t)std::max<int64_t>(P->n_obs, 1));
+  if (refine) { A(s->ji, 18 * (size_t)std::max<int64_t>(s->no_loc(), 1)); A(s->Apc, 27 * n_pt * n_cam); A(s->pt_cam_mask, n_pt); }
   s->grid_obs = grid_stride(std::max<int64_t>(s->no_loc(), 1), 256);
   { // the exchange buffer: S | rhs | gc | ud | scalars, contiguous so that one all-reduce moves it
     const size_t nS = 36 * (size_t)std::max<int64_t>(s->nblk, 1), nv = 6 * n_img;

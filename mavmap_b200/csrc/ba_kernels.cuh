@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256, WITH_J ? 2 : 3) k_residual_jacobian(
         double2* j2 = reinterpret_cast<double2*>(ji + 18 * (size_t)(i0 + lane));
         double t[18];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) { const double m = intr_mask[k] * sr; t[k] = dP[0][k] * m; t[9 + k] = dP[1][k] * m; }
+        for (int k = 0; k < 9; ++k) { const double m = intr_mask[9 * (size_t)cam + k] * sr; t[k] = dP[0][k] * m; t[9 + k] = dP[1][k] * m; }
 #pragma unroll
         for (int k = 0; k < 9; ++k) j2[k] = make_double2(t[2 * k], t[2 * k + 1]);
       }
@@ -1066,45 +1066,75 @@ __global__ void __launch_bounds__(THREADS, 1) k_pcg_cached(PcgArgs A, int e_cap)
   if (blockIdx.x == 0 && threadIdx.x == 0) A.ic[1] = it;
 }
 
-// ---- refined intrinsics (single shared camera): dense border of the reduced system ----------------------
-// Unknowns of the reduced system become [poses (6 n_img) | intrinsics (9)].  With E = d r / d intr (scaled):
-//   A_p  = sum_{obs of p} E' Jp                       (9 x 3, stored per point for the back-substitution)
-//   C    = sum_obs E'E + D_i^2 - sum_p A_p V_p^-1 A_p'   (9 x 9)
-//   b_i  = sum_obs E'r - sum_p A_p V_p^-1 g_p
-//   B_a  = sum_{obs of image a} (Jc'E - Y_obs A_p')       (6 x 9), Y_obs = Jc'Jp V_p^-1
-// intr_acc layout (doubles): [0,81) C   [81,90) b_i   [90,99) diag(E'E)   [99,108) E'r (unreduced gradient)
-__global__ void k_colnorm_intr(int64_t n_obs, const double* __restrict__ ji, double* __restrict__ out9) {
-  __shared__ double red[32];
+// ---- refined intrinsics: dense border of the reduced system ----------------------------------------------
+// One intrinsics block of 9 per camera (bundle_adjustment.cc:246-247: camera_params is one parameter block per camera id,
+// shared by all its images; refine_camera_params is the mapper's default, mapper.cc:878-886).  Unknowns of the reduced system
+// become [poses (6 n_img) | intrinsics (9 n_cam)].  With E = d r / d intr of the observation's camera (scaled):
+//   A_pc   = sum_{obs of p in camera c} E' Jp                   (9 x 3, stored per point and camera for the back-substitution)
+//   C_cc'  = [c = c'] (sum_obs E'E + D_i^2) - sum_p A_pc V_p^-1 A_pc''      (9 x 9 blocks)
+//   b_c    = sum_obs E'r - sum_p A_pc V_p^-1 g_p
+//   B_ac'  = [c' = cam(a)] sum_{obs of a} Jc'E - sum_{obs of a} Y_obs A_pc''   (6 x 9), Y_obs = Jc'Jp V_p^-1
+// intr_acc layout (doubles, n9 = 9 n_cam): [0, n9^2) C row-major | b (n9) | diag(E'E) (n9) | E'r, the unreduced gradient (n9)
+__global__ void __launch_bounds__(128) k_colnorm_intr_img(int n_img, const int* __restrict__ cam_lo, const int* __restrict__ cam_hi, const int* __restrict__ cam_perm,
+                                                          const double* __restrict__ ji /* indexed by global observation position */, double* __restrict__ img_sq /*[n_img][9]*/) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n_img) return;
   double a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_obs; i += (int64_t)gridDim.x * blockDim.x) {
-    const double* j = ji + 18 * (size_t)i;
+  for (int q = cam_lo[w] + lane; q < cam_hi[w]; q += 32) {
+    const double* j = ji + 18 * (size_t)cam_perm[q];
 #pragma unroll
     for (int k = 0; k < 9; ++k) a[k] += j[k] * j[k] + j[9 + k] * j[9 + k];
   }
 #pragma unroll
-  for (int k = 0; k < 9; ++k) { const double v = block_sum(a[k], red); if (threadIdx.x == 0) atomicAdd(out9 + k, v); }
+  for (int k = 0; k < 9; ++k) { const double v = warp_sum(a[k]); if (lane == 0) img_sq[9 * (size_t)w + k] = v; }
 }
-__global__ void k_intr_scale(const double* __restrict__ sq9, double* __restrict__ scale_i) {
-  if (threadIdx.x < 9) scale_i[threadIdx.x] = 1.0 / (1.0 + sqrt(sq9[threadIdx.x]));
+// one CTA per camera: column sums over its images in a fixed order -> Jacobi scale 1 / (1 + norm)
+__global__ void __launch_bounds__(256) k_intr_scale(int n_img, const int* __restrict__ img_cam, const double* __restrict__ img_sq, double* __restrict__ scale_i) {
+  __shared__ double red[32];
+  const int c = blockIdx.x;
+  double a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = threadIdx.x; i < n_img; i += blockDim.x) if (img_cam[i] == c) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a[k] += img_sq[9 * (size_t)i + k];
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { const double v = block_sum(a[k], red); if (threadIdx.x == 0) scale_i[9 * (size_t)c + k] = 1.0 / (1.0 + sqrt(v)); }
 }
 
+// thread per point of this rank: A_pc for every camera that sees the point, and the point's contributions to C, b, diag, gradient.
+// cam_mask[p]: bit c set = A_pc is non-zero (cameras beyond 32 are refused at session creation).
 __global__ void __launch_bounds__(128) k_schur_intr_point(
-    int n_pt, const int* __restrict__ pt_start, const double* __restrict__ rec, const double* __restrict__ ji,
+    int n_pt, int n_cam, const int* __restrict__ pt_start, const int* __restrict__ obs_img, const int* __restrict__ img_cam,
+    const double* __restrict__ rec, const double* __restrict__ ji,
     const double* __restrict__ scale_p, const double* __restrict__ scale_i, const double* __restrict__ Vinv, const double* __restrict__ gp,
-    double* __restrict__ Apc, double* __restrict__ intr_acc) {
-  __shared__ double red[32];
+    double* __restrict__ Apc, unsigned* __restrict__ cam_mask, double* __restrict__ intr_acc) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  double A[9][3], Cc[45], rh[9], ud[9], gu[9];
+  const int lane = threadIdx.x & 31;
+  const int n9 = 9 * n_cam;
+  double* Cm = intr_acc; double* bi = intr_acc + (size_t)n9 * n9; double* dg = bi + n9; double* gr = dg + n9;
+  const bool live = p < n_pt;
+  const int o0 = live ? pt_start[p] : 0, o1 = live ? pt_start[p + 1] : 0;
+  double sp[3] = {1, 1, 1}, I[6] = {0, 0, 0, 0, 0, 0}, g3[3] = {0, 0, 0};
+  if (live) {
 #pragma unroll
-  for (int a = 0; a < 9; ++a) { A[a][0] = A[a][1] = A[a][2] = 0.0; rh[a] = 0.0; ud[a] = 0.0; gu[a] = 0.0; }
+    for (int k = 0; k < 3; ++k) { sp[k] = scale_p[3 * (size_t)p + k]; g3[k] = gp[3 * (size_t)p + k]; }
 #pragma unroll
-  for (int k = 0; k < 45; ++k) Cc[k] = 0.0;
-  if (p < n_pt) {
+    for (int k = 0; k < 6; ++k) I[k] = Vinv[6 * (size_t)p + k];
+  }
+  unsigned mask = 0;
+  for (int c = 0; c < n_cam; ++c) {
+    double A[9][3], Cc[45], rh[9], ud[9], gu[9];
+#pragma unroll
+    for (int a = 0; a < 9; ++a) { A[a][0] = A[a][1] = A[a][2] = 0.0; rh[a] = 0.0; ud[a] = 0.0; gu[a] = 0.0; }
+#pragma unroll
+    for (int k = 0; k < 45; ++k) Cc[k] = 0.0;
+    bool any = false;
     double si[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) si[k] = scale_i[k];
-    const double sp[3] = { scale_p[3 * (size_t)p], scale_p[3 * (size_t)p + 1], scale_p[3 * (size_t)p + 2] };
-    for (int o = pt_start[p]; o < pt_start[p + 1]; ++o) {
+    for (int k = 0; k < 9; ++k) si[k] = scale_i[9 * (size_t)c + k];
+    for (int o = o0; o < o1; ++o) {
+      if (img_cam[obs_img[o]] != c) continue;
+      any = true;
       const double2* r2 = reinterpret_cast<const double2*>(rec + REC * (size_t)o);
       const double2 rr = r2[0], q7 = r2[7], q8 = r2[8], q9 = r2[9];
       const double jp0[3] = { q7.x * sp[0], q7.y * sp[1], q8.x * sp[2] }, jp1[3] = { q8.y * sp[0], q9.x * sp[1], q9.y * sp[2] };
@@ -1120,121 +1150,143 @@ __global__ void __launch_bounds__(128) k_schur_intr_point(
         for (int b = a; b < 9; ++b, ++k) Cc[k] += e0 * (j[b] * si[b]) + e1 * (j[9 + b] * si[b]);
       }
     }
-    const double* I = Vinv + 6 * (size_t)p;
-    const double g0 = gp[3 * (size_t)p], g1 = gp[3 * (size_t)p + 1], g2 = gp[3 * (size_t)p + 2];
-    int k = 0;
+    if (any) mask |= 1u << c;
+    // t = A_pc V^-1;  b_c -= t g_p;  C_cc -= t A_pc';  C_cc' -= t A_pc'' (c' < c, A_pc' written by this thread in an earlier round)
+    double t[9][3];
 #pragma unroll
     for (int a = 0; a < 9; ++a) {
-      const double t0 = A[a][0] * I[0] + A[a][1] * I[1] + A[a][2] * I[2];
-      const double t1 = A[a][0] * I[1] + A[a][1] * I[3] + A[a][2] * I[4];
-      const double t2 = A[a][0] * I[2] + A[a][1] * I[4] + A[a][2] * I[5];
-      rh[a] -= t0 * g0 + t1 * g1 + t2 * g2;
+      t[a][0] = A[a][0] * I[0] + A[a][1] * I[1] + A[a][2] * I[2];
+      t[a][1] = A[a][0] * I[1] + A[a][1] * I[3] + A[a][2] * I[4];
+      t[a][2] = A[a][0] * I[2] + A[a][1] * I[4] + A[a][2] * I[5];
+      rh[a] -= t[a][0] * g3[0] + t[a][1] * g3[1] + t[a][2] * g3[2];
+    }
+    {
+      int k = 0;
 #pragma unroll
-      for (int b = a; b < 9; ++b, ++k) Cc[k] -= t0 * A[b][0] + t1 * A[b][1] + t2 * A[b][2];
-      Apc[27 * (size_t)p + 3 * a] = A[a][0]; Apc[27 * (size_t)p + 3 * a + 1] = A[a][1]; Apc[27 * (size_t)p + 3 * a + 2] = A[a][2];
+      for (int a = 0; a < 9; ++a)
+#pragma unroll
+        for (int b = a; b < 9; ++b, ++k) Cc[k] -= t[a][0] * A[b][0] + t[a][1] * A[b][1] + t[a][2] * A[b][2];
+    }
+    if (live && any) {
+      double* dst = Apc + 27 * ((size_t)p * n_cam + c);
+#pragma unroll
+      for (int a = 0; a < 9; ++a) { dst[3 * a] = A[a][0]; dst[3 * a + 1] = A[a][1]; dst[3 * a + 2] = A[a][2]; }
+    }
+    // warp reductions, one atomic per warp and value (skipped when no lane of the warp has the camera)
+    const unsigned warp_any = __ballot_sync(0xffffffffu, any);
+    if (warp_any) {
+      int k = 0;
+#pragma unroll
+      for (int a = 0; a < 9; ++a)
+#pragma unroll
+        for (int b = a; b < 9; ++b, ++k) {
+          const double v = warp_sum(Cc[k]);
+          if (lane == 0 && v != 0.0) { atomicAdd(Cm + (size_t)(9 * c + a) * n9 + 9 * c + b, v); if (b != a) atomicAdd(Cm + (size_t)(9 * c + b) * n9 + 9 * c + a, v); }
+        }
+#pragma unroll
+      for (int a = 0; a < 9; ++a) {
+        const double v0 = warp_sum(rh[a]), v1 = warp_sum(ud[a]), v2 = warp_sum(gu[a]);
+        if (lane == 0) { atomicAdd(bi + 9 * c + a, v0); atomicAdd(dg + 9 * c + a, v1); atomicAdd(gr + 9 * c + a, v2); }
+      }
+    }
+    for (int c2 = 0; c2 < c; ++c2) {
+      const bool both = any && ((mask >> c2) & 1u);
+      if (!__ballot_sync(0xffffffffu, both)) continue;
+      const double* A2 = Apc + 27 * ((size_t)(live ? p : 0) * n_cam + c2);
+#pragma unroll
+      for (int a = 0; a < 9; ++a)
+#pragma unroll
+        for (int b = 0; b < 9; ++b) {
+          double v = both ? -(t[a][0] * A2[3 * b] + t[a][1] * A2[3 * b + 1] + t[a][2] * A2[3 * b + 2]) : 0.0;
+          v = warp_sum(v);
+          if (lane == 0 && v != 0.0) { atomicAdd(Cm + (size_t)(9 * c + a) * n9 + 9 * c2 + b, v); atomicAdd(Cm + (size_t)(9 * c2 + b) * n9 + 9 * c + a, v); }
+        }
     }
   }
-  int k = 0;
-#pragma unroll
-  for (int a = 0; a < 9; ++a)
-#pragma unroll
-    for (int b = a; b < 9; ++b, ++k) {
-      const double v = block_sum(Cc[k], red);
-      if (threadIdx.x == 0 && v != 0.0) { atomicAdd(intr_acc + 9 * a + b, v); if (b != a) atomicAdd(intr_acc + 9 * b + a, v); }
-    }
-#pragma unroll
-  for (int a = 0; a < 9; ++a) {
-    const double v0 = block_sum(rh[a], red), v1 = block_sum(ud[a], red), v2 = block_sum(gu[a], red);
-    if (threadIdx.x == 0) { atomicAdd(intr_acc + 81 + a, v0); atomicAdd(intr_acc + 90 + a, v1); atomicAdd(intr_acc + 99 + a, v2); }
-  }
+  if (live) cam_mask[p] = mask;
 }
 
-// warp per image: B_a (6 x 9)
+// warp per image: B_ac' (6 x 9) for every camera c'
 __global__ void __launch_bounds__(128) k_schur_cam_intr(
-    int n_img, const int* __restrict__ cam_start, const int* __restrict__ cam_perm, const int* __restrict__ obs_pt,
-    const double* __restrict__ rec, const double* __restrict__ ji, const double* __restrict__ scale_c, const double* __restrict__ scale_p,
-    const double* __restrict__ scale_i, const double* __restrict__ Vinv, const double* __restrict__ Apc, double* __restrict__ Bm) {
+    int n_img, int n_cam, const int* __restrict__ cam_lo, const int* __restrict__ cam_hi, const int* __restrict__ cam_perm, const int* __restrict__ obs_pt,
+    const int* __restrict__ img_cam, const double* __restrict__ rec, const double* __restrict__ ji, const double* __restrict__ scale_c, const double* __restrict__ scale_p,
+    const double* __restrict__ scale_i, const double* __restrict__ Vinv, const double* __restrict__ Apc, const unsigned* __restrict__ cam_mask, double* __restrict__ Bm) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= n_img) return;
-  double sc[6], si[9], acc[6][9];
+  const int cam = img_cam[w];
+  double sc[6], si[9];
 #pragma unroll
   for (int k = 0; k < 6; ++k) sc[k] = scale_c[6 * (size_t)w + k];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) si[k] = scale_i[k];
+  for (int k = 0; k < 9; ++k) si[k] = scale_i[9 * (size_t)cam + k];
+  for (int c2 = 0; c2 < n_cam; ++c2) {
+    double acc[6][9];
 #pragma unroll
-  for (int a = 0; a < 6; ++a)
+    for (int a = 0; a < 6; ++a)
 #pragma unroll
-    for (int m = 0; m < 9; ++m) acc[a][m] = 0.0;
-  for (int q = cam_start[w] + lane; q < cam_start[w + 1]; q += 32) {
-    const int o = cam_perm[q], p = obs_pt[o];
-    const double sp[3] = { scale_p[3 * (size_t)p], scale_p[3 * (size_t)p + 1], scale_p[3 * (size_t)p + 2] };
-    double Jc[2][6], Jp[2][3];
-    load_scaled(rec, o, sc, sp, Jc, Jp);
-    double I[6];
+      for (int m = 0; m < 9; ++m) acc[a][m] = 0.0;
+    for (int q = cam_lo[w] + lane; q < cam_hi[w]; q += 32) {
+      const int o = cam_perm[q], p = obs_pt[o];
+      const bool has = (cam_mask[p] >> c2) & 1u;
+      if (!has && c2 != cam) continue;
+      const double sp[3] = { scale_p[3 * (size_t)p], scale_p[3 * (size_t)p + 1], scale_p[3 * (size_t)p + 2] };
+      double Jc[2][6], Jp[2][3];
+      load_scaled(rec, o, sc, sp, Jc, Jp);
+      if (c2 == cam) {
+        const double* j = ji + 18 * (size_t)o;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) I[k] = Vinv[6 * (size_t)p + k];
-    const double* j = ji + 18 * (size_t)o;
-    const double* Ap = Apc + 27 * (size_t)p;
-    double e0[9], e1[9];
+        for (int m = 0; m < 9; ++m) {
+          const double e0 = j[m] * si[m], e1 = j[9 + m] * si[m];
 #pragma unroll
-    for (int m = 0; m < 9; ++m) { e0[m] = j[m] * si[m]; e1[m] = j[9 + m] * si[m]; }
+          for (int a = 0; a < 6; ++a) acc[a][m] += Jc[0][a] * e0 + Jc[1][a] * e1;
+        }
+      }
+      if (has) {
+        double I[6];
 #pragma unroll
-    for (int a = 0; a < 6; ++a) {
-      const double w0 = Jc[0][a] * Jp[0][0] + Jc[1][a] * Jp[1][0];
-      const double w1 = Jc[0][a] * Jp[0][1] + Jc[1][a] * Jp[1][1];
-      const double w2 = Jc[0][a] * Jp[0][2] + Jc[1][a] * Jp[1][2];
-      const double y0 = w0 * I[0] + w1 * I[1] + w2 * I[2], y1 = w0 * I[1] + w1 * I[3] + w2 * I[4], y2 = w0 * I[2] + w1 * I[4] + w2 * I[5];
+        for (int k = 0; k < 6; ++k) I[k] = Vinv[6 * (size_t)p + k];
+        const double* Ap = Apc + 27 * ((size_t)p * n_cam + c2);
 #pragma unroll
-      for (int m = 0; m < 9; ++m)
-        acc[a][m] += Jc[0][a] * e0[m] + Jc[1][a] * e1[m] - (y0 * Ap[3 * m] + y1 * Ap[3 * m + 1] + y2 * Ap[3 * m + 2]);
+        for (int a = 0; a < 6; ++a) {
+          const double w0 = Jc[0][a] * Jp[0][0] + Jc[1][a] * Jp[1][0];
+          const double w1 = Jc[0][a] * Jp[0][1] + Jc[1][a] * Jp[1][1];
+          const double w2 = Jc[0][a] * Jp[0][2] + Jc[1][a] * Jp[1][2];
+          const double y0 = w0 * I[0] + w1 * I[1] + w2 * I[2], y1 = w0 * I[1] + w1 * I[3] + w2 * I[4], y2 = w0 * I[2] + w1 * I[4] + w2 * I[5];
+#pragma unroll
+          for (int m = 0; m < 9; ++m) acc[a][m] -= y0 * Ap[3 * m] + y1 * Ap[3 * m + 1] + y2 * Ap[3 * m + 2];
+        }
+      }
     }
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int m = 0; m < 9; ++m) { const double v = warp_sum(acc[a][m]); if (lane == 0) Bm[54 * ((size_t)w * n_cam + c2) + 9 * a + m] = v; }
   }
-#pragma unroll
-  for (int a = 0; a < 6; ++a)
-#pragma unroll
-    for (int m = 0; m < 9; ++m) { const double v = warp_sum(acc[a][m]); if (lane == 0) Bm[54 * (size_t)w + 9 * a + m] = v; }
 }
 
-// one warp: LM diagonal of the intrinsics, C^-1 (preconditioner block), gradient max-norm
-__global__ void k_intr_finalize(LMDiag lm, const double* __restrict__ scale_i, double* __restrict__ intr_acc, double* __restrict__ Cinv,
-                                double* __restrict__ gi_out, double* __restrict__ di_out, double* __restrict__ gmax, int* __restrict__ fail) {
-  if (threadIdx.x != 0) return;
-  double C[9][9], L[9][9];
-  double gm = 0.0;
-  for (int a = 0; a < 9; ++a) {
-    const double d = fmin(fmax(intr_acc[90 + a], lm.min_diag), lm.max_diag) / lm.radius;
-    di_out[a] = d; gi_out[a] = intr_acc[99 + a];
-    intr_acc[9 * a + a] += d;
-    gm = fmax(gm, fabs(intr_acc[99 + a] / scale_i[a]));
-  }
-  for (int a = 0; a < 9; ++a) for (int b = 0; b < 9; ++b) C[a][b] = intr_acc[9 * a + b];
-  bool ok = true;
-  for (int j = 0; j < 9; ++j) {
-    double d = C[j][j];
-    for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
-    if (!(d > 0.0)) { ok = false; d = 1.0; }
-    L[j][j] = sqrt(d);
-    for (int r = j + 1; r < 9; ++r) { double s = C[r][j]; for (int k = 0; k < j; ++k) s -= L[r][k] * L[j][k]; L[r][j] = s / L[j][j]; }
-  }
-  for (int c = 0; c < 9; ++c) {
-    double y[9];
-    for (int r = 0; r < 9; ++r) { double s = (r == c) ? 1.0 : 0.0; for (int k = 0; k < r; ++k) s -= L[r][k] * y[k]; y[r] = s / L[r][r]; }
-    for (int r = 8; r >= 0; --r) { double s = y[r]; for (int k = r + 1; k < 9; ++k) s -= L[k][r] * y[k]; y[r] = s / L[r][r]; }
-    for (int r = 0; r < 9; ++r) Cinv[9 * r + c] = y[r];
-  }
-  if (!ok) *fail = 1;
+// after the exchange step: LM diagonal of the intrinsics onto C, gradient, its max-norm.  One thread per intrinsics unknown.
+__global__ void k_intr_finalize(int n9, LMDiag lm, const double* __restrict__ scale_i, double* __restrict__ intr_acc,
+                                double* __restrict__ gi_out, double* __restrict__ di_out, double* __restrict__ gmax) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n9) return;
+  double* Cm = intr_acc; const double* dg = intr_acc + (size_t)n9 * n9 + n9; const double* gr = dg + n9;
+  const double d = fmin(fmax(dg[a], lm.min_diag), lm.max_diag) / lm.radius;
+  di_out[a] = d; gi_out[a] = gr[a];
+  Cm[(size_t)a * n9 + a] += d;
+  const double gm = fabs(gr[a] / scale_i[a]);
   if (gm > 0.0) atomic_max_nonneg(gmax, gm);
 }
 
-// candidate intrinsics + their share of ||step||^2 and of the model cost change
-__global__ void k_update_intr(const double* __restrict__ yi, const double* __restrict__ scale_i, const double* __restrict__ gi, const double* __restrict__ di,
+// candidate intrinsics + their share of ||step||^2 and of the model cost change (one warp, fixed order)
+__global__ void k_update_intr(int n_cam, const double* __restrict__ yi, const double* __restrict__ scale_i, const double* __restrict__ gi, const double* __restrict__ di,
                               const double* __restrict__ intr, double* __restrict__ intr2, double* __restrict__ part2) {
   if (threadIdx.x != 0) return;
   double sn = 0.0, mc = 0.0;
-  for (int k = 0; k < 9; ++k) {
-    const double y = yi[k], e = -y * scale_i[k];
-    intr2[k] = intr[k] + e; sn += e * e; mc += 0.5 * y * (gi[k] + di[k] * y);
-  }
+  for (int c = 0; c < n_cam; ++c)
+    for (int k = 0; k < 9; ++k) {
+      const double y = yi[9 * c + k], e = -y * scale_i[9 * c + k];
+      intr2[MM_INTR_STRIDE * c + k] = intr[MM_INTR_STRIDE * c + k] + e; sn += e * e; mc += 0.5 * y * (gi[9 * c + k] + di[9 * c + k] * y);
+    }
   part2[0] = sn; part2[1] = mc;
 }
 
@@ -1246,7 +1298,7 @@ __global__ void __launch_bounds__(128) k_backsub(
     const double* __restrict__ scale_c, const double* __restrict__ scale_p, const double* __restrict__ Vinv,
     const double* __restrict__ gp, const double* __restrict__ dp, const double* __restrict__ yc,
     const double* __restrict__ pts, double* __restrict__ pts2, double* __restrict__ part /*[2*grid]*/,
-    const double* __restrict__ Apc = nullptr, const double* __restrict__ yi = nullptr) {
+    const double* __restrict__ Apc = nullptr, const double* __restrict__ yi = nullptr, int n_cam = 0, const unsigned* __restrict__ cam_mask = nullptr) {
   __shared__ double red[32];
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   double sn = 0.0, mc = 0.0;
@@ -1264,10 +1316,13 @@ __global__ void __launch_bounds__(128) k_backsub(
 #pragma unroll
       for (int k = 0; k < 3; ++k) t[k] -= Jp[0][k] * q0 + Jp[1][k] * q1;
     }
-    if (Apc) {        // - A_p' y_i (refined intrinsics)
-      const double* Ap = Apc + 27 * (size_t)p;
+    if (Apc) {        // - sum_c A_pc' y_c (refined intrinsics)
+      const unsigned mask = cam_mask[p];
+      for (int c = 0; c < n_cam; ++c) if ((mask >> c) & 1u) {
+        const double* Ap = Apc + 27 * ((size_t)p * n_cam + c);
 #pragma unroll
-      for (int a = 0; a < 9; ++a) { const double y = yi[a]; t[0] -= Ap[3 * a] * y; t[1] -= Ap[3 * a + 1] * y; t[2] -= Ap[3 * a + 2] * y; }
+        for (int a = 0; a < 9; ++a) { const double y = yi[9 * c + a]; t[0] -= Ap[3 * a] * y; t[1] -= Ap[3 * a + 1] * y; t[2] -= Ap[3 * a + 2] * y; }
+      }
     }
     const double* I = Vinv + 6 * (size_t)p;
     const double y0 = I[0] * t[0] + I[1] * t[1] + I[2] * t[2];
@@ -1313,10 +1368,10 @@ __global__ void k_reduce_pairs(const double* __restrict__ partA, int nA, const d
 // sum of squares of the active parameters (x_norm of the reduced program)
 __global__ void k_xnorm(int n_c, const double* __restrict__ poses, const double* __restrict__ pose_mask,
                         int n_pt, const double* __restrict__ pts, const double* __restrict__ pt_mask, double* __restrict__ part,
-                        const double* __restrict__ intr = nullptr, const double* __restrict__ intr_mask = nullptr) {
+                        const double* __restrict__ intr = nullptr, const double* __restrict__ intr_mask = nullptr, int n_cam = 0) {
   __shared__ double red[32];
   double s = 0.0;
-  if (intr && blockIdx.x == 0 && threadIdx.x < 9) s += intr_mask[threadIdx.x] * intr[threadIdx.x] * intr[threadIdx.x];
+  if (intr && blockIdx.x == 0) for (int i = threadIdx.x; i < 9 * n_cam; i += blockDim.x) { const double v = intr[MM_INTR_STRIDE * (i / 9) + i % 9]; s += intr_mask[i] * v * v; }
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_c; i += (int64_t)gridDim.x * blockDim.x)
     s += pose_mask[i] * poses[i] * poses[i];
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < 3 * (int64_t)n_pt; i += (int64_t)gridDim.x * blockDim.x)

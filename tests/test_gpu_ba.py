@@ -232,7 +232,7 @@ def test_sharded_ba_two_gpus_matches_single_gpu(mm):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sk = socket.socket(); sk.bind(("127.0.0.1", 0)); port = sk.getsockname()[1]; sk.close()
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                        "--master-port", str(port), os.path.join(root, "tools", "sharded_ba.py"), "mid"], capture_output=True, text=True, timeout=600)
+                        "--master-port", str(port), os.path.join(root, "tools", "sharded_ba.py"), "mid", "midrefine"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
@@ -320,6 +320,40 @@ def test_mixed_camera_rig_parity(mm, orc):
     # three cameras incl. CATA, with the two-level preconditioner switched on (>= 64 images)
     flat3, _ = synthetic.make_ba_problem(outlier_frac=0.0, models=[1, 2, 3], n_img=90, n_obs_target=60000, track_len=4, seed=31)
     _assert_parity(*_both(orc, flat3, 8))
+
+
+@pytest.mark.parametrize("models,cfg", [([1, 2], "small"), ([1, 2, 3], None), ([2, 2, 1, 3, 1, 2], None)])
+def test_refine_camera_params_with_several_cameras(mm, orc, models, cfg):
+    """refine_camera_params=true with a rig of several cameras (the mapper's default options on BASELINE.json configs[4]):
+    one intrinsics block of 9 per camera id (bundle_adjustment.cc:246-247, sequential_mapper.cc:954-973), shared by the camera's
+    images -> a border of 9 n_cam columns on the reduced system, cross-camera blocks where cameras see common points."""
+    kw = synthetic.BA_CONFIGS[cfg] if cfg else dict(n_img=90, n_obs_target=60000, track_len=4, seed=31 + len(models))
+    flat, truth = synthetic.make_ba_problem(outlier_frac=0.0, models=models, refine_camera_params=True, **kw)
+    flat.intr[:, :2] *= 0.997; flat.intr[:, 2:4] += 1.5
+    g, c, sg, so = _both(orc, flat, 8)
+    _assert_parity(g, c, sg, so, param_rel=4e-6)
+    assert not np.allclose(g.intr[:, :4], flat.intr[:, :4])
+    pin = np.array(models) != 3               # (the focal length of a CATA camera trades against xi: weakly determined, checked by parity only)
+    assert np.all(np.abs(g.intr[pin, 0] - truth["intr"][pin, 0]) < np.abs(flat.intr[pin, 0] - truth["intr"][pin, 0]))       # the cameras moved towards the truth
+    # a camera held constant inside a refining adjustment keeps its parameters exactly (and the others still move)
+    f2 = flat.copy(); f2.intr_const = f2.intr_const.copy(); f2.intr_const[0] = 1
+    g2, c2, sg2, so2 = _both(orc, f2, 6)
+    _assert_parity(g2, c2, sg2, so2, param_rel=4e-6)
+    assert np.array_equal(g2.intr[0], flat.intr[0]) and not np.allclose(g2.intr[1, :4], flat.intr[1, :4])
+
+
+def test_refine_camera_params_with_rotation_constraints(mm, orc):
+    """refine_camera_params together with constrain_rotation (both allowed by bundle_adjustment.cc:535-540)"""
+    from scipy.spatial.transform import Rotation
+    flat, _ = synthetic.make_ba_problem(outlier_frac=0.0, models=[1, 2], refine_camera_params=True, **synthetic.BA_CONFIGS["small"])
+    flat.intr[:, :2] *= 1.003
+    rng = np.random.default_rng(5)
+    r0 = np.stack([(Rotation.from_rotvec(p[:3]).inv() * Rotation.from_rotvec(rng.normal(0, 0.01, 3))).as_rotvec() for p in flat.poses])
+    w = np.full(flat.n_img, 30.0); w[:2] = 0.0
+    flat.set_rotation_constraints(r0, w)
+    g, c, sg, so = _both(orc, flat, 8)
+    _assert_parity(g, c, sg, so, param_rel=4e-6)
+    assert sg["num_residuals"] == 2 * flat.n_obs + flat.n_img - 2
 
 
 def test_device_reproduces_committed_golden_traces(mm):

@@ -13,6 +13,7 @@ from mavmap_b200.parallel import make_allreduce_callback
 
 CFG = dict(synthetic.BA_CONFIGS)
 CFG["mid"] = dict(n_img=120, n_obs_target=120000, track_len=4, seed=777)
+CFG["midrefine"] = dict(n_img=120, n_obs_target=120000, track_len=4, seed=779, models=[1, 2], refine_camera_params=True)      # refined intrinsics of a two-camera rig, sharded
 
 
 def main():
@@ -39,7 +40,7 @@ def main():
         f1, d1, ms_1, n_1 = run(False)
         rel = lambda a, b: float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1.0)))
         cost_rel = max(abs(a - b) / b for a, b in zip(ds["trace_cost"], d1["trace_cost"]))
-        good = ds["trace_accepted"] == d1["trace_accepted"] and cost_rel < 1e-9 and rel(fs.poses, f1.poses) < 1e-6 and rel(fs.pts, f1.pts) < 1e-5
+        good = ds["trace_accepted"] == d1["trace_accepted"] and cost_rel < 1e-9 and rel(fs.poses, f1.poses) < 1e-6 and rel(fs.pts, f1.pts) < 1e-5 and rel(fs.intr, f1.intr) < 1e-6
         t = torch.tensor([ms_s], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ok = ok and good
         print("[rank %d] %s: %d imgs %d obs | sharded x%d: %d it in %.1f ms (%.1f it/s, pcg %s) | single: %.1f ms (%.1f it/s) | cost rel %.1e poses %.1e pts %.1e accepted-equal %s -> %s" % (
