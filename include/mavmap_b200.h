@@ -93,6 +93,10 @@ int mm_triangulate_two_view(const double* P1, const double* P2, int64_t n,
                             double* reproj1, double* reproj2,
                             double* depth1, double* depth2, double* angle);
 
+/* calc_tri_angles (triangulation.cc:101-147) for GIVEN 3-D points X [n*3]: the angle between the two rays of each point
+ * (law of cosines with the camera centres of P1 and P2, NaN -> 0).  angle [n].  Host buffers. */
+int mm_tri_angles(const double* P1, const double* P2, int64_t n, const double* X, double* angle);
+
 /* calc_reproj_errors (projection.cc:107-130) and calc_depth (projection.cc:133-149) for given 3-D points
  * (the continued-track filter of sequential_mapper.cc:767-777).  x2d [n*2] normalised coordinates, X [n*3];
  * err and depth are [n]; either output may be NULL.  Host buffers. */

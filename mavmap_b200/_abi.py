@@ -117,6 +117,7 @@ PROTOTYPES = {
     "mm_triangulate_two_view": (C.c_int, [p_f64, p_f64, C.c_int64, p_f64, p_f64, p_f64,
                                           p_f64, p_f64, p_f64, p_f64, p_f64]),
     "mm_reproj_errors": (C.c_int, [p_f64, C.c_int64, p_f64, p_f64, p_f64, p_f64]),
+    "mm_tri_angles": (C.c_int, [p_f64, p_f64, C.c_int64, p_f64, p_f64]),
     "mm_match_options_default": (None, [C.POINTER(MatchOptions)]),
     "mm_match_pair": (C.c_int, [p_f32, C.c_int32, p_f32, C.c_int32, C.c_int32, p_f32, p_f32,
                                 C.POINTER(MatchOptions), p_i32, p_i32, p_f32, p_i32]),

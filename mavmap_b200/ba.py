@@ -313,6 +313,11 @@ def bundle_adjustment(feature_manager, free_image_ids, fixed_image_ids, fixed_x_
     """Drop-in for bundle_adjustment() (bundle_adjustment.cc:449-613); returns
     sqrt(final_cost / num_residuals) (.cc:610).  Raises ValueError where the reference
     throws std::invalid_argument (.cc:462-471)."""
+    # the two argument checks come first (.cc:459-471): a ValueError must leave the caller's feature manager untouched
+    if len(fixed_image_ids) * 6 + len(fixed_x_image_ids) + len(set(gcp_ids)) * 3 < 7:
+        raise ValueError(_DATUM_MSG)
+    if options.min_track_len < 2:
+        raise ValueError(_TRACK_MSG)
     if options.constrain_rotation:
         _rotate_into_constraint_frame(feature_manager, fixed_image_ids, rotation_constraints)
     flat, image_ids, camera_ids, point3D_ids = flatten(

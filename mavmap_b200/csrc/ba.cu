@@ -216,7 +216,9 @@ struct Timer {
 int validate_problem(const mm_ba_problem* P) {
   if (!P || P->n_img < 0 || P->n_cam < 0 || P->n_pt < 0 || P->n_obs < 0) { set_error("invalid problem sizes"); return MM_ERR_INVALID_ARG; }
   if (P->n_obs >= (int64_t)1 << 31) { set_error("n_obs >= 2^31 not supported"); return MM_ERR_UNSUPPORTED; }
-  if (P->n_obs > 0 && (!P->poses || !P->pose_const || !P->img_cam || !P->intr || !P->cam_model || !P->intr_const || !P->pts || !P->pt_const || !P->obs_xy || !P->obs_img || !P->obs_pt)) { set_error("null array in problem"); return MM_ERR_INVALID_ARG; }
+  // every array is checked against its own count: an empty-observation problem with images / cameras / points still dereferences them
+  if ((P->n_img > 0 && (!P->poses || !P->pose_const || !P->img_cam)) || (P->n_cam > 0 && (!P->intr || !P->cam_model || !P->intr_const)) ||
+      (P->n_pt > 0 && (!P->pts || !P->pt_const)) || (P->n_obs > 0 && (!P->obs_xy || !P->obs_img || !P->obs_pt))) { set_error("null array in problem"); return MM_ERR_INVALID_ARG; }
   for (int c = 0; c < P->n_cam; ++c) if (model_num_params(P->cam_model[c]) < 0) { set_error("unknown camera model code %d", P->cam_model[c]); return MM_ERR_INVALID_ARG; }
   for (int i = 0; i < P->n_img; ++i) if (P->img_cam[i] < 0 || P->img_cam[i] >= P->n_cam) { set_error("img_cam out of range"); return MM_ERR_INVALID_ARG; }
   for (int64_t o = 0; o < P->n_obs; ++o)
@@ -764,8 +766,8 @@ int launch_pcg(mm_ba_session* s) {
     // local-BA sized system: dense Cholesky in one CTA (ba_coarse.cuh); reported as 0 linear iterations
     const int n = 6 * s->n_img;
     const size_t smem = sizeof(double) * ((size_t)n * (n + 1) + n);
-    static bool configured = false;
-    if (!configured) { MM_CUDA(cudaFuncSetAttribute(k_dense_chol_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ((size_t)6 * DENSE_MAX_IMG * (6 * DENSE_MAX_IMG + 1) + 6 * DENSE_MAX_IMG)))); configured = true; }
+    // (the attribute belongs to the current device / context: set on every call, it is cheap)
+    MM_CUDA(cudaFuncSetAttribute(k_dense_chol_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ((size_t)6 * DENSE_MAX_IMG * (6 * DENSE_MAX_IMG + 1) + 6 * DENSE_MAX_IMG))));
     k_dense_chol_solve<<<1, 512, smem, st>>>(s->n_img, s->nblk, s->blk_a.p, s->blk_b.p, s->S.p, s->rhs.p, s->vx.p, s->fail.p); MM_LAUNCH_CHECK();
     return pcg_broadcast(s);
   }

@@ -122,7 +122,12 @@ __global__ void __launch_bounds__(256, 1) k_pose_refine(int n, const double2* __
     else if (sm.gmax <= sm.abs_gtol) { S->termination = MM_TERM_GRADIENT_TOLERANCE; sm.done = 1; }
   }
   __syncthreads();
-  while (!sm.done) {
+  // The loop flags live in shared memory and are written by thread 0 only.  Every thread copies a flag into a register right
+  // after the barrier that publishes it, and a second barrier keeps thread 0 from rewriting it before all have read it.
+  for (;;) {
+    const int done_top = sm.done;
+    __syncthreads();
+    if (done_top) break;
     // ---- step: (S A S + D^2) y = S g ; candidate x2 = x - S y
     if (threadIdx.x == 0) {
       if (sm.iter >= O.max_num_iterations) { S->termination = MM_TERM_NO_CONVERGENCE; sm.done = 1; }
@@ -158,7 +163,9 @@ __global__ void __launch_bounds__(256, 1) k_pose_refine(int n, const double2* __
       }
     }
     __syncthreads();
-    if (sm.done) break;
+    const int done_step = sm.done;
+    __syncthreads();
+    if (done_step) break;
     pose_pass<false>(n, uv, X, model, intr, sm.x2, &sm, L, wred);
     // ---- accept / reject (thread 0), then re-linearize if accepted
     if (threadIdx.x == 0) {
@@ -191,7 +198,9 @@ __global__ void __launch_bounds__(256, 1) k_pose_refine(int n, const double2* __
       }
     }
     __syncthreads();
-    if (sm.want) {                                        // (uniform: shared flag)
+    const int want = sm.want;                             // (uniform: every thread reads the same published value)
+    __syncthreads();
+    if (want) {
       pose_pass<true>(n, uv, X, model, intr, sm.x, &sm, L, wred);
       if (threadIdx.x == 0) {
         pose_take_linearization(&sm);

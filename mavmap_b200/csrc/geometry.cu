@@ -155,6 +155,18 @@ __global__ void k_reproj(Proj p, int64_t n, const double* __restrict__ x, const 
   }
 }
 
+// calc_tri_angles (triangulation.cc:101-147) for GIVEN 3-D points: law of cosines in the triangle (centre 1, centre 2, point)
+__global__ void k_tri_angles(double c1x, double c1y, double c1z, double c2x, double c2y, double c2z, double baseline2, int64_t n,
+                             const double* __restrict__ X, double* __restrict__ ang) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double x = X[3 * i], y = X[3 * i + 1], z = X[3 * i + 2];
+    const double r1 = sqrt((x - c1x) * (x - c1x) + (y - c1y) * (y - c1y) + (z - c1z) * (z - c1z));
+    const double r2 = sqrt((x - c2x) * (x - c2x) + (y - c2y) * (y - c2y) + (z - c2z) * (z - c2z));
+    const double a = acos((r1 * r1 + r2 * r2 - baseline2) / (2.0 * r1 * r2));
+    ang[i] = isnan(a) ? 0.0 : a;                         // triangulation.cc:134-140
+  }
+}
+
 static void camera_center(const double* P, double* C) {       // projection.cc:82-88 translation column
   const double a = P[0], b = P[1], c = P[2], d = P[4], e = P[5], f = P[6], g = P[8], h = P[9], i = P[10];
   const double A = e * i - f * h, B = -(d * i - f * g), Cc = d * h - e * g;
@@ -327,6 +339,21 @@ int mm_triangulate_two_view(const double* P1, const double* P2, int64_t n, const
   MM_LAUNCH_CHECK();
   MM_CUDA(cudaMemcpy(X, dX, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost));
   for (int k = 0; k < 5; ++k) if (host_out[k]) MM_CUDA(cudaMemcpy(host_out[k], dev_out[k], sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+  return MM_OK;
+}
+
+int mm_tri_angles(const double* P1, const double* P2, int64_t n, const double* X, double* angle) {
+  if (n < 0 || !P1 || !P2 || (n > 0 && (!X || !angle))) { set_error("invalid argument"); return MM_ERR_INVALID_ARG; }
+  int rc = ensure_device(); if (rc != MM_OK) return rc;
+  if (n == 0) return MM_OK;
+  double C1[3], C2[3];
+  camera_center(P1, C1); camera_center(P2, C2);
+  const double bl = sqrt((C1[0] - C2[0]) * (C1[0] - C2[0]) + (C1[1] - C2[1]) * (C1[1] - C2[1]) + (C1[2] - C2[2]) * (C1[2] - C2[2]));
+  DevBuf<double> buf; MM_CUDA(buf.alloc((size_t)n * 4));
+  MM_CUDA(cudaMemcpy(buf.p, X, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice));
+  k_tri_angles<<<grid_for(n, 128), 128>>>(C1[0], C1[1], C1[2], C2[0], C2[1], C2[2], bl * bl, n, buf.p, buf.p + 3 * n);
+  MM_LAUNCH_CHECK();
+  MM_CUDA(cudaMemcpy(angle, buf.p + 3 * n, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
   return MM_OK;
 }
 

@@ -173,8 +173,7 @@ int knn2_simt(cudaStream_t st, const float* Q, int nq, const float* T, int nt, i
   int chunk = std::max(TT, ((nt + n_chunks - 1) / n_chunks + TT - 1) / TT * TT);
   n_chunks = std::max(1, (nt + chunk - 1) / chunk);
   const size_t smem = sizeof(double) * ((size_t)K * QT + (size_t)TT * K);
-  static size_t configured = 0;
-  if (smem > configured) { MM_CUDA(cudaFuncSetAttribute(k_knn2_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = smem; }
+  MM_CUDA(cudaFuncSetAttribute(k_knn2_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      // per device / context: set on every call
   k_knn2_simt<<<dim3(row_blocks, n_chunks), QT, smem, st>>>(Q, nq, T, nt, K, xyq, xyt, max_distance * max_distance, use_mask, chunk, part_scratch);
   MM_LAUNCH_CHECK();
   k_knn2_merge<<<(nq + 127) / 128, 128, 0, st>>>(nq, n_chunks, part_scratch, out);

@@ -8,14 +8,17 @@
 //               A'[i] = [ a_i            | 1      1      h1  h2 | 0.. ]   h1+h2 = |a_i|^2 + 1 (tf32 split)
 //               B'[j] = [ -2 b_j         | g1     g2     1   1  | 0.. ]   g1+g2 = |b_j|^2     (tf32 split)
 //             so that  A'[i] . B'[j] = 1 + |a_i - b_j|^2  up to the TF32 rounding of the cross term.
-//   k_match_tc  persistent, warp-specialised: warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle,
-//             4-stage mbarrier ring), warp 1 = tcgen05.mma issuer (kind::tf32, M=128, N=256, accumulators
-//             double-buffered in all 512 TMEM columns), warps 2-5 = epilogue: tcgen05.ld the 128 x 256 tile,
-//             one thread per query row keeps the 4 smallest approximate distances of its row across all
-//             column tiles (the epilogue of tile t overlaps the MMAs of tile t+1).
-//   k_rerank  exact fp64-accumulated distances (same arithmetic as match.cu / the oracle) of the 4
-//             candidates -> exact top-2, plus a rigorous test that no other column can enter the top-2
-//             given the TF32 error bound; rows that fail the test are re-scanned exactly (k_rescan).
+//   k_match_tc  persistent, warp-specialised: warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle; the 128-row A tile
+//             of a work item stays resident, B tiles run through a 3-stage mbarrier ring), warp 1 = tcgen05.mma issuer
+//             (kind::tf32, M=128, N=256, accumulators double-buffered in all 512 TMEM columns), warps 2-9 = epilogue (two
+//             per TMEM lane quarter, each half of the columns, tcgen05.ld.32x32b.x32, one thread per query row; the
+//             epilogue of tile t overlaps the MMAs of tile t+1).  Two passes:
+//               <0> "bound":   a quarter of the column tiles; per row the minima of eight disjoint column groups (3-input
+//                              minimum instructions); the second smallest of the eight bounds the row's true second-nearest value
+//               <1> "collect": all tiles; every column with value <= bound + 2 eps goes to the row's hit list (32-bit hit mask
+//                              per 32-column chunk), eps = the rigorous TF32 error bound 2^-9 |a||b|
+//   k_rerank  exact fp64-accumulated distances (same arithmetic as match.cu / the oracle) of the listed columns -> exact
+//             top-2 by (distance, index); a row whose list overflowed is re-scanned exactly (k_rescan).
 // The result is bit-identical to the exact SIMT path; the tensor cores only prune.
 #include <cuda.h>
 #include <float.h>
@@ -548,12 +551,8 @@ int match_tc_pairs(const float* desc, const float* xy, int K, const int64_t* off
   if (!items.empty()) {
     MM_CUDA(cudaMemcpyAsync(g_scr.items.p, items.data(), sizeof(TcItem) * items.size(), cudaMemcpyHostToDevice, st));
     const size_t smem = (size_t)TC_MAX_KB * TC_A_BYTES + (size_t)TC_STAGES * TC_B_BYTES + 1024 + 256 + (size_t)TC_M * 16;
-    static bool configured = false;
-    if (!configured) {
-      MM_CUDA(cudaFuncSetAttribute(k_match_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      MM_CUDA(cudaFuncSetAttribute(k_match_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = true;
-    }
+    MM_CUDA(cudaFuncSetAttribute(k_match_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      // per device / context: set on every call
+    MM_CUDA(cudaFuncSetAttribute(k_match_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = std::min((int)items.size(), num_sms());
     const int num_kb = P->Kp / TC_KB;
     k_match_tc<0><<<grid, TC_THREADS, smem, st>>>(P->mapA, P->mapB, g_scr.items.p, (int)items.size(), num_kb, P->norms.p, g_scr.bound.p, g_scr.hits.p, g_scr.hcnt.p);

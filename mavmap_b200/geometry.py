@@ -75,8 +75,14 @@ def triangulate_points(proj_matrix1, proj_matrix2, points1, points2):
     return triangulate_two_view(proj_matrix1, proj_matrix2, points1, points2)["X"]
 
 
-def calc_tri_angles(proj_matrix1, proj_matrix2, points1, points2):
-    return triangulate_two_view(proj_matrix1, proj_matrix2, points1, points2)["angle"]
+def calc_tri_angles(proj_matrix1, proj_matrix2, points3D):
+    """calc_tri_angles (triangulation.cc:101-147): angle between the two rays of each GIVEN 3-D point."""
+    P1 = np.ascontiguousarray(proj_matrix1, dtype=np.float64).reshape(3, 4)
+    P2 = np.ascontiguousarray(proj_matrix2, dtype=np.float64).reshape(3, 4)
+    X = np.ascontiguousarray(points3D, dtype=np.float64).reshape(-1, 3)
+    ang = np.empty(len(X))
+    check(lib().mm_tri_angles(as_ptr(P1, p_f64), as_ptr(P2, p_f64), len(X), as_ptr(X, p_f64), as_ptr(ang, p_f64)))
+    return ang
 
 
 def calc_reproj_errors(points2D, points3D, proj_matrix):

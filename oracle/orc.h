@@ -50,6 +50,8 @@ int orc_triangulate_two_view(const double* P1, const double* P2, int64_t n,
                              double* reproj1, double* reproj2,
                              double* depth1, double* depth2, double* angle);
 
+int orc_tri_angles(const double* P1, const double* P2, int64_t n, const double* X, double* angle);
+
 /* feature.cc:52-133 with exact (double-accumulated, float-rounded) L2 distances */
 int orc_match_pair(const float* d1, int32_t n1, const float* d2, int32_t n2, int32_t k,
                    const float* xy1, const float* xy2, const mm_match_options* opt,

@@ -126,6 +126,16 @@ def triangulate_two_view(P1, P2, x1, x2):
     return out
 
 
+def tri_angles(P1, P2, X):
+    """triangulation.cc:101-147 for given points"""
+    P1 = np.ascontiguousarray(P1, dtype=np.float64).reshape(3, 4); P2 = np.ascontiguousarray(P2, dtype=np.float64).reshape(3, 4)
+    X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1, 3)
+    ang = np.empty(len(X))
+    L = lib(); L.orc_tri_angles.restype = C.c_int; L.orc_tri_angles.argtypes = [p_f64, p_f64, C.c_int64, p_f64, p_f64]
+    _chk(L.orc_tri_angles(as_ptr(P1, p_f64), as_ptr(P2, p_f64), len(X), as_ptr(X, p_f64), as_ptr(ang, p_f64)))
+    return ang
+
+
 # ---- matching --------------------------------------------------------------------
 def match_options(ratio_test=True, max_ratio=0.6, max_distance=-1.0, impl=0):
     o = MatchOptions()

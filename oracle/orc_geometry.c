@@ -109,6 +109,23 @@ int orc_triangulate_two_view(const double* P1, const double* P2, int64_t n,
 }
 
 
+/* calc_tri_angles, triangulation.cc:101-147, for given 3-D points */
+int orc_tri_angles(const double* P1, const double* P2, int64_t n, const double* X, double* angle) {
+  if (n < 0 || !P1 || !P2 || (n > 0 && (!X || !angle))) return MM_ERR_INVALID_ARG;
+  double C1[3], C2[3];
+  camera_center(P1, C1); camera_center(P2, C2);                 /* :106-113 translation column of the inverted projection matrices */
+  const double bl = sqrt((C1[0]-C2[0])*(C1[0]-C2[0]) + (C1[1]-C2[1])*(C1[1]-C2[1]) + (C1[2]-C2[2])*(C1[2]-C2[2]));   /* :116 */
+  const double baseline2 = bl * bl;
+  for (int64_t i = 0; i < n; ++i) {
+    const double* Xi = X + 3*i;
+    const double r1 = sqrt((Xi[0]-C1[0])*(Xi[0]-C1[0]) + (Xi[1]-C1[1])*(Xi[1]-C1[1]) + (Xi[2]-C1[2])*(Xi[2]-C1[2]));      /* :127-128 */
+    const double r2 = sqrt((Xi[0]-C2[0])*(Xi[0]-C2[0]) + (Xi[1]-C2[1])*(Xi[1]-C2[1]) + (Xi[2]-C2[2])*(Xi[2]-C2[2]));
+    const double a = acos((r1*r1 + r2*r2 - baseline2) / (2.0 * r1 * r2));                                          /* :132-133 */
+    angle[i] = isnan(a) ? 0.0 : a;                                                                                  /* :134-140 */
+  }
+  return MM_OK;
+}
+
 /* ---- RANSAC hypothesis scoring: util/estimation.cc:83-126 with the residuals of p3p.cc:172-199 (kind 0),
  * projective_transform.cc:48-74 (kind 1) and essential_matrix.cc:131-162 (kind 2).  Row-major models. */
 static double ransac_residual(int kind, const double* m, const double* x, const double* y, int64_t i) {

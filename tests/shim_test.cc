@@ -16,6 +16,10 @@ std::vector<Eigen::Vector3d> triangulate_points(const Eigen::Matrix<double, 3, 4
                                                 const std::vector<Eigen::Vector2d>&, const std::vector<Eigen::Vector2d>&);
 std::vector<double> calc_reproj_errors(const std::vector<Eigen::Vector2d>&, const std::vector<Eigen::Vector3d>&, const Eigen::Matrix<double, 3, 4>&);
 double calc_depth(const Eigen::Matrix<double, 3, 4>&, const Eigen::Vector3d&);
+Eigen::Vector3d triangulate_point(const Eigen::Matrix<double, 3, 4>&, const Eigen::Matrix<double, 3, 4>&, const Eigen::Vector2d&, const Eigen::Vector2d&);
+Eigen::Matrix<double, Eigen::Dynamic, 3> triangulate_points(const Eigen::Matrix<double, 3, 4>&, const Eigen::Matrix<double, 3, 4>&,
+                                                            const Eigen::Matrix<double, Eigen::Dynamic, 2>&, const Eigen::Matrix<double, Eigen::Dynamic, 2>&);
+std::vector<double> calc_tri_angles(const Eigen::Matrix<double, 3, 4>&, const Eigen::Matrix<double, 3, 4>&, const std::vector<Eigen::Vector3d>&);
 
 static int fails = 0;
 #define CHECK(cond, what) do { const bool ok_ = (cond); std::printf("%s %s\n", ok_ ? "ok  " : "FAIL", what); if (!ok_) ++fails; } while (0)
@@ -108,6 +112,31 @@ int main() {
   const std::vector<double> re = calc_reproj_errors(x2, T, P2);
   double wre = 0; for (double e : re) wre = std::fmax(wre, e);
   CHECK(wre < 1e-10 && std::fabs(calc_depth(P2, T[0]) - X[0](2)) < 1e-9, "calc_reproj_errors / calc_depth");
+  {
+    // single-point triangulation runs on the host (mapper.cc:499), same algorithm as the batched kernel
+    double w1 = 0; for (int p = 0; p < n_pt; ++p) { const Eigen::Vector3d t1 = triangulate_point(P1, P2, x1[p], x2[p]); for (int c = 0; c < 3; ++c) w1 = std::fmax(w1, std::fabs(t1(c) - T[p](c))); }
+    CHECK(w1 < 1e-12, "triangulate_point (host) agrees with the batched kernel");
+    Eigen::Matrix<double, Eigen::Dynamic, 2> m1(n_pt, 2), m2(n_pt, 2);
+    for (int p = 0; p < n_pt; ++p) { m1(p, 0) = x1[p](0); m1(p, 1) = x1[p](1); m2(p, 0) = x2[p](0); m2(p, 1) = x2[p](1); }
+    const Eigen::Matrix<double, Eigen::Dynamic, 3> TM = triangulate_points(P1, P2, m1, m2);
+    double w2 = 0; for (int p = 0; p < n_pt; ++p) for (int c = 0; c < 3; ++c) w2 = std::fmax(w2, std::fabs(TM(p, c) - T[p](c)));
+    CHECK(TM.rows() == (size_t)n_pt && w2 == 0.0, "triangulate_points, Nx2 matrix overload (triangulation.cc:77-98)");
+    // calc_tri_angles on GIVEN points (triangulation.cc:101-147): camera centres (0,0,0) and (1,0,0); incl. a point on the
+    // principal plane of view 1 (z = 0), which has no projection but a perfectly good ray angle, and a far point
+    std::vector<Eigen::Vector3d> G = { Eigen::Vector3d(0.5, 0.0, 10.0), Eigen::Vector3d(0.5, 2.0, 0.0), Eigen::Vector3d(0.5, 0.0, 1e9), Eigen::Vector3d(3.0, -1.0, 4.0) };
+    const std::vector<double> ang = calc_tri_angles(P1, P2, G);
+    bool aok = ang.size() == G.size();
+    for (size_t i = 0; i < G.size() && aok; ++i) {
+      const double ax = G[i](0), ay = G[i](1), az = G[i](2), bx = ax - 1.0;
+      const double ra = std::sqrt(ax * ax + ay * ay + az * az), rb = std::sqrt(bx * bx + ay * ay + az * az);
+      double ref = std::acos((ra * ra + rb * rb - 1.0) / (2 * ra * rb)); if (std::isnan(ref)) ref = 0.0;
+      aok = std::fabs(ang[i] - ref) < 1e-12;
+    }
+    CHECK(aok && ang[1] > 0.4, "calc_tri_angles uses the given points (valid on the principal plane, ~0 at infinity)");
+    Eigen::Matrix<double, 3, 4> Pd; Pd(0, 0) = 0.6; Pd(0, 2) = 0.8; Pd(1, 1) = 1; Pd(2, 0) = -0.8; Pd(2, 2) = 0.6; Pd(2, 3) = 2.0;
+    const Eigen::Vector3d q(1.0, 2.0, 3.0);
+    CHECK(std::fabs(calc_depth(Pd, q) - (-0.8 * 1.0 + 0.6 * 3.0 + 2.0) * std::sqrt(0.8 * 0.8 + 0.6 * 0.6)) < 1e-15, "calc_depth: closed form of projection.cc:133-149 (host, no device round trip)");
+  }
   // ---- a larger feature manager: what the marshalling costs next to the device call (printed with MM_SHIM_TIMING=1)
   {
     FeatureManager big;

@@ -79,3 +79,29 @@ def test_ransac_score_bit_exact_against_oracle(mm, orc, kind):
     e = ransac_score(kind, models[:0], x, y, thr)
     assert e["best"] == -1
 
+
+
+def test_tri_angles_of_given_points_vs_oracle(mm, orc):
+    """calc_tri_angles (triangulation.cc:101-147) takes the 3-D points as given: device vs oracle vs the closed form, including
+    points on a camera's principal plane and (numerically) at infinity, and a non-rotation projection matrix"""
+    rng = np.random.default_rng(21)
+    from mavmap_b200.synthetic import _rodrigues
+    R2 = _rodrigues(np.array([0.1, -0.2, 0.05]))[0]
+    P1 = np.hstack([np.eye(3), np.zeros((3, 1))]); P2 = np.hstack([R2, np.array([[-1.5], [0.2], [0.1]])])
+    X = rng.uniform([-3, -3, 2], [3, 3, 30], (500, 3))
+    X[0] = [0.3, -0.4, 0.0]; X[1] = [1e8, 2e8, 5e9]; X[2] = -R2.T @ P2[:, 3]            # principal plane, far away, ON the second centre
+    a = mm.calc_tri_angles(P1, P2, X)
+    # acos amplifies the last bit of its argument near +-1 (rays almost parallel): sqrt(2 ulp) ~ 2e-8 there, 1e-15 elsewhere
+    o = orc.tri_angles(P1, P2, X)
+    np.testing.assert_allclose(a, o, atol=5e-8); np.testing.assert_allclose(a[o > 1e-3], o[o > 1e-3], rtol=1e-12)
+    c1 = np.zeros(3); c2 = -R2.T @ P2[:, 3]
+    r1 = np.linalg.norm(X - c1, axis=1); r2 = np.linalg.norm(X - c2, axis=1)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        ref = np.arccos((r1 ** 2 + r2 ** 2 - np.sum((c1 - c2) ** 2)) / (2 * r1 * r2))
+    ref[np.isnan(ref)] = 0.0
+    np.testing.assert_allclose(a[3:], ref[3:], atol=1e-9)
+    assert a[0] > 0.1 and a[1] < 1e-6 and a[2] < 1e-6
+    # consistent with the fused kernel on points that it triangulated itself
+    x1 = X[3:, :2] / X[3:, 2:]; Xc = X[3:] @ R2.T + P2[:, 3]; x2 = Xc[:, :2] / Xc[:, 2:]
+    tri = mm.triangulate_two_view(P1, P2, x1, x2)
+    np.testing.assert_allclose(mm.calc_tri_angles(P1, P2, tri["X"]), tri["angle"], atol=1e-9)
