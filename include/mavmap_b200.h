@@ -247,6 +247,10 @@ typedef struct mm_ba_options {
   int32_t pcg_max_iterations;   /* 2000 */
   int32_t print_progress;       /* 0 */
   int32_t pcg_preconditioner;   /* MM_PRECOND_AUTO */
+  double  tile_cholesky_tolerance; /* 1e-8: with the exact tile factorisation as preconditioner the first PCG iteration IS
+                                   the direct solve the reference performs (SPARSE_SCHUR, bundle_adjustment.cc:555); further
+                                   iterations refine it only while ||S y - b|| / ||b|| exceeds this (pcg_tolerance applies to
+                                   the iterative preconditioners) */
 } mm_ba_options;
 
 void mm_ba_options_default(mm_ba_options* o);

@@ -63,7 +63,7 @@ class BAOptions(C.Structure):
                 ("max_num_consecutive_invalid_steps", C.c_int32),
                 ("linear_solver", C.c_int32), ("pcg_tolerance", C.c_double),
                 ("pcg_max_iterations", C.c_int32), ("print_progress", C.c_int32),
-                ("pcg_preconditioner", C.c_int32)]
+                ("pcg_preconditioner", C.c_int32), ("tile_cholesky_tolerance", C.c_double)]
 
 
 class BASummary(C.Structure):

@@ -66,6 +66,8 @@ def default_c_options():
     o.pcg_tolerance = 1e-13
     o.pcg_max_iterations = 2000
     o.print_progress = 0
+    o.pcg_preconditioner = _abi.MM_PRECOND_AUTO
+    o.tile_cholesky_tolerance = 1e-8
     return o
 
 

@@ -729,7 +729,8 @@ int launch_dpcg(mm_ba_session* s) {
   MM_CUDA(cudaMemcpyAsync(s->dv_b.p, s->rhs.p, sizeof(double) * n6, cudaMemcpyDeviceToDevice, st));
   if (s->ncb) MM_CUDA(cudaMemcpyAsync(s->dv_b.p + n6, s->intr_acc.p + 81 * (size_t)s->ncb * s->ncb, sizeof(double) * 9 * (size_t)s->ncb, cudaMemcpyDeviceToDevice, st));
   DpcgVec V; V.n = s->n_unk; V.x = s->vx.p; V.r = s->dv_r.p; V.z = s->dv_z.p; V.p = s->dv_p.p; V.Ap = s->dv_Ap.p; V.b = s->dv_b.p; V.sc = s->pcg_sc.p; V.ic = s->pcg_ic.p;
-  V.tol2 = s->opt.pcg_tolerance * s->opt.pcg_tolerance; V.max_iter = s->opt.pcg_max_iterations;
+  const double tol = s->opt.tile_cholesky_tolerance > 0.0 ? s->opt.tile_cholesky_tolerance : s->opt.pcg_tolerance;      // (0: refine down to pcg_tolerance)
+  V.tol2 = tol * tol; V.max_iter = s->opt.pcg_max_iterations;
   k_dpcg_init<<<1, 1024, 0, st>>>(V); MM_LAUNCH_CHECK();
   int done_it = 0;
   while (done_it < V.max_iter) {
@@ -969,7 +970,7 @@ void mm_ba_options_default(mm_ba_options* o) {
   o->min_trust_region_radius = 1e-32; o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32;
   o->jacobi_scaling = 1; o->max_num_consecutive_invalid_steps = 10;
   o->linear_solver = MM_SOLVER_PCG; o->pcg_tolerance = 1e-13; o->pcg_max_iterations = 2000; o->print_progress = 0;
-  o->pcg_preconditioner = MM_PRECOND_AUTO;
+  o->pcg_preconditioner = MM_PRECOND_AUTO; o->tile_cholesky_tolerance = 1e-8;
 }
 
 void mm_ba_session_destroy(mm_ba_session* s) {

@@ -32,7 +32,7 @@ def test_struct_layouts_match_header_sizes():
     # numbers printed by gcc (sizeof / offsetof on include/mavmap_b200.h)
     assert C.sizeof(_abi.MatchOptions) == 32
     assert C.sizeof(_abi.BAProblem) == 136 and _abi.BAProblem.rot_prior.offset == 120
-    assert _abi.BAOptions.pcg_tolerance.offset == 112 and C.sizeof(_abi.BAOptions) == 136 and _abi.BAOptions.pcg_preconditioner.offset == 128
+    assert _abi.BAOptions.pcg_tolerance.offset == 112 and C.sizeof(_abi.BAOptions) == 144 and _abi.BAOptions.pcg_preconditioner.offset == 128 and _abi.BAOptions.tile_cholesky_tolerance.offset == 136
     assert _abi.BASummary.trace_cost.offset == 48 and C.sizeof(_abi.BASummary) == 16480
 
 
