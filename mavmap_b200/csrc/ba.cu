@@ -519,17 +519,32 @@ LossParams loss_of(const mm_ba_options& o) {
 }
 LMDiag lm_of(const mm_ba_session* s) { LMDiag d; d.radius = s->radius; d.min_diag = s->opt.min_lm_diagonal; d.max_diag = s->opt.max_lm_diagonal; return d; }
 
-// K1 at the current iterate: records + cost -> red[0]
-int launch_linearize(mm_ba_session* s) {
+// K1 at the current iterate: records + cost -> red[0].  reuse_candidate_cost: the iterate is the candidate that the cost-only
+// pass has just evaluated (accepted step), so its cost (and that of the rotation constraints) is taken over instead of recomputed.
+template <bool WITH_COST>
+int launch_k1(mm_ba_session* s) {
   cudaStream_t st = s->stream;
-  k_pose_aux<<<blocks_for(s->n_img, 128), 128, 0, st>>>(s->n_img, s->poses.p, s->pose_mask.p, s->aux.p); MM_LAUNCH_CHECK();
   if (s->refine)
-    k_residual_jacobian<true, true><<<s->grid_obs, 256, K1_SMEM, st>>>(s->no_loc(), s->obs_xy.p + s->o_lo, s->obs_img.p + s->o_lo, s->obs_pt.p + s->o_lo, s->aux.p, s->pts.p, s->intr.p,
+    k_residual_jacobian<true, true, WITH_COST><<<s->grid_obs, 256, K1_SMEM, st>>>(s->no_loc(), s->obs_xy.p + s->o_lo, s->obs_img.p + s->o_lo, s->obs_pt.p + s->o_lo, s->aux.p, s->pts.p, s->intr.p,
         s->img_cam.p, s->cam_model.p, s->pose_mask.p, s->pt_mask.p, loss_of(s->opt), s->rec.p, s->part_cost.p, s->ji.p, s->intr_mask.p);
   else
-    k_residual_jacobian<true><<<s->grid_obs, 256, K1_SMEM, st>>>(s->no_loc(), s->obs_xy.p + s->o_lo, s->obs_img.p + s->o_lo, s->obs_pt.p + s->o_lo, s->aux.p, s->pts.p, s->intr.p,
+    k_residual_jacobian<true, false, WITH_COST><<<s->grid_obs, 256, K1_SMEM, st>>>(s->no_loc(), s->obs_xy.p + s->o_lo, s->obs_img.p + s->o_lo, s->obs_pt.p + s->o_lo, s->aux.p, s->pts.p, s->intr.p,
         s->img_cam.p, s->cam_model.p, s->pose_mask.p, s->pt_mask.p, loss_of(s->opt), s->rec.p, s->part_cost.p);
   MM_LAUNCH_CHECK();
+  return MM_OK;
+}
+int launch_linearize(mm_ba_session* s, bool reuse_candidate_cost = false) {
+  cudaStream_t st = s->stream;
+  k_pose_aux<<<blocks_for(s->n_img, 128), 128, 0, st>>>(s->n_img, s->poses.p, s->pose_mask.p, s->aux.p); MM_LAUNCH_CHECK();
+  if (reuse_candidate_cost) {
+    int rc = launch_k1<false>(s); if (rc) return rc;
+    MM_CUDA(cudaMemcpyAsync(s->loc.p + 0, s->loc.p + 1, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (s->n_prior) {      // the constraints' Jacobian at the new iterate; their cost was evaluated with the candidate
+      k_rot_prior<<<1, 256, 0, st>>>(s->n_img, s->poses.p, s->pose_mask.p, s->pr_rot0.p, s->pr_w.p, s->pr_r.p, s->pr_J.p, s->loc.p + 6); MM_LAUNCH_CHECK();
+    }
+    return MM_OK;
+  }
+  int rc = launch_k1<true>(s); if (rc) return rc;
   k_reduce_sum<<<1, 256, 0, st>>>(s->part_cost.p, s->grid_obs, s->loc.p + 0); MM_LAUNCH_CHECK();
   if (s->n_prior) { k_rot_prior<<<1, 256, 0, st>>>(s->n_img, s->poses.p, s->pose_mask.p, s->pr_rot0.p, s->pr_w.p, s->pr_r.p, s->pr_J.p, s->loc.p + 6); MM_LAUNCH_CHECK(); }
   return MM_OK;
@@ -928,7 +943,7 @@ int lm_iterate(mm_ba_session* s) {
     // x_min only after it)
     std::swap(s->poses.p, s->poses2.p); std::swap(s->pts.p, s->pts2.p); std::swap(s->aux.p, s->aux2.p); if (s->refine) std::swap(s->intr.p, s->intr2.p);
     cudaEventRecord(s->evs[3], s->stream);
-    if ((rc = launch_linearize(s))) return rc;
+    if ((rc = launch_linearize(s, !getenv("MM_K1_RECOMPUTE_COST")))) return rc;
     if ((rc = launch_xnorm(s))) return rc;
     cudaEventRecord(s->evs[4], s->stream);
     if ((rc = launch_schur(s))) return rc;
@@ -1019,8 +1034,10 @@ int mm_ba_session_create_sharded(const mm_ba_problem* P, const mm_ba_options* op
   A(s->loc, 8); A(s->stepbuf, 8);
   A(s->vx, 6 * n_img + 9 * n_cam); A(s->vr, 6 * n_img); A(s->vz, 6 * n_img); A(s->vp0, 6 * n_img); A(s->vp1, 6 * n_img); A(s->vAp, 6 * n_img);
   A(s->pcg_sc, 16); A(s->pcg_ic, 4); A(s->red, 8); A(s->fail, 1); A(s->img_cam, n_img); A(s->cam_model, n_cam); A(s->Minv, 36 * n_img);
-  MM_CUDA(cudaFuncSetAttribute((const void*)k_residual_jacobian<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM));
-  MM_CUDA(cudaFuncSetAttribute((const void*)k_residual_jacobian<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM));
+  MM_CUDA(cudaFuncSetAttribute((const void*)k_residual_jacobian<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM));
+  MM_CUDA(cudaFuncSetAttribute((const void*)k_residual_jacobian<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM));
+  MM_CUDA(cudaFuncSetAttribute((const void*)k_residual_jacobian<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM));
+  MM_CUDA(cudaFuncSetAttribute((const void*)k_residual_jacobian<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM));
   MM_CUDA(cudaFuncSetAttribute((const void*)k_residual_jacobian<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM_COST));
   s->grid_x = grid_stride(std::max<int64_t>(3 * (int64_t)P->n_pt, 1), 256);
   A(s->part_cost, (size_t)grid_stride(std::max<int64_t>(P->n_obs, 1), 256)); A(s->part_pt, 2 * (size_t)blocks_for(P->n_pt, 128)); A(s->part_cam, 2 * (size_t)blocks_for(6 * (int64_t)P->n_img, 128) + 2);
@@ -1294,7 +1311,7 @@ int mm_ba_session_time_kernel(mm_ba_session* s, int32_t which, int32_t reps, dou
   for (int r = -1; r < reps; ++r) {
     if (r == 0) MM_CUDA(cudaEventRecord(s->ev0, st));
     switch (which) {
-      case 0: k_residual_jacobian<true><<<s->grid_obs, 256, K1_SMEM, st>>>(s->no_loc(), s->obs_xy.p + s->o_lo, s->obs_img.p + s->o_lo, s->obs_pt.p + s->o_lo, s->aux.p, s->pts.p, s->intr.p,
+      case 0: k_residual_jacobian<true, false, false><<<s->grid_obs, 256, K1_SMEM, st>>>(s->no_loc(), s->obs_xy.p + s->o_lo, s->obs_img.p + s->o_lo, s->obs_pt.p + s->o_lo, s->aux.p, s->pts.p, s->intr.p,
                   s->img_cam.p, s->cam_model.p, s->pose_mask.p, s->pt_mask.p, loss_of(s->opt), s->rec.p, s->part_cost.p); count_launch(); break;
       case 1: rc = launch_schur(s, false); break;
       case 4: rc = launch_coarse_setup(s); break;

@@ -25,10 +25,11 @@ constexpr int AUX = 24;     // doubles per image: R(9) t(3) Jl(9) masks(2) pad =
 
 struct LossParams { int type; double b; double c; };   // Cauchy: b = a^2, c = 1/b
 
+template <bool WITH_COST = true>
 __device__ __forceinline__ void loss_eval(const LossParams& L, double s, double& rho0, double& sqrt_rho1) {
   if (L.type == MM_LOSS_CAUCHY) {
     const double sum = 1.0 + s * L.c, inv = 1.0 / sum;
-    rho0 = L.b * log(sum);
+    rho0 = WITH_COST ? L.b * log(sum) : 0.0;
     sqrt_rho1 = sqrt(fmax(inv, 2.2250738585072014e-308));
   } else { rho0 = s; sqrt_rho1 = 1.0; }
 }
@@ -61,11 +62,26 @@ __global__ void k_pose_aux(int n_img, const double* __restrict__ poses, const do
 constexpr int K1_SLOT = 26;                                   // doubles per image slot (208 B pitch: 16-byte aligned, bank-conflict-free)
 constexpr int K1_PITCH = 22;                                  // doubles per staged record
 constexpr int K1_WARP_DOUBLES = 32 * K1_SLOT;                 // >= 32 * K1_PITCH
-constexpr size_t K1_SMEM = sizeof(double) * 8 * K1_WARP_DOUBLES + sizeof(int) * 8 * 32 + sizeof(double) * 32;
+constexpr size_t K1_SMEM = sizeof(double) * 8 * K1_WARP_DOUBLES + sizeof(int) * 8 * 32 + sizeof(double) * 32 + sizeof(unsigned long long) * 8;
 constexpr size_t K1_SMEM_COST = K1_SMEM;
 
 
-template <bool WITH_J, bool WITH_JI = false>
+// K1 fetches the per-image records with 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP): the leader lane of every distinct
+// image of the warp issues one copy of the record into the image's shared-memory slot, completion on the warp's mbarrier.
+__device__ __forceinline__ void k1_bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void k1_mbar_wait(unsigned bar, unsigned parity) {
+  unsigned ok = 0;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+
+// WITH_COST = false: the Jacobian pass after an accepted step (the cost of the new iterate is the candidate cost that the
+// cost-only pass has just computed, so the logarithm of the Cauchy loss is not evaluated again).
+template <bool WITH_J, bool WITH_JI = false, bool WITH_COST = true>
 __global__ void __launch_bounds__(256, WITH_J ? 2 : 3) k_residual_jacobian(
     int64_t n_obs, const double2* __restrict__ obs_xy, const int* __restrict__ obs_img, const int* __restrict__ obs_pt,
     const double* __restrict__ aux, const double* __restrict__ pts, const double* __restrict__ intr,
@@ -78,6 +94,11 @@ __global__ void __launch_bounds__(256, WITH_J ? 2 : 3) k_residual_jacobian(
   double* wbuf = reinterpret_cast<double*>(k1_smem) + (size_t)wib * K1_WARP_DOUBLES;       // image slots, then staged records
   int* wimg = reinterpret_cast<int*>(k1_smem + sizeof(double) * 8 * K1_WARP_DOUBLES) + wib * 32;
   double* red = reinterpret_cast<double*>(k1_smem + sizeof(double) * 8 * K1_WARP_DOUBLES + sizeof(int) * 8 * 32);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(red + 32);
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(bars + wib);
+  unsigned phase = 0;
+  if (lane == 0) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory"); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncwarp();
   constexpr int NCH = WITH_J ? 12 : 6;                        // 16-byte chunks of the image record that this pass needs
   double cost = 0.0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -95,22 +116,18 @@ __global__ void __launch_bounds__(256, WITH_J ? 2 : 3) k_residual_jacobian(
     const int leader = __ffs(grp) - 1;
     const unsigned lead_mask = __ballot_sync(0xffffffffu, lane == leader);
     const int slot = __popc(lead_mask & ((1u << leader) - 1u));
-    const int total = __popc(lead_mask) * NCH;
-    if (lane == leader) wimg[slot] = img;
-    __syncwarp();
-    for (int it = lane; it < total; it += 32) {
-      const int k = it / NCH, c = it - k * NCH;
-      const double2 v = __ldg(reinterpret_cast<const double2*>(aux + AUX * (size_t)wimg[k]) + c);
-      *reinterpret_cast<double2*>(wbuf + k * K1_SLOT + 2 * c) = v;
-    }
-    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"((unsigned)(__popc(lead_mask) * NCH * 16)) : "memory");
+    if (lane == leader) k1_bulk_g2s(wbuf + slot * K1_SLOT, aux + AUX * (size_t)img, NCH * 16, bar);
+    k1_mbar_wait(bar, phase); phase ^= 1;
     double a[AUX];
     {
       const double2* s2 = reinterpret_cast<const double2*>(wbuf + slot * K1_SLOT);
 #pragma unroll
       for (int k = 0; k < NCH; ++k) { const double2 t = s2[k]; a[2 * k] = t.x; a[2 * k + 1] = t.y; }
     }
+    if (!WITH_J) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // (the Jacobian pass fences after it has staged its records)
     __syncwarp();                                             // slots are free again: the same area stages the records below
+    (void)wimg;
     const double* R = a;
     const double Y0 = R[0] * X0 + R[1] * X1 + R[2] * X2;
     const double Y1 = R[3] * X0 + R[4] * X1 + R[5] * X2;
@@ -122,8 +139,8 @@ __global__ void __launch_bounds__(256, WITH_J ? 2 : 3) k_residual_jacobian(
     world2image<WITH_J>(model, intr + MM_INTR_STRIDE * (size_t)cam, xc, yc, zc, u, v, dX, WITH_JI ? dP : nullptr);
     const double r0 = u - xy.x, r1 = v - xy.y;
     double rho0, sr;
-    loss_eval(L, r0 * r0 + r1 * r1, rho0, sr);
-    if (valid) cost += 0.5 * rho0;
+    loss_eval<WITH_COST>(L, r0 * r0 + r1 * r1, rho0, sr);
+    if (WITH_COST && valid) cost += 0.5 * rho0;
     if (WITH_JI) {        // d r / d intrinsics (2 x 9), robustified and masked; 144 B per observation
       if (valid) {
         double2* j2 = reinterpret_cast<double2*>(ji + 18 * (size_t)(i0 + lane));
@@ -174,11 +191,14 @@ __global__ void __launch_bounds__(256, WITH_J ? 2 : 3) k_residual_jacobian(
         const int c = k * 32 + lane, src = c / 10, part = c - 10 * src;
         if (src < nvalid) g2[c] = *reinterpret_cast<const double2*>(wbuf + (size_t)src * K1_PITCH + 2 * part);
       }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic accesses to the slots before the next round's bulk copies land there
       __syncwarp();
     }
   }
-  cost = block_sum(cost, red);
-  if (threadIdx.x == 0) cost_part[blockIdx.x] = cost;
+  if (WITH_COST) {
+    cost = block_sum(cost, red);
+    if (threadIdx.x == 0) cost_part[blockIdx.x] = cost;
+  }
 }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
