@@ -194,7 +194,7 @@ struct mm_ba_session {
   DevBuf<int4> tc_upd; DevBuf<int2> tc_items;
   DevBuf<int> tc_ready, tc_sflag, tc_counters;
   DevBuf<int64_t> tc_col_ptr;
-  DevBuf<double> tc_L, tc_WC, tc_WR, tc_slots, dv_b, dv_r, dv_z, dv_p, dv_Ap;
+  DevBuf<double> tc_L, tc_WC, tc_WR, tc_slots, tc_invd, dv_b, dv_r, dv_z, dv_p, dv_Ap;
   int grid_obs = 1, grid_pt = 1, grid_cam6 = 1, grid_x = 1, pcg_grid = 0, pcg_ecap = 0, pcg_threads = 0; bool pcg_cached = false; size_t pcg_smem = 0; const void* pcg_fn = nullptr;
   cudaEvent_t evs[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // LM state (host)
@@ -663,18 +663,24 @@ int build_tilechol(mm_ba_session* s) {
   std::vector<int> sched(8 * n_tasks), sdesc(16 * (size_t)P.n_stasks, 0);
   std::vector<int4> upd((size_t)(P.n_upd + P.n_wupd)); std::vector<int2> items(P.it_mat.size());
   for (int64_t u = 0; u < P.n_upd; ++u) upd[u] = make_int4(P.upd_a[u], P.upd_b[u], P.upd_a[u], P.upd_b[u]);
-  for (int64_t u = 0; u < P.n_wupd; ++u) upd[P.n_upd + u] = make_int4(P.wupd_l[u], P.wupd_w[u], P.wupd_l[u], P.wupd_flag[u] | (1 << 30));
+  // flags: [0, n_tasks) one per factor task (a diagonal task sets its flag when L(j,j) is stored), then one per tile row, set when
+  // the inverse W(j,j) is stored as well
+  for (int64_t u = 0; u < P.n_wupd; ++u) {
+    int fl = P.wupd_flag[u];
+    if (fl < P.n_l) fl = (int)n_tasks + P.col_idx[fl];            // operand W(k,k): produced by the diagonal task of column k, second flag
+    upd[P.n_upd + u] = make_int4(P.wupd_l[u], P.wupd_w[u], P.wupd_l[u], fl | (1 << 30));
+  }
   for (size_t slot = 0; slot < n_tasks; ++slot) {
     const int t = P.task_order[slot]; int* d = sched.data() + 8 * slot;
     d[0] = t;
     if (t < P.n_l) {
       const int j = P.col_idx[t]; const bool diag = P.row_idx[t] == j;
       d[1] = diag ? 1 : 0; d[2] = (int)P.upd_ptr[t]; d[3] = (int)(P.upd_ptr[t + 1] - P.upd_ptr[t]);
-      d[4] = (int)(P.w_row_ptr[j + 1] - 1); d[5] = (int)P.col_ptr[j]; d[6] = P.has_a[t]; d[7] = diag ? P.tile_nunk[j] : 0;
+      d[4] = diag ? (int)(P.w_row_ptr[j + 1] - 1) : (int)P.col_ptr[j]; d[5] = (int)P.col_ptr[j]; d[6] = P.has_a[t] | (j << 1); d[7] = diag ? P.tile_nunk[j] : 0;
     } else {
       const int w = t - (int)P.n_l; const int i = P.wt_row[w];
       d[1] = 2; d[2] = (int)(P.n_upd + P.wupd_ptr[w]); d[3] = (int)(P.wupd_ptr[w + 1] - P.wupd_ptr[w]);
-      d[4] = (int)(P.w_row_ptr[i + 1] - 1); d[5] = (int)P.col_ptr[i]; d[6] = 0; d[7] = P.wt_store[w];
+      d[4] = (int)(P.w_row_ptr[i + 1] - 1); d[5] = (int)n_tasks + i; d[6] = i << 1; d[7] = P.wt_store[w];
     }
   }
   for (int k = 0; k < P.n_stasks; ++k) {
@@ -690,8 +696,8 @@ int build_tilechol(mm_ba_session* s) {
       (rc = tc_upload(s->tc_sched, sched)) || (rc = tc_upload(s->tc_sdesc, sdesc)) || (rc = tc_upload(s->tc_upd, upd)) || (rc = tc_upload(s->tc_items, items))) return rc;
   MM_CUDA(s->tc_L.alloc((size_t)TC_TT * (size_t)P.n_l)); MM_CUDA(s->tc_WC.alloc((size_t)TC_TT * (size_t)P.n_w)); MM_CUDA(s->tc_WR.alloc((size_t)TC_TT * (size_t)P.n_w));
   MM_CUDA(s->tc_slots.alloc((size_t)TC_T * (size_t)P.n_slots));
-  MM_CUDA(s->tc_ready.alloc(n_tasks)); MM_CUDA(s->tc_sflag.alloc((size_t)P.n_slots)); MM_CUDA(s->tc_counters.alloc(4));
-  MM_CUDA(cudaMemset(s->tc_ready.p, 0, sizeof(int) * n_tasks)); MM_CUDA(cudaMemset(s->tc_sflag.p, 0, sizeof(int) * (size_t)P.n_slots));
+  MM_CUDA(s->tc_ready.alloc(n_tasks + (size_t)P.nt)); MM_CUDA(s->tc_sflag.alloc((size_t)P.n_slots)); MM_CUDA(s->tc_counters.alloc(4)); MM_CUDA(s->tc_invd.alloc((size_t)TC_T * P.nt));
+  MM_CUDA(cudaMemset(s->tc_ready.p, 0, sizeof(int) * (n_tasks + (size_t)P.nt))); MM_CUDA(cudaMemset(s->tc_sflag.p, 0, sizeof(int) * (size_t)P.n_slots));
   s->n_unk = 6 * n + 9 * s->ncb;
   MM_CUDA(s->dv_b.alloc((size_t)s->n_unk)); MM_CUDA(s->dv_r.alloc((size_t)s->n_unk)); MM_CUDA(s->dv_z.alloc((size_t)s->n_unk)); MM_CUDA(s->dv_p.alloc((size_t)s->n_unk)); MM_CUDA(s->dv_Ap.alloc((size_t)s->n_unk));
   TcDev& D = s->tc;
@@ -699,7 +705,7 @@ int build_tilechol(mm_ba_session* s) {
   D.n_tasks = (int)n_tasks; D.n_stasks = P.n_stasks; D.n_slots = P.n_slots;
   D.unk_of = s->tc_unk_of.p; D.sc_tile = s->tc_sc_tile.p; D.sc_off = s->tc_sc_off.p; D.a_tiles = s->tc_a_tiles.p; D.img_tile = s->tc_img_tile.p; D.img_slot = s->tc_img_slot.p;
   D.col_ptr = s->tc_col_ptr.p; D.sched = s->tc_sched.p; D.upd = s->tc_upd.p; D.sdesc = s->tc_sdesc.p; D.items = s->tc_items.p;
-  D.L = s->tc_L.p; D.WC = s->tc_WC.p; D.WR = s->tc_WR.p; D.slots = s->tc_slots.p;
+  D.L = s->tc_L.p; D.WC = s->tc_WC.p; D.WR = s->tc_WR.p; D.slots = s->tc_slots.p; D.invd = s->tc_invd.p;
   D.ready = s->tc_ready.p; D.sflag = s->tc_sflag.p; D.counters = s->tc_counters.p; D.trace = nullptr; D.trace_diag = nullptr;
   MM_CUDA(cudaFuncSetAttribute((const void*)k_tc_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_FACTOR_SMEM));
   int per_sm = 0;

@@ -27,7 +27,8 @@ namespace mm {
 
 // Packed device copies of the plan (built by the session from TileCholPlan):
 //   sched[slot]  8 ints  {task, kind (0 off-diagonal L, 1 diagonal L, 2 W), first update, number of updates,
-//                         W index of the inverse the task finishes with, task whose flag guards it, has_a, tile_nunk | W store index}
+//                         tile the task finishes with (0: L(j,j); 1: W index of its own inverse; 2: W index of inv(L(i,i))), flag that guards it,
+//                         has_a | tile column j << 1, tile_nunk | W store index}
 //   upd[u]       int4    {tile of the first operand (L), tile of the second (L, or WR with bit 30 of .w set), flag of the first, flag of the second}
 //   sdesc[k]     8 ints  {kind, out slot, base, tile row, first item, number of items, 0, 0}
 //   items[q]     int2    {matrix selector << 28 | tile, source slot}
@@ -36,8 +37,8 @@ struct TcDev {
   const int *sc_tile, *sc_off, *a_tiles, *img_tile, *img_slot, *unk_of;
   const int64_t* col_ptr;
   const int* sched; const int4* upd; const int* sdesc; const int2* items;
-  double *L, *WC, *WR, *slots;              // tiles of L; W (inverse of the node blocks) column-major and row-major; 48-vector slots
-  int *ready, *sflag, *counters;            // ready: per factor task; sflag: per slot; counters: [0] factor tasks, [1] substitution tasks
+  double *L, *WC, *WR, *slots, *invd;       // tiles of L; W (inverse of the node blocks) column-major and row-major; 48-vector slots; 1 / diag(L) per tile row
+  int *ready, *sflag, *counters;            // ready: per factor task, then per tile row (its inverse W(j,j) is stored); sflag: per slot; counters: [0] factor, [1] substitution tasks
   unsigned long long* trace;                // optional (test hook): {start, end} in ns per factor task, then per substitution task
   unsigned long long* trace_diag;           // optional (test hook): 8 phase stamps per diagonal task (indexed by W index of its inverse)
 };
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(TC_FACTOR_THREADS, 2) k_tc_factor(TcDev P, int
       }
       const int dv = lane < 8 ? P.sched[8 * (size_t)slot + lane] : 0;
       const int t = __shfl_sync(0xffffffffu, dv, 0), kind = __shfl_sync(0xffffffffu, dv, 1), ub = __shfl_sync(0xffffffffu, dv, 2), nu = __shfl_sync(0xffffffffu, dv, 3);
-      const int fin_idx = __shfl_sync(0xffffffffu, dv, 4), fin_flag = __shfl_sync(0xffffffffu, dv, 5), has_a = __shfl_sync(0xffffffffu, dv, 6), aux = __shfl_sync(0xffffffffu, dv, 7);
+      const int fin_idx = __shfl_sync(0xffffffffu, dv, 4), fin_flag = __shfl_sync(0xffffffffu, dv, 5), hasa_j = __shfl_sync(0xffffffffu, dv, 6), aux = __shfl_sync(0xffffffffu, dv, 7);
       if (P.trace && lane == 0) P.trace[2 * (size_t)t] = tc_gtimer();
       const int upd_kind = kind == 2 ? TC_KIND_WUPD : TC_KIND_UPD;
       for (int base = 0; base < nu; base += 32) {
@@ -233,18 +234,19 @@ __global__ void __launch_bounds__(TC_FACTOR_THREADS, 2) k_tc_factor(TcDev P, int
         }
       }
       if (lane == 0) {
-        // finishing stage: the entries of A(i,j) (what the assembly left in the tile's own storage) into the first half,
-        // the inverse of the diagonal tile into the second half
+        // finishing stage: the entries of A(i,j) (what the assembly left in the tile's own storage) into the first half; into the
+        // second half L(j,j) for an off-diagonal tile of L (triangular solve), inv(L(i,i)) for a tile of W
         tc_mbar_wait(bar0 + 8 * (TC_STAGES + stage), phase ^ 1);
         const uint32_t dstA = tc_smem_addr(bufs + (size_t)2 * TC_TT * stage);
+        const int has_a = hasa_j & 1, jcol = hasa_j >> 1;
         if (kind != 1) { tc_wait_flag(P.ready + fin_flag, epoch); tc_fence_proxy_async_global(); }
-        meta[stage] = make_int4(t, (kind == 1 ? TC_KIND_FIN_DIAG : (kind == 2 ? TC_KIND_FIN_W : TC_KIND_FIN_OFF)) | (has_a << 10), aux, fin_idx);
+        meta[stage] = make_int4(t, (kind == 1 ? TC_KIND_FIN_DIAG : (kind == 2 ? TC_KIND_FIN_W : TC_KIND_FIN_OFF)) | (has_a << 10) | (jcol << 12), aux, fin_idx);
         const uint32_t bytes = TILE_BYTES * ((has_a ? 1 : 0) + (kind != 1 ? 1 : 0));
         if (bytes == 0) tc_mbar_arrive(bar0 + 8 * stage);
         else {
           tc_mbar_expect_tx(bar0 + 8 * stage, bytes);
           if (has_a) tc_bulk_g2s(dstA, P.L + (size_t)TC_TT * t, TILE_BYTES, bar0 + 8 * stage);
-          if (kind != 1) tc_bulk_g2s(dstA + TILE_BYTES, P.WC + (size_t)TC_TT * fin_idx, TILE_BYTES, bar0 + 8 * stage);      // inverse of the diagonal tile, column-major
+          if (kind != 1) tc_bulk_g2s(dstA + TILE_BYTES, (kind == 0 ? P.L : P.WC) + (size_t)TC_TT * fin_idx, TILE_BYTES, bar0 + 8 * stage);
         }
       }
       if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
@@ -307,16 +309,32 @@ __global__ void __launch_bounds__(TC_FACTOR_THREADS, 2) k_tc_factor(TcDev P, int
       cur = -1;
       tc_bar_consumers();
       if (skind == TC_KIND_FIN_OFF) {
-        // L(i,j) = C inv(L(j,j))'
-        double out[6][3];
-#pragma unroll
-        for (int a = 0; a < 6; ++a) { out[a][0] = 0.0; out[a][1] = 0.0; out[a][2] = 0.0; }
-        tc_frag_gemm<false>(out, A, B, r0, c0);
-        double* dst = P.L + (size_t)TC_TT * t;
-#pragma unroll
-        for (int b = 0; b < 3; ++b)
-#pragma unroll
-          for (int a = 0; a < 6; a += 2) __stcg(reinterpret_cast<double2*>(dst + (c0 + b) * TC_T + r0 + a), make_double2(out[a][b], out[a + 1][b]));
+        // L(i,j) L(j,j)' = C:  one thread per row of C, right-looking substitution with the row in registers; L(j,j) (second half
+        // of the stage) is read as broadcasts, its reciprocal diagonal comes from the diagonal task.  No inverse on this path.
+        const int jcol = m.y >> 12;
+        if (tid < TC_T) invd[tid] = __ldcg(P.invd + (size_t)TC_T * jcol + tid);
+        tc_bar_consumers();
+        if (tid < TC_T) {
+          // in place in the first half (column-major: thread r owns the words c * 48 + r, conflict-free), panels of four columns
+          const int r = tid;
+          for (int p = 0; p < TC_T; p += 4) {
+            const double* L0 = B + p * TC_T; const double* L1 = L0 + TC_T; const double* L2 = L1 + TC_T;           // columns p .. p+2 of L(j,j)
+            const double x0 = A[p * TC_T + r] * invd[p];
+            const double x1 = (A[(p + 1) * TC_T + r] - x0 * L0[p + 1]) * invd[p + 1];
+            const double x2 = (A[(p + 2) * TC_T + r] - x0 * L0[p + 2] - x1 * L1[p + 2]) * invd[p + 2];
+            const double x3 = (A[(p + 3) * TC_T + r] - x0 * L0[p + 3] - x1 * L1[p + 3] - x2 * L2[p + 3]) * invd[p + 3];
+            A[p * TC_T + r] = x0; A[(p + 1) * TC_T + r] = x1; A[(p + 2) * TC_T + r] = x2; A[(p + 3) * TC_T + r] = x3;
+            const double* L3 = L2 + TC_T;
+#pragma unroll 4
+            for (int c2 = p + 4; c2 < TC_T; ++c2) A[c2 * TC_T + r] -= x0 * L0[c2] + x1 * L1[c2] + x2 * L2[c2] + x3 * L3[c2];
+          }
+        }
+        tc_bar_consumers();
+        {
+          double2* dst = reinterpret_cast<double2*>(P.L + (size_t)TC_TT * t); const double2* src = reinterpret_cast<const double2*>(A);
+#pragma unroll 3
+          for (int e = tid; e < TC_TT / 2; e += TC_CONSUMERS) __stcg(dst + e, src[e]);
+        }
       } else if (skind == TC_KIND_FIN_W) {
         // W(i,j) = -inv(L(i,i)) C   (C row-major in A, inverse column-major in B)
         double out[6][3];
@@ -336,7 +354,7 @@ __global__ void __launch_bounds__(TC_FACTOR_THREADS, 2) k_tc_factor(TcDev P, int
         // panel the owners put its columns into shared memory, 48 row threads factor the 6 x 6 diagonal block (each its own
         // copy: cheaper than a barrier) and solve their row of the panel, then all threads update their fragments.
         if (P.trace_diag && tid == 0) P.trace_diag[8 * (size_t)m.w + 1] = tc_gtimer();
-        const int nunk = m.z;
+        const int nunk = m.z, jcol = m.y >> 12;
         double f[6][3];
 #pragma unroll
         for (int b = 0; b < 3; ++b)
@@ -429,7 +447,11 @@ __global__ void __launch_bounds__(TC_FACTOR_THREADS, 2) k_tc_factor(TcDev P, int
             *reinterpret_cast<double2*>(A + (c0 + b) * TC_T + r0 + a) = make_double2(v0, v1);
             __stcg(reinterpret_cast<double2*>(dstL + (c0 + b) * TC_T + r0 + a), make_double2(v0, v1));
           }
-        tc_bar_consumers();
+        if (tid < TC_T) __stcg(P.invd + (size_t)TC_T * jcol + tid, invd[tid]);
+        // L(j,j) is what the tiles below it wait for: publish it now; the inverse (needed by the node-block inverses and the
+        // substitutions only) follows under its own flag
+        tc_publish(P.ready + t, epoch, tid);
+        if (P.trace && tid == 0) P.trace[2 * (size_t)t + 1] = tc_gtimer();
         // inverse W of L = [[L11, 0], [L21, L22]] (24 x 24 blocks), row-major in the free half B:
         //   W11, W22: one thread per column, right-looking substitution in panels of four rows (two warps side by side)
         //   W21 = -W22 (L21 W11): two 24^3 products on 96 threads
@@ -494,9 +516,14 @@ __global__ void __launch_bounds__(TC_FACTOR_THREADS, 2) k_tc_factor(TcDev P, int
         }
       }
       if (P.trace_diag && tid == 0 && skind == TC_KIND_FIN_DIAG) P.trace_diag[8 * (size_t)m.w + 6] = tc_gtimer();
-      tc_publish(P.ready + t, epoch, tid);
-      if (P.trace && tid == 0) P.trace[2 * (size_t)t + 1] = tc_gtimer();
+      if (skind == TC_KIND_FIN_DIAG) tc_publish(P.ready + P.n_tasks + (m.y >> 12), epoch, tid);       // W(j,j) stored
+      else { tc_publish(P.ready + t, epoch, tid); if (P.trace && tid == 0) P.trace[2 * (size_t)t + 1] = tc_gtimer(); }
       if (P.trace_diag && tid == 0 && skind == TC_KIND_FIN_DIAG) P.trace_diag[8 * (size_t)m.w + 7] = tc_gtimer();
+      // (the partial sum is dead from here to the next task: saying so keeps its registers free for the finishing code)
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = 0; b < 6; ++b) acc[a][b] = 0.0;
     }
     __syncwarp();
     if (lane == 0) tc_mbar_arrive(bar0 + 8 * (TC_STAGES + stage));
