@@ -12,6 +12,8 @@
 #include <vector>
 #include <string>
 #include <algorithm>
+#include <thread>
+#include <time.h>
 #include "ba_kernels.cuh"
 #include "ba_pose.cuh"
 #include "tilechol.cuh"
@@ -145,6 +147,41 @@ __global__ void k_fill(int64_t n, double* p, double v) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
+// range check of the observation indices on the device (the host does not walk the 10^7 observations): flag = 1 if any is out of range
+__global__ void k_obs_check(int64_t n, const int* __restrict__ img, const int* __restrict__ pt, int n_img, int n_pt, int* __restrict__ flag) {
+  bool bad = false;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    bad |= (unsigned)img[i] >= (unsigned)n_img || (unsigned)pt[i] >= (unsigned)n_pt;
+  if (bad) *flag = 1;
+}
+// masks: 1.0 = free and present in at least one residual block.  pose_const: 4 bytes per image (rvec, tx, ty, tz)
+__global__ void k_pose_mask(int n_img, const unsigned char* __restrict__ pose_const, const int* __restrict__ cam_start, double* __restrict__ mask) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_img) return;
+  const bool seen = cam_start[i + 1] > cam_start[i];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) mask[6 * (size_t)i + k] = (seen && !pose_const[4 * (size_t)i + (k < 3 ? 0 : k - 2)]) ? 1.0 : 0.0;
+}
+__global__ void k_pt_mask(int n_pt, const unsigned char* __restrict__ pt_const /*caller order*/, const int* __restrict__ new2old, const int* __restrict__ pt_start, double* __restrict__ mask) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n_pt) mask[p] = (pt_start[p + 1] > pt_start[p] && !pt_const[new2old[p]]) ? 1.0 : 0.0;
+}
+// rows of 1 or 3 doubles between the caller's point order and the internal one
+__global__ void k_gather_rows3(int n, const int* __restrict__ new2old, const double* __restrict__ src /*caller order*/, double* __restrict__ dst) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) { const size_t o = (size_t)new2old[p]; dst[3 * (size_t)p] = src[3 * o]; dst[3 * (size_t)p + 1] = src[3 * o + 1]; dst[3 * (size_t)p + 2] = src[3 * o + 2]; }
+}
+__global__ void k_scatter_rows3(int n, const int* __restrict__ new2old, const double* __restrict__ src /*internal order*/, double* __restrict__ dst) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) { const size_t o = (size_t)new2old[p]; dst[3 * o] = src[3 * (size_t)p]; dst[3 * o + 1] = src[3 * (size_t)p + 1]; dst[3 * o + 2] = src[3 * (size_t)p + 2]; }
+}
+__global__ void k_gather_rows1(int n, const int* __restrict__ new2old, const double* __restrict__ src, double* __restrict__ dst) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x; if (p < n) dst[p] = src[new2old[p]];
+}
+__global__ void k_scatter_rows1(int n, const int* __restrict__ new2old, const double* __restrict__ src, double* __restrict__ dst) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x; if (p < n) dst[new2old[p]] = src[p];
+}
+
 static inline int blocks_for(int64_t n, int block) { int64_t g = (n + block - 1) / block; return (int)(g < 1 ? 1 : g); }
 static inline int grid_stride(int64_t n, int block) { int64_t g = (n + block - 1) / block; const int cap = num_sms() * 8; return (int)(g < 1 ? 1 : (g > cap ? cap : g)); }
 
@@ -159,7 +196,8 @@ struct mm_ba_session {
   int n_img = 0, n_cam = 0, n_pt = 0; int64_t n_obs = 0;
   int n_off = 0; int64_t nblk = 0, n_pairs = 0, n_ent = 0;
   std::vector<double> h_poses0, h_intr0, h_pts0;
-  std::vector<double> h_pt_mask; std::vector<int> h_pt_new2old;         // internal point order (spatially clustered) -> caller's order
+  DevBuf<int> pt_new2old;                                               // internal point order (spatially clustered) -> caller's order
+  bool keep_host_pts = true;                                            // mm_ba_solve: no session reset, so no host copy of the points
   DevBuf<double2> obs_xy; DevBuf<int> obs_img, obs_pt, pt_start, cam_perm, cam_start, img_cam, cam_model;
   DevBuf<int64_t> pair_off; DevBuf<int> row_start, row_col, row_blk, sp_lo, sp_hi, sp_pt, bp_start, bp_end; DevBuf<double> pinfo;
   DevBuf<double> S, Minv, poses, intr, pts, poses2, pts2, aux, aux2, rec;
@@ -190,6 +228,9 @@ struct mm_ba_session {
   // sparse tile Cholesky preconditioner of the PCG solve (tilechol.cuh): plan (host), its device copy, tiles, PCG vectors
   bool tc_on = false; int tc_epoch = 0, tc_sepoch = 0, tc_grid_f = 0, tc_grid_s = 0, n_unk = 0, ncb = 0;
   TileCholPlan tc_plan; TcDev tc;
+  // the symbolic analysis runs on a host thread beside the rest of the setup (tc_begin / tc_finish)
+  std::thread tc_thread; int tc_plan_rc = 0; std::vector<int> tc_ha, tc_hb; std::vector<double> tc_pos;
+  std::vector<int> tc_h_sched, tc_h_sdesc; std::vector<int4> tc_h_upd; std::vector<int2> tc_h_items; bool tc_force = false;
   DevBuf<int> tc_unk_of, tc_sc_tile, tc_sc_off, tc_a_tiles, tc_img_tile, tc_img_slot, tc_sched, tc_sdesc;
   DevBuf<int4> tc_upd; DevBuf<int2> tc_items;
   DevBuf<int> tc_ready, tc_sflag, tc_counters;
@@ -213,6 +254,64 @@ struct Timer {
   ~Timer() { cudaEventRecord(s->ev1, s->stream); cudaEventSynchronize(s->ev1); float ms = 0; cudaEventElapsedTime(&ms, s->ev0, s->ev1); *acc += ms; }
 };
 
+// host wall-clock stamps of the phases of mm_ba_session_create (MM_SETUP_TIMING=1 prints them; the stream is drained at every stamp)
+struct SetupClock {
+  bool on; cudaStream_t st; double t0, last;
+  static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return 1e3 * ts.tv_sec + 1e-6 * ts.tv_nsec; }
+  explicit SetupClock(cudaStream_t s) : on(getenv("MM_SETUP_TIMING") != nullptr), st(s) { t0 = last = now(); }
+  void mark(const char* what) { if (!on) return; cudaStreamSynchronize(st); const double t = now(); fprintf(stderr, "[setup] %-28s %8.3f ms  (at %8.3f)\n", what, t - last, t - t0); last = t; }
+};
+
+// Large host -> device copies of pageable caller memory (mm_ba_solve hands over 10^7 observations = 240 MB): the driver's own
+// staging moves them at ~10 GB/s because one thread feeds it.  Here several host threads copy slices of a chunk into one half of
+// a persistent pinned double buffer while the DMA engine drains the other half.  Stream-ordered like cudaMemcpyAsync; the source
+// has been read completely when the call returns.
+struct Staging {
+  static constexpr size_t CHUNK = (size_t)32 << 20;
+  char* buf[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr}; bool ok = false; int dev = -1;
+  static Staging& get() { static thread_local Staging st; return st; }
+  bool ready() {
+    int d = 0; cudaGetDevice(&d);
+    if (ok && d == dev) return true;
+    if (ok) return false;                       // created for another device: fall back to plain copies
+    for (int b = 0; b < 2; ++b)
+      if (cudaHostAlloc((void**)&buf[b], CHUNK, cudaHostAllocDefault) != cudaSuccess || cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return false; }
+    ok = true; dev = d; return true;
+  }
+};
+cudaError_t upload_async(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  Staging& S = Staging::get();
+  if (bytes < ((size_t)4 << 20) || getenv("MM_NO_STAGING") || !S.ready()) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+  static const unsigned n_thr = std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
+  size_t off = 0; int b = 0;
+  while (off < bytes) {
+    const size_t len = std::min(Staging::CHUNK, bytes - off);
+    cudaError_t e = cudaEventSynchronize(S.ev[b]); if (e != cudaSuccess) return e;          // the previous copy out of this half has finished
+    const char* from = static_cast<const char*>(src) + off; char* to = S.buf[b];
+    const size_t slice = ((len + n_thr - 1) / n_thr + 4095) & ~(size_t)4095;
+    std::thread workers[8]; unsigned nw = 0;
+    for (unsigned t = 1; t < n_thr; ++t) { const size_t o = t * slice; if (o >= len) break; workers[nw++] = std::thread([=] { memcpy(to + o, from + o, std::min(slice, len - o)); }); }
+    memcpy(to, from, std::min(slice, len));
+    for (unsigned t = 0; t < nw; ++t) workers[t].join();
+    e = cudaMemcpyAsync(static_cast<char*>(dst) + off, to, len, cudaMemcpyHostToDevice, st); if (e != cudaSuccess) return e;
+    e = cudaEventRecord(S.ev[b], st); if (e != cudaSuccess) return e;
+    off += len; b ^= 1;
+  }
+  return cudaSuccess;
+}
+
+// One pool allocation for a group of temporaries (the structure setup used ~20 separate ones of 40 - 160 MB each; their
+// alloc / free pattern fragmented the stream-ordered pool from call to call).  take() hands out 256-byte aligned pieces.
+struct Arena {
+  DevBuf<char> mem; size_t used = 0, cap = 0;
+  static size_t pad(size_t b) { return (b + 255) & ~(size_t)255; }
+  cudaError_t reserve(size_t bytes) { used = 0; cap = bytes; return mem.alloc(std::max<size_t>(bytes, 256)); }
+  template <typename T> T* take(size_t count) { T* q = reinterpret_cast<T*>(mem.p + used); used += pad(count * sizeof(T)); return used <= cap ? q : nullptr; }
+};
+
+thread_local SetupClock* g_setup_clock = nullptr;
+#define SETUP_MARK(what) do { if (g_setup_clock) g_setup_clock->mark(what); } while (0)
+
 int validate_problem(const mm_ba_problem* P) {
   if (!P || P->n_img < 0 || P->n_cam < 0 || P->n_pt < 0 || P->n_obs < 0) { set_error("invalid problem sizes"); return MM_ERR_INVALID_ARG; }
   if (P->n_obs >= (int64_t)1 << 31) { set_error("n_obs >= 2^31 not supported"); return MM_ERR_UNSUPPORTED; }
@@ -221,136 +320,178 @@ int validate_problem(const mm_ba_problem* P) {
       (P->n_pt > 0 && (!P->pts || !P->pt_const)) || (P->n_obs > 0 && (!P->obs_xy || !P->obs_img || !P->obs_pt))) { set_error("null array in problem"); return MM_ERR_INVALID_ARG; }
   for (int c = 0; c < P->n_cam; ++c) if (model_num_params(P->cam_model[c]) < 0) { set_error("unknown camera model code %d", P->cam_model[c]); return MM_ERR_INVALID_ARG; }
   for (int i = 0; i < P->n_img; ++i) if (P->img_cam[i] < 0 || P->img_cam[i] >= P->n_cam) { set_error("img_cam out of range"); return MM_ERR_INVALID_ARG; }
-  for (int64_t o = 0; o < P->n_obs; ++o)
-    if (P->obs_img[o] < 0 || P->obs_img[o] >= P->n_img || P->obs_pt[o] < 0 || P->obs_pt[o] >= P->n_pt) { set_error("observation index out of range"); return MM_ERR_INVALID_ARG; }
-  return MM_OK;
+  if (P->n_obs > 0 && (P->n_img == 0 || P->n_pt == 0)) { set_error("observation index out of range"); return MM_ERR_INVALID_ARG; }
+  return MM_OK;       // (the observation indices themselves are range-checked on the device, build_structure)
 }
 
 template <typename K, typename V>
-int sort_pairs(cudaStream_t st, const K* kin, K* kout, const V* vin, V* vout, int64_t n, int end_bit) {
-  size_t bytes = 0;
-  MM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)n, 0, end_bit, st));
-  DevBuf<char> tmp; MM_CUDA(tmp.alloc(bytes));
-  MM_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, kin, kout, vin, vout, (int)n, 0, end_bit, st));
+size_t sort_bytes(int64_t n, int end_bit) {
+  size_t b = 0;
+  cub::DeviceRadixSort::SortPairs((void*)nullptr, b, (const K*)nullptr, (K*)nullptr, (const V*)nullptr, (V*)nullptr, (int)std::max<int64_t>(n, 1), 0, end_bit);
+  return b;
+}
+template <typename K, typename V>
+int sort_pairs(cudaStream_t st, void* tmp, size_t bytes, const K* kin, K* kout, const V* vin, V* vout, int64_t n, int end_bit) {
+  MM_CUDA(cub::DeviceRadixSort::SortPairs(tmp, bytes, kin, kout, vin, vout, (int)n, 0, end_bit, st));
   count_launch(4);
-  MM_CUDA(cudaStreamSynchronize(st));
   return MM_OK;
 }
 template <typename T>
-int exclusive_sum(cudaStream_t st, const T* in, T* out, int64_t n) {
-  size_t bytes = 0;
-  MM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int)n, st));
-  DevBuf<char> tmp; MM_CUDA(tmp.alloc(bytes));
-  MM_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, in, out, (int)n, st));
+size_t scan_bytes(int64_t n) { size_t b = 0; cub::DeviceScan::ExclusiveSum((void*)nullptr, b, (const T*)nullptr, (T*)nullptr, (int)std::max<int64_t>(n, 1)); size_t c = 0; cub::DeviceScan::InclusiveSum((void*)nullptr, c, (const T*)nullptr, (T*)nullptr, (int)std::max<int64_t>(n, 1)); return std::max(b, c); }
+template <typename T>
+int exclusive_sum(cudaStream_t st, void* tmp, size_t bytes, const T* in, T* out, int64_t n) {
+  MM_CUDA(cub::DeviceScan::ExclusiveSum(tmp, bytes, in, out, (int)n, st));
   count_launch(2);
-  MM_CUDA(cudaStreamSynchronize(st));
   return MM_OK;
 }
 template <typename T>
-int inclusive_sum(cudaStream_t st, const T* in, T* out, int64_t n) {
-  size_t bytes = 0;
-  MM_CUDA(cub::DeviceScan::InclusiveSum(nullptr, bytes, in, out, (int)n, st));
-  DevBuf<char> tmp; MM_CUDA(tmp.alloc(bytes));
-  MM_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, bytes, in, out, (int)n, st));
+int inclusive_sum(cudaStream_t st, void* tmp, size_t bytes, const T* in, T* out, int64_t n) {
+  MM_CUDA(cub::DeviceScan::InclusiveSum(tmp, bytes, in, out, (int)n, st));
   count_launch(2);
-  MM_CUDA(cudaStreamSynchronize(st));
   return MM_OK;
 }
 static int bits_for(unsigned long long maxval) { int b = 1; while (b < 64 && (maxval >> b)) ++b; return b; }
 
+// Structure of the problem on the device.  Everything that walks the observations runs here (range check of the indices, the
+// masks of parameters without residuals, the point renumbering): the host only hands the arrays over.
 int build_structure(mm_ba_session* s, const mm_ba_problem* P) {
   cudaStream_t st = s->stream;
   const int64_t n = s->n_obs; const int n_img = s->n_img, n_pt = s->n_pt;
   const int B = 256;
-  // upload observations in caller order
-  DevBuf<double2> xy_in; DevBuf<int> img_in, pt_in, perm, iota;
-  MM_CUDA(xy_in.alloc(n)); MM_CUDA(img_in.alloc(n)); MM_CUDA(pt_in.alloc(n)); MM_CUDA(perm.alloc(n)); MM_CUDA(iota.alloc(n));
-  MM_CUDA(cudaMemcpyAsync(xy_in.p, P->obs_xy, sizeof(double2) * n, cudaMemcpyHostToDevice, st));
-  MM_CUDA(cudaMemcpyAsync(img_in.p, P->obs_img, sizeof(int) * n, cudaMemcpyHostToDevice, st));
-  MM_CUDA(cudaMemcpyAsync(pt_in.p, P->obs_pt, sizeof(int) * n, cudaMemcpyHostToDevice, st));
-  MM_CUDA(s->obs_xy.alloc(n)); MM_CUDA(s->obs_img.alloc(n)); MM_CUDA(s->obs_pt.alloc(n));
-  MM_CUDA(s->pt_start.alloc((size_t)n_pt + 1)); MM_CUDA(s->cam_start.alloc((size_t)n_img + 1)); MM_CUDA(s->cam_perm.alloc(n));
+  const size_t n1 = (size_t)std::max<int64_t>(n, 1), np1 = (size_t)n_pt + 1, ni1 = (size_t)n_img + 1;
+  const int bits_pt = bits_for((unsigned long long)std::max(n_pt, 1)), bits_img = bits_for((unsigned long long)std::max(n_img, 1));
+  const int bits_key = bits_for((unsigned long long)(n_img + 1) * (unsigned long long)(n_img + 1));
+  MM_CUDA(s->obs_xy.alloc(n1)); MM_CUDA(s->obs_img.alloc(n1)); MM_CUDA(s->obs_pt.alloc(n1));
+  MM_CUDA(s->pt_start.alloc(np1)); MM_CUDA(s->cam_start.alloc(ni1)); MM_CUDA(s->cam_perm.alloc(n1)); MM_CUDA(s->pt_new2old.alloc((size_t)std::max(n_pt, 1)));
+  MM_CUDA(s->pair_off.alloc(np1));
+  // ---- arena 1: temporaries at observation / point granularity
+  Arena A1;
+  size_t cub1 = std::max(std::max(sort_bytes<int, int>(n, bits_pt), sort_bytes<int, int>(n, bits_img)), sort_bytes<unsigned long long, int>(n_pt, bits_key));
+  cub1 = std::max(cub1, std::max(scan_bytes<int>((int64_t)np1), scan_bytes<int64_t>((int64_t)np1)));
+  { size_t need = 0;
+    const size_t sizes[] = { 16 * n1, 4 * n1, 4 * n1, 4 * n1, 4 * n1, 4 * n1, 4 * np1, 4 * ni1, 8 * np1, 4 * np1, 4 * np1, 4 * np1, 4 * np1, 8 * np1, 8 * np1, np1, 4 * ni1, 256, cub1 };
+    for (size_t b : sizes) need += Arena::pad(b);
+    MM_CUDA(A1.reserve(need)); }
+  double2* xy_in = A1.take<double2>(n1); int* img_in = A1.take<int>(n1); int* pt_in = A1.take<int>(n1); int* perm = A1.take<int>(n1); int* iota = A1.take<int>(n1);
+  int* keys_out = A1.take<int>(n1); int* cnt_pt = A1.take<int>(np1); int* cnt_img = A1.take<int>(ni1); int64_t* cnt64 = A1.take<int64_t>(np1);
+  int* mn = A1.take<int>(np1); int* mx = A1.take<int>(np1); int* ids = A1.take<int>(np1); int* old2new = A1.take<int>(np1);
+  unsigned long long* key = A1.take<unsigned long long>(np1); unsigned long long* key_s = A1.take<unsigned long long>(np1);
+  unsigned char* pt_const = A1.take<unsigned char>(np1); unsigned char* pose_const = A1.take<unsigned char>(4 * ni1); int* flag = A1.take<int>(64);
+  void* cub_tmp = A1.take<char>(cub1);
+  if (!cub_tmp) { set_error("internal: setup arena too small"); return MM_ERR_ALLOC; }
+  // upload in caller order
+  if (n > 0) {
+    MM_CUDA(upload_async(img_in, P->obs_img, sizeof(int) * n, st));
+    MM_CUDA(upload_async(pt_in, P->obs_pt, sizeof(int) * n, st));
+    MM_CUDA(upload_async(xy_in, P->obs_xy, sizeof(double2) * n, st));
+  }
+  if (n_pt > 0) MM_CUDA(upload_async(pt_const, P->pt_const, (size_t)n_pt, st));
+  if (n_img > 0) MM_CUDA(cudaMemcpyAsync(pose_const, P->pose_const, 4 * (size_t)n_img, cudaMemcpyHostToDevice, st));
+  MM_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  if (n > 0) {
+    k_obs_check<<<grid_stride(n, B), B, 0, st>>>(n, img_in, pt_in, n_img, n_pt, flag); MM_LAUNCH_CHECK();
+    int bad = 0;
+    MM_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, st)); MM_CUDA(cudaStreamSynchronize(st));
+    if (bad) { set_error("observation index out of range"); return MM_ERR_INVALID_ARG; }
+  }
+  SETUP_MARK("structure: upload + check");
   // 0. renumber the points so that points seen by the same images are neighbours: gives the per-image gathers of
-  //    K1/K2b/K4 and the atomics of K2a cache locality.  The caller's numbering is restored on download.
-  s->h_pt_new2old.resize((size_t)n_pt);
+  //    K1/K2b/K4 cache locality.  The caller's numbering is restored on download (pt_new2old stays on the device).
   if (n > 0 && n_pt > 1 && !getenv("MM_BA_NO_REORDER")) {
-    DevBuf<int> mn, mx, ids, new2old, old2new; DevBuf<unsigned long long> key, key_s;
-    MM_CUDA(mn.alloc(n_pt)); MM_CUDA(mx.alloc(n_pt)); MM_CUDA(ids.alloc(n_pt)); MM_CUDA(new2old.alloc(n_pt)); MM_CUDA(old2new.alloc(n_pt)); MM_CUDA(key.alloc(n_pt)); MM_CUDA(key_s.alloc(n_pt));
-    k_fill_int<<<blocks_for(n_pt, B), B, 0, st>>>(n_pt, mn.p, n_img); MM_LAUNCH_CHECK();
-    k_fill_int<<<blocks_for(n_pt, B), B, 0, st>>>(n_pt, mx.p, -1); MM_LAUNCH_CHECK();
-    k_pt_minmax<<<grid_stride(n, B), B, 0, st>>>(n, img_in.p, pt_in.p, mn.p, mx.p); MM_LAUNCH_CHECK();
-    k_pt_key<<<blocks_for(n_pt, B), B, 0, st>>>(n_pt, n_img, mn.p, mx.p, key.p); MM_LAUNCH_CHECK();
-    k_iota<<<blocks_for(n_pt, B), B, 0, st>>>(n_pt, ids.p); MM_LAUNCH_CHECK();
-    int rc = sort_pairs<unsigned long long, int>(st, key.p, key_s.p, ids.p, new2old.p, n_pt, bits_for((unsigned long long)(n_img + 1) * (unsigned long long)(n_img + 1))); if (rc) return rc;
-    k_invert_perm<<<blocks_for(n_pt, B), B, 0, st>>>(n_pt, new2old.p, old2new.p); MM_LAUNCH_CHECK();
-    k_remap<<<grid_stride(n, B), B, 0, st>>>(n, old2new.p, pt_in.p); MM_LAUNCH_CHECK();
-    MM_CUDA(cudaMemcpyAsync(s->h_pt_new2old.data(), new2old.p, sizeof(int) * (size_t)n_pt, cudaMemcpyDeviceToHost, st));
-    MM_CUDA(cudaStreamSynchronize(st));
-  } else {
-    for (int p = 0; p < n_pt; ++p) s->h_pt_new2old[p] = p;
+    k_fill_int<<<blocks_for(n_pt, B), B, 0, st>>>(n_pt, mn, n_img); MM_LAUNCH_CHECK();
+    k_fill_int<<<blocks_for(n_pt, B), B, 0, st>>>(n_pt, mx, -1); MM_LAUNCH_CHECK();
+    k_pt_minmax<<<grid_stride(n, B), B, 0, st>>>(n, img_in, pt_in, mn, mx); MM_LAUNCH_CHECK();
+    k_pt_key<<<blocks_for(n_pt, B), B, 0, st>>>(n_pt, n_img, mn, mx, key); MM_LAUNCH_CHECK();
+    k_iota<<<blocks_for(n_pt, B), B, 0, st>>>(n_pt, ids); MM_LAUNCH_CHECK();
+    int rc = sort_pairs<unsigned long long, int>(st, cub_tmp, cub1, key, key_s, ids, s->pt_new2old.p, n_pt, bits_key); if (rc) return rc;
+    k_invert_perm<<<blocks_for(n_pt, B), B, 0, st>>>(n_pt, s->pt_new2old.p, old2new); MM_LAUNCH_CHECK();
+    k_remap<<<grid_stride(n, B), B, 0, st>>>(n, old2new, pt_in); MM_LAUNCH_CHECK();
+  } else if (n_pt > 0) {
+    k_iota<<<blocks_for(n_pt, B), B, 0, st>>>(n_pt, s->pt_new2old.p); MM_LAUNCH_CHECK();
   }
   if (n > 0) {
-    k_iota<<<blocks_for(n, B), B, 0, st>>>((int)n, iota.p); MM_LAUNCH_CHECK();
+    k_iota<<<blocks_for(n, B), B, 0, st>>>((int)n, iota); MM_LAUNCH_CHECK();
     // 1. stable sort by point (keeps the caller's order inside a track)
-    int rc = sort_pairs<int, int>(st, pt_in.p, s->obs_pt.p, iota.p, perm.p, n, bits_for((unsigned long long)std::max(n_pt, 1))); if (rc) return rc;
-    k_gather_obs<<<grid_stride(n, B), B, 0, st>>>(n, perm.p, xy_in.p, img_in.p, s->obs_xy.p, s->obs_img.p); MM_LAUNCH_CHECK();
+    int rc = sort_pairs<int, int>(st, cub_tmp, cub1, pt_in, s->obs_pt.p, iota, perm, n, bits_pt); if (rc) return rc;
+    k_gather_obs<<<grid_stride(n, B), B, 0, st>>>(n, perm, xy_in, img_in, s->obs_xy.p, s->obs_img.p); MM_LAUNCH_CHECK();
   }
   // 2. point -> observation CSR
-  { DevBuf<int> cnt; MM_CUDA(cnt.alloc((size_t)n_pt + 1)); MM_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(int) * ((size_t)n_pt + 1), st));
-    if (n > 0) { k_hist<<<grid_stride(n, B), B, 0, st>>>(n, s->obs_pt.p, cnt.p); MM_LAUNCH_CHECK(); }
-    int rc = exclusive_sum<int>(st, cnt.p, s->pt_start.p, (int64_t)n_pt + 1); if (rc) return rc; }
+  MM_CUDA(cudaMemsetAsync(cnt_pt, 0, sizeof(int) * np1, st));
+  if (n > 0) { k_hist<<<grid_stride(n, B), B, 0, st>>>(n, s->obs_pt.p, cnt_pt); MM_LAUNCH_CHECK(); }
+  { int rc = exclusive_sum<int>(st, cub_tmp, cub1, cnt_pt, s->pt_start.p, (int64_t)np1); if (rc) return rc; }
   // 3. camera-sorted permutation of the (point-sorted) observation positions
-  { DevBuf<int> cnt, keys_out; MM_CUDA(cnt.alloc((size_t)n_img + 1)); MM_CUDA(keys_out.alloc(n));
-    MM_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(int) * ((size_t)n_img + 1), st));
-    if (n > 0) {
-      k_hist<<<grid_stride(n, B), B, 0, st>>>(n, s->obs_img.p, cnt.p); MM_LAUNCH_CHECK();
-      int rc = sort_pairs<int, int>(st, s->obs_img.p, keys_out.p, iota.p, s->cam_perm.p, n, bits_for((unsigned long long)std::max(n_img, 1))); if (rc) return rc;
-    }
-    int rc = exclusive_sum<int>(st, cnt.p, s->cam_start.p, (int64_t)n_img + 1); if (rc) return rc; }
+  MM_CUDA(cudaMemsetAsync(cnt_img, 0, sizeof(int) * ni1, st));
+  if (n > 0) {
+    k_hist<<<grid_stride(n, B), B, 0, st>>>(n, s->obs_img.p, cnt_img); MM_LAUNCH_CHECK();
+    int rc = sort_pairs<int, int>(st, cub_tmp, cub1, s->obs_img.p, keys_out, iota, s->cam_perm.p, n, bits_img); if (rc) return rc;
+  }
+  { int rc = exclusive_sum<int>(st, cub_tmp, cub1, cnt_img, s->cam_start.p, (int64_t)ni1); if (rc) return rc; }
+  // masks: 1.0 = free and present in at least one residual block
+  if (n_img > 0) { k_pose_mask<<<blocks_for(n_img, B), B, 0, st>>>(n_img, pose_const, s->cam_start.p, s->pose_mask.p); MM_LAUNCH_CHECK(); }
+  if (n_pt > 0) { k_pt_mask<<<blocks_for(n_pt, B), B, 0, st>>>(n_pt, pt_const, s->pt_new2old.p, s->pt_start.p, s->pt_mask.p); MM_LAUNCH_CHECK(); }
   // 4. pairs of observations of one point -> blocks of the reduced camera system
-  MM_CUDA(s->pair_off.alloc((size_t)n_pt + 1));
-  { DevBuf<int64_t> cnt; MM_CUDA(cnt.alloc((size_t)n_pt + 1)); MM_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(int64_t) * ((size_t)n_pt + 1), st));
-    if (n_pt > 0) { k_pair_count<<<blocks_for(n_pt, B), B, 0, st>>>(n_pt, s->pt_start.p, cnt.p); MM_LAUNCH_CHECK(); }
-    int rc = exclusive_sum<int64_t>(st, cnt.p, s->pair_off.p, (int64_t)n_pt + 1); if (rc) return rc; }
+  MM_CUDA(cudaMemsetAsync(cnt64, 0, sizeof(int64_t) * np1, st));
+  if (n_pt > 0) { k_pair_count<<<blocks_for(n_pt, B), B, 0, st>>>(n_pt, s->pt_start.p, cnt64); MM_LAUNCH_CHECK(); }
+  { int rc = exclusive_sum<int64_t>(st, cub_tmp, cub1, cnt64, s->pair_off.p, (int64_t)np1); if (rc) return rc; }
   int64_t n_pairs = 0;
-  MM_CUDA(cudaMemcpy(&n_pairs, s->pair_off.p + n_pt, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  MM_CUDA(cudaMemcpyAsync(&n_pairs, s->pair_off.p + n_pt, sizeof(int64_t), cudaMemcpyDeviceToHost, st)); MM_CUDA(cudaStreamSynchronize(st));
   if (n_pairs >= ((int64_t)1 << 31)) { set_error("too many observation pairs (%lld)", (long long)n_pairs); return MM_ERR_UNSUPPORTED; }
   s->n_pairs = n_pairs;
+  A1.mem.release();
+  SETUP_MARK("structure: sorts + CSR");
   DevBuf<int>& blk_a = s->blk_a; DevBuf<int>& blk_b = s->blk_b;
   int n_off = 0;
   MM_CUDA(s->sp_lo.alloc((size_t)n_pairs)); MM_CUDA(s->sp_hi.alloc((size_t)n_pairs)); MM_CUDA(s->sp_pt.alloc((size_t)n_pairs));
   if (n_pairs > 0) {
-    DevBuf<unsigned long long> keys, keys_s; DevBuf<int> slot, slot_s, head, incl, pair_lo, pair_hi;
-    MM_CUDA(keys.alloc(n_pairs)); MM_CUDA(keys_s.alloc(n_pairs)); MM_CUDA(slot.alloc(n_pairs)); MM_CUDA(slot_s.alloc(n_pairs));
-    MM_CUDA(head.alloc(n_pairs)); MM_CUDA(incl.alloc(n_pairs)); MM_CUDA(pair_lo.alloc(n_pairs)); MM_CUDA(pair_hi.alloc(n_pairs));
-    k_pair_keys<<<blocks_for(n_pt, B), B, 0, st>>>(n_pt, n_img, s->pt_start.p, s->obs_img.p, s->pair_off.p, keys.p, pair_lo.p, pair_hi.p); MM_LAUNCH_CHECK();
-    k_iota<<<blocks_for(n_pairs, B), B, 0, st>>>((int)n_pairs, slot.p); MM_LAUNCH_CHECK();
-    int rc = sort_pairs<unsigned long long, int>(st, keys.p, keys_s.p, slot.p, slot_s.p, n_pairs, bits_for((unsigned long long)n_img * (unsigned long long)n_img)); if (rc) return rc;
-    k_pair_heads<<<grid_stride(n_pairs, B), B, 0, st>>>(n_pairs, n_img, keys_s.p, head.p); MM_LAUNCH_CHECK();
-    rc = inclusive_sum<int>(st, head.p, incl.p, n_pairs); if (rc) return rc;
-    MM_CUDA(cudaMemcpy(&n_off, incl.p + (n_pairs - 1), sizeof(int), cudaMemcpyDeviceToHost));
+    Arena A2;
+    const int bits_pair = bits_for((unsigned long long)n_img * (unsigned long long)n_img);
+    const size_t cub2 = std::max(sort_bytes<unsigned long long, int>(n_pairs, bits_pair), scan_bytes<int>(n_pairs));
+    const size_t np = (size_t)n_pairs;
+    MM_CUDA(A2.reserve(2 * Arena::pad(8 * np) + 6 * Arena::pad(4 * np) + Arena::pad(cub2)));
+    unsigned long long* keys = A2.take<unsigned long long>(np); unsigned long long* keys_s = A2.take<unsigned long long>(np);
+    int* slot = A2.take<int>(np); int* slot_s = A2.take<int>(np); int* head = A2.take<int>(np); int* incl = A2.take<int>(np); int* pair_lo = A2.take<int>(np); int* pair_hi = A2.take<int>(np);
+    void* tmp2 = A2.take<char>(cub2);
+    if (!tmp2) { set_error("internal: setup arena too small"); return MM_ERR_ALLOC; }
+    k_pair_keys<<<blocks_for(n_pt, B), B, 0, st>>>(n_pt, n_img, s->pt_start.p, s->obs_img.p, s->pair_off.p, keys, pair_lo, pair_hi); MM_LAUNCH_CHECK();
+    k_iota<<<blocks_for(n_pairs, B), B, 0, st>>>((int)n_pairs, slot); MM_LAUNCH_CHECK();
+    int rc = sort_pairs<unsigned long long, int>(st, tmp2, cub2, keys, keys_s, slot, slot_s, n_pairs, bits_pair); if (rc) return rc;
+    k_pair_heads<<<grid_stride(n_pairs, B), B, 0, st>>>(n_pairs, n_img, keys_s, head); MM_LAUNCH_CHECK();
+    rc = inclusive_sum<int>(st, tmp2, cub2, head, incl, n_pairs); if (rc) return rc;
+    MM_CUDA(cudaMemcpyAsync(&n_off, incl + (n_pairs - 1), sizeof(int), cudaMemcpyDeviceToHost, st)); MM_CUDA(cudaStreamSynchronize(st));
     MM_CUDA(blk_a.alloc((size_t)n_off)); MM_CUDA(blk_b.alloc((size_t)n_off));
     MM_CUDA(s->bp_start.alloc((size_t)n_img + n_off)); MM_CUDA(s->bp_end.alloc((size_t)n_img + n_off));
     MM_CUDA(cudaMemsetAsync(s->bp_start.p, 0, sizeof(int) * ((size_t)n_img + n_off), st)); MM_CUDA(cudaMemsetAsync(s->bp_end.p, 0, sizeof(int) * ((size_t)n_img + n_off), st));
-    k_pair_assign<<<grid_stride(n_pairs, B), B, 0, st>>>(n_pairs, n_img, keys_s.p, incl.p, head.p, slot_s.p, blk_a.p, blk_b.p,
-        pair_lo.p, pair_hi.p, s->sp_lo.p, s->sp_hi.p, s->obs_pt.p, s->sp_pt.p, s->bp_start.p, s->bp_end.p); MM_LAUNCH_CHECK();
+    k_pair_assign<<<grid_stride(n_pairs, B), B, 0, st>>>(n_pairs, n_img, keys_s, incl, head, slot_s, blk_a.p, blk_b.p,
+        pair_lo, pair_hi, s->sp_lo.p, s->sp_hi.p, s->obs_pt.p, s->sp_pt.p, s->bp_start.p, s->bp_end.p); MM_LAUNCH_CHECK();
     MM_CUDA(cudaStreamSynchronize(st));
   }
   if (!s->bp_start.p) { MM_CUDA(s->bp_start.alloc((size_t)std::max(n_img, 1))); MM_CUDA(s->bp_end.alloc((size_t)std::max(n_img, 1)));
     MM_CUDA(cudaMemsetAsync(s->bp_start.p, 0, sizeof(int) * (size_t)std::max(n_img, 1), st)); MM_CUDA(cudaMemsetAsync(s->bp_end.p, 0, sizeof(int) * (size_t)std::max(n_img, 1), st)); }
   if (!blk_a.p) { MM_CUDA(blk_a.alloc(1)); MM_CUDA(blk_b.alloc(1)); }
   s->n_off = n_off; s->nblk = (int64_t)n_img + n_off;
-  // 5. block-CSR rows for the SpMV (each off-diagonal block referenced from both rows)
+  SETUP_MARK("structure: pair lists");
+  return MM_OK;
+}
+
+// 5. block-CSR rows for the SpMV (each off-diagonal block referenced from both rows)
+int build_block_csr(mm_ba_session* s) {
+  cudaStream_t st = s->stream; const int n_img = s->n_img, n_off = s->n_off; const int B = 256;
   const int64_t n_ent = (int64_t)n_img + 2 * (int64_t)n_off; s->n_ent = n_ent;
   MM_CUDA(s->row_start.alloc((size_t)n_img + 1)); MM_CUDA(s->row_col.alloc((size_t)n_ent)); MM_CUDA(s->row_blk.alloc((size_t)n_ent));
   if (n_ent > 0) {
-    DevBuf<unsigned long long> keys, keys_s; DevBuf<int> vals, cnt;
-    MM_CUDA(keys.alloc(n_ent)); MM_CUDA(keys_s.alloc(n_ent)); MM_CUDA(vals.alloc(n_ent)); MM_CUDA(cnt.alloc((size_t)n_img + 1));
-    MM_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(int) * ((size_t)n_img + 1), st));
-    k_csr_entries<<<blocks_for(std::max(n_img, n_off), B), B, 0, st>>>(n_img, n_off, blk_a.p, blk_b.p, keys.p, vals.p); MM_LAUNCH_CHECK();
-    int rc = sort_pairs<unsigned long long, int>(st, keys.p, keys_s.p, vals.p, s->row_blk.p, n_ent, bits_for((unsigned long long)n_img * (unsigned long long)n_img)); if (rc) return rc;
-    k_csr_rows<<<grid_stride(n_ent, B), B, 0, st>>>(n_ent, n_img, keys_s.p, s->row_col.p, cnt.p); MM_LAUNCH_CHECK();
-    rc = exclusive_sum<int>(st, cnt.p, s->row_start.p, (int64_t)n_img + 1); if (rc) return rc;
+    Arena A3; const size_t ne = (size_t)n_ent, ni1 = (size_t)n_img + 1;
+    const int bits = bits_for((unsigned long long)n_img * (unsigned long long)n_img);
+    const size_t cub3 = std::max(sort_bytes<unsigned long long, int>(n_ent, bits), scan_bytes<int>((int64_t)ni1));
+    MM_CUDA(A3.reserve(2 * Arena::pad(8 * ne) + Arena::pad(4 * ne) + Arena::pad(4 * ni1) + Arena::pad(cub3)));
+    unsigned long long* keys = A3.take<unsigned long long>(ne); unsigned long long* keys_s = A3.take<unsigned long long>(ne); int* vals = A3.take<int>(ne); int* cnt = A3.take<int>(ni1);
+    void* tmp3 = A3.take<char>(cub3);
+    if (!tmp3) { set_error("internal: setup arena too small"); return MM_ERR_ALLOC; }
+    MM_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * ni1, st));
+    k_csr_entries<<<blocks_for(std::max(n_img, n_off), B), B, 0, st>>>(n_img, n_off, s->blk_a.p, s->blk_b.p, keys, vals); MM_LAUNCH_CHECK();
+    int rc = sort_pairs<unsigned long long, int>(st, tmp3, cub3, keys, keys_s, vals, s->row_blk.p, n_ent, bits); if (rc) return rc;
+    k_csr_rows<<<grid_stride(n_ent, B), B, 0, st>>>(n_ent, n_img, keys_s, s->row_col.p, cnt); MM_LAUNCH_CHECK();
+    rc = exclusive_sum<int>(st, tmp3, cub3, cnt, s->row_start.p, (int64_t)ni1); if (rc) return rc;
+    MM_CUDA(cudaStreamSynchronize(st));
   } else {
     MM_CUDA(cudaMemsetAsync(s->row_start.p, 0, sizeof(int) * ((size_t)n_img + 1), st));
   }
@@ -358,14 +499,17 @@ int build_structure(mm_ba_session* s, const mm_ba_problem* P) {
   return MM_OK;
 }
 
-int upload_params(mm_ba_session* s) {
+// parameters of the first iterate: poses / intrinsics from the session's host copies, points from `pts_host` (caller order)
+// through the renumbering on the device
+int upload_params(mm_ba_session* s, const double* pts_host) {
   cudaStream_t st = s->stream;
   MM_CUDA(cudaMemcpyAsync(s->poses.p, s->h_poses0.data(), sizeof(double) * 6 * (size_t)s->n_img, cudaMemcpyHostToDevice, st));
   MM_CUDA(cudaMemcpyAsync(s->intr.p, s->h_intr0.data(), sizeof(double) * MM_INTR_STRIDE * (size_t)s->n_cam, cudaMemcpyHostToDevice, st));
   MM_CUDA(cudaMemcpyAsync(s->intr2.p, s->h_intr0.data(), sizeof(double) * MM_INTR_STRIDE * (size_t)s->n_cam, cudaMemcpyHostToDevice, st));
-  { std::vector<double> tmp(3 * (size_t)s->n_pt);
-    for (int p = 0; p < s->n_pt; ++p) { const size_t o = (size_t)s->h_pt_new2old[p]; tmp[3 * (size_t)p] = s->h_pts0[3 * o]; tmp[3 * (size_t)p + 1] = s->h_pts0[3 * o + 1]; tmp[3 * (size_t)p + 2] = s->h_pts0[3 * o + 2]; }
-    MM_CUDA(cudaMemcpy(s->pts.p, tmp.data(), sizeof(double) * 3 * (size_t)s->n_pt, cudaMemcpyHostToDevice)); }
+  if (s->n_pt > 0) {      // pts2 (the candidate buffer) is free before the first iteration: staging in caller order
+    MM_CUDA(upload_async(s->pts2.p, pts_host, sizeof(double) * 3 * (size_t)s->n_pt, st));
+    k_gather_rows3<<<blocks_for(s->n_pt, 256), 256, 0, st>>>(s->n_pt, s->pt_new2old.p, s->pts2.p, s->pts.p); MM_LAUNCH_CHECK();
+  }
   return MM_OK;
 }
 
@@ -451,6 +595,10 @@ int build_shard(mm_ba_session* s) {
 int build_coarse_basis(mm_ba_session* s) {
   if (!s->cm) return MM_OK;
   const int n = s->n_img;
+  if (s->h_pose_mask.size() != 6 * (size_t)n) {
+    s->h_pose_mask.resize(6 * (size_t)n);
+    MM_CUDA(cudaMemcpyAsync(s->h_pose_mask.data(), s->pose_mask.p, sizeof(double) * 6 * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+  }
   std::vector<double> sc(6 * (size_t)n), P((size_t)PCS * n, 0.0), R(9 * (size_t)n), M(9 * (size_t)n), C(3 * (size_t)n), cen(3 * (size_t)s->n_agg, 0.0);
   std::vector<int> cnt((size_t)s->n_agg, 0);
   MM_CUDA(cudaMemcpyAsync(sc.data(), s->scale_c.p, sizeof(double) * sc.size(), cudaMemcpyDeviceToHost, s->stream));
@@ -627,41 +775,16 @@ int tc_upload(DevBuf<T>& d, const std::vector<U>& h) {
   if (!h.empty()) MM_CUDA(cudaMemcpy(d.p, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice));
   return MM_OK;
 }
-int build_tilechol(mm_ba_session* s) {
-  s->tc_on = false;
-  const int pre = s->opt.pcg_preconditioner;
-  const char* env = getenv("MM_PCG_PRECOND");               // "twolevel" | "tilechol" overrides the option (experiments)
-  const bool force_two = (env && !strcmp(env, "twolevel")) || (!env && pre == MM_PRECOND_TWO_LEVEL);
-  const bool force_tc = (env && !strcmp(env, "tilechol")) || (!env && pre == MM_PRECOND_TILE_CHOLESKY);
-  if (s->n_img <= 0 || s->n_obs == 0) return MM_OK;
-  if (force_two && !s->refine) return MM_OK;
-  if (!s->refine && !force_tc && s->n_img <= DENSE_MAX_IMG) return MM_OK;          // dense Cholesky in one CTA
+// host part (no CUDA calls: runs on a worker thread): symbolic analysis + the packed copies of the plan
+void tc_plan_host(mm_ba_session* s) {
   const int n = s->n_img;
-  std::vector<int> ha((size_t)std::max(s->n_off, 1)), hb((size_t)std::max(s->n_off, 1));
-  if (s->n_off > 0) {
-    MM_CUDA(cudaMemcpy(ha.data(), s->blk_a.p, sizeof(int) * (size_t)s->n_off, cudaMemcpyDeviceToHost));
-    MM_CUDA(cudaMemcpy(hb.data(), s->blk_b.p, sizeof(int) * (size_t)s->n_off, cudaMemcpyDeviceToHost));
-  }
-  // camera centres C = -R' t guide the dissection
-  std::vector<double> pos(3 * (size_t)n);
-  for (int i = 0; i < n; ++i) {
-    const double* p = s->h_poses0.data() + 6 * (size_t)i; double R[9], Jl[9];
-    rotation_and_left_jacobian(p, R, Jl);
-    for (int q = 0; q < 3; ++q) pos[3 * (size_t)i + q] = -(R[q] * p[3] + R[3 + q] * p[4] + R[6 + q] * p[5]);
-  }
-  s->ncb = s->refine ? s->n_cam : 0;
   TileCholPlan& P = s->tc_plan;
-  const int prc = build_tilechol_plan(n, s->n_off, ha.data(), hb.data(), getenv("MM_TC_NO_GEOMETRY") ? nullptr : pos.data(), s->ncb, P);
-  if (prc != 0) { set_error("tile Cholesky plan failed (%d)", prc); return MM_ERR_UNSUPPORTED; }
-  // memory: the tiles of L must fit comfortably beside the Jacobian records
-  size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
-  const size_t need = sizeof(double) * TC_TT * ((size_t)P.n_l + 2 * (size_t)P.n_w);
-  if (need > free_b / 2 && !force_tc && !s->refine) { P = TileCholPlan(); return MM_OK; }          // falls back to the two-level PCG
-  // packed device copies (layouts: TcDev in tilechol.cuh)
+  s->tc_plan_rc = build_tilechol_plan(n, s->n_off, s->tc_ha.data(), s->tc_hb.data(), getenv("MM_TC_NO_GEOMETRY") ? nullptr : s->tc_pos.data(), s->ncb, P);
+  if (s->tc_plan_rc != 0) return;
   const size_t n_tasks = (size_t)(P.n_l + P.n_wtask);
-  if (P.n_upd + P.n_wupd >= ((int64_t)1 << 31) || (int64_t)P.it_mat.size() >= ((int64_t)1 << 31)) { set_error("tile Cholesky plan too large"); return MM_ERR_UNSUPPORTED; }
-  std::vector<int> sched(8 * n_tasks), sdesc(16 * (size_t)P.n_stasks, 0);
-  std::vector<int4> upd((size_t)(P.n_upd + P.n_wupd)); std::vector<int2> items(P.it_mat.size());
+  if (P.n_upd + P.n_wupd >= ((int64_t)1 << 31) || (int64_t)P.it_mat.size() >= ((int64_t)1 << 31)) { s->tc_plan_rc = -100; return; }
+  std::vector<int>& sched = s->tc_h_sched; std::vector<int>& sdesc = s->tc_h_sdesc; std::vector<int4>& upd = s->tc_h_upd; std::vector<int2>& items = s->tc_h_items;
+  sched.assign(8 * n_tasks, 0); sdesc.assign(16 * (size_t)P.n_stasks, 0); upd.resize((size_t)(P.n_upd + P.n_wupd)); items.resize(P.it_mat.size());
   for (int64_t u = 0; u < P.n_upd; ++u) upd[u] = make_int4(P.upd_a[u], P.upd_b[u], P.upd_a[u], P.upd_b[u]);
   // flags: [0, n_tasks) one per factor task (a diagonal task sets its flag when L(j,j) is stored), then one per tile row, set when
   // the inverse W(j,j) is stored as well
@@ -690,10 +813,57 @@ int build_tilechol(mm_ba_session* s) {
     for (int q = 0; q < 4 && b + q < e; ++q) { d[8 + 2 * q] = P.it_mat[b + q]; d[9 + 2 * q] = P.it_src[b + q]; }
   }
   for (size_t q = 0; q < items.size(); ++q) items[q] = make_int2(P.it_mat[q], P.it_src[q]);
+}
+// decides whether the session solves through the tile factorisation and starts the symbolic analysis on a host thread
+int tc_begin(mm_ba_session* s) {
+  s->tc_on = false; s->tc_plan_rc = 1;           // 1 = not attempted
+  const int pre = s->opt.pcg_preconditioner;
+  const char* env = getenv("MM_PCG_PRECOND");               // "twolevel" | "tilechol" overrides the option (experiments)
+  const bool force_two = (env && !strcmp(env, "twolevel")) || (!env && pre == MM_PRECOND_TWO_LEVEL);
+  const bool force_tc = (env && !strcmp(env, "tilechol")) || (!env && pre == MM_PRECOND_TILE_CHOLESKY);
+  s->tc_force = force_tc;
+  if (s->n_img <= 0 || s->n_obs == 0) return MM_OK;
+  if (force_two && !s->refine) return MM_OK;
+  if (!s->refine && !force_tc && s->n_img <= DENSE_MAX_IMG) return MM_OK;          // dense Cholesky in one CTA
+  const int n = s->n_img;
+  s->tc_ha.assign((size_t)std::max(s->n_off, 1), 0); s->tc_hb.assign((size_t)std::max(s->n_off, 1), 0);
+  if (s->n_off > 0) {
+    MM_CUDA(cudaMemcpyAsync(s->tc_ha.data(), s->blk_a.p, sizeof(int) * (size_t)s->n_off, cudaMemcpyDeviceToHost, s->stream));
+    MM_CUDA(cudaMemcpyAsync(s->tc_hb.data(), s->blk_b.p, sizeof(int) * (size_t)s->n_off, cudaMemcpyDeviceToHost, s->stream));
+    MM_CUDA(cudaStreamSynchronize(s->stream));
+  }
+  // camera centres C = -R' t guide the dissection
+  s->tc_pos.resize(3 * (size_t)n);
+  for (int i = 0; i < n; ++i) {
+    const double* p = s->h_poses0.data() + 6 * (size_t)i; double R[9], Jl[9];
+    rotation_and_left_jacobian(p, R, Jl);
+    for (int q = 0; q < 3; ++q) s->tc_pos[3 * (size_t)i + q] = -(R[q] * p[3] + R[3 + q] * p[4] + R[6 + q] * p[5]);
+  }
+  s->ncb = s->refine ? s->n_cam : 0;
+  s->tc_plan_rc = 2;                              // 2 = running
+  if (getenv("MM_TC_PLAN_INLINE")) tc_plan_host(s); else s->tc_thread = std::thread(tc_plan_host, s);
+  return MM_OK;
+}
+// joins the analysis and puts the plan on the device.  *fallback = true: the session goes on with the two-level preconditioner
+int tc_finish(mm_ba_session* s, bool* fallback) {
+  *fallback = false;
+  if (s->tc_thread.joinable()) s->tc_thread.join();
+  if (s->tc_plan_rc == 1) { *fallback = true; return MM_OK; }
+  s->tc_ha = std::vector<int>(); s->tc_hb = std::vector<int>(); s->tc_pos = std::vector<double>();
+  TileCholPlan& P = s->tc_plan;
+  if (s->tc_plan_rc != 0) { set_error("tile Cholesky plan failed (%d)", s->tc_plan_rc); return MM_ERR_UNSUPPORTED; }
+  SETUP_MARK("tilechol: wait for the host plan");
+  // memory: the tiles of L must fit comfortably beside the Jacobian records
+  size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
+  const size_t need = sizeof(double) * TC_TT * ((size_t)P.n_l + 2 * (size_t)P.n_w);
+  if (need > free_b / 2 && !s->tc_force && !s->refine) { P = TileCholPlan(); *fallback = true; return MM_OK; }          // falls back to the two-level PCG
+  const int n = s->n_img;
+  const size_t n_tasks = (size_t)(P.n_l + P.n_wtask);
   int rc;
   if ((rc = tc_upload(s->tc_unk_of, P.unk_of)) || (rc = tc_upload(s->tc_sc_tile, P.sc_tile)) || (rc = tc_upload(s->tc_sc_off, P.sc_off)) || (rc = tc_upload(s->tc_a_tiles, P.a_tiles)) ||
       (rc = tc_upload(s->tc_img_tile, P.img_tile)) || (rc = tc_upload(s->tc_img_slot, P.img_slot)) || (rc = tc_upload(s->tc_col_ptr, P.col_ptr)) ||
-      (rc = tc_upload(s->tc_sched, sched)) || (rc = tc_upload(s->tc_sdesc, sdesc)) || (rc = tc_upload(s->tc_upd, upd)) || (rc = tc_upload(s->tc_items, items))) return rc;
+      (rc = tc_upload(s->tc_sched, s->tc_h_sched)) || (rc = tc_upload(s->tc_sdesc, s->tc_h_sdesc)) || (rc = tc_upload(s->tc_upd, s->tc_h_upd)) || (rc = tc_upload(s->tc_items, s->tc_h_items))) return rc;
+  s->tc_h_sched = std::vector<int>(); s->tc_h_sdesc = std::vector<int>(); s->tc_h_upd = std::vector<int4>(); s->tc_h_items = std::vector<int2>();
   MM_CUDA(s->tc_L.alloc((size_t)TC_TT * (size_t)P.n_l)); MM_CUDA(s->tc_WC.alloc((size_t)TC_TT * (size_t)P.n_w)); MM_CUDA(s->tc_WR.alloc((size_t)TC_TT * (size_t)P.n_w));
   MM_CUDA(s->tc_slots.alloc((size_t)TC_T * (size_t)P.n_slots));
   MM_CUDA(s->tc_ready.alloc(n_tasks + (size_t)P.nt)); MM_CUDA(s->tc_sflag.alloc((size_t)P.n_slots)); MM_CUDA(s->tc_counters.alloc(4)); MM_CUDA(s->tc_invd.alloc((size_t)TC_T * P.nt));
@@ -718,6 +888,7 @@ int build_tilechol(mm_ba_session* s) {
   const int apply_per_sm = getenv("MM_TC_APPLY_CTAS") ? std::max(1, atoi(getenv("MM_TC_APPLY_CTAS"))) : 4;
   s->tc_grid_s = std::max(1, std::min(std::min(std::max(1, per_sm_s), apply_per_sm) * num_sms(), P.n_stasks));
   s->tc_on = true; s->tc_epoch = 0; s->tc_sepoch = 0;
+  SETUP_MARK("tilechol: upload + tiles");
   return MM_OK;
 }
 // assembly of S (and the intrinsics border) into the tiles + numeric factorisation
@@ -996,41 +1167,40 @@ void mm_ba_options_default(mm_ba_options* o) {
 
 void mm_ba_session_destroy(mm_ba_session* s) {
   if (!s) return;
+  if (s->tc_thread.joinable()) s->tc_thread.join();
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   for (int i = 0; i < 8; ++i) if (s->evs[i]) cudaEventDestroy(s->evs[i]);
   delete s;
 }
 
-int mm_ba_session_create(const mm_ba_problem* P, const mm_ba_options* opt, void* stream, mm_ba_session** out) {
-  return mm_ba_session_create_sharded(P, opt, stream, 0, 1, nullptr, nullptr, out);
-}
-
-int mm_ba_session_create_sharded(const mm_ba_problem* P, const mm_ba_options* opt, void* stream, int32_t rank, int32_t world,
-                                 mm_allreduce_fn allreduce, void* user, mm_ba_session** out) {
+namespace {
+int session_create(const mm_ba_problem* P, const mm_ba_options* opt, void* stream, int32_t rank, int32_t world,
+                   mm_allreduce_fn allreduce, void* user, bool keep_host_pts, mm_ba_session** out) {
   if (!out || !opt) { set_error("null argument"); return MM_ERR_INVALID_ARG; }
   *out = nullptr;
   if (world < 1 || rank < 0 || rank >= world || (world > 1 && !allreduce)) { set_error("invalid shard (rank %d of %d) or missing all-reduce callback", rank, world); return MM_ERR_INVALID_ARG; }
   int rc = validate_problem(P); if (rc) return rc;
   if (opt->linear_solver != MM_SOLVER_PCG) { set_error("the device engine solves the reduced system with PCG only"); return MM_ERR_UNSUPPORTED; }
+  std::vector<char> cam_used((size_t)std::max(P->n_cam, 1), 0);
+  for (int i = 0; i < P->n_img; ++i) cam_used[P->img_cam[i]] = 1;
   bool refine = false;
-  for (int c = 0; c < P->n_cam; ++c) if (!P->intr_const[c]) {
-    bool used = false; for (int i = 0; i < P->n_img; ++i) if (P->img_cam[i] == c) used = true;
-    if (used) refine = true;
-  }
+  for (int c = 0; c < P->n_cam; ++c) if (!P->intr_const[c] && cam_used[c]) refine = true;
   if (refine && P->n_cam > 32) { set_error("refine_camera_params handles up to 32 cameras (got %d)", P->n_cam); return MM_ERR_UNSUPPORTED; }
   rc = ensure_device(); if (rc) return rc;
+  const double t_enter = SetupClock::now();
   mm_ba_session* s = new mm_ba_session();
-  s->stream = (cudaStream_t)stream; s->opt = *opt;
+  s->stream = (cudaStream_t)stream; s->opt = *opt; s->keep_host_pts = keep_host_pts;
   s->n_img = P->n_img; s->n_cam = P->n_cam; s->n_pt = P->n_pt; s->n_obs = P->n_obs; s->refine = refine;
   s->rank = rank; s->world = world; s->ar = allreduce; s->ar_user = user;
   auto fail_out = [&](int code) { mm_ba_session_destroy(s); return code; };
   if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess) { set_error("cudaEventCreate failed"); return fail_out(MM_ERR_CUDA); }
   for (int i = 0; i < 8; ++i) if (cudaEventCreate(&s->evs[i]) != cudaSuccess) { set_error("cudaEventCreate failed"); return fail_out(MM_ERR_CUDA); }
-  float ms = 0; cudaEventRecord(s->ev0, s->stream);
+  SetupClock clk(s->stream);
+  struct ClockScope { ClockScope(SetupClock* c) { g_setup_clock = c->on ? c : nullptr; } ~ClockScope() { g_setup_clock = nullptr; } } clock_scope(&clk);
   s->h_poses0.assign(P->poses, P->poses + 6 * (size_t)P->n_img);
   s->h_intr0.assign(P->intr, P->intr + MM_INTR_STRIDE * (size_t)P->n_cam);
-  s->h_pts0.assign(P->pts, P->pts + 3 * (size_t)P->n_pt);
+  if (keep_host_pts) s->h_pts0.assign(P->pts, P->pts + 3 * (size_t)P->n_pt);      // (mm_ba_session_reset starts again from them)
   const size_t n_img = (size_t)std::max(P->n_img, 1), n_pt = (size_t)std::max(P->n_pt, 1), n_cam = (size_t)std::max(P->n_cam, 1);
 #define A(buf, count) do { if ((buf).alloc(count) != cudaSuccess) { set_error("cudaMalloc failed for " #buf); cudaGetLastError(); return fail_out(MM_ERR_ALLOC); } } while (0)
   A(s->poses, 6 * n_img); A(s->poses2, 6 * n_img); A(s->intr, MM_INTR_STRIDE * n_cam); A(s->pts, 3 * n_pt); A(s->pts2, 3 * n_pt);
@@ -1058,22 +1228,9 @@ int mm_ba_session_create_sharded(const mm_ba_problem* P, const mm_ba_options* op
   }
   { // free intrinsics: the parameters of the camera's model, for cameras that are used and not held constant
     std::vector<double> im(9 * n_cam, 0.0), ones(9 * n_cam, 1.0);
-    for (int c = 0; c < P->n_cam; ++c) {
-      bool used = false; for (int i = 0; i < P->n_img; ++i) if (P->img_cam[i] == c) used = true;
-      if (refine && used && !P->intr_const[c]) for (int k = 0; k < model_num_params(P->cam_model[c]); ++k) im[9 * (size_t)c + k] = 1.0;
-    }
-    if (cudaMemcpy(s->intr_mask.p, im.data(), sizeof(double) * im.size(), cudaMemcpyHostToDevice) != cudaSuccess || cudaMemcpy(s->scale_i.p, ones.data(), sizeof(double) * ones.size(), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("mask upload failed"); return fail_out(MM_ERR_CUDA); } }
-  // masks: 1.0 = free and present in at least one residual block
-  { std::vector<int> img_n(n_img, 0), pt_n(n_pt, 0);
-    for (int64_t o = 0; o < P->n_obs; ++o) { img_n[P->obs_img[o]]++; pt_n[P->obs_pt[o]]++; }
-    std::vector<double> pm(6 * n_img, 0.0); std::vector<double>& tm = s->h_pt_mask; tm.assign(n_pt, 0.0);
-    for (int i = 0; i < P->n_img; ++i) if (img_n[i]) {
-      for (int k = 0; k < 3; ++k) pm[6 * (size_t)i + k] = P->pose_const[4 * (size_t)i] ? 0.0 : 1.0;
-      for (int k = 0; k < 3; ++k) pm[6 * (size_t)i + 3 + k] = P->pose_const[4 * (size_t)i + 1 + k] ? 0.0 : 1.0;
-    }
-    for (int p = 0; p < P->n_pt; ++p) if (pt_n[p] && !P->pt_const[p]) tm[p] = 1.0;
-    s->h_pose_mask = pm;
-    if (cudaMemcpy(s->pose_mask.p, pm.data(), sizeof(double) * pm.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+    for (int c = 0; c < P->n_cam; ++c)
+      if (refine && cam_used[c] && !P->intr_const[c]) for (int k = 0; k < model_num_params(P->cam_model[c]); ++k) im[9 * (size_t)c + k] = 1.0;
+    if (cudaMemcpy(s->intr_mask.p, im.data(), sizeof(double) * im.size(), cudaMemcpyHostToDevice) != cudaSuccess || cudaMemcpy(s->scale_i.p, ones.data(), sizeof(double) * ones.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(s->img_cam.p, P->img_cam, sizeof(int) * (size_t)P->n_img, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(s->cam_model.p, P->cam_model, sizeof(int) * (size_t)P->n_cam, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("mask upload failed"); return fail_out(MM_ERR_CUDA); } }
   if (P->rot_prior && P->rot_prior_w) {
@@ -1087,9 +1244,14 @@ int mm_ba_session_create_sharded(const mm_ba_problem* P, const mm_ba_options* op
   cudaMemsetAsync(s->fail.p, 0, sizeof(int), s->stream);
   cudaMemsetAsync(s->red.p, 0, sizeof(double) * 8, s->stream);
   cudaMemsetAsync(s->loc.p, 0, sizeof(double) * 8, s->stream);
+  SETUP_MARK("allocations");
+  // structure on the device (also: index check, masks, point renumbering); the symbolic analysis of the tile Cholesky starts
+  // on a host thread as soon as the block list of the reduced system exists and runs beside everything up to the first solve
   rc = build_structure(s, P); if (rc) return fail_out(rc);
-  rc = build_tilechol(s); if (rc) return fail_out(rc);
-  rc = s->tc_on ? MM_OK : build_aggregates(s); if (rc) return fail_out(rc);
+  rc = tc_begin(s); if (rc) return fail_out(rc);
+  SETUP_MARK("tilechol: block list -> host thread");
+  rc = build_block_csr(s); if (rc) return fail_out(rc);
+  if (s->tc_plan_rc == 1) { rc = build_aggregates(s); if (rc) return fail_out(rc); }      // no tile factorisation for this session
   rc = build_shard(s); if (rc) return fail_out(rc);
   A(s->rec, (size_t)REC * (size_t)std::max<int64_t>(s->no_loc(), 1));
   if (refine) { A(s->ji, 18 * (size_t)std::max<int64_t>(s->no_loc(), 1)); A(s->Apc, 27 * n_pt * n_cam); A(s->pt_cam_mask, n_pt); }
@@ -1100,22 +1262,41 @@ int mm_ba_session_create_sharded(const mm_ba_problem* P, const mm_ba_options* op
     A(s->xch, s->xch_count);
     s->S.view(s->xch.p, nS); s->rhs.view(s->xch.p + nS, nv); s->gc.view(s->xch.p + nS + nv, nv); s->ud.view(s->xch.p + nS + 2 * nv, nv);
     cudaMemsetAsync(s->xch.p, 0, sizeof(double) * s->xch_count, s->stream); }
-  { std::vector<double> tmp((size_t)std::max(P->n_pt, 1), 0.0);
-    for (int p = 0; p < P->n_pt; ++p) tmp[p] = s->h_pt_mask[(size_t)s->h_pt_new2old[p]];
-    if (cudaMemcpy(s->pt_mask.p, tmp.data(), sizeof(double) * tmp.size(), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("mask upload failed"); return fail_out(MM_ERR_CUDA); } }
 #undef A
-  rc = upload_params(s); if (rc) return fail_out(rc);
+  rc = upload_params(s, P->pts); if (rc) return fail_out(rc);
+  SETUP_MARK("block CSR + records + parameters");
   memset(&s->sum, 0, sizeof s->sum);
-  cudaEventRecord(s->ev1, s->stream); cudaEventSynchronize(s->ev1); cudaEventElapsedTime(&ms, s->ev0, s->ev1);
   rc = lm_start(s); if (rc) return fail_out(rc);
-  s->sum.ms_setup = ms;
+  SETUP_MARK("lm_start (first linearisation)");
+  { bool fallback = false;
+    rc = tc_finish(s, &fallback); if (rc) return fail_out(rc);
+    if (fallback && s->tc_plan_rc != 1 && !s->finished) {
+      // (rare) the tile factorisation was dropped after the first linearisation: two-level preconditioner on the assembled system
+      if ((rc = build_aggregates(s)) || (rc = build_coarse_basis(s))) return fail_out(rc);
+      k_precond<<<blocks_for(s->n_img, 64), 64, 0, s->stream>>>(s->n_img, s->S.p, s->Minv.p, s->fail.p); count_launch();
+      if ((rc = launch_coarse_setup(s))) return fail_out(rc);
+      s->coarse_iter = s->iter; s->coarse_radius = s->radius;
+    } }
+  MM_CUDA(cudaStreamSynchronize(s->stream));
+  s->sum.ms_setup = std::max(0.0, SetupClock::now() - t_enter - s->sum.ms_linearize - s->sum.ms_schur);
   *out = s;
   return MM_OK;
+}
+}  // namespace
+
+int mm_ba_session_create(const mm_ba_problem* P, const mm_ba_options* opt, void* stream, mm_ba_session** out) {
+  return session_create(P, opt, stream, 0, 1, nullptr, nullptr, true, out);
+}
+
+int mm_ba_session_create_sharded(const mm_ba_problem* P, const mm_ba_options* opt, void* stream, int32_t rank, int32_t world,
+                                 mm_allreduce_fn allreduce, void* user, mm_ba_session** out) {
+  return session_create(P, opt, stream, rank, world, allreduce, user, true, out);
 }
 
 int mm_ba_session_reset(mm_ba_session* s) {
   if (!s) return MM_ERR_INVALID_ARG;
-  int rc = upload_params(s); if (rc) return rc;
+  if (!s->keep_host_pts) { set_error("this session keeps no host copy of the initial points"); return MM_ERR_UNSUPPORTED; }
+  int rc = upload_params(s, s->h_pts0.data()); if (rc) return rc;
   const double setup = s->sum.ms_setup;
   rc = lm_start(s);
   s->sum.ms_setup = setup;
@@ -1242,7 +1423,8 @@ int mm_debug_tilechol_solve(int32_t n_img, int32_t n_off, const int32_t* blk_a, 
     MM_CUDA(cudaMemcpy(s->Bm.p, Bm, sizeof(double) * 54 * (size_t)n_img * ncb, cudaMemcpyHostToDevice));
     MM_CUDA(cudaMemcpy(s->intr_acc.p, Cm, sizeof(double) * 81 * (size_t)ncb * ncb, cudaMemcpyHostToDevice));
   }
-  rc = build_tilechol(s); if (rc) return rc;
+  rc = tc_begin(s); if (rc) return rc;
+  { bool fallback = false; rc = tc_finish(s, &fallback); if (rc) return rc; }
   if (!s->tc_on) { set_error("tile Cholesky not enabled"); return MM_ERR_UNSUPPORTED; }
   DevBuf<double> d_r, d_z; MM_CUDA(d_r.alloc((size_t)s->n_unk)); MM_CUDA(d_z.alloc((size_t)s->n_unk));
   MM_CUDA(cudaMemcpy(d_r.p, rhs, sizeof(double) * (size_t)s->n_unk, cudaMemcpyHostToDevice));
@@ -1286,23 +1468,21 @@ int mm_ba_session_download(mm_ba_session* s, double* poses, double* intr, double
     if (s->p_hi < s->n_pt) MM_CUDA(cudaMemsetAsync(s->pts.p + 3 * (size_t)s->p_hi, 0, sizeof(double) * 3 * (size_t)(s->n_pt - s->p_hi), st));
     int rc = all_reduce(s, s->pts.p, 3 * (size_t)s->n_pt); if (rc) return rc;
   }
+  // pts2 (candidate buffer) and Vinv are free between LM iterations: staging for the caller's point order
   if (pts && s->n_pt > 0) {
-    std::vector<double> tmp(3 * (size_t)s->n_pt);
-    MM_CUDA(cudaMemcpyAsync(tmp.data(), s->pts.p, sizeof(double) * 3 * (size_t)s->n_pt, cudaMemcpyDeviceToHost, st));
-    MM_CUDA(cudaStreamSynchronize(st));
-    for (int p = 0; p < s->n_pt; ++p) { const size_t o = (size_t)s->h_pt_new2old[p]; pts[3 * o] = tmp[3 * (size_t)p]; pts[3 * o + 1] = tmp[3 * (size_t)p + 1]; pts[3 * o + 2] = tmp[3 * (size_t)p + 2]; }
+    k_scatter_rows3<<<blocks_for(s->n_pt, 256), 256, 0, st>>>(s->n_pt, s->pt_new2old.p, s->pts.p, s->pts2.p); MM_LAUNCH_CHECK();
+    MM_CUDA(cudaMemcpyAsync(pts, s->pts2.p, sizeof(double) * 3 * (size_t)s->n_pt, cudaMemcpyDeviceToHost, st));
   }
   if (pt_err && s->n_pt > 0 && s->n_obs > 0) {
-    // Vinv is free between LM iterations: reuse it as the staging buffer for the per-point errors
-    std::vector<double> host((size_t)s->n_pt);
-    for (int p = 0; p < s->n_pt; ++p) host[p] = pt_err[(size_t)s->h_pt_new2old[p]];
-    MM_CUDA(cudaMemcpyAsync(s->Vinv.p, host.data(), sizeof(double) * (size_t)s->n_pt, cudaMemcpyHostToDevice, st));
+    double* e_int = s->Vinv.p; double* e_ext = s->Vinv.p + (size_t)s->n_pt;       // internal order | caller order
+    MM_CUDA(cudaMemcpyAsync(e_ext, pt_err, sizeof(double) * (size_t)s->n_pt, cudaMemcpyHostToDevice, st));
+    k_gather_rows1<<<blocks_for(s->n_pt, 256), 256, 0, st>>>(s->n_pt, s->pt_new2old.p, e_ext, e_int); MM_LAUNCH_CHECK();
     k_pose_aux<<<blocks_for(s->n_img, 128), 128, 0, st>>>(s->n_img, s->poses.p, s->pose_mask.p, s->aux.p); MM_LAUNCH_CHECK();
     k_point_errors<<<blocks_for(s->n_pt, 128), 128, 0, st>>>(s->n_pt, s->pt_start.p, s->obs_xy.p, s->obs_img.p, s->aux.p, s->pts.p, s->intr.p,
-        s->img_cam.p, s->cam_model.p, s->Vinv.p); MM_LAUNCH_CHECK();     // (all points are current on every rank after the gather above)
-    MM_CUDA(cudaMemcpyAsync(host.data(), s->Vinv.p, sizeof(double) * (size_t)s->n_pt, cudaMemcpyDeviceToHost, st));
+        s->img_cam.p, s->cam_model.p, e_int); MM_LAUNCH_CHECK();     // (all points are current on every rank after the gather above)
+    k_scatter_rows1<<<blocks_for(s->n_pt, 256), 256, 0, st>>>(s->n_pt, s->pt_new2old.p, e_int, e_ext); MM_LAUNCH_CHECK();
+    MM_CUDA(cudaMemcpyAsync(pt_err, e_ext, sizeof(double) * (size_t)s->n_pt, cudaMemcpyDeviceToHost, st));
     MM_CUDA(cudaStreamSynchronize(st));
-    for (int p = 0; p < s->n_pt; ++p) pt_err[(size_t)s->h_pt_new2old[p]] = host[p];
     // the Schur data must be rebuilt if the session continues
     if (!s->finished) { int rc = launch_schur(s); if (rc) return rc; }
   }
@@ -1344,7 +1524,7 @@ int mm_ba_session_time_kernel(mm_ba_session* s, int32_t which, int32_t reps, dou
 int mm_ba_solve(mm_ba_problem* P, const mm_ba_options* opt, mm_ba_summary* summary) {
   if (!P || !opt) { set_error("null argument"); return MM_ERR_INVALID_ARG; }
   mm_ba_session* s = nullptr;
-  int rc = mm_ba_session_create(P, opt, nullptr, &s); if (rc) return rc;
+  int rc = session_create(P, opt, nullptr, 0, 1, nullptr, nullptr, false, &s); if (rc) return rc;
   int32_t done = 0;
   rc = mm_ba_session_iterate(s, opt->max_num_iterations + 1, &done);
   if (rc == MM_OK) rc = mm_ba_session_download(s, P->poses, P->intr, P->pts, P->pt_err);
