@@ -60,9 +60,11 @@ __global__ void k_iota(int n, int* out) { const int i = blockIdx.x * blockDim.x 
 __global__ void k_hist(int64_t n, const int* __restrict__ keys, int* __restrict__ cnt) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) atomicAdd(cnt + keys[i], 1);
 }
-__global__ void k_gather_obs(int64_t n, const int* __restrict__ perm, const double2* __restrict__ xy_in, const int* __restrict__ img_in,
-                             double2* __restrict__ xy, int* __restrict__ img) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) { const int s = perm[i]; xy[i] = xy_in[s]; img[i] = img_in[s]; }
+__global__ void k_gather_img(int64_t n, const int* __restrict__ perm, const int* __restrict__ img_in, int* __restrict__ img) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) img[i] = img_in[perm[i]];
+}
+__global__ void k_gather_xy(int64_t n, const int* __restrict__ perm, const double2* __restrict__ xy_in, double2* __restrict__ xy) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) xy[i] = xy_in[perm[i]];
 }
 __global__ void k_pair_count(int n_pt, const int* __restrict__ pt_start, int64_t* __restrict__ cnt) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -196,6 +198,7 @@ struct mm_ba_session {
   int n_img = 0, n_cam = 0, n_pt = 0; int64_t n_obs = 0;
   int n_off = 0; int64_t nblk = 0, n_pairs = 0, n_ent = 0;
   std::vector<double> h_poses0, h_intr0, h_pts0;
+  DevBuf<int> obs_perm;                                                 // setup only: point-sorted position -> caller's observation index (until the image coordinates are in)
   DevBuf<int> pt_new2old;                                               // internal point order (spatially clustered) -> caller's order
   bool keep_host_pts = true;                                            // mm_ba_solve: no session reset, so no host copy of the points
   DevBuf<double2> obs_xy; DevBuf<int> obs_img, obs_pt, pt_start, cam_perm, cam_start, img_cam, cam_model;
@@ -369,10 +372,11 @@ int build_structure(mm_ba_session* s, const mm_ba_problem* P) {
   size_t cub1 = std::max(std::max(sort_bytes<int, int>(n, bits_pt), sort_bytes<int, int>(n, bits_img)), sort_bytes<unsigned long long, int>(n_pt, bits_key));
   cub1 = std::max(cub1, std::max(scan_bytes<int>((int64_t)np1), scan_bytes<int64_t>((int64_t)np1)));
   { size_t need = 0;
-    const size_t sizes[] = { 16 * n1, 4 * n1, 4 * n1, 4 * n1, 4 * n1, 4 * n1, 4 * np1, 4 * ni1, 8 * np1, 4 * np1, 4 * np1, 4 * np1, 4 * np1, 8 * np1, 8 * np1, np1, 4 * ni1, 256, cub1 };
+    const size_t sizes[] = { 4 * n1, 4 * n1, 4 * n1, 4 * n1, 4 * np1, 4 * ni1, 8 * np1, 4 * np1, 4 * np1, 4 * np1, 4 * np1, 8 * np1, 8 * np1, np1, 4 * ni1, 256, cub1 };
     for (size_t b : sizes) need += Arena::pad(b);
     MM_CUDA(A1.reserve(need)); }
-  double2* xy_in = A1.take<double2>(n1); int* img_in = A1.take<int>(n1); int* pt_in = A1.take<int>(n1); int* perm = A1.take<int>(n1); int* iota = A1.take<int>(n1);
+  int* img_in = A1.take<int>(n1); int* pt_in = A1.take<int>(n1); int* iota = A1.take<int>(n1);
+  MM_CUDA(s->obs_perm.alloc(n1)); int* perm = s->obs_perm.p;
   int* keys_out = A1.take<int>(n1); int* cnt_pt = A1.take<int>(np1); int* cnt_img = A1.take<int>(ni1); int64_t* cnt64 = A1.take<int64_t>(np1);
   int* mn = A1.take<int>(np1); int* mx = A1.take<int>(np1); int* ids = A1.take<int>(np1); int* old2new = A1.take<int>(np1);
   unsigned long long* key = A1.take<unsigned long long>(np1); unsigned long long* key_s = A1.take<unsigned long long>(np1);
@@ -383,7 +387,6 @@ int build_structure(mm_ba_session* s, const mm_ba_problem* P) {
   if (n > 0) {
     MM_CUDA(upload_async(img_in, P->obs_img, sizeof(int) * n, st));
     MM_CUDA(upload_async(pt_in, P->obs_pt, sizeof(int) * n, st));
-    MM_CUDA(upload_async(xy_in, P->obs_xy, sizeof(double2) * n, st));
   }
   if (n_pt > 0) MM_CUDA(upload_async(pt_const, P->pt_const, (size_t)n_pt, st));
   if (n_img > 0) MM_CUDA(cudaMemcpyAsync(pose_const, P->pose_const, 4 * (size_t)n_img, cudaMemcpyHostToDevice, st));
@@ -413,7 +416,7 @@ int build_structure(mm_ba_session* s, const mm_ba_problem* P) {
     k_iota<<<blocks_for(n, B), B, 0, st>>>((int)n, iota); MM_LAUNCH_CHECK();
     // 1. stable sort by point (keeps the caller's order inside a track)
     int rc = sort_pairs<int, int>(st, cub_tmp, cub1, pt_in, s->obs_pt.p, iota, perm, n, bits_pt); if (rc) return rc;
-    k_gather_obs<<<grid_stride(n, B), B, 0, st>>>(n, perm, xy_in, img_in, s->obs_xy.p, s->obs_img.p); MM_LAUNCH_CHECK();
+    k_gather_img<<<grid_stride(n, B), B, 0, st>>>(n, perm, img_in, s->obs_img.p); MM_LAUNCH_CHECK();
   }
   // 2. point -> observation CSR
   MM_CUDA(cudaMemsetAsync(cnt_pt, 0, sizeof(int) * np1, st));
@@ -470,6 +473,20 @@ int build_structure(mm_ba_session* s, const mm_ba_problem* P) {
   if (!blk_a.p) { MM_CUDA(blk_a.alloc(1)); MM_CUDA(blk_b.alloc(1)); }
   s->n_off = n_off; s->nblk = (int64_t)n_img + n_off;
   SETUP_MARK("structure: pair lists");
+  return MM_OK;
+}
+
+// the image coordinates of the observations are not needed for the structure: they follow once the symbolic analysis of the
+// tile Cholesky is running on its host thread (160 MB at cfg4, the largest part of the upload)
+int upload_obs_xy(mm_ba_session* s, const mm_ba_problem* P) {
+  cudaStream_t st = s->stream; const int64_t n = s->n_obs;
+  if (n > 0) {
+    DevBuf<double2> xy_in; MM_CUDA(xy_in.alloc((size_t)n));
+    MM_CUDA(upload_async(xy_in.p, P->obs_xy, sizeof(double2) * n, st));
+    k_gather_xy<<<grid_stride(n, 256), 256, 0, st>>>(n, s->obs_perm.p, xy_in.p, s->obs_xy.p); MM_LAUNCH_CHECK();
+    MM_CUDA(cudaStreamSynchronize(st));
+  }
+  s->obs_perm.release();
   return MM_OK;
 }
 
@@ -864,10 +881,12 @@ int tc_finish(mm_ba_session* s, bool* fallback) {
       (rc = tc_upload(s->tc_img_tile, P.img_tile)) || (rc = tc_upload(s->tc_img_slot, P.img_slot)) || (rc = tc_upload(s->tc_col_ptr, P.col_ptr)) ||
       (rc = tc_upload(s->tc_sched, s->tc_h_sched)) || (rc = tc_upload(s->tc_sdesc, s->tc_h_sdesc)) || (rc = tc_upload(s->tc_upd, s->tc_h_upd)) || (rc = tc_upload(s->tc_items, s->tc_h_items))) return rc;
   s->tc_h_sched = std::vector<int>(); s->tc_h_sdesc = std::vector<int>(); s->tc_h_upd = std::vector<int4>(); s->tc_h_items = std::vector<int2>();
+  SETUP_MARK("tilechol: plan upload");
   MM_CUDA(s->tc_L.alloc((size_t)TC_TT * (size_t)P.n_l)); MM_CUDA(s->tc_WC.alloc((size_t)TC_TT * (size_t)P.n_w)); MM_CUDA(s->tc_WR.alloc((size_t)TC_TT * (size_t)P.n_w));
   MM_CUDA(s->tc_slots.alloc((size_t)TC_T * (size_t)P.n_slots));
   MM_CUDA(s->tc_ready.alloc(n_tasks + (size_t)P.nt)); MM_CUDA(s->tc_sflag.alloc((size_t)P.n_slots)); MM_CUDA(s->tc_counters.alloc(4)); MM_CUDA(s->tc_invd.alloc((size_t)TC_T * P.nt));
   MM_CUDA(cudaMemset(s->tc_ready.p, 0, sizeof(int) * (n_tasks + (size_t)P.nt))); MM_CUDA(cudaMemset(s->tc_sflag.p, 0, sizeof(int) * (size_t)P.n_slots));
+  SETUP_MARK("tilechol: tile allocation");
   s->n_unk = 6 * n + 9 * s->ncb;
   MM_CUDA(s->dv_b.alloc((size_t)s->n_unk)); MM_CUDA(s->dv_r.alloc((size_t)s->n_unk)); MM_CUDA(s->dv_z.alloc((size_t)s->n_unk)); MM_CUDA(s->dv_p.alloc((size_t)s->n_unk)); MM_CUDA(s->dv_Ap.alloc((size_t)s->n_unk));
   TcDev& D = s->tc;
@@ -1250,6 +1269,8 @@ int session_create(const mm_ba_problem* P, const mm_ba_options* opt, void* strea
   rc = build_structure(s, P); if (rc) return fail_out(rc);
   rc = tc_begin(s); if (rc) return fail_out(rc);
   SETUP_MARK("tilechol: block list -> host thread");
+  rc = upload_obs_xy(s, P); if (rc) return fail_out(rc);
+  SETUP_MARK("image coordinates");
   rc = build_block_csr(s); if (rc) return fail_out(rc);
   if (s->tc_plan_rc == 1) { rc = build_aggregates(s); if (rc) return fail_out(rc); }      // no tile factorisation for this session
   rc = build_shard(s); if (rc) return fail_out(rc);

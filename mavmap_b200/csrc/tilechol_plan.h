@@ -20,7 +20,10 @@
 #include <stdlib.h>
 #include <algorithm>
 #include <cmath>
+#include <atomic>
+#include <memory>
 #include <numeric>
+#include <thread>
 #include <vector>
 
 namespace mm {
@@ -104,62 +107,93 @@ inline Graph build_graph(int n, int n_off, const int* a, const int* b) {
 
 struct NDNode { std::vector<int> own; int parent = -1; int height = 0; };
 
+// Nested dissection.  The two parts of a separated subset are dissected side by side on host threads (top levels only); every
+// call works on its own vertices, reads foreign vertices only through their stamp (relaxed atomics, marks are drawn from one
+// global counter and therefore never collide), and the tree is flattened in the order a sequential run creates its nodes, so
+// the plan does not depend on the number of threads.
 struct Dissector {
+  struct Tree { std::vector<int> own; std::vector<Tree*> kids; ~Tree() { for (Tree* k : kids) delete k; } };
   const Graph& g; const double* pos; int leaf;
-  std::vector<int> stamp, level; int cur = 0;
+  std::unique_ptr<std::atomic<int>[]> stamp, stamp_visit; std::vector<int> level; std::atomic<int> cur{0};
   std::vector<NDNode> nodes;
-  Dissector(const Graph& g_, const double* pos_, int leaf_) : g(g_), pos(pos_), leaf(leaf_), stamp((size_t)g_.n, 0), level((size_t)g_.n, 0) {}
+  int par_depth = 3;
+  Dissector(const Graph& g_, const double* pos_, int leaf_) : g(g_), pos(pos_), leaf(leaf_), stamp(new std::atomic<int>[(size_t)std::max(g_.n, 1)]),
+      stamp_visit(new std::atomic<int>[(size_t)std::max(g_.n, 1)]), level((size_t)g_.n, 0) {
+    for (int i = 0; i < g.n; ++i) { stamp[i].store(0, std::memory_order_relaxed); stamp_visit[i].store(0, std::memory_order_relaxed); }
+    if (const char* e = getenv("MM_TC_PLAN_THREADS")) par_depth = atoi(e) <= 1 ? 0 : 3;
+    if (std::thread::hardware_concurrency() < 4) par_depth = 0;
+  }
+  int st(int v) const { return stamp[v].load(std::memory_order_relaxed); }
+  int sv(int v) const { return stamp_visit[v].load(std::memory_order_relaxed); }
+  int next_mark() { return cur.fetch_add(1, std::memory_order_relaxed) + 1; }
 
   // breadth-first levels inside the subset marked with `mark`; returns the visit order (one component from `start`)
   void bfs(int start, int mark, std::vector<int>& order, std::vector<int>& lvl_start) {
     order.clear(); lvl_start.clear();
-    const int visited = ++cur;
-    order.push_back(start); stamp_visit[start] = visited; level[start] = 0; lvl_start.push_back(0);
+    const int visited = next_mark();
+    order.push_back(start); stamp_visit[start].store(visited, std::memory_order_relaxed); level[start] = 0; lvl_start.push_back(0);
     size_t head = 0; int cur_level = 0;
     while (head < order.size()) {
       const int v = order[head++];
       if (level[v] > cur_level) { cur_level = level[v]; lvl_start.push_back((int)head - 1); }
       for (int e = g.ptr[v]; e < g.ptr[v + 1]; ++e) {
         const int u = g.adj[e];
-        if (stamp[u] == mark && stamp_visit[u] != visited) { stamp_visit[u] = visited; level[u] = level[v] + 1; order.push_back(u); }
+        if (st(u) == mark && sv(u) != visited) { stamp_visit[u].store(visited, std::memory_order_relaxed); level[u] = level[v] + 1; order.push_back(u); }
       }
     }
     lvl_start.push_back((int)order.size());
   }
-  std::vector<int> stamp_visit;
 
+  void flatten(Tree* t, int parent) {
+    // a Tree without vertices only groups the components of a disconnected subset: its kids hang under `parent`
+    int id = parent;
+    if (!t->own.empty()) { NDNode nd; nd.own.swap(t->own); nd.parent = parent; nodes.push_back(std::move(nd)); id = (int)nodes.size() - 1; }
+    for (Tree* k : t->kids) flatten(k, id);
+  }
   void run(std::vector<int>& all) {
-    stamp_visit.assign((size_t)g.n, 0);
-    dissect(all, -1);
+    Tree root;
+    dissect(all, &root, 0);
+    flatten(&root, -1);
     // heights bottom-up (children were created after their parent)
     for (int i = (int)nodes.size() - 1; i >= 0; --i) if (nodes[i].parent >= 0) nodes[nodes[i].parent].height = std::max(nodes[nodes[i].parent].height, nodes[i].height + 1);
   }
 
-  void dissect(std::vector<int>& sub, int parent) {
+  // appends the dissection of `sub` to `out->kids`
+  void dissect(std::vector<int>& sub, Tree* out, int depth) {
     if (sub.empty()) return;
     // connected components of the subset become siblings
-    const int mark = ++cur;
-    for (int v : sub) stamp[v] = mark;
+    const int mark = next_mark();
+    for (int v : sub) stamp[v].store(mark, std::memory_order_relaxed);
     std::vector<int> order, lvl;
     std::vector<std::vector<int>> comps;
     {
-      const int seen = ++cur;
+      const int seen = next_mark();
       for (int v : sub) {
-        if (stamp_visit[v] >= seen) continue;       // reached by a sweep of this call (their stamps are > seen)
+        if (sv(v) >= seen) continue;       // reached by a sweep of this call (their stamps are > seen)
         bfs(v, mark, order, lvl);
         comps.push_back(order);
       }
     }
     if (comps.size() > 1) {
-      for (auto& c : comps) dissect(c, parent);
+      for (auto& c : comps) dissect(c, out, depth);
       return;
     }
-    if ((int)sub.size() <= leaf) { NDNode nd; nd.own = sub; nd.parent = parent; nodes.push_back(nd); return; }
+    Tree* nd = new Tree(); out->kids.push_back(nd);
+    if ((int)sub.size() <= leaf) { nd->own = sub; return; }
     std::vector<int> S, A, B;
-    if (!separate(sub, S, A, B)) { NDNode nd; nd.own = sub; nd.parent = parent; nodes.push_back(nd); return; }
-    NDNode nd; nd.own = S; nd.parent = parent; nodes.push_back(nd);
-    const int id = (int)nodes.size() - 1;
-    dissect(A, id); dissect(B, id);
+    if (!separate(sub, S, A, B)) { nd->own = sub; return; }
+    nd->own = S;
+    if (depth < par_depth && (int)A.size() > 256 && (int)B.size() > 256) {
+      Tree ta;                                   // A's nodes come first in the sequential order
+      std::thread th([&] { dissect(A, &ta, depth + 1); });
+      Tree tb; dissect(B, &tb, depth + 1);
+      th.join();
+      for (Tree* k : ta.kids) nd->kids.push_back(k);
+      for (Tree* k : tb.kids) nd->kids.push_back(k);
+      ta.kids.clear(); tb.kids.clear();
+    } else {
+      dissect(A, nd, depth + 1); dissect(B, nd, depth + 1);
+    }
   }
 
   // vertex separator of a connected subset: the best of (a) the boundary of a median cut along each coordinate axis and
@@ -168,8 +202,8 @@ struct Dissector {
     const int n = (int)sub.size();
     double best = 1e300; std::vector<int> side_best;      // side: 0 = A, 1 = B, 2 = separator (indexed like sub)
     std::vector<int> side((size_t)n);
-    const int mark = ++cur;
-    for (int v : sub) stamp[v] = mark;
+    const int mark = next_mark();
+    for (int v : sub) stamp[v].store(mark, std::memory_order_relaxed);
     auto evaluate = [&](const std::vector<int>& sd) {
       int na = 0, nb = 0, ns = 0;
       for (int s : sd) { if (s == 0) ++na; else if (s == 1) ++nb; else ++ns; }
@@ -182,26 +216,26 @@ struct Dissector {
     auto cut_to_separator = [&](std::vector<int>& sd) {
       // sd holds 0/1 from an edge cut: the smaller of the two boundaries becomes the separator
       int ba = 0, bb = 0;
+      std::vector<char> touch((size_t)n, 0);
       for (int i = 0; i < n; ++i) {
-        const int v = sub[i]; bool touch = false;
-        for (int e = g.ptr[v]; e < g.ptr[v + 1] && !touch; ++e) { const int u = g.adj[e]; if (stamp[u] == mark && sd[level[u]] != sd[i]) touch = true; }
-        if (touch) { if (sd[i] == 0) ++ba; else ++bb; }
+        const int v = sub[i];
+        for (int e = g.ptr[v]; e < g.ptr[v + 1]; ++e) { const int u = g.adj[e]; if (st(u) == mark && sd[level[u]] != sd[i]) { touch[i] = 1; break; } }
+        if (touch[i]) { if (sd[i] == 0) ++ba; else ++bb; }
       }
       const int pick = ba <= bb ? 0 : 1;
-      std::vector<int> out(sd);
-      for (int i = 0; i < n; ++i) {
-        if (sd[i] != pick) continue;
-        const int v = sub[i];
-        for (int e = g.ptr[v]; e < g.ptr[v + 1]; ++e) { const int u = g.adj[e]; if (stamp[u] == mark && sd[level[u]] != pick) { out[i] = 2; break; } }
-      }
-      sd.swap(out);
+      for (int i = 0; i < n; ++i) if (sd[i] == pick && touch[i]) sd[i] = 3;     // (marked first, renamed below: the test above reads the 0/1 sides)
+      for (int i = 0; i < n; ++i) if (sd[i] == 3) sd[i] = 2;
     };
     if (pos) {
       std::vector<int> idx((size_t)n);
+      double ext[3]; double ext_max = 0.0;
       for (int ax = 0; ax < 3; ++ax) {
         double lo = 1e300, hi = -1e300;
         for (int v : sub) { lo = std::min(lo, pos[3 * (size_t)v + ax]); hi = std::max(hi, pos[3 * (size_t)v + ax]); }
-        if (!(hi - lo > 0.0)) continue;
+        ext[ax] = hi - lo; ext_max = std::max(ext_max, ext[ax]);
+      }
+      for (int ax = 0; ax < 3; ++ax) {
+        if (!(ext[ax] > 0.0) || ext[ax] < 0.05 * ext_max) continue;      // (a cut across a thin direction, e.g. the flying height, never separates well)
         std::iota(idx.begin(), idx.end(), 0);
         std::sort(idx.begin(), idx.end(), [&](int x, int y) { const double px = pos[3 * (size_t)sub[x] + ax], py = pos[3 * (size_t)sub[y] + ax]; return px < py || (px == py && sub[x] < sub[y]); });
         for (int r = 0; r < n; ++r) side[idx[r]] = r < n / 2 ? 0 : 1;
@@ -353,52 +387,154 @@ inline int build_tilechol_plan(int n_img, int n_off, const int* blk_a, const int
   P.rowp_tile.resize((size_t)P.rowp_ptr[nt]); P.rowp_col.resize((size_t)P.rowp_ptr[nt]);
   { std::vector<int64_t> fill(P.rowp_ptr.begin(), P.rowp_ptr.end() - 1);
     for (int k = 0; k < nt; ++k) for (size_t q = 0; q < st[k].size(); ++q) { const int r = st[k][q]; P.rowp_tile[fill[r]] = (int)(P.col_ptr[k] + 1 + (int64_t)q); P.rowp_col[fill[r]] = k; fill[r]++; } }
-  // ---- update lists: task (i, j) subtracts L(i,k) L(j,k)' for every k < j with i, j in struct(k)
-  P.upd_ptr.assign((size_t)P.n_l + 1, 0);
-  for (int pass = 0; pass < 2; ++pass) {
-    std::vector<int64_t> fill;
-    if (pass == 1) {
-      for (int64_t t = 0; t < P.n_l; ++t) P.upd_ptr[t + 1] += P.upd_ptr[t];
-      P.n_upd = P.upd_ptr[P.n_l];
-      P.upd_a.resize((size_t)P.n_upd); P.upd_b.resize((size_t)P.n_upd);
-      fill.assign(P.upd_ptr.begin(), P.upd_ptr.end() - 1);
-    }
-    for (int j = 0; j < nt; ++j) {
-      for (int64_t q = P.rowp_ptr[j]; q < P.rowp_ptr[j + 1]; ++q) {
-        const int k = P.rowp_col[q]; const int tjk = P.rowp_tile[q];
-        const std::vector<int>& s = st[k];
-        const size_t first = std::lower_bound(s.begin(), s.end(), j) - s.begin();      // s[first] == j
-        for (size_t u = first; u < s.size(); ++u) {
-          const int i = s[u];
-          const int64_t t = tile_id(i, j);
-          if (t < 0) return -5;                  // fill must contain it
-          if (pass == 0) P.upd_ptr[t + 1]++;
-          else { P.upd_a[fill[t]] = (int)(P.col_ptr[k] + 1 + (int64_t)u); P.upd_b[fill[t]] = tjk; fill[t]++; }
-        }
-      }
-    }
-  }
-  P.flops = 2.0 * TC_T * TC_T * TC_T * ((double)P.n_upd + (double)(P.n_l - nt)) + (double)nt * TC_T * TC_T * TC_T * (2.0 / 3.0);
-  // ---- scatter map of the stored S blocks
-  P.sc_tile.resize((size_t)n_img + n_off); P.sc_off.resize((size_t)n_img + n_off);
-  for (int i = 0; i < n_img; ++i) { P.sc_tile[i] = (int)P.col_ptr[P.img_tile[i]]; P.sc_off[i] = tile_elem(6 * P.img_slot[i], 6 * P.img_slot[i]); }
-  for (int e = 0; e < n_off; ++e) {
-    const int a = blk_a[e], b = blk_b[e];          // stored block = S(a, b), a < b in the caller's numbering
-    const int ta = P.img_tile[a], tb = P.img_tile[b], sa = P.img_slot[a], sb = P.img_slot[b];
-    // lower triangle in the new numbering: row = the later of the two
-    const bool a_is_row = ta > tb || (ta == tb && sa > sb);
-    const int tr = a_is_row ? ta : tb, tcn = a_is_row ? tb : ta, sr = a_is_row ? sa : sb, scn = a_is_row ? sb : sa;
-    const int64_t t = tile_id(tr, tcn);
-    if (t < 0) return -6;
-    P.sc_tile[n_img + e] = (int)t;
-    // a_is_row: the tile entry (row of a, column of b) is S(a,b) as stored; otherwise the entry (row of b, column of a) is S(a,b)'
-    P.sc_off[n_img + e] = tile_elem(6 * sr, 6 * scn) | (a_is_row ? 0 : (1 << 30));
-  }
-  // ---- W: inverse of every node's diagonal block
   P.w_row_ptr.assign((size_t)nt + 1, 0);
   for (int i = 0; i < nt; ++i) P.w_row_ptr[i + 1] = P.w_row_ptr[i] + (i - P.node_first[P.tile_node[i]] + 1);
   P.n_w = P.w_row_ptr[nt];
   auto w_index = [&](int i, int j) -> int { return (int)(P.w_row_ptr[i] + (j - P.node_first[P.tile_node[i]])); };
+  // The scatter map and the substitution task list depend only on the symbolic structure: they are built on a second host
+  // thread beside the update lists and the schedule of the factorisation.
+  auto side_work = [&]() -> int {
+    // ---- scatter map of the stored S blocks
+    P.sc_tile.resize((size_t)n_img + n_off); P.sc_off.resize((size_t)n_img + n_off);
+    for (int i = 0; i < n_img; ++i) { P.sc_tile[i] = (int)P.col_ptr[P.img_tile[i]]; P.sc_off[i] = tile_elem(6 * P.img_slot[i], 6 * P.img_slot[i]); }
+    for (int e = 0; e < n_off; ++e) {
+      const int a = blk_a[e], b = blk_b[e];          // stored block = S(a, b), a < b in the caller's numbering
+      const int ta = P.img_tile[a], tb = P.img_tile[b], sa = P.img_slot[a], sb = P.img_slot[b];
+      // lower triangle in the new numbering: row = the later of the two
+      const bool a_is_row = ta > tb || (ta == tb && sa > sb);
+      const int tr = a_is_row ? ta : tb, tcn = a_is_row ? tb : ta, sr = a_is_row ? sa : sb, scn = a_is_row ? sb : sa;
+      const int64_t t = tile_id(tr, tcn);
+      if (t < 0) return -6;
+      P.sc_tile[n_img + e] = (int)t;
+      // a_is_row: the tile entry (row of a, column of b) is S(a,b) as stored; otherwise the entry (row of b, column of a) is S(a,b)'
+      P.sc_off[n_img + e] = tile_elem(6 * sr, 6 * scn) | (a_is_row ? 0 : (1 << 30));
+    }
+    // ---- substitution tasks
+    {
+      // slots: [0, nt) forward right-hand sides t, [nt, 2nt) y, [2nt, 3nt) backward right-hand sides s, [3nt, 4nt) x, then partial sums
+      int n_slots = 4 * nt;
+      auto push_task = [&](int kind, int out, int base, int tile) {
+        P.st_kind.push_back(kind); P.st_out.push_back(out); P.st_base.push_back(base); P.st_tile.push_back(tile);
+        P.st_item_ptr.push_back((int64_t)P.it_mat.size());
+      };
+      auto push_item = [&](int sel, int64_t idx, int src) { P.it_mat.push_back((sel << 28) | (int)idx); P.it_src.push_back(src); };
+      if (P.n_l >= (1 << 28) || P.n_w >= (1 << 28)) return -7;
+      const int H = P.tile_height.empty() ? 0 : *std::max_element(P.tile_height.begin(), P.tile_height.end());
+      std::vector<std::vector<int>> by_h((size_t)H + 1);
+      for (int i = 0; i < nt; ++i) by_h[P.tile_height[i]].push_back(i);
+      std::vector<std::vector<int>> partials((size_t)nt);
+      // forward: level by level, bottom-up
+      for (int h = 0; h <= H; ++h) {
+        for (int i : by_h[h]) {                                  // accumulation over the columns of descendant nodes
+          const int f = P.node_first[P.tile_node[i]];
+          int in_chunk = 0;
+          for (int64_t q = P.rowp_ptr[i]; q < P.rowp_ptr[i + 1]; ++q) {
+            const int k = P.rowp_col[q];
+            if (k >= f) continue;                                 // same node: covered by W
+            if (in_chunk == 0) { push_task(TC_ST_MV, n_slots, -1, i); partials[i].push_back(n_slots); ++n_slots; }
+            push_item(TC_MAT_L, P.rowp_tile[q], nt + k);
+            if (++in_chunk == TC_SOLVE_CHUNK) in_chunk = 0;
+          }
+        }
+        for (int i : by_h[h]) {                                  // t_i = b_i - sum of the partial sums
+          push_task(TC_ST_SUM, i, -1, i);
+          for (int sl : partials[i]) push_item(0, 0, sl);
+        }
+        for (int i : by_h[h]) {                                  // y_i = sum_j W(i,j) t_j over the node
+          const int f = P.node_first[P.tile_node[i]];
+          push_task(TC_ST_MV, nt + i, -1, i);
+          for (int j = f; j <= i; ++j) push_item(TC_MAT_WC, w_index(i, j), j);
+        }
+      }
+      // backward: top-down
+      for (auto& v : partials) v.clear();
+      for (int h = H; h >= 0; --h) {
+        for (int j : by_h[h]) {                                  // sum over the rows of ancestor nodes of L(i,j)' x_i
+          const int last = P.node_first[P.tile_node[j]] + P.node_nt[P.tile_node[j]] - 1;
+          int in_chunk = 0;
+          for (int64_t id = P.col_ptr[j] + 1; id < P.col_ptr[j + 1]; ++id) {
+            const int i = P.row_idx[id];
+            if (i <= last) continue;
+            if (in_chunk == 0) { push_task(TC_ST_MVT, n_slots, -1, j); partials[j].push_back(n_slots); ++n_slots; }
+            push_item(TC_MAT_L, id, 3 * nt + i);
+            if (++in_chunk == TC_SOLVE_CHUNK) in_chunk = 0;
+          }
+        }
+        for (int j : by_h[h]) {                                  // s_j = y_j - partial sums
+          push_task(TC_ST_SUM, 2 * nt + j, nt + j, j);
+          for (int sl : partials[j]) push_item(0, 0, sl);
+        }
+        for (int j : by_h[h]) {                                  // x_j = sum_i W(i,j)' s_i over the node  (row-major W(i,j) = column-major W(i,j)')
+          const int last = P.node_first[P.tile_node[j]] + P.node_nt[P.tile_node[j]] - 1;
+          push_task(TC_ST_MV_OUT, 3 * nt + j, -1, j);
+          for (int i = j; i <= last; ++i) push_item(TC_MAT_WR, w_index(i, j), 2 * nt + i);
+        }
+      }
+      P.st_item_ptr.push_back((int64_t)P.it_mat.size());
+      P.n_slots = n_slots; P.n_stasks = (int)P.st_kind.size();
+    }
+    return 0;
+  };
+  int side_rc = 0;
+  std::thread side_thread;
+  const bool side_par = std::thread::hardware_concurrency() >= 4 && !getenv("MM_TC_PLAN_SERIAL");
+  if (side_par) side_thread = std::thread([&] { side_rc = side_work(); });
+  struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } side_joiner{ side_thread };
+  // ---- update lists: task (i, j) subtracts L(i,k) L(j,k)' for every k < j with i, j in struct(k).  One enumeration (j, then k
+  // ascending, then i ascending: struct(k) and struct(j) are both sorted, so the tile of (i, j) is found by a merge walk), then a
+  // stable counting sort by task keeps that order inside every task.
+  {
+    // (the columns j are independent: ranges of them are enumerated on host threads and concatenated in order)
+    const int n_part = (std::thread::hardware_concurrency() >= 4 && !getenv("MM_TC_PLAN_SERIAL") && nt >= 64) ? 4 : 1;
+    std::vector<int> put[4], pua[4], pub[4]; int perr[4] = {0, 0, 0, 0};
+    auto enumerate = [&](int part) {
+      // balanced by the number of row-pattern entries
+      const int64_t tot = P.rowp_ptr[nt];
+      const int j0 = (int)(std::lower_bound(P.rowp_ptr.begin(), P.rowp_ptr.end(), tot * part / n_part) - P.rowp_ptr.begin());
+      const int j1 = part + 1 == n_part ? nt : (int)(std::lower_bound(P.rowp_ptr.begin(), P.rowp_ptr.end(), tot * (part + 1) / n_part) - P.rowp_ptr.begin());
+      std::vector<int> ut, ua, ub;                  // (locals: the headers of put[] share cache lines)
+      const size_t guess = (size_t)(P.n_l * 20 / n_part) + 1024; ut.reserve(guess); ua.reserve(guess); ub.reserve(guess);
+      for (int j = std::min(j0, nt); j < std::min(j1, nt); ++j) {
+        const std::vector<int>& sj = st[j];
+        for (int64_t q = P.rowp_ptr[j]; q < P.rowp_ptr[j + 1]; ++q) {
+          const int k = P.rowp_col[q]; const int tjk = P.rowp_tile[q];
+          const std::vector<int>& s = st[k];
+          const size_t first = std::lower_bound(s.begin(), s.end(), j) - s.begin();      // s[first] == j
+          size_t w = 0;
+          for (size_t u = first; u < s.size(); ++u) {
+            const int i = s[u];
+            int64_t t;
+            if (i == j) t = P.col_ptr[j];
+            else {
+              while (w < sj.size() && sj[w] < i) ++w;
+              if (w == sj.size() || sj[w] != i) { perr[part] = -5; return; }                  // fill must contain it
+              t = P.col_ptr[j] + 1 + (int64_t)w;
+            }
+            ut.push_back((int)t); ua.push_back((int)(P.col_ptr[k] + 1 + (int64_t)u)); ub.push_back(tjk);
+          }
+        }
+      }
+      put[part].swap(ut); pua[part].swap(ua); pub[part].swap(ub);
+    };
+    { std::thread th[4];
+      for (int part = 1; part < n_part; ++part) th[part] = std::thread(enumerate, part);
+      enumerate(0);
+      for (int part = 1; part < n_part; ++part) th[part].join(); }
+    for (int part = 0; part < n_part; ++part) if (perr[part]) return perr[part];
+    std::vector<int> ut, ua, ub;
+    { size_t tot = 0; for (int part = 0; part < n_part; ++part) tot += put[part].size();
+      ut.reserve(tot); ua.reserve(tot); ub.reserve(tot);
+      for (int part = 0; part < n_part; ++part) { ut.insert(ut.end(), put[part].begin(), put[part].end()); ua.insert(ua.end(), pua[part].begin(), pua[part].end()); ub.insert(ub.end(), pub[part].begin(), pub[part].end()); } }
+    P.n_upd = (int64_t)ut.size();
+    P.upd_ptr.assign((size_t)P.n_l + 1, 0);
+    for (int t : ut) P.upd_ptr[(size_t)t + 1]++;
+    for (int64_t t = 0; t < P.n_l; ++t) P.upd_ptr[t + 1] += P.upd_ptr[t];
+    P.upd_a.resize((size_t)P.n_upd); P.upd_b.resize((size_t)P.n_upd);
+    std::vector<int64_t> fill(P.upd_ptr.begin(), P.upd_ptr.end() - 1);
+    for (size_t e = 0; e < ut.size(); ++e) { const int64_t d = fill[ut[e]]++; P.upd_a[d] = ua[e]; P.upd_b[d] = ub[e]; }
+  }
+  P.flops = 2.0 * TC_T * TC_T * TC_T * ((double)P.n_upd + (double)(P.n_l - nt)) + (double)nt * TC_T * TC_T * TC_T * (2.0 / 3.0);
+  // ---- W: inverse of every node's diagonal block
   std::vector<int> w_task_of((size_t)P.n_w, -1);          // W storage index -> task id whose flag covers it
   for (int j = 0; j < nt; ++j) w_task_of[w_index(j, j)] = (int)P.col_ptr[j];
   P.wupd_ptr.assign(1, 0);
@@ -462,70 +598,8 @@ inline int build_tilechol_plan(int n_img, int n_off, const int* blk_a, const int
     if (!getenv("MM_TC_NO_SCHEDULE"))
       std::stable_sort(P.task_order.begin(), P.task_order.end(), [&](int x, int y) { return key[x] < key[y]; });
   }
-  // ---- substitution tasks
-  {
-    // slots: [0, nt) forward right-hand sides t, [nt, 2nt) y, [2nt, 3nt) backward right-hand sides s, [3nt, 4nt) x, then partial sums
-    int n_slots = 4 * nt;
-    auto push_task = [&](int kind, int out, int base, int tile) {
-      P.st_kind.push_back(kind); P.st_out.push_back(out); P.st_base.push_back(base); P.st_tile.push_back(tile);
-      P.st_item_ptr.push_back((int64_t)P.it_mat.size());
-    };
-    auto push_item = [&](int sel, int64_t idx, int src) { P.it_mat.push_back((sel << 28) | (int)idx); P.it_src.push_back(src); };
-    if (P.n_l >= (1 << 28) || P.n_w >= (1 << 28)) return -7;
-    const int H = P.tile_height.empty() ? 0 : *std::max_element(P.tile_height.begin(), P.tile_height.end());
-    std::vector<std::vector<int>> by_h((size_t)H + 1);
-    for (int i = 0; i < nt; ++i) by_h[P.tile_height[i]].push_back(i);
-    std::vector<std::vector<int>> partials((size_t)nt);
-    // forward: level by level, bottom-up
-    for (int h = 0; h <= H; ++h) {
-      for (int i : by_h[h]) {                                  // accumulation over the columns of descendant nodes
-        const int f = P.node_first[P.tile_node[i]];
-        int in_chunk = 0;
-        for (int64_t q = P.rowp_ptr[i]; q < P.rowp_ptr[i + 1]; ++q) {
-          const int k = P.rowp_col[q];
-          if (k >= f) continue;                                 // same node: covered by W
-          if (in_chunk == 0) { push_task(TC_ST_MV, n_slots, -1, i); partials[i].push_back(n_slots); ++n_slots; }
-          push_item(TC_MAT_L, P.rowp_tile[q], nt + k);
-          if (++in_chunk == TC_SOLVE_CHUNK) in_chunk = 0;
-        }
-      }
-      for (int i : by_h[h]) {                                  // t_i = b_i - sum of the partial sums
-        push_task(TC_ST_SUM, i, -1, i);
-        for (int sl : partials[i]) push_item(0, 0, sl);
-      }
-      for (int i : by_h[h]) {                                  // y_i = sum_j W(i,j) t_j over the node
-        const int f = P.node_first[P.tile_node[i]];
-        push_task(TC_ST_MV, nt + i, -1, i);
-        for (int j = f; j <= i; ++j) push_item(TC_MAT_WC, w_index(i, j), j);
-      }
-    }
-    // backward: top-down
-    for (auto& v : partials) v.clear();
-    for (int h = H; h >= 0; --h) {
-      for (int j : by_h[h]) {                                  // sum over the rows of ancestor nodes of L(i,j)' x_i
-        const int last = P.node_first[P.tile_node[j]] + P.node_nt[P.tile_node[j]] - 1;
-        int in_chunk = 0;
-        for (int64_t id = P.col_ptr[j] + 1; id < P.col_ptr[j + 1]; ++id) {
-          const int i = P.row_idx[id];
-          if (i <= last) continue;
-          if (in_chunk == 0) { push_task(TC_ST_MVT, n_slots, -1, j); partials[j].push_back(n_slots); ++n_slots; }
-          push_item(TC_MAT_L, id, 3 * nt + i);
-          if (++in_chunk == TC_SOLVE_CHUNK) in_chunk = 0;
-        }
-      }
-      for (int j : by_h[h]) {                                  // s_j = y_j - partial sums
-        push_task(TC_ST_SUM, 2 * nt + j, nt + j, j);
-        for (int sl : partials[j]) push_item(0, 0, sl);
-      }
-      for (int j : by_h[h]) {                                  // x_j = sum_i W(i,j)' s_i over the node  (row-major W(i,j) = column-major W(i,j)')
-        const int last = P.node_first[P.tile_node[j]] + P.node_nt[P.tile_node[j]] - 1;
-        push_task(TC_ST_MV_OUT, 3 * nt + j, -1, j);
-        for (int i = j; i <= last; ++i) push_item(TC_MAT_WR, w_index(i, j), 2 * nt + i);
-      }
-    }
-    P.st_item_ptr.push_back((int64_t)P.it_mat.size());
-    P.n_slots = n_slots; P.n_stasks = (int)P.st_kind.size();
-  }
+  if (side_par) side_thread.join(); else side_rc = side_work();
+  if (side_rc) return side_rc;
   return 0;
 }
 
