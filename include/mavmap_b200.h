@@ -352,6 +352,15 @@ int mm_pose_refine(double* rvec, double* tvec, int model_code, const double* par
                    const uint8_t* inlier_mask, const mm_ba_options* opt,
                    mm_ba_summary* summary, double* ret);
 
+/* A batch of independent pose refinements in ONE kernel launch (one CTA per problem; SURVEY.md 8f-1 "batched across candidate
+ * pairs": candidate poses of one image, or the images of a re-localisation sweep after a loop closure).  Problem b owns the 2D-3D
+ * pairs offsets[b] .. offsets[b+1] of points2D [2 each] / points3D [3 each] (inliers only), the camera (model_codes[b],
+ * params + 9 b) and the pose rvecs + 3 b / tvecs + 3 b (in/out).  Every problem is solved exactly as mm_pose_refine solves it.
+ * summaries / rets: optional [n_problems]. */
+int mm_pose_refine_batch(int32_t n_problems, double* rvecs, double* tvecs, const int32_t* model_codes, const double* params,
+                         const int64_t* offsets, const double* points2D, const double* points3D, const mm_ba_options* opt,
+                         mm_ba_summary* summaries, double* rets);
+
 #ifdef __cplusplus
 }
 #endif

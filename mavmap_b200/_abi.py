@@ -158,6 +158,8 @@ PROTOTYPES = {
     "mm_ba_session_destroy": (None, [C.c_void_p]),
     "mm_pose_refine": (C.c_int, [p_f64, p_f64, C.c_int, p_f64, C.c_int64, p_f64, p_f64, p_u8,
                                  C.POINTER(BAOptions), C.POINTER(BASummary), p_f64]),
+    "mm_pose_refine_batch": (C.c_int, [C.c_int32, p_f64, p_f64, p_i32, p_f64, p_i64, p_f64, p_f64,
+                                       C.POINTER(BAOptions), C.POINTER(BASummary), p_f64]),
 }
 
 

@@ -17,7 +17,7 @@ import numpy as np
 
 from . import _abi
 from ._abi import (BAOptions, BAProblem, BASummary, MODEL_NUM_PARAMS, MM_INTR_STRIDE, as_ptr,
-                   p_f64, p_i32, p_u8)
+                   p_f64, p_i32, p_i64, p_u8)
 
 BA_POSE_FREE, BA_POSE_FIXED, BA_POSE_FIXED_X = 0, 1, 2
 
@@ -378,6 +378,33 @@ def pose_refinement(rvec, tvec, camera_params, points2D, points3D, inlier_mask, 
         print("%18s%.6g [px]" % ("Final cost : ", math.sqrt(summary.final_cost / nr)))
         print()
     return ret.value
+
+
+def pose_refinement_batch(rvecs, tvecs, camera_params, points2D, points3D, inlier_masks, options):
+    """Many independent pose_refinement() problems in one kernel launch (mm_pose_refine_batch; one CTA per problem).
+    rvecs / tvecs: [B, 3] arrays updated in place; camera_params: one parameter vector (model code last) per problem;
+    points2D / points3D / inlier_masks: per-problem arrays.  Returns the B values pose_refinement() would return."""
+    B = len(rvecs)
+    codes = np.zeros(B, np.int32); params = np.zeros((B, MM_INTR_STRIDE)); off = np.zeros(B + 1, np.int64)
+    p2s, p3s = [], []
+    for b in range(B):
+        code = int(camera_params[b][-1])
+        if code not in MODEL_NUM_PARAMS:
+            raise ValueError("unknown camera model code %d" % code)
+        codes[b] = code; params[b, :MODEL_NUM_PARAMS[code]] = camera_params[b][:MODEL_NUM_PARAMS[code]]
+        p2 = np.asarray(points2D[b], dtype=np.float64).reshape(-1, 2); p3 = np.asarray(points3D[b], dtype=np.float64).reshape(-1, 3)
+        if inlier_masks is not None and inlier_masks[b] is not None:
+            m = np.asarray(inlier_masks[b], dtype=bool); p2, p3 = p2[m], p3[m]
+        p2s.append(p2); p3s.append(p3); off[b + 1] = off[b] + len(p2)
+    p2a = np.ascontiguousarray(np.concatenate(p2s)) if B else np.zeros((0, 2)); p3a = np.ascontiguousarray(np.concatenate(p3s)) if B else np.zeros((0, 3))
+    rv = np.ascontiguousarray(rvecs, dtype=np.float64).reshape(B, 3).copy(); tv = np.ascontiguousarray(tvecs, dtype=np.float64).reshape(B, 3).copy()
+    rets = np.zeros(B)
+    from ._lib import lib, check
+    co = to_c_options(options)
+    check(lib().mm_pose_refine_batch(B, as_ptr(rv, p_f64), as_ptr(tv, p_f64), as_ptr(codes, p_i32), as_ptr(params, p_f64), as_ptr(off, p_i64),
+                                     as_ptr(p2a, p_f64), as_ptr(p3a, p_f64), C.byref(co), None, as_ptr(rets, p_f64)))
+    np.asarray(rvecs)[...] = rv; np.asarray(tvecs)[...] = tv
+    return rets
 
 
 class BASession:

@@ -1120,6 +1120,9 @@ int lm_iterate(mm_ba_session* s) {
   const double new_cost = red[1], step_norm = sqrt(red[3]), mcc = red[4];
   bool valid = !fail && isfinite(step_norm) && isfinite(mcc) && isfinite(new_cost) && !(mcc < 0.0);
   bool successful = false; double rel_dec = 0.0;
+  if (getenv("MM_BA_DIAG") && (!valid || !(s->cost - new_cost > O.min_relative_decrease * mcc)))      // a step that is about to be refused: say why
+    fprintf(stderr, "[mm_ba] iteration %d refused: fail flag %d, cost %.9e -> %.9e, model change %.6e, |step| %.6e, radius %.3e, %d PCG iterations\n",
+            s->iter, fail, s->cost, new_cost, mcc, step_norm, s->radius, pcg_it);
   if (!valid) {
     if (++s->n_invalid >= O.max_num_consecutive_invalid_steps) { S.termination = MM_TERM_NUMERICAL_FAILURE; s->finished = true; return MM_OK; }
   } else {
@@ -1601,6 +1604,53 @@ int mm_pose_refine(double* rvec, double* tvec, int model_code, const double* par
   mm_ba_summary S; int rc = mm_ba_solve(&P, opt, &S);
   if (rc == MM_OK) { for (int k = 0; k < 3; ++k) { rvec[k] = poses[k]; tvec[k] = poses[3 + k]; } if (ret) *ret = S.return_value; if (summary) *summary = S; }
   return rc;
+}
+
+/* Batch of independent pose refinements in one launch ("batched across candidate pairs").  Problem b refines
+ * rvecs/tvecs[b] against its own 2D-3D pairs offsets[b] .. offsets[b+1] of the concatenated arrays (already inlier-filtered), with
+ * its own camera (model_codes[b], params[b][9]).  Each problem is solved exactly as mm_pose_refine solves it (same kernel body). */
+int mm_pose_refine_batch(int32_t n_problems, double* rvecs, double* tvecs, const int32_t* model_codes, const double* params,
+                         const int64_t* offsets, const double* points2D, const double* points3D, const mm_ba_options* opt,
+                         mm_ba_summary* summaries, double* rets) {
+  if (n_problems < 0 || !opt || (n_problems > 0 && (!rvecs || !tvecs || !model_codes || !params || !offsets))) { set_error("invalid argument"); return MM_ERR_INVALID_ARG; }
+  if (n_problems == 0) return MM_OK;
+  const size_t B = (size_t)n_problems;
+  if (offsets[0] != 0) { set_error("offsets[0] must be 0"); return MM_ERR_INVALID_ARG; }
+  for (size_t b = 0; b < B; ++b) {
+    if (offsets[b + 1] <= offsets[b]) { set_error("problem %zu has no 2D-3D pairs", b); return MM_ERR_INVALID_ARG; }
+    if (model_num_params(model_codes[b]) < 0) { set_error("unknown camera model code %d", model_codes[b]); return MM_ERR_INVALID_ARG; }
+  }
+  const size_t m = (size_t)offsets[B];
+  if (!points2D || !points3D) { set_error("null buffer"); return MM_ERR_INVALID_ARG; }
+  int rc = ensure_device(); if (rc) return rc;
+  DevBuf<double> d_in, d_pose, d_intr; DevBuf<int64_t> d_off; DevBuf<int> d_model; DevBuf<mm_ba_summary> d_sum;      // d_in = [uv (2m) | X (3m)]
+  MM_CUDA(d_in.alloc(5 * m)); MM_CUDA(d_pose.alloc(6 * B)); MM_CUDA(d_intr.alloc(MM_INTR_STRIDE * B)); MM_CUDA(d_off.alloc(B + 1)); MM_CUDA(d_model.alloc(B)); MM_CUDA(d_sum.alloc(B));
+  std::vector<double> poses(6 * B), intr(MM_INTR_STRIDE * B, 0.0);
+  for (size_t b = 0; b < B; ++b) {
+    for (int k = 0; k < 3; ++k) { poses[6 * b + k] = rvecs[3 * b + k]; poses[6 * b + 3 + k] = tvecs[3 * b + k]; }
+    memcpy(intr.data() + MM_INTR_STRIDE * b, params + MM_INTR_STRIDE * b, sizeof(double) * (size_t)model_num_params(model_codes[b]));
+  }
+  MM_CUDA(cudaMemcpyAsync(d_in.p, points2D, sizeof(double) * 2 * m, cudaMemcpyHostToDevice, nullptr));
+  MM_CUDA(cudaMemcpyAsync(d_in.p + 2 * m, points3D, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, nullptr));
+  MM_CUDA(cudaMemcpyAsync(d_intr.p, intr.data(), sizeof(double) * intr.size(), cudaMemcpyHostToDevice, nullptr));
+  MM_CUDA(cudaMemcpyAsync(d_pose.p, poses.data(), sizeof(double) * poses.size(), cudaMemcpyHostToDevice, nullptr));
+  MM_CUDA(cudaMemcpyAsync(d_off.p, offsets, sizeof(int64_t) * (B + 1), cudaMemcpyHostToDevice, nullptr));
+  MM_CUDA(cudaMemcpyAsync(d_model.p, model_codes, sizeof(int) * B, cudaMemcpyHostToDevice, nullptr));
+  k_pose_refine_batch<<<(unsigned)B, 256, 0, nullptr>>>(d_off.p, reinterpret_cast<const double2*>(d_in.p), d_in.p + 2 * m, d_model.p, d_intr.p, *opt, d_pose.p, d_sum.p);
+  MM_LAUNCH_CHECK();
+  std::vector<mm_ba_summary> S(B);
+  MM_CUDA(cudaMemcpyAsync(S.data(), d_sum.p, sizeof(mm_ba_summary) * B, cudaMemcpyDeviceToHost, nullptr));
+  MM_CUDA(cudaMemcpyAsync(poses.data(), d_pose.p, sizeof(double) * poses.size(), cudaMemcpyDeviceToHost, nullptr));
+  MM_CUDA(cudaStreamSynchronize(nullptr));
+  for (size_t b = 0; b < B; ++b) {
+    S[b].return_value = sqrt(S[b].final_cost / (double)std::max<int64_t>(S[b].num_residuals, 1));
+    S[b].ms_setup = S[b].ms_linearize = S[b].ms_schur = S[b].ms_pcg = S[b].ms_update = S[b].ms_total = 0.0;
+    if (S[b].termination == MM_TERM_NUMERICAL_FAILURE && !isfinite(S[b].initial_cost)) { set_error("non-finite initial cost in problem %zu", b); return MM_ERR_NUMERICAL; }
+    for (int k = 0; k < 3; ++k) { rvecs[3 * b + k] = poses[6 * b + k]; tvecs[3 * b + k] = poses[6 * b + 3 + k]; }
+    if (rets) rets[b] = S[b].return_value;
+    if (summaries) summaries[b] = S[b];
+  }
+  return MM_OK;
 }
 
 }  // extern "C"

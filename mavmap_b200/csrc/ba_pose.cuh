@@ -96,9 +96,10 @@ __device__ __forceinline__ void pose_take_linearization(PoseLM* sm) {
   sm->gmax = gm; sm->x_norm = sqrt(xn);
 }
 
-__global__ void __launch_bounds__(256, 1) k_pose_refine(int n, const double2* __restrict__ uv, const double* __restrict__ X, int model,
-                                                         const double* __restrict__ intr, mm_ba_options O, double* __restrict__ pose_io,
-                                                         mm_ba_summary* __restrict__ S) {
+// the whole LM loop of one pose refinement, executed by one CTA of 256 threads
+__device__ __forceinline__ void pose_refine_cta(int n, const double2* __restrict__ uv, const double* __restrict__ X, int model,
+                                                const double* __restrict__ intr, const mm_ba_options& O, double* __restrict__ pose_io,
+                                                mm_ba_summary* __restrict__ S) {
   __shared__ PoseLM sm;
   __shared__ double wred[8][28];
   LossParams L; L.type = O.loss_type; L.b = O.loss_scale * O.loss_scale; L.c = 1.0 / L.b;
@@ -215,6 +216,22 @@ __global__ void __launch_bounds__(256, 1) k_pose_refine(int n, const double2* __
     }
   }
   if (threadIdx.x == 0) for (int k = 0; k < 6; ++k) pose_io[k] = sm.x[k];
+}
+
+__global__ void __launch_bounds__(256, 1) k_pose_refine(int n, const double2* __restrict__ uv, const double* __restrict__ X, int model,
+                                                         const double* __restrict__ intr, mm_ba_options O, double* __restrict__ pose_io,
+                                                         mm_ba_summary* __restrict__ S) {
+  pose_refine_cta(n, uv, X, model, intr, O, pose_io, S);
+}
+
+// A batch of independent pose refinements (candidate poses of one image, or the images of a re-localisation sweep) in ONE launch:
+// CTA b runs the LM loop of problem b.  off[b] .. off[b+1] are its 2D-3D pairs in the concatenated arrays; intr [B][9], pose [B][6].
+__global__ void __launch_bounds__(256, 1) k_pose_refine_batch(const int64_t* __restrict__ off, const double2* __restrict__ uv, const double* __restrict__ X,
+                                                               const int* __restrict__ model, const double* __restrict__ intr, mm_ba_options O,
+                                                               double* __restrict__ pose_io, mm_ba_summary* __restrict__ S) {
+  const int b = blockIdx.x;
+  const int64_t o0 = off[b];
+  pose_refine_cta((int)(off[b + 1] - o0), uv + o0, X + 3 * o0, model[b], intr + MM_INTR_STRIDE * (size_t)b, O, pose_io + 6 * (size_t)b, S + b);
 }
 
 }  // namespace mm

@@ -518,7 +518,20 @@ static int validate(const mm_ba_problem* P) {
   return MM_OK;
 }
 
+/* ORC_DETERMINISTIC=1 (what tests/conftest.py sets): every loop of the solve runs on one thread, so that all sums - the cost, and the
+ * entries of the reduced system, which the threads otherwise accumulate with `omp atomic` in scheduling order - have ONE fixed
+ * order and the oracle reproduces itself bit for bit on any machine.  The timed CPU arms of bench.py leave it unset. */
+static void orc_apply_threading(void) {
+#ifdef _OPENMP
+  static int default_threads = 0;
+  if (!default_threads) default_threads = omp_get_max_threads();
+  const char* e = getenv("ORC_DETERMINISTIC");
+  omp_set_num_threads(e && e[0] == '1' ? 1 : default_threads);
+#endif
+}
+
 int orc_ba_solve(mm_ba_problem* P, const mm_ba_options* O, mm_ba_summary* S) {
+  orc_apply_threading();
   mm_ba_summary local; if (!S) S = &local;
   memset(S, 0, sizeof *S);
   int rc = validate(P); if (rc != MM_OK) return rc;

@@ -9,6 +9,10 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+# the CPU oracle on one thread: fixed summation order, bit-reproducible on any machine (oracle/orc_ba.c: orc_apply_threading)
+os.environ.setdefault("ORC_DETERMINISTIC", "1")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
 

@@ -44,6 +44,7 @@ static int fails = 0;
 #define CHECK(cond, what) do { const bool ok_ = (cond); std::printf("%s %s\n", ok_ ? "ok  " : "FAIL", what); if (!ok_) ++fails; } while (0)
 
 int main() {
+  setvbuf(stdout, nullptr, _IOLBF, 0);
   std::mt19937 rng(20); std::normal_distribution<double> N(0.0, 1.0); std::uniform_real_distribution<double> U(-1.0, 1.0);
   const int n_img = 20, n_pt = 1000;
   std::vector<Image> images(n_img);
@@ -99,11 +100,14 @@ int main() {
   CHECK(fm.tvecs[ids[1]](0) == t_true[1](0), "FIXED_X image keeps its x translation");
   // refined intrinsics (the mapper's default, mapper.cc:878-886): start 1 % off in the focal length
   fm.camera_params[cam][0] *= 1.01; fm.camera_params[cam][1] *= 1.01;
-  global.refine_camera_params = true;
+  global.refine_camera_params = true; global.update_point3D_errors = true;
   const double c_ref = mapper.adjust_global_bundle(global);
   std::printf("refine: cost %.4f px, fx %.3f fy %.3f\n", c_ref, fm.camera_params[cam][0], fm.camera_params[cam][1]);
   CHECK(c_ref < 0.5 && std::fabs(fm.camera_params[cam][0] - 1000.0) < 5.0 && std::fabs(fm.camera_params[cam][1] - 1000.0) < 5.0, "refine_camera_params pulls the focal length back");
-  CHECK(mapper.get_point3D_error(pid[0]) >= 0.0, "point3D errors available from the mapper after BA");
+  size_t seen_pid = 0; for (int p = 0; p < n_pt; ++p) if (fm.point3D_to_points2D[pid[p]].size() >= 2) { seen_pid = pid[p]; break; }
+  bool have_err = false; double e0 = -1.0;
+  try { e0 = mapper.get_point3D_error(seen_pid); have_err = true; } catch (const std::range_error&) {}
+  CHECK(have_err && e0 >= 0.0 && e0 < 5.0, "point3D errors available from the mapper after BA (update_point3D_errors)");
   std::printf(fails ? "FAILED (%d)\n" : "all ok\n", fails);
   return fails ? 1 : 0;
 }

@@ -51,7 +51,7 @@ if os.path.exists(fn):
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         lines.append("%-72s n=%5d total %10.1f us  avg %9.2f us  %5.1f%%" % (k, a[0], a[1], a[1] / a[0], 100 * a[1] / tot))
     open(os.path.join(P, "launches_%s.txt" % tag), "w").write("\n".join(lines) + "\n")
-for f in ("cfg2", "cfg4", "ref"):
-    src = os.path.join(G, "bench_%s_%s.json" % (tag, f))
-    if os.path.exists(src): open(os.path.join(P, "bench_%s_%s.json" % (tag, f)), "w").write(open(src).read())
+for f in ("", "_cfg2", "_cfg4", "_ref"):
+    src = os.path.join(G, "bench_%s%s.json" % (tag, f))
+    if os.path.exists(src): open(os.path.join(P, "bench_%s%s.json" % (tag, f)), "w").write(open(src).read())
 print(open(os.path.join(P, "ncu_traffic.json")).read()[:600])

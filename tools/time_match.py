@@ -13,7 +13,8 @@ pairs = pairs * 4
 cnt = torch.zeros(len(pairs), dtype=torch.int32, device="cuda"); q = torch.empty(len(pairs) * n_feat, dtype=torch.int32, device="cuda")
 t = torch.empty_like(q); d = torch.empty(len(pairs) * n_feat, dtype=torch.float32, device="cuda")
 st = torch.cuda.current_stream().cuda_stream
-for impl, name in ((1, "simt"), (2, "tcgen05")):
+only_tc = len(sys.argv) > 2 and sys.argv[2] == "tc"
+for impl, name in ((2, "tcgen05"),) if only_tc else ((1, "simt"), (2, "tcgen05")):
     run = lambda: ms.match_pairs_device(pairs, cnt.data_ptr(), q.data_ptr(), t.data_ptr(), d.data_ptr(), n_feat, st, True, 0.9, -1, impl)
     run(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
