@@ -5,8 +5,10 @@
 // pose_refinement() :139-225 — i.e. the ceres::Problem construction + ceres::Solve(SPARSE_SCHUR).
 // The LM control flow restates Ceres 1.8 (trust_region_minimizer.cc,
 // levenberg_marquardt_strategy.cc; rules listed in SURVEY.md §8a-a3' and oracle/orc_ba.c); the
-// linear solve is block-Jacobi PCG on the explicitly assembled reduced camera system.
-// The host only sequences kernels and reads a handful of scalars per LM iteration.
+// linear solve is PCG on the explicitly assembled reduced camera system, preconditioned by its exact sparse tile Cholesky
+// (tilechol.cuh; two-level aggregate preconditioner as the fallback, dense Cholesky in one CTA up to 26 images).
+// The host only sequences kernels and reads a handful of scalars per LM iteration; the session setup (structure, masks,
+// renumbering, index check) runs on the device and the symbolic analysis of the factorisation on a host thread beside it.
 #include <cub/cub.cuh>
 #include <math.h>
 #include <vector>

@@ -386,17 +386,39 @@ __global__ void __launch_bounds__(128) k_rerank(const RerankJob* __restrict__ jo
 }
 
 // exact full scan of one flagged row per warp (same arithmetic and tie rule as the SIMT path)
-__global__ void k_rescan(const RerankJob* __restrict__ jobs, const float* __restrict__ desc, int K,
+__global__ void __launch_bounds__(256) k_rescan(const RerankJob* __restrict__ jobs, const float* __restrict__ desc, int K,
                          const int* __restrict__ flagged, const int* __restrict__ n_flagged, int flag_cap, Knn2* __restrict__ knn) {
+  // one CTA per flagged row (a warp per row took 0.1 ms per row at 5000 x 64: the fp64 chain of a distance is serial by design)
+  __shared__ float sb0[8], sb1[8]; __shared__ int si0[8], si1[8];
   const int nf = min(*n_flagged, flag_cap);
-  const int lane = threadIdx.x & 31;
-  for (int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); f < nf; f += gridDim.x * (blockDim.x >> 5)) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  for (int f = blockIdx.x; f < nf; f += gridDim.x) {
     const RerankJob job = jobs[flagged[2 * f]];
     const int i = flagged[2 * f + 1];
     const float* a = desc + (size_t)(job.rowA0 + i) * K;
     float b0 = FLT_MAX, b1 = FLT_MAX; int i0 = -1, i1 = -1;
-    for (int j = lane; j < job.nB; j += 32)
-      top2_insert_f(__fsqrt_rn((float)exact_d2(a, desc + (size_t)(job.rowB0 + j) * K, K)), j, b0, i0, b1, i1);
+    for (int j = threadIdx.x; j < job.nB; j += blockDim.x) {
+      // same arithmetic as exact_d2 (ascending k, separate multiply and add); the row is fetched 16 floats ahead of the serial
+      // fp64 chain so that the chain, not the loads, sets the pace (K % 4 == 0 on this path)
+      const float* b = desc + (size_t)(job.rowB0 + j) * K;
+      double s2 = 0.0;
+      int k0 = 0;
+      for (; k0 + 16 <= K; k0 += 16) {
+        float4 av[4], bv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { av[q] = *reinterpret_cast<const float4*>(a + k0 + 4 * q); bv[q] = *reinterpret_cast<const float4*>(b + k0 + 4 * q); }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          double t;
+          t = (double)av[q].x - (double)bv[q].x; s2 = __dadd_rn(s2, __dmul_rn(t, t));
+          t = (double)av[q].y - (double)bv[q].y; s2 = __dadd_rn(s2, __dmul_rn(t, t));
+          t = (double)av[q].z - (double)bv[q].z; s2 = __dadd_rn(s2, __dmul_rn(t, t));
+          t = (double)av[q].w - (double)bv[q].w; s2 = __dadd_rn(s2, __dmul_rn(t, t));
+        }
+      }
+      for (; k0 < K; ++k0) { const double t = (double)a[k0] - (double)b[k0]; s2 = __dadd_rn(s2, __dmul_rn(t, t)); }
+      top2_insert_f(__fsqrt_rn((float)s2), j, b0, i0, b1, i1);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const float ob0 = __shfl_xor_sync(0xffffffffu, b0, o), ob1 = __shfl_xor_sync(0xffffffffu, b1, o);
@@ -404,7 +426,21 @@ __global__ void k_rescan(const RerankJob* __restrict__ jobs, const float* __rest
       if (oi0 >= 0) top2_insert_f(ob0, oi0, b0, i0, b1, i1);
       if (oi1 >= 0) top2_insert_f(ob1, oi1, b0, i0, b1, i1);
     }
-    if (lane == 0) { Knn2 r; r.d0 = b0; r.d1 = b1; r.i0 = i0; r.i1 = i1; knn[job.knn_off + i] = r; }
+    if (lane == 0) { sb0[wib] = b0; sb1[wib] = b1; si0[wib] = i0; si1[wib] = i1; }
+    __syncthreads();
+    if (wib == 0) {
+      const bool have = lane < (int)(blockDim.x >> 5);
+      b0 = have ? sb0[lane] : FLT_MAX; b1 = have ? sb1[lane] : FLT_MAX; i0 = have ? si0[lane] : -1; i1 = have ? si1[lane] : -1;
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        const float ob0 = __shfl_xor_sync(0xffffffffu, b0, o), ob1 = __shfl_xor_sync(0xffffffffu, b1, o);
+        const int oi0 = __shfl_xor_sync(0xffffffffu, i0, o), oi1 = __shfl_xor_sync(0xffffffffu, i1, o);
+        if (oi0 >= 0) top2_insert_f(ob0, oi0, b0, i0, b1, i1);
+        if (oi1 >= 0) top2_insert_f(ob1, oi1, b0, i0, b1, i1);
+      }
+      if (lane == 0) { Knn2 r; r.d0 = b0; r.d1 = b1; r.i0 = i0; r.i1 = i1; knn[job.knn_off + i] = r; }
+    }
+    __syncthreads();
   }
 }
 
@@ -566,7 +602,7 @@ int match_tc_pairs(const float* desc, const float* xy, int K, const int64_t* off
   if (!j12.empty()) {
     k_rerank<<<dim3((max_nA + 127) / 128, (unsigned)j12.size()), 128, 0, st>>>(g_scr.jobs.p, desc, K, g_scr.hits.p, g_scr.hcnt.p, knn12, g_scr.flagged.p, g_scr.n_flagged.p, flag_cap);
     MM_LAUNCH_CHECK();
-    k_rescan<<<num_sms() * 2, 256, 0, st>>>(g_scr.jobs.p, desc, K, g_scr.flagged.p, g_scr.n_flagged.p, flag_cap, knn12);
+    k_rescan<<<num_sms() * 4, 256, 0, st>>>(g_scr.jobs.p, desc, K, g_scr.flagged.p, g_scr.n_flagged.p, flag_cap, knn12);
     MM_LAUNCH_CHECK();
   }
   int nf12 = 0;
@@ -576,7 +612,7 @@ int match_tc_pairs(const float* desc, const float* xy, int K, const int64_t* off
     MM_CUDA(cudaMemsetAsync(g_scr.n_flagged.p, 0, sizeof(int), st));
     k_rerank<<<dim3((max_nA + 127) / 128, (unsigned)j21.size()), 128, 0, st>>>(g_scr.jobs.p + j12.size(), desc, K, g_scr.hits.p, g_scr.hcnt.p, knn21, g_scr.flagged.p, g_scr.n_flagged.p, flag_cap);
     MM_LAUNCH_CHECK();
-    k_rescan<<<num_sms() * 2, 256, 0, st>>>(g_scr.jobs.p + j12.size(), desc, K, g_scr.flagged.p, g_scr.n_flagged.p, flag_cap, knn21);
+    k_rescan<<<num_sms() * 4, 256, 0, st>>>(g_scr.jobs.p + j12.size(), desc, K, g_scr.flagged.p, g_scr.n_flagged.p, flag_cap, knn21);
     MM_LAUNCH_CHECK();
   }
   g_tc_rows.fetch_add((uint64_t)cand_rows);
