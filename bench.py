@@ -195,7 +195,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=3, help="LM iterations of the CPU oracle for cpu_baseline and the parity block")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-match", action="store_true")
-    ap.add_argument("--no-cfg2", action="store_true", help="skip the secondary 500-image measurement")
+    ap.add_argument("--no-cfg2", action="store_true", help="skip the secondary 500-image and 1000-image-rig measurements")
     ap.add_argument("--ba-mode", default="auto", choices=["auto", "replicas", "sharded"],
                     help="N > 1: ONE problem with its points sharded (auto / sharded: strong scaling) or independent problems per GPU")
     args = ap.parse_args()
@@ -364,6 +364,25 @@ def main():
         except Exception as e:          # the headline line must not depend on the extra measurement
             cfg2 = {"error": repr(e)}
 
+    # ------------------------------------------------------------------ cfg5-sized rig with refined intrinsics (N = 1)
+    cfg5 = None
+    if rank == 0 and world == 1 and not args.no_cfg2 and name != "cfg5":
+        try:
+            f5 = make_problem("cfg5")
+            ms5, _, sum5, s5 = timed_session(f5, lambda f: BASession(f, options(W + K), stream=stream))
+            s5.close()
+            cfg5 = {"workload": "cfg5-sized: %d images of a PINHOLE + OPENCV rig, %d points, %d observations, refine_camera_params (2 x 9 intrinsics in the border of the reduced system), global BA only (no mapper loop)" % (f5.n_img, f5.n_pt, f5.n_obs),
+                    "value": K / (ms5 * 1e-3), "unit": UNIT, "ms_per_step": ms5 / K, "steps": K,
+                    "pcg_iterations": sum5["trace_linear_iterations"][W + 1:W + 1 + K], "breakdown_ms": sum5["ms_timed"]}
+            if not args.no_cpu:
+                dtc, scc, cc = cpu_ba(f5, args.cpu_steps)
+                cfg5["cpu_baseline"] = {"value": (scc.num_successful_steps + scc.num_unsuccessful_steps) / dtc, "unit": UNIT, "kind": "port", "sample": "full problem, %d LM iterations of the oracle, %.1f s" % (args.cpu_steps, dtc)}
+                gg = f5.copy(); sgg = solve_flat(gg, options(args.cpu_steps)).as_dict()
+                cfg5["parity"] = parity_block(gg, sgg, cc, scc.as_dict(), args.cpu_steps)
+                cfg5["parity"]["max_rel_intrinsics_diff"] = float(np.max(np.abs(gg.intr - cc.intr) / np.maximum(np.abs(cc.intr), 1.0)))
+        except Exception as e:
+            cfg5 = {"error": repr(e)}
+
     # ------------------------------------------------------------------ matching (secondary), sharded by pair
     secondary = None
     if not args.no_match:
@@ -454,7 +473,7 @@ def main():
                               "note": "device ms inside the %d timed LM iterations (CUDA events in the library)" % K,
                               "k1_ms": k1_ms, "k2_ms": k2_ms, "k4_cost_ms": k4_ms,
                               "dominant_by_time": max((("K3 solve", lin_ms["pcg"]), ("K2 Schur assembly", lin_ms["schur"]), ("K1 linearize", lin_ms["linearize"]), ("K4 update", lin_ms["update"])), key=lambda kv: kv[1])[0]},
-                "parity": parity, "cpu_baseline": cpu, "secondary": secondary, "secondary_cfg2": cfg2, "replicas": replicas, "tertiary": pose_lat, "final_cost": summ["final_cost"]}
+                "parity": parity, "cpu_baseline": cpu, "secondary": secondary, "secondary_cfg2": cfg2, "secondary_cfg5": cfg5, "replicas": replicas, "tertiary": pose_lat, "final_cost": summ["final_cost"]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

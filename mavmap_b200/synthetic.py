@@ -190,6 +190,8 @@ BA_CONFIGS = {
     "cfg1": dict(n_img=20, n_obs_target=12000, track_len=4, seed=0xBA5E + 1),
     "cfg2": dict(n_img=500, n_obs_target=1_000_000, track_len=4, seed=0xBA5E + 2),
     "cfg4": dict(n_img=5000, n_obs_target=10_000_000, track_len=5, seed=0xBA5E + 4, exact_track=True),
+    # configs[4]: mixed multi-camera (PINHOLE + OPENCV) 1000-image sequence, intrinsics refined as the mapper does by default
+    "cfg5": dict(n_img=1000, n_obs_target=2_000_000, track_len=4, seed=0xBA5E + 5, models=[1, 2], refine_camera_params=True),
     "tiny": dict(n_img=8, n_obs_target=1500, track_len=4, seed=0xBA5E + 9),
     "small": dict(n_img=40, n_obs_target=40000, track_len=4, seed=0xBA5E + 10),
 }

@@ -8,5 +8,7 @@ for r in d["roofline_other"]:
     print("  ", r["kernel"], "ms", r["ms"], "frac", r["frac"], "share", r.get("share_of_step"))
 c = d.get("secondary_cfg2")
 if c: print("cfg2", {k: c[k] for k in c if k != "workload"})
+c = d.get("secondary_cfg5")
+if c: print("cfg5", {k: c[k] for k in c if k != "workload"})
 if d.get("secondary"): print("matching", d["secondary"]["value"], d["secondary"]["e2e"], d["secondary"].get("cpu_baseline"))
 print("pose", d.get("tertiary"))
