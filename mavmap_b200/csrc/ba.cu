@@ -294,9 +294,14 @@ cudaError_t upload_async(void* dst, const void* src, size_t bytes, cudaStream_t 
     cudaError_t e = cudaEventSynchronize(S.ev[b]); if (e != cudaSuccess) return e;          // the previous copy out of this half has finished
     const char* from = static_cast<const char*>(src) + off; char* to = S.buf[b];
     const size_t slice = ((len + n_thr - 1) / n_thr + 4095) & ~(size_t)4095;
-    std::thread workers[8]; unsigned nw = 0;
-    for (unsigned t = 1; t < n_thr; ++t) { const size_t o = t * slice; if (o >= len) break; workers[nw++] = std::thread([=] { memcpy(to + o, from + o, std::min(slice, len - o)); }); }
+    std::thread workers[8]; unsigned nw = 0; size_t done_to = std::min(slice, len);
+    for (unsigned t = 1; t < n_thr; ++t) {
+      const size_t o = t * slice; if (o >= len) break;
+      try { workers[nw] = std::thread([=] { memcpy(to + o, from + o, std::min(slice, len - o)); }); ++nw; done_to = std::min(o + slice, len); }
+      catch (...) { break; }                      // no more threads to be had: this thread copies the rest
+    }
     memcpy(to, from, std::min(slice, len));
+    if (done_to < len) memcpy(to + done_to, from + done_to, len - done_to);
     for (unsigned t = 0; t < nw; ++t) workers[t].join();
     e = cudaMemcpyAsync(static_cast<char*>(dst) + off, to, len, cudaMemcpyHostToDevice, st); if (e != cudaSuccess) return e;
     e = cudaEventRecord(S.ev[b], st); if (e != cudaSuccess) return e;
@@ -860,7 +865,9 @@ int tc_begin(mm_ba_session* s) {
   }
   s->ncb = s->refine ? s->n_cam : 0;
   s->tc_plan_rc = 2;                              // 2 = running
-  if (getenv("MM_TC_PLAN_INLINE")) tc_plan_host(s); else s->tc_thread = std::thread(tc_plan_host, s);
+  bool started = false;
+  if (!getenv("MM_TC_PLAN_INLINE")) { try { s->tc_thread = std::thread(tc_plan_host, s); started = true; } catch (...) {} }
+  if (!started) tc_plan_host(s);
   return MM_OK;
 }
 // joins the analysis and puts the plan on the device.  *fallback = true: the session goes on with the two-level preconditioner

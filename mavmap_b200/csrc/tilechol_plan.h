@@ -185,9 +185,11 @@ struct Dissector {
     nd->own = S;
     if (depth < par_depth && (int)A.size() > 256 && (int)B.size() > 256) {
       Tree ta;                                   // A's nodes come first in the sequential order
-      std::thread th([&] { dissect(A, &ta, depth + 1); });
+      std::thread th; bool spawned = false;
+      try { th = std::thread([&] { dissect(A, &ta, depth + 1); }); spawned = true; } catch (...) {}
+      if (!spawned) dissect(A, &ta, depth + 1);
       Tree tb; dissect(B, &tb, depth + 1);
-      th.join();
+      if (spawned) th.join();
       for (Tree* k : ta.kids) nd->kids.push_back(k);
       for (Tree* k : tb.kids) nd->kids.push_back(k);
       ta.kids.clear(); tb.kids.clear();
@@ -478,7 +480,8 @@ inline int build_tilechol_plan(int n_img, int n_off, const int* blk_a, const int
   int side_rc = 0;
   std::thread side_thread;
   const bool side_par = std::thread::hardware_concurrency() >= 4 && !getenv("MM_TC_PLAN_SERIAL");
-  if (side_par) side_thread = std::thread([&] { side_rc = side_work(); });
+  bool side_spawned = false;
+  if (side_par) { try { side_thread = std::thread([&] { side_rc = side_work(); }); side_spawned = true; } catch (...) {} }
   struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } side_joiner{ side_thread };
   // ---- update lists: task (i, j) subtracts L(i,k) L(j,k)' for every k < j with i, j in struct(k).  One enumeration (j, then k
   // ascending, then i ascending: struct(k) and struct(j) are both sorted, so the tile of (i, j) is found by a merge walk), then a
@@ -516,10 +519,10 @@ inline int build_tilechol_plan(int n_img, int n_off, const int* blk_a, const int
       }
       put[part].swap(ut); pua[part].swap(ua); pub[part].swap(ub);
     };
-    { std::thread th[4];
-      for (int part = 1; part < n_part; ++part) th[part] = std::thread(enumerate, part);
+    { std::thread th[4]; bool spawned[4] = {false, false, false, false};
+      for (int part = 1; part < n_part; ++part) { try { th[part] = std::thread(enumerate, part); spawned[part] = true; } catch (...) {} }
       enumerate(0);
-      for (int part = 1; part < n_part; ++part) th[part].join(); }
+      for (int part = 1; part < n_part; ++part) { if (spawned[part]) th[part].join(); else enumerate(part); } }
     for (int part = 0; part < n_part; ++part) if (perr[part]) return perr[part];
     std::vector<int> ut, ua, ub;
     { size_t tot = 0; for (int part = 0; part < n_part; ++part) tot += put[part].size();
@@ -598,7 +601,7 @@ inline int build_tilechol_plan(int n_img, int n_off, const int* blk_a, const int
     if (!getenv("MM_TC_NO_SCHEDULE"))
       std::stable_sort(P.task_order.begin(), P.task_order.end(), [&](int x, int y) { return key[x] < key[y]; });
   }
-  if (side_par) side_thread.join(); else side_rc = side_work();
+  if (side_spawned) side_thread.join(); else side_rc = side_work();
   if (side_rc) return side_rc;
   return 0;
 }
