@@ -454,6 +454,17 @@ def main():
             mmod.pose_refinement(rv + 0.03, tv - 0.08, prm, uvp, Xp, msk, po)
         pose_lat = {"metric": "pose_refinement_latency", "value": (time.perf_counter() - t0) / 20 * 1e6, "unit": "us per call (host buffers in, pose out)",
                     "config": {"workload": "%d 2D-3D pairs, PINHOLE, 10 LM iterations, single-CTA kernel" % npts}}
+        try:        # the same problem 64 times through mm_pose_refine_batch: one launch, one CTA per problem
+            nb = 64
+            args_b = lambda: (np.tile(rv + 0.03, (nb, 1)), np.tile(tv - 0.08, (nb, 1)), [prm] * nb, [uvp] * nb, [Xp] * nb, None, po)
+            mmod.pose_refinement_batch(*args_b())
+            t0 = time.perf_counter()
+            for _ in range(5):
+                mmod.pose_refinement_batch(*args_b())
+            pose_lat["batch"] = {"problems": nb, "us_per_problem": (time.perf_counter() - t0) / 5 / nb * 1e6,
+                                 "note": "mm_pose_refine_batch, host buffers in, poses out (includes packing %d x %d pairs on the host)" % (nb, npts)}
+        except Exception as e:
+            pose_lat["batch"] = {"error": repr(e)}
 
     if rank == 0:
         step_ms = ms / K
