@@ -1584,6 +1584,7 @@ int mm_pose_refine(double* rvec, double* tvec, int model_code, const double* par
     MM_CUDA(d_in.alloc(5 * m + MM_INTR_STRIDE)); MM_CUDA(d_pose.alloc(6)); MM_CUDA(d_sum.alloc(1));
     double intr9[MM_INTR_STRIDE] = {0};
     memcpy(intr9, params, sizeof(double) * (size_t)model_num_params(model_code));
+    MM_CUDA(cudaMemsetAsync(d_sum.p, 0, sizeof(mm_ba_summary), nullptr));             // (the kernel fills the trace only up to num_iterations)
     MM_CUDA(cudaMemcpyAsync(d_in.p, obs.data(), sizeof(double) * 2 * m, cudaMemcpyHostToDevice, nullptr));
     MM_CUDA(cudaMemcpyAsync(d_in.p + 2 * m, pts.data(), sizeof(double) * 3 * m, cudaMemcpyHostToDevice, nullptr));
     MM_CUDA(cudaMemcpyAsync(d_in.p + 5 * m, intr9, sizeof intr9, cudaMemcpyHostToDevice, nullptr));
@@ -1639,6 +1640,7 @@ int mm_pose_refine_batch(int32_t n_problems, double* rvecs, double* tvecs, const
     for (int k = 0; k < 3; ++k) { poses[6 * b + k] = rvecs[3 * b + k]; poses[6 * b + 3 + k] = tvecs[3 * b + k]; }
     memcpy(intr.data() + MM_INTR_STRIDE * b, params + MM_INTR_STRIDE * b, sizeof(double) * (size_t)model_num_params(model_codes[b]));
   }
+  MM_CUDA(cudaMemsetAsync(d_sum.p, 0, sizeof(mm_ba_summary) * B, nullptr));          // (the kernel fills the trace only up to num_iterations)
   MM_CUDA(cudaMemcpyAsync(d_in.p, points2D, sizeof(double) * 2 * m, cudaMemcpyHostToDevice, nullptr));
   MM_CUDA(cudaMemcpyAsync(d_in.p + 2 * m, points3D, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, nullptr));
   MM_CUDA(cudaMemcpyAsync(d_intr.p, intr.data(), sizeof(double) * intr.size(), cudaMemcpyHostToDevice, nullptr));
