@@ -240,6 +240,7 @@ struct mm_ba_session {
   DevBuf<int4> tc_upd; DevBuf<int2> tc_items;
   DevBuf<int> tc_ready, tc_sflag, tc_counters;
   DevBuf<int64_t> tc_col_ptr;
+  DevBuf<double> tc_Ls;
   DevBuf<double> tc_L, tc_WC, tc_WR, tc_slots, tc_invd, dv_b, dv_r, dv_z, dv_p, dv_Ap;
   int grid_obs = 1, grid_pt = 1, grid_cam6 = 1, grid_x = 1, pcg_grid = 0, pcg_ecap = 0, pcg_threads = 0; bool pcg_cached = false; size_t pcg_smem = 0; const void* pcg_fn = nullptr;
   cudaEvent_t evs[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -881,7 +882,7 @@ int tc_finish(mm_ba_session* s, bool* fallback) {
   SETUP_MARK("tilechol: wait for the host plan");
   // memory: the tiles of L must fit comfortably beside the Jacobian records
   size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
-  const size_t need = sizeof(double) * TC_TT * ((size_t)P.n_l + 2 * (size_t)P.n_w);
+  const size_t need = sizeof(double) * TC_TT * (2 * (size_t)P.n_l + 2 * (size_t)P.n_w);      // L, its operand copy, W in both orientations
   if (need > free_b / 2 && !s->tc_force && !s->refine) { P = TileCholPlan(); *fallback = true; return MM_OK; }          // falls back to the two-level PCG
   const int n = s->n_img;
   const size_t n_tasks = (size_t)(P.n_l + P.n_wtask);
@@ -891,6 +892,7 @@ int tc_finish(mm_ba_session* s, bool* fallback) {
       (rc = tc_upload(s->tc_sched, s->tc_h_sched)) || (rc = tc_upload(s->tc_sdesc, s->tc_h_sdesc)) || (rc = tc_upload(s->tc_upd, s->tc_h_upd)) || (rc = tc_upload(s->tc_items, s->tc_h_items))) return rc;
   s->tc_h_sched = std::vector<int>(); s->tc_h_sdesc = std::vector<int>(); s->tc_h_upd = std::vector<int4>(); s->tc_h_items = std::vector<int2>();
   SETUP_MARK("tilechol: plan upload");
+  MM_CUDA(s->tc_Ls.alloc((size_t)TC_TT * (size_t)P.n_l));
   MM_CUDA(s->tc_L.alloc((size_t)TC_TT * (size_t)P.n_l)); MM_CUDA(s->tc_WC.alloc((size_t)TC_TT * (size_t)P.n_w)); MM_CUDA(s->tc_WR.alloc((size_t)TC_TT * (size_t)P.n_w));
   MM_CUDA(s->tc_slots.alloc((size_t)TC_T * (size_t)P.n_slots));
   MM_CUDA(s->tc_ready.alloc(n_tasks + (size_t)P.nt)); MM_CUDA(s->tc_sflag.alloc((size_t)P.n_slots)); MM_CUDA(s->tc_counters.alloc(4)); MM_CUDA(s->tc_invd.alloc((size_t)TC_T * P.nt));
@@ -903,6 +905,7 @@ int tc_finish(mm_ba_session* s, bool* fallback) {
   D.n_tasks = (int)n_tasks; D.n_stasks = P.n_stasks; D.n_slots = P.n_slots;
   D.unk_of = s->tc_unk_of.p; D.sc_tile = s->tc_sc_tile.p; D.sc_off = s->tc_sc_off.p; D.a_tiles = s->tc_a_tiles.p; D.img_tile = s->tc_img_tile.p; D.img_slot = s->tc_img_slot.p;
   D.col_ptr = s->tc_col_ptr.p; D.sched = s->tc_sched.p; D.upd = s->tc_upd.p; D.sdesc = s->tc_sdesc.p; D.items = s->tc_items.p;
+  D.Ls = s->tc_Ls.p;
   D.L = s->tc_L.p; D.WC = s->tc_WC.p; D.WR = s->tc_WR.p; D.slots = s->tc_slots.p; D.invd = s->tc_invd.p;
   D.ready = s->tc_ready.p; D.sflag = s->tc_sflag.p; D.counters = s->tc_counters.p; D.trace = nullptr; D.trace_diag = nullptr;
   MM_CUDA(cudaFuncSetAttribute((const void*)k_tc_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_FACTOR_SMEM));
@@ -1363,7 +1366,7 @@ int mm_ba_session_solver_info(mm_ba_session* s, double* out8) {
   for (int k = 0; k < 8; ++k) out8[k] = 0.0;
   const TileCholPlan& P = s->tc_plan;
   if (s->tc_on) { out8[0] = 2; out8[1] = (double)P.n_l; out8[2] = (double)(P.n_upd + P.n_wupd); out8[3] = P.flops; out8[4] = P.nt; out8[5] = (double)P.n_w; out8[6] = P.n_stasks;
-                  out8[7] = sizeof(double) * (double)TC_TT * ((double)P.n_l + 2.0 * (double)P.n_w) / 1e6; }
+                  out8[7] = sizeof(double) * (double)TC_TT * (2.0 * (double)P.n_l + 2.0 * (double)P.n_w) / 1e6; }
   else if (s->cm) { out8[0] = 1; out8[4] = s->cm; }
   return MM_OK;
 }

@@ -37,6 +37,7 @@ struct TcDev {
   const int *sc_tile, *sc_off, *a_tiles, *img_tile, *img_slot, *unk_of;
   const int64_t* col_ptr;
   const int* sched; const int4* upd; const int* sdesc; const int2* items;
+  double *Ls;                               // second copy of the off-diagonal tiles of L with swizzled rows: the operand form of the fp64 tensor-core products
   double *L, *WC, *WR, *slots, *invd;       // tiles of L; W (inverse of the node blocks) column-major and row-major; 48-vector slots; 1 / diag(L) per tile row
   int *ready, *sflag, *counters;            // ready: per factor task, then per tile row (its inverse W(j,j) is stored); sflag: per slot; counters: [0] factor, [1] substitution tasks
   unsigned long long* trace;                // optional (test hook): {start, end} in ns per factor task, then per substitution task
@@ -168,6 +169,32 @@ __device__ __forceinline__ void tc_frag_gemm66(double (&acc)[6][6], const double
   }
 }
 
+// ---- tile products on the fp64 tensor path (mma.sync.m8n8k4.f64, SASS DMMA).  Measured per 48 x 48 x 48 product and CTA at two
+// CTAs per SM (tools/bench_dmma.cu): 6 x 3 FMA fragments 2.86 us, DMMA from column-major tiles (leading dimension 48: 4-way bank
+// conflicts on the fragment loads) 2.37 us, DMMA from tiles whose rows are XOR-swizzled per column 1.83 us (96 % of the nominal
+// fp64 rate).  The operands arrive by contiguous TMA copies, so the swizzle has to be their layout in global memory: every
+// finished off-diagonal tile of L is stored a second time in that form (TcDev::Ls), and only the products read it.
+__host__ __device__ inline int tile_elem_swz(int r, int c) { return c * TC_T + (r ^ ((c & 3) << 2)); }
+__device__ __forceinline__ void tc_dmma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+// acc[i][j][e] = element (r0 + 8 i + g, c0 + 8 j + 2 t + e) of the warp's 24 x 24 quadrant, g = lane >> 2, t = lane & 3:
+//   C(r, c) -= sum_q A(r, q) B(c, q)     (A, B swizzled tiles in shared memory)
+__device__ __forceinline__ void tc_dmma_product(double (&acc)[3][3][2], const double* A, const double* B, int r0, int c0, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll 3
+  for (int q0 = 0; q0 < TC_T; q0 += 4) {
+    double a[3], b[3];
+    const int col = (q0 + t) * TC_T, sw = t << 2;                  // (q0 + t) & 3 == t
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { a[i] = -A[col + ((r0 + 8 * i + g) ^ sw)]; b[i] = B[col + ((c0 + 8 * i + g) ^ sw)]; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) tc_dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+  }
+}
+
 // Consumers: two groups of 64 threads.  Every tile product is split along its inner dimension (group g takes k in
 // [24 g, 24 g + 24)), each group keeps its partial sum in a 6 x 6 register fragment per thread (36 FMAs per six 16-byte
 // shared-memory loads), and the finishing stage of the task adds the two partial sums to the entries of A - which the
@@ -226,8 +253,10 @@ __global__ void __launch_bounds__(TC_FACTOR_THREADS, 2) k_tc_factor(TcDev P, int
             meta[stage] = make_int4(t, upd_kind | ((int)same << 9), 0, 0);
             const uint32_t dstA = tc_smem_addr(bufs + (size_t)2 * TC_TT * stage);
             tc_mbar_expect_tx(bar0 + 8 * stage, TILE_BYTES * (same ? 1 : 2));
-            tc_bulk_g2s(dstA, P.L + (size_t)TC_TT * rec.x, TILE_BYTES, bar0 + 8 * stage);
-            if (!same) tc_bulk_g2s(dstA + TILE_BYTES, (b_wr ? P.WR : P.L) + (size_t)TC_TT * rec.y, TILE_BYTES, bar0 + 8 * stage);
+            // products of L tiles run on the tensor path and read the swizzled copies; the W products (L tile x row-major W) stay on the FMA path
+            const double* srcL = upd_kind == TC_KIND_UPD ? P.Ls : P.L;
+            tc_bulk_g2s(dstA, srcL + (size_t)TC_TT * rec.x, TILE_BYTES, bar0 + 8 * stage);
+            if (!same) tc_bulk_g2s(dstA + TILE_BYTES, (b_wr ? P.WR : srcL) + (size_t)TC_TT * rec.y, TILE_BYTES, bar0 + 8 * stage);
           }
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           __syncwarp();
@@ -257,8 +286,10 @@ __global__ void __launch_bounds__(TC_FACTOR_THREADS, 2) k_tc_factor(TcDev P, int
   // -------------------------------------------------- consumers (4 warps = 2 groups)
   const int grp = tid >> 6, gt = tid & 63, R0 = 6 * (gt >> 3), C0 = 6 * (gt & 7);       // 6 x 6 fragment of the group's partial sum
   const int tr = tid >> 4, tcn = tid & 15, r0 = 6 * tr, c0 = 3 * tcn, lane = tid & 31;  // 6 x 3 fragment of the finishing steps
-  double acc[6][6];
-  int cur = -1;                                          // task whose partial sum `acc` holds
+  double acc[6][6];                                       // W products: split along k between the two groups (FMA path)
+  double accd[3][3][2];                                   // L products: the warp's 24 x 24 quadrant in the DMMA fragment layout
+  const int wq = tid >> 5, qr0 = 24 * (wq >> 1), qc0 = 24 * (wq & 1);
+  int cur = -1;                                          // task whose partial sum `acc` / `accd` holds
   int stage = 0; uint32_t phase = 0;
   for (;;) {
     tc_mbar_wait(bar0 + 8 * stage, phase);
@@ -274,16 +305,34 @@ __global__ void __launch_bounds__(TC_FACTOR_THREADS, 2) k_tc_factor(TcDev P, int
         for (int a = 0; a < 6; ++a)
 #pragma unroll
           for (int b = 0; b < 6; ++b) acc[a][b] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) { accd[i][j][0] = 0.0; accd[i][j][1] = 0.0; }
       }
       const int q0 = grp * (TC_T / 2);
-      if (skind == TC_KIND_UPD) tc_frag_gemm66<true>(acc, A, ((m.y >> 9) & 1) ? A : B, R0, C0, q0, q0 + TC_T / 2);
+      if (skind == TC_KIND_UPD) tc_dmma_product(accd, A, ((m.y >> 9) & 1) ? A : B, qr0, qc0, lane);
       else tc_frag_gemm66<false>(acc, A, B, R0, C0, q0, q0 + TC_T / 2);
     } else {
       // ---- finishing stage: C = A(i,j) + partial sums, assembled in the first half of the stage.  Column-major for the tiles
       // of L, row-major for W (there it is the second operand of the final product; W tiles have no entries of A).
       const bool rowmajor = skind == TC_KIND_FIN_W, has_a = (m.y >> 10) & 1, mine = cur == t;
       if (P.trace_diag && tid == 0 && skind == TC_KIND_FIN_DIAG) P.trace_diag[8 * (size_t)m.w + 0] = tc_gtimer();
-      if (grp == 0) {
+      if (!rowmajor) {
+        // tiles of L: the partial sum sits in the DMMA fragments, every thread owns 18 entries of the tile (column-major in A)
+        const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int e2 = 0; e2 < 2; ++e2) {
+              double* e = A + (qc0 + 8 * j + 2 * tq + e2) * TC_T + qr0 + 8 * i + g;
+              double v = has_a ? *e : 0.0;
+              if (mine) v += accd[i][j][e2];
+              *e = v;
+            }
+      } else if (grp == 0) {
 #pragma unroll
         for (int b = 0; b < 6; ++b)
 #pragma unroll
@@ -297,7 +346,7 @@ __global__ void __launch_bounds__(TC_FACTOR_THREADS, 2) k_tc_factor(TcDev P, int
           }
       }
       tc_bar_consumers();
-      if (grp == 1 && mine) {
+      if (rowmajor && grp == 1 && mine) {
 #pragma unroll
         for (int b = 0; b < 6; ++b)
 #pragma unroll
@@ -332,8 +381,14 @@ __global__ void __launch_bounds__(TC_FACTOR_THREADS, 2) k_tc_factor(TcDev P, int
         tc_bar_consumers();
         {
           double2* dst = reinterpret_cast<double2*>(P.L + (size_t)TC_TT * t); const double2* src = reinterpret_cast<const double2*>(A);
+          double2* dsw = reinterpret_cast<double2*>(P.Ls + (size_t)TC_TT * t);           // operand form for the products: rows r ^ 4 (c & 3); pairs of rows stay together
 #pragma unroll 3
-          for (int e = tid; e < TC_TT / 2; e += TC_CONSUMERS) __stcg(dst + e, src[e]);
+          for (int e = tid; e < TC_TT / 2; e += TC_CONSUMERS) {
+            const double2 v = src[e];
+            __stcg(dst + e, v);
+            const int c = e / (TC_T / 2), r = 2 * (e - c * (TC_T / 2));
+            __stcg(dsw + (tile_elem_swz(r, c) >> 1), v);
+          }
         }
       } else if (skind == TC_KIND_FIN_W) {
         // W(i,j) = -inv(L(i,i)) C   (C row-major in A, inverse column-major in B)
@@ -524,6 +579,10 @@ __global__ void __launch_bounds__(TC_FACTOR_THREADS, 2) k_tc_factor(TcDev P, int
       for (int a = 0; a < 6; ++a)
 #pragma unroll
         for (int b = 0; b < 6; ++b) acc[a][b] = 0.0;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { accd[i][j][0] = 0.0; accd[i][j][1] = 0.0; }
     }
     __syncwarp();
     if (lane == 0) tc_mbar_arrive(bar0 + 8 * (TC_STAGES + stage));
