@@ -15,10 +15,12 @@
 //             epilogue of tile t overlaps the MMAs of tile t+1).  Two passes:
 //               <0> "bound":   a quarter of the column tiles; per row the minima of eight disjoint column groups (3-input
 //                              minimum instructions); the second smallest of the eight bounds the row's true second-nearest value
-//               <1> "collect": all tiles; every column with value <= bound + 2 eps goes to the row's hit list (32-bit hit mask
-//                              per 32-column chunk), eps = the rigorous TF32 error bound 2^-9 |a||b|
-//   k_rerank  exact fp64-accumulated distances (same arithmetic as match.cu / the oracle) of the listed columns -> exact
-//             top-2 by (distance, index); a row whose list overflowed is re-scanned exactly (k_rescan).
+//               <1> "collect": all tiles; every column with value <= bound + 2 eps sets its bit in the row's hit mask (one
+//                              32-bit word per row and 32-column chunk, stored coalesced, no warp collective);
+//                              eps = the rigorous TF32 error bound 2^-9 |a||b|
+//   k_rerank  expands the row's hit masks into a candidate list (global scratch, slot-major), then exact fp64-accumulated
+//             distances (same arithmetic as match.cu / the oracle) of the listed columns -> exact top-2 by (distance, index);
+//             a row with more than TC_HCAP candidates is re-scanned exactly (k_rescan).
 // The result is bit-identical to the exact SIMT path; the tensor cores only prune.
 #include <cuda.h>
 #include <float.h>
@@ -35,12 +37,14 @@ constexpr int TC_M = 128, TC_N = 256, TC_KB = 32;           // tile rows, tile c
 constexpr int TC_STAGES = 3;                                  // B-operand ring (32 KB per stage)
 constexpr int TC_MAX_KB = 6;                                  // A tile stays resident for a whole item: K' <= 192
 constexpr int TC_A_BYTES = TC_M * TC_KB * 4, TC_B_BYTES = TC_N * TC_KB * 4;
-constexpr int TC_HCAP = 32;                                   // hit slots per (row, column half)
+constexpr int TC_HCAP = 64;                                   // candidates a row may have before it is re-scanned exactly
 constexpr int TC_BOUND_DIV = 4;                               // the bound pass looks at 1/TC_BOUND_DIV of the column tiles
 constexpr int TC_THREADS = 320;                               // warp0 TMA, warp1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 constexpr uint32_t SPIN_LIMIT = 1u << 24;                     // watchdog: trap instead of hanging the GPU
 
-struct TcItem { int rowA0, nA, rowB0, nB; int64_t out_off; float bmax; int pad; };  // one 128-row block of one direction of one pair
+// one 128-row block of one direction of one pair; mask_off: first word of the block's hit masks (collect pass): word
+// [mask_off + chunk * 128 + row] has bit e set iff column 32 chunk + e of the B image is a candidate of the block's row `row`
+struct TcItem { int rowA0, nA, rowB0, nB; int64_t out_off; int64_t mask_off; float bmax; int pad; };
 
 // ---------------------------------------------------------------- PTX wrappers (sm_100a)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -142,13 +146,13 @@ __device__ __forceinline__ float tc_eps(float na, float bmax) {
 // MODE 0 ("bound"): only the first ~1/4 of the column tiles; every row keeps the two smallest approximate values seen
 //          -> bound[row] = 2nd smallest over that column subset, an upper bound of the row's true 2nd-nearest value.
 // MODE 1 ("collect"): all column tiles; the epilogue only compares against the per-row threshold
-//          T = bound + 2 eps (+ rounding slack) and appends the (rare) columns below it to the row's hit list.
-//          Every column that can be in the exact top-2 is below T, so the hit lists are complete by construction.
+//          T = bound + 2 eps (+ rounding slack) and sets the bits of the (rare) columns below it in the row's hit masks.
+//          Every column that can be in the exact top-2 is below T, so the hit masks are complete by construction.
 template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(
     const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
     const TcItem* __restrict__ items, int n_items, int num_kb, const float* __restrict__ norms,
-    float* __restrict__ bound, int* __restrict__ hits, int* __restrict__ hcnt) {
+    float* __restrict__ bound, uint32_t* __restrict__ masks) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -238,14 +242,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(
       // MODE 0: minima of four disjoint column groups (chunk index within the tile half).  The 2nd smallest of the row's
       // eight group minima (both halves) is >= the row's 2nd smallest value: a valid bound at one FMNMX3 per two columns.
       float g0 = FLT_MAX, g1 = FLT_MAX, g2 = FLT_MAX, g3 = FLT_MAX;
-      float T = 0.f; int cnt = 0;                                   // MODE 1: threshold, hits so far
-      int* my_hits = nullptr;
+      float T = 0.f;                                                // MODE 1: the row's threshold
+      uint32_t* my_masks = nullptr;
       if (MODE == 1) {
         const int64_t r = w.out_off + (row_ok ? row_in_tile : 0);
         const float bd = bound[r];
         const float na = norms[w.rowA0 + (row_ok ? row_in_tile : 0)];
         T = row_ok ? (bd + 2.0f * tc_eps(na, w.bmax)) * (1.0f + 4e-6f) : -1.f;    // FLT_MAX bound stays +inf
-        my_hits = hits + (r * 2 + half) * TC_HCAP;
+        my_masks = masks + w.mask_off + row_in_tile;
       }
       for (int nt = 0; nt < n_tiles; ++nt) {
         mbar_wait(bar_tfull + 8 * acc, acc_phase);
@@ -278,20 +282,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(
             const float m = fminf(fminf(fminf(s[0], s[1]), s[2]), s[3]);
             if (ch == 0) g0 = fminf(g0, m); else if (ch == 1) g1 = fminf(g1, m); else if (ch == 2) g2 = fminf(g2, m); else g3 = fminf(g3, m);
           } else {
-            // Uniform work per chunk: a 32-bit hit mask, one warp OR, then a warp-uniform walk over the (few) set bits.
-            // Measured alternatives on B200 (60 pairs, 5k x 5k x 64): a 3-input-min tree with a voted slow path, 1.79 ms;
-            // the same with predicated appends, 2.10 ms; this form, 1.17 ms - the epilogue is bound by the latency of the
-            // dependent warp collectives at two epilogue warps per scheduler, not by instruction count.
+            // A 32-bit hit mask per (row, chunk of 32 columns), stored as it is: consecutive lanes = consecutive rows write one
+            // 128-byte line, no warp collective, no walk over the set bits - the re-rank kernel expands the masks.
+            // (Forms that did the expansion here, measured on B200 at 60 pairs of 5000 x 5000 x 64: one warp OR + a warp-uniform
+            // walk over the set bits 1.17 - 1.26 ms; a 3-input-min tree with a voted slow path 1.79 ms; predicated appends 2.10 ms.)
             uint32_t mask = 0;
 #pragma unroll
             for (int e = 0; e < 32; ++e) mask |= (__uint_as_float(v[e]) <= T) ? (1u << e) : 0u;
             if (lim < 32) mask &= (1u << lim) - 1u;
-            uint32_t umask = __reduce_or_sync(0xffffffffu, mask);
-            const int cbase = col0 + ch * 32;
-            while (umask) {                                         // warp-uniform; a handful of columns per row in total
-              const int e = __ffs(umask) - 1; umask &= umask - 1;
-              if ((mask >> e) & 1u) { if (cnt < TC_HCAP) my_hits[cnt] = cbase + e; ++cnt; }
-            }
+            my_masks[(size_t)(nt * (TC_N / 32) + half * (TC_N / 64) + ch) * TC_M] = mask;
           }
         }
         tc_fence_before();
@@ -311,8 +310,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_match_tc(
           if (row_ok) bound[w.out_off + row_in_tile] = m2;
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
-      } else {
-        if (row_ok) hcnt[(w.out_off + row_in_tile) * 2 + half] = cnt;
       }
     }
   }
@@ -335,50 +332,69 @@ __device__ __forceinline__ void top2_insert_f(float d, int j, float& b0, int& i0
   }
 }
 
-struct RerankJob { int rowA0, nA, rowB0, nB; int64_t out_off; int64_t knn_off; float bmax; };
+// mask_off / item_stride: the hit masks of the job's row block m start at mask_off + m * item_stride (see TcItem)
+struct RerankJob { int rowA0, nA, rowB0, nB; int64_t out_off; int64_t knn_off; int64_t mask_off; int item_stride; float bmax; };
 
-// thread per query row: exact fp64-accumulated distances (strictly ascending k, separate multiply and add — the same
-// arithmetic as match.cu and the oracle) of the row's hit columns, four independent chains at a time, then the exact
-// top-2 by (distance, index).  A row whose hit list overflowed is re-scanned exactly (k_rescan).
+// thread per query row: expands the row's hit masks (one word per chunk of 32 columns; the 128 threads of a block read one line
+// per chunk) and computes the exact fp64-accumulated distances (strictly ascending k, separate multiply and add - the same
+// arithmetic as match.cu and the oracle) of the hit columns, four independent chains at a time, then the exact top-2 by
+// (distance, index).  A row with more than TC_HCAP candidates is re-scanned exactly by a whole CTA (k_rescan).
 __global__ void __launch_bounds__(128) k_rerank(const RerankJob* __restrict__ jobs, const float* __restrict__ desc, int K,
-                         const int* __restrict__ hits, const int* __restrict__ hcnt, Knn2* __restrict__ knn,
+                         const uint32_t* __restrict__ masks, int* __restrict__ cand_g, Knn2* __restrict__ knn,
                          int* __restrict__ flagged, int* __restrict__ n_flagged, int flag_cap) {
   const RerankJob job = jobs[blockIdx.y];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= job.nA) return;
-  const int64_t r = job.out_off + i;
   const float* a = desc + (size_t)(job.rowA0 + i) * K;
+  const uint32_t* mrow = masks + job.mask_off + (size_t)(i >> 7) * job.item_stride + (i & 127);
   float b0 = FLT_MAX, b1 = FLT_MAX; int i0 = -1, i1 = -1;
-  bool overflow = false;
-  for (int half = 0; half < 2; ++half) {
-    const int n = hcnt[r * 2 + half];
-    if (n > TC_HCAP) overflow = true;
-    const int* h = hits + (r * 2 + half) * TC_HCAP;
-    for (int c0 = 0; c0 < min(n, TC_HCAP); c0 += 4) {
-      int col[4]; const float* bp[4]; double e2[4];
+  // phase 1: the set bits of the row's masks -> its candidate list in shared memory (slot-major: conflict-free).  Light and
+  // divergent; the heavy part below then runs in lockstep over the lanes (expanding and computing in one loop made every lane
+  // wait for the distance batches of all the others: 1.54 ms instead of 0.3 ms per direction).
+  // (the list lives in global scratch, slot-major per block: as 32 KB of shared memory it took the L1 capacity that the sixteen
+  // 16-byte reads of every candidate row rely on, and the kernel ran at 0.52 instead of 0.3 ms)
+  int* cand = cand_g + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (TC_HCAP * 128);
+  int n = 0;
+  // (a one-byte-per-half-tile summary of the non-zero words, written by the collect pass and read first here, did not pay: the
+  // scan is not what this kernel waits for, and the collect pass lost 1.4 points of tensor-pipe activity to the extra stores)
+  const int n_chunks = (job.nB + 31) >> 5;
+  for (int c = 0; c < n_chunks; c += 20) {                     // twenty independent loads in flight per thread: the scan is a stream, not a chain
+    uint32_t wv[20];
+#pragma unroll
+    for (int k = 0; k < 20; ++k) wv[k] = (c + k < n_chunks) ? __ldg(mrow + (size_t)(c + k) * TC_M) : 0u;
+#pragma unroll
+    for (int k = 0; k < 20; ++k) {
+      uint32_t wbits = wv[k];
+      while (wbits) { const int e = __ffs(wbits) - 1; wbits &= wbits - 1; if (n < TC_HCAP) cand[n * 128 + threadIdx.x] = 32 * (c + k) + e; ++n; }
+    }
+  }
+  const bool overflow = n > TC_HCAP;
+  const int nc = min(n, TC_HCAP);
+  // phase 2: exact distances, four independent chains at a time
+  for (int c0 = 0; c0 < nc; c0 += 4) {
+    int col[4]; const float* bp[4]; double e2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      col[k] = (c0 + k < nc) ? cand[(c0 + k) * 128 + threadIdx.x] : -1;
+      bp[k] = desc + (size_t)(job.rowB0 + (col[k] >= 0 ? col[k] : 0)) * K;
+      e2[k] = 0.0;
+    }
+    for (int k0 = 0; k0 < K; k0 += 4) {                           // K % 4 == 0 on this path
+      const float4 av = *reinterpret_cast<const float4*>(a + k0);
+      float4 bv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) bv[k] = *reinterpret_cast<const float4*>(bp[k] + k0);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        col[k] = (c0 + k < min(n, TC_HCAP)) ? h[c0 + k] : -1;
-        bp[k] = desc + (size_t)(job.rowB0 + (col[k] >= 0 && col[k] < job.nB ? col[k] : 0)) * K;
-        e2[k] = 0.0;
+        double t;
+        t = (double)av.x - (double)bv[k].x; e2[k] = __dadd_rn(e2[k], __dmul_rn(t, t));
+        t = (double)av.y - (double)bv[k].y; e2[k] = __dadd_rn(e2[k], __dmul_rn(t, t));
+        t = (double)av.z - (double)bv[k].z; e2[k] = __dadd_rn(e2[k], __dmul_rn(t, t));
+        t = (double)av.w - (double)bv[k].w; e2[k] = __dadd_rn(e2[k], __dmul_rn(t, t));
       }
-      for (int k0 = 0; k0 < K; k0 += 4) {                           // K % 4 == 0 on this path
-        const float4 av = *reinterpret_cast<const float4*>(a + k0);
-        float4 bv[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) bv[k] = *reinterpret_cast<const float4*>(bp[k] + k0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          double t;
-          t = (double)av.x - (double)bv[k].x; e2[k] = __dadd_rn(e2[k], __dmul_rn(t, t));
-          t = (double)av.y - (double)bv[k].y; e2[k] = __dadd_rn(e2[k], __dmul_rn(t, t));
-          t = (double)av.z - (double)bv[k].z; e2[k] = __dadd_rn(e2[k], __dmul_rn(t, t));
-          t = (double)av.w - (double)bv[k].w; e2[k] = __dadd_rn(e2[k], __dmul_rn(t, t));
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) if (col[k] >= 0 && col[k] < job.nB) top2_insert_f(__fsqrt_rn((float)e2[k]), col[k], b0, i0, b1, i1);
     }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (col[k] >= 0) top2_insert_f(__fsqrt_rn((float)e2[k]), col[k], b0, i0, b1, i1);
   }
   Knn2 out; out.d0 = b0; out.d1 = b1; out.i0 = i0; out.i1 = i1;
   knn[job.knn_off + i] = out;
@@ -517,7 +533,7 @@ int get_prepared(const float* desc, int64_t rows, int K, cudaStream_t st, Prepar
   return MM_OK;
 }
 
-struct TcScratch { DevBuf<TcItem> items; DevBuf<RerankJob> jobs; DevBuf<float> bound; DevBuf<int> hits, hcnt, flagged, n_flagged; size_t items_cap = 0, jobs_cap = 0, cand_cap = 0; };
+struct TcScratch { DevBuf<TcItem> items; DevBuf<RerankJob> jobs; DevBuf<float> bound; DevBuf<uint32_t> masks; DevBuf<int> flagged, n_flagged, lists; size_t items_cap = 0, jobs_cap = 0, cand_cap = 0, mask_cap = 0, lists_cap = 0; };
 TcScratch g_scr;
 std::atomic<uint64_t> g_tc_rows{0}, g_tc_flagged{0};
 
@@ -551,7 +567,7 @@ int match_tc_pairs(const float* desc, const float* xy, int K, const int64_t* off
 
   // work items: (pair, direction, 128-row block); knn12 and knn21 live in different arrays -> two candidate regions
   std::vector<TcItem> items; std::vector<RerankJob> rjobs;
-  int64_t cand_rows = 0;
+  int64_t cand_rows = 0, mask_words = 0;
   for (int p = 0; p < n_pairs; ++p) {
     const PairJob& j = jobs_host[p];
     for (int dir = 0; dir < 2; ++dir) {
@@ -565,8 +581,11 @@ int match_tc_pairs(const float* desc, const float* xy, int K, const int64_t* off
         else { for (int64_t r = offs[imgB]; r < offs[imgB] + nB; ++r) bmax = std::max(bmax, P->h_norms[(size_t)r]); P->bmax_cache[key] = bmax; } }
       RerankJob rj; rj.rowA0 = (int)offs[imgA]; rj.nA = nA; rj.rowB0 = (int)offs[imgB]; rj.nB = nB; rj.out_off = cand_rows;
       rj.knn_off = dir == 0 ? j.knn12_off : -(j.knn21_off + 1); rj.bmax = std::sqrt(bmax);
+      // hit masks: per 128-row block one word per (chunk of 32 columns, row), chunks padded to whole column tiles
+      rj.item_stride = (nB + TC_N - 1) / TC_N * (TC_N / 32) * TC_M; rj.mask_off = mask_words;
       rjobs.push_back(rj);
-      if (nB > 0) for (int m = 0; m < nA; m += TC_M) { TcItem t; t.rowA0 = (int)offs[imgA] + m; t.nA = std::min(TC_M, nA - m); t.rowB0 = (int)offs[imgB]; t.nB = nB; t.out_off = cand_rows + m; t.bmax = rj.bmax; t.pad = 0; items.push_back(t); }
+      if (nB > 0) for (int m = 0; m < nA; m += TC_M) { TcItem t; t.rowA0 = (int)offs[imgA] + m; t.nA = std::min(TC_M, nA - m); t.rowB0 = (int)offs[imgB]; t.nB = nB; t.out_off = cand_rows + m; t.mask_off = mask_words + (int64_t)(m / TC_M) * rj.item_stride; t.bmax = rj.bmax; t.pad = 0; items.push_back(t); }
+      mask_words += (int64_t)((nA + TC_M - 1) / TC_M) * rj.item_stride;
       cand_rows += nA;
     }
   }
@@ -574,16 +593,15 @@ int match_tc_pairs(const float* desc, const float* xy, int K, const int64_t* off
   if (rjobs.size() > g_scr.jobs_cap) { MM_CUDA(g_scr.jobs.alloc(rjobs.size())); g_scr.jobs_cap = rjobs.size(); }
   if ((size_t)cand_rows > g_scr.cand_cap) {
     const size_t c = (size_t)cand_rows + (size_t)cand_rows / 4;
-    MM_CUDA(g_scr.bound.alloc(c)); MM_CUDA(g_scr.hits.alloc(c * 2 * TC_HCAP)); MM_CUDA(g_scr.hcnt.alloc(c * 2)); MM_CUDA(g_scr.flagged.alloc(2 * c + 2)); g_scr.cand_cap = c; }
+    MM_CUDA(g_scr.bound.alloc(c)); MM_CUDA(g_scr.flagged.alloc(2 * c + 2)); g_scr.cand_cap = c; }
+  if ((size_t)mask_words > g_scr.mask_cap) { const size_t c = (size_t)mask_words + (size_t)mask_words / 4; MM_CUDA(g_scr.masks.alloc(c)); g_scr.mask_cap = c; }
   if (!g_scr.n_flagged.p) MM_CUDA(g_scr.n_flagged.alloc(1));
   // knn21 jobs were tagged with a negative offset: split the re-rank into the two output arrays
   std::vector<RerankJob> j12, j21;
   for (auto& r : rjobs) { if (r.knn_off >= 0) j12.push_back(r); else { RerankJob t = r; t.knn_off = -r.knn_off - 1; j21.push_back(t); } }
   std::vector<RerankJob> all = j12; all.insert(all.end(), j21.begin(), j21.end());
   MM_CUDA(cudaMemcpyAsync(g_scr.jobs.p, all.data(), sizeof(RerankJob) * all.size(), cudaMemcpyHostToDevice, st));
-  // candidates of rows with nB == 0 are never written: give them empty lists
-  // rows of jobs with nB == 0 are never visited by the kernels: empty hit lists
-  MM_CUDA(cudaMemsetAsync(g_scr.hcnt.p, 0, sizeof(int) * 2 * (size_t)cand_rows, st));
+  // (a job with nB == 0 has no chunks, a block's masks are written for every chunk the re-rank reads: nothing to clear)
   if (!items.empty()) {
     MM_CUDA(cudaMemcpyAsync(g_scr.items.p, items.data(), sizeof(TcItem) * items.size(), cudaMemcpyHostToDevice, st));
     const size_t smem = (size_t)TC_MAX_KB * TC_A_BYTES + (size_t)TC_STAGES * TC_B_BYTES + 1024 + 256 + (size_t)TC_M * 16;
@@ -591,16 +609,18 @@ int match_tc_pairs(const float* desc, const float* xy, int K, const int64_t* off
     MM_CUDA(cudaFuncSetAttribute(k_match_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = std::min((int)items.size(), num_sms());
     const int num_kb = P->Kp / TC_KB;
-    k_match_tc<0><<<grid, TC_THREADS, smem, st>>>(P->mapA, P->mapB, g_scr.items.p, (int)items.size(), num_kb, P->norms.p, g_scr.bound.p, g_scr.hits.p, g_scr.hcnt.p);
+    k_match_tc<0><<<grid, TC_THREADS, smem, st>>>(P->mapA, P->mapB, g_scr.items.p, (int)items.size(), num_kb, P->norms.p, g_scr.bound.p, g_scr.masks.p);
     MM_LAUNCH_CHECK();
-    k_match_tc<1><<<grid, TC_THREADS, smem, st>>>(P->mapA, P->mapB, g_scr.items.p, (int)items.size(), num_kb, P->norms.p, g_scr.bound.p, g_scr.hits.p, g_scr.hcnt.p);
+    k_match_tc<1><<<grid, TC_THREADS, smem, st>>>(P->mapA, P->mapB, g_scr.items.p, (int)items.size(), num_kb, P->norms.p, g_scr.bound.p, g_scr.masks.p);
     MM_LAUNCH_CHECK();
   }
   MM_CUDA(cudaMemsetAsync(g_scr.n_flagged.p, 0, sizeof(int), st));
   const int flag_cap = (int)cand_rows;
   int max_nA = 1; for (auto& r : all) max_nA = std::max(max_nA, r.nA);
+  { const size_t need = (size_t)((max_nA + 127) / 128) * std::max(j12.size(), j21.size()) * TC_HCAP * 128;      // candidate lists of one re-rank launch
+    if (need > g_scr.lists_cap) { MM_CUDA(g_scr.lists.alloc(need)); g_scr.lists_cap = need; } }
   if (!j12.empty()) {
-    k_rerank<<<dim3((max_nA + 127) / 128, (unsigned)j12.size()), 128, 0, st>>>(g_scr.jobs.p, desc, K, g_scr.hits.p, g_scr.hcnt.p, knn12, g_scr.flagged.p, g_scr.n_flagged.p, flag_cap);
+    k_rerank<<<dim3((max_nA + 127) / 128, (unsigned)j12.size()), 128, 0, st>>>(g_scr.jobs.p, desc, K, g_scr.masks.p, g_scr.lists.p, knn12, g_scr.flagged.p, g_scr.n_flagged.p, flag_cap);
     MM_LAUNCH_CHECK();
     k_rescan<<<num_sms() * 4, 256, 0, st>>>(g_scr.jobs.p, desc, K, g_scr.flagged.p, g_scr.n_flagged.p, flag_cap, knn12);
     MM_LAUNCH_CHECK();
@@ -610,7 +630,7 @@ int match_tc_pairs(const float* desc, const float* xy, int K, const int64_t* off
   if (want_stats) MM_CUDA(cudaMemcpyAsync(&nf12, g_scr.n_flagged.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   if (!j21.empty()) {
     MM_CUDA(cudaMemsetAsync(g_scr.n_flagged.p, 0, sizeof(int), st));
-    k_rerank<<<dim3((max_nA + 127) / 128, (unsigned)j21.size()), 128, 0, st>>>(g_scr.jobs.p + j12.size(), desc, K, g_scr.hits.p, g_scr.hcnt.p, knn21, g_scr.flagged.p, g_scr.n_flagged.p, flag_cap);
+    k_rerank<<<dim3((max_nA + 127) / 128, (unsigned)j21.size()), 128, 0, st>>>(g_scr.jobs.p + j12.size(), desc, K, g_scr.masks.p, g_scr.lists.p, knn21, g_scr.flagged.p, g_scr.n_flagged.p, flag_cap);
     MM_LAUNCH_CHECK();
     k_rescan<<<num_sms() * 4, 256, 0, st>>>(g_scr.jobs.p + j12.size(), desc, K, g_scr.flagged.p, g_scr.n_flagged.p, flag_cap, knn21);
     MM_LAUNCH_CHECK();
