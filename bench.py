@@ -419,19 +419,30 @@ def main():
         m_launch = _lib.kernel_launch_count() - lm0
         pairs_s = len(pairs_all) / (mms * 1e-3)
         flops = 2.0 * n_feat * n_feat * kdim
-        # e2e: host descriptors per pair (H2D 2 x n x k x 4 B, D2H the match list)
+        # e2e: the one-pair entry point on HOST descriptor arrays, in the mapper's order (image i against i-1 and i-2,
+        # sequential_mapper.cc process()); the library keeps its last four images resident, so an image is uploaded when it
+        # first appears - the bytes below are counted by the library (mm_match_pair_counters), the D2H is count | q | t | dist
         import mavmap_b200 as mm
+        seq = [(i - d, i) for i in range(2, n_imgs) for d in (1, 2)]
+        n_e2e = max(2, min(24, np_)); warm_e2e = 4
+        host_desc = [np.ascontiguousarray(desc[i]) for i in range(n_imgs)]
+        for (i, j) in seq[:warm_e2e]:
+            mm.match_brute_force(None, host_desc[i], None, host_desc[j], True, 0.9, -1)
+        c0 = _lib.match_pair_counters()
         t0 = time.perf_counter()
-        for (i, j) in mine[: max(2, min(6, np_))]:
-            mm.match_brute_force(None, desc[i], None, desc[j], True, 0.9, -1)
-        m_e2e = max_over_ranks((time.perf_counter() - t0) / max(2, min(6, np_)))
+        for (i, j) in seq[warm_e2e:warm_e2e + n_e2e]:
+            mm.match_brute_force(None, host_desc[i], None, host_desc[j], True, 0.9, -1)
+        m_e2e = max_over_ranks((time.perf_counter() - t0) / n_e2e)
+        c1 = _lib.match_pair_counters()
         secondary = {"metric": "image_pairs_matched_per_sec", "value": pairs_s, "unit": "pairs/s", "ms_per_pair": mms / max(np_, 1),
                      "config": {"workload": "5000 x 5000 SURF-%d descriptors per pair, ratio 0.9 + cross-check, %d pairs/rank out of a resident %d-image sequence (%.0f MB of descriptors + TF32 operand copies per GPU), image i against i+1 and i+2" % (kdim, np_, n_imgs, n_imgs * n_feat * (kdim + 2 * 96) * 4 / 1e6),
                                 "exchange": ("ragged all_gather of counts + packed lists, %d matches = %.1f MB per step" % (gathered.get("matches", 0), gathered.get("bytes", 0) / 1e6)) if world > 1 else "none (single GPU)"},
                      "impl": "simt (exact fp64-accumulate CUDA cores)" if os.environ.get("MM_MATCH_NO_TC") else "tcgen05 TF32 candidate GEMM + exact re-rank", "gpu_launches": int(m_launch),
                      "algorithmic_tflops": pairs_s * flops / 1e12, "algorithmic_tflops_per_gpu": pairs_s * flops / 1e12 / world,
                      "tensor_roofline_frac_of_bf16_peak_per_gpu": pairs_s * flops / 1e12 / world / peaks["bf16_tflops"],
-                     "e2e": {"value": world / m_e2e, "unit": "pairs/s", "h2d_bytes_per_step": 2 * n_feat * kdim * 4, "d2h_bytes_per_step": 12 * 3000}}
+                     "e2e": {"value": world / m_e2e, "unit": "pairs/s", "h2d_bytes_per_step": int((c1[2] - c0[2]) / n_e2e), "d2h_bytes_per_step": 16 + 12 * n_feat,
+                             "pairs": n_e2e, "descriptor_arrays_uploaded": int(c1[1] - c0[1]),
+                             "note": "mm_match_pair on host arrays, image i against i-1 and i-2; the last four images stay resident in the library"}}
         if rank == 0 and world == 1 and not args.no_cpu:
             secondary["cpu_baseline"] = {"value": cpu_match_pairs(desc, 3), "unit": "pairs/s", "cores": os.cpu_count(), "kind": "reference",
                                          "sample": "3 pairs, cv2.BFMatcher knnMatch x2 + ratio + cross-check (OpenCV %s)" % __import__("cv2").__version__}

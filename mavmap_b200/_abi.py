@@ -108,6 +108,7 @@ PROTOTYPES = {
     "mm_last_error": (C.c_char_p, []),
     "mm_device_count": (C.c_int, []),
     "mm_kernel_launch_count": (C.c_uint64, []),
+    "mm_match_pair_counters": (None, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "mm_camera_model_name_to_code": (C.c_int, [C.c_char_p]),
     "mm_camera_model_num_params": (C.c_int, [C.c_int]),
     "mm_camera_image2world_threshold": (C.c_double, [C.c_double, C.c_int, p_f64]),

@@ -47,3 +47,11 @@ def device_count():
 
 def kernel_launch_count():
     return int(lib().mm_kernel_launch_count())
+
+
+def match_pair_counters():
+    """(calls, descriptor arrays uploaded, bytes uploaded) of mm_match_pair since process start."""
+    import ctypes as C
+    a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+    lib().mm_match_pair_counters(C.byref(a), C.byref(b), C.byref(c))
+    return a.value, b.value, c.value

@@ -15,6 +15,7 @@
 //   MM_MATCH_IMPL_TCGEN05  match_tc.cu: TF32 tcgen05 distance GEMM selects candidates, which are
 //                          then re-ranked with the exact arithmetic above
 #include <float.h>
+#include <chrono>
 #include <vector>
 #include <algorithm>
 #include <mutex>
@@ -345,12 +346,61 @@ int mm_match_set_pairs(mm_match_set* s, const int32_t* ia, const int32_t* ib, in
   return MM_OK;
 }
 
-// one-pair entry point: a process-wide workspace keeps every device buffer (descriptors, TF32 operand copies,
-// top-2 lists, outputs) alive between calls, so a call costs two H2D copies, the kernels and one D2H of the matches
-static mm_match_set* g_pair_set = nullptr;
-static DevBuf<float> g_pair_desc, g_pair_xy, g_pair_dist; static DevBuf<int32_t> g_pair_q, g_pair_t, g_pair_cnt;
-static size_t g_pair_desc_cap = 0, g_pair_xy_cap = 0, g_pair_out_cap = 0;
-static std::mutex g_pair_mu;
+// One-pair entry point.  A process-wide workspace keeps every device buffer alive between calls, and the descriptor
+// arrays of the last PAIR_SLOTS images stay resident in fixed-size slots of one device array: the mapper matches image i
+// against i-1 and i-2 (sequential_mapper.cc process()), so one of the two arrays of a call has normally been uploaded and
+// prepared (TF32 operand copies, norms) by an earlier call.  A host array is recognised by (address, rows, k) and a hash
+// of its content taken on every call - all of it up to 32 KB, above that the first and last row and 64 bytes of every KB (a
+// part of every 4th SURF-64 row); an array rewritten in place without touching any sampled byte would go unnoticed,
+// MM_MATCH_PAIR_NO_CACHE=1 uploads always.
+// The result comes back as one copy (count | q | t | dist) into pinned memory.
+namespace {
+constexpr int PAIR_SLOTS = 4;
+struct PairSlot { const float* host = nullptr; int n = 0; uint64_t hash = 0, stamp = 0; };
+struct PairWorkspace {
+  mm_match_set set; DevBuf<float> desc, xy; DevBuf<int32_t> out; int32_t* host_out = nullptr;
+  size_t slot_rows = 0, out_cap = 0; int k = 0; bool xy_alloc = false; uint64_t clock = 0; PairSlot slot[PAIR_SLOTS];
+};
+PairWorkspace* g_pair = nullptr;
+std::mutex g_pair_mu;
+uint64_t g_pair_calls = 0, g_pair_uploads = 0, g_pair_bytes = 0;       // under g_pair_mu
+
+uint64_t sample_hash(const float* d, size_t n, size_t k) {
+  const size_t row = k * sizeof(float), bytes = n * row;
+  const unsigned char* b = reinterpret_cast<const unsigned char*>(d);
+  uint64_t h = 0x9E3779B97F4A7C15ull ^ bytes;
+  auto mix = [&h](const unsigned char* p, size_t len) {
+    for (size_t i = 0; i < len; i += 8) { uint64_t w = 0; memcpy(&w, p + i, std::min<size_t>(8, len - i)); h = (h ^ w) * 0x100000001B3ull; h ^= h >> 29; }
+  };
+  if (bytes <= ((size_t)32 << 10)) { mix(b, bytes); return h; }        // small arrays: all of it
+  mix(b, row); mix(b + bytes - row, row);
+  for (size_t o = 1024; o + 64 <= bytes; o += 1024) mix(b + o, 64);
+  return h;
+}
+
+int pair_find(const PairWorkspace* w, const float* d, int n, uint64_t h) {
+  for (int i = 0; i < PAIR_SLOTS; ++i) if (w->slot[i].host == d && w->slot[i].n == n && w->slot[i].hash == h) return i;
+  return -1;
+}
+// copies `d` into the least recently used slot other than `keep`
+int pair_upload(PairWorkspace* w, const float* d, int n, int k, uint64_t h, int keep, int* slot_out) {
+  int victim = -1;
+  for (int i = 0; i < PAIR_SLOTS; ++i) if (i != keep && (victim < 0 || w->slot[i].stamp < w->slot[victim].stamp)) victim = i;
+  w->slot[victim] = PairSlot();                // not valid unless the copy has been issued
+  MM_CUDA(cudaMemcpyAsync(w->desc.p + (size_t)victim * w->slot_rows * k, d, sizeof(float) * (size_t)n * k, cudaMemcpyHostToDevice, nullptr));
+  w->slot[victim].host = d; w->slot[victim].n = n; w->slot[victim].hash = h;
+  ++g_pair_uploads; g_pair_bytes += sizeof(float) * (size_t)n * k;
+  *slot_out = victim;
+  return MM_OK;
+}
+}  // namespace
+
+void mm_match_pair_counters(uint64_t* calls, uint64_t* arrays_uploaded, uint64_t* bytes_uploaded) {
+  std::lock_guard<std::mutex> lk(g_pair_mu);
+  if (calls) *calls = g_pair_calls;
+  if (arrays_uploaded) *arrays_uploaded = g_pair_uploads;
+  if (bytes_uploaded) *bytes_uploaded = g_pair_bytes;
+}
 
 int mm_match_pair(const float* d1, int32_t n1, const float* d2, int32_t n2, int32_t k, const float* xy1, const float* xy2,
                   const mm_match_options* opt, int32_t* q, int32_t* t, float* dist, int32_t* n_out) {
@@ -361,36 +411,83 @@ int mm_match_pair(const float* d1, int32_t n1, const float* d2, int32_t n2, int3
   if (!d1 || !d2 || !q || !t || !dist) { set_error("null buffer"); return MM_ERR_INVALID_ARG; }
   if (opt->max_distance != -1.0 && (!xy1 || !xy2)) { set_error("max_distance >= 0 needs keypoints"); return MM_ERR_INVALID_ARG; }
   std::lock_guard<std::mutex> lk(g_pair_mu);
-  const size_t rows = (size_t)n1 + (size_t)n2, need = (rows + 256) * (size_t)k;
-  if (need > g_pair_desc_cap) { match_tc_release(g_pair_desc.p); MM_CUDA(g_pair_desc.alloc(need + need / 2)); g_pair_desc_cap = need + need / 2; }
+  if (!g_pair) g_pair = new PairWorkspace();
+  PairWorkspace* w = g_pair;
+  ++g_pair_calls;
+  static const bool no_cache = getenv("MM_MATCH_PAIR_NO_CACHE") != nullptr;
+  static const bool timing = getenv("MM_MATCH_PAIR_TIMING") != nullptr;      // host microseconds per phase of a call, to stderr
+  double t_ph[6] = {0, 0, 0, 0, 0, 0}; int n_ph = 0;
+  auto t_last = std::chrono::steady_clock::now();
+  auto mark = [&](bool sync) {
+    if (!timing) return;
+    if (sync) cudaStreamSynchronize(nullptr);
+    const auto now = std::chrono::steady_clock::now();
+    t_ph[n_ph++] = std::chrono::duration<double, std::micro>(now - t_last).count(); t_last = now;
+  };
+  const size_t big = (size_t)std::max(n1, n2);
+  if (big > w->slot_rows || k != w->k) {          // (re)size the slots: everything resident is dropped
+    match_tc_release(w->desc.p);
+    for (auto& sl : w->slot) sl = PairSlot();
+    const size_t rows = std::max(w->slot_rows, (big + big / 4 + 255) / 256 * 256), total = (size_t)PAIR_SLOTS * rows + 256;
+    w->slot_rows = 0; w->k = 0; w->xy_alloc = false;
+    MM_CUDA(w->desc.alloc(total * (size_t)k));
+    MM_CUDA(cudaMemsetAsync(w->desc.p, 0, sizeof(float) * total * (size_t)k, nullptr));
+    w->slot_rows = rows; w->k = k;
+  }
   const bool use_xy = xy1 && xy2;
-  if (use_xy && 2 * rows > g_pair_xy_cap) { MM_CUDA(g_pair_xy.alloc(3 * rows)); g_pair_xy_cap = 3 * rows; }
+  if (use_xy && !w->xy_alloc) { MM_CUDA(w->xy.alloc(2 * ((size_t)PAIR_SLOTS * w->slot_rows + 1))); w->xy_alloc = true; }
   const size_t cap = (size_t)std::min(n1, n2);
-  if (cap > g_pair_out_cap) { MM_CUDA(g_pair_q.alloc(2 * cap)); MM_CUDA(g_pair_t.alloc(2 * cap)); MM_CUDA(g_pair_dist.alloc(2 * cap)); g_pair_out_cap = 2 * cap; if (!g_pair_cnt.p) MM_CUDA(g_pair_cnt.alloc(1)); }
-  MM_CUDA(cudaMemcpyAsync(g_pair_desc.p, d1, sizeof(float) * (size_t)n1 * k, cudaMemcpyHostToDevice, nullptr));
-  MM_CUDA(cudaMemcpyAsync(g_pair_desc.p + (size_t)n1 * k, d2, sizeof(float) * (size_t)n2 * k, cudaMemcpyHostToDevice, nullptr));
-  if (use_xy) {
-    MM_CUDA(cudaMemcpyAsync(g_pair_xy.p, xy1, sizeof(float) * 2 * (size_t)n1, cudaMemcpyHostToDevice, nullptr));
-    MM_CUDA(cudaMemcpyAsync(g_pair_xy.p + 2 * (size_t)n1, xy2, sizeof(float) * 2 * (size_t)n2, cudaMemcpyHostToDevice, nullptr));
+  if (cap > w->out_cap || !w->host_out) {
+    const size_t c = 2 * cap;
+    if (w->host_out) { cudaFreeHost(w->host_out); w->host_out = nullptr; w->out_cap = 0; }
+    MM_CUDA(w->out.alloc(4 + 3 * c));
+    MM_CUDA(cudaHostAlloc((void**)&w->host_out, sizeof(int32_t) * (4 + 3 * c), cudaHostAllocDefault));
+    w->out_cap = c;
   }
-  if (!g_pair_set) g_pair_set = new mm_match_set();
-  mm_match_set* s = g_pair_set;
-  int32_t counts[2] = { n1, n2 };
-  s->max_count = 0;
-  rc = set_init(s, counts, 2, k); if (rc) return rc;
-  s->desc = g_pair_desc.p; s->xy = use_xy ? g_pair_xy.p : nullptr;
-  match_tc_invalidate(s->desc);                 // same buffer, new contents: the TF32 operand copies must be refreshed
-  int32_t ia = 0, ib = 1;
-  rc = match_pairs_device(s, &ia, &ib, 1, opt, g_pair_cnt.p, g_pair_q.p, g_pair_t.p, g_pair_dist.p, (int)cap, nullptr); if (rc) return rc;
-  int32_t c = 0;
-  MM_CUDA(cudaMemcpy(&c, g_pair_cnt.p, sizeof(int32_t), cudaMemcpyDeviceToHost));
-  if (c > 0) {
-    MM_CUDA(cudaMemcpyAsync(q, g_pair_q.p, sizeof(int32_t) * (size_t)c, cudaMemcpyDeviceToHost, nullptr));
-    MM_CUDA(cudaMemcpyAsync(t, g_pair_t.p, sizeof(int32_t) * (size_t)c, cudaMemcpyDeviceToHost, nullptr));
-    MM_CUDA(cudaMemcpyAsync(dist, g_pair_dist.p, sizeof(float) * (size_t)c, cudaMemcpyDeviceToHost, nullptr));
-    MM_CUDA(cudaStreamSynchronize(nullptr));
+  int sa = -1, sb = -1; bool up_a = false, up_b = false;
+  {
+    const bool same = d2 == d1 && n2 == n1;
+    const bool share = same && !no_cache && !(use_xy && xy1 != xy2);      // one slot serves both sides (its keypoints too)
+    const uint64_t h1 = sample_hash(d1, (size_t)n1, (size_t)k), h2 = same ? h1 : sample_hash(d2, (size_t)n2, (size_t)k);
+    if (!no_cache) { sa = pair_find(w, d1, n1, h1); sb = same ? (share ? sa : -1) : pair_find(w, d2, n2, h2); }
+    if (sa < 0) { rc = pair_upload(w, d1, n1, k, h1, sb, &sa); if (rc) return rc; up_a = true; if (share) sb = sa; }
+    if (sb < 0) { rc = pair_upload(w, d2, n2, k, h2, sa, &sb); if (rc) return rc; up_b = true; }
+    w->slot[sa].stamp = ++w->clock; w->slot[sb].stamp = ++w->clock;
   }
+  mark(true);             // [0] workspace, content hashes, descriptor uploads
+  if (use_xy) {           // the keypoints are small: copied on every call, not part of what identifies a slot
+    MM_CUDA(cudaMemcpyAsync(w->xy.p + 2 * (size_t)sa * w->slot_rows, xy1, sizeof(float) * 2 * (size_t)n1, cudaMemcpyHostToDevice, nullptr));
+    MM_CUDA(cudaMemcpyAsync(w->xy.p + 2 * (size_t)sb * w->slot_rows, xy2, sizeof(float) * 2 * (size_t)n2, cudaMemcpyHostToDevice, nullptr));
+  }
+  {                       // rows of the TF32 operand copies that changed (no-op until the tensor-core path has prepared the array)
+    int64_t r0[2], nr[2]; int cnt = 0;
+    if (up_a) { r0[cnt] = (int64_t)sa * (int64_t)w->slot_rows; nr[cnt] = n1; ++cnt; }
+    if (up_b) { r0[cnt] = (int64_t)sb * (int64_t)w->slot_rows; nr[cnt] = n2; ++cnt; }
+    rc = match_tc_refresh_rows(w->desc.p, k, r0, nr, cnt, nullptr); if (rc) return rc;
+  }
+  mark(true);             // [1] keypoints, TF32 operand copies and norms of the uploaded rows
+  mm_match_set* s = &w->set;
+  s->n_images = PAIR_SLOTS; s->k = k; s->desc = w->desc.p; s->xy = use_xy ? w->xy.p : nullptr;
+  s->counts.assign(PAIR_SLOTS, 0); s->offs.resize(PAIR_SLOTS + 1); s->max_count = 0;
+  for (int i = 0; i <= PAIR_SLOTS; ++i) s->offs[i] = (int64_t)i * (int64_t)w->slot_rows;
+  for (int i = 0; i < PAIR_SLOTS; ++i) { s->counts[i] = w->slot[i].host ? w->slot[i].n : 0; s->max_count = std::max(s->max_count, s->counts[i]); }
+  int32_t ia = sa, ib = sb;
+  int32_t* o = w->out.p;
+  rc = match_pairs_device(s, &ia, &ib, 1, opt, o, o + 4, o + 4 + cap, reinterpret_cast<float*>(o + 4 + 2 * cap), (int)cap, nullptr);
+  if (rc) { for (auto& sl : w->slot) sl = PairSlot(); match_tc_invalidate(w->desc.p); return rc; }
+  mark(false);            // [2] host side of the kernel launches
+  mark(true);             // [3] the kernels
+  MM_CUDA(cudaMemcpyAsync(w->host_out, o, sizeof(int32_t) * (4 + 3 * cap), cudaMemcpyDeviceToHost, nullptr));
+  MM_CUDA(cudaStreamSynchronize(nullptr));
+  const int32_t c = w->host_out[0];
+  if (c < 0 || (size_t)c > cap) { set_error("internal: match count %d out of range", c); return MM_ERR_CUDA; }
+  memcpy(q, w->host_out + 4, sizeof(int32_t) * (size_t)c);
+  memcpy(t, w->host_out + 4 + cap, sizeof(int32_t) * (size_t)c);
+  memcpy(dist, w->host_out + 4 + 2 * cap, sizeof(float) * (size_t)c);
   *n_out = c;
+  mark(false);            // [4] result copy
+  if (timing) fprintf(stderr, "[mm_match_pair] us: hash+upload %.1f (%d arrays)  prepare %.1f  launch %.1f  kernels %.1f  result %.1f\n",
+                      t_ph[0], (int)up_a + (int)up_b, t_ph[1], t_ph[2], t_ph[3], t_ph[4]);
   return MM_OK;
 }
 

@@ -28,6 +28,9 @@ int match_tc_pairs(const float* desc, const float* xy, int K, const int64_t* off
 void match_tc_release(const float* desc);
 // the descriptor array at `desc` was overwritten: refresh the cached copies on next use (buffers are kept)
 void match_tc_invalidate(const float* desc);
+// rows [r0[i], r0[i] + n[i]) of a prepared array were overwritten: redo their TF32 copies and norms (no-op when the array
+// has not been prepared yet - the first tensor-core call prepares all of it)
+int match_tc_refresh_rows(const float* desc, int K, const int64_t* r0, const int64_t* n, int count, cudaStream_t st);
 void match_tc_stats(uint64_t* rows, uint64_t* flagged);
 
 }  // namespace mm

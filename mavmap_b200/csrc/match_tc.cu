@@ -547,6 +547,23 @@ void match_tc_invalidate(const float* desc) {
   std::lock_guard<std::mutex> lk(g_prep_mu);
   for (Prepared* p : g_prepared) if (p->desc == desc) p->valid = false;
 }
+int match_tc_refresh_rows(const float* desc, int K, const int64_t* r0, const int64_t* n, int count, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_prep_mu);
+  for (Prepared* p : g_prepared) if (p->desc == desc && p->K == K && p->valid) {
+    bool any = false;
+    for (int i = 0; i < count; ++i) {
+      if (n[i] <= 0) continue;
+      if (r0[i] < 0 || r0[i] + n[i] > p->rows) { p->valid = false; return MM_OK; }      // outside what was prepared: redo all of it on next use
+      k_tc_prep<<<(unsigned)((n[i] + 7) / 8), 256, 0, st>>>(desc + r0[i] * K, n[i], K, p->Kp, p->PA.p + r0[i] * p->Kp, p->PB.p + r0[i] * p->Kp, p->norms.p + r0[i]);
+      MM_LAUNCH_CHECK();
+      MM_CUDA(cudaMemcpyAsync(p->h_norms.data() + r0[i], p->norms.p + r0[i], sizeof(float) * (size_t)n[i], cudaMemcpyDeviceToHost, st));
+      any = true;
+    }
+    if (any) { MM_CUDA(cudaStreamSynchronize(st)); p->bmax_cache.clear(); }
+    return MM_OK;
+  }
+  return MM_OK;
+}
 void match_tc_stats(uint64_t* rows, uint64_t* flagged) { *rows = g_tc_rows.load(); *flagged = g_tc_flagged.load(); }
 
 int match_tc_pairs(const float* desc, const float* xy, int K, const int64_t* offs, int64_t total_rows, const int32_t* ia, const int32_t* ib,

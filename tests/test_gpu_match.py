@@ -1,5 +1,7 @@
 """GPU parity tests (through the C ABI): match_brute_force index lists are bit-exact against the
 oracle and against the cv2.BFMatcher golden lists."""
+import os
+
 import numpy as np
 import pytest
 
@@ -75,3 +77,44 @@ def test_match_set_batch_equals_single_pairs(mm):
         sl = slice(off[p], off[p + 1])
         assert np.array_equal(q[sl], qs) and np.array_equal(t[sl], ts) and np.array_equal(d[sl], ds)
     ms.close()
+
+
+def test_match_pair_resident_slots(mm, orc):
+    """mm_match_pair keeps the descriptor arrays of the last images resident (recognised by address, shape and sampled
+    content): call sequences that reuse, evict, rewrite, resize and alias the host arrays all see the current contents."""
+    desc, xy = synthetic.make_descriptors(7, 1300, 64, seed=0xBEEF)
+    imgs = [np.ascontiguousarray(desc[i]) for i in range(7)]
+    pts = [np.ascontiguousarray(xy[i]) for i in range(7)]
+
+    def check(a, b, xa=None, xb=None, variant="ratio09"):
+        kw = VARIANTS[variant]
+        qg, tg, dg = mm.match_brute_force(xa, a, xb, b, kw["ratio_test"], kw["max_ratio"], kw["max_distance"])
+        qo, to, do = orc.match_pair(a, b, xa, xb, **kw)
+        assert np.array_equal(qg, qo) and np.array_equal(tg, to) and np.array_equal(dg, do)
+        return len(qg)
+
+    from mavmap_b200 import _lib
+    c0 = _lib.match_pair_counters()
+    for i in range(2, 7):                                   # the mapper's pattern: more images than slots, so slots are evicted
+        assert check(imgs[i - 1], imgs[i]) > 100
+        assert check(imgs[i - 2], imgs[i]) > 100
+    c1 = _lib.match_pair_counters()
+    assert c1[0] - c0[0] == 10
+    if not os.environ.get("MM_MATCH_PAIR_NO_CACHE"):
+        assert c1[1] - c0[1] <= 7                           # every image uploaded once, not once per call
+    check(imgs[0], imgs[6])                                 # an evicted image comes back
+    imgs[6][:] = imgs[1][::-1]                              # rewritten in place: same address, new content
+    check(imgs[5], imgs[6])
+    assert check(imgs[6], imgs[1]) >= 1000                  # (a permutation of image 1)
+    assert check(imgs[2], imgs[2], variant="mutual") >= 1000    # the same array on both sides
+    check(imgs[3][:100], imgs[4][:777])                     # same addresses as resident arrays, fewer rows
+    check(imgs[3], imgs[4][:1])
+    check(imgs[1], imgs[2], pts[1], pts[2], "mask")         # keypoint mask (CUDA-core path) on resident slots
+    check(imgs[2], imgs[3], pts[2], pts[3], "mask")
+    big, _ = synthetic.make_descriptors(2, 3100, 64, seed=77)      # larger than the slots: the workspace is resized
+    assert check(np.ascontiguousarray(big[0]), np.ascontiguousarray(big[1])) > 100
+    assert check(imgs[1], imgs[2]) > 100
+    d128, _ = synthetic.make_descriptors(3, 900, 128, seed=78)     # another descriptor length
+    for a, b in [(0, 1), (1, 2), (0, 2)]:
+        assert check(np.ascontiguousarray(d128[a]), np.ascontiguousarray(d128[b])) > 100
+    check(imgs[4], imgs[5], variant="ratio06")

@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU-box visit: parity tests, the bench lines, the ncu launch list and the --set full captures.
-# usage (under gpurun): bash tools/gpu_round.sh <tag> [stages...]   stages: test smoke bench ref launches full
+# usage (under gpurun): bash tools/gpu_round.sh <tag> [stages...]   stages: test smoke bench ref launches full matchprof
 set -u
 TAG=${1:-r2}; shift || true
 STAGES=${*:-"test smoke bench ref launches full"}
@@ -33,6 +33,8 @@ if has full; then
         python tools/time_ba.py $cfg 1 > $OUT/prof_ba_${cfg}_$TAG.log 2>&1
     ncu -i $OUT/prof_ba_${cfg}_$TAG.ncu-rep --page raw --csv > $OUT/prof_ba_${cfg}_$TAG.csv 2>/dev/null; rm -f $OUT/prof_ba_${cfg}_$TAG.ncu-rep
   done
+fi
+if has full || has matchprof; then
   timeout 600 ncu --set full --clock-control none \
       -k regex:'k_match_tc|k_rerank|k_tc_prep' -c 4 -f -o $OUT/prof_match_$TAG \
       python tools/time_match.py 64 tc > $OUT/prof_match_$TAG.log 2>&1
