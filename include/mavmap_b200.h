@@ -141,7 +141,7 @@ int mm_match_pair(const float* d1, int32_t n1, const float* d2, int32_t n2, int3
 /* mm_match_pair keeps the descriptor arrays of its last four images on the device (the mapper matches image i
  * against i-1 and i-2, sequential_mapper.cc process()); a host array is recognised by address, shape and a hash of a
  * sample of its content taken on every call (everything up to 32 KB; above that the first and last row and 64 bytes
- * of every KB).  MM_MATCH_PAIR_NO_CACHE=1 in the environment uploads both arrays on every call.
+ * of every 4 KB page).  MM_MATCH_PAIR_NO_CACHE=1 in the environment uploads both arrays on every call.
  * Counters since process start: calls, descriptor arrays uploaded, bytes uploaded. */
 void mm_match_pair_counters(uint64_t* calls, uint64_t* arrays_uploaded, uint64_t* bytes_uploaded);
 

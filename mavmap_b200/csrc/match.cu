@@ -99,13 +99,17 @@ __device__ __forceinline__ int row_size(const Knn2& r, int ratio_test, double ma
   return sz;
 }
 
-__global__ void __launch_bounds__(256) k_match_finalize(
+// One CTA of 1024 threads per pair: the passes below are chains of dependent gathers (a row of direction 1->2, then the row
+// of 2->1 it points at) between block-wide barriers, so the time of a pair is the number of sweeps over its rows (256 threads:
+// 36 us for 5000 rows, most of what a single-pair call waited for after the distance kernels).
+__global__ void __launch_bounds__(1024) k_match_finalize(
     const PairJob* __restrict__ jobs, const Knn2* __restrict__ knn12_all, const Knn2* __restrict__ knn21_all,
     int ratio_test, double max_ratio, int mode /*0 ratio, 1 mutual-NN, 2 masked no-ratio*/,
     int32_t* __restrict__ q_out, int32_t* __restrict__ t_out, float* __restrict__ d_out, int32_t* __restrict__ cnt_out,
     int32_t* __restrict__ scratch /* mode 2: per-pair compacted matches21 train indices, stride = out stride */) {
-  __shared__ int warp_cnt[8];
+  __shared__ int warp_cnt[32];
   __shared__ int base;
+  const int n_warps = blockDim.x >> 5;
   const PairJob job = jobs[blockIdx.x];
   const Knn2* k12 = knn12_all + job.knn12_off;
   const Knn2* k21 = knn21_all + job.knn21_off;
@@ -128,7 +132,7 @@ __global__ void __launch_bounds__(256) k_match_finalize(
       // c21 can hold at most min(n1,n2) entries in the output slot; guard the rest
       if (keep) { const int pos = off + __popc(m & ((1u << lane) - 1)); if (pos < job.scr_cap) c21[pos] = k21[j].i0; }
       __syncthreads();
-      if (threadIdx.x == 0) { int tot = 0; for (int x = 0; x < 8; ++x) tot += warp_cnt[x]; base += tot; }
+      if (threadIdx.x == 0) { int tot = 0; for (int x = 0; x < n_warps; ++x) tot += warp_cnt[x]; base += tot; }
       __syncthreads();
     }
     nc21 = base;
@@ -159,7 +163,7 @@ __global__ void __launch_bounds__(256) k_match_finalize(
     for (int x = 0; x < w; ++x) off += warp_cnt[x];
     if (keep) { const int pos = off + __popc(m & ((1u << lane) - 1)); qo[pos] = i; to[pos] = tj; dd[pos] = dist; }
     __syncthreads();
-    if (threadIdx.x == 0) { int tot = 0; for (int x = 0; x < 8; ++x) tot += warp_cnt[x]; base += tot; }
+    if (threadIdx.x == 0) { int tot = 0; for (int x = 0; x < n_warps; ++x) tot += warp_cnt[x]; base += tot; }
     __syncthreads();
   }
   if (threadIdx.x == 0) cnt_out[blockIdx.x] = base;
@@ -252,7 +256,7 @@ int match_pairs_device(mm_match_set* s, const int32_t* ia, const int32_t* ib, in
       rc = knn2_simt(st, B, j.n2, A, j.n1, s->k, xb, xa, opt->max_distance, s->knn21.p + j.knn21_off, s->part.p, MAX_CHUNKS); if (rc) return rc;
     }
   }
-  k_match_finalize<<<n_pairs, 256, 0, st>>>(s->jobs.p, s->knn12.p, s->knn21.p, opt->ratio_test, opt->max_ratio, mode,
+  k_match_finalize<<<n_pairs, 1024, 0, st>>>(s->jobs.p, s->knn12.p, s->knn21.p, opt->ratio_test, opt->max_ratio, mode,
                                             q_dev, t_dev, dist_dev, cnt_dev, s->scratch.p);
   MM_LAUNCH_CHECK();
   return MM_OK;
@@ -350,9 +354,9 @@ int mm_match_set_pairs(mm_match_set* s, const int32_t* ia, const int32_t* ib, in
 // arrays of the last PAIR_SLOTS images stay resident in fixed-size slots of one device array: the mapper matches image i
 // against i-1 and i-2 (sequential_mapper.cc process()), so one of the two arrays of a call has normally been uploaded and
 // prepared (TF32 operand copies, norms) by an earlier call.  A host array is recognised by (address, rows, k) and a hash
-// of its content taken on every call - all of it up to 32 KB, above that the first and last row and 64 bytes of every KB (a
-// part of every 4th SURF-64 row); an array rewritten in place without touching any sampled byte would go unnoticed,
-// MM_MATCH_PAIR_NO_CACHE=1 uploads always.
+// of its content taken on every call - all of it up to 32 KB, above that the first and last row and 64 bytes of every 4 KB
+// page; an array rewritten in place without touching any sampled byte would go unnoticed, MM_MATCH_PAIR_NO_CACHE=1 uploads
+// always.
 // The result comes back as one copy (count | q | t | dist) into pinned memory.
 namespace {
 constexpr int PAIR_SLOTS = 4;
@@ -374,7 +378,15 @@ uint64_t sample_hash(const float* d, size_t n, size_t k) {
   };
   if (bytes <= ((size_t)32 << 10)) { mix(b, bytes); return h; }        // small arrays: all of it
   mix(b, row); mix(b + bytes - row, row);
-  for (size_t o = 1024; o + 64 <= bytes; o += 1024) mix(b + o, 64);
+  // one 64-byte line of every 4 KB page, eight independent accumulators and a prefetch a dozen pages ahead: the sample is a
+  // stream of cache misses, 11 us per 1.28 MB array this way against 35 us (64 bytes per KB: 90 us) as one dependent chain
+  uint64_t acc[8] = {1, 2, 3, 4, 5, 6, 7, 8};
+  for (size_t o = 2048; o + 64 <= bytes; o += 4096) {
+    if (o + 12 * 4096 < bytes) __builtin_prefetch(b + o + 12 * 4096);
+    uint64_t wv[8]; memcpy(wv, b + o, 64);
+    for (int j = 0; j < 8; ++j) acc[j] = (acc[j] ^ wv[j]) * 0x100000001B3ull + (acc[j] >> 31);
+  }
+  for (int j = 0; j < 8; ++j) { h = (h ^ acc[j]) * 0x100000001B3ull; h ^= h >> 29; }
   return h;
 }
 

@@ -340,9 +340,10 @@ struct RerankJob { int rowA0, nA, rowB0, nB; int64_t out_off; int64_t knn_off; i
 // arithmetic as match.cu and the oracle) of the hit columns, four independent chains at a time, then the exact top-2 by
 // (distance, index).  A row with more than TC_HCAP candidates is re-scanned exactly by a whole CTA (k_rescan).
 __global__ void __launch_bounds__(128) k_rerank(const RerankJob* __restrict__ jobs, const float* __restrict__ desc, int K,
-                         const uint32_t* __restrict__ masks, int* __restrict__ cand_g, Knn2* __restrict__ knn,
-                         int* __restrict__ flagged, int* __restrict__ n_flagged, int flag_cap) {
+                         const uint32_t* __restrict__ masks, int* __restrict__ cand_g, Knn2* __restrict__ knn12, Knn2* __restrict__ knn21,
+                         int n12 /* jobs [0, n12) write knn12, the rest knn21 */, int* __restrict__ flagged, int* __restrict__ n_flagged, int flag_cap) {
   const RerankJob job = jobs[blockIdx.y];
+  Knn2* __restrict__ knn = (int)blockIdx.y < n12 ? knn12 : knn21;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= job.nA) return;
   const float* a = desc + (size_t)(job.rowA0 + i) * K;
@@ -370,9 +371,21 @@ __global__ void __launch_bounds__(128) k_rerank(const RerankJob* __restrict__ jo
   }
   const bool overflow = n > TC_HCAP;
   const int nc = min(n, TC_HCAP);
-  // phase 2: exact distances, four independent chains at a time
+  // phase 2: exact distances, four independent chains at a time.  The rows of the next four candidates are prefetched into
+  // L1 while the current four are summed: every step of the serial k loop was a scattered 16-byte read at L2 latency, which
+  // is what a call with few pairs (40 blocks per direction, nothing to overlap with) spent its time on.
+  const int row_bytes = K * (int)sizeof(float);
+  auto prefetch_rows = [&](int c) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (c + k < nc) {
+      const char* r = reinterpret_cast<const char*>(desc + (size_t)(job.rowB0 + cand[(c + k) * 128 + threadIdx.x]) * K);
+      for (int o = 0; o < row_bytes; o += 128) asm volatile("prefetch.global.L1 [%0];" :: "l"(r + o));
+    }
+  };
+  prefetch_rows(0);
   for (int c0 = 0; c0 < nc; c0 += 4) {
     int col[4]; const float* bp[4]; double e2[4];
+    prefetch_rows(c0 + 4);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       col[k] = (c0 + k < nc) ? cand[(c0 + k) * 128 + threadIdx.x] : -1;
@@ -403,13 +416,14 @@ __global__ void __launch_bounds__(128) k_rerank(const RerankJob* __restrict__ jo
 
 // exact full scan of one flagged row per warp (same arithmetic and tie rule as the SIMT path)
 __global__ void __launch_bounds__(256) k_rescan(const RerankJob* __restrict__ jobs, const float* __restrict__ desc, int K,
-                         const int* __restrict__ flagged, const int* __restrict__ n_flagged, int flag_cap, Knn2* __restrict__ knn) {
+                         const int* __restrict__ flagged, const int* __restrict__ n_flagged, int flag_cap, Knn2* __restrict__ knn12, Knn2* __restrict__ knn21, int n12) {
   // one CTA per flagged row (a warp per row took 0.1 ms per row at 5000 x 64: the fp64 chain of a distance is serial by design)
   __shared__ float sb0[8], sb1[8]; __shared__ int si0[8], si1[8];
   const int nf = min(*n_flagged, flag_cap);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   for (int f = blockIdx.x; f < nf; f += gridDim.x) {
     const RerankJob job = jobs[flagged[2 * f]];
+    Knn2* __restrict__ knn = flagged[2 * f] < n12 ? knn12 : knn21;
     const int i = flagged[2 * f + 1];
     const float* a = desc + (size_t)(job.rowA0 + i) * K;
     float b0 = FLT_MAX, b1 = FLT_MAX; int i0 = -1, i1 = -1;
@@ -566,26 +580,13 @@ int match_tc_refresh_rows(const float* desc, int K, const int64_t* r0, const int
 }
 void match_tc_stats(uint64_t* rows, uint64_t* flagged) { *rows = g_tc_rows.load(); *flagged = g_tc_flagged.load(); }
 
-int match_tc_pairs(const float* desc, const float* xy, int K, const int64_t* offs, int64_t total_rows, const int32_t* ia, const int32_t* ib,
-                   const PairJob* jobs_host, int n_pairs, double max_distance, Knn2* knn12, Knn2* knn21,
-                   cudaStream_t st, bool required) {
-  (void)xy;
-  if (max_distance != -1.0) { if (required) set_error("the tcgen05 path does not take the keypoint-distance mask"); return MM_ERR_UNSUPPORTED; }
-  if (K % 4 != 0 || K < 8 || (K + 4 + TC_KB - 1) / TC_KB > TC_MAX_KB) { if (required) set_error("tcgen05 path needs K %% 4 == 0 and K <= %d", TC_MAX_KB * TC_KB - 4); return MM_ERR_UNSUPPORTED; }
-  if (getenv("MM_MATCH_NO_TC") && !required) return MM_ERR_UNSUPPORTED;
-
-  // the whole descriptor array of the set: its row count is the offset past the last image referenced
-  const int64_t rows = total_rows;
-  // prepared copies are keyed by the base pointer; use the full extent the set was created with when known
-  Prepared* P = nullptr;
-  { std::lock_guard<std::mutex> lk(g_prep_mu);
-    for (Prepared* q : g_prepared) if (q->desc == desc && q->K == K && q->valid && q->rows >= rows) { P = q; break; } }
-  if (!P) { int rc = get_prepared(desc, rows, K, st, &P); if (rc) return required ? rc : MM_ERR_UNSUPPORTED; }
-
-  // work items: (pair, direction, 128-row block); knn12 and knn21 live in different arrays -> two candidate regions
+// one range [p0, p1) of the pairs of a call: bound pass, collect pass, re-rank (+ re-scan of overflowing rows)
+static int tc_run_range(Prepared* P, const float* desc, int K, const int64_t* offs, const int32_t* ia, const int32_t* ib,
+                        const PairJob* jobs_host, int p0, int p1, Knn2* knn12, Knn2* knn21, cudaStream_t st) {
+  // work items: (pair, direction, 128-row block); knn12 and knn21 live in different arrays
   std::vector<TcItem> items; std::vector<RerankJob> rjobs;
   int64_t cand_rows = 0, mask_words = 0;
-  for (int p = 0; p < n_pairs; ++p) {
+  for (int p = p0; p < p1; ++p) {
     const PairJob& j = jobs_host[p];
     for (int dir = 0; dir < 2; ++dir) {
       const int imgA = dir == 0 ? ia[p] : ib[p], imgB = dir == 0 ? ib[p] : ia[p];
@@ -634,29 +635,60 @@ int match_tc_pairs(const float* desc, const float* xy, int K, const int64_t* off
   MM_CUDA(cudaMemsetAsync(g_scr.n_flagged.p, 0, sizeof(int), st));
   const int flag_cap = (int)cand_rows;
   int max_nA = 1; for (auto& r : all) max_nA = std::max(max_nA, r.nA);
-  { const size_t need = (size_t)((max_nA + 127) / 128) * std::max(j12.size(), j21.size()) * TC_HCAP * 128;      // candidate lists of one re-rank launch
-    if (need > g_scr.lists_cap) { MM_CUDA(g_scr.lists.alloc(need)); g_scr.lists_cap = need; } }
-  if (!j12.empty()) {
-    k_rerank<<<dim3((max_nA + 127) / 128, (unsigned)j12.size()), 128, 0, st>>>(g_scr.jobs.p, desc, K, g_scr.masks.p, g_scr.lists.p, knn12, g_scr.flagged.p, g_scr.n_flagged.p, flag_cap);
+  if (!all.empty()) {
+    // both directions in one launch (the job index says which top-2 array a row belongs to): a single pair is forty blocks
+    // per direction, and two launches in a row left most of the machine idle twice
+    const size_t need = (size_t)((max_nA + 127) / 128) * all.size() * TC_HCAP * 128;      // candidate lists, slot-major per block
+    if (need > g_scr.lists_cap) { MM_CUDA(g_scr.lists.alloc(need)); g_scr.lists_cap = need; }
+    k_rerank<<<dim3((max_nA + 127) / 128, (unsigned)all.size()), 128, 0, st>>>(g_scr.jobs.p, desc, K, g_scr.masks.p, g_scr.lists.p, knn12, knn21, (int)j12.size(),
+                                                                             g_scr.flagged.p, g_scr.n_flagged.p, flag_cap);
     MM_LAUNCH_CHECK();
-    k_rescan<<<num_sms() * 4, 256, 0, st>>>(g_scr.jobs.p, desc, K, g_scr.flagged.p, g_scr.n_flagged.p, flag_cap, knn12);
-    MM_LAUNCH_CHECK();
-  }
-  int nf12 = 0;
-  const bool want_stats = getenv("MM_MATCH_TC_STATS") != nullptr;       // (a D2H copy into pageable memory would stall the launch queue here)
-  if (want_stats) MM_CUDA(cudaMemcpyAsync(&nf12, g_scr.n_flagged.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-  if (!j21.empty()) {
-    MM_CUDA(cudaMemsetAsync(g_scr.n_flagged.p, 0, sizeof(int), st));
-    k_rerank<<<dim3((max_nA + 127) / 128, (unsigned)j21.size()), 128, 0, st>>>(g_scr.jobs.p + j12.size(), desc, K, g_scr.masks.p, g_scr.lists.p, knn21, g_scr.flagged.p, g_scr.n_flagged.p, flag_cap);
-    MM_LAUNCH_CHECK();
-    k_rescan<<<num_sms() * 4, 256, 0, st>>>(g_scr.jobs.p + j12.size(), desc, K, g_scr.flagged.p, g_scr.n_flagged.p, flag_cap, knn21);
+    k_rescan<<<num_sms() * 4, 256, 0, st>>>(g_scr.jobs.p, desc, K, g_scr.flagged.p, g_scr.n_flagged.p, flag_cap, knn12, knn21, (int)j12.size());
     MM_LAUNCH_CHECK();
   }
   g_tc_rows.fetch_add((uint64_t)cand_rows);
-  if (want_stats) {
-    int nf21 = 0; MM_CUDA(cudaMemcpyAsync(&nf21, g_scr.n_flagged.p, sizeof(int), cudaMemcpyDeviceToHost, st)); MM_CUDA(cudaStreamSynchronize(st));
-    g_tc_flagged.fetch_add((uint64_t)nf12 + (uint64_t)nf21);
-    fprintf(stderr, "[match_tc] rows %lld flagged for exact rescan: %d + %d\n", (long long)cand_rows, nf12, nf21);
+  if (getenv("MM_MATCH_TC_STATS") != nullptr) {       // (a D2H copy into pageable memory stalls the launch queue: only on request)
+    int nf = 0; MM_CUDA(cudaMemcpyAsync(&nf, g_scr.n_flagged.p, sizeof(int), cudaMemcpyDeviceToHost, st)); MM_CUDA(cudaStreamSynchronize(st));
+    g_tc_flagged.fetch_add((uint64_t)nf);
+    fprintf(stderr, "[match_tc] rows %lld flagged for exact rescan: %d\n", (long long)cand_rows, nf);
+  }
+  return MM_OK;
+}
+
+int match_tc_pairs(const float* desc, const float* xy, int K, const int64_t* offs, int64_t total_rows, const int32_t* ia, const int32_t* ib,
+                   const PairJob* jobs_host, int n_pairs, double max_distance, Knn2* knn12, Knn2* knn21,
+                   cudaStream_t st, bool required) {
+  (void)xy;
+  if (max_distance != -1.0) { if (required) set_error("the tcgen05 path does not take the keypoint-distance mask"); return MM_ERR_UNSUPPORTED; }
+  if (K % 4 != 0 || K < 8 || (K + 4 + TC_KB - 1) / TC_KB > TC_MAX_KB) { if (required) set_error("tcgen05 path needs K %% 4 == 0 and K <= %d", TC_MAX_KB * TC_KB - 4); return MM_ERR_UNSUPPORTED; }
+  if (getenv("MM_MATCH_NO_TC") && !required) return MM_ERR_UNSUPPORTED;
+
+  // the whole descriptor array of the set: its row count is the offset past the last image referenced
+  const int64_t rows = total_rows;
+  // prepared copies are keyed by the base pointer; use the full extent the set was created with when known
+  Prepared* P = nullptr;
+  { std::lock_guard<std::mutex> lk(g_prep_mu);
+    for (Prepared* q : g_prepared) if (q->desc == desc && q->K == K && q->valid && q->rows >= rows) { P = q; break; } }
+  if (!P) { int rc = get_prepared(desc, rows, K, st, &P); if (rc) return required ? rc : MM_ERR_UNSUPPORTED; }
+
+  // The hit masks and candidate lists are scratch per (pair, direction, row block): a call with many pairs runs as a
+  // sequence of pair ranges whose scratch stays below a fixed budget (~9 MB per 5000 x 5000 pair, 3 GB by default:
+  // ranges of ~330 pairs = 26 000 work items each, far more than the machine needs to be full).
+  int64_t budget_words = (int64_t)768 << 20;
+  if (const char* e = getenv("MM_MATCH_TC_SCRATCH_WORDS")) budget_words = std::max<int64_t>(1, atoll(e));      // (tests force several ranges)
+  auto pair_words = [&](int p) {
+    int64_t w = 0;
+    for (int dir = 0; dir < 2; ++dir) {
+      const int64_t nA = dir == 0 ? jobs_host[p].n1 : jobs_host[p].n2, nB = dir == 0 ? jobs_host[p].n2 : jobs_host[p].n1;
+      w += (nA + TC_M - 1) / TC_M * ((nB + TC_N - 1) / TC_N * (TC_N / 32) * TC_M + (int64_t)TC_HCAP * 128);
+    }
+    return w;
+  };
+  for (int p0 = 0; p0 < n_pairs;) {
+    int p1 = p0; int64_t words = 0;
+    while (p1 < n_pairs && (p1 == p0 || words + pair_words(p1) <= budget_words)) { words += pair_words(p1); ++p1; }
+    const int rc = tc_run_range(P, desc, K, offs, ia, ib, jobs_host, p0, p1, knn12, knn21, st); if (rc) return rc;
+    p0 = p1;
   }
   return MM_OK;
 }

@@ -118,3 +118,17 @@ def test_match_pair_resident_slots(mm, orc):
     for a, b in [(0, 1), (1, 2), (0, 2)]:
         assert check(np.ascontiguousarray(d128[a]), np.ascontiguousarray(d128[b])) > 100
     check(imgs[4], imgs[5], variant="ratio06")
+
+
+def test_many_pairs_run_in_bounded_scratch_ranges(mm, monkeypatch):
+    """The hit masks and candidate lists are per-pair scratch: a long pair list runs as a sequence of ranges under a budget."""
+    desc, xy = synthetic.make_descriptors(5, 700, 64, seed=6)
+    ms = mm.MatchSet(desc, None)
+    pairs = [(i, j) for i in range(5) for j in range(i + 1, 5)]
+    want = ms.match_pairs(pairs, True, 0.9, -1)
+    for words in (300000, 1):                               # two pairs per range (135 168 words per pair), one pair per range
+        monkeypatch.setenv("MM_MATCH_TC_SCRATCH_WORDS", str(words))
+        got = ms.match_pairs(pairs, True, 0.9, -1)
+        for a, b in zip(want, got):
+            assert np.array_equal(a, b)
+    ms.close()
